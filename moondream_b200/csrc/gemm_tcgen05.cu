@@ -1,0 +1,442 @@
+// Persistent, warp-specialised bf16 GEMM for sm_100a:  D[M,N] = A[M,K] * B[N,K]^T  (fp32 accum).
+//
+// Replaces every F.linear on the hot path of the reference (moondream/torch/layers.py:34-35,
+// vision.py:67, text.py:30,53,166, layers.py:130,139, region.py:43,57,71,93).
+//
+//   warp 0 : TMA producer   (cp.async.bulk.tensor, 128B-swizzled K-major tiles, mbarrier ring)
+//   warp 1 : MMA issuer     (one elected lane issues tcgen05.mma 128 x BN x 16, accumulators in TMEM)
+//   warp 2 : TMEM allocator
+//   warps 4-7 : epilogue    (tcgen05.ld -> bias / GELU-tanh / residual -> bf16 -> global)
+//
+// TMEM holds two accumulator stages so the epilogue of tile i overlaps the MMAs of tile i+1.
+// Tails in M, N and K are handled by TMA out-of-bounds zero fill plus masked stores, so the
+// awkward reference shapes (K=588->592, N=4304, M=B*729) need no padded copies of activations.
+//
+// Two output forms:
+//   * row form   (activations are the M side): bf16 out[M,N] with fused epilogue.
+//   * swapped form (weights are the M side, the small decode batch is the N side, optional split-K):
+//     fp32 partial sums ws[split][n(batch)][m(feature)], finished by splitk_epilogue_kernel.
+#include "kernels.cuh"
+#include "ptx.cuh"
+
+namespace md {
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int kGemmThreads = 256;
+
+struct GemmParams {
+  int M, N, K;
+  int m_blocks, n_blocks, k_blocks;   // k_blocks = ceil(K / BK)
+  int k_splits;                        // >1 only in swapped form
+  int mode;                            // EPI_* (row form) or EPI_PARTIAL (swapped form)
+  // row form
+  __nv_bfloat16* out;
+  long long ldo;
+  const __nv_bfloat16* bias;           // [N] or nullptr
+  const __nv_bfloat16* res;            // residual [*, N]
+  long long ldr;
+  int res_mod;                         // residual row = row % res_mod when > 0 (pos_emb broadcast)
+  int remap_gin, remap_gout, remap_goff;  // out row = (r / gin) * gout + r % gin + goff when gin > 0
+  // swapped form
+  float* ws;                           // [k_splits][N][M] fp32
+};
+
+template <int BN, int STAGES>
+struct GemmSmem {
+  static constexpr int kABytes = BM * BK * 2;
+  static constexpr int kBBytes = BN * BK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kBarOffset = STAGES * kStageBytes;
+  static constexpr int kTotal = kBarOffset + (2 * STAGES + 4) * 8 + 16 + 1024;  // +1024 align slack
+};
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const GemmParams p) {
+  using S = GemmSmem<BN, STAGES>;
+  constexpr uint32_t kTmemCols = (2 * BN < 32) ? 32 : 2 * BN;  // power of two for BN in {32..256}
+  static_assert(BN == 32 || BN == 64 || BN == 128 || BN == 256, "BN must be a power of two");
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::kBarOffset);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;   // [2]
+  uint64_t* tmem_empty = tmem_full + 2;       // [2]
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tensormap(&tmA);
+    prefetch_tensormap(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_ptr_smem, kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  const int total_tiles = p.m_blocks * p.n_blocks * p.k_splits;
+  const int kb_per_split = (p.k_blocks + p.k_splits - 1) / p.k_splits;
+
+  if (warp == 0) {
+    // ------------------------------ TMA producer ------------------------------
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int split = tile % p.k_splits;
+        const int t2 = tile / p.k_splits;
+        const int n_blk = t2 % p.n_blocks;
+        const int m_blk = t2 / p.n_blocks;
+        const int kb0 = split * kb_per_split;
+        const int kb1 = min(p.k_blocks, kb0 + kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * S::kStageBytes;
+          uint8_t* sb = sa + S::kABytes;
+          mbar_arrive_expect_tx(&full_bar[stage], S::kStageBytes);
+          tma_load_2d(sa, &tmA, &full_bar[stage], kb * BK, m_blk * BM);
+          tma_load_2d(sb, &tmB, &full_bar[stage], kb * BK, n_blk * BN);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------ MMA issuer ------------------------------
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16_f32(BM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        const int split = tile % p.k_splits;
+        const int kb0 = split * kb_per_split;
+        const int kb1 = min(p.k_blocks, kb0 + kb_per_split);
+        const int as = it & 1;
+        const uint32_t aphase = (it >> 1) & 1;
+        mbar_wait(&tmem_empty[as], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(as * BN);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * S::kStageBytes);
+          const uint32_t sb = sa + S::kABytes;
+          const uint64_t da = make_desc_k_sw128(sa);
+          const uint64_t db = make_desc_k_sw128(sb);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            // advance 16 elements (32 B) along K inside the 128-byte swizzle row: +2 in 16-B units
+            umma_bf16(tmem_d, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k),
+                      idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);   // smem slot reusable once these MMAs have read it
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tmem_full[as]);        // accumulator complete
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------ epilogue ------------------------------
+    const int q = warp & 3;                 // TMEM lane quadrant this warp may read
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int split = tile % p.k_splits;
+      const int t2 = tile / p.k_splits;
+      const int n_blk = t2 % p.n_blocks;
+      const int m_blk = t2 / p.n_blocks;
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      mbar_wait(&tmem_full[as], aphase);
+      tc_fence_after();
+      const int row = m_blk * BM + q * 32 + lane;          // accumulator row of this thread
+      const bool row_ok = row < p.M;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
+                             static_cast<uint32_t>(as * BN);
+
+      long long out_row = row;
+      if (p.remap_gin > 0)
+        out_row = static_cast<long long>(row / p.remap_gin) * p.remap_gout + row % p.remap_gin +
+                  p.remap_goff;
+      const int res_row = (p.res_mod > 0) ? (row % p.res_mod) : row;
+
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t acc[32];
+        tmem_ld_32x32(taddr + static_cast<uint32_t>(c * 32), acc);
+        tmem_ld_wait();
+        const int col0 = n_blk * BN + c * 32;
+        if (p.mode == EPI_PARTIAL) {
+          // swapped form: rows are output features (contiguous across lanes), columns are batch
+          if (row_ok) {
+            float* wsp = p.ws + (static_cast<long long>(split) * p.N) * p.M + row;
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < p.N) wsp[static_cast<long long>(col0 + j) * p.M] = __uint_as_float(acc[j]);
+          }
+          continue;
+        }
+        if (!row_ok || col0 >= p.N) continue;
+        __nv_bfloat16* optr = p.out + out_row * p.ldo + col0;
+        const __nv_bfloat16* rptr = p.res ? p.res + static_cast<long long>(res_row) * p.ldr + col0 : nullptr;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {          // 4 groups of 8 columns = 16-byte stores
+          if (col0 + g * 8 >= p.N) break;       // N is a multiple of 8 (checked on the host)
+          float v[8];
+          uint4 bq = make_uint4(0, 0, 0, 0);
+          if (p.bias) bq = *reinterpret_cast<const uint4*>(p.bias + col0 + g * 8);
+          const uint32_t bw[4] = {bq.x, bq.y, bq.z, bq.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            // the reference rounds the Linear output to bf16 before anything else touches it
+            v[2 * j] = bf16_round(__uint_as_float(acc[g * 8 + 2 * j]) + bf16_lo(bw[j]));
+            v[2 * j + 1] = bf16_round(__uint_as_float(acc[g * 8 + 2 * j + 1]) + bf16_hi(bw[j]));
+          }
+          if (p.mode == EPI_BIAS_GELU) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = gelu_tanh(v[j]);
+          } else if (p.mode == EPI_BIAS_RESIDUAL) {
+            const uint4 rq = *reinterpret_cast<const uint4*>(rptr + g * 8);
+            const uint32_t rw[4] = {rq.x, rq.y, rq.z, rq.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              v[2 * j] += bf16_lo(rw[j]);
+              v[2 * j + 1] += bf16_hi(rw[j]);
+            }
+          }
+          uint4 o;
+          o.x = pack_bf16x2(v[0], v[1]);
+          o.y = pack_bf16x2(v[2], v[3]);
+          o.z = pack_bf16x2(v[4], v[5]);
+          o.w = pack_bf16x2(v[6], v[7]);
+          *reinterpret_cast<uint4*>(optr + g * 8) = o;
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tmem_empty[as]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// Finishes a swapped-form GEMM: out[b][n] = epi( sum_s ws[s][b][n] + bias[n] ) in a fixed
+// summation order (deterministic, unlike atomics).
+__global__ void splitk_epilogue_kernel(const float* __restrict__ ws, int splits, int B, int N,
+                                       int mode, const __nv_bfloat16* __restrict__ bias,
+                                       const __nv_bfloat16* __restrict__ res, long long ldr,
+                                       __nv_bfloat16* __restrict__ out, long long ldo) {
+  const int n = (blockIdx.x * blockDim.x + threadIdx.x) * 2;
+  const int b = blockIdx.y;
+  if (n >= N) return;
+  float a0 = 0.f, a1 = 0.f;
+  for (int s = 0; s < splits; ++s) {
+    const float2 v = *reinterpret_cast<const float2*>(ws + (static_cast<long long>(s) * B + b) * N + n);
+    a0 += v.x;
+    a1 += v.y;
+  }
+  if (bias) {
+    const uint32_t bw = *reinterpret_cast<const uint32_t*>(bias + n);
+    a0 += bf16_lo(bw);
+    a1 += bf16_hi(bw);
+  }
+  a0 = bf16_round(a0);
+  a1 = bf16_round(a1);
+  if (mode == EPI_BIAS_GELU) {
+    a0 = gelu_tanh(a0);
+    a1 = gelu_tanh(a1);
+  } else if (mode == EPI_BIAS_RESIDUAL) {
+    const uint32_t rw = *reinterpret_cast<const uint32_t*>(res + static_cast<long long>(b) * ldr + n);
+    a0 += bf16_lo(rw);
+    a1 += bf16_hi(rw);
+  }
+  *reinterpret_cast<uint32_t*>(out + static_cast<long long>(b) * ldo + n) = pack_bf16x2(a0, a1);
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !ptr) return nullptr;
+    fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+// bf16 row-major [rows, cols] with row stride ld (elements); box = [box_rows, 64] 128B-swizzled.
+int make_tmap_bf16_2d(CUtensorMap* tm, const void* base, long long rows, long long cols,
+                      long long ld, int box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return set_error("cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
+  if ((reinterpret_cast<uintptr_t>(base) & 15) || (ld * 2) % 16)
+    return set_error("TMA operand must be 16-byte aligned with a 16-byte multiple row pitch");
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 2};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(BK), static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides,
+                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error("cuTensorMapEncodeTiled failed");
+  return 0;
+}
+
+static int g_num_sms = 0;
+int num_sms() {
+  if (!g_num_sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms <= 0) g_num_sms = 148;
+  }
+  return g_num_sms;
+}
+
+template <int BN, int STAGES>
+static int launch_gemm(const CUtensorMap& tA, const CUtensorMap& tB, const GemmParams& p,
+                       cudaStream_t stream) {
+  using S = GemmSmem<BN, STAGES>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_kernel<BN, STAGES>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal);
+    if (e != cudaSuccess) return set_error(cudaGetErrorString(e));
+    configured = true;
+  }
+  const int total = p.m_blocks * p.n_blocks * p.k_splits;
+  const int grid = total < num_sms() ? total : num_sms();
+  gemm_bf16_kernel<BN, STAGES><<<grid, kGemmThreads, S::kTotal, stream>>>(tA, tB, p);
+  count_launch();
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error(cudaGetErrorString(e));
+  return 0;
+}
+
+static int dispatch_gemm(int bn, const CUtensorMap& tA, const CUtensorMap& tB, const GemmParams& p,
+                         cudaStream_t stream) {
+  switch (bn) {
+    case 256: return launch_gemm<256, 4>(tA, tB, p, stream);
+    case 128: return launch_gemm<128, 6>(tA, tB, p, stream);
+    case 64: return launch_gemm<64, 8>(tA, tB, p, stream);
+    case 32: return launch_gemm<32, 10>(tA, tB, p, stream);
+  }
+  return set_error("unsupported BN");
+}
+
+static int pick_bn_rows(int N) {
+  // 256-wide tiles give the tensor pipe the longest uninterrupted run; fall back for narrow N.
+  if (N >= 192) return 256;
+  if (N >= 96) return 128;
+  if (N >= 48) return 64;
+  return 32;
+}
+
+int gemm_rowform(const __nv_bfloat16* A, long long lda, const __nv_bfloat16* W, long long ldw, int M,
+                 int N, int K, int mode, const __nv_bfloat16* bias, const __nv_bfloat16* res,
+                 long long ldr, int res_mod, __nv_bfloat16* out, long long ldo, int remap_gin,
+                 int remap_gout, int remap_goff, cudaStream_t stream) {
+  if (M <= 0 || N <= 0 || K <= 0) return set_error("gemm: empty problem");
+  if (N % 8 || K % 8) return set_error("gemm: N and K must be multiples of 8");
+  if (mode == EPI_BIAS_RESIDUAL && !res) return set_error("gemm: residual mode without residual");
+  if ((ldo % 8) || (res && (ldr % 8))) return set_error("gemm: ldo/ldr must be multiples of 8");
+  const int bn = pick_bn_rows(N);
+  CUtensorMap tA, tB;
+  if (make_tmap_bf16_2d(&tA, A, M, K, lda, BM)) return 1;
+  if (make_tmap_bf16_2d(&tB, W, N, K, ldw, bn)) return 1;
+  GemmParams p{};
+  p.M = M; p.N = N; p.K = K;
+  p.m_blocks = (M + BM - 1) / BM;
+  p.n_blocks = (N + bn - 1) / bn;
+  p.k_blocks = (K + BK - 1) / BK;
+  p.k_splits = 1;
+  p.mode = mode;
+  p.out = out; p.ldo = ldo; p.bias = bias; p.res = res; p.ldr = ldr; p.res_mod = res_mod;
+  p.remap_gin = remap_gin; p.remap_gout = remap_gout; p.remap_goff = remap_goff;
+  p.ws = nullptr;
+  return dispatch_gemm(bn, tA, tB, p, stream);
+}
+
+int gemm_swapped_splits(int n_out, int K) {
+  // enough (feature-block x K-split) work items to give every SM a weight stream
+  const int m_blocks = (n_out + BM - 1) / BM;
+  const int k_blocks = (K + BK - 1) / BK;
+  int splits = (num_sms() + m_blocks - 1) / m_blocks;
+  if (splits > k_blocks / 4) splits = k_blocks / 4;   // keep >= 4 k-blocks (256 of K) per split
+  if (splits < 1) splits = 1;
+  if (splits > 16) splits = 16;
+  return splits;
+}
+
+// ws[splits][batch][n_out] (fp32) = W[n_out,K] * X[batch,K]^T  partial sums.
+int gemm_swapped(const __nv_bfloat16* W, long long ldw, const __nv_bfloat16* X, long long ldx,
+                 int n_out, int batch, int K, int splits, float* ws, cudaStream_t stream) {
+  if (n_out <= 0 || batch <= 0 || K <= 0) return set_error("gemm_swapped: empty problem");
+  if (K % 8) return set_error("gemm_swapped: K must be a multiple of 8");
+  const int bn = batch <= 32 ? 32 : batch <= 64 ? 64 : batch <= 128 ? 128 : 256;
+  CUtensorMap tA, tB;
+  if (make_tmap_bf16_2d(&tA, W, n_out, K, ldw, BM)) return 1;
+  if (make_tmap_bf16_2d(&tB, X, batch, K, ldx, bn)) return 1;
+  GemmParams p{};
+  p.M = n_out; p.N = batch; p.K = K;
+  p.m_blocks = (n_out + BM - 1) / BM;
+  p.n_blocks = (batch + bn - 1) / bn;
+  p.k_blocks = (K + BK - 1) / BK;
+  // every split must own at least one k-block, otherwise its accumulator is never written
+  if (splits > p.k_blocks) splits = p.k_blocks;
+  const int per = (p.k_blocks + splits - 1) / splits;
+  splits = (p.k_blocks + per - 1) / per;
+  p.k_splits = splits;
+  p.mode = EPI_PARTIAL;
+  p.ws = ws;
+  int rc = dispatch_gemm(bn, tA, tB, p, stream);
+  return rc ? -1 : splits;     // returns the split count actually used (>0), -1 on error
+}
+
+int splitk_epilogue(const float* ws, int splits, int B, int N, int mode, const __nv_bfloat16* bias,
+                    const __nv_bfloat16* res, long long ldr, __nv_bfloat16* out, long long ldo,
+                    cudaStream_t stream) {
+  if (N % 2) return set_error("splitk_epilogue: N must be even");
+  dim3 grid((N / 2 + 127) / 128, B);
+  splitk_epilogue_kernel<<<grid, 128, 0, stream>>>(ws, splits, B, N, mode, bias, res, ldr, out, ldo);
+  count_launch();
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error(cudaGetErrorString(e));
+  return 0;
+}
+
+}  // namespace md

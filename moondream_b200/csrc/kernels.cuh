@@ -1,0 +1,68 @@
+// Internal (C++) interface between the kernel translation units and the C-ABI layer (api.cu).
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace md {
+
+// epilogue modes shared by the GEMM kernels (values are part of the C-ABI, see include/moondream_b200.h)
+enum : int {
+  EPI_BIAS = 0,            // out = bf16(acc + bias)
+  EPI_BIAS_GELU = 1,       // out = bf16(gelu_tanh(bf16(acc + bias)))
+  EPI_BIAS_RESIDUAL = 2,   // out = bf16(bf16(acc + bias) + residual)
+  EPI_PARTIAL = 3,         // swapped form: fp32 partial sums to workspace
+};
+
+// error plumbing: every entry point returns 0 on success; the message is kept per thread.
+int set_error(const char* msg);
+const char* last_error();
+void count_launch();
+long long launch_count();
+void reset_launch_count();
+int num_sms();
+
+// ---- gemm_tcgen05.cu ----
+int make_tmap_bf16_2d(CUtensorMap* tm, const void* base, long long rows, long long cols,
+                      long long ld, int box_rows);
+int gemm_rowform(const __nv_bfloat16* A, long long lda, const __nv_bfloat16* W, long long ldw, int M,
+                 int N, int K, int mode, const __nv_bfloat16* bias, const __nv_bfloat16* res,
+                 long long ldr, int res_mod, __nv_bfloat16* out, long long ldo, int remap_gin,
+                 int remap_gout, int remap_goff, cudaStream_t stream);
+int gemm_swapped_splits(int n_out, int K);
+int gemm_swapped(const __nv_bfloat16* W, long long ldw, const __nv_bfloat16* X, long long ldx,
+                 int n_out, int batch, int K, int splits, float* ws, cudaStream_t stream);
+int splitk_epilogue(const float* ws, int splits, int B, int N, int mode, const __nv_bfloat16* bias,
+                    const __nv_bfloat16* res, long long ldr, __nv_bfloat16* out, long long ldo,
+                    cudaStream_t stream);
+
+// ---- elementwise.cu ----
+int layernorm(const __nv_bfloat16* x, long long ldx, const __nv_bfloat16* w, const __nv_bfloat16* b,
+              __nv_bfloat16* y, long long ldy, int rows, int dim, float eps, cudaStream_t stream);
+int patchify(const uint8_t* crops, int n_crops, int crop, int patch, int k_pad, __nv_bfloat16* out,
+             cudaStream_t stream);
+int stitch_pool_concat(const __nv_bfloat16* feats, const int* crop_offsets, const int* tilings,
+                       int n_images, int grid, int margin, int dim, __nv_bfloat16* out,
+                       cudaStream_t stream);
+int embed_tokens(const int* ids, int n, const __nv_bfloat16* wte, int dim, __nv_bfloat16* out,
+                 long long ldo, cudaStream_t stream);
+int rope_kv_write(const __nv_bfloat16* qkv, int n_tokens, int n_heads, const int* tok_seq,
+                  const int* tok_pos, const float* freqs, __nv_bfloat16* q_out,
+                  __nv_bfloat16* kv_pool, const int* block_tables, int max_blocks, int layer,
+                  int n_layers, cudaStream_t stream);
+int argmax_logits(const float* logits, int B, int V, const __nv_bfloat16* bias, const int* mask_ids,
+                  int n_mask, int* out_ids, cudaStream_t stream);
+
+// ---- attention.cu ----
+int vit_attention(const __nv_bfloat16* qkv, int n_crops, int seq, int n_heads, __nv_bfloat16* out,
+                  cudaStream_t stream);
+int prefill_attention(const __nv_bfloat16* q, int n_heads, const int* q_offsets, const int* start_pos,
+                      int n_seqs, int max_q, int prefix_len, const __nv_bfloat16* kv_pool,
+                      const int* block_tables, int max_blocks, int layer, int n_layers,
+                      __nv_bfloat16* out, cudaStream_t stream);
+int decode_attention(const __nv_bfloat16* q, int n_heads, const int* pos, int n_seqs,
+                     const __nv_bfloat16* kv_pool, const int* block_tables, int max_blocks, int layer,
+                     int n_layers, __nv_bfloat16* out, cudaStream_t stream);
+
+}  // namespace md
