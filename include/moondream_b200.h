@@ -4,17 +4,21 @@
  * Conventions (all entry points):
  *   - plain pointers and sizes; device pointers unless marked HOST; bf16 = raw uint16 storage;
  *   - `stream` is a cudaStream_t passed as void*; entry points never synchronise and never
- *     allocate: the caller passes outputs and workspaces (see the *_workspace_bytes queries);
+ *     allocate device memory: the caller passes outputs and workspaces (see the *_workspace_bytes
+ *     queries); all launches are CUDA-graph capturable;
  *   - return 0 on success, non-zero on error; md_last_error() returns the message (thread-local);
- *   - leading dimensions (`ld*`) are in elements.
+ *   - leading dimensions (`ld*`) and strides are in elements.
  *
  * The reference (vikhyat/moondream, /root/reference) has no FFI: its swap seam is the four bound
  * methods MoondreamModel._vis_enc/_vis_proj/_prefill/_decode_one_tok (moondream/torch/moondream.py
- * :168-192) that compile() rebinds (:194-204).  Each entry point below cites the reference lines
- * whose arithmetic it replaces; INTEGRATION.md shows the ctypes stubs that bind them.
+ * :168-192) that compile() rebinds (:194-204).  The model-level entry points below are those four
+ * methods generalised with a leading batch dimension; each cites the reference lines whose
+ * arithmetic it replaces.  INTEGRATION.md shows the ctypes stubs that bind them.
  */
 #ifndef MOONDREAM_B200_H
 #define MOONDREAM_B200_H
+
+#include <stdint.h>
 
 #ifdef __cplusplus
 extern "C" {
@@ -27,11 +31,17 @@ extern "C" {
 #define MD_EPI_BIAS_GELU 1     /* y = bf16(gelu_tanh(bf16(x W^T + b)))       layers.py:130,137 */
 #define MD_EPI_BIAS_RESIDUAL 2 /* y = bf16(bf16(x W^T + b) + r)              vision.py:70-71, text.py:158 */
 
+#define MD_PAGE_TOKENS 64      /* tokens per KV page */
+
 const char* md_last_error(void);
 int md_abi_version(void);
 /* number of kernels this library has launched since the last reset (bench.py's gpu_launches) */
 long long md_launch_count(void);
 void md_reset_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Operator level
+ * ---------------------------------------------------------------------------------------------- */
 
 /*
  * y[M,N] = epilogue(x[M,K] @ w[N,K]^T + bias[N])            (tcgen05 + TMA GEMM, bf16 in/out)
@@ -50,16 +60,144 @@ int md_linear_bf16(const void* x, long long ldx, const void* w, long long ldw, i
                    void* stream);
 
 /*
- * Same contraction for a small batch (decode step, region head): the weight matrix is the
+ * Same contraction for a small batch (decode step, LM head, region head): the weight matrix is the
  * M side of the MMA so every SM streams weights at HBM rate; K is split across CTAs and the fp32
  * partial sums are reduced in a fixed order (deterministic).  Replaces the M=1 F.linear calls the
- * reference issues per generated token (text.py:30,53; layers.py:130,139; region.py:43-93).
+ * reference issues per generated token (text.py:30,53,166; layers.py:130,139; region.py:43-93).
  */
 int md_linear_small_batch_splits(int n_out, int K);
 long long md_linear_small_batch_workspace_bytes(int n_out, int batch, int K);
 int md_linear_small_batch_bf16(const void* x, long long ldx, const void* w, long long ldw, int batch,
                                int n_out, int K, int epilogue, const void* bias, const void* residual,
                                long long ldr, void* out, long long ldo, void* workspace, void* stream);
+
+/* y = LayerNorm(x) * w + b, eps 1e-5, fp32 statistics (layers.py:118-119). dim % 8 == 0, <= 4096. */
+int md_layernorm_bf16(const void* x, long long ldx, const void* w, const void* b, void* y,
+                      long long ldy, int rows, int dim, void* stream);
+
+/*
+ * ViT self-attention over the fused qkv activations (layers.py:155-166): qkv [n_crops*seq, 3*H*72]
+ * -> out [n_crops*seq, H*72]; softmax(QK^T / sqrt(72)) V, no mask.
+ */
+int md_vit_attention_bf16(const void* qkv, int n_crops, int seq, int n_heads, void* out, void* stream);
+
+/* Paged KV cache handle: pool bf16 [layers][n_pages][2][heads][64 tokens][64 dims];
+ * block_tables int32 [n_seqs][max_blocks] (page of positions 64*i..64*i+63 of each sequence). */
+typedef struct md_kv {
+  void* pool;
+  int n_pages;
+  const int* block_tables;
+  int max_blocks;
+} md_kv;
+
+/* Partial RoPE (first 32 of 64 dims, split-half in / interleaved out, rope.py:20-48) on q and k of
+ * fused qkv [tokens, 3*H*64]; q -> q_out [tokens, H*64]; k, v -> KV pages (moondream.py:74-78).
+ * q_offsets == NULL means one token per sequence at position start_pos[seq] (decode). */
+int md_rope_kv_write_bf16(const void* qkv, int n_tokens, int n_heads, const int* q_offsets,
+                          const int* start_pos, int n_seqs, const float* rope_table, void* q_out,
+                          const md_kv* kv, int layer, void* stream);
+
+/* Prefix-LM attention for prefill (text.py:46-50 under the mask of moondream.py:138-146). */
+int md_prefill_attention_bf16(const void* q, int n_heads, const int* q_offsets, const int* start_pos,
+                              int n_seqs, int max_q, int prefix_len, const md_kv* kv, int layer,
+                              void* out, void* stream);
+
+/* One-query attention for decode (text.py:46-50 with the [1,1,2048] mask of moondream.py:472-474). */
+int md_decode_attention_bf16(const void* q, int n_heads, const int* pos, int n_seqs, const md_kv* kv,
+                             int layer, void* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Model level (the four seam methods, batched)
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct md_dims {
+  /* vision (VisionConfig, config.py:19-31); vis_ff and patch_k are the PADDED sizes the prepared
+   * weights use (multiples of 8: 588 -> 592, 2690 -> 2696) */
+  int vis_dim, vis_ff, vis_layers, vis_heads, crop, patch, patch_k, grid, margin, proj_inner;
+  /* text (TextConfig, config.py:5-15) */
+  int txt_dim, txt_ff, txt_layers, txt_heads, vocab, max_context, prefix_len;
+  /* region (RegionConfig, config.py:34-41) */
+  int reg_inner, coord_feat, coord_out, size_feat, size_out;
+} md_dims;
+
+typedef struct md_model md_model;
+
+/* Number of weight tensors md_model_create expects: the canonical state_dict order of the
+ * reference (moondream_b200/synth.py:state_dict_spec). */
+int md_model_num_weights(const md_dims* dims);
+
+/*
+ * weights: HOST array of device pointers in canonical order (bf16, contiguous, prepared/padded);
+ * pixel_lut: device bf16[256] = the reference's pixel normalisation chain (vision.py:36-40);
+ * rope_table: device f32 [max_context][16][2] = precompute_freqs_cis (rope.py:6-17, text.py:215-219).
+ * The model object only stores pointers (host memory); it owns no device memory.
+ */
+int md_model_create(const md_dims* dims, const void* const* weights, int n_weights,
+                    const void* pixel_lut, const float* rope_table, md_model** out);
+void md_model_destroy(md_model* model);
+
+/* _vis_enc (vision.py:64-74 + prepare_crops' normalisation :36-40 + create_patches :44-61):
+ * crops uint8 NHWC [n_crops, crop, crop, 3] -> feats bf16 [n_crops * grid^2, vis_dim]. */
+long long md_vision_encode_workspace_bytes(const md_model* model, int n_crops);
+int md_vision_encode(md_model* model, const uint8_t* crops, int n_crops, void* feats, void* workspace,
+                     void* stream);
+
+/* reconstruct_from_crops + _vis_proj (image_crops.py:170-231, vision.py:77-89) for n_images at once:
+ * crop_offsets int32 [n_images+1] (first crop of an image is its global crop), tilings int32
+ * [n_images][2].  Writes the projected rows of image i to embeds rows i*prefix_len+1 .. +grid^2
+ * (row i*prefix_len is left for the BOS embedding, moondream.py:250-254); embeds is
+ * [n_images*prefix_len, txt_dim] bf16. */
+long long md_vision_project_workspace_bytes(const md_model* model, int n_images);
+int md_vision_project(md_model* model, const void* feats, const int* crop_offsets, const int* tilings,
+                      int n_images, void* embeds, void* workspace, void* stream);
+
+/* text_encoder (text.py:12-13): out[i] = wte[ids[i * id_stride]]. */
+int md_embed_tokens(md_model* model, const int* ids, long long id_stride, int n, void* out,
+                    long long ldo, void* stream);
+
+/* _prefill (text.py:128-160) over a ragged batch: x [total_tokens, txt_dim] embeddings in, hidden
+ * states out (in place); sequence s owns rows q_offsets[s]..q_offsets[s+1] at positions
+ * start_pos[s]...; K/V are written to the pages. */
+long long md_text_prefill_workspace_bytes(const md_model* model, int total_tokens);
+int md_text_prefill(md_model* model, void* x, int total_tokens, const int* q_offsets,
+                    const int* start_pos, int n_seqs, int max_q, const md_kv* kv, void* workspace,
+                    void* stream);
+
+/* _decode_one_tok's decoder half (text.py:128-160 with T=1) for `batch` sequences:
+ * x [batch, txt_dim] embeddings in, hidden out (in place); pos int32 [batch] (device). */
+long long md_text_decode_workspace_bytes(const md_model* model, int batch);
+int md_text_decode_step(md_model* model, void* x, const int* pos, int batch, const md_kv* kv,
+                        void* workspace, void* stream);
+
+/* lm_head + greedy argmax (text.py:163-167, moondream.py:313-314,517-524): hidden rows
+ * [batch] x txt_dim (stride ld_hidden).  Token ids go to out_ids[b * out_stride + *out_index]
+ * (out_index: device int or NULL = 0); mask_id >= 0 is excluded (answer_id, moondream.py:517).
+ * Optional: out_margin (same addressing, top1 - top2 of the bf16 logits), out_logits bf16 [batch, vocab]. */
+long long md_lm_head_workspace_bytes(const md_model* model, int batch);
+int md_lm_head_argmax(md_model* model, const void* hidden, long long ld_hidden, int batch, int mask_id,
+                      int* out_ids, long long out_stride, const int* out_index, float* out_margin,
+                      void* out_logits, void* workspace, void* stream);
+
+/* Decode-loop bookkeeping on the device (the generator loop of moondream.py:481-530 without the
+ * per-token .item() sync): cur_tok[b] = (forced ? forced : preds)[b*stride + step+1]; pos[b] += 1;
+ * finished[b] |= (cur_tok[b] == eos_id); step += 1. */
+int md_decode_advance(int* cur_tok, int* pos, int* step, const int* preds, const int* forced,
+                      long long stride, int batch, int eos_id, int* finished, void* stream);
+
+/* out[i, :] = src[row_index[i], :] (picks each sequence's last prompt row, text.py:164). */
+int md_gather_rows_bf16(const void* src, long long ld_src, const int* row_index, int n, int dim,
+                        void* out, long long ldo, void* stream);
+
+/* Region head (region.py).  which: 0 = coordinate (decode: 1024 bins -> out_bins [batch]),
+ * 1 = size (decode: view(2,-1) -> out_bins [batch][2] = (w_bin, h_bin)). */
+long long md_region_workspace_bytes(const md_model* model, int batch);
+int md_region_decode(md_model* model, int which, const void* hidden, long long ld_hidden, int batch,
+                     int* out_bins, void* workspace, void* stream);
+/* values fp32 [batch][1 or 2] (coordinate in [0,1] / (w, h)); out bf16 [batch, txt_dim]
+ * (region.py:32-43, 60-71 incl. fourier_features :12-29). */
+int md_region_encode(md_model* model, int which, const float* values, int batch, void* out,
+                     long long ldo, void* workspace, void* stream);
+/* bins -> values (moondream.py:673,683,701-702): coord = bin / 1024; size = 2^(bin/1023*10 - 10). */
+int md_region_bins_to_values(int which, const int* bins, int n, float* out, void* stream);
 
 #ifdef __cplusplus
 }

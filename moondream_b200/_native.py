@@ -14,24 +14,59 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libmoondream_b200.so")
 
 _lib = None
 
-# name -> (restype, [argtypes])
+class md_kv(ctypes.Structure):
+    _fields_ = [("pool", c_void_p), ("n_pages", c_int), ("block_tables", c_void_p), ("max_blocks", c_int)]
+
+
+class md_dims(ctypes.Structure):
+    _fields_ = [(n, c_int) for n in (
+        "vis_dim", "vis_ff", "vis_layers", "vis_heads", "crop", "patch", "patch_k", "grid", "margin",
+        "proj_inner", "txt_dim", "txt_ff", "txt_layers", "txt_heads", "vocab", "max_context",
+        "prefix_len", "reg_inner", "coord_feat", "coord_out", "size_feat", "size_out")]
+
+
+_P = c_void_p
+_LL = c_longlong
+_KV = ctypes.POINTER(md_kv)
+_DIMS = ctypes.POINTER(md_dims)
+
+# name -> (restype, [argtypes]); must list every function include/moondream_b200.h declares
 _SIGNATURES = {
     "md_last_error": (c_char_p, []),
     "md_abi_version": (c_int, []),
     "md_launch_count": (c_longlong, []),
     "md_reset_launch_count": (None, []),
-    "md_linear_bf16": (
-        c_int,
-        [c_void_p, c_longlong, c_void_p, c_longlong, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
-         c_longlong, c_int, c_void_p, c_longlong, c_int, c_int, c_int, c_void_p],
-    ),
+    "md_linear_bf16": (c_int, [_P, _LL, _P, _LL, c_int, c_int, c_int, c_int, _P, _P, _LL, c_int, _P, _LL,
+                               c_int, c_int, c_int, _P]),
     "md_linear_small_batch_splits": (c_int, [c_int, c_int]),
-    "md_linear_small_batch_workspace_bytes": (c_longlong, [c_int, c_int, c_int]),
-    "md_linear_small_batch_bf16": (
-        c_int,
-        [c_void_p, c_longlong, c_void_p, c_longlong, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
-         c_longlong, c_void_p, c_longlong, c_void_p, c_void_p],
-    ),
+    "md_linear_small_batch_workspace_bytes": (_LL, [c_int, c_int, c_int]),
+    "md_linear_small_batch_bf16": (c_int, [_P, _LL, _P, _LL, c_int, c_int, c_int, c_int, _P, _P, _LL, _P,
+                                           _LL, _P, _P]),
+    "md_layernorm_bf16": (c_int, [_P, _LL, _P, _P, _P, _LL, c_int, c_int, _P]),
+    "md_vit_attention_bf16": (c_int, [_P, c_int, c_int, c_int, _P, _P]),
+    "md_rope_kv_write_bf16": (c_int, [_P, c_int, c_int, _P, _P, c_int, _P, _P, _KV, c_int, _P]),
+    "md_prefill_attention_bf16": (c_int, [_P, c_int, _P, _P, c_int, c_int, c_int, _KV, c_int, _P, _P]),
+    "md_decode_attention_bf16": (c_int, [_P, c_int, _P, c_int, _KV, c_int, _P, _P]),
+    "md_model_num_weights": (c_int, [_DIMS]),
+    "md_model_create": (c_int, [_DIMS, ctypes.POINTER(c_void_p), c_int, _P, _P, ctypes.POINTER(c_void_p)]),
+    "md_model_destroy": (None, [_P]),
+    "md_vision_encode_workspace_bytes": (_LL, [_P, c_int]),
+    "md_vision_encode": (c_int, [_P, _P, c_int, _P, _P, _P]),
+    "md_vision_project_workspace_bytes": (_LL, [_P, c_int]),
+    "md_vision_project": (c_int, [_P, _P, _P, _P, c_int, _P, _P, _P]),
+    "md_embed_tokens": (c_int, [_P, _P, _LL, c_int, _P, _LL, _P]),
+    "md_text_prefill_workspace_bytes": (_LL, [_P, c_int]),
+    "md_text_prefill": (c_int, [_P, _P, c_int, _P, _P, c_int, c_int, _KV, _P, _P]),
+    "md_text_decode_workspace_bytes": (_LL, [_P, c_int]),
+    "md_text_decode_step": (c_int, [_P, _P, _P, c_int, _KV, _P, _P]),
+    "md_lm_head_workspace_bytes": (_LL, [_P, c_int]),
+    "md_lm_head_argmax": (c_int, [_P, _P, _LL, c_int, c_int, _P, _LL, _P, _P, _P, _P, _P]),
+    "md_decode_advance": (c_int, [_P, _P, _P, _P, _P, _LL, c_int, c_int, _P, _P]),
+    "md_gather_rows_bf16": (c_int, [_P, _LL, _P, c_int, c_int, _P, _LL, _P]),
+    "md_region_workspace_bytes": (_LL, [_P, c_int]),
+    "md_region_decode": (c_int, [_P, c_int, _P, _LL, c_int, _P, _P, _P]),
+    "md_region_encode": (c_int, [_P, c_int, _P, c_int, _P, _LL, _P, _P]),
+    "md_region_bins_to_values": (c_int, [c_int, _P, c_int, _P, _P]),
 }
 
 

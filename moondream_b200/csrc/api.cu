@@ -1,10 +1,8 @@
 // C-ABI of libmoondream_b200.so: plain pointers and sizes, no torch types (see include/moondream_b200.h
 // for the contract and the reference call sites each entry point replaces).
-#include "../../include/moondream_b200.h"
-
 #include <string.h>
 
-#include "kernels.cuh"
+#include "engine.h"
 
 namespace md {
 
@@ -23,10 +21,12 @@ void reset_launch_count() { g_launches = 0; }
 
 }  // namespace md
 
-using bf16 = __nv_bfloat16;
+using md::bf16;
 #define BF(p) reinterpret_cast<const bf16*>(p)
 #define BFM(p) reinterpret_cast<bf16*>(p)
 #define STREAM(s) reinterpret_cast<cudaStream_t>(s)
+#define NEED(p, what) \
+  if (!(p)) return md::set_error(what ": null pointer")
 
 extern "C" {
 
@@ -35,10 +35,13 @@ long long md_launch_count(void) { return md::launch_count(); }
 void md_reset_launch_count(void) { md::reset_launch_count(); }
 int md_abi_version(void) { return MD_ABI_VERSION; }
 
+// ---------------------------------------------------------------- operator level
 int md_linear_bf16(const void* x, long long ldx, const void* w, long long ldw, int M, int N, int K,
                    int epilogue, const void* bias, const void* residual, long long ldr, int res_mod,
                    void* out, long long ldo, int remap_gin, int remap_gout, int remap_goff,
                    void* stream) {
+  NEED(x && w && out, "md_linear_bf16");
+  if (epilogue < 0 || epilogue > 2) return md::set_error("md_linear_bf16: bad epilogue");
   return md::gemm_rowform(BF(x), ldx, BF(w), ldw, M, N, K, epilogue, BF(bias), BF(residual), ldr,
                           res_mod, BFM(out), ldo, remap_gin, remap_gout, remap_goff, STREAM(stream));
 }
@@ -53,12 +56,157 @@ int md_linear_small_batch_bf16(const void* x, long long ldx, const void* w, long
                                int n_out, int K, int epilogue, const void* bias, const void* residual,
                                long long ldr, void* out, long long ldo, void* workspace,
                                void* stream) {
+  NEED(x && w && out && workspace, "md_linear_small_batch_bf16");
+  if (epilogue < 0 || epilogue > 2) return md::set_error("md_linear_small_batch_bf16: bad epilogue");
   const int want = md::gemm_swapped_splits(n_out, K);
   const int used = md::gemm_swapped(BF(w), ldw, BF(x), ldx, n_out, batch, K, want,
                                     reinterpret_cast<float*>(workspace), STREAM(stream));
   if (used < 0) return 1;
   return md::splitk_epilogue(reinterpret_cast<const float*>(workspace), used, batch, n_out, epilogue,
                              BF(bias), BF(residual), ldr, BFM(out), ldo, STREAM(stream));
+}
+
+int md_layernorm_bf16(const void* x, long long ldx, const void* w, const void* b, void* y,
+                      long long ldy, int rows, int dim, void* stream) {
+  NEED(x && w && b && y, "md_layernorm_bf16");
+  return md::layernorm(BF(x), ldx, BF(w), BF(b), BFM(y), ldy, rows, dim, 1e-5f, STREAM(stream));
+}
+
+int md_vit_attention_bf16(const void* qkv, int n_crops, int seq, int n_heads, void* out, void* stream) {
+  NEED(qkv && out, "md_vit_attention_bf16");
+  return md::vit_attention(BF(qkv), n_crops, seq, n_heads, BFM(out), STREAM(stream));
+}
+
+int md_rope_kv_write_bf16(const void* qkv, int n_tokens, int n_heads, const int* q_offsets,
+                          const int* start_pos, int n_seqs, const float* rope_table, void* q_out,
+                          const md_kv* kv, int layer, void* stream) {
+  NEED(qkv && start_pos && rope_table && q_out && kv && kv->pool && kv->block_tables, "md_rope_kv_write_bf16");
+  return md::rope_kv_write(BF(qkv), n_tokens, n_heads, q_offsets, start_pos, n_seqs, rope_table,
+                           BFM(q_out), BFM(kv->pool), kv->n_pages, kv->block_tables, kv->max_blocks,
+                           layer, STREAM(stream));
+}
+
+int md_prefill_attention_bf16(const void* q, int n_heads, const int* q_offsets, const int* start_pos,
+                              int n_seqs, int max_q, int prefix_len, const md_kv* kv, int layer,
+                              void* out, void* stream) {
+  NEED(q && q_offsets && start_pos && kv && kv->pool && kv->block_tables && out, "md_prefill_attention_bf16");
+  return md::prefill_attention(BF(q), n_heads, q_offsets, start_pos, n_seqs, max_q, prefix_len,
+                               BF(kv->pool), kv->n_pages, kv->block_tables, kv->max_blocks, layer,
+                               BFM(out), STREAM(stream));
+}
+
+int md_decode_attention_bf16(const void* q, int n_heads, const int* pos, int n_seqs, const md_kv* kv,
+                             int layer, void* out, void* stream) {
+  NEED(q && pos && kv && kv->pool && kv->block_tables && out, "md_decode_attention_bf16");
+  return md::decode_attention(BF(q), n_heads, pos, n_seqs, BF(kv->pool), kv->n_pages, kv->block_tables,
+                              kv->max_blocks, layer, BFM(out), STREAM(stream));
+}
+
+// ---------------------------------------------------------------- model level
+int md_model_num_weights(const md_dims* dims) {
+  if (!dims) return -1;
+  return md::model_num_weights(*dims);
+}
+
+int md_model_create(const md_dims* dims, const void* const* weights, int n_weights,
+                    const void* pixel_lut, const float* rope_table, md_model** out) {
+  NEED(dims && weights && pixel_lut && rope_table && out, "md_model_create");
+  md::Model* m = nullptr;
+  if (md::model_create(*dims, weights, n_weights, pixel_lut, rope_table, &m)) return 1;
+  *out = static_cast<md_model*>(m);
+  return 0;
+}
+
+void md_model_destroy(md_model* model) { delete static_cast<md::Model*>(model); }
+
+long long md_vision_encode_workspace_bytes(const md_model* model, int n_crops) {
+  return model ? md::vision_encode_ws_bytes(*model, n_crops) : -1;
+}
+int md_vision_encode(md_model* model, const uint8_t* crops, int n_crops, void* feats, void* workspace,
+                     void* stream) {
+  NEED(model && crops && feats && workspace, "md_vision_encode");
+  return md::vision_encode(*model, crops, n_crops, BFM(feats), workspace, STREAM(stream));
+}
+
+long long md_vision_project_workspace_bytes(const md_model* model, int n_images) {
+  return model ? md::vision_project_ws_bytes(*model, n_images) : -1;
+}
+int md_vision_project(md_model* model, const void* feats, const int* crop_offsets, const int* tilings,
+                      int n_images, void* embeds, void* workspace, void* stream) {
+  NEED(model && feats && crop_offsets && tilings && embeds && workspace, "md_vision_project");
+  return md::vision_project(*model, BF(feats), crop_offsets, tilings, n_images, BFM(embeds), workspace,
+                            STREAM(stream));
+}
+
+int md_embed_tokens(md_model* model, const int* ids, long long id_stride, int n, void* out,
+                    long long ldo, void* stream) {
+  NEED(model && ids && out, "md_embed_tokens");
+  return md::embed_tokens(ids, id_stride, n, model->wte, model->d.txt_dim, model->d.vocab, BFM(out), ldo,
+                          STREAM(stream));
+}
+
+long long md_text_prefill_workspace_bytes(const md_model* model, int total_tokens) {
+  return model ? md::text_prefill_ws_bytes(*model, total_tokens) : -1;
+}
+int md_text_prefill(md_model* model, void* x, int total_tokens, const int* q_offsets,
+                    const int* start_pos, int n_seqs, int max_q, const md_kv* kv, void* workspace,
+                    void* stream) {
+  NEED(model && x && q_offsets && start_pos && kv && kv->pool && kv->block_tables && workspace, "md_text_prefill");
+  return md::text_prefill(*model, BFM(x), total_tokens, q_offsets, start_pos, n_seqs, max_q, *kv, workspace,
+                          STREAM(stream));
+}
+
+long long md_text_decode_workspace_bytes(const md_model* model, int batch) {
+  return model ? md::text_decode_ws_bytes(*model, batch) : -1;
+}
+int md_text_decode_step(md_model* model, void* x, const int* pos, int batch, const md_kv* kv,
+                        void* workspace, void* stream) {
+  NEED(model && x && pos && kv && kv->pool && kv->block_tables && workspace, "md_text_decode_step");
+  return md::text_decode_step(*model, BFM(x), pos, batch, *kv, workspace, STREAM(stream));
+}
+
+long long md_lm_head_workspace_bytes(const md_model* model, int batch) {
+  return model ? md::lm_head_ws_bytes(*model, batch) : -1;
+}
+int md_lm_head_argmax(md_model* model, const void* hidden, long long ld_hidden, int batch, int mask_id,
+                      int* out_ids, long long out_stride, const int* out_index, float* out_margin,
+                      void* out_logits, void* workspace, void* stream) {
+  NEED(model && hidden && out_ids && workspace, "md_lm_head_argmax");
+  return md::lm_head_argmax(*model, BF(hidden), ld_hidden, batch, mask_id, out_ids, out_stride, out_index,
+                            out_margin, BFM(out_logits), workspace, STREAM(stream));
+}
+
+int md_decode_advance(int* cur_tok, int* pos, int* step, const int* preds, const int* forced,
+                      long long stride, int batch, int eos_id, int* finished, void* stream) {
+  NEED(cur_tok && pos && step && preds, "md_decode_advance");
+  return md::decode_advance(cur_tok, pos, step, preds, forced, stride, batch, eos_id, finished,
+                            STREAM(stream));
+}
+
+int md_gather_rows_bf16(const void* src, long long ld_src, const int* row_index, int n, int dim,
+                        void* out, long long ldo, void* stream) {
+  NEED(src && row_index && out, "md_gather_rows_bf16");
+  return md::gather_rows(BF(src), ld_src, row_index, n, dim, BFM(out), ldo, STREAM(stream));
+}
+
+long long md_region_workspace_bytes(const md_model* model, int batch) {
+  return model ? md::region_ws_bytes(*model, batch) : -1;
+}
+int md_region_decode(md_model* model, int which, const void* hidden, long long ld_hidden, int batch,
+                     int* out_bins, void* workspace, void* stream) {
+  NEED(model && hidden && out_bins && workspace, "md_region_decode");
+  if (which != 0 && which != 1) return md::set_error("md_region_decode: which must be 0 or 1");
+  return md::region_decode(*model, which, BF(hidden), ld_hidden, batch, out_bins, workspace, STREAM(stream));
+}
+int md_region_encode(md_model* model, int which, const float* values, int batch, void* out,
+                     long long ldo, void* workspace, void* stream) {
+  NEED(model && values && out && workspace, "md_region_encode");
+  if (which != 0 && which != 1) return md::set_error("md_region_encode: which must be 0 or 1");
+  return md::region_encode(*model, which, values, batch, BFM(out), ldo, workspace, STREAM(stream));
+}
+int md_region_bins_to_values(int which, const int* bins, int n, float* out, void* stream) {
+  NEED(bins && out, "md_region_bins_to_values");
+  return md::bins_to_values(which, bins, n, out, STREAM(stream));
 }
 
 }  // extern "C"

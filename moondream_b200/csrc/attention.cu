@@ -1,0 +1,445 @@
+// Attention kernels.
+//
+//  * flash_attention_kernel<HD, DP, PAGED>: tiled online-softmax attention, 64 queries x 64 keys per
+//    step, bf16 mma.sync m16n8k16 with fp32 accumulation, cp.async double-buffered K/V tiles.
+//      - PAGED=false: ViT self-attention (reference layers.py:155-166: softmax(QK^T/sqrt(72))V, no
+//        mask, 729 tokens, head_dim 72 padded to 80 in shared memory only), reading Q/K/V straight
+//        out of the fused qkv GEMM output [B*729, 3*D] and writing token-major [B*729, D].
+//      - PAGED=true: decoder prefill (reference text.py:46-50 under the mask of moondream.py:138-146):
+//        prefix-LM mask computed from indices (positions < prefix attend bidirectionally inside the
+//        prefix, causal afterwards); K/V come from the paged KV pool and only the pos+T keys that
+//        exist are visited (the reference scans all 2048 cache slots under a bool mask).
+//  * decode_attention_kernel: one query per (sequence, head), streams that head's K/V pages with
+//    coalesced 128-byte rows; HBM-bound (reference text.py:46-50 with the [1,1,2048] mask of
+//    moondream.py:472-474,514).
+//
+// KV pool layout (bf16): [layer][page][2 (k,v)][head][64 tokens][64 dims]; block_tables[seq][i] is
+// the page holding positions 64*i .. 64*i+63 of that sequence.
+#include <math.h>
+
+#include "kernels.cuh"
+#include "ptx.cuh"
+
+namespace md {
+
+constexpr int kPageTokens = 64;
+
+struct FlashParams {
+  // dense (ViT) addressing
+  const __nv_bfloat16* q;
+  const __nv_bfloat16* k;
+  const __nv_bfloat16* v;
+  long long q_stride, kv_stride;   // row strides in elements
+  int seq_len;                     // dense: rows per batch item
+  // paged (text) addressing
+  const int* q_offsets;            // [n_seqs + 1] row offsets into q/out
+  const int* start_pos;            // [n_seqs]
+  const __nv_bfloat16* kv_pool;
+  const int* block_tables;
+  int max_blocks, layer, n_pages, prefix_len;
+  // common
+  __nv_bfloat16* out;
+  long long out_stride;
+  int n_heads;
+  float scale_log2;                // softmax scale * log2(e)
+};
+
+template <int HD, int DP, bool PAGED>
+__global__ void __launch_bounds__(128)
+flash_attention_kernel(const FlashParams p) {
+  constexpr int BM = 64, BN = 64;
+  constexpr int LDS = DP + 8;                 // padded row pitch (elements): conflict-free ldmatrix
+  constexpr int CH = HD / 8;                  // 16-byte chunks per global row
+  constexpr int KSTEPS = DP / 16;             // k16 steps of QK^T
+  constexpr int DT = (HD + 7) / 8;            // n8 tiles of the output (head dim)
+  extern __shared__ __align__(16) uint8_t fa_smem[];
+  __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(fa_smem);
+  __nv_bfloat16* sK = sQ + BM * LDS;          // [2][BN][LDS]
+  __nv_bfloat16* sV = sK + 2 * BN * LDS;      // [2][BN][LDS]
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int head = blockIdx.y;
+  const int item = blockIdx.z;
+  const int q0 = blockIdx.x * BM;
+
+  int n_q, kv_len, q_pos0;
+  long long q_row0;
+  const int* btab = nullptr;
+  if (PAGED) {
+    const int off = p.q_offsets[item];
+    n_q = p.q_offsets[item + 1] - off;
+    q_pos0 = p.start_pos[item];
+    kv_len = q_pos0 + n_q;
+    q_row0 = off;
+    btab = p.block_tables + static_cast<long long>(item) * p.max_blocks;
+  } else {
+    n_q = p.seq_len;
+    q_pos0 = 0;
+    kv_len = p.seq_len;
+    q_row0 = static_cast<long long>(item) * p.seq_len;
+  }
+  if (q0 >= n_q) return;
+
+  // zero the padding columns [HD, DP) of Q and K tiles once (cp.async never touches them)
+  if constexpr (DP > HD) {
+    for (int i = tid; i < (BM + 2 * BN) * (DP - HD); i += 128) {
+      const int r = i / (DP - HD), c = HD + i % (DP - HD);
+      sQ[r * LDS + c] = __float2bfloat16(0.f);   // sQ and sK are contiguous: rows 0..BM+2BN-1
+    }
+  }
+
+  // ---- async tile loaders ----
+  auto load_q = [&]() {
+    for (int i = tid; i < BM * CH; i += 128) {
+      const int r = i / CH, c = i % CH;
+      const bool ok = q0 + r < n_q;
+      const __nv_bfloat16* src =
+          p.q + (q_row0 + (ok ? q0 + r : 0)) * p.q_stride + head * HD + c * 8;
+      cp_async_16(sQ + r * LDS + c * 8, src, ok);
+    }
+  };
+  auto load_kv = [&](int tile, int buf) {
+    const int k0 = tile * BN;
+    const __nv_bfloat16 *kbase, *vbase;
+    long long stride;
+    if (PAGED) {
+      const int page = btab[tile];
+      const long long pbase =
+          ((static_cast<long long>(p.layer) * p.n_pages + page) * 2) * p.n_heads * (kPageTokens * 64);
+      kbase = p.kv_pool + pbase + static_cast<long long>(head) * (kPageTokens * 64);
+      vbase = kbase + static_cast<long long>(p.n_heads) * (kPageTokens * 64);
+      stride = 64;
+    } else {
+      kbase = p.k + (q_row0 + k0) * p.kv_stride + head * HD;
+      vbase = p.v + (q_row0 + k0) * p.kv_stride + head * HD;
+      stride = p.kv_stride;
+    }
+    __nv_bfloat16* dk = sK + buf * BN * LDS;
+    __nv_bfloat16* dv = sV + buf * BN * LDS;
+    for (int i = tid; i < BN * CH; i += 128) {
+      const int r = i / CH, c = i % CH;
+      const bool ok = k0 + r < kv_len;
+      const long long ro = ok ? r * stride : 0;
+      cp_async_16(dk + r * LDS + c * 8, kbase + ro + c * 8, ok);
+      cp_async_16(dv + r * LDS + c * 8, vbase + ro + c * 8, ok);
+    }
+  };
+
+  // how many key tiles this query tile can see
+  int n_tiles;
+  {
+    const int q_hi = q_pos0 + min(q0 + BM, n_q) - 1;     // last query position of the tile
+    int reach = q_hi + 1;
+    if (PAGED) {
+      if (q_pos0 + q0 < p.prefix_len) reach = max(reach, p.prefix_len);
+      reach = min(reach, kv_len);
+    } else {
+      reach = kv_len;
+    }
+    n_tiles = (reach + BN - 1) / BN;
+  }
+
+  load_q();
+  load_kv(0, 0);
+  cp_async_commit();
+
+  float o_acc[DT][4];
+#pragma unroll
+  for (int i = 0; i < DT; ++i) o_acc[i][0] = o_acc[i][1] = o_acc[i][2] = o_acc[i][3] = 0.f;
+  float row_max[2] = {-INFINITY, -INFINITY};
+  float row_sum[2] = {0.f, 0.f};
+  uint32_t qf[KSTEPS][4];
+
+  const int r_lo = warp * 16 + (lane >> 2);            // this thread's two query rows in the tile
+  const int qpos_lo = q_pos0 + q0 + r_lo, qpos_hi = qpos_lo + 8;
+
+  for (int tile = 0; tile < n_tiles; ++tile) {
+    const int buf = tile & 1;
+    if (tile + 1 < n_tiles) load_kv(tile + 1, buf ^ 1);
+    cp_async_commit();
+    cp_async_wait<1>();
+    __syncthreads();
+
+    if (tile == 0) {
+#pragma unroll
+      for (int ks = 0; ks < KSTEPS; ++ks)
+        ldmatrix_x4(qf[ks], smem_u32(sQ + (warp * 16 + (lane & 15)) * LDS + ks * 16 + (lane >> 4) * 8));
+    }
+
+    // ---- S = Q K^T ----
+    float s[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f;
+    const __nv_bfloat16* bK = sK + buf * BN * LDS;
+#pragma unroll
+    for (int ks = 0; ks < KSTEPS; ++ks) {
+#pragma unroll
+      for (int np = 0; np < 4; ++np) {             // pairs of n8 tiles
+        uint32_t kb[4];
+        ldmatrix_x4(kb, smem_u32(bK + (np * 16 + (lane & 7) + (lane >> 4) * 8) * LDS + ks * 16 +
+                                 ((lane >> 3) & 1) * 8));
+        const uint32_t b0[2] = {kb[0], kb[1]};
+        const uint32_t b1[2] = {kb[2], kb[3]};
+        mma_bf16_16816(s[2 * np], qf[ks], b0);
+        mma_bf16_16816(s[2 * np + 1], qf[ks], b1);
+      }
+    }
+
+    // ---- mask + online softmax ----
+    const int kcol0 = tile * BN + (lane & 3) * 2;
+    const bool need_mask = PAGED ? true : (tile * BN + BN > kv_len);
+    if (need_mask) {
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int kpos = kcol0 + nt * 8 + (e & 1);
+          const int qpos = (e < 2) ? qpos_lo : qpos_hi;
+          bool ok = kpos < kv_len;
+          if (PAGED) ok = ok && (kpos <= qpos || (kpos < p.prefix_len && qpos < p.prefix_len));
+          if (!ok) s[nt][e] = -INFINITY;
+        }
+      }
+    }
+    float mx[2] = {row_max[0], row_max[1]};
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      mx[0] = fmaxf(mx[0], fmaxf(s[nt][0], s[nt][1]));
+      mx[1] = fmaxf(mx[1], fmaxf(s[nt][2], s[nt][3]));
+    }
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      mx[h] = fmaxf(mx[h], __shfl_xor_sync(0xffffffffu, mx[h], 1));
+      mx[h] = fmaxf(mx[h], __shfl_xor_sync(0xffffffffu, mx[h], 2));
+    }
+    float corr[2], base[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      // a fully masked row so far keeps max = -inf: use 0 as the exponent base to avoid inf - inf
+      base[h] = (mx[h] == -INFINITY) ? 0.f : mx[h] * p.scale_log2;
+      corr[h] = (row_max[h] == -INFINITY) ? 0.f : exp2f(row_max[h] * p.scale_log2 - base[h]);
+      row_max[h] = mx[h];
+      row_sum[h] *= corr[h];
+    }
+#pragma unroll
+    for (int i = 0; i < DT; ++i) {
+      o_acc[i][0] *= corr[0]; o_acc[i][1] *= corr[0];
+      o_acc[i][2] *= corr[1]; o_acc[i][3] *= corr[1];
+    }
+    uint32_t pf[4][4];                              // P as A fragments for 4 k16 steps
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      const float p0 = exp2f(s[nt][0] * p.scale_log2 - base[0]);
+      const float p1 = exp2f(s[nt][1] * p.scale_log2 - base[0]);
+      const float p2 = exp2f(s[nt][2] * p.scale_log2 - base[1]);
+      const float p3 = exp2f(s[nt][3] * p.scale_log2 - base[1]);
+      row_sum[0] += p0 + p1;
+      row_sum[1] += p2 + p3;
+      pf[nt >> 1][(nt & 1) * 2 + 0] = pack_bf16x2(p0, p1);
+      pf[nt >> 1][(nt & 1) * 2 + 1] = pack_bf16x2(p2, p3);
+    }
+
+    // ---- O += P V ----
+    const __nv_bfloat16* bV = sV + buf * BN * LDS;
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {                // 16 keys per step
+#pragma unroll
+      for (int dp = 0; dp < DT / 2; ++dp) {         // pairs of n8 tiles over the head dim
+        uint32_t vb[4];
+        ldmatrix_x4_trans(vb, smem_u32(bV + (ks * 16 + (lane & 15)) * LDS + dp * 16 + (lane >> 4) * 8));
+        const uint32_t b0[2] = {vb[0], vb[1]};
+        const uint32_t b1[2] = {vb[2], vb[3]};
+        mma_bf16_16816(o_acc[2 * dp], pf[ks], b0);
+        mma_bf16_16816(o_acc[2 * dp + 1], pf[ks], b1);
+      }
+      if (DT & 1) {                                  // odd tile count (head_dim 72 -> 9 tiles)
+        uint32_t vb[2];
+        ldmatrix_x2_trans(vb, smem_u32(bV + (ks * 16 + (lane & 15)) * LDS + (DT - 1) * 8));
+        mma_bf16_16816(o_acc[DT - 1], pf[ks], vb);
+      }
+    }
+    __syncthreads();                                 // everyone done with `buf` before it is refilled
+  }
+  cp_async_wait<0>();
+
+  // ---- normalise and store ----
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    row_sum[h] += __shfl_xor_sync(0xffffffffu, row_sum[h], 1);
+    row_sum[h] += __shfl_xor_sync(0xffffffffu, row_sum[h], 2);
+  }
+  const float inv0 = row_sum[0] > 0.f ? 1.f / row_sum[0] : 0.f;
+  const float inv1 = row_sum[1] > 0.f ? 1.f / row_sum[1] : 0.f;
+  const int col = (lane & 3) * 2;
+  if (q0 + r_lo < n_q) {
+    __nv_bfloat16* o = p.out + (q_row0 + q0 + r_lo) * p.out_stride + head * HD + col;
+#pragma unroll
+    for (int i = 0; i < DT; ++i)
+      *reinterpret_cast<uint32_t*>(o + i * 8) = pack_bf16x2(o_acc[i][0] * inv0, o_acc[i][1] * inv0);
+  }
+  if (q0 + r_lo + 8 < n_q) {
+    __nv_bfloat16* o = p.out + (q_row0 + q0 + r_lo + 8) * p.out_stride + head * HD + col;
+#pragma unroll
+    for (int i = 0; i < DT; ++i)
+      *reinterpret_cast<uint32_t*>(o + i * 8) = pack_bf16x2(o_acc[i][2] * inv1, o_acc[i][3] * inv1);
+  }
+}
+
+template <int HD, int DP, bool PAGED>
+static int launch_flash(const FlashParams& p, dim3 grid, cudaStream_t stream) {
+  constexpr int smem = (64 + 4 * 64) * (DP + 8) * 2;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(flash_attention_kernel<HD, DP, PAGED>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return set_error(cudaGetErrorString(e));
+    configured = true;
+  }
+  flash_attention_kernel<HD, DP, PAGED><<<grid, 128, smem, stream>>>(p);
+  count_launch();
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error(cudaGetErrorString(e));
+  return 0;
+}
+
+int vit_attention(const __nv_bfloat16* qkv, int n_crops, int seq, int n_heads, __nv_bfloat16* out,
+                  cudaStream_t stream) {
+  if (n_crops <= 0) return set_error("vit_attention: empty batch");
+  const int D = n_heads * 72;
+  FlashParams p{};
+  p.q = qkv; p.k = qkv + D; p.v = qkv + 2 * D;
+  p.q_stride = 3LL * D; p.kv_stride = 3LL * D;
+  p.seq_len = seq;
+  p.out = out; p.out_stride = D;
+  p.n_heads = n_heads;
+  p.scale_log2 = (1.0f / sqrtf(72.0f)) * 1.4426950408889634f;
+  dim3 grid((seq + 63) / 64, n_heads, n_crops);
+  return launch_flash<72, 80, false>(p, grid, stream);
+}
+
+int prefill_attention(const __nv_bfloat16* q, int n_heads, const int* q_offsets, const int* start_pos,
+                      int n_seqs, int max_q, int prefix_len, const __nv_bfloat16* kv_pool, int n_pages,
+                      const int* block_tables, int max_blocks, int layer, __nv_bfloat16* out,
+                      cudaStream_t stream) {
+  if (n_seqs <= 0 || max_q <= 0) return set_error("prefill_attention: empty batch");
+  FlashParams p{};
+  p.q = q; p.q_stride = static_cast<long long>(n_heads) * 64;
+  p.q_offsets = q_offsets; p.start_pos = start_pos;
+  p.kv_pool = kv_pool; p.block_tables = block_tables; p.max_blocks = max_blocks;
+  p.layer = layer; p.n_pages = n_pages; p.prefix_len = prefix_len;
+  p.out = out; p.out_stride = static_cast<long long>(n_heads) * 64;
+  p.n_heads = n_heads;
+  p.scale_log2 = 0.125f * 1.4426950408889634f;
+  dim3 grid((max_q + 63) / 64, n_heads, n_seqs);
+  return launch_flash<64, 64, true>(p, grid, stream);
+}
+
+// ------------------------------------------------------------------------------------------------
+// decode attention: one (sequence, head) per CTA, 4 warps split the keys, 8 lanes per key row.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+decode_attention_kernel(const __nv_bfloat16* __restrict__ q, int n_heads, const int* __restrict__ pos,
+                        const __nv_bfloat16* __restrict__ kv_pool, int n_pages,
+                        const int* __restrict__ block_tables, int max_blocks, int layer,
+                        __nv_bfloat16* __restrict__ out, float scale_log2) {
+  const int head = blockIdx.x, seq = blockIdx.y;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int sub = lane & 7;            // which 16-byte chunk (8 dims) of the 64-dim row
+  const int rowi = lane >> 3;          // 4 key rows per warp step
+  const int kv_len = pos[seq] + 1;     // the current token's K/V was written just before this kernel
+  const int* btab = block_tables + static_cast<long long>(seq) * max_blocks;
+
+  float qv[8];
+  {
+    const uint4 qq = *reinterpret_cast<const uint4*>(q + (static_cast<long long>(seq) * n_heads + head) * 64 + sub * 8);
+    const uint32_t w[4] = {qq.x, qq.y, qq.z, qq.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { qv[2 * j] = bf16_lo(w[j]); qv[2 * j + 1] = bf16_hi(w[j]); }
+  }
+  float m = -INFINITY, l = 0.f;
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+
+  const long long head_off = static_cast<long long>(head) * (kPageTokens * 64);
+  const long long v_off = static_cast<long long>(n_heads) * (kPageTokens * 64);
+  // each warp takes 16 consecutive keys (4 steps of 4 rows) per iteration, warps interleave
+  for (int k0 = warp * 16; k0 < kv_len; k0 += 64) {
+    const int page = btab[k0 >> 6];
+    const __nv_bfloat16* kp = kv_pool +
+        ((static_cast<long long>(layer) * n_pages + page) * 2) * n_heads * (kPageTokens * 64) + head_off;
+    uint4 kq[4], vq[4];
+#pragma unroll
+    for (int st = 0; st < 4; ++st) {
+      const int kpos = k0 + st * 4 + rowi;
+      const bool ok = kpos < kv_len;
+      const long long ro = static_cast<long long>(kpos & 63) * 64 + sub * 8;
+      kq[st] = ok ? *reinterpret_cast<const uint4*>(kp + ro) : make_uint4(0, 0, 0, 0);
+      vq[st] = ok ? *reinterpret_cast<const uint4*>(kp + v_off + ro) : make_uint4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int st = 0; st < 4; ++st) {
+      const int kpos = k0 + st * 4 + rowi;
+      const uint32_t w[4] = {kq[st].x, kq[st].y, kq[st].z, kq[st].w};
+      float d = 0.f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) d += qv[2 * j] * bf16_lo(w[j]) + qv[2 * j + 1] * bf16_hi(w[j]);
+      d += __shfl_xor_sync(0xffffffffu, d, 1);
+      d += __shfl_xor_sync(0xffffffffu, d, 2);
+      d += __shfl_xor_sync(0xffffffffu, d, 4);
+      if (kpos < kv_len) {               // uniform within the 8-lane group
+        const float sc = d * scale_log2;
+        const float mn = fmaxf(m, sc);
+        const float c = exp2f(m - mn);   // m = -inf on the first key: exp2(-inf) = 0
+        const float pw = exp2f(sc - mn);
+        l = l * c + pw;
+        const uint32_t u[4] = {vq[st].x, vq[st].y, vq[st].z, vq[st].w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          acc[2 * j] = acc[2 * j] * c + pw * bf16_lo(u[j]);
+          acc[2 * j + 1] = acc[2 * j + 1] * c + pw * bf16_hi(u[j]);
+        }
+        m = mn;
+      }
+    }
+  }
+
+  // merge the 16 partial states (4 row groups x 4 warps) that share each dim chunk
+  __shared__ float sm_m[16][8], sm_l[16][8], sm_acc[16][8][8];
+  const int slot = warp * 4 + rowi;
+  sm_m[slot][sub] = m;
+  sm_l[slot][sub] = l;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) sm_acc[slot][sub][j] = acc[j];
+  __syncthreads();
+  if (tid < 64) {
+    const int c = tid >> 3, j = tid & 7;   // output dim = c * 8 + j
+    float M = -INFINITY;
+#pragma unroll
+    for (int s2 = 0; s2 < 16; ++s2) M = fmaxf(M, sm_m[s2][c]);
+    float L = 0.f, A = 0.f;
+#pragma unroll
+    for (int s2 = 0; s2 < 16; ++s2) {
+      const float w = (sm_m[s2][c] == -INFINITY) ? 0.f : exp2f(sm_m[s2][c] - M);
+      L += sm_l[s2][c] * w;
+      A += sm_acc[s2][c][j] * w;
+    }
+    out[(static_cast<long long>(seq) * n_heads + head) * 64 + c * 8 + j] = __float2bfloat16_rn(A / L);
+  }
+}
+
+int decode_attention(const __nv_bfloat16* q, int n_heads, const int* pos, int n_seqs,
+                     const __nv_bfloat16* kv_pool, int n_pages, const int* block_tables,
+                     int max_blocks, int layer, __nv_bfloat16* out, cudaStream_t stream) {
+  if (n_seqs <= 0) return set_error("decode_attention: empty batch");
+  dim3 grid(n_heads, n_seqs);
+  decode_attention_kernel<<<grid, 128, 0, stream>>>(q, n_heads, pos, kv_pool, n_pages, block_tables,
+                                                    max_blocks, layer, out,
+                                                    0.125f * 1.4426950408889634f);
+  count_launch();
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error(cudaGetErrorString(e));
+  return 0;
+}
+
+}  // namespace md

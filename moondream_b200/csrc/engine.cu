@@ -1,0 +1,306 @@
+// Native runtime: composes the kernels into the reference's four seam operations, batched.
+//   md_vision_encode   <- MoondreamModel._vis_enc    (vision.py:64-74)
+//   md_vision_project  <- reconstruct_from_crops + _vis_proj (image_crops.py:170-231, vision.py:77-89)
+//   md_text_prefill    <- _prefill                   (text.py:128-160)
+//   md_text_decode_step + md_lm_head_argmax <- _decode_one_tok (moondream.py:183-192)
+// The model object stores pointers only (host memory); device memory belongs to the caller.
+#include "engine.h"
+
+#include <new>
+
+namespace md {
+
+static inline char* align_up(char* p, size_t a = 256) {
+  return reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(p) + a - 1) & ~(uintptr_t)(a - 1));
+}
+static inline long long pad256(long long b) { return (b + 255) & ~255LL; }
+
+int model_num_weights(const md_dims& d) { return 3 + 12 * d.vis_layers + 6 + 1 + 10 * d.txt_layers + 4 + 14; }
+
+int model_create(const md_dims& d, const void* const* w, int n, const void* lut, const float* rope,
+                 Model** out) {
+  if (n != model_num_weights(d)) return set_error("md_model_create: wrong number of weight tensors");
+  if (d.vis_dim != d.vis_heads * 72) return set_error("md_model_create: vision head_dim must be 72");
+  if (d.txt_dim != d.txt_heads * 64) return set_error("md_model_create: text head_dim must be 64");
+  if (d.patch_k % 8 || d.vis_ff % 8 || d.vis_dim % 8 || d.txt_dim % 8 || d.txt_ff % 8 || d.vocab % 8 ||
+      d.proj_inner % 8 || d.reg_inner % 8)
+    return set_error("md_model_create: every GEMM dimension must be a multiple of 8 (pad when preparing)");
+  if (d.grid * d.patch != d.crop || d.prefix_len != d.grid * d.grid + 1)
+    return set_error("md_model_create: inconsistent crop geometry");
+  for (int i = 0; i < n; ++i)
+    if (!w[i] || (reinterpret_cast<uintptr_t>(w[i]) & 15))
+      return set_error("md_model_create: weight pointers must be non-null and 16-byte aligned");
+  Model* m = new (std::nothrow) Model();
+  if (!m) return set_error("md_model_create: out of host memory");
+  m->d = d;
+  m->lut = reinterpret_cast<const bf16*>(lut);
+  m->rope = rope;
+  int k = 0;
+  auto next = [&]() { return reinterpret_cast<const bf16*>(w[k++]); };
+  auto lin = [&]() { Lin l; l.w = next(); l.b = next(); return l; };
+  m->pos_emb = next();
+  m->patch_emb = lin();
+  m->vis.resize(d.vis_layers);
+  for (auto& b : m->vis) { b.ln1 = lin(); b.qkv = lin(); b.proj = lin(); b.ln2 = lin(); b.fc1 = lin(); b.fc2 = lin(); }
+  m->vis_post_ln = lin();
+  m->proj_fc1 = lin();
+  m->proj_fc2 = lin();
+  m->wte = next();
+  m->txt.resize(d.txt_layers);
+  for (auto& b : m->txt) { b.ln = lin(); b.qkv = lin(); b.proj = lin(); b.fc1 = lin(); b.fc2 = lin(); }
+  m->txt_post_ln = lin();
+  m->lm_head = lin();
+  m->coord_features = next();
+  m->size_features = next();
+  m->coord_enc = lin();
+  m->coord_dec1 = lin();
+  m->coord_dec2 = lin();
+  m->size_enc = lin();
+  m->size_dec1 = lin();
+  m->size_dec2 = lin();
+  *out = m;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// vision encoder
+// ------------------------------------------------------------------------------------------------
+long long vision_encode_ws_bytes(const Model& m, int n_crops) {
+  const md_dims& d = m.d;
+  const long long T = static_cast<long long>(n_crops) * d.grid * d.grid;
+  // patches | x | ln | qkv | attn | hidden(ff)
+  return pad256(T * d.patch_k * 2) + 2 * pad256(T * d.vis_dim * 2) + pad256(T * 3 * d.vis_dim * 2) +
+         pad256(T * d.vis_dim * 2) + pad256(T * d.vis_ff * 2) + 4096;
+}
+
+int vision_encode(Model& m, const uint8_t* crops, int n_crops, bf16* feats, void* ws, cudaStream_t st) {
+  const md_dims& d = m.d;
+  if (n_crops <= 0) return set_error("md_vision_encode: empty batch");
+  const int tok = d.grid * d.grid;
+  const int T = n_crops * tok;
+  const int D = d.vis_dim;
+  char* p = align_up(reinterpret_cast<char*>(ws));
+  bf16* patches = reinterpret_cast<bf16*>(p); p += pad256(1LL * T * d.patch_k * 2);
+  bf16* x = reinterpret_cast<bf16*>(p); p += pad256(1LL * T * D * 2);
+  bf16* ln = reinterpret_cast<bf16*>(p); p += pad256(1LL * T * D * 2);
+  bf16* qkv = reinterpret_cast<bf16*>(p); p += pad256(1LL * T * 3 * D * 2);
+  bf16* att = reinterpret_cast<bf16*>(p); p += pad256(1LL * T * D * 2);
+  bf16* hid = reinterpret_cast<bf16*>(p);
+
+  if (patchify(crops, n_crops, d.crop, d.patch, d.patch_k, m.lut, patches, st)) return 1;
+  // x = bf16(bf16(patches W^T + b) + pos_emb[token])           vision.py:67-68
+  if (gemm_rowform(patches, d.patch_k, m.patch_emb.w, d.patch_k, T, D, d.patch_k, EPI_BIAS_RESIDUAL,
+                   m.patch_emb.b, m.pos_emb, D, tok, x, D, 0, 0, 0, st)) return 1;
+  for (int i = 0; i < d.vis_layers; ++i) {
+    const VisBlock& b = m.vis[i];
+    // x = x + attn(ln1(x))                                      vision.py:70, layers.py:155-166
+    if (layernorm(x, D, b.ln1.w, b.ln1.b, ln, D, T, D, 1e-5f, st)) return 1;
+    if (gemm_rowform(ln, D, b.qkv.w, D, T, 3 * D, D, EPI_BIAS, b.qkv.b, nullptr, 0, 0, qkv, 3 * D, 0, 0, 0, st)) return 1;
+    if (vit_attention(qkv, n_crops, tok, d.vis_heads, att, st)) return 1;
+    if (gemm_rowform(att, D, b.proj.w, D, T, D, D, EPI_BIAS_RESIDUAL, b.proj.b, x, D, 0, x, D, 0, 0, 0, st)) return 1;
+    // x = x + fc2(gelu(fc1(ln2(x))))                            vision.py:71, layers.py:129-146
+    if (layernorm(x, D, b.ln2.w, b.ln2.b, ln, D, T, D, 1e-5f, st)) return 1;
+    if (gemm_rowform(ln, D, b.fc1.w, D, T, d.vis_ff, D, EPI_BIAS_GELU, b.fc1.b, nullptr, 0, 0, hid, d.vis_ff, 0, 0, 0, st)) return 1;
+    if (gemm_rowform(hid, d.vis_ff, b.fc2.w, d.vis_ff, T, D, d.vis_ff, EPI_BIAS_RESIDUAL, b.fc2.b, x, D, 0, x, D, 0, 0, 0, st)) return 1;
+  }
+  return layernorm(x, D, m.vis_post_ln.w, m.vis_post_ln.b, feats, D, T, D, 1e-5f, st);
+}
+
+// ------------------------------------------------------------------------------------------------
+// stitch + pool + projection MLP
+// ------------------------------------------------------------------------------------------------
+long long vision_project_ws_bytes(const Model& m, int n_images) {
+  const md_dims& d = m.d;
+  const long long T = static_cast<long long>(n_images) * d.grid * d.grid;
+  return pad256(T * 2 * d.vis_dim * 2) + pad256(T * d.proj_inner * 2) + 4096;
+}
+
+int vision_project(Model& m, const bf16* feats, const int* crop_offsets, const int* tilings, int n_images,
+                   bf16* embeds, void* ws, cudaStream_t st) {
+  const md_dims& d = m.d;
+  if (n_images <= 0) return set_error("md_vision_project: empty batch");
+  const int tok = d.grid * d.grid;
+  const int T = n_images * tok;
+  char* p = align_up(reinterpret_cast<char*>(ws));
+  bf16* cat = reinterpret_cast<bf16*>(p); p += pad256(1LL * T * 2 * d.vis_dim * 2);
+  bf16* hid = reinterpret_cast<bf16*>(p);
+  if (stitch_pool_concat(feats, crop_offsets, tilings, n_images, d.grid, d.margin, d.vis_dim, cat, st)) return 1;
+  if (gemm_rowform(cat, 2 * d.vis_dim, m.proj_fc1.w, 2 * d.vis_dim, T, d.proj_inner, 2 * d.vis_dim,
+                   EPI_BIAS_GELU, m.proj_fc1.b, nullptr, 0, 0, hid, d.proj_inner, 0, 0, 0, st)) return 1;
+  // rows of image i land at i*prefix_len + 1 .. (row i*prefix_len is the BOS embedding)
+  return gemm_rowform(hid, d.proj_inner, m.proj_fc2.w, d.proj_inner, T, d.txt_dim, d.proj_inner, EPI_BIAS,
+                      m.proj_fc2.b, nullptr, 0, 0, embeds, d.txt_dim, tok, d.prefix_len, 1, st);
+}
+
+// ------------------------------------------------------------------------------------------------
+// text decoder: prefill
+// ------------------------------------------------------------------------------------------------
+long long text_prefill_ws_bytes(const Model& m, int T) {
+  const md_dims& d = m.d;
+  // ln | qkv | q | attn | tmp | hidden(ff)
+  return pad256(1LL * T * d.txt_dim * 2) * 4 + pad256(1LL * T * 3 * d.txt_dim * 2) +
+         pad256(1LL * T * d.txt_ff * 2) + 4096;
+}
+
+int text_prefill(Model& m, bf16* x, int T, const int* q_offsets, const int* start_pos, int n_seqs,
+                 int max_q, const md_kv& kv, void* ws, cudaStream_t st) {
+  const md_dims& d = m.d;
+  if (T <= 0 || n_seqs <= 0) return set_error("md_text_prefill: empty batch");
+  const int D = d.txt_dim, H = d.txt_heads;
+  char* p = align_up(reinterpret_cast<char*>(ws));
+  bf16* ln = reinterpret_cast<bf16*>(p); p += pad256(1LL * T * D * 2);
+  bf16* qkv = reinterpret_cast<bf16*>(p); p += pad256(1LL * T * 3 * D * 2);
+  bf16* q = reinterpret_cast<bf16*>(p); p += pad256(1LL * T * D * 2);
+  bf16* att = reinterpret_cast<bf16*>(p); p += pad256(1LL * T * D * 2);
+  bf16* tmp = reinterpret_cast<bf16*>(p); p += pad256(1LL * T * D * 2);
+  bf16* hid = reinterpret_cast<bf16*>(p);
+  bf16* pool = reinterpret_cast<bf16*>(kv.pool);
+  for (int i = 0; i < d.txt_layers; ++i) {
+    const TxtBlock& b = m.txt[i];
+    // l = ln(x); x = x + attn(l) + mlp(l)                       text.py:145-158
+    if (layernorm(x, D, b.ln.w, b.ln.b, ln, D, T, D, 1e-5f, st)) return 1;
+    if (gemm_rowform(ln, D, b.qkv.w, D, T, 3 * D, D, EPI_BIAS, b.qkv.b, nullptr, 0, 0, qkv, 3 * D, 0, 0, 0, st)) return 1;
+    if (rope_kv_write(qkv, T, H, q_offsets, start_pos, n_seqs, m.rope, q, pool, kv.n_pages, kv.block_tables,
+                      kv.max_blocks, i, st)) return 1;
+    if (prefill_attention(q, H, q_offsets, start_pos, n_seqs, max_q, d.prefix_len, pool, kv.n_pages,
+                          kv.block_tables, kv.max_blocks, i, att, st)) return 1;
+    // tmp = bf16(x + bf16(proj(att)))  -- the reference adds l_attn first, then l_mlp (text.py:158)
+    if (gemm_rowform(att, D, b.proj.w, D, T, D, D, EPI_BIAS_RESIDUAL, b.proj.b, x, D, 0, tmp, D, 0, 0, 0, st)) return 1;
+    if (gemm_rowform(ln, D, b.fc1.w, D, T, d.txt_ff, D, EPI_BIAS_GELU, b.fc1.b, nullptr, 0, 0, hid, d.txt_ff, 0, 0, 0, st)) return 1;
+    if (gemm_rowform(hid, d.txt_ff, b.fc2.w, d.txt_ff, T, D, d.txt_ff, EPI_BIAS_RESIDUAL, b.fc2.b, tmp, D, 0, x, D, 0, 0, 0, st)) return 1;
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// text decoder: one decode step for `batch` sequences
+// ------------------------------------------------------------------------------------------------
+static long long smallbatch_ws_floats(const Model& m, int batch) {
+  const md_dims& d = m.d;
+  long long need = 0;
+  auto upd = [&](int n_out, int K) {
+    const long long f = 1LL * gemm_swapped_splits(n_out, K) * batch * n_out;
+    if (f > need) need = f;
+  };
+  upd(3 * d.txt_dim, d.txt_dim); upd(d.txt_dim, d.txt_dim); upd(d.txt_ff, d.txt_dim); upd(d.txt_dim, d.txt_ff);
+  upd(d.vocab, d.txt_dim);
+  upd(d.reg_inner, d.txt_dim); upd(d.coord_out, d.reg_inner); upd(d.size_out, d.reg_inner);
+  upd(d.txt_dim, d.coord_feat); upd(d.txt_dim, d.size_feat);
+  return need;
+}
+
+long long text_decode_ws_bytes(const Model& m, int batch) {
+  const md_dims& d = m.d;
+  return pad256(1LL * batch * d.txt_dim * 2) * 4 + pad256(1LL * batch * 3 * d.txt_dim * 2) +
+         pad256(1LL * batch * d.txt_ff * 2) + pad256(smallbatch_ws_floats(m, batch) * 4) + 4096;
+}
+
+static int small_linear(const bf16* x, long long ldx, const Lin& l, int batch, int n_out, int K, int mode,
+                        const bf16* res, long long ldr, bf16* out, long long ldo, float* ws, cudaStream_t st) {
+  const int used = gemm_swapped(l.w, K, x, ldx, n_out, batch, K, gemm_swapped_splits(n_out, K), ws, st);
+  if (used < 0) return 1;
+  return splitk_epilogue(ws, used, batch, n_out, mode, l.b, res, ldr, out, ldo, st);
+}
+
+int text_decode_step(Model& m, bf16* x, const int* pos, int batch, const md_kv& kv, void* ws, cudaStream_t st) {
+  const md_dims& d = m.d;
+  if (batch <= 0) return set_error("md_text_decode_step: empty batch");
+  const int D = d.txt_dim, H = d.txt_heads;
+  char* p = align_up(reinterpret_cast<char*>(ws));
+  bf16* ln = reinterpret_cast<bf16*>(p); p += pad256(1LL * batch * D * 2);
+  bf16* qkv = reinterpret_cast<bf16*>(p); p += pad256(1LL * batch * 3 * D * 2);
+  bf16* q = reinterpret_cast<bf16*>(p); p += pad256(1LL * batch * D * 2);
+  bf16* att = reinterpret_cast<bf16*>(p); p += pad256(1LL * batch * D * 2);
+  bf16* tmp = reinterpret_cast<bf16*>(p); p += pad256(1LL * batch * D * 2);
+  bf16* hid = reinterpret_cast<bf16*>(p); p += pad256(1LL * batch * d.txt_ff * 2);
+  float* wsf = reinterpret_cast<float*>(p);
+  bf16* pool = reinterpret_cast<bf16*>(kv.pool);
+  for (int i = 0; i < d.txt_layers; ++i) {
+    const TxtBlock& b = m.txt[i];
+    if (layernorm(x, D, b.ln.w, b.ln.b, ln, D, batch, D, 1e-5f, st)) return 1;
+    if (small_linear(ln, D, b.qkv, batch, 3 * D, D, EPI_BIAS, nullptr, 0, qkv, 3 * D, wsf, st)) return 1;
+    if (rope_kv_write(qkv, batch, H, nullptr, pos, batch, m.rope, q, pool, kv.n_pages, kv.block_tables,
+                      kv.max_blocks, i, st)) return 1;
+    if (decode_attention(q, H, pos, batch, pool, kv.n_pages, kv.block_tables, kv.max_blocks, i, att, st)) return 1;
+    if (small_linear(att, D, b.proj, batch, D, D, EPI_BIAS_RESIDUAL, x, D, tmp, D, wsf, st)) return 1;
+    if (small_linear(ln, D, b.fc1, batch, d.txt_ff, D, EPI_BIAS_GELU, nullptr, 0, hid, d.txt_ff, wsf, st)) return 1;
+    if (small_linear(hid, d.txt_ff, b.fc2, batch, D, d.txt_ff, EPI_BIAS_RESIDUAL, tmp, D, x, D, wsf, st)) return 1;
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// LM head + argmax
+// ------------------------------------------------------------------------------------------------
+long long lm_head_ws_bytes(const Model& m, int batch) {
+  return pad256(1LL * batch * m.d.txt_dim * 2) + pad256(smallbatch_ws_floats(m, batch) * 4) + 4096;
+}
+
+int lm_head_argmax(Model& m, const bf16* hidden, long long ldh, int batch, int mask_id, int* out_ids,
+                   long long out_stride, const int* out_index, float* out_margin, bf16* out_logits,
+                   void* ws, cudaStream_t st) {
+  const md_dims& d = m.d;
+  if (batch <= 0) return set_error("md_lm_head_argmax: empty batch");
+  char* p = align_up(reinterpret_cast<char*>(ws));
+  bf16* ln = reinterpret_cast<bf16*>(p); p += pad256(1LL * batch * d.txt_dim * 2);
+  float* wsf = reinterpret_cast<float*>(p);
+  if (layernorm(hidden, ldh, m.txt_post_ln.w, m.txt_post_ln.b, ln, d.txt_dim, batch, d.txt_dim, 1e-5f, st)) return 1;
+  const int used = gemm_swapped(m.lm_head.w, d.txt_dim, ln, d.txt_dim, d.vocab, batch, d.txt_dim,
+                                gemm_swapped_splits(d.vocab, d.txt_dim), wsf, st);
+  if (used < 0) return 1;
+  return argmax_logits(wsf, used, batch, d.vocab, m.lm_head.b, 1, mask_id, out_ids, out_stride, out_index,
+                       out_margin, out_logits, st);
+}
+
+// ------------------------------------------------------------------------------------------------
+// region head
+// ------------------------------------------------------------------------------------------------
+long long region_ws_bytes(const Model& m, int batch) {
+  const md_dims& d = m.d;
+  const int feat = d.size_feat > d.coord_feat ? d.size_feat : d.coord_feat;
+  return pad256(1LL * batch * d.reg_inner * 2) + pad256(1LL * batch * feat * 2) +
+         pad256(smallbatch_ws_floats(m, batch) * 4) + 4096;
+}
+
+int region_decode(Model& m, int which, const bf16* hidden, long long ldh, int batch, int* out_bins,
+                  void* ws, cudaStream_t st) {
+  const md_dims& d = m.d;
+  if (batch <= 0) return set_error("md_region_decode: empty batch");
+  char* p = align_up(reinterpret_cast<char*>(ws));
+  bf16* hid = reinterpret_cast<bf16*>(p); p += pad256(1LL * batch * d.reg_inner * 2);
+  const int feat = d.size_feat > d.coord_feat ? d.size_feat : d.coord_feat;
+  p += pad256(1LL * batch * feat * 2);
+  float* wsf = reinterpret_cast<float*>(p);
+  const Lin& l1 = which == 0 ? m.coord_dec1 : m.size_dec1;
+  const Lin& l2 = which == 0 ? m.coord_dec2 : m.size_dec2;
+  const int n_out = which == 0 ? d.coord_out : d.size_out;
+  // mlp(hidden): fc1 + gelu, fc2 (region.py:46-57, 74-93)
+  if (small_linear(hidden, ldh, l1, batch, d.reg_inner, d.txt_dim, EPI_BIAS_GELU, nullptr, 0, hid,
+                   d.reg_inner, wsf, st)) return 1;
+  const int used = gemm_swapped(l2.w, d.reg_inner, hid, d.reg_inner, n_out, batch, d.reg_inner,
+                                gemm_swapped_splits(n_out, d.reg_inner), wsf, st);
+  if (used < 0) return 1;
+  if (which == 0)
+    return argmax_logits(wsf, used, batch, n_out, l2.b, 1, -1, out_bins, 1, nullptr, nullptr, nullptr, st);
+  // size logits are viewed as (2, -1): rows 2b (width bins) and 2b+1 (height bins)
+  return argmax_logits(wsf, used, 2 * batch, n_out / 2, l2.b, 2, -1, out_bins, 1, nullptr, nullptr, nullptr, st);
+}
+
+int region_encode(Model& m, int which, const float* values, int batch, bf16* out, long long ldo, void* ws,
+                  cudaStream_t st) {
+  const md_dims& d = m.d;
+  if (batch <= 0) return set_error("md_region_encode: empty batch");
+  char* p = align_up(reinterpret_cast<char*>(ws));
+  p += pad256(1LL * batch * d.reg_inner * 2);
+  bf16* ff = reinterpret_cast<bf16*>(p);
+  const int feat_max = d.size_feat > d.coord_feat ? d.size_feat : d.coord_feat;
+  p += pad256(1LL * batch * feat_max * 2);
+  float* wsf = reinterpret_cast<float*>(p);
+  const int feat = which == 0 ? d.coord_feat : d.size_feat;
+  const bf16* fw = which == 0 ? m.coord_features : m.size_features;
+  const Lin& enc = which == 0 ? m.coord_enc : m.size_enc;
+  if (fourier_features(values, batch, which == 0 ? 1 : 2, fw, feat / 2, ff, feat, st)) return 1;
+  return small_linear(ff, feat, enc, batch, d.txt_dim, feat, EPI_BIAS, nullptr, 0, out, ldo, wsf, st);
+}
+
+}  // namespace md

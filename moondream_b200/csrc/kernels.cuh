@@ -40,29 +40,37 @@ int splitk_epilogue(const float* ws, int splits, int B, int N, int mode, const _
 // ---- elementwise.cu ----
 int layernorm(const __nv_bfloat16* x, long long ldx, const __nv_bfloat16* w, const __nv_bfloat16* b,
               __nv_bfloat16* y, long long ldy, int rows, int dim, float eps, cudaStream_t stream);
-int patchify(const uint8_t* crops, int n_crops, int crop, int patch, int k_pad, __nv_bfloat16* out,
-             cudaStream_t stream);
+int patchify(const uint8_t* crops, int n_crops, int crop, int patch, int k_pad,
+             const __nv_bfloat16* lut, __nv_bfloat16* out, cudaStream_t stream);
 int stitch_pool_concat(const __nv_bfloat16* feats, const int* crop_offsets, const int* tilings,
                        int n_images, int grid, int margin, int dim, __nv_bfloat16* out,
                        cudaStream_t stream);
-int embed_tokens(const int* ids, int n, const __nv_bfloat16* wte, int dim, __nv_bfloat16* out,
-                 long long ldo, cudaStream_t stream);
-int rope_kv_write(const __nv_bfloat16* qkv, int n_tokens, int n_heads, const int* tok_seq,
-                  const int* tok_pos, const float* freqs, __nv_bfloat16* q_out,
-                  __nv_bfloat16* kv_pool, const int* block_tables, int max_blocks, int layer,
-                  int n_layers, cudaStream_t stream);
-int argmax_logits(const float* logits, int B, int V, const __nv_bfloat16* bias, const int* mask_ids,
-                  int n_mask, int* out_ids, cudaStream_t stream);
+int embed_tokens(const int* ids, long long id_stride, int n, const __nv_bfloat16* wte, int dim,
+                 int vocab, __nv_bfloat16* out, long long ldo, cudaStream_t stream);
+int rope_kv_write(const __nv_bfloat16* qkv, int n_tokens, int n_heads, const int* q_offsets,
+                  const int* start_pos, int n_seqs, const float* freqs, __nv_bfloat16* q_out,
+                  __nv_bfloat16* kv_pool, int n_pages, const int* block_tables, int max_blocks,
+                  int layer, cudaStream_t stream);
+int argmax_logits(const float* ws, int splits, int B, int V, const __nv_bfloat16* bias, int bias_period,
+                  int mask_id, int* out_ids, long long out_stride, const int* out_index,
+                  float* out_margin, __nv_bfloat16* out_logits, cudaStream_t stream);
+int decode_advance(int* cur_tok, int* pos, int* step, const int* preds, const int* forced,
+                   long long stride, int batch, int eos_id, int* finished, cudaStream_t stream);
+int gather_rows(const __nv_bfloat16* src, long long ld_src, const int* idx, int n, int dim,
+                __nv_bfloat16* out, long long ldo, cudaStream_t stream);
+int bins_to_values(int which, const int* bins, int n, float* out, cudaStream_t stream);
+int fourier_features(const float* x, int B, int n_in, const __nv_bfloat16* w, int half,
+                     __nv_bfloat16* out, long long ldo, cudaStream_t stream);
 
 // ---- attention.cu ----
 int vit_attention(const __nv_bfloat16* qkv, int n_crops, int seq, int n_heads, __nv_bfloat16* out,
                   cudaStream_t stream);
 int prefill_attention(const __nv_bfloat16* q, int n_heads, const int* q_offsets, const int* start_pos,
-                      int n_seqs, int max_q, int prefix_len, const __nv_bfloat16* kv_pool,
-                      const int* block_tables, int max_blocks, int layer, int n_layers,
-                      __nv_bfloat16* out, cudaStream_t stream);
+                      int n_seqs, int max_q, int prefix_len, const __nv_bfloat16* kv_pool, int n_pages,
+                      const int* block_tables, int max_blocks, int layer, __nv_bfloat16* out,
+                      cudaStream_t stream);
 int decode_attention(const __nv_bfloat16* q, int n_heads, const int* pos, int n_seqs,
-                     const __nv_bfloat16* kv_pool, const int* block_tables, int max_blocks, int layer,
-                     int n_layers, __nv_bfloat16* out, cudaStream_t stream);
+                     const __nv_bfloat16* kv_pool, int n_pages, const int* block_tables,
+                     int max_blocks, int layer, __nv_bfloat16* out, cudaStream_t stream);
 
 }  // namespace md

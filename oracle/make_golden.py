@@ -1,0 +1,105 @@
+"""TEST INFRASTRUCTURE (build container only): generate tests/golden/* from the UNMODIFIED reference.
+
+    python -m oracle.make_golden
+
+Runs /root/reference (stub tokenizer, seeded synthetic weights, moondream_b200.synth) on the tiny
+configuration and records what its public API returns: generated token ids (through
+MoondreamModel._generate_answer, the call caption()/query() make, moondream.py:645), detect boxes and
+points.  The oracle restatement is asserted bit-identical on the way (tokens, KV prefix, boxes) and
+contributes what the reference API does not expose (top-1/top-2 margins, region bins).
+Also pins the synthetic-weight recipe and the host crop geometry (hashes).
+"""
+from __future__ import annotations
+
+import hashlib
+import json
+import os
+
+import numpy as np
+import torch
+from PIL import Image
+
+from moondream_b200 import config as C, synth
+from oracle import reference_shim as R
+from oracle.moondream_oracle import OracleModel, overlap_crops
+
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+CASES = [  # name, image index, H, W, prompt length, new tokens
+    ("single_crop", 0, 378, 378, 5, 20),
+    ("multi_crop_2x3", 1, 500, 700, 9, 20),
+    ("multi_crop_4x2", 2, 800, 600, 32, 16),
+    ("small_image", 3, 300, 200, 3, 12),
+]
+
+
+def main():
+    assert R.reference_available(), "run in the build container (/root/reference)"
+    os.makedirs(OUT, exist_ok=True)
+    torch.manual_seed(0)
+    cfg = C.tiny()
+    sd = synth.synthetic_state_dict(cfg, 0)
+    ref = R.load_reference_model(cfg, sd)
+    orc = OracleModel(cfg, sd)
+    cases = []
+    for name, idx, h, w, plen, ntok in CASES:
+        img = synth.synthetic_image(idx, h, w)
+        prompt = synth.synthetic_prompt(idx, plen, cfg.text.vocab_size)
+        with torch.inference_mode():
+            enc = ref.encode_image(Image.fromarray(img))
+        ref.load_encoded_image(enc)
+        text = "".join(ref._generate_answer(torch.tensor([prompt]), enc.pos,
+                                            {"temperature": 0, "max_tokens": ntok}))
+        tokens = R.tokens_from_text(text)
+        o_enc = orc.encode_image(img)
+        assert all(torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) for a, b in zip(enc.caches, o_enc.caches))
+        gen = orc.generate(o_enc, prompt, ntok)
+        assert gen.tokens == tokens, (name, gen.tokens, tokens)
+        tk = cfg.tokenizer
+        det = ref.detect(enc, "17 23", settings={"max_objects": 3})["objects"]
+        dprompt = tk.templates["detect"]["prefix"] + [17, 23] + tk.templates["detect"]["suffix"]
+        o_det = orc.generate_points(o_enc, dprompt, True, 3)
+        assert [{k: o[k] for k in d} for o, d in zip(o_det, det)] == det
+        pts = ref.point(enc, "17 23", settings={"max_objects": 3})["points"]
+        pprompt = tk.templates["point"]["prefix"] + [17, 23] + tk.templates["point"]["suffix"]
+        o_pts = orc.generate_points(o_enc, pprompt, False, 3)
+        assert [{"x": o["x"], "y": o["y"]} for o in o_pts] == pts
+        kv_probe = [float(enc.caches[i][0].float().abs().mean()) for i in (0, cfg.text.n_layers - 1)]
+        cases.append({"name": name, "image_index": idx, "height": h, "width": w, "prompt": prompt,
+                      "tokens": tokens, "margins": gen.margins, "detect_prompt": dprompt,
+                      "detect_boxes": det, "detect_bins": [o["bins"] for o in o_det],
+                      "point_prompt": pprompt, "points": pts, "point_bins": [o["bins"] for o in o_pts],
+                      "kv_abs_mean_first_last": kv_probe})
+        print(name, tokens[:8], det[:1])
+    json.dump({"generator": "oracle/make_golden.py (unmodified reference, tiny preset, seed 0)",
+               "torch": torch.__version__, "cases": cases},
+              open(os.path.join(OUT, "tiny_reference.json"), "w"), indent=1)
+
+    hashes = {}
+    for preset in ("tiny", "moondream-0.5b"):
+        c = C.preset(preset)
+        s = sd if preset == "tiny" else synth.synthetic_state_dict(c, 0)
+        hashes[preset] = synth.state_dict_fingerprint(s, synth.FINGERPRINT_KEYS)
+        del s
+    json.dump(hashes, open(os.path.join(OUT, "synth_hashes.json"), "w"), indent=1)
+
+    import sys
+    sys.path.insert(0, R.REFERENCE_ROOT)
+    from moondream.torch.image_crops import overlap_crop_image as ref_crop  # the reference itself
+    crops = []
+    for (h, w) in [(378, 378), (300, 200), (500, 700), (800, 600), (768, 1024), (1024, 768), (1080, 1920),
+                   (756, 756), (50, 1000), (2000, 3000)]:
+        img = synth.synthetic_image(h + w, h, w)
+        out = ref_crop(img, overlap_margin=4, max_crops=12)
+        mine, tiling = overlap_crops(img, 4, 12)
+        assert tuple(out["tiling"]) == tiling and np.array_equal(out["crops"], mine)
+        crops.append({"height": h, "width": w, "image_index": h + w, "tiling": list(out["tiling"]),
+                      "n_crops": int(out["crops"].shape[0]),
+                      "sha256": hashlib.sha256(out["crops"].tobytes()).hexdigest()[:16]})
+    json.dump({"generator": "reference overlap_crop_image (PIL Lanczos branch)", "cases": crops},
+              open(os.path.join(OUT, "crops.json"), "w"), indent=1)
+    print("wrote", os.listdir(OUT))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,172 @@
+"""Model-level parity on the GPU: the CUDA engine against the oracle (CPU restatement of the
+reference, bit-identical to it) on the same seeded weights and inputs, plus the committed golden
+fixtures generated from the unmodified reference.
+
+Tolerances (written here on purpose):
+  * integer outputs (token ids, region bins, tilings): exact, except that a greedy token may differ
+    where the ORACLE's own top-1/top-2 logit margin is below MARGIN_EPS (a bf16 near-tie; the
+    reference's own argmax moves there between 1 and 8 CPU threads);
+  * hidden states / KV contents: norm-wise relative error <= REL_TOL against the bf16 oracle, and no
+    further from the fp32 truth than 1.5x the bf16 oracle's own distance + 2e-3 (bf16's unit roundoff
+    is 3.9e-3, so BASELINE.json's 1e-3 cannot hold element-wise).
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+REL_TOL = 3e-2
+MARGIN_EPS = 0.13       # ~2 bf16 ulps at the typical top-logit magnitude of the synthetic models
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def rel(a, b):
+    a, b = a.float().cpu(), b.float().cpu()
+    return ((a - b).norm() / (b.norm() + 1e-12)).item()
+
+
+@pytest.fixture(scope="module")
+def tiny():
+    from moondream_b200 import config as C, synth
+    from moondream_b200.engine import Engine
+    from oracle.moondream_oracle import OracleModel
+
+    cfg = C.tiny()
+    sd = synth.synthetic_state_dict(cfg, 0)
+    return cfg, sd, Engine(cfg, sd, max_batch=8), OracleModel(cfg, sd), OracleModel(cfg, sd, dtype=torch.float32)
+
+
+IMAGES = [(378, 378), (500, 700), (800, 600)]
+
+
+@pytest.mark.parametrize("hw", IMAGES)
+def test_encode_image_stages(tiny, hw):
+    from moondream_b200 import synth
+
+    cfg, sd, eng, orc, truth = tiny
+    img = synth.synthetic_image(3, *hw)
+    prefixes, feats, img_emb, hidden = eng.encode_images([img], return_hidden=True)
+    torch.cuda.synchronize()
+    crops, tiling = orc.prepare_crops(img)
+    o_feats = orc.vision_encoder(crops)
+    t_feats = truth.vision_encoder(truth.prepare_crops(img)[0])
+    e_oracle = rel(o_feats, t_feats)
+    got = feats.view(o_feats.shape)
+    assert rel(got, o_feats) < REL_TOL, rel(got, o_feats)
+    assert rel(got, t_feats) < 1.5 * e_oracle + 2e-3, (rel(got, t_feats), e_oracle)
+    o_enc, o_emb, o_hid = orc.encode_image(img, return_embeds=True)
+    assert rel(img_emb[0], o_emb) < REL_TOL, rel(img_emb[0], o_emb)
+    assert rel(hidden.view(1, 730, -1), o_hid) < REL_TOL, rel(hidden.view(1, 730, -1), o_hid)
+    kv = eng.prefix_kv_tensors(prefixes[0])
+    assert prefixes[0].pos == o_enc.pos == 730
+    for (k, v), (ok, ov) in zip(kv, o_enc.caches):
+        assert k.shape == ok.shape
+        assert rel(k, ok) < REL_TOL and rel(v, ov) < REL_TOL, (rel(k, ok), rel(v, ov))
+
+
+def _check_tokens(got, oracle_gen, what):
+    """exact match, or first divergence at a step where the oracle itself is at a near-tie."""
+    n = len(oracle_gen.tokens)
+    for i in range(n):
+        if got[i] != oracle_gen.tokens[i]:
+            assert oracle_gen.margins[i] < MARGIN_EPS, \
+                f"{what}: token {i} differs ({got[i]} vs {oracle_gen.tokens[i]}) at oracle margin {oracle_gen.margins[i]}"
+            return i
+    return n
+
+
+def test_greedy_generation_batch(tiny):
+    """free-running greedy caption for a ragged batch vs the oracle run image by image."""
+    from moondream_b200 import synth
+
+    cfg, sd, eng, orc, _ = tiny
+    imgs = [synth.synthetic_image(i, *IMAGES[i % 3]) for i in range(5)]
+    prompts = [synth.synthetic_prompt(i, 4 + 3 * i, cfg.text.vocab_size) for i in range(5)]
+    prefixes = eng.encode_images(imgs)
+    res = eng.generate(prefixes, prompts, max_tokens=24)
+    exact = 0
+    for i in range(5):
+        o = orc.generate(orc.encode_image(imgs[i]), prompts[i], 24)
+        n = _check_tokens(res.tokens[i].tolist(), o, f"image {i}")
+        exact += int(n == len(o.tokens))
+    assert exact >= 3, f"only {exact}/5 sequences matched the oracle exactly"
+
+
+def test_teacher_forced_generation(tiny):
+    """feed a seeded random token history; every argmax must equal the oracle's wherever the oracle's
+    margin is above the near-tie threshold.  Exercises varied KV content at every step."""
+    from moondream_b200 import synth
+
+    cfg, sd, eng, orc, _ = tiny
+    imgs = [synth.synthetic_image(10 + i, *IMAGES[i % 3]) for i in range(3)]
+    prompts = [synth.synthetic_prompt(20 + i, 6, cfg.text.vocab_size) for i in range(3)]
+    forced = [synth.synthetic_prompt(40 + i, 33, cfg.text.vocab_size) for i in range(3)]
+    prefixes = eng.encode_images(imgs)
+    res = eng.generate(prefixes, prompts, max_tokens=32, forced=forced)
+    checked = agree = 0
+    for i in range(3):
+        o = orc.generate(orc.encode_image(imgs[i]), prompts[i], 32, forced=forced[i])
+        for s in range(32):
+            if o.margins[s] >= MARGIN_EPS:
+                checked += 1
+                agree += int(res.tokens[i, s].item() == o.predicted[s])
+        # margins themselves agree to bf16 resolution
+        ours = res.margins[i, :32]
+        assert (ours - torch.tensor(o.margins)).abs().max().item() < 0.3
+    assert checked > 60 and agree == checked, (agree, checked)
+
+
+def test_graph_and_eager_decode_agree(tiny):
+    from moondream_b200 import synth
+
+    cfg, sd, eng, orc, _ = tiny
+    imgs = [synth.synthetic_image(7, 378, 378)]
+    prompt = [synth.synthetic_prompt(7, 5, cfg.text.vocab_size)]
+    a = eng.generate(eng.encode_images(imgs), prompt, 12, use_graph=True).tokens
+    b = eng.generate(eng.encode_images(imgs), prompt, 12, use_graph=False).tokens
+    assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("include_size", [True, False])
+def test_detect_point(tiny, include_size):
+    from moondream_b200 import synth
+
+    cfg, sd, eng, orc, _ = tiny
+    kind = "detect" if include_size else "point"
+    tpl = cfg.tokenizer.templates[kind]
+    imgs = [synth.synthetic_image(30 + i, *IMAGES[i % 3]) for i in range(3)]
+    prompts = [tpl["prefix"] + [17 + i, 23] + tpl["suffix"] for i in range(3)]
+    prefixes = eng.encode_images(imgs)
+    got = eng.generate_points(prefixes, prompts, include_size, max_objects=3)
+    for i in range(3):
+        want = orc.generate_points(orc.encode_image(imgs[i]), prompts[i], include_size, 3)
+        assert len(got[i]) == len(want)
+        for g, w in zip(got[i], want):
+            assert g["bins"] == w["bins"], (i, g, w)
+            for k in w:
+                if k != "bins":
+                    assert abs(g[k] - w[k]) < 1e-5
+
+
+def test_golden_reference_fixture(tiny):
+    """tokens / bins produced by the UNMODIFIED reference (oracle/make_golden.py) reproduce here."""
+    from moondream_b200 import synth
+
+    cfg, sd, eng, _, _ = tiny
+    path = os.path.join(GOLDEN, "tiny_reference.json")
+    gold = json.load(open(path))
+    for case in gold["cases"]:
+        img = synth.synthetic_image(case["image_index"], case["height"], case["width"])
+        prefixes = eng.encode_images([img])
+        res = eng.generate(prefixes, [case["prompt"]], len(case["tokens"]))
+        got = res.tokens[0].tolist()
+        for s, (tok, margin) in enumerate(zip(case["tokens"], case["margins"])):
+            if got[s] != tok:
+                assert margin < MARGIN_EPS, (case["name"], s, got[s], tok, margin)
+                break
+        pts = eng.generate_points(eng.encode_images([img]), [case["detect_prompt"]], True, 3)[0]
+        assert [p["bins"] for p in pts] == case["detect_bins"], case["name"]
