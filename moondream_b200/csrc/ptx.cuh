@@ -35,10 +35,12 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-// Bounded spin: a protocol bug must become a trap (reported launch failure), never a hung GPU.
+// Bounded wait: a protocol bug must become a trap (reported launch failure), never a hung GPU.
+// try_wait may itself suspend for a system-dependent time, so the bound is on elapsed clocks.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
   uint32_t done = 0;
+  long long t0 = 0;
   for (uint32_t spins = 0; !done; ++spins) {
     asm volatile(
         "{\n\t"
@@ -49,7 +51,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "=r"(done)
         : "r"(addr), "r"(parity)
         : "memory");
-    if (spins > (1u << 26)) __trap();
+    if (!done && (spins & 0xFF) == 0xFF) {
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 4000000000LL) __trap();      // ~2 s at 2 GHz
+    }
   }
 }
 
