@@ -38,6 +38,11 @@ int md_abi_version(void);
 /* number of kernels this library has launched since the last reset (bench.py's gpu_launches) */
 long long md_launch_count(void);
 void md_reset_launch_count(void);
+/* Optional CUDA-event timing around every md_linear_bf16-class launch made outside graph capture
+ * (bench.py's roofline leg): enable, run, then read the summed device time, algorithmic FLOPs
+ * (2*M*N*K) and launch count.  md_profile_linear_read synchronises on the recorded events. */
+void md_profile_linear(int enable);
+int md_profile_linear_read(double* total_ms, double* total_flops, long long* launches);
 
 /* ------------------------------------------------------------------------------------------------
  * Operator level

@@ -36,6 +36,9 @@ _SIGNATURES = {
     "md_abi_version": (c_int, []),
     "md_launch_count": (c_longlong, []),
     "md_reset_launch_count": (None, []),
+    "md_profile_linear": (None, [c_int]),
+    "md_profile_linear_read": (c_int, [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double),
+                                       ctypes.POINTER(c_longlong)]),
     "md_linear_bf16": (c_int, [_P, _LL, _P, _LL, c_int, c_int, c_int, c_int, _P, _P, _LL, c_int, _P, _LL,
                                c_int, c_int, c_int, _P]),
     "md_linear_small_batch_splits": (c_int, [c_int, c_int]),

@@ -34,6 +34,11 @@ const char* md_last_error(void) { return md::last_error(); }
 long long md_launch_count(void) { return md::launch_count(); }
 void md_reset_launch_count(void) { md::reset_launch_count(); }
 int md_abi_version(void) { return MD_ABI_VERSION; }
+void md_profile_linear(int enable) { md::gemm_profile_enable(enable); }
+int md_profile_linear_read(double* total_ms, double* total_flops, long long* launches) {
+  NEED(total_ms && total_flops && launches, "md_profile_linear_read");
+  return md::gemm_profile_read(total_ms, total_flops, launches);
+}
 
 // ---------------------------------------------------------------- operator level
 int md_linear_bf16(const void* x, long long ldx, const void* w, long long ldw, int M, int N, int K,

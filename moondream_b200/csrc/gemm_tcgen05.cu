@@ -16,6 +16,8 @@
 //   * row form   (activations are the M side): bf16 out[M,N] with fused epilogue.
 //   * swapped form (weights are the M side, the small decode batch is the N side, optional split-K):
 //     fp32 partial sums ws[split][n(batch)][m(feature)], finished by splitk_epilogue_kernel.
+#include <vector>
+
 #include "kernels.cuh"
 #include "ptx.cuh"
 
@@ -316,6 +318,42 @@ int make_tmap_bf16_2d(CUtensorMap* tm, const void* base, long long rows, long lo
   return 0;
 }
 
+// ---- optional per-launch timing of the row-form GEMM (bench.py's roofline leg) ----
+struct GemmProfile {
+  bool on = false;
+  std::vector<cudaEvent_t> pool;
+  size_t used = 0;
+  double flops = 0.0;
+  long long launches = 0;
+};
+static GemmProfile g_prof;
+
+void gemm_profile_enable(int on) {
+  g_prof.on = on != 0;
+  if (on) { g_prof.used = 0; g_prof.flops = 0.0; g_prof.launches = 0; }
+}
+// Sums the recorded start/stop pairs (synchronises on the last event). Returns 0 on success.
+int gemm_profile_read(double* total_ms, double* total_flops, long long* launches) {
+  double ms = 0.0;
+  for (size_t i = 0; i + 1 < g_prof.used; i += 2) {
+    if (cudaEventSynchronize(g_prof.pool[i + 1]) != cudaSuccess) return set_error("profile: event sync failed");
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, g_prof.pool[i], g_prof.pool[i + 1]) != cudaSuccess)
+      return set_error("profile: elapsed time failed");
+    ms += t;
+  }
+  *total_ms = ms; *total_flops = g_prof.flops; *launches = g_prof.launches;
+  return 0;
+}
+static cudaEvent_t profile_event() {
+  if (g_prof.used == g_prof.pool.size()) {
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    g_prof.pool.push_back(e);
+  }
+  return g_prof.pool[g_prof.used++];
+}
+
 static int g_num_sms = 0;
 int num_sms() {
   if (!g_num_sms) {
@@ -388,7 +426,17 @@ int gemm_rowform(const __nv_bfloat16* A, long long lda, const __nv_bfloat16* W, 
   p.out = out; p.ldo = ldo; p.bias = bias; p.res = res; p.ldr = ldr; p.res_mod = res_mod;
   p.remap_gin = remap_gin; p.remap_gout = remap_gout; p.remap_goff = remap_goff;
   p.ws = nullptr;
-  return dispatch_gemm(bn, tA, tB, p, stream);
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  const bool prof = g_prof.on && cudaStreamIsCapturing(stream, &cap) == cudaSuccess &&
+                    cap == cudaStreamCaptureStatusNone;
+  if (prof) cudaEventRecord(profile_event(), stream);
+  const int rc = dispatch_gemm(bn, tA, tB, p, stream);
+  if (prof) {
+    cudaEventRecord(profile_event(), stream);
+    g_prof.flops += 2.0 * M * static_cast<double>(N) * K;
+    g_prof.launches += 1;
+  }
+  return rc;
 }
 
 int gemm_swapped_splits(int n_out, int K) {

@@ -357,7 +357,7 @@ class Engine:
     def generate(self, prefixes: Sequence[PrefixKV], prompts: Sequence[Sequence[int]], max_tokens: int,
                  forced: Optional[Sequence[Sequence[int]]] = None, consume: bool = False,
                  use_graph: bool = True, stop_on_eos: bool = True,
-                 prompt_embeds: Optional[torch.Tensor] = None) -> GenerationResult:
+                 prompt_embeds: Optional[torch.Tensor] = None, to_host: bool = True) -> GenerationResult:
         """Greedy `_generate_answer` (moondream.py:434-539) for a batch: ragged prompt prefill, first
         token from the LM head, then `max_tokens` decode steps (the reference also runs the step after
         the last emitted token).  Returns the argmax at every step; callers cut at eos."""
@@ -398,7 +398,6 @@ class Engine:
             else:
                 st["cur"].copy_(st["preds"][:, 0])
             st["pos"].copy_(self._i32([prefixes[i].pos + lens[i] for i in range(B)]))
-            self.last_prompt_hidden = st["x"].clone()
             # ---- decode loop (moondream.py:481-530), one graph replay per token ----
             gkey = (use_forced, tk.answer_id)
             graph = st["graphs"].get(gkey) if use_graph else None
@@ -424,9 +423,11 @@ class Engine:
                 steps += 1
                 if stop_on_eos and not use_forced and (s % 16 == 15) and bool(st["finished"].all().item()):
                     break
-            tokens = st["preds"].to("cpu")
-            margins = st["margins"].to("cpu")
-            self.last_hidden = st["x"].clone()
+            if to_host:
+                tokens = st["preds"].to("cpu")          # the one device->host read of the call
+                margins = st["margins"].to("cpu")
+            else:
+                tokens, margins = st["preds"].clone(), st["margins"].clone()
         finally:
             for pages in owned:
                 self.pages.release(pages)

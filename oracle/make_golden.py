@@ -59,16 +59,16 @@ def main():
         det = ref.detect(enc, "17 23", settings={"max_objects": 3})["objects"]
         dprompt = tk.templates["detect"]["prefix"] + [17, 23] + tk.templates["detect"]["suffix"]
         o_det = orc.generate_points(o_enc, dprompt, True, 3)
-        assert [{k: o[k] for k in d} for o, d in zip(o_det, det)] == det
+        assert [{k: o[k] for k in d} for o, d in zip(o_det, det)] == det and len(o_det) == len(det)
         pts = ref.point(enc, "17 23", settings={"max_objects": 3})["points"]
         pprompt = tk.templates["point"]["prefix"] + [17, 23] + tk.templates["point"]["suffix"]
         o_pts = orc.generate_points(o_enc, pprompt, False, 3)
         assert [{"x": o["x"], "y": o["y"]} for o in o_pts] == pts
         kv_probe = [float(enc.caches[i][0].float().abs().mean()) for i in (0, cfg.text.n_layers - 1)]
         cases.append({"name": name, "image_index": idx, "height": h, "width": w, "prompt": prompt,
-                      "tokens": tokens, "margins": gen.margins, "detect_prompt": dprompt,
-                      "detect_boxes": det, "detect_bins": [o["bins"] for o in o_det],
-                      "point_prompt": pprompt, "points": pts, "point_bins": [o["bins"] for o in o_pts],
+                      "tokens": tokens, "margins": gen.margins, "margin_ulps": gen.margin_ulps, "detect_prompt": dprompt,
+                      "detect_boxes": det, "detect_bins": [o["bins"] for o in o_det], "detect_ulps": [o["ulps"] for o in o_det],
+                      "point_prompt": pprompt, "points": pts, "point_bins": [o["bins"] for o in o_pts], "point_ulps": [o["ulps"] for o in o_pts],
                       "kv_abs_mean_first_last": kv_probe})
         print(name, tokens[:8], det[:1])
     json.dump({"generator": "oracle/make_golden.py (unmodified reference, tiny preset, seed 0)",

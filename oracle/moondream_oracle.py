@@ -144,6 +144,7 @@ class Generation:
     margins: List[float]         # top1 - top2 logit margin at each emission (after masking)
     predicted: List[int]         # argmax at each step (== tokens unless teacher-forced)
     last_hidden: Optional[Tensor] = None
+    margin_ulps: Optional[List[float]] = None   # the margins in bf16 ulps of the top logit
 
 
 class OracleModel:
@@ -319,6 +320,14 @@ class OracleModel:
         top = torch.topk(logits.float().flatten(), 2).values
         return float(top[0] - top[1])
 
+    @staticmethod
+    def _margin_ulps(logits: Tensor) -> float:
+        """top1 - top2 in units of the bf16 spacing at |top1| (8 significand bits)."""
+        top = torch.topk(logits.float().flatten(), 2).values
+        mag = max(abs(float(top[0])), 1e-30)
+        ulp = 2.0 ** (math.floor(math.log2(mag)) - 7)
+        return float(top[0] - top[1]) / ulp
+
     def generate(self, enc: Encoded, prompt: Sequence[int], max_tokens: int,
                  forced: Optional[Sequence[int]] = None) -> Generation:
         """Greedy ``_generate_answer`` (moondream.py:434-539) reduced to token ids: prompt prefill,
@@ -329,10 +338,11 @@ class OracleModel:
         tk = self.cfg.tokenizer
         self.load_encoded(enc)
         logits, hidden, nxt, pos = self.prefill_prompt(prompt, enc.pos)
-        out = Generation([], [], [])
+        out = Generation([], [], [], margin_ulps=[])
         n = 0
         pred = int(nxt.item())
         margin = self._margin(logits)
+        ulps = self._margin_ulps(logits)
         while True:
             if n >= max_tokens:
                 break
@@ -342,11 +352,13 @@ class OracleModel:
             out.tokens.append(tok)
             out.predicted.append(pred)
             out.margins.append(margin)
+            out.margin_ulps.append(ulps)
             logits, hidden = self.decode_one(self.embed(torch.tensor([[tok]])), pos)
             logits[:, tk.answer_id] = float("-inf")
             pos += 1
             pred = int(torch.argmax(logits, dim=-1).item())
             margin = self._margin(logits)
+            ulps = self._margin_ulps(logits)
             n += 1
         out.last_hidden = hidden
         return out
@@ -379,11 +391,15 @@ class OracleModel:
                     emb = self.encode_size(torch.tensor([wv, hv], dtype=sl.dtype)).unsqueeze(0).unsqueeze(0)
                     objs.append({"x_min": xc.item() - wv.item() / 2, "y_min": yc.item() - hv.item() / 2,
                                  "x_max": xc.item() + wv.item() / 2, "y_max": yc.item() + hv.item() / 2,
-                                 "bins": [int(torch.argmax(xl)), int(torch.argmax(yl)), int(wb), int(hb)]})
+                                 "bins": [int(torch.argmax(xl)), int(torch.argmax(yl)), int(wb), int(hb)],
+                                 "ulps": [self._margin_ulps(xl), self._margin_ulps(yl),
+                                          self._margin_ulps(sl[0]), self._margin_ulps(sl[1])]})
                 else:
                     objs.append({"x": xc.item(), "y": yc.item(),
-                                 "bins": [int(torch.argmax(xl)), int(torch.argmax(yl))]})
+                                 "bins": [int(torch.argmax(xl)), int(torch.argmax(yl))],
+                                 "ulps": [self._margin_ulps(xl), self._margin_ulps(yl)]})
                 logits, hidden = self.decode_one(emb, pos)
                 pos += 1
                 nxt = torch.argmax(logits, dim=-1)
+                objs[-1]["ulps"].append(self._margin_ulps(logits))     # the continue/stop decision
         return objs

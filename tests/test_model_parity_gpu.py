@@ -3,9 +3,11 @@ reference, bit-identical to it) on the same seeded weights and inputs, plus the 
 fixtures generated from the unmodified reference.
 
 Tolerances (written here on purpose):
-  * integer outputs (token ids, region bins, tilings): exact, except that a greedy token may differ
-    where the ORACLE's own top-1/top-2 logit margin is below MARGIN_EPS (a bf16 near-tie; the
-    reference's own argmax moves there between 1 and 8 CPU threads, SURVEY.md §7);
+  * integer outputs (token ids, region bins, tilings): exact, except that an argmax may differ where
+    the ORACLE's own top-1/top-2 logit margin is below NEAR_TIE_ULPS bf16 ulps of the top logit (the
+    reference rounds logits to bf16, so such decisions are ties up to rounding; its own argmax moves
+    there between 1 and 8 CPU threads).  After such a legitimate flip the two sequences
+    diverge, so the comparison of that sequence stops there;
   * hidden states / KV contents: norm-wise relative error <= REL_TOL against the bf16 oracle, and no
     further from the fp32 truth than 1.5x the bf16 oracle's own distance + 2e-3 (bf16's unit roundoff
     is 3.9e-3, so BASELINE.json's 1e-3 cannot hold element-wise).
@@ -20,7 +22,7 @@ import torch
 pytestmark = pytest.mark.gpu
 
 REL_TOL = 3e-2
-MARGIN_EPS = 0.13       # ~2 bf16 ulps at the typical top-logit magnitude of the synthetic models
+NEAR_TIE_ULPS = 3.0     # hidden states agree to ~1e-2 relative => logits to ~2 bf16 ulps
 GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
 
 
@@ -73,10 +75,29 @@ def _check_tokens(got, oracle_gen, what):
     n = len(oracle_gen.tokens)
     for i in range(n):
         if got[i] != oracle_gen.tokens[i]:
-            assert oracle_gen.margins[i] < MARGIN_EPS, \
-                f"{what}: token {i} differs ({got[i]} vs {oracle_gen.tokens[i]}) at oracle margin {oracle_gen.margins[i]}"
+            assert oracle_gen.margin_ulps[i] < NEAR_TIE_ULPS, \
+                f"{what}: token {i} differs ({got[i]} vs {oracle_gen.tokens[i]}) at oracle margin " \
+                f"{oracle_gen.margins[i]} = {oracle_gen.margin_ulps[i]:.1f} ulps"
             return i
     return n
+
+
+def _check_objects(got, want, what):
+    """bins exact; a differing decision is accepted only at an oracle near-tie, after which the
+    sequences legitimately diverge (comparison stops)."""
+    for n, w in enumerate(want):
+        assert n < len(got), f"{what}: object {n} missing"
+        g = got[n]
+        for j, (gb, wb) in enumerate(zip(g["bins"], w["bins"])):
+            if gb != wb:
+                assert w["ulps"][j] < NEAR_TIE_ULPS, f"{what}: object {n} bin {j}: {gb} vs {wb} at {w['ulps'][j]:.1f} ulps"
+                return
+        for k in w:
+            if k not in ("bins", "ulps"):
+                assert abs(g[k] - w[k]) < 1e-5, (what, n, k, g[k], w[k])
+        if w["ulps"][-1] < NEAR_TIE_ULPS:       # the continue/stop token itself is a near-tie
+            return
+    assert len(got) == len(want), f"{what}: {len(got)} objects vs {len(want)}"
 
 
 def test_greedy_generation_batch(tiny):
@@ -111,7 +132,7 @@ def test_teacher_forced_generation(tiny):
     for i in range(3):
         o = orc.generate(orc.encode_image(imgs[i]), prompts[i], 32, forced=forced[i])
         for s in range(32):
-            if o.margins[s] >= MARGIN_EPS:
+            if o.margin_ulps[s] >= NEAR_TIE_ULPS:
                 checked += 1
                 agree += int(res.tokens[i, s].item() == o.predicted[s])
         # margins themselves agree to bf16 resolution
@@ -144,12 +165,7 @@ def test_detect_point(tiny, include_size):
     got = eng.generate_points(prefixes, prompts, include_size, max_objects=3)
     for i in range(3):
         want = orc.generate_points(orc.encode_image(imgs[i]), prompts[i], include_size, 3)
-        assert len(got[i]) == len(want)
-        for g, w in zip(got[i], want):
-            assert g["bins"] == w["bins"], (i, g, w)
-            for k in w:
-                if k != "bins":
-                    assert abs(g[k] - w[k]) < 1e-5
+        _check_objects(got[i], want, f"image {i}")
 
 
 def test_golden_reference_fixture(tiny):
