@@ -180,9 +180,11 @@ def test_golden_reference_fixture(tiny):
         prefixes = eng.encode_images([img])
         res = eng.generate(prefixes, [case["prompt"]], len(case["tokens"]))
         got = res.tokens[0].tolist()
-        for s, (tok, margin) in enumerate(zip(case["tokens"], case["margins"])):
+        for s, (tok, ulps) in enumerate(zip(case["tokens"], case["margin_ulps"])):
             if got[s] != tok:
-                assert margin < MARGIN_EPS, (case["name"], s, got[s], tok, margin)
+                assert ulps < NEAR_TIE_ULPS, (case["name"], s, got[s], tok, ulps)
                 break
-        pts = eng.generate_points(eng.encode_images([img]), [case["detect_prompt"]], True, 3)[0]
-        assert [p["bins"] for p in pts] == case["detect_bins"], case["name"]
+        for kind, size in (("detect", True), ("point", False)):
+            pts = eng.generate_points(eng.encode_images([img]), [case[f"{kind}_prompt"]], size, 3)[0]
+            want = [{"bins": b, "ulps": u} for b, u in zip(case[f"{kind}_bins"], case[f"{kind}_ulps"])]
+            _check_objects(pts, want, f"{case['name']} {kind}")
