@@ -263,19 +263,22 @@ def run_main(args, cfg, sd, rank, world, local_rank):
     value = world * B * args.steps / (ms_max / 1000.0)
 
     # e2e: host buffers in, token ids out, wall clock around a synchronised region
-    step_e2e()
+    if args.no_e2e:
+        out = step_e2e() if False else None
+    else:
+        step_e2e()
     barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
+    for _ in range(0 if args.no_e2e else args.steps):
         out = step_e2e()
     barrier()
-    e2e_s = time.perf_counter() - t0
+    e2e_s = max(time.perf_counter() - t0, 1e-9)
     t_e = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
     e2e_value = world * B * args.steps / float(t_e.item())
     h2d = int(crops_host.numel() + B * PROMPT_LEN * 4 + 3 * 4 * (B + 1) + B * eng.max_blocks * 4)
-    d2h = int(out.tokens.numel() * 4 + out.margins.numel() * 4)
+    d2h = int(out.tokens.numel() * 4 + out.margins.numel() * 4) if out is not None else 0
 
     if rank != 0:
         return
@@ -313,6 +316,7 @@ def run_main(args, cfg, sd, rank, world, local_rank):
 
 
 def main():
+    global NEW_TOKENS
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -321,7 +325,11 @@ def main():
     ap.add_argument("--model", default="moondream-2b")
     ap.add_argument("--batch", type=int, default=BATCH_PER_GPU)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="profiling runs only (ncu launch lists)")
+    ap.add_argument("--new-tokens", type=int, default=NEW_TOKENS,
+                    help="profiling runs only: anything but 64 is not the BASELINE.json metric")
     args = ap.parse_args()
+    NEW_TOKENS = args.new_tokens
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
