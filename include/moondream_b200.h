@@ -122,6 +122,11 @@ typedef struct md_dims {
   int txt_dim, txt_ff, txt_layers, txt_heads, vocab, max_context, prefix_len;
   /* region (RegionConfig, config.py:34-41) */
   int reg_inner, coord_feat, coord_out, size_feat, size_out;
+  /* 1: the decoder weights use the fused decode layout.  Per text block the canonical pointers are
+   * views into two buffers:  W1 = [qkv.weight ; fc1.weight]  ([3D + FF, D], bias likewise), and
+   * W2 = [proj.weight | fc2.weight]  ([D, D + FF], row pitch D + FF).  md_model_create checks the
+   * pointer relationships.  md_text_decode_step requires it (one weight stream per pair). */
+  int txt_fused;
 } md_dims;
 
 typedef struct md_model md_model;
@@ -168,19 +173,24 @@ int md_text_prefill(md_model* model, void* x, int total_tokens, const int* q_off
                     void* stream);
 
 /* _decode_one_tok's decoder half (text.py:128-160 with T=1) for `batch` sequences:
- * x [batch, txt_dim] embeddings in, hidden out (in place); pos int32 [batch] (device). */
+ * x [batch, txt_dim] embeddings in, hidden out (in place); pos int32 [batch] (device).
+ * normed_out (optional) receives post_ln(hidden) [batch, txt_dim] (text.py:165) computed by the last
+ * block's fused epilogue; pass it to md_lm_head_argmax with prenormed = 1.
+ * Per block: one [qkv;fc1] weight stream, RoPE/KV-write/GELU epilogue, paged attention, one
+ * [proj|fc2] weight stream, residual + next-LayerNorm epilogue (5 launches). */
 long long md_text_decode_workspace_bytes(const md_model* model, int batch);
 int md_text_decode_step(md_model* model, void* x, const int* pos, int batch, const md_kv* kv,
-                        void* workspace, void* stream);
+                        void* normed_out, void* workspace, void* stream);
 
 /* lm_head + greedy argmax (text.py:163-167, moondream.py:313-314,517-524): hidden rows
  * [batch] x txt_dim (stride ld_hidden).  Token ids go to out_ids[b * out_stride + *out_index]
  * (out_index: device int or NULL = 0); mask_id >= 0 is excluded (answer_id, moondream.py:517).
+ * prenormed != 0: `hidden` already holds post_ln(hidden) (from md_text_decode_step's normed_out).
  * Optional: out_margin (same addressing, top1 - top2 of the bf16 logits), out_logits bf16 [batch, vocab]. */
 long long md_lm_head_workspace_bytes(const md_model* model, int batch);
-int md_lm_head_argmax(md_model* model, const void* hidden, long long ld_hidden, int batch, int mask_id,
-                      int* out_ids, long long out_stride, const int* out_index, float* out_margin,
-                      void* out_logits, void* workspace, void* stream);
+int md_lm_head_argmax(md_model* model, const void* hidden, long long ld_hidden, int prenormed, int batch,
+                      int mask_id, int* out_ids, long long out_stride, const int* out_index,
+                      float* out_margin, void* out_logits, void* workspace, void* stream);
 
 /* Decode-loop bookkeeping on the device (the generator loop of moondream.py:481-530 without the
  * per-token .item() sync): cur_tok[b] = (forced ? forced : preds)[b*stride + step+1]; pos[b] += 1;

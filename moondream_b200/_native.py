@@ -22,7 +22,7 @@ class md_dims(ctypes.Structure):
     _fields_ = [(n, c_int) for n in (
         "vis_dim", "vis_ff", "vis_layers", "vis_heads", "crop", "patch", "patch_k", "grid", "margin",
         "proj_inner", "txt_dim", "txt_ff", "txt_layers", "txt_heads", "vocab", "max_context",
-        "prefix_len", "reg_inner", "coord_feat", "coord_out", "size_feat", "size_out")]
+        "prefix_len", "reg_inner", "coord_feat", "coord_out", "size_feat", "size_out", "txt_fused")]
 
 
 _P = c_void_p
@@ -61,9 +61,9 @@ _SIGNATURES = {
     "md_text_prefill_workspace_bytes": (_LL, [_P, c_int]),
     "md_text_prefill": (c_int, [_P, _P, c_int, _P, _P, c_int, c_int, _KV, _P, _P]),
     "md_text_decode_workspace_bytes": (_LL, [_P, c_int]),
-    "md_text_decode_step": (c_int, [_P, _P, _P, c_int, _KV, _P, _P]),
+    "md_text_decode_step": (c_int, [_P, _P, _P, c_int, _KV, _P, _P, _P]),
     "md_lm_head_workspace_bytes": (_LL, [_P, c_int]),
-    "md_lm_head_argmax": (c_int, [_P, _P, _LL, c_int, c_int, _P, _LL, _P, _P, _P, _P, _P]),
+    "md_lm_head_argmax": (c_int, [_P, _P, _LL, c_int, c_int, c_int, _P, _LL, _P, _P, _P, _P, _P]),
     "md_decode_advance": (c_int, [_P, _P, _P, _P, _P, _LL, c_int, c_int, _P, _P]),
     "md_gather_rows_bf16": (c_int, [_P, _LL, _P, c_int, c_int, _P, _LL, _P]),
     "md_region_workspace_bytes": (_LL, [_P, c_int]),

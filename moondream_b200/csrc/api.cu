@@ -104,7 +104,8 @@ int md_decode_attention_bf16(const void* q, int n_heads, const int* pos, int n_s
                              int layer, void* out, void* stream) {
   NEED(q && pos && kv && kv->pool && kv->block_tables && out, "md_decode_attention_bf16");
   return md::decode_attention(BF(q), n_heads, pos, n_seqs, BF(kv->pool), kv->n_pages, kv->block_tables,
-                              kv->max_blocks, layer, BFM(out), STREAM(stream));
+                              kv->max_blocks, layer, BFM(out), static_cast<long long>(n_heads) * 64,
+                              STREAM(stream));
 }
 
 // ---------------------------------------------------------------- model level
@@ -165,20 +166,20 @@ long long md_text_decode_workspace_bytes(const md_model* model, int batch) {
   return model ? md::text_decode_ws_bytes(*model, batch) : -1;
 }
 int md_text_decode_step(md_model* model, void* x, const int* pos, int batch, const md_kv* kv,
-                        void* workspace, void* stream) {
+                        void* normed_out, void* workspace, void* stream) {
   NEED(model && x && pos && kv && kv->pool && kv->block_tables && workspace, "md_text_decode_step");
-  return md::text_decode_step(*model, BFM(x), pos, batch, *kv, workspace, STREAM(stream));
+  return md::text_decode_step(*model, BFM(x), pos, batch, *kv, BFM(normed_out), workspace, STREAM(stream));
 }
 
 long long md_lm_head_workspace_bytes(const md_model* model, int batch) {
   return model ? md::lm_head_ws_bytes(*model, batch) : -1;
 }
-int md_lm_head_argmax(md_model* model, const void* hidden, long long ld_hidden, int batch, int mask_id,
-                      int* out_ids, long long out_stride, const int* out_index, float* out_margin,
-                      void* out_logits, void* workspace, void* stream) {
+int md_lm_head_argmax(md_model* model, const void* hidden, long long ld_hidden, int prenormed, int batch,
+                      int mask_id, int* out_ids, long long out_stride, const int* out_index,
+                      float* out_margin, void* out_logits, void* workspace, void* stream) {
   NEED(model && hidden && out_ids && workspace, "md_lm_head_argmax");
-  return md::lm_head_argmax(*model, BF(hidden), ld_hidden, batch, mask_id, out_ids, out_stride, out_index,
-                            out_margin, BFM(out_logits), workspace, STREAM(stream));
+  return md::lm_head_argmax(*model, BF(hidden), ld_hidden, prenormed, batch, mask_id, out_ids, out_stride,
+                            out_index, out_margin, BFM(out_logits), workspace, STREAM(stream));
 }
 
 int md_decode_advance(int* cur_tok, int* pos, int* step, const int* preds, const int* forced,

@@ -341,7 +341,7 @@ __global__ void __launch_bounds__(128)
 decode_attention_kernel(const __nv_bfloat16* __restrict__ q, int n_heads, const int* __restrict__ pos,
                         const __nv_bfloat16* __restrict__ kv_pool, int n_pages,
                         const int* __restrict__ block_tables, int max_blocks, int layer,
-                        __nv_bfloat16* __restrict__ out, float scale_log2) {
+                        __nv_bfloat16* __restrict__ out, long long ld_out, float scale_log2) {
   const int head = blockIdx.x, seq = blockIdx.y;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int sub = lane & 7;            // which 16-byte chunk (8 dims) of the 64-dim row
@@ -424,17 +424,17 @@ decode_attention_kernel(const __nv_bfloat16* __restrict__ q, int n_heads, const 
       L += sm_l[s2][c] * w;
       A += sm_acc[s2][c][j] * w;
     }
-    out[(static_cast<long long>(seq) * n_heads + head) * 64 + c * 8 + j] = __float2bfloat16_rn(A / L);
+    out[static_cast<long long>(seq) * ld_out + head * 64 + c * 8 + j] = __float2bfloat16_rn(A / L);
   }
 }
 
 int decode_attention(const __nv_bfloat16* q, int n_heads, const int* pos, int n_seqs,
                      const __nv_bfloat16* kv_pool, int n_pages, const int* block_tables,
-                     int max_blocks, int layer, __nv_bfloat16* out, cudaStream_t stream) {
+                     int max_blocks, int layer, __nv_bfloat16* out, long long ld_out, cudaStream_t stream) {
   if (n_seqs <= 0) return set_error("decode_attention: empty batch");
   dim3 grid(n_heads, n_seqs);
   decode_attention_kernel<<<grid, 128, 0, stream>>>(q, n_heads, pos, kv_pool, n_pages, block_tables,
-                                                    max_blocks, layer, out,
+                                                    max_blocks, layer, out, ld_out,
                                                     0.125f * 1.4426950408889634f);
   count_launch();
   cudaError_t e = cudaGetLastError();

@@ -37,7 +37,7 @@ int model_create(const md_dims& d, const void* const* w, int n, const void* lut,
   m->rope = rope;
   int k = 0;
   auto next = [&]() { return reinterpret_cast<const bf16*>(w[k++]); };
-  auto lin = [&]() { Lin l; l.w = next(); l.b = next(); return l; };
+  auto lin = [&]() { Lin l; l.w = next(); l.b = next(); l.ld = 0; return l; };
   m->pos_emb = next();
   m->patch_emb = lin();
   m->vis.resize(d.vis_layers);
@@ -58,6 +58,28 @@ int model_create(const md_dims& d, const void* const* w, int n, const void* lut,
   m->size_enc = lin();
   m->size_dec1 = lin();
   m->size_dec2 = lin();
+  // natural row pitches (= fan-in) ...
+  m->patch_emb.ld = d.patch_k;
+  for (auto& b : m->vis) { b.qkv.ld = d.vis_dim; b.proj.ld = d.vis_dim; b.fc1.ld = d.vis_dim; b.fc2.ld = d.vis_ff; }
+  m->proj_fc1.ld = 2 * d.vis_dim; m->proj_fc2.ld = d.proj_inner;
+  m->lm_head.ld = d.txt_dim;
+  m->coord_enc.ld = d.coord_feat; m->coord_dec1.ld = d.txt_dim; m->coord_dec2.ld = d.reg_inner;
+  m->size_enc.ld = d.size_feat; m->size_dec1.ld = d.txt_dim; m->size_dec2.ld = d.reg_inner;
+  const long long D = d.txt_dim, FF = d.txt_ff;
+  for (auto& b : m->txt) {
+    b.qkv.ld = D; b.fc1.ld = D;
+    if (d.txt_fused) {
+      // ... except the fused decode layout: W1 = [qkv ; fc1] rows, W2 = [proj | fc2] columns
+      if (b.fc1.w != b.qkv.w + 3 * D * D || b.fc1.b != b.qkv.b + 3 * D || b.fc2.w != b.proj.w + D) {
+        delete m;
+        return set_error("md_model_create: txt_fused is set but the decoder weights are not views of "
+                         "[qkv;fc1] / [proj|fc2] buffers");
+      }
+      b.proj.ld = D + FF; b.fc2.ld = D + FF;
+    } else {
+      b.proj.ld = D; b.fc2.ld = FF;
+    }
+  }
   *out = m;
   return 0;
 }
@@ -165,16 +187,34 @@ int text_prefill(Model& m, bf16* x, int T, const int* q_offsets, const int* star
     if (prefill_attention(q, H, q_offsets, start_pos, n_seqs, max_q, d.prefix_len, pool, kv.n_pages,
                           kv.block_tables, kv.max_blocks, i, att, st)) return 1;
     // tmp = bf16(x + bf16(proj(att)))  -- the reference adds l_attn first, then l_mlp (text.py:158)
-    if (gemm_rowform(att, D, b.proj.w, D, T, D, D, EPI_BIAS_RESIDUAL, b.proj.b, x, D, 0, tmp, D, 0, 0, 0, st)) return 1;
-    if (gemm_rowform(ln, D, b.fc1.w, D, T, d.txt_ff, D, EPI_BIAS_GELU, b.fc1.b, nullptr, 0, 0, hid, d.txt_ff, 0, 0, 0, st)) return 1;
-    if (gemm_rowform(hid, d.txt_ff, b.fc2.w, d.txt_ff, T, D, d.txt_ff, EPI_BIAS_RESIDUAL, b.fc2.b, tmp, D, 0, x, D, 0, 0, 0, st)) return 1;
+    if (gemm_rowform(att, D, b.proj.w, b.proj.ld, T, D, D, EPI_BIAS_RESIDUAL, b.proj.b, x, D, 0, tmp, D, 0, 0, 0, st)) return 1;
+    if (gemm_rowform(ln, D, b.fc1.w, b.fc1.ld, T, d.txt_ff, D, EPI_BIAS_GELU, b.fc1.b, nullptr, 0, 0, hid, d.txt_ff, 0, 0, 0, st)) return 1;
+    if (gemm_rowform(hid, d.txt_ff, b.fc2.w, b.fc2.ld, T, D, d.txt_ff, EPI_BIAS_RESIDUAL, b.fc2.b, tmp, D, 0, x, D, 0, 0, 0, st)) return 1;
   }
   return 0;
 }
 
 // ------------------------------------------------------------------------------------------------
-// text decoder: one decode step for `batch` sequences
+// text decoder: one decode step for `batch` sequences (fused layout, 5 launches per block)
 // ------------------------------------------------------------------------------------------------
+// k-blocks per split of the K-concatenated [proj | fc2] stream: a divisor of D/64 (so no split
+// straddles the proj/fc2 boundary) that minimises waves x tile length, at most 32 splits.
+static int pick_cat_kb(const md_dims& d) {
+  const int kb_d = d.txt_dim / 64, total = (d.txt_dim + d.txt_ff) / 64;
+  const int m_blocks = (d.txt_dim + 127) / 128;
+  int best = kb_d;
+  long long best_cost = -1;
+  for (int c = kb_d; c >= 1; --c) {
+    if (kb_d % c) continue;
+    const int splits = (total + c - 1) / c;
+    if (splits > 32) break;
+    const int tiles = m_blocks * splits;
+    const long long cost = 1LL * ((tiles + num_sms() - 1) / num_sms()) * c;
+    if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = c; }
+  }
+  return best;
+}
+
 static long long smallbatch_ws_floats(const Model& m, int batch) {
   const md_dims& d = m.d;
   long long need = 0;
@@ -182,7 +222,12 @@ static long long smallbatch_ws_floats(const Model& m, int batch) {
     const long long f = 1LL * gemm_swapped_splits(n_out, K) * batch * n_out;
     if (f > need) need = f;
   };
-  upd(3 * d.txt_dim, d.txt_dim); upd(d.txt_dim, d.txt_dim); upd(d.txt_ff, d.txt_dim); upd(d.txt_dim, d.txt_ff);
+  upd(3 * d.txt_dim + d.txt_ff, d.txt_dim);
+  {
+    const int kb = pick_cat_kb(d);
+    const long long f = 1LL * (((d.txt_dim + d.txt_ff) / 64 + kb - 1) / kb) * batch * d.txt_dim;
+    if (f > need) need = f;
+  }
   upd(d.vocab, d.txt_dim);
   upd(d.reg_inner, d.txt_dim); upd(d.coord_out, d.reg_inner); upd(d.size_out, d.reg_inner);
   upd(d.txt_dim, d.coord_feat); upd(d.txt_dim, d.size_feat);
@@ -191,40 +236,48 @@ static long long smallbatch_ws_floats(const Model& m, int batch) {
 
 long long text_decode_ws_bytes(const Model& m, int batch) {
   const md_dims& d = m.d;
-  return pad256(1LL * batch * d.txt_dim * 2) * 4 + pad256(1LL * batch * 3 * d.txt_dim * 2) +
-         pad256(1LL * batch * d.txt_ff * 2) + pad256(smallbatch_ws_floats(m, batch) * 4) + 4096;
+  return pad256(1LL * batch * d.txt_dim * 2) * 3 + pad256(1LL * batch * (d.txt_dim + d.txt_ff) * 2) +
+         pad256(smallbatch_ws_floats(m, batch) * 4) + 4096;
 }
 
 static int small_linear(const bf16* x, long long ldx, const Lin& l, int batch, int n_out, int K, int mode,
                         const bf16* res, long long ldr, bf16* out, long long ldo, float* ws, cudaStream_t st) {
-  const int used = gemm_swapped(l.w, K, x, ldx, n_out, batch, K, gemm_swapped_splits(n_out, K), ws, st);
+  const int used = gemm_swapped(l.w, l.ld, x, ldx, n_out, batch, K, gemm_swapped_splits(n_out, K), ws, st);
   if (used < 0) return 1;
   return splitk_epilogue(ws, used, batch, n_out, mode, l.b, res, ldr, out, ldo, st);
 }
 
-int text_decode_step(Model& m, bf16* x, const int* pos, int batch, const md_kv& kv, void* ws, cudaStream_t st) {
+int text_decode_step(Model& m, bf16* x, const int* pos, int batch, const md_kv& kv, bf16* normed_out, void* ws,
+                     cudaStream_t st) {
   const md_dims& d = m.d;
   if (batch <= 0) return set_error("md_text_decode_step: empty batch");
-  const int D = d.txt_dim, H = d.txt_heads;
+  if (!d.txt_fused) return set_error("md_text_decode_step: the model was created without the fused decode layout");
+  const int D = d.txt_dim, FF = d.txt_ff, H = d.txt_heads;
   char* p = align_up(reinterpret_cast<char*>(ws));
   bf16* ln = reinterpret_cast<bf16*>(p); p += pad256(1LL * batch * D * 2);
-  bf16* qkv = reinterpret_cast<bf16*>(p); p += pad256(1LL * batch * 3 * D * 2);
   bf16* q = reinterpret_cast<bf16*>(p); p += pad256(1LL * batch * D * 2);
-  bf16* att = reinterpret_cast<bf16*>(p); p += pad256(1LL * batch * D * 2);
-  bf16* tmp = reinterpret_cast<bf16*>(p); p += pad256(1LL * batch * D * 2);
-  bf16* hid = reinterpret_cast<bf16*>(p); p += pad256(1LL * batch * d.txt_ff * 2);
+  bf16* ln_last = reinterpret_cast<bf16*>(p); p += pad256(1LL * batch * D * 2);
+  bf16* xcat = reinterpret_cast<bf16*>(p); p += pad256(1LL * batch * (D + FF) * 2);   // [att | gelu(fc1)]
   float* wsf = reinterpret_cast<float*>(p);
   bf16* pool = reinterpret_cast<bf16*>(kv.pool);
+  const int kb = pick_cat_kb(d);
+  const int proj_splits = (D / 64) / kb;
+  if (layernorm(x, D, m.txt[0].ln.w, m.txt[0].ln.b, ln, D, batch, D, 1e-5f, st)) return 1;
   for (int i = 0; i < d.txt_layers; ++i) {
     const TxtBlock& b = m.txt[i];
-    if (layernorm(x, D, b.ln.w, b.ln.b, ln, D, batch, D, 1e-5f, st)) return 1;
-    if (small_linear(ln, D, b.qkv, batch, 3 * D, D, EPI_BIAS, nullptr, 0, qkv, 3 * D, wsf, st)) return 1;
-    if (rope_kv_write(qkv, batch, H, nullptr, pos, batch, m.rope, q, pool, kv.n_pages, kv.block_tables,
-                      kv.max_blocks, i, st)) return 1;
-    if (decode_attention(q, H, pos, batch, pool, kv.n_pages, kv.block_tables, kv.max_blocks, i, att, st)) return 1;
-    if (small_linear(att, D, b.proj, batch, D, D, EPI_BIAS_RESIDUAL, x, D, tmp, D, wsf, st)) return 1;
-    if (small_linear(ln, D, b.fc1, batch, d.txt_ff, D, EPI_BIAS_GELU, nullptr, 0, hid, d.txt_ff, wsf, st)) return 1;
-    if (small_linear(hid, d.txt_ff, b.fc2, batch, D, d.txt_ff, EPI_BIAS_RESIDUAL, tmp, D, x, D, wsf, st)) return 1;
+    // [qkv ; fc1] share the input l = ln(x) (text.py:145-157): one weight stream
+    const int s1 = gemm_swapped(b.qkv.w, D, ln, D, 3 * D + FF, batch, D, gemm_swapped_splits(3 * D + FF, D), wsf, st);
+    if (s1 < 0) return 1;
+    if (decode_qkv_mlp_epilogue(wsf, s1, batch, D, FF, H, b.qkv.b, pos, m.rope, q, xcat + D, D + FF, pool,
+                                kv.n_pages, kv.block_tables, kv.max_blocks, i, st)) return 1;
+    if (decode_attention(q, H, pos, batch, pool, kv.n_pages, kv.block_tables, kv.max_blocks, i, xcat, D + FF, st)) return 1;
+    // proj(att) and fc2(hid) both land in the residual: one K-concatenated weight stream
+    const int s2 = gemm_swapped_kb(b.proj.w, D + FF, xcat, D + FF, D, batch, D + FF, kb, wsf, st);
+    if (s2 < 0) return 1;
+    const bool last = i + 1 == d.txt_layers;
+    const Lin& nln = last ? m.txt_post_ln : m.txt[i + 1].ln;
+    bf16* ln_dst = last ? (normed_out ? normed_out : ln_last) : ln;
+    if (decode_residual_ln_epilogue(wsf, s2, proj_splits, batch, D, b.proj.b, b.fc2.b, x, nln.w, nln.b, ln_dst, st)) return 1;
   }
   return 0;
 }
@@ -236,16 +289,22 @@ long long lm_head_ws_bytes(const Model& m, int batch) {
   return pad256(1LL * batch * m.d.txt_dim * 2) + pad256(smallbatch_ws_floats(m, batch) * 4) + 4096;
 }
 
-int lm_head_argmax(Model& m, const bf16* hidden, long long ldh, int batch, int mask_id, int* out_ids,
-                   long long out_stride, const int* out_index, float* out_margin, bf16* out_logits,
-                   void* ws, cudaStream_t st) {
+int lm_head_argmax(Model& m, const bf16* hidden, long long ldh, int prenormed, int batch, int mask_id,
+                   int* out_ids, long long out_stride, const int* out_index, float* out_margin,
+                   bf16* out_logits, void* ws, cudaStream_t st) {
   const md_dims& d = m.d;
   if (batch <= 0) return set_error("md_lm_head_argmax: empty batch");
   char* p = align_up(reinterpret_cast<char*>(ws));
   bf16* ln = reinterpret_cast<bf16*>(p); p += pad256(1LL * batch * d.txt_dim * 2);
   float* wsf = reinterpret_cast<float*>(p);
-  if (layernorm(hidden, ldh, m.txt_post_ln.w, m.txt_post_ln.b, ln, d.txt_dim, batch, d.txt_dim, 1e-5f, st)) return 1;
-  const int used = gemm_swapped(m.lm_head.w, d.txt_dim, ln, d.txt_dim, d.vocab, batch, d.txt_dim,
+  const bf16* normed = hidden;
+  long long ldn = ldh;
+  if (!prenormed) {
+    if (layernorm(hidden, ldh, m.txt_post_ln.w, m.txt_post_ln.b, ln, d.txt_dim, batch, d.txt_dim, 1e-5f, st)) return 1;
+    normed = ln;
+    ldn = d.txt_dim;
+  }
+  const int used = gemm_swapped(m.lm_head.w, d.txt_dim, normed, ldn, d.vocab, batch, d.txt_dim,
                                 gemm_swapped_splits(d.vocab, d.txt_dim), wsf, st);
   if (used < 0) return 1;
   return argmax_logits(wsf, used, batch, d.vocab, m.lm_head.b, 1, mask_id, out_ids, out_stride, out_index,
@@ -277,7 +336,7 @@ int region_decode(Model& m, int which, const bf16* hidden, long long ldh, int ba
   // mlp(hidden): fc1 + gelu, fc2 (region.py:46-57, 74-93)
   if (small_linear(hidden, ldh, l1, batch, d.reg_inner, d.txt_dim, EPI_BIAS_GELU, nullptr, 0, hid,
                    d.reg_inner, wsf, st)) return 1;
-  const int used = gemm_swapped(l2.w, d.reg_inner, hid, d.reg_inner, n_out, batch, d.reg_inner,
+  const int used = gemm_swapped(l2.w, l2.ld, hid, d.reg_inner, n_out, batch, d.reg_inner,
                                 gemm_swapped_splits(n_out, d.reg_inner), wsf, st);
   if (used < 0) return 1;
   if (which == 0)

@@ -9,7 +9,7 @@ namespace md {
 
 using bf16 = __nv_bfloat16;
 
-struct Lin { const bf16* w; const bf16* b; };        // Linear (weight [out,in], bias) or LayerNorm (w, b)
+struct Lin { const bf16* w; const bf16* b; long long ld; };   // Linear (weight [out,in], row pitch ld, bias) or LayerNorm (w, b)
 struct VisBlock { Lin ln1, qkv, proj, ln2, fc1, fc2; };
 struct TxtBlock { Lin ln, qkv, proj, fc1, fc2; };
 
@@ -41,9 +41,10 @@ long long text_prefill_ws_bytes(const Model& m, int T);
 int text_prefill(Model& m, bf16* x, int T, const int* q_offsets, const int* start_pos, int n_seqs,
                  int max_q, const md_kv& kv, void* ws, cudaStream_t st);
 long long text_decode_ws_bytes(const Model& m, int batch);
-int text_decode_step(Model& m, bf16* x, const int* pos, int batch, const md_kv& kv, void* ws, cudaStream_t st);
+int text_decode_step(Model& m, bf16* x, const int* pos, int batch, const md_kv& kv, bf16* normed_out, void* ws,
+                     cudaStream_t st);
 long long lm_head_ws_bytes(const Model& m, int batch);
-int lm_head_argmax(Model& m, const bf16* hidden, long long ldh, int batch, int mask_id, int* out_ids,
+int lm_head_argmax(Model& m, const bf16* hidden, long long ldh, int prenormed, int batch, int mask_id, int* out_ids,
                    long long out_stride, const int* out_index, float* out_margin, bf16* out_logits,
                    void* ws, cudaStream_t st);
 long long region_ws_bytes(const Model& m, int batch);

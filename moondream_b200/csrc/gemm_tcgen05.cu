@@ -31,6 +31,7 @@ struct GemmParams {
   int M, N, K;
   int m_blocks, n_blocks, k_blocks;   // k_blocks = ceil(K / BK)
   int k_splits;                        // >1 only in swapped form
+  int kb_per_split;                    // k-blocks owned by each split (last one may be shorter)
   int mode;                            // EPI_* (row form) or EPI_PARTIAL (swapped form)
   // row form
   __nv_bfloat16* out;
@@ -98,7 +99,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const uint32_t tmem_base = *tmem_ptr_smem;
 
   const int total_tiles = p.m_blocks * p.n_blocks * p.k_splits;
-  const int kb_per_split = (p.k_blocks + p.k_splits - 1) / p.k_splits;
+  const int kb_per_split = p.kb_per_split;
 
   if (warp == 0) {
     // ------------------------------ TMA producer ------------------------------
@@ -422,6 +423,7 @@ int gemm_rowform(const __nv_bfloat16* A, long long lda, const __nv_bfloat16* W, 
   p.n_blocks = (N + bn - 1) / bn;
   p.k_blocks = (K + BK - 1) / BK;
   p.k_splits = 1;
+  p.kb_per_split = p.k_blocks;
   p.mode = mode;
   p.out = out; p.ldo = ldo; p.bias = bias; p.res = res; p.ldr = ldr; p.res_mod = res_mod;
   p.remap_gin = remap_gin; p.remap_gout = remap_gout; p.remap_goff = remap_goff;
@@ -450,29 +452,42 @@ int gemm_swapped_splits(int n_out, int K) {
   return splits;
 }
 
-// ws[splits][batch][n_out] (fp32) = W[n_out,K] * X[batch,K]^T  partial sums.
-int gemm_swapped(const __nv_bfloat16* W, long long ldw, const __nv_bfloat16* X, long long ldx,
-                 int n_out, int batch, int K, int splits, float* ws, cudaStream_t stream) {
-  if (n_out <= 0 || batch <= 0 || K <= 0) return set_error("gemm_swapped: empty problem");
-  if (K % 8) return set_error("gemm_swapped: K must be a multiple of 8");
+// ws[splits][batch][n_out] (fp32) = W[n_out,K] * X[batch,K]^T  partial sums; split s owns k-blocks
+// [s * kb_per_split, (s+1) * kb_per_split).  Returns the number of splits (>0), -1 on error.
+static int gemm_swapped_impl(const __nv_bfloat16* W, long long ldw, const __nv_bfloat16* X, long long ldx,
+                             int n_out, int batch, int K, int kb_per_split, float* ws, cudaStream_t stream) {
+  if (n_out <= 0 || batch <= 0 || K <= 0) { set_error("gemm_swapped: empty problem"); return -1; }
+  if (K % 8) { set_error("gemm_swapped: K must be a multiple of 8"); return -1; }
   const int bn = batch <= 32 ? 32 : batch <= 64 ? 64 : batch <= 128 ? 128 : 256;
   CUtensorMap tA, tB;
-  if (make_tmap_bf16_2d(&tA, W, n_out, K, ldw, BM)) return 1;
-  if (make_tmap_bf16_2d(&tB, X, batch, K, ldx, bn)) return 1;
+  if (make_tmap_bf16_2d(&tA, W, n_out, K, ldw, BM)) return -1;
+  if (make_tmap_bf16_2d(&tB, X, batch, K, ldx, bn)) return -1;
   GemmParams p{};
   p.M = n_out; p.N = batch; p.K = K;
   p.m_blocks = (n_out + BM - 1) / BM;
   p.n_blocks = (batch + bn - 1) / bn;
   p.k_blocks = (K + BK - 1) / BK;
-  // every split must own at least one k-block, otherwise its accumulator is never written
-  if (splits > p.k_blocks) splits = p.k_blocks;
-  const int per = (p.k_blocks + splits - 1) / splits;
-  splits = (p.k_blocks + per - 1) / per;
-  p.k_splits = splits;
+  if (kb_per_split < 1) kb_per_split = 1;
+  if (kb_per_split > p.k_blocks) kb_per_split = p.k_blocks;
+  p.kb_per_split = kb_per_split;
+  p.k_splits = (p.k_blocks + kb_per_split - 1) / kb_per_split;   // every split owns >= 1 k-block
   p.mode = EPI_PARTIAL;
   p.ws = ws;
-  int rc = dispatch_gemm(bn, tA, tB, p, stream);
-  return rc ? -1 : splits;     // returns the split count actually used (>0), -1 on error
+  const int rc = dispatch_gemm(bn, tA, tB, p, stream);
+  return rc ? -1 : p.k_splits;
+}
+
+int gemm_swapped(const __nv_bfloat16* W, long long ldw, const __nv_bfloat16* X, long long ldx,
+                 int n_out, int batch, int K, int splits, float* ws, cudaStream_t stream) {
+  const int k_blocks = (K + BK - 1) / BK;
+  if (splits < 1) splits = 1;
+  if (splits > k_blocks) splits = k_blocks;
+  return gemm_swapped_impl(W, ldw, X, ldx, n_out, batch, K, (k_blocks + splits - 1) / splits, ws, stream);
+}
+
+int gemm_swapped_kb(const __nv_bfloat16* W, long long ldw, const __nv_bfloat16* X, long long ldx,
+                    int n_out, int batch, int K, int kb_per_split, float* ws, cudaStream_t stream) {
+  return gemm_swapped_impl(W, ldw, X, ldx, n_out, batch, K, kb_per_split, ws, stream);
 }
 
 int splitk_epilogue(const float* ws, int splits, int B, int N, int mode, const __nv_bfloat16* bias,

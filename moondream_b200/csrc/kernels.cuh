@@ -35,6 +35,9 @@ int gemm_profile_read(double* total_ms, double* total_flops, long long* launches
 int gemm_swapped_splits(int n_out, int K);
 int gemm_swapped(const __nv_bfloat16* W, long long ldw, const __nv_bfloat16* X, long long ldx,
                  int n_out, int batch, int K, int splits, float* ws, cudaStream_t stream);
+// same, with an explicit number of 64-wide k-blocks per split (split boundaries the caller relies on)
+int gemm_swapped_kb(const __nv_bfloat16* W, long long ldw, const __nv_bfloat16* X, long long ldx,
+                    int n_out, int batch, int K, int kb_per_split, float* ws, cudaStream_t stream);
 int splitk_epilogue(const float* ws, int splits, int B, int N, int mode, const __nv_bfloat16* bias,
                     const __nv_bfloat16* res, long long ldr, __nv_bfloat16* out, long long ldo,
                     cudaStream_t stream);
@@ -61,6 +64,15 @@ int decode_advance(int* cur_tok, int* pos, int* step, const int* preds, const in
 int gather_rows(const __nv_bfloat16* src, long long ld_src, const int* idx, int n, int dim,
                 __nv_bfloat16* out, long long ldo, cudaStream_t stream);
 int bins_to_values(int which, const int* bins, int n, float* out, cudaStream_t stream);
+int decode_qkv_mlp_epilogue(const float* ws, int splits, int B, int D, int FF, int n_heads,
+                            const __nv_bfloat16* bias, const int* pos, const float* freqs,
+                            __nv_bfloat16* q_out, __nv_bfloat16* hid, long long ld_hid,
+                            __nv_bfloat16* kv_pool, int n_pages, const int* block_tables, int max_blocks,
+                            int layer, cudaStream_t stream);
+int decode_residual_ln_epilogue(const float* ws, int splits, int proj_splits, int B, int D,
+                                const __nv_bfloat16* bias_proj, const __nv_bfloat16* bias_fc2,
+                                __nv_bfloat16* x, const __nv_bfloat16* ln_w, const __nv_bfloat16* ln_b,
+                                __nv_bfloat16* ln_out, cudaStream_t stream);
 int fourier_features(const float* x, int B, int n_in, const __nv_bfloat16* w, int half,
                      __nv_bfloat16* out, long long ldo, cudaStream_t stream);
 
@@ -73,6 +85,6 @@ int prefill_attention(const __nv_bfloat16* q, int n_heads, const int* q_offsets,
                       cudaStream_t stream);
 int decode_attention(const __nv_bfloat16* q, int n_heads, const int* pos, int n_seqs,
                      const __nv_bfloat16* kv_pool, int n_pages, const int* block_tables,
-                     int max_blocks, int layer, __nv_bfloat16* out, cudaStream_t stream);
+                     int max_blocks, int layer, __nv_bfloat16* out, long long ld_out, cudaStream_t stream);
 
 }  // namespace md

@@ -69,6 +69,34 @@ def prepare_weights(cfg: MoondreamConfig, sd: Dict[str, torch.Tensor]) -> Tuple[
     return out, patch_k, vis_ff
 
 
+def upload_weights(cfg: MoondreamConfig, prepared: List[torch.Tensor], device) -> Tuple[List[torch.Tensor], list]:
+    """Upload in canonical order.  The decoder blocks use the fused decode layout the C runtime checks
+    (md_dims.txt_fused): W1 = [qkv.weight ; fc1.weight], b1 = [qkv.bias ; fc1.bias] and
+    W2 = [proj.weight | fc2.weight]; the canonical entries become views of those buffers, so prefill
+    (separate GEMMs) and decode (one weight stream per pair) share the same memory."""
+    keys = [k for k, _, _ in state_dict_spec(cfg)]
+    idx = {k: i for i, k in enumerate(keys)}
+    dev: List[Optional[torch.Tensor]] = [None] * len(keys)
+    owners = []
+    D = cfg.text.dim
+    for i in range(cfg.text.n_layers):
+        p = f"text.blocks.{i}."
+        w1 = torch.cat([prepared[idx[p + "attn.qkv.weight"]], prepared[idx[p + "mlp.fc1.weight"]]], 0).to(device)
+        b1 = torch.cat([prepared[idx[p + "attn.qkv.bias"]], prepared[idx[p + "mlp.fc1.bias"]]], 0).to(device)
+        w2 = torch.cat([prepared[idx[p + "attn.proj.weight"]], prepared[idx[p + "mlp.fc2.weight"]]], 1).to(device)
+        owners += [w1, b1, w2]
+        dev[idx[p + "attn.qkv.weight"]] = w1[: 3 * D]
+        dev[idx[p + "mlp.fc1.weight"]] = w1[3 * D:]
+        dev[idx[p + "attn.qkv.bias"]] = b1[: 3 * D]
+        dev[idx[p + "mlp.fc1.bias"]] = b1[3 * D:]
+        dev[idx[p + "attn.proj.weight"]] = w2[:, :D]
+        dev[idx[p + "mlp.fc2.weight"]] = w2[:, D:]
+    for i, t in enumerate(prepared):
+        if dev[i] is None:
+            dev[i] = t.to(device)
+    return dev, owners  # type: ignore[return-value]
+
+
 class PagePool:
     """KV pages: bf16 [layers, n_pages, 2, heads, 64, 64]; a free list hands out page ids."""
 
@@ -130,7 +158,8 @@ class Engine:
         self.device = torch.device(device)
         self.lib = N.lib()
         prepared, self.patch_k, self.vis_ff = prepare_weights(cfg, state_dict)
-        self.weights = [t.to(self.device) for t in prepared]          # keeps device memory alive
+        self.weights, self._owners = upload_weights(cfg, prepared, self.device)   # keeps device memory alive
+        del prepared
         self.lut = pixel_lut().to(self.device)
         self.rope = rope_table(cfg.text.head_dim, cfg.text.max_context).to(self.device)
         v, t, r = cfg.vision, cfg.text, cfg.region
@@ -140,7 +169,7 @@ class Engine:
             margin=v.overlap_margin, proj_inner=v.proj_inner_dim, txt_dim=t.dim, txt_ff=t.ff_dim,
             txt_layers=t.n_layers, txt_heads=t.n_heads, vocab=t.vocab_size, max_context=t.max_context,
             prefix_len=t.prefix_attn, reg_inner=r.inner_dim, coord_feat=r.coord_feat_dim,
-            coord_out=r.coord_out_dim, size_feat=r.size_feat_dim, size_out=r.size_out_dim)
+            coord_out=r.coord_out_dim, size_feat=r.size_feat_dim, size_out=r.size_out_dim, txt_fused=1)
         n = self.lib.md_model_num_weights(ctypes.byref(self.dims))
         assert n == len(self.weights), (n, len(self.weights))
         arr = (ctypes.c_void_p * n)(*[w.data_ptr() for w in self.weights])
@@ -226,13 +255,13 @@ class Engine:
     def lm_head(self, hidden: torch.Tensor, out_ids: torch.Tensor, out_stride: int, mask_id: int = -1,
                 out_index: Optional[torch.Tensor] = None, margins: Optional[torch.Tensor] = None,
                 logits: Optional[torch.Tensor] = None, ws: Optional[torch.Tensor] = None,
-                out_offset: int = 0):
+                out_offset: int = 0, prenormed: bool = False):
         B = hidden.shape[0]
         if ws is None:
             ws = self._workspace(self.lib.md_lm_head_workspace_bytes(self.model, B))
         ids_ptr = ctypes.c_void_p(out_ids.data_ptr() + 4 * out_offset)
         mar_ptr = None if margins is None else ctypes.c_void_p(margins.data_ptr() + 4 * out_offset)
-        N.check(self.lib.md_lm_head_argmax(self.model, N.ptr(hidden), hidden.stride(0), B, mask_id, ids_ptr,
+        N.check(self.lib.md_lm_head_argmax(self.model, N.ptr(hidden), hidden.stride(0), int(prenormed), B, mask_id, ids_ptr,
                                            out_stride, N.ptr(out_index), mar_ptr, N.ptr(logits), N.ptr(ws),
                                            N.current_stream()), "md_lm_head_argmax")
 
@@ -324,6 +353,7 @@ class Engine:
             dev = self.device
             st = {
                 "x": torch.empty((B, t.dim), dtype=torch.bfloat16, device=dev),
+                "normed": torch.empty((B, t.dim), dtype=torch.bfloat16, device=dev),
                 "pos": torch.zeros(B, dtype=torch.int32, device=dev),
                 "cur": torch.zeros(B, dtype=torch.int32, device=dev),
                 "step": torch.zeros(1, dtype=torch.int32, device=dev),
@@ -346,10 +376,10 @@ class Engine:
         kv = self._kv(st["bt"])
         self.embed(st["cur"], st["x"])
         N.check(lib.md_text_decode_step(self.model, N.ptr(st["x"]), N.ptr(st["pos"]), B, ctypes.byref(kv),
-                                        N.ptr(st["ws"]), s), "md_text_decode_step")
+                                        N.ptr(st["normed"]), N.ptr(st["ws"]), s), "md_text_decode_step")
         off = int(lib.md_text_decode_workspace_bytes(self.model, B))
-        self.lm_head(st["x"], st["preds"], S, mask_id=mask_id, out_index=st["step"], margins=st["margins"],
-                     ws=st["ws"][off:], out_offset=1)
+        self.lm_head(st["normed"], st["preds"], S, mask_id=mask_id, out_index=st["step"], margins=st["margins"],
+                     ws=st["ws"][off:], out_offset=1, prenormed=True)
         N.check(lib.md_decode_advance(N.ptr(st["cur"]), N.ptr(st["pos"]), N.ptr(st["step"]), N.ptr(st["preds"]),
                                       N.ptr(st["forced"]) if use_forced else None, S, B,
                                       self.cfg.tokenizer.eos_id, N.ptr(st["finished"]), s), "md_decode_advance")
@@ -492,7 +522,7 @@ class Engine:
 
             def step(emb):
                 N.check(self.lib.md_text_decode_step(self.model, N.ptr(emb), N.ptr(pos), B, ctypes.byref(kv),
-                                                     N.ptr(ws), N.current_stream()), "md_text_decode_step")
+                                                     None, N.ptr(ws), N.current_stream()), "md_text_decode_step")
                 pos.add_(1)
                 return emb
 

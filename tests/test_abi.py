@@ -38,7 +38,7 @@ def test_binding_table_matches_header():
 def test_struct_layouts():
     from moondream_b200 import _native as N
 
-    assert ctypes.sizeof(N.md_dims) == 22 * 4
+    assert ctypes.sizeof(N.md_dims) == 23 * 4
     assert ctypes.sizeof(N.md_kv) == 32          # ptr, int(+pad), ptr, int(+pad)
 
 
