@@ -43,6 +43,9 @@ void md_reset_launch_count(void);
  * (2*M*N*K) and launch count.  md_profile_linear_read synchronises on the recorded events. */
 void md_profile_linear(int enable);
 int md_profile_linear_read(double* total_ms, double* total_flops, long long* launches);
+/* Testing / A-B timing only: 0 = automatic tile choice, 1 = single-CTA tiles, 2 = CTA-pair (cta_group::2)
+ * tiles wherever the shape allows. */
+void md_debug_force_cta_group(int cta_group);
 
 /* ------------------------------------------------------------------------------------------------
  * Operator level

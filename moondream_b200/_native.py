@@ -37,6 +37,7 @@ _SIGNATURES = {
     "md_launch_count": (c_longlong, []),
     "md_reset_launch_count": (None, []),
     "md_profile_linear": (None, [c_int]),
+    "md_debug_force_cta_group": (None, [c_int]),
     "md_profile_linear_read": (c_int, [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double),
                                        ctypes.POINTER(c_longlong)]),
     "md_linear_bf16": (c_int, [_P, _LL, _P, _LL, c_int, c_int, c_int, c_int, _P, _P, _LL, c_int, _P, _LL,

@@ -35,6 +35,7 @@ long long md_launch_count(void) { return md::launch_count(); }
 void md_reset_launch_count(void) { md::reset_launch_count(); }
 int md_abi_version(void) { return MD_ABI_VERSION; }
 void md_profile_linear(int enable) { md::gemm_profile_enable(enable); }
+void md_debug_force_cta_group(int cta_group) { md::gemm_force_cta_group(cta_group); }
 int md_profile_linear_read(double* total_ms, double* total_flops, long long* launches) {
   NEED(total_ms && total_flops && launches, "md_profile_linear_read");
   return md::gemm_profile_read(total_ms, total_flops, launches);

@@ -25,11 +25,12 @@ namespace md {
 
 constexpr int BM = 128;
 constexpr int BK = 64;
-constexpr int kGemmThreads = 256;
+constexpr int kEpiWarps = 8;                        // two warps per TMEM lane quadrant
+constexpr int kGemmThreads = 128 + kEpiWarps * 32;  // producer, MMA, TMEM-alloc, spare + epilogue
 
 struct GemmParams {
   int M, N, K;
-  int m_blocks, n_blocks, k_blocks;   // k_blocks = ceil(K / BK)
+  int m_blocks, n_blocks, k_blocks;   // m_blocks counts (BM * CG)-row tiles; k_blocks = ceil(K / BK)
   int k_splits;                        // >1 only in swapped form
   int kb_per_split;                    // k-blocks owned by each split (last one may be shorter)
   int mode;                            // EPI_* (row form) or EPI_PARTIAL (swapped form)
@@ -45,22 +46,26 @@ struct GemmParams {
   float* ws;                           // [k_splits][N][M] fp32
 };
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int CG>
 struct GemmSmem {
   static constexpr int kABytes = BM * BK * 2;
-  static constexpr int kBBytes = BN * BK * 2;
+  static constexpr int kBBytes = (BN / CG) * BK * 2;   // a CTA pair splits the B tile between its CTAs
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kBarOffset = STAGES * kStageBytes;
   static constexpr int kTotal = kBarOffset + (2 * STAGES + 4) * 8 + 16 + 1024;  // +1024 align slack
 };
 
-template <int BN, int STAGES>
+// CG = 1: one CTA per 128 x BN tile.  CG = 2: a CTA pair (cluster of 2, cta_group::2) per 256 x BN
+// tile; each CTA stages its own 128 rows of A and half of the B tile, the leader issues the MMAs,
+// each CTA's TMEM holds the accumulator rows it will write.
+template <int BN, int STAGES, int CG>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const GemmParams p) {
-  using S = GemmSmem<BN, STAGES>;
+  using S = GemmSmem<BN, STAGES, CG>;
   constexpr uint32_t kTmemCols = (2 * BN < 32) ? 32 : 2 * BN;  // power of two for BN in {32..256}
   static_assert(BN == 32 || BN == 64 || BN == 128 || BN == 256, "BN must be a power of two");
+  static_assert(CG == 1 || CG == 2, "cta group");
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -73,6 +78,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const int rank = (CG == 2) ? static_cast<int>(cluster_ctarank()) : 0;
+  const bool leader = rank == 0;
 
   if (warp == 0 && lane == 0) {
     prefetch_tensormap(&tmA);
@@ -80,58 +87,68 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < STAGES; ++i) {
-      mbar_init(&full_bar[i], 1);
+      mbar_init(&full_bar[i], CG);            // pair: the leader's barrier collects both producers
       mbar_init(&empty_bar[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 128);
+      mbar_init(&tmem_empty[i], kEpiWarps * 32 * CG);
     }
     fence_barrier_init();
   }
   if (warp == 2) {
-    tmem_alloc(tmem_ptr_smem, kTmemCols);
-    tmem_relinquish();
+    if (CG == 2) { tmem_alloc_pair(tmem_ptr_smem, kTmemCols); tmem_relinquish_pair(); }
+    else { tmem_alloc(tmem_ptr_smem, kTmemCols); tmem_relinquish(); }
   }
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
   const int total_tiles = p.m_blocks * p.n_blocks * p.k_splits;
   const int kb_per_split = p.kb_per_split;
+  const int unit = blockIdx.x / CG, n_units = gridDim.x / CG;
 
   if (warp == 0) {
     // ------------------------------ TMA producer ------------------------------
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile = unit; tile < total_tiles; tile += n_units) {
         const int split = tile % p.k_splits;
         const int t2 = tile / p.k_splits;
         const int n_blk = t2 % p.n_blocks;
         const int m_blk = t2 / p.n_blocks;
         const int kb0 = split * kb_per_split;
         const int kb1 = min(p.k_blocks, kb0 + kb_per_split);
+        const int a_row = m_blk * (BM * CG) + rank * BM;
+        const int b_row = n_blk * BN + rank * (BN / CG);
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * S::kStageBytes;
           uint8_t* sb = sa + S::kABytes;
-          mbar_arrive_expect_tx(&full_bar[stage], S::kStageBytes);
-          tma_load_2d(sa, &tmA, &full_bar[stage], kb * BK, m_blk * BM);
-          tma_load_2d(sb, &tmB, &full_bar[stage], kb * BK, n_blk * BN);
+          if (CG == 2) {
+            if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * S::kStageBytes);
+            else mbar_arrive_leader(&full_bar[stage]);
+            tma_load_2d_pair(sa, &tmA, &full_bar[stage], kb * BK, a_row);
+            tma_load_2d_pair(sb, &tmB, &full_bar[stage], kb * BK, b_row);
+          } else {
+            mbar_arrive_expect_tx(&full_bar[stage], S::kStageBytes);
+            tma_load_2d(sa, &tmA, &full_bar[stage], kb * BK, a_row);
+            tma_load_2d(sb, &tmB, &full_bar[stage], kb * BK, b_row);
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    // ------------------------------ MMA issuer ------------------------------
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16_f32(BM, BN);
+    // ------------------------------ MMA issuer (leader CTA only) ------------------------------
+    if (lane == 0 && leader) {
+      constexpr uint32_t idesc = make_idesc_bf16_f32(BM * CG, BN);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      for (int tile = unit; tile < total_tiles; tile += n_units, ++it) {
         const int split = tile % p.k_splits;
         const int kb0 = split * kb_per_split;
         const int kb1 = min(p.k_blocks, kb0 + kb_per_split);
@@ -150,43 +167,60 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             // advance 16 elements (32 B) along K inside the 128-byte swizzle row: +2 in 16-B units
-            umma_bf16(tmem_d, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k),
-                      idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            const uint32_t acc = (kb > kb0 || k > 0) ? 1u : 0u;
+            if (CG == 2) umma_bf16_pair(tmem_d, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k), idesc, acc);
+            else umma_bf16(tmem_d, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k), idesc, acc);
           }
-          umma_commit(&empty_bar[stage]);   // smem slot reusable once these MMAs have read it
+          // smem slot reusable (in both CTAs of a pair) once these MMAs have read it
+          if (CG == 2) umma_commit_pair(&empty_bar[stage]); else umma_commit(&empty_bar[stage]);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tmem_full[as]);        // accumulator complete
+        if (CG == 2) umma_commit_pair(&tmem_full[as]); else umma_commit(&tmem_full[as]);   // accumulator complete
       }
     }
   } else if (warp >= 4) {
     // ------------------------------ epilogue ------------------------------
     const int q = warp & 3;                 // TMEM lane quadrant this warp may read
+    const int half = (warp - 4) >> 2;       // the two warps of a quadrant interleave 32-column chunks
     int it = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+    for (int tile = unit; tile < total_tiles; tile += n_units, ++it) {
       const int split = tile % p.k_splits;
       const int t2 = tile / p.k_splits;
       const int n_blk = t2 % p.n_blocks;
       const int m_blk = t2 / p.n_blocks;
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
-      mbar_wait(&tmem_full[as], aphase);
-      tc_fence_after();
-      const int row = m_blk * BM + q * 32 + lane;          // accumulator row of this thread
+      const int row = m_blk * (BM * CG) + rank * BM + q * 32 + lane;   // accumulator row of this thread
       const bool row_ok = row < p.M;
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
-                             static_cast<uint32_t>(as * BN);
-
       long long out_row = row;
       if (p.remap_gin > 0)
         out_row = static_cast<long long>(row / p.remap_gin) * p.remap_gout + row % p.remap_gin +
                   p.remap_goff;
       const int res_row = (p.res_mod > 0) ? (row % p.res_mod) : row;
+      const bool use_res = p.mode == EPI_BIAS_RESIDUAL && row_ok;
+      const __nv_bfloat16* rbase = use_res ? p.res + static_cast<long long>(res_row) * p.ldr : nullptr;
+
+      // the residual does not depend on the accumulator: fetch the first chunk before waiting for the MMAs
+      uint4 rq[4], rq_next[4];
+      auto load_res = [&](int cc, uint4 (&dst)[4]) {
+        const int c0 = n_blk * BN + cc * 32;
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+          dst[g] = (use_res && cc < BN / 32 && c0 + g * 8 < p.N)
+                       ? *reinterpret_cast<const uint4*>(rbase + c0 + g * 8) : make_uint4(0, 0, 0, 0);
+      };
+      load_res(half, rq);
+
+      mbar_wait(&tmem_full[as], aphase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
+                             static_cast<uint32_t>(as * BN);
 
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = half; c < BN / 32; c += 2) {
         uint32_t acc[32];
         tmem_ld_32x32(taddr + static_cast<uint32_t>(c * 32), acc);
+        load_res(c + 2, rq_next);
         tmem_ld_wait();
         const int col0 = n_blk * BN + c * 32;
         if (p.mode == EPI_PARTIAL) {
@@ -199,52 +233,53 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
           continue;
         }
-        if (!row_ok || col0 >= p.N) continue;
-        __nv_bfloat16* optr = p.out + out_row * p.ldo + col0;
-        const __nv_bfloat16* rptr = p.res ? p.res + static_cast<long long>(res_row) * p.ldr + col0 : nullptr;
+        if (row_ok && col0 < p.N) {
+          __nv_bfloat16* optr = p.out + out_row * p.ldo + col0;
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {          // 4 groups of 8 columns = 16-byte stores
-          if (col0 + g * 8 >= p.N) break;       // N is a multiple of 8 (checked on the host)
-          float v[8];
-          uint4 bq = make_uint4(0, 0, 0, 0);
-          if (p.bias) bq = *reinterpret_cast<const uint4*>(p.bias + col0 + g * 8);
-          const uint32_t bw[4] = {bq.x, bq.y, bq.z, bq.w};
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            // the reference rounds the Linear output to bf16 before anything else touches it
-            v[2 * j] = bf16_round(__uint_as_float(acc[g * 8 + 2 * j]) + bf16_lo(bw[j]));
-            v[2 * j + 1] = bf16_round(__uint_as_float(acc[g * 8 + 2 * j + 1]) + bf16_hi(bw[j]));
-          }
-          if (p.mode == EPI_BIAS_GELU) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = gelu_tanh(v[j]);
-          } else if (p.mode == EPI_BIAS_RESIDUAL) {
-            const uint4 rq = *reinterpret_cast<const uint4*>(rptr + g * 8);
-            const uint32_t rw[4] = {rq.x, rq.y, rq.z, rq.w};
+          for (int g = 0; g < 4; ++g) {          // 4 groups of 8 columns = 16-byte stores
+            if (col0 + g * 8 >= p.N) break;       // N is a multiple of 8 (checked on the host)
+            float v[8];
+            uint4 bq = make_uint4(0, 0, 0, 0);
+            if (p.bias) bq = *reinterpret_cast<const uint4*>(p.bias + col0 + g * 8);
+            const uint32_t bw[4] = {bq.x, bq.y, bq.z, bq.w};
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              v[2 * j] += bf16_lo(rw[j]);
-              v[2 * j + 1] += bf16_hi(rw[j]);
+              // the reference rounds the Linear output to bf16 before anything else touches it
+              v[2 * j] = bf16_round(__uint_as_float(acc[g * 8 + 2 * j]) + bf16_lo(bw[j]));
+              v[2 * j + 1] = bf16_round(__uint_as_float(acc[g * 8 + 2 * j + 1]) + bf16_hi(bw[j]));
             }
+            if (p.mode == EPI_BIAS_GELU) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[j] = gelu_tanh(v[j]);
+            } else if (p.mode == EPI_BIAS_RESIDUAL) {
+              const uint32_t rw[4] = {rq[g].x, rq[g].y, rq[g].z, rq[g].w};
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                v[2 * j] += bf16_lo(rw[j]);
+                v[2 * j + 1] += bf16_hi(rw[j]);
+              }
+            }
+            uint4 o;
+            o.x = pack_bf16x2(v[0], v[1]);
+            o.y = pack_bf16x2(v[2], v[3]);
+            o.z = pack_bf16x2(v[4], v[5]);
+            o.w = pack_bf16x2(v[6], v[7]);
+            *reinterpret_cast<uint4*>(optr + g * 8) = o;
           }
-          uint4 o;
-          o.x = pack_bf16x2(v[0], v[1]);
-          o.y = pack_bf16x2(v[2], v[3]);
-          o.z = pack_bf16x2(v[4], v[5]);
-          o.w = pack_bf16x2(v[6], v[7]);
-          *reinterpret_cast<uint4*>(optr + g * 8) = o;
         }
+#pragma unroll
+        for (int g = 0; g < 4; ++g) rq[g] = rq_next[g];
       }
       tc_fence_before();
-      mbar_arrive(&tmem_empty[as]);
+      if (CG == 2) mbar_arrive_leader(&tmem_empty[as]); else mbar_arrive(&tmem_empty[as]);
     }
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, kTmemCols);
+    if (CG == 2) tmem_dealloc_pair(tmem_base, kTmemCols); else tmem_dealloc(tmem_base, kTmemCols);
   }
 }
 
@@ -366,33 +401,54 @@ int num_sms() {
   return g_num_sms;
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int CG>
 static int launch_gemm(const CUtensorMap& tA, const CUtensorMap& tB, const GemmParams& p,
                        cudaStream_t stream) {
-  using S = GemmSmem<BN, STAGES>;
+  using S = GemmSmem<BN, STAGES, CG>;
+  static_assert(S::kTotal <= 227 * 1024, "shared memory budget");
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_kernel<BN, STAGES>,
+    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_kernel<BN, STAGES, CG>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal);
     if (e != cudaSuccess) return set_error(cudaGetErrorString(e));
     configured = true;
   }
   const int total = p.m_blocks * p.n_blocks * p.k_splits;
-  const int grid = total < num_sms() ? total : num_sms();
-  gemm_bf16_kernel<BN, STAGES><<<grid, kGemmThreads, S::kTotal, stream>>>(tA, tB, p);
+  const int max_units = num_sms() / CG;
+  const int units = total < max_units ? total : max_units;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(units * CG);
+  cfg.blockDim = dim3(kGemmThreads);
+  cfg.dynamicSmemBytes = S::kTotal;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_bf16_kernel<BN, STAGES, CG>, tA, tB, p);
   count_launch();
-  cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(cudaGetErrorString(e));
   return 0;
 }
 
-static int dispatch_gemm(int bn, const CUtensorMap& tA, const CUtensorMap& tB, const GemmParams& p,
+static int g_force_cg = 0;   // 0 = auto, 1 / 2 = force (tests and A/B timing)
+void gemm_force_cta_group(int cg) { g_force_cg = cg; }
+
+// bn: B-tile rows; cg: CTAs per tile
+static int dispatch_gemm(int bn, int cg, const CUtensorMap& tA, const CUtensorMap& tB, const GemmParams& p,
                          cudaStream_t stream) {
+  if (cg == 2) {
+    if (bn == 256) return launch_gemm<256, 6, 2>(tA, tB, p, stream);
+    return set_error("pair GEMM needs BN = 256");
+  }
   switch (bn) {
-    case 256: return launch_gemm<256, 4>(tA, tB, p, stream);
-    case 128: return launch_gemm<128, 6>(tA, tB, p, stream);
-    case 64: return launch_gemm<64, 8>(tA, tB, p, stream);
-    case 32: return launch_gemm<32, 10>(tA, tB, p, stream);
+    case 256: return launch_gemm<256, 4, 1>(tA, tB, p, stream);
+    case 128: return launch_gemm<128, 6, 1>(tA, tB, p, stream);
+    case 64: return launch_gemm<64, 8, 1>(tA, tB, p, stream);
+    case 32: return launch_gemm<32, 10, 1>(tA, tB, p, stream);
   }
   return set_error("unsupported BN");
 }
@@ -414,12 +470,15 @@ int gemm_rowform(const __nv_bfloat16* A, long long lda, const __nv_bfloat16* W, 
   if (mode == EPI_BIAS_RESIDUAL && !res) return set_error("gemm: residual mode without residual");
   if ((ldo % 8) || (res && (ldr % 8))) return set_error("gemm: ldo/ldr must be multiples of 8");
   const int bn = pick_bn_rows(N);
+  int cg = (bn == 256 && M > BM) ? 2 : 1;          // CTA pairs for the large prefill / ViT GEMMs
+  if (g_force_cg == 1) cg = 1;
+  if (g_force_cg == 2 && bn == 256) cg = 2;
   CUtensorMap tA, tB;
   if (make_tmap_bf16_2d(&tA, A, M, K, lda, BM)) return 1;
-  if (make_tmap_bf16_2d(&tB, W, N, K, ldw, bn)) return 1;
+  if (make_tmap_bf16_2d(&tB, W, N, K, ldw, bn / cg)) return 1;
   GemmParams p{};
   p.M = M; p.N = N; p.K = K;
-  p.m_blocks = (M + BM - 1) / BM;
+  p.m_blocks = (M + BM * cg - 1) / (BM * cg);
   p.n_blocks = (N + bn - 1) / bn;
   p.k_blocks = (K + BK - 1) / BK;
   p.k_splits = 1;
@@ -432,7 +491,7 @@ int gemm_rowform(const __nv_bfloat16* A, long long lda, const __nv_bfloat16* W, 
   const bool prof = g_prof.on && cudaStreamIsCapturing(stream, &cap) == cudaSuccess &&
                     cap == cudaStreamCaptureStatusNone;
   if (prof) cudaEventRecord(profile_event(), stream);
-  const int rc = dispatch_gemm(bn, tA, tB, p, stream);
+  const int rc = dispatch_gemm(bn, cg, tA, tB, p, stream);
   if (prof) {
     cudaEventRecord(profile_event(), stream);
     g_prof.flops += 2.0 * M * static_cast<double>(N) * K;
@@ -473,7 +532,7 @@ static int gemm_swapped_impl(const __nv_bfloat16* W, long long ldw, const __nv_b
   p.k_splits = (p.k_blocks + kb_per_split - 1) / kb_per_split;   // every split owns >= 1 k-block
   p.mode = EPI_PARTIAL;
   p.ws = ws;
-  const int rc = dispatch_gemm(bn, tA, tB, p, stream);
+  const int rc = dispatch_gemm(bn, 1, tA, tB, p, stream);
   return rc ? -1 : p.k_splits;
 }
 

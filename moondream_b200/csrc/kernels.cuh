@@ -30,6 +30,7 @@ int gemm_rowform(const __nv_bfloat16* A, long long lda, const __nv_bfloat16* W, 
                  int N, int K, int mode, const __nv_bfloat16* bias, const __nv_bfloat16* res,
                  long long ldr, int res_mod, __nv_bfloat16* out, long long ldo, int remap_gin,
                  int remap_gout, int remap_goff, cudaStream_t stream);
+void gemm_force_cta_group(int cg);
 void gemm_profile_enable(int on);
 int gemm_profile_read(double* total_ms, double* total_flops, long long* launches);
 int gemm_swapped_splits(int n_out, int K);

@@ -38,9 +38,19 @@ SHAPES = [
 ]
 
 
+@pytest.fixture(params=[1, 2], ids=["cta1", "ctapair"])
+def cta_group(request):
+    """run every row-form case with single-CTA tiles and with cta_group::2 pairs (where BN = 256)"""
+    from moondream_b200 import _native as N
+
+    N.lib().md_debug_force_cta_group(request.param)
+    yield request.param
+    N.lib().md_debug_force_cta_group(0)
+
+
 @pytest.mark.parametrize("M,N,K", SHAPES)
 @pytest.mark.parametrize("mode", [0, 1, 2])
-def test_linear_rowform(M, N, K, mode):
+def test_linear_rowform(M, N, K, mode, cta_group):
     from moondream_b200 import ops
 
     g = torch.Generator(device="cuda").manual_seed(M * 7 + N * 3 + K + mode)
@@ -53,7 +63,7 @@ def test_linear_rowform(M, N, K, mode):
     _close(y, _ref(x, w, b, mode, res), f"linear {M}x{N}x{K} mode {mode}")
 
 
-def test_linear_posemb_broadcast_and_remap():
+def test_linear_posemb_broadcast_and_remap(cta_group):
     from moondream_b200 import ops
 
     g = torch.Generator(device="cuda").manual_seed(5)
@@ -72,7 +82,7 @@ def test_linear_posemb_broadcast_and_remap():
     assert got[:, 0].abs().max().item() == 0
 
 
-def test_linear_strided_views():
+def test_linear_strided_views(cta_group):
     from moondream_b200 import ops
 
     g = torch.Generator(device="cuda").manual_seed(9)

@@ -32,10 +32,16 @@ def main():
         b = torch.randn(N, device="cuda").bfloat16()
         r = torch.randn(M, N, device="cuda").bfloat16()
         y = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
-        ms = timeit(lambda: ops.linear(x, w, b, epilogue=mode, residual=r if mode == 2 else None, out=y))
+        from moondream_b200 import _native as N_
+        res = {}
+        for cg in (1, 2):
+            N_.lib().md_debug_force_cta_group(cg)
+            res[cg] = timeit(lambda: ops.linear(x, w, b, epilogue=mode, residual=r if mode == 2 else None, out=y))
+        N_.lib().md_debug_force_cta_group(0)
         ms_t = timeit(lambda: torch.nn.functional.linear(x, w, b))
-        out.append({"M": M, "N": N, "K": K, "mode": mode, "ms": ms, "tflops": 2 * M * N * K / ms / 1e9,
-                    "torch_ms": ms_t, "torch_tflops": 2 * M * N * K / ms_t / 1e9})
+        fl = 2 * M * N * K / 1e9
+        out.append({"M": M, "N": N, "K": K, "mode": mode, "cta1_tflops": fl / res[1], "ctapair_tflops": fl / res[2],
+                    "torch_tflops": fl / ms_t})
         print(out[-1], flush=True)
     for (B, N, K) in [(32, 6144, 2048), (32, 2048, 2048), (32, 8192, 2048), (32, 2048, 8192),
                       (32, 51200, 2048), (128, 3072, 1024)]:
