@@ -296,66 +296,124 @@ int rope_kv_write(const __nv_bfloat16* qkv, int n_tokens, int n_heads, const int
 // (torch.argmax).  `mask_id` >= 0 is forced to -inf (answer_id from the 2nd generated token on).
 // Optionally writes the top1 - top2 margin and the bf16-rounded logits.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024)
-argmax_kernel(const float* __restrict__ ws, int splits, int B, int V,
-              const __nv_bfloat16* __restrict__ bias, int bias_period, int mask_id,
-              int* __restrict__ out_ids, long long out_stride, const int* __restrict__ out_index,
-              float* __restrict__ out_margin, __nv_bfloat16* __restrict__ out_logits) {
-  const int b = blockIdx.x;
+struct ArgTop {
+  float best, second;
+  int idx;
+};
+__device__ __forceinline__ void argtop_merge(ArgTop& a, float ob, float os, int oi) {
+  // value descending, index ascending (torch.argmax returns the first maximum)
+  if (ob > a.best || (ob == a.best && oi < a.idx)) { a.second = fmaxf(a.best, os); a.best = ob; a.idx = oi; }
+  else a.second = fmaxf(a.second, ob);
+}
+__device__ __forceinline__ ArgTop argtop_block_reduce(ArgTop t, float* sb, float* ss, int* si) {
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ob = __shfl_xor_sync(0xffffffffu, t.best, o);
+    const float os = __shfl_xor_sync(0xffffffffu, t.second, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, t.idx, o);
+    argtop_merge(t, ob, os, oi);
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { sb[warp] = t.best; ss[warp] = t.second; si[warp] = t.idx; }
+  __syncthreads();
+  if (warp == 0) {
+    const int nw = blockDim.x >> 5;
+    t.best = lane < nw ? sb[lane] : -INFINITY;
+    t.second = lane < nw ? ss[lane] : -INFINITY;
+    t.idx = lane < nw ? si[lane] : 0x7fffffff;
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ob = __shfl_xor_sync(0xffffffffu, t.best, o);
+      const float os = __shfl_xor_sync(0xffffffffu, t.second, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, t.idx, o);
+      argtop_merge(t, ob, os, oi);
+    }
+  }
+  return t;   // valid in warp 0
+}
+
+// stage 1: block (part, b) scans vocabulary slice `part` of row b.  parts == 1 writes the result directly.
+__global__ void __launch_bounds__(512)
+argmax_partial_kernel(const float* __restrict__ ws, int splits, int B, int V, int parts,
+                      const __nv_bfloat16* __restrict__ bias, int bias_period, int mask_id,
+                      float* __restrict__ part_best, float* __restrict__ part_second, int* __restrict__ part_idx,
+                      int* __restrict__ out_ids, long long out_stride, const int* __restrict__ out_index,
+                      float* __restrict__ out_margin, __nv_bfloat16* __restrict__ out_logits) {
+  const int part = blockIdx.x, b = blockIdx.y;
+  const int per = (V + parts - 1) / parts;
+  const int v0 = part * per, v1 = min(V, v0 + per);
   const __nv_bfloat16* brow = bias ? bias + static_cast<long long>(b % bias_period) * V : nullptr;
-  float best = -INFINITY, second = -INFINITY;
-  int best_i = 0x7fffffff;
-  for (int v = threadIdx.x; v < V; v += blockDim.x) {
+  ArgTop t{-INFINITY, -INFINITY, 0x7fffffff};
+  for (int v = v0 + threadIdx.x; v < v1; v += blockDim.x) {
     float a = 0.f;
     for (int s = 0; s < splits; ++s) a += ws[(static_cast<long long>(s) * B + b) * V + v];
     if (brow) a += __bfloat162float(brow[v]);
     a = bf16_round(a);
     if (v == mask_id) a = -INFINITY;
     if (out_logits) out_logits[static_cast<long long>(b) * V + v] = __float2bfloat16_rn(a);
-    if (a > best) { second = best; best = a; best_i = v; }
-    else if (a > second) second = a;
-  }
-  // warp reduce (value desc, index asc)
-  for (int o = 16; o > 0; o >>= 1) {
-    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
-    const float os = __shfl_xor_sync(0xffffffffu, second, o);
-    const int oi = __shfl_xor_sync(0xffffffffu, best_i, o);
-    if (ob > best || (ob == best && oi < best_i)) { second = fmaxf(best, os); best = ob; best_i = oi; }
-    else second = fmaxf(second, ob);
+    if (a > t.best) { t.second = t.best; t.best = a; t.idx = v; }
+    else if (a > t.second) t.second = a;
   }
   __shared__ float sb[32], ss[32];
   __shared__ int si[32];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (lane == 0) { sb[warp] = best; ss[warp] = second; si[warp] = best_i; }
-  __syncthreads();
-  if (warp == 0) {
-    const int nw = blockDim.x >> 5;
-    best = lane < nw ? sb[lane] : -INFINITY;
-    second = lane < nw ? ss[lane] : -INFINITY;
-    best_i = lane < nw ? si[lane] : 0x7fffffff;
-    for (int o = 16; o > 0; o >>= 1) {
-      const float ob = __shfl_xor_sync(0xffffffffu, best, o);
-      const float os = __shfl_xor_sync(0xffffffffu, second, o);
-      const int oi = __shfl_xor_sync(0xffffffffu, best_i, o);
-      if (ob > best || (ob == best && oi < best_i)) { second = fmaxf(best, os); best = ob; best_i = oi; }
-      else second = fmaxf(second, ob);
-    }
-    if (lane == 0) {
+  t = argtop_block_reduce(t, sb, ss, si);
+  if (threadIdx.x == 0) {
+    if (parts == 1) {
       const long long at = static_cast<long long>(b) * out_stride + (out_index ? *out_index : 0);
-      out_ids[at] = best_i;
-      if (out_margin) out_margin[at] = best - second;
+      out_ids[at] = t.idx;
+      if (out_margin) out_margin[at] = t.best - t.second;
+    } else {
+      part_best[b * parts + part] = t.best;
+      part_second[b * parts + part] = t.second;
+      part_idx[b * parts + part] = t.idx;
     }
   }
 }
 
+// stage 2: one warp per row merges the slices (slices are visited in index order, ties keep the lowest)
+__global__ void __launch_bounds__(128)
+argmax_final_kernel(const float* __restrict__ part_best, const float* __restrict__ part_second,
+                    const int* __restrict__ part_idx, int B, int parts, int* __restrict__ out_ids,
+                    long long out_stride, const int* __restrict__ out_index, float* __restrict__ out_margin) {
+  const int b = blockIdx.x * 4 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (b >= B) return;
+  ArgTop t{-INFINITY, -INFINITY, 0x7fffffff};
+  for (int p = lane; p < parts; p += 32)
+    argtop_merge(t, part_best[b * parts + p], part_second[b * parts + p], part_idx[b * parts + p]);
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ob = __shfl_xor_sync(0xffffffffu, t.best, o);
+    const float os = __shfl_xor_sync(0xffffffffu, t.second, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, t.idx, o);
+    argtop_merge(t, ob, os, oi);
+  }
+  if (lane == 0) {
+    const long long at = static_cast<long long>(b) * out_stride + (out_index ? *out_index : 0);
+    out_ids[at] = t.idx;
+    if (out_margin) out_margin[at] = t.best - t.second;
+  }
+}
+
+constexpr int kArgmaxMaxParts = 16;
+long long argmax_scratch_floats(int B) { return 3LL * B * kArgmaxMaxParts; }
+
 int argmax_logits(const float* ws, int splits, int B, int V, const __nv_bfloat16* bias, int bias_period,
                   int mask_id, int* out_ids, long long out_stride, const int* out_index,
-                  float* out_margin, __nv_bfloat16* out_logits, cudaStream_t stream) {
+                  float* out_margin, __nv_bfloat16* out_logits, float* scratch, cudaStream_t stream) {
   if (B <= 0 || V <= 0) return set_error("argmax_logits: empty input");
   if (bias_period < 1) bias_period = 1;
-  argmax_kernel<<<B, 1024, 0, stream>>>(ws, splits, B, V, bias, bias_period, mask_id, out_ids, out_stride,
-                                        out_index, out_margin, out_logits);
+  int parts = V >= 8192 ? kArgmaxMaxParts : 1;
+  if (!scratch) parts = 1;
+  float* pb = scratch;
+  float* ps = scratch ? scratch + 1LL * B * kArgmaxMaxParts : nullptr;
+  int* pi = scratch ? reinterpret_cast<int*>(scratch + 2LL * B * kArgmaxMaxParts) : nullptr;
+  argmax_partial_kernel<<<dim3(parts, B), 512, 0, stream>>>(ws, splits, B, V, parts, bias, bias_period, mask_id,
+                                                           pb, ps, pi, out_ids, out_stride, out_index,
+                                                           out_margin, out_logits);
   MD_CHECK_LAUNCH();
+  if (parts > 1) {
+    argmax_final_kernel<<<(B + 3) / 4, 128, 0, stream>>>(pb, ps, pi, B, parts, out_ids, out_stride, out_index,
+                                                        out_margin);
+    MD_CHECK_LAUNCH();
+  }
   return 0;
 }
 
@@ -535,54 +593,91 @@ decode_residual_ln_epilogue_kernel(const float* __restrict__ ws, int splits, int
                                    const __nv_bfloat16* __restrict__ bias_fc2, __nv_bfloat16* __restrict__ x,
                                    const __nv_bfloat16* __restrict__ ln_w, const __nv_bfloat16* __restrict__ ln_b,
                                    __nv_bfloat16* __restrict__ ln_out, float eps) {
-  constexpr int kMaxPer = 16;                          // D <= 256 * 16
+  constexpr int kMaxChunks = 2;                        // 8-element chunks per thread: D <= 4096
   const int b = blockIdx.x;
   const int tid = threadIdx.x;
-  float v[kMaxPer];
+  const int chunks = D >> 3;
+  float v[kMaxChunks][8];
   float sum = 0.f;
-  int n = 0;
-  for (int d = tid; d < D; d += 256, ++n) {
-    float a = 0.f, m = 0.f;
-    for (int s = 0; s < proj_splits; ++s) a += ws[(static_cast<long long>(s) * B + b) * D + d];
-    for (int s = proj_splits; s < splits; ++s) m += ws[(static_cast<long long>(s) * B + b) * D + d];
-    a = bf16_round(a + __bfloat162float(bias_proj[d]));
-    m = bf16_round(m + __bfloat162float(bias_fc2[d]));
-    float r = bf16_round(__bfloat162float(x[static_cast<long long>(b) * D + d]) + a);
-    r = bf16_round(r + m);
-    x[static_cast<long long>(b) * D + d] = __float2bfloat16_rn(r);
-    v[n] = r;
-    sum += r;
+#pragma unroll
+  for (int i = 0; i < kMaxChunks; ++i) {
+    const int c = tid + i * 256;
+    if (c >= chunks) continue;
+    const int d0 = c * 8;
+    float a[8], m[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a[k] = m[k] = 0.f;
+    // all loads of a thread are independent 16-byte reads: the split loop pipelines freely
+    for (int s = 0; s < splits; ++s) {
+      const float4* src = reinterpret_cast<const float4*>(ws + (static_cast<long long>(s) * B + b) * D + d0);
+      const float4 lo = src[0], hi = src[1];
+      float* dst = s < proj_splits ? a : m;
+      dst[0] += lo.x; dst[1] += lo.y; dst[2] += lo.z; dst[3] += lo.w;
+      dst[4] += hi.x; dst[5] += hi.y; dst[6] += hi.z; dst[7] += hi.w;
+    }
+    const uint4 bp = *reinterpret_cast<const uint4*>(bias_proj + d0);
+    const uint4 bf = *reinterpret_cast<const uint4*>(bias_fc2 + d0);
+    const uint4 xq = *reinterpret_cast<const uint4*>(x + static_cast<long long>(b) * D + d0);
+    const uint32_t bpw[4] = {bp.x, bp.y, bp.z, bp.w}, bfw[4] = {bf.x, bf.y, bf.z, bf.w}, xw[4] = {xq.x, xq.y, xq.z, xq.w};
+    uint32_t ow[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float a0 = bf16_round(a[2 * k] + bf16_lo(bpw[k])), a1 = bf16_round(a[2 * k + 1] + bf16_hi(bpw[k]));
+      const float m0 = bf16_round(m[2 * k] + bf16_lo(bfw[k])), m1 = bf16_round(m[2 * k + 1] + bf16_hi(bfw[k]));
+      const float r0 = bf16_round(bf16_round(bf16_lo(xw[k]) + a0) + m0);
+      const float r1 = bf16_round(bf16_round(bf16_hi(xw[k]) + a1) + m1);
+      v[i][2 * k] = r0; v[i][2 * k + 1] = r1;
+      sum += r0 + r1;
+      ow[k] = pack_bf16x2(r0, r1);
+    }
+    *reinterpret_cast<uint4*>(x + static_cast<long long>(b) * D + d0) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
   }
   __shared__ float red[8];
-  __shared__ float stat[2];
   auto block_sum = [&](float val) {
     for (int o = 16; o > 0; o >>= 1) val += __shfl_xor_sync(0xffffffffu, val, o);
     __syncthreads();
     if ((tid & 31) == 0) red[tid >> 5] = val;
     __syncthreads();
     float t = 0.f;
+#pragma unroll
     for (int i = 0; i < 8; ++i) t += red[i];
     return t;
   };
   const float mean = block_sum(sum) / D;
   float sq = 0.f;
-  for (int i = 0; i < n; ++i) sq += (v[i] - mean) * (v[i] - mean);
+#pragma unroll
+  for (int i = 0; i < kMaxChunks; ++i) {
+    if (tid + i * 256 >= chunks) continue;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) sq += (v[i][k] - mean) * (v[i][k] - mean);
+  }
   const float var = block_sum(sq) / D;
   const float rstd = 1.0f / sqrtf(var + eps);
   const float shift = -rstd * mean;
-  n = 0;
-  for (int d = tid; d < D; d += 256, ++n) {
-    const float y = (v[n] * rstd + shift) * __bfloat162float(ln_w[d]) + __bfloat162float(ln_b[d]);
-    ln_out[static_cast<long long>(b) * D + d] = __float2bfloat16_rn(y);
+#pragma unroll
+  for (int i = 0; i < kMaxChunks; ++i) {
+    const int c = tid + i * 256;
+    if (c >= chunks) continue;
+    const int d0 = c * 8;
+    const uint4 wq = *reinterpret_cast<const uint4*>(ln_w + d0);
+    const uint4 bq = *reinterpret_cast<const uint4*>(ln_b + d0);
+    const uint32_t ww[4] = {wq.x, wq.y, wq.z, wq.w}, bw[4] = {bq.x, bq.y, bq.z, bq.w};
+    uint32_t ow[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float y0 = (v[i][2 * k] * rstd + shift) * bf16_lo(ww[k]) + bf16_lo(bw[k]);
+      const float y1 = (v[i][2 * k + 1] * rstd + shift) * bf16_hi(ww[k]) + bf16_hi(bw[k]);
+      ow[k] = pack_bf16x2(y0, y1);
+    }
+    *reinterpret_cast<uint4*>(ln_out + static_cast<long long>(b) * D + d0) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
   }
-  (void)stat;
 }
 
 int decode_residual_ln_epilogue(const float* ws, int splits, int proj_splits, int B, int D,
                                 const __nv_bfloat16* bias_proj, const __nv_bfloat16* bias_fc2,
                                 __nv_bfloat16* x, const __nv_bfloat16* ln_w, const __nv_bfloat16* ln_b,
                                 __nv_bfloat16* ln_out, cudaStream_t stream) {
-  if (D > 256 * 16) return set_error("decode epilogue: dim too large");
+  if (D > 4096 || D % 8) return set_error("decode epilogue: dim must be a multiple of 8 and <= 4096");
   decode_residual_ln_epilogue_kernel<<<B, 256, 0, stream>>>(ws, splits, proj_splits, B, D, bias_proj,
                                                            bias_fc2, x, ln_w, ln_b, ln_out, 1e-5f);
   MD_CHECK_LAUNCH();

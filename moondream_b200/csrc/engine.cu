@@ -286,7 +286,8 @@ int text_decode_step(Model& m, bf16* x, const int* pos, int batch, const md_kv& 
 // LM head + argmax
 // ------------------------------------------------------------------------------------------------
 long long lm_head_ws_bytes(const Model& m, int batch) {
-  return pad256(1LL * batch * m.d.txt_dim * 2) + pad256(smallbatch_ws_floats(m, batch) * 4) + 4096;
+  return pad256(1LL * batch * m.d.txt_dim * 2) + pad256(smallbatch_ws_floats(m, batch) * 4) +
+         pad256(argmax_scratch_floats(batch) * 4) + 4096;
 }
 
 int lm_head_argmax(Model& m, const bf16* hidden, long long ldh, int prenormed, int batch, int mask_id,
@@ -296,7 +297,8 @@ int lm_head_argmax(Model& m, const bf16* hidden, long long ldh, int prenormed, i
   if (batch <= 0) return set_error("md_lm_head_argmax: empty batch");
   char* p = align_up(reinterpret_cast<char*>(ws));
   bf16* ln = reinterpret_cast<bf16*>(p); p += pad256(1LL * batch * d.txt_dim * 2);
-  float* wsf = reinterpret_cast<float*>(p);
+  float* wsf = reinterpret_cast<float*>(p); p += pad256(smallbatch_ws_floats(m, batch) * 4);
+  float* scratch = reinterpret_cast<float*>(p);
   const bf16* normed = hidden;
   long long ldn = ldh;
   if (!prenormed) {
@@ -308,7 +310,7 @@ int lm_head_argmax(Model& m, const bf16* hidden, long long ldh, int prenormed, i
                                 gemm_swapped_splits(d.vocab, d.txt_dim), wsf, st);
   if (used < 0) return 1;
   return argmax_logits(wsf, used, batch, d.vocab, m.lm_head.b, 1, mask_id, out_ids, out_stride, out_index,
-                       out_margin, out_logits, st);
+                       out_margin, out_logits, scratch, st);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -340,9 +342,9 @@ int region_decode(Model& m, int which, const bf16* hidden, long long ldh, int ba
                                 gemm_swapped_splits(n_out, d.reg_inner), wsf, st);
   if (used < 0) return 1;
   if (which == 0)
-    return argmax_logits(wsf, used, batch, n_out, l2.b, 1, -1, out_bins, 1, nullptr, nullptr, nullptr, st);
+    return argmax_logits(wsf, used, batch, n_out, l2.b, 1, -1, out_bins, 1, nullptr, nullptr, nullptr, nullptr, st);
   // size logits are viewed as (2, -1): rows 2b (width bins) and 2b+1 (height bins)
-  return argmax_logits(wsf, used, 2 * batch, n_out / 2, l2.b, 2, -1, out_bins, 1, nullptr, nullptr, nullptr, st);
+  return argmax_logits(wsf, used, 2 * batch, n_out / 2, l2.b, 2, -1, out_bins, 1, nullptr, nullptr, nullptr, nullptr, st);
 }
 
 int region_encode(Model& m, int which, const float* values, int batch, bf16* out, long long ldo, void* ws,

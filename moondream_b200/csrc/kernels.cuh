@@ -59,7 +59,8 @@ int rope_kv_write(const __nv_bfloat16* qkv, int n_tokens, int n_heads, const int
                   int layer, cudaStream_t stream);
 int argmax_logits(const float* ws, int splits, int B, int V, const __nv_bfloat16* bias, int bias_period,
                   int mask_id, int* out_ids, long long out_stride, const int* out_index,
-                  float* out_margin, __nv_bfloat16* out_logits, cudaStream_t stream);
+                  float* out_margin, __nv_bfloat16* out_logits, float* scratch, cudaStream_t stream);
+long long argmax_scratch_floats(int B);
 int decode_advance(int* cur_tok, int* pos, int* step, const int* preds, const int* forced,
                    long long stride, int batch, int eos_id, int* finished, cudaStream_t stream);
 int gather_rows(const __nv_bfloat16* src, long long ld_src, const int* idx, int n, int dim,

@@ -137,14 +137,22 @@ def test_rope_prefill_decode_attention():
         assert rel(out[s], ref) < 6e-3, (s, rel(out[s], ref))
 
 
-def test_small_batch_argmax_ties_and_mask():
-    """lm_head + argmax: ties resolve to the lowest index (torch.argmax), mask_id is excluded."""
+@pytest.mark.parametrize("vocab", [2048, 16384])
+def test_small_batch_argmax_ties_and_mask(vocab):
+    """lm_head + argmax: ties resolve to the lowest index (torch.argmax), mask_id is excluded.
+    vocab 16384 exercises the two-stage (sliced) argmax, 2048 the single-stage one."""
+    import dataclasses
+
     from moondream_b200 import config as C, synth
     from moondream_b200.engine import Engine
 
     cfg = C.tiny()
+    cfg = dataclasses.replace(cfg, text=dataclasses.replace(cfg.text, vocab_size=vocab))
     sd = synth.synthetic_state_dict(cfg, 0)
-    sd["text.lm_head.weight"][7] = sd["text.lm_head.weight"][5]       # rows 5 and 7 identical -> tie
+    hi = vocab - 3                                                       # a tie across argmax slices
+    sd["text.lm_head.weight"][hi] = sd["text.lm_head.weight"][5]       # rows 5 and hi identical -> tie
+    sd["text.lm_head.bias"][hi] = sd["text.lm_head.bias"][5]
+    sd["text.lm_head.weight"][7] = sd["text.lm_head.weight"][5]
     sd["text.lm_head.bias"][7] = sd["text.lm_head.bias"][5]
     eng = Engine(cfg, sd, max_batch=4)
     B = 6
@@ -158,7 +166,11 @@ def test_small_batch_argmax_ties_and_mask():
     ref = (ln.float() @ w["text.lm_head.weight"].float().t() + w["text.lm_head.bias"].float()).bfloat16()
     assert rel(logits, ref) < 1e-2
     assert torch.equal(ids.long(), torch.argmax(logits.float(), dim=-1))
-    assert torch.equal(logits[:, 5], logits[:, 7])
+    assert torch.equal(logits[:, 5], logits[:, 7]) and torch.equal(logits[:, 5], logits[:, hi])
+    # make the tied rows the winners for one sequence: the lowest index must be returned
+    h2 = w["text.lm_head.weight"][5:6].float().repeat(B, 1).bfloat16() * 4
+    eng.lm_head(h2, ids, 1, logits=logits, margins=mar)
+    assert torch.equal(ids.long(), torch.argmax(logits.float(), dim=-1))
     top2 = torch.topk(logits.float(), 2, dim=-1).values
     assert torch.allclose(mar, top2[:, 0] - top2[:, 1])
     best = ids.clone()
