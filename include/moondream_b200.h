@@ -96,6 +96,7 @@ typedef struct md_kv {
   int n_pages;
   const int* block_tables;
   int max_blocks;
+  int n_layers;            /* layers in the pool (bounds the TMA view of the pool) */
 } md_kv;
 
 /* Partial RoPE (first 32 of 64 dims, split-half in / interleaved out, rope.py:20-48) on q and k of
@@ -105,10 +106,14 @@ int md_rope_kv_write_bf16(const void* qkv, int n_tokens, int n_heads, const int*
                           const int* start_pos, int n_seqs, const float* rope_table, void* q_out,
                           const md_kv* kv, int layer, void* stream);
 
-/* Prefix-LM attention for prefill (text.py:46-50 under the mask of moondream.py:138-146). */
-int md_prefill_attention_bf16(const void* q, int n_heads, const int* q_offsets, const int* start_pos,
-                              int n_seqs, int max_q, int prefix_len, const md_kv* kv, int layer,
-                              void* out, void* stream);
+/* Prefix-LM attention for prefill (text.py:46-50 under the mask of moondream.py:138-146):
+ * tcgen05/TMA flash attention; q / out are [total_tokens, H*64].  The pool must hold finite values
+ * in unused slots (zero-initialise it): masked keys still flow through the P V product as 0 * v. */
+int md_prefill_attention_bf16(const void* q, int n_heads, int total_tokens, const int* q_offsets,
+                              const int* start_pos, int n_seqs, int max_q, int prefix_len,
+                              const md_kv* kv, int layer, void* out, void* stream);
+/* Testing / A-B timing only: 0 = tcgen05 attention (default), 1 = the legacy mma.sync kernel. */
+void md_debug_attention_impl(int impl);
 
 /* One-query attention for decode (text.py:46-50 with the [1,1,2048] mask of moondream.py:472-474). */
 int md_decode_attention_bf16(const void* q, int n_heads, const int* pos, int n_seqs, const md_kv* kv,

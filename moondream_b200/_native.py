@@ -15,7 +15,8 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libmoondream_b200.so")
 _lib = None
 
 class md_kv(ctypes.Structure):
-    _fields_ = [("pool", c_void_p), ("n_pages", c_int), ("block_tables", c_void_p), ("max_blocks", c_int)]
+    _fields_ = [("pool", c_void_p), ("n_pages", c_int), ("block_tables", c_void_p), ("max_blocks", c_int),
+                ("n_layers", c_int)]
 
 
 class md_dims(ctypes.Structure):
@@ -49,7 +50,8 @@ _SIGNATURES = {
     "md_layernorm_bf16": (c_int, [_P, _LL, _P, _P, _P, _LL, c_int, c_int, _P]),
     "md_vit_attention_bf16": (c_int, [_P, c_int, c_int, c_int, _P, _P]),
     "md_rope_kv_write_bf16": (c_int, [_P, c_int, c_int, _P, _P, c_int, _P, _P, _KV, c_int, _P]),
-    "md_prefill_attention_bf16": (c_int, [_P, c_int, _P, _P, c_int, c_int, c_int, _KV, c_int, _P, _P]),
+    "md_prefill_attention_bf16": (c_int, [_P, c_int, c_int, _P, _P, c_int, c_int, c_int, _KV, c_int, _P, _P]),
+    "md_debug_attention_impl": (None, [c_int]),
     "md_decode_attention_bf16": (c_int, [_P, c_int, _P, c_int, _KV, c_int, _P, _P]),
     "md_model_num_weights": (c_int, [_DIMS]),
     "md_model_create": (c_int, [_DIMS, ctypes.POINTER(c_void_p), c_int, _P, _P, ctypes.POINTER(c_void_p)]),

@@ -8,6 +8,7 @@ namespace md {
 
 static thread_local char g_err[512] = "";
 static long long g_launches = 0;
+int g_attention_impl = 0;
 
 int set_error(const char* msg) {
   strncpy(g_err, msg ? msg : "unknown error", sizeof(g_err) - 1);
@@ -92,14 +93,19 @@ int md_rope_kv_write_bf16(const void* qkv, int n_tokens, int n_heads, const int*
                            layer, STREAM(stream));
 }
 
-int md_prefill_attention_bf16(const void* q, int n_heads, const int* q_offsets, const int* start_pos,
-                              int n_seqs, int max_q, int prefix_len, const md_kv* kv, int layer,
-                              void* out, void* stream) {
+int md_prefill_attention_bf16(const void* q, int n_heads, int total_tokens, const int* q_offsets,
+                              const int* start_pos, int n_seqs, int max_q, int prefix_len,
+                              const md_kv* kv, int layer, void* out, void* stream) {
   NEED(q && q_offsets && start_pos && kv && kv->pool && kv->block_tables && out, "md_prefill_attention_bf16");
-  return md::prefill_attention(BF(q), n_heads, q_offsets, start_pos, n_seqs, max_q, prefix_len,
-                               BF(kv->pool), kv->n_pages, kv->block_tables, kv->max_blocks, layer,
-                               BFM(out), STREAM(stream));
+  if (md::g_attention_impl == 1)
+    return md::prefill_attention(BF(q), n_heads, q_offsets, start_pos, n_seqs, max_q, prefix_len,
+                                 BF(kv->pool), kv->n_pages, kv->block_tables, kv->max_blocks, layer,
+                                 BFM(out), STREAM(stream));
+  return md::prefill_attention_tc(BF(q), n_heads, total_tokens, q_offsets, start_pos, n_seqs, max_q, prefix_len,
+                                  BF(kv->pool), kv->n_pages, kv->n_layers, kv->block_tables, kv->max_blocks,
+                                  layer, BFM(out), STREAM(stream));
 }
+void md_debug_attention_impl(int impl) { md::g_attention_impl = impl; }
 
 int md_decode_attention_bf16(const void* q, int n_heads, const int* pos, int n_seqs, const md_kv* kv,
                              int layer, void* out, void* stream) {

@@ -1,0 +1,312 @@
+// tcgen05 / TMA flash attention for the decoder prefill (head_dim 64, paged K/V, prefix-LM mask).
+//
+// Replaces F.scaled_dot_product_attention at reference text.py:46-50 under the mask of
+// moondream.py:138-146 for prefill-sized query blocks.
+//
+// One CTA = 128 queries of one (sequence, head); key tiles of 128 (= two 64-token KV pages).
+//   warp 0     : TMA loader      (Q once; K and V page boxes into a 2-stage ring)
+//   warp 1     : MMA issuer      (S = Q K^T -> TMEM; O += P V -> TMEM), one elected lane
+//   warps 2-5  : softmax         (thread = query row = TMEM lane: no shuffles; online softmax in the
+//                                 exp2 domain; P written to 128B-swizzled smem as the A operand of PV;
+//                                 O rescaled in TMEM only when a row maximum moved; final normalise + store)
+// TMEM: S 128 columns + O 64 columns (256 allocated) and ~113 KB of shared memory, so two CTAs fit on an
+// SM and their softmax / MMA phases interleave on the shared tensor pipe.
+// V is consumed as an MN-major B operand straight from the [tokens, 64] page image TMA writes: no
+// transpose anywhere.
+#include <math.h>
+
+#include "kernels.cuh"
+#include "ptx.cuh"
+
+namespace md {
+
+namespace fa {
+constexpr int BM = 128;              // queries per CTA
+constexpr int BN = 128;              // keys per tile
+constexpr int HD = 64;
+constexpr int kStages = 2;
+constexpr int kQBytes = BM * HD * 2;            // 16 KB
+constexpr int kKVBytes = BN * HD * 2;           // 16 KB each for K and V
+constexpr int kPBytes = BM * BN * 2;            // 32 KB (two 64-key blocks of [128 x 64])
+constexpr int kSmemTiles = kQBytes + kStages * 2 * kKVBytes + kPBytes;   // 112 KB
+constexpr int kSmemTotal = kSmemTiles + 256;   // two CTAs per SM: 2 x (kSmemTotal + 1 KB reserved) <= 228 KB
+constexpr int kThreads = 192;
+constexpr uint32_t kTmemCols = 256;
+constexpr uint32_t kColS = 0, kColO = 128;
+}  // namespace fa
+
+struct FaTcParams {
+  const int* q_offsets;     // [n_seqs + 1]
+  const int* start_pos;     // [n_seqs]
+  const int* block_tables;  // [n_seqs][max_blocks]
+  int max_blocks, n_heads, layer, n_pages, prefix_len;
+  __nv_bfloat16* out;       // [T_total, n_heads * 64]
+  float scale_log2;
+};
+
+__global__ void __launch_bounds__(fa::kThreads, 2)
+fa_tc_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
+                     const FaTcParams p) {
+  using namespace fa;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if (smem_u32(smem) & 1023) __trap();             // swizzled tiles need 1024-byte alignment
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + kQBytes;                       // [stage][16 KB]
+  uint8_t* sV = sK + kStages * kKVBytes;            // [stage][16 KB]
+  uint8_t* sP = sV + kStages * kKVBytes;            // 32 KB
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kSmemTiles);
+  uint64_t* q_full = bars;                          // 1
+  uint64_t* kv_full = bars + 1;                     // [2]
+  uint64_t* kv_empty = bars + 3;                    // [2]
+  uint64_t* s_full = bars + 5;                      // 1
+  uint64_t* s_empty = bars + 6;                     // 1 (128 arrivals)
+  uint64_t* p_full = bars + 7;                      // 1 (128 arrivals)
+  uint64_t* p_empty = bars + 8;                     // 1
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 9);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int head = blockIdx.y, seq = blockIdx.z;
+  const int q0 = blockIdx.x * BM;
+  const int q_off = p.q_offsets[seq];
+  const int n_q = p.q_offsets[seq + 1] - q_off;
+  if (q0 >= n_q) return;                            // uniform per CTA
+  const int q_pos0 = p.start_pos[seq];
+  const int kv_len = q_pos0 + n_q;
+  const int* btab = p.block_tables + static_cast<long long>(seq) * p.max_blocks;
+
+  // keys this query tile can see (prefix rows see the whole prefix; later rows are causal)
+  int reach = q_pos0 + min(q0 + BM, n_q);
+  if (q_pos0 + q0 < p.prefix_len) reach = max(reach, p.prefix_len);
+  reach = min(reach, kv_len);
+  const int n_tiles = (reach + BN - 1) / BN;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tensormap(&tmQ);
+    prefetch_tensormap(&tmKV);
+  }
+  if (warp == 1 && lane == 0) {
+    mbar_init(q_full, 1);
+    for (int i = 0; i < kStages; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
+    mbar_init(s_full, 1);
+    mbar_init(s_empty, 128);
+    mbar_init(p_full, 128);
+    mbar_init(p_empty, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_ptr_smem, kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    // ------------------------------ TMA loader ------------------------------
+    if (lane == 0) {
+      mbar_arrive_expect_tx(q_full, kQBytes);
+      tma_load_2d(sQ, &tmQ, q_full, head * HD, q_off + q0);
+      const long long page_rows = 2LL * p.n_heads * 64;                 // rows of one page (k then v)
+      for (int j = 0; j < n_tiles; ++j) {
+        const int st = j & 1;
+        const uint32_t u = static_cast<uint32_t>(j >> 1);
+        mbar_wait(&kv_empty[st], (u & 1) ^ 1);
+        mbar_arrive_expect_tx(&kv_full[st], 2 * kKVBytes);
+#pragma unroll
+        for (int h2 = 0; h2 < 2; ++h2) {
+          const int blk = min(2 * j + h2, p.max_blocks - 1);
+          const long long row_k = (static_cast<long long>(p.layer) * p.n_pages + btab[blk]) * page_rows +
+                                  static_cast<long long>(head) * 64;
+          tma_load_2d(sK + st * kKVBytes + h2 * (kKVBytes / 2), &tmKV, &kv_full[st], 0, static_cast<int32_t>(row_k));
+          tma_load_2d(sV + st * kKVBytes + h2 * (kKVBytes / 2), &tmKV, &kv_full[st], 0,
+                      static_cast<int32_t>(row_k + static_cast<long long>(p.n_heads) * 64));
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------ MMA issuer ------------------------------
+    if (lane == 0) {
+      constexpr uint32_t idesc_qk = make_idesc_bf16_f32(BM, BN);          // S[128,128] = Q K^T
+      constexpr uint32_t idesc_pv = make_idesc_bf16_f32_bmn(BM, HD);      // O[128,64] += P V (V MN-major)
+      const uint32_t tS = tmem_base + kColS, tO = tmem_base + kColO;
+      const uint64_t dQ = make_desc_k_sw128(smem_u32(sQ));
+      mbar_wait(q_full, 0);
+      auto issue_pv = [&](int j) {
+        const int st = j & 1;
+        mbar_wait(p_full, static_cast<uint32_t>(j & 1));
+        tc_fence_after();
+        const uint32_t sp = smem_u32(sP), sv = smem_u32(sV + st * kKVBytes);
+#pragma unroll
+        for (int k = 0; k < BN / 16; ++k) {
+          // A: P, K-major: 16 keys = 32 B inside the 128-byte row; the second 64-key block is 16 KB on
+          // B: V, MN-major: 16 keys = 16 rows of 128 B = 2048 B
+          const uint64_t da = make_desc_k_sw128(sp + (k >> 2) * (BM * 128)) + static_cast<uint64_t>(2 * (k & 3));
+          const uint64_t db = make_desc_mn_sw128(sv + k * 2048, 16);
+          umma_bf16(tO, da, db, idesc_pv, (j > 0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(p_empty);            // P buffer reusable, O updated
+        umma_commit(&kv_empty[st]);      // K/V stage reusable
+      };
+      for (int j = 0; j < n_tiles; ++j) {
+        const int st = j & 1;
+        const uint32_t u = static_cast<uint32_t>(j >> 1);
+        mbar_wait(&kv_full[st], u & 1);
+        mbar_wait(s_empty, static_cast<uint32_t>(j & 1) ^ 1);             // softmax(j-1) has read S
+        tc_fence_after();
+        const uint64_t dK = make_desc_k_sw128(smem_u32(sK + st * kKVBytes));
+#pragma unroll
+        for (int k = 0; k < HD / 16; ++k)
+          umma_bf16(tS, dQ + static_cast<uint64_t>(2 * k), dK + static_cast<uint64_t>(2 * k), idesc_qk, k > 0 ? 1u : 0u);
+        umma_commit(s_full);
+        if (j > 0) issue_pv(j - 1);
+      }
+      issue_pv(n_tiles - 1);
+    }
+  } else {
+    // ------------------------------ softmax (128 threads, one query row each) ------------------------------
+    const int quad = warp & 3;
+    const int r = quad * 32 + lane;                       // row in the tile = TMEM lane
+    const int qpos = q_pos0 + q0 + r;
+    const bool row_ok = q0 + r < n_q;
+    const uint32_t lane_addr = static_cast<uint32_t>(quad * 32) << 16;
+    const uint32_t tS = tmem_base + lane_addr + kColS, tO = tmem_base + lane_addr + kColO;
+    float m_run = -INFINITY, l_run = 0.f;
+    for (int j = 0; j < n_tiles; ++j) {
+      mbar_wait(s_full, static_cast<uint32_t>(j & 1));
+      tc_fence_after();
+      // pass 1: row maximum over the 128 scores of this tile (mask applied)
+      float mx = m_run;
+      const int k0 = j * BN;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32(tS + c * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const int kpos = k0 + c * 32 + i;
+          const bool ok = kpos < kv_len && (kpos <= qpos || (kpos < p.prefix_len && qpos < p.prefix_len));
+          if (ok) mx = fmaxf(mx, __uint_as_float(v[i]));
+        }
+      }
+      const float base = (mx == -INFINITY) ? 0.f : mx * p.scale_log2;
+      const float alpha = (m_run == -INFINITY) ? 0.f : exp2f(m_run * p.scale_log2 - base);
+      // the previous P V must have completed before O is rescaled and P is overwritten
+      if (j > 0) {
+        mbar_wait(p_empty, static_cast<uint32_t>((j - 1) & 1));
+        tc_fence_after();
+        if (__any_sync(0xffffffffu, mx != m_run)) {      // warp-uniform: rescale this warp's 32 rows of O
+#pragma unroll 1
+          for (int c = 0; c < HD / 32; ++c) {
+            uint32_t o[32];
+            tmem_ld_32x32(tO + c * 32, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st_32x32(tO + c * 32, o);
+          }
+          tmem_st_wait();
+        }
+      }
+      l_run *= alpha;
+      m_run = mx;
+      // pass 2: probabilities -> bf16 -> swizzled smem (A operand of P V)
+      uint8_t* prow = sP + r * 128;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32(tS + c * 32, v);
+        tmem_ld_wait();
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          float e[2];
+#pragma unroll
+          for (int h2 = 0; h2 < 2; ++h2) {
+            const int kpos = k0 + c * 32 + 2 * i + h2;
+            const bool ok = kpos < kv_len && (kpos <= qpos || (kpos < p.prefix_len && qpos < p.prefix_len));
+            e[h2] = ok ? exp2f(__uint_as_float(v[2 * i + h2]) * p.scale_log2 - base) : 0.f;
+          }
+          l_run += e[0] + e[1];
+          pk[i] = pack_bf16x2(e[0], e[1]);
+        }
+        // 32 keys = four 16-byte chunks of this row; 64-key block = c / 2, chunk index within the 128-byte row
+        uint8_t* blk = prow + (c >> 1) * (BM * 128);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const int chunk = (c & 1) * 4 + g;
+          *reinterpret_cast<uint4*>(blk + ((chunk ^ (r & 7)) << 4)) =
+              make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
+        }
+      }
+      // S has been consumed; P is in shared memory: publish both
+      tc_fence_before();
+      mbar_arrive(s_empty);
+      fence_proxy_async_smem();
+      mbar_arrive(p_full);
+    }
+    // ---- epilogue: O / l -> bf16 -> global ----
+    mbar_wait(p_empty, static_cast<uint32_t>((n_tiles - 1) & 1));
+    tc_fence_after();
+    const float inv = l_run > 0.f ? 1.0f / l_run : 0.f;
+    __nv_bfloat16* orow = p.out + (static_cast<long long>(q_off) + q0 + r) * (static_cast<long long>(p.n_heads) * HD) + head * HD;
+#pragma unroll 1
+    for (int c = 0; c < HD / 32; ++c) {
+      uint32_t o[32];
+      tmem_ld_32x32(tO + c * 32, o);
+      tmem_ld_wait();
+      if (row_ok) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint4 w;
+          w.x = pack_bf16x2(__uint_as_float(o[8 * g]) * inv, __uint_as_float(o[8 * g + 1]) * inv);
+          w.y = pack_bf16x2(__uint_as_float(o[8 * g + 2]) * inv, __uint_as_float(o[8 * g + 3]) * inv);
+          w.z = pack_bf16x2(__uint_as_float(o[8 * g + 4]) * inv, __uint_as_float(o[8 * g + 5]) * inv);
+          w.w = pack_bf16x2(__uint_as_float(o[8 * g + 6]) * inv, __uint_as_float(o[8 * g + 7]) * inv);
+          *reinterpret_cast<uint4*>(orow + c * 32 + g * 8) = w;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, fa::kTmemCols);
+  }
+}
+
+int prefill_attention_tc(const __nv_bfloat16* q, int n_heads, int total_tokens, const int* q_offsets,
+                         const int* start_pos, int n_seqs, int max_q, int prefix_len,
+                         const __nv_bfloat16* kv_pool, int n_pages, int n_layers, const int* block_tables,
+                         int max_blocks, int layer, __nv_bfloat16* out, cudaStream_t stream) {
+  if (n_seqs <= 0 || max_q <= 0) return set_error("prefill_attention: empty batch");
+  CUtensorMap tQ, tKV;
+  if (make_tmap_bf16_2d(&tQ, q, total_tokens, static_cast<long long>(n_heads) * 64,
+                        static_cast<long long>(n_heads) * 64, fa::BM)) return 1;
+  const long long pool_rows = static_cast<long long>(n_layers) * n_pages * 2 * n_heads * 64;
+  if (pool_rows >= (1LL << 31)) return set_error("prefill_attention: KV pool too large for 32-bit TMA coordinates");
+  if (make_tmap_bf16_2d(&tKV, kv_pool, pool_rows, 64, 64, 64)) return 1;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(fa_tc_prefill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         fa::kSmemTotal);
+    if (e != cudaSuccess) return set_error(cudaGetErrorString(e));
+    configured = true;
+  }
+  FaTcParams p{};
+  p.q_offsets = q_offsets; p.start_pos = start_pos; p.block_tables = block_tables;
+  p.max_blocks = max_blocks; p.n_heads = n_heads; p.layer = layer; p.n_pages = n_pages;
+  p.prefix_len = prefix_len; p.out = out;
+  p.scale_log2 = 0.125f * 1.4426950408889634f;
+  dim3 grid((max_q + fa::BM - 1) / fa::BM, n_heads, n_seqs);
+  fa_tc_prefill_kernel<<<grid, fa::kThreads, fa::kSmemTotal, stream>>>(tQ, tKV, p);
+  count_launch();
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error(cudaGetErrorString(e));
+  return 0;
+}
+
+}  // namespace md

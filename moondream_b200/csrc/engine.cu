@@ -184,8 +184,13 @@ int text_prefill(Model& m, bf16* x, int T, const int* q_offsets, const int* star
     if (gemm_rowform(ln, D, b.qkv.w, D, T, 3 * D, D, EPI_BIAS, b.qkv.b, nullptr, 0, 0, qkv, 3 * D, 0, 0, 0, st)) return 1;
     if (rope_kv_write(qkv, T, H, q_offsets, start_pos, n_seqs, m.rope, q, pool, kv.n_pages, kv.block_tables,
                       kv.max_blocks, i, st)) return 1;
-    if (prefill_attention(q, H, q_offsets, start_pos, n_seqs, max_q, d.prefix_len, pool, kv.n_pages,
-                          kv.block_tables, kv.max_blocks, i, att, st)) return 1;
+    if (g_attention_impl == 1) {
+      if (prefill_attention(q, H, q_offsets, start_pos, n_seqs, max_q, d.prefix_len, pool, kv.n_pages,
+                            kv.block_tables, kv.max_blocks, i, att, st)) return 1;
+    } else {
+      if (prefill_attention_tc(q, H, T, q_offsets, start_pos, n_seqs, max_q, d.prefix_len, pool, kv.n_pages,
+                               kv.n_layers, kv.block_tables, kv.max_blocks, i, att, st)) return 1;
+    }
     // tmp = bf16(x + bf16(proj(att)))  -- the reference adds l_attn first, then l_mlp (text.py:158)
     if (gemm_rowform(att, D, b.proj.w, b.proj.ld, T, D, D, EPI_BIAS_RESIDUAL, b.proj.b, x, D, 0, tmp, D, 0, 0, 0, st)) return 1;
     if (gemm_rowform(ln, D, b.fc1.w, b.fc1.ld, T, d.txt_ff, D, EPI_BIAS_GELU, b.fc1.b, nullptr, 0, 0, hid, d.txt_ff, 0, 0, 0, st)) return 1;

@@ -78,6 +78,13 @@ int decode_residual_ln_epilogue(const float* ws, int splits, int proj_splits, in
 int fourier_features(const float* x, int B, int n_in, const __nv_bfloat16* w, int half,
                      __nv_bfloat16* out, long long ldo, cudaStream_t stream);
 
+// ---- attention_tc.cu ----
+int prefill_attention_tc(const __nv_bfloat16* q, int n_heads, int total_tokens, const int* q_offsets,
+                         const int* start_pos, int n_seqs, int max_q, int prefix_len,
+                         const __nv_bfloat16* kv_pool, int n_pages, int n_layers, const int* block_tables,
+                         int max_blocks, int layer, __nv_bfloat16* out, cudaStream_t stream);
+extern int g_attention_impl;   // 0 tcgen05, 1 legacy mma.sync
+
 // ---- attention.cu ----
 int vit_attention(const __nv_bfloat16* qkv, int n_crops, int seq, int n_heads, __nv_bfloat16* out,
                   cudaStream_t stream);

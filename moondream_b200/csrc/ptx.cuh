@@ -216,6 +216,39 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16_f32(int m, int n) {
          (static_cast<uint32_t>(m >> 4) << 24);
 }
 
+__device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+        "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]),
+        "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]),
+        "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() {
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+// 128-byte-swizzled operand tiles: rows of 128 B (64 bf16), 8-row groups 1024 B apart.
+//  * K-major (rows = M/N index, the 64 elements of a row run along K): used for Q, K and P.
+//  * MN-major (rows = K index, the 64 elements of a row run along N): used for V in O += P V; the
+//    smem image is the same as TMA writes for a [keys, 64] box, only the descriptor differs
+//    (instruction-descriptor bit 16 = B is MN-major).  SBO = 1024 B between 8-row K groups; LBO =
+//    byte distance between successive 64-wide N blocks.
+__device__ __forceinline__ uint64_t make_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+__host__ __device__ constexpr uint32_t make_idesc_bf16_f32_bmn(int m, int n) {
+  return make_idesc_bf16_f32(m, n) | (1u << 16);   // B operand MN-major
+}
+
 // ----------------------------------------------------------------------------------------------
 // Ampere-style async copy / ldmatrix / mma.sync (used by the attention kernels)
 // ----------------------------------------------------------------------------------------------

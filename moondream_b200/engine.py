@@ -103,7 +103,8 @@ class PagePool:
     def __init__(self, cfg: MoondreamConfig, n_pages: int, device):
         t = cfg.text
         self.n_pages = n_pages
-        self.pool = torch.empty((t.n_layers, n_pages, 2, t.n_heads, PAGE, 64), dtype=torch.bfloat16,
+        # zeros, not empty: masked / not-yet-written slots still flow through P.V as 0 * v and must be finite
+        self.pool = torch.zeros((t.n_layers, n_pages, 2, t.n_heads, PAGE, 64), dtype=torch.bfloat16,
                                 device=device)
         self._free = list(range(n_pages - 1, -1, -1))
 
@@ -201,7 +202,8 @@ class Engine:
 
     def _kv(self, block_tables: torch.Tensor) -> N.md_kv:
         return N.md_kv(pool=self.pages.pool.data_ptr(), n_pages=self.pages.n_pages,
-                       block_tables=block_tables.data_ptr(), max_blocks=block_tables.shape[1])
+                       block_tables=block_tables.data_ptr(), max_blocks=block_tables.shape[1],
+                       n_layers=self.cfg.text.n_layers)
 
     def _i32(self, values) -> torch.Tensor:
         return torch.tensor(values, dtype=torch.int32).to(self.device, non_blocking=True)

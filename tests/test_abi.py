@@ -39,7 +39,7 @@ def test_struct_layouts():
     from moondream_b200 import _native as N
 
     assert ctypes.sizeof(N.md_dims) == 23 * 4
-    assert ctypes.sizeof(N.md_kv) == 32          # ptr, int(+pad), ptr, int(+pad)
+    assert ctypes.sizeof(N.md_kv) == 32          # ptr, int(+pad), ptr, int, int
 
 
 def test_errors_are_reported_not_crashed():

@@ -73,10 +73,12 @@ def _rope_ref(x, table, pos):
     return torch.cat([rot, x[..., 32:]], dim=-1)
 
 
-def test_rope_prefill_decode_attention():
+@pytest.mark.parametrize("impl", [0, 1], ids=["tcgen05", "mma_sync"])
+def test_rope_prefill_decode_attention(impl):
     from moondream_b200.engine import rope_table
 
     N, lib = _lib()
+    lib.md_debug_attention_impl(impl)
     heads, layers, n_pages, max_blocks, prefix = 4, 2, 64, 16, 730
     D = heads * 64
     lens = [730, 730, 17]
@@ -84,7 +86,8 @@ def test_rope_prefill_decode_attention():
     n_seqs = len(lens)
     pool, bt = _paged_setup(n_seqs, heads, layers, n_pages, max_blocks, 1)
     table = rope_table(64, 2048).cuda()
-    kv = N.md_kv(pool=pool.data_ptr(), n_pages=n_pages, block_tables=bt.data_ptr(), max_blocks=max_blocks)
+    kv = N.md_kv(pool=pool.data_ptr(), n_pages=n_pages, block_tables=bt.data_ptr(), max_blocks=max_blocks,
+                 n_layers=layers)
     g = torch.Generator(device="cuda").manual_seed(3)
     layer = 1
     # sequence 2 needs its prefix (positions 0..729) in the cache first: run a 730-token prefill for it
@@ -97,7 +100,7 @@ def test_rope_prefill_decode_attention():
         N.check(lib.md_rope_kv_write_bf16(N.ptr(qkv), T, heads, N.ptr(qo), N.ptr(sp), n_seqs, N.ptr(table),
                                           N.ptr(q_out), ctypes.byref(kv), layer, N.current_stream()))
         out = torch.empty(T, D, device="cuda", dtype=torch.bfloat16)
-        N.check(lib.md_prefill_attention_bf16(N.ptr(q_out), heads, N.ptr(qo), N.ptr(sp), n_seqs, max(lens_i),
+        N.check(lib.md_prefill_attention_bf16(N.ptr(q_out), heads, T, N.ptr(qo), N.ptr(sp), n_seqs, max(lens_i),
                                               prefix, ctypes.byref(kv), layer, N.ptr(out), N.current_stream()))
         torch.cuda.synchronize()
         off = 0
@@ -135,6 +138,7 @@ def test_rope_prefill_decode_attention():
         q = q_out[s].float().view(heads, 1, 64)
         ref = F.scaled_dot_product_attention(q, kc, vc).reshape(D)
         assert rel(out[s], ref) < 6e-3, (s, rel(out[s], ref))
+    lib.md_debug_attention_impl(0)
 
 
 @pytest.mark.parametrize("vocab", [2048, 16384])
@@ -173,6 +177,7 @@ def test_small_batch_argmax_ties_and_mask(vocab):
     assert torch.equal(ids.long(), torch.argmax(logits.float(), dim=-1))
     top2 = torch.topk(logits.float(), 2, dim=-1).values
     assert torch.allclose(mar, top2[:, 0] - top2[:, 1])
+    eng.lm_head(h, ids, 1, logits=logits)
     best = ids.clone()
     eng.lm_head(h, ids, 1, mask_id=int(best[0]))
     lg = logits.float().clone()
