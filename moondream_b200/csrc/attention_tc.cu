@@ -172,22 +172,35 @@ fa_tc_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     const uint32_t lane_addr = static_cast<uint32_t>(quad * 32) << 16;
     const uint32_t tS = tmem_base + lane_addr + kColS, tO = tmem_base + lane_addr + kColO;
     float m_run = -INFINITY, l_run = 0.f;
+    const int q_lo = q_pos0 + q0;                          // smallest query position of this CTA
     for (int j = 0; j < n_tiles; ++j) {
+      const int k0 = j * BN;
+      // interior tiles need no masking: every key exists and every row of the CTA may attend to it
+      const bool full = (k0 + BN <= kv_len) && (k0 + BN - 1 <= q_lo || (k0 + BN <= p.prefix_len && q_lo + BM <= p.prefix_len));
+      auto allowed = [&](int kpos) {
+        return kpos < kv_len && (kpos <= qpos || (kpos < p.prefix_len && qpos < p.prefix_len));
+      };
       mbar_wait(s_full, static_cast<uint32_t>(j & 1));
       tc_fence_after();
-      // pass 1: row maximum over the 128 scores of this tile (mask applied)
+      // pass 1: row maximum over the 128 scores of this tile; TMEM loads are double-buffered
       float mx = m_run;
-      const int k0 = j * BN;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32(tS + c * 32, v);
-        tmem_ld_wait();
+      {
+        uint32_t va[32], vb[32];
+        tmem_ld_32x32(tS, va);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const int kpos = k0 + c * 32 + i;
-          const bool ok = kpos < kv_len && (kpos <= qpos || (kpos < p.prefix_len && qpos < p.prefix_len));
-          if (ok) mx = fmaxf(mx, __uint_as_float(v[i]));
+        for (int c = 0; c < 4; ++c) {
+          uint32_t (&cur)[32] = (c & 1) ? vb : va;
+          uint32_t (&nxt)[32] = (c & 1) ? va : vb;
+          tmem_ld_wait();
+          if (c < 3) tmem_ld_32x32(tS + (c + 1) * 32, nxt);
+          if (full) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(cur[i]));
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (allowed(k0 + c * 32 + i)) mx = fmaxf(mx, __uint_as_float(cur[i]));
+          }
         }
       }
       const float base = (mx == -INFINITY) ? 0.f : mx * p.scale_log2;
@@ -197,15 +210,17 @@ fa_tc_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         mbar_wait(p_empty, static_cast<uint32_t>((j - 1) & 1));
         tc_fence_after();
         if (__any_sync(0xffffffffu, mx != m_run)) {      // warp-uniform: rescale this warp's 32 rows of O
-#pragma unroll 1
-          for (int c = 0; c < HD / 32; ++c) {
-            uint32_t o[32];
-            tmem_ld_32x32(tO + c * 32, o);
-            tmem_ld_wait();
+          uint32_t o0[32], o1[32];
+          tmem_ld_32x32(tO, o0);
+          tmem_ld_32x32(tO + 32, o1);
+          tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-            tmem_st_32x32(tO + c * 32, o);
+          for (int i = 0; i < 32; ++i) {
+            o0[i] = __float_as_uint(__uint_as_float(o0[i]) * alpha);
+            o1[i] = __float_as_uint(__uint_as_float(o1[i]) * alpha);
           }
+          tmem_st_32x32(tO, o0);
+          tmem_st_32x32(tO + 32, o1);
           tmem_st_wait();
         }
       }
@@ -213,31 +228,38 @@ fa_tc_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       m_run = mx;
       // pass 2: probabilities -> bf16 -> swizzled smem (A operand of P V)
       uint8_t* prow = sP + r * 128;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32(tS + c * 32, v);
-        tmem_ld_wait();
-        uint32_t pk[16];
+      {
+        uint32_t va[32], vb[32];
+        tmem_ld_32x32(tS, va);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          float e[2];
+        for (int c = 0; c < 4; ++c) {
+          uint32_t (&cur)[32] = (c & 1) ? vb : va;
+          uint32_t (&nxt)[32] = (c & 1) ? va : vb;
+          tmem_ld_wait();
+          if (c < 3) tmem_ld_32x32(tS + (c + 1) * 32, nxt);
+          uint32_t pk[16];
+          float acc0 = 0.f, acc1 = 0.f;
 #pragma unroll
-          for (int h2 = 0; h2 < 2; ++h2) {
-            const int kpos = k0 + c * 32 + 2 * i + h2;
-            const bool ok = kpos < kv_len && (kpos <= qpos || (kpos < p.prefix_len && qpos < p.prefix_len));
-            e[h2] = ok ? exp2f(__uint_as_float(v[2 * i + h2]) * p.scale_log2 - base) : 0.f;
+          for (int i = 0; i < 16; ++i) {
+            float e0 = exp2f(fmaf(__uint_as_float(cur[2 * i]), p.scale_log2, -base));
+            float e1 = exp2f(fmaf(__uint_as_float(cur[2 * i + 1]), p.scale_log2, -base));
+            if (!full) {
+              if (!allowed(k0 + c * 32 + 2 * i)) e0 = 0.f;
+              if (!allowed(k0 + c * 32 + 2 * i + 1)) e1 = 0.f;
+            }
+            acc0 += e0;
+            acc1 += e1;
+            pk[i] = pack_bf16x2(e0, e1);
           }
-          l_run += e[0] + e[1];
-          pk[i] = pack_bf16x2(e[0], e[1]);
-        }
-        // 32 keys = four 16-byte chunks of this row; 64-key block = c / 2, chunk index within the 128-byte row
-        uint8_t* blk = prow + (c >> 1) * (BM * 128);
+          l_run += acc0 + acc1;
+          // 32 keys = four 16-byte chunks of this row; 64-key block = c / 2
+          uint8_t* blk = prow + (c >> 1) * (BM * 128);
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          const int chunk = (c & 1) * 4 + g;
-          *reinterpret_cast<uint4*>(blk + ((chunk ^ (r & 7)) << 4)) =
-              make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
+          for (int g = 0; g < 4; ++g) {
+            const int chunk = (c & 1) * 4 + g;
+            *reinterpret_cast<uint4*>(blk + ((chunk ^ (r & 7)) << 4)) =
+                make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
+          }
         }
       }
       // S has been consumed; P is in shared memory: publish both
@@ -293,6 +315,10 @@ int prefill_attention_tc(const __nv_bfloat16* q, int n_heads, int total_tokens, 
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(fa_tc_prefill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          fa::kSmemTotal);
+    if (e != cudaSuccess) return set_error(cudaGetErrorString(e));
+    // two CTAs per SM need the full shared-memory carve-out
+    e = cudaFuncSetAttribute(fa_tc_prefill_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                             cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return set_error(cudaGetErrorString(e));
     configured = true;
   }
