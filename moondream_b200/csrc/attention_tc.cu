@@ -35,6 +35,76 @@ constexpr uint32_t kTmemCols = 256;
 constexpr uint32_t kColS = 0, kColO = 128;
 }  // namespace fa
 
+
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// max over one 32-score chunk of a row; `full` (tile-uniform) skips the prefix-LM / length mask
+__device__ __forceinline__ float chunk_max(const uint32_t (&v)[32], bool full, int k_first, int kv_len,
+                                           int qpos, int prefix_len) {
+  float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+  if (full) {
+#pragma unroll
+    for (int i = 0; i < 32; i += 4) {
+      m0 = fmaxf(m0, __uint_as_float(v[i]));
+      m1 = fmaxf(m1, __uint_as_float(v[i + 1]));
+      m2 = fmaxf(m2, __uint_as_float(v[i + 2]));
+      m3 = fmaxf(m3, __uint_as_float(v[i + 3]));
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      const int kpos = k_first + i;
+      const bool ok = kpos < kv_len && (kpos <= qpos || (kpos < prefix_len && qpos < prefix_len));
+      if (ok) m0 = fmaxf(m0, __uint_as_float(v[i]));
+    }
+  }
+  return fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+}
+
+// exp2(s * scale - base) for one 32-score chunk -> bf16 -> four swizzled 16-byte chunks of the row's
+// 128-byte line (chunk slots chunk0 .. chunk0+3); returns the row-sum contribution
+__device__ __forceinline__ float chunk_probs(const uint32_t (&v)[32], bool full, int k_first, int kv_len, int qpos,
+                                             int prefix_len, float scale_log2, float base, uint8_t* line,
+                                             int chunk0, int r) {
+  uint32_t pk[16];
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  if (full) {
+#pragma unroll
+    for (int i = 0; i < 16; i += 2) {
+      const float e0 = ex2_approx(fmaf(__uint_as_float(v[2 * i]), scale_log2, -base));
+      const float e1 = ex2_approx(fmaf(__uint_as_float(v[2 * i + 1]), scale_log2, -base));
+      const float e2 = ex2_approx(fmaf(__uint_as_float(v[2 * i + 2]), scale_log2, -base));
+      const float e3 = ex2_approx(fmaf(__uint_as_float(v[2 * i + 3]), scale_log2, -base));
+      a0 += e0; a1 += e1; a2 += e2; a3 += e3;
+      pk[i] = pack_bf16x2(e0, e1);
+      pk[i + 1] = pack_bf16x2(e2, e3);
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      float e[2];
+#pragma unroll
+      for (int h2 = 0; h2 < 2; ++h2) {
+        const int kpos = k_first + 2 * i + h2;
+        const bool ok = kpos < kv_len && (kpos <= qpos || (kpos < prefix_len && qpos < prefix_len));
+        e[h2] = ok ? ex2_approx(fmaf(__uint_as_float(v[2 * i + h2]), scale_log2, -base)) : 0.f;
+      }
+      a0 += e[0];
+      a1 += e[1];
+      pk[i] = pack_bf16x2(e[0], e[1]);
+    }
+  }
+#pragma unroll
+  for (int g = 0; g < 4; ++g)
+    *reinterpret_cast<uint4*>(line + (((chunk0 + g) ^ (r & 7)) << 4)) =
+        make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
+  return (a0 + a1) + (a2 + a3);
+}
+
 struct FaTcParams {
   const int* q_offsets;     // [n_seqs + 1]
   const int* start_pos;     // [n_seqs]
@@ -173,38 +243,32 @@ fa_tc_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     const uint32_t tS = tmem_base + lane_addr + kColS, tO = tmem_base + lane_addr + kColO;
     float m_run = -INFINITY, l_run = 0.f;
     const int q_lo = q_pos0 + q0;                          // smallest query position of this CTA
+    uint8_t* prow = sP + r * 128;
     for (int j = 0; j < n_tiles; ++j) {
       const int k0 = j * BN;
       // interior tiles need no masking: every key exists and every row of the CTA may attend to it
-      const bool full = (k0 + BN <= kv_len) && (k0 + BN - 1 <= q_lo || (k0 + BN <= p.prefix_len && q_lo + BM <= p.prefix_len));
-      auto allowed = [&](int kpos) {
-        return kpos < kv_len && (kpos <= qpos || (kpos < p.prefix_len && qpos < p.prefix_len));
-      };
+      const bool full = (k0 + BN <= kv_len) &&
+                        (k0 + BN - 1 <= q_lo || (k0 + BN <= p.prefix_len && q_lo + BM <= p.prefix_len));
       mbar_wait(s_full, static_cast<uint32_t>(j & 1));
       tc_fence_after();
-      // pass 1: row maximum over the 128 scores of this tile; TMEM loads are double-buffered
+
+      // ---- pass 1: row maximum (two 32-column chunks in flight) ----
       float mx = m_run;
       {
         uint32_t va[32], vb[32];
         tmem_ld_32x32(tS, va);
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          uint32_t (&cur)[32] = (c & 1) ? vb : va;
-          uint32_t (&nxt)[32] = (c & 1) ? va : vb;
+#pragma unroll 1
+        for (int cc = 0; cc < 2; ++cc) {
           tmem_ld_wait();
-          if (c < 3) tmem_ld_32x32(tS + (c + 1) * 32, nxt);
-          if (full) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(cur[i]));
-          } else {
-#pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (allowed(k0 + c * 32 + i)) mx = fmaxf(mx, __uint_as_float(cur[i]));
-          }
+          tmem_ld_32x32(tS + (2 * cc + 1) * 32, vb);
+          mx = fmaxf(mx, chunk_max(va, full, k0 + (2 * cc) * 32, kv_len, qpos, p.prefix_len));
+          tmem_ld_wait();
+          if (cc == 0) tmem_ld_32x32(tS + 64, va);
+          mx = fmaxf(mx, chunk_max(vb, full, k0 + (2 * cc + 1) * 32, kv_len, qpos, p.prefix_len));
         }
       }
       const float base = (mx == -INFINITY) ? 0.f : mx * p.scale_log2;
-      const float alpha = (m_run == -INFINITY) ? 0.f : exp2f(m_run * p.scale_log2 - base);
+      const float alpha = (m_run == -INFINITY) ? 0.f : ex2_approx(m_run * p.scale_log2 - base);
       // the previous P V must have completed before O is rescaled and P is overwritten
       if (j > 0) {
         mbar_wait(p_empty, static_cast<uint32_t>((j - 1) & 1));
@@ -226,40 +290,21 @@ fa_tc_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       }
       l_run *= alpha;
       m_run = mx;
-      // pass 2: probabilities -> bf16 -> swizzled smem (A operand of P V)
-      uint8_t* prow = sP + r * 128;
+
+      // ---- pass 2: probabilities -> bf16 -> swizzled smem (A operand of P V) ----
       {
         uint32_t va[32], vb[32];
         tmem_ld_32x32(tS, va);
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          uint32_t (&cur)[32] = (c & 1) ? vb : va;
-          uint32_t (&nxt)[32] = (c & 1) ? va : vb;
+#pragma unroll 1
+        for (int cc = 0; cc < 2; ++cc) {
           tmem_ld_wait();
-          if (c < 3) tmem_ld_32x32(tS + (c + 1) * 32, nxt);
-          uint32_t pk[16];
-          float acc0 = 0.f, acc1 = 0.f;
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            float e0 = exp2f(fmaf(__uint_as_float(cur[2 * i]), p.scale_log2, -base));
-            float e1 = exp2f(fmaf(__uint_as_float(cur[2 * i + 1]), p.scale_log2, -base));
-            if (!full) {
-              if (!allowed(k0 + c * 32 + 2 * i)) e0 = 0.f;
-              if (!allowed(k0 + c * 32 + 2 * i + 1)) e1 = 0.f;
-            }
-            acc0 += e0;
-            acc1 += e1;
-            pk[i] = pack_bf16x2(e0, e1);
-          }
-          l_run += acc0 + acc1;
-          // 32 keys = four 16-byte chunks of this row; 64-key block = c / 2
-          uint8_t* blk = prow + (c >> 1) * (BM * 128);
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const int chunk = (c & 1) * 4 + g;
-            *reinterpret_cast<uint4*>(blk + ((chunk ^ (r & 7)) << 4)) =
-                make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
-          }
+          tmem_ld_32x32(tS + (2 * cc + 1) * 32, vb);
+          l_run += chunk_probs(va, full, k0 + (2 * cc) * 32, kv_len, qpos, p.prefix_len, p.scale_log2, base,
+                               prow + cc * (BM * 128), 0, r);
+          tmem_ld_wait();
+          if (cc == 0) tmem_ld_32x32(tS + 64, va);
+          l_run += chunk_probs(vb, full, k0 + (2 * cc + 1) * 32, kv_len, qpos, p.prefix_len, p.scale_log2, base,
+                               prow + cc * (BM * 128), 4, r);
         }
       }
       // S has been consumed; P is in shared memory: publish both
