@@ -81,7 +81,8 @@ int md_layernorm_bf16(const void* x, long long ldx, const void* w, const void* b
 
 int md_vit_attention_bf16(const void* qkv, int n_crops, int seq, int n_heads, void* out, void* stream) {
   NEED(qkv && out, "md_vit_attention_bf16");
-  return md::vit_attention(BF(qkv), n_crops, seq, n_heads, BFM(out), STREAM(stream));
+  if (md::g_attention_impl == 1) return md::vit_attention(BF(qkv), n_crops, seq, n_heads, BFM(out), STREAM(stream));
+  return md::vit_attention_tc(BF(qkv), n_crops, seq, n_heads, BFM(out), STREAM(stream));
 }
 
 int md_rope_kv_write_bf16(const void* qkv, int n_tokens, int n_heads, const int* q_offsets,

@@ -380,4 +380,286 @@ int prefill_attention_tc(const __nv_bfloat16* q, int n_heads, int total_tokens, 
   return 0;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// ViT self-attention (reference layers.py:155-166): head_dim 72, 729 tokens per crop, no mask.
+// Same warp roles and softmax as the prefill kernel.  The 72-wide head is staged as a 64-wide
+// 128B-swizzled block plus a 16-wide 32B-swizzled block (dims 64..79; 72..79 are TMA out-of-bounds
+// zero fill through a 3-D view [token][3*H heads][72]), so
+//   S  = Q K^T : 4 k-steps on the 64-block + 1 k-step on the 16-block,
+//   O += P V   : N = 64 columns from the 64-block and N = 16 columns from the 16-block (both MN-major).
+// K is double-buffered (released as soon as S is complete), V single-buffered: 112 KB, 2 CTAs per SM.
+// ------------------------------------------------------------------------------------------------
+namespace fv {
+constexpr int BM = 128, BN = 128, HD = 72;
+constexpr int kBlk0 = 128 * 128;                 // [128 rows x 64] bf16, 16 KB
+constexpr int kBlk1 = 128 * 32;                  // [128 rows x 16] bf16, 4 KB
+constexpr int kTile = kBlk0 + kBlk1;             // 20 KB
+constexpr int kPBytes = BM * BN * 2;             // 32 KB
+constexpr int kSmemTiles = kTile /*Q*/ + 2 * kTile /*K*/ + kTile /*V*/ + kPBytes;   // 112 KB
+constexpr int kSmemTotal = kSmemTiles + 256;
+constexpr int kThreads = 192;
+constexpr uint32_t kTmemCols = 256;
+constexpr uint32_t kColS = 0, kColO = 128;       // O: 80 columns (64 + 16)
+}  // namespace fv
+
+struct FaVitParams {
+  int seq, n_heads;
+  __nv_bfloat16* out;        // [n_crops * seq, n_heads * 72]
+  float scale_log2;
+};
+
+__global__ void __launch_bounds__(fv::kThreads, 2)
+fa_tc_vit_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_constant__ CUtensorMap tm16,
+                 const FaVitParams p) {
+  using namespace fv;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if (smem_u32(smem) & 1023) __trap();
+  uint8_t* sQ = smem;                               // blk0 | blk1
+  uint8_t* sK = sQ + kTile;                         // [2][blk0 | blk1]
+  uint8_t* sV = sK + 2 * kTile;
+  uint8_t* sP = sV + kTile;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kSmemTiles);
+  uint64_t* q_full = bars;
+  uint64_t* k_full = bars + 1;                      // [2]
+  uint64_t* k_empty = bars + 3;                     // [2]
+  uint64_t* v_full = bars + 5;
+  uint64_t* v_empty = bars + 6;
+  uint64_t* s_full = bars + 7;
+  uint64_t* s_empty = bars + 8;                     // 128 arrivals
+  uint64_t* p_full = bars + 9;                      // 128 arrivals
+  uint64_t* p_empty = bars + 10;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 11);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int head = blockIdx.y, crop = blockIdx.z;
+  const int q0 = blockIdx.x * BM;
+  const int n_q = p.seq, kv_len = p.seq;
+  const int n_tiles = (kv_len + BN - 1) / BN;
+  const int row0 = crop * p.seq;                    // first token row of this crop
+  const int H = p.n_heads;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tensormap(&tm64);
+    prefetch_tensormap(&tm16);
+  }
+  if (warp == 1 && lane == 0) {
+    mbar_init(q_full, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1); }
+    mbar_init(v_full, 1);
+    mbar_init(v_empty, 1);
+    mbar_init(s_full, 1);
+    mbar_init(s_empty, 128);
+    mbar_init(p_full, 128);
+    mbar_init(p_empty, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_ptr_smem, kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    // ------------------------------ TMA loader ------------------------------
+    if (lane == 0) {
+      mbar_arrive_expect_tx(q_full, kTile);
+      tma_load_3d(sQ, &tm64, q_full, 0, head, row0 + q0);
+      tma_load_3d(sQ + kBlk0, &tm16, q_full, 64, head, row0 + q0);
+      for (int j = 0; j < n_tiles; ++j) {
+        const int st = j & 1;
+        const uint32_t u = static_cast<uint32_t>(j >> 1);
+        mbar_wait(&k_empty[st], (u & 1) ^ 1);
+        mbar_arrive_expect_tx(&k_full[st], kTile);
+        tma_load_3d(sK + st * kTile, &tm64, &k_full[st], 0, H + head, row0 + j * BN);
+        tma_load_3d(sK + st * kTile + kBlk0, &tm16, &k_full[st], 64, H + head, row0 + j * BN);
+        mbar_wait(v_empty, static_cast<uint32_t>(j & 1) ^ 1);
+        mbar_arrive_expect_tx(v_full, kTile);
+        tma_load_3d(sV, &tm64, v_full, 0, 2 * H + head, row0 + j * BN);
+        tma_load_3d(sV + kBlk0, &tm16, v_full, 64, 2 * H + head, row0 + j * BN);
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------ MMA issuer ------------------------------
+    if (lane == 0) {
+      constexpr uint32_t idesc_qk = make_idesc_bf16_f32(BM, BN);
+      constexpr uint32_t idesc_pv64 = make_idesc_bf16_f32_bmn(BM, 64);
+      constexpr uint32_t idesc_pv16 = make_idesc_bf16_f32_bmn(BM, 16);
+      const uint32_t tS = tmem_base + kColS, tO = tmem_base + kColO;
+      const uint64_t dQ0 = make_desc_k_sw128(smem_u32(sQ));
+      const uint64_t dQ1 = make_desc_sw32(smem_u32(sQ + kBlk0));
+      mbar_wait(q_full, 0);
+      auto issue_pv = [&](int j) {
+        mbar_wait(v_full, static_cast<uint32_t>(j & 1));
+        mbar_wait(p_full, static_cast<uint32_t>(j & 1));
+        tc_fence_after();
+        const uint32_t sp = smem_u32(sP), sv0 = smem_u32(sV), sv1 = smem_u32(sV + kBlk0);
+#pragma unroll
+        for (int k = 0; k < BN / 16; ++k) {
+          const uint64_t da = make_desc_k_sw128(sp + (k >> 2) * (BM * 128)) + static_cast<uint64_t>(2 * (k & 3));
+          const uint32_t acc = (j > 0 || k > 0) ? 1u : 0u;
+          umma_bf16(tO, da, make_desc_mn_sw128(sv0 + k * 2048, 16), idesc_pv64, acc);       // dims 0..63
+          umma_bf16(tO + 64, da, make_desc_sw32(sv1 + k * 512), idesc_pv16, acc);           // dims 64..79
+        }
+        umma_commit(p_empty);
+        umma_commit(v_empty);
+      };
+      for (int j = 0; j < n_tiles; ++j) {
+        const int st = j & 1;
+        const uint32_t u = static_cast<uint32_t>(j >> 1);
+        mbar_wait(&k_full[st], u & 1);
+        mbar_wait(s_empty, static_cast<uint32_t>(j & 1) ^ 1);
+        tc_fence_after();
+        const uint64_t dK0 = make_desc_k_sw128(smem_u32(sK + st * kTile));
+        const uint64_t dK1 = make_desc_sw32(smem_u32(sK + st * kTile + kBlk0));
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_bf16(tS, dQ0 + static_cast<uint64_t>(2 * k), dK0 + static_cast<uint64_t>(2 * k), idesc_qk, k > 0 ? 1u : 0u);
+        umma_bf16(tS, dQ1, dK1, idesc_qk, 1u);                     // dims 64..79 (72..79 are zero)
+        umma_commit(s_full);
+        umma_commit(&k_empty[st]);
+        if (j > 0) issue_pv(j - 1);
+      }
+      issue_pv(n_tiles - 1);
+    }
+  } else {
+    // ------------------------------ softmax ------------------------------
+    const int quad = warp & 3;
+    const int r = quad * 32 + lane;
+    const bool row_ok = q0 + r < n_q;
+    const uint32_t lane_addr = static_cast<uint32_t>(quad * 32) << 16;
+    const uint32_t tS = tmem_base + lane_addr + kColS, tO = tmem_base + lane_addr + kColO;
+    float m_run = -INFINITY, l_run = 0.f;
+    uint8_t* prow = sP + r * 128;
+    const int qpos = 1 << 30;                                  // no causal structure: every key is allowed
+    for (int j = 0; j < n_tiles; ++j) {
+      const int k0 = j * BN;
+      const bool full = k0 + BN <= kv_len;
+      mbar_wait(s_full, static_cast<uint32_t>(j & 1));
+      tc_fence_after();
+      float mx = m_run;
+      {
+        uint32_t va[32], vb[32];
+        tmem_ld_32x32(tS, va);
+#pragma unroll 1
+        for (int cc = 0; cc < 2; ++cc) {
+          tmem_ld_wait();
+          tmem_ld_32x32(tS + (2 * cc + 1) * 32, vb);
+          mx = fmaxf(mx, chunk_max(va, full, k0 + (2 * cc) * 32, kv_len, qpos, 0));
+          tmem_ld_wait();
+          if (cc == 0) tmem_ld_32x32(tS + 64, va);
+          mx = fmaxf(mx, chunk_max(vb, full, k0 + (2 * cc + 1) * 32, kv_len, qpos, 0));
+        }
+      }
+      const float base = (mx == -INFINITY) ? 0.f : mx * p.scale_log2;
+      const float alpha = (m_run == -INFINITY) ? 0.f : ex2_approx(m_run * p.scale_log2 - base);
+      if (j > 0) {
+        mbar_wait(p_empty, static_cast<uint32_t>((j - 1) & 1));
+        tc_fence_after();
+        if (__any_sync(0xffffffffu, mx != m_run)) {
+          uint32_t o0[32], o1[32], o2[16];
+          tmem_ld_32x32(tO, o0);
+          tmem_ld_32x32(tO + 32, o1);
+          tmem_ld_32x16(tO + 64, o2);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            o0[i] = __float_as_uint(__uint_as_float(o0[i]) * alpha);
+            o1[i] = __float_as_uint(__uint_as_float(o1[i]) * alpha);
+          }
+#pragma unroll
+          for (int i = 0; i < 16; ++i) o2[i] = __float_as_uint(__uint_as_float(o2[i]) * alpha);
+          tmem_st_32x32(tO, o0);
+          tmem_st_32x32(tO + 32, o1);
+          tmem_st_32x16(tO + 64, o2);
+          tmem_st_wait();
+        }
+      }
+      l_run *= alpha;
+      m_run = mx;
+      {
+        uint32_t va[32], vb[32];
+        tmem_ld_32x32(tS, va);
+#pragma unroll 1
+        for (int cc = 0; cc < 2; ++cc) {
+          tmem_ld_wait();
+          tmem_ld_32x32(tS + (2 * cc + 1) * 32, vb);
+          l_run += chunk_probs(va, full, k0 + (2 * cc) * 32, kv_len, qpos, 0, p.scale_log2, base,
+                               prow + cc * (BM * 128), 0, r);
+          tmem_ld_wait();
+          if (cc == 0) tmem_ld_32x32(tS + 64, va);
+          l_run += chunk_probs(vb, full, k0 + (2 * cc + 1) * 32, kv_len, qpos, 0, p.scale_log2, base,
+                               prow + cc * (BM * 128), 4, r);
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(s_empty);
+      fence_proxy_async_smem();
+      mbar_arrive(p_full);
+    }
+    // ---- epilogue: 72 of the 80 O columns ----
+    mbar_wait(p_empty, static_cast<uint32_t>((n_tiles - 1) & 1));
+    tc_fence_after();
+    const float inv = l_run > 0.f ? 1.0f / l_run : 0.f;
+    __nv_bfloat16* orow = p.out + (static_cast<long long>(row0) + q0 + r) * (static_cast<long long>(H) * HD) + head * HD;
+    uint32_t o0[32], o1[32], o2[16];
+    tmem_ld_32x32(tO, o0);
+    tmem_ld_32x32(tO + 32, o1);
+    tmem_ld_32x16(tO + 64, o2);
+    tmem_ld_wait();
+    if (row_ok) {
+      auto st8 = [&](const uint32_t* o, int col) {
+        uint4 w;
+        w.x = pack_bf16x2(__uint_as_float(o[0]) * inv, __uint_as_float(o[1]) * inv);
+        w.y = pack_bf16x2(__uint_as_float(o[2]) * inv, __uint_as_float(o[3]) * inv);
+        w.z = pack_bf16x2(__uint_as_float(o[4]) * inv, __uint_as_float(o[5]) * inv);
+        w.w = pack_bf16x2(__uint_as_float(o[6]) * inv, __uint_as_float(o[7]) * inv);
+        *reinterpret_cast<uint4*>(orow + col) = w;
+      };
+#pragma unroll
+      for (int g = 0; g < 4; ++g) { st8(o0 + 8 * g, 8 * g); st8(o1 + 8 * g, 32 + 8 * g); }
+      st8(o2, 64);                                           // dims 64..71; 72..79 are padding
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, fv::kTmemCols);
+  }
+}
+
+int vit_attention_tc(const __nv_bfloat16* qkv, int n_crops, int seq, int n_heads, __nv_bfloat16* out,
+                     cudaStream_t stream) {
+  if (n_crops <= 0) return set_error("vit_attention: empty batch");
+  const long long D = static_cast<long long>(n_heads) * 72;
+  const long long T = static_cast<long long>(n_crops) * seq;
+  CUtensorMap t64, t16;
+  // view [token][3*H heads][72]: reading dims 64..79 of a head zero-fills 72..79
+  if (make_tmap_bf16_3d(&t64, qkv, 72, 3LL * n_heads, T, 144, 3 * D * 2, 64, 1, 128, 128)) return 1;
+  if (make_tmap_bf16_3d(&t16, qkv, 72, 3LL * n_heads, T, 144, 3 * D * 2, 16, 1, 128, 32)) return 1;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(fa_tc_vit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, fv::kSmemTotal);
+    if (e != cudaSuccess) return set_error(cudaGetErrorString(e));
+    e = cudaFuncSetAttribute(fa_tc_vit_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                             cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return set_error(cudaGetErrorString(e));
+    configured = true;
+  }
+  FaVitParams p{};
+  p.seq = seq; p.n_heads = n_heads; p.out = out;
+  p.scale_log2 = (1.0f / sqrtf(72.0f)) * 1.4426950408889634f;
+  dim3 grid((seq + fv::BM - 1) / fv::BM, n_heads, n_crops);
+  fa_tc_vit_kernel<<<grid, fv::kThreads, fv::kSmemTotal, stream>>>(t64, t16, p);
+  count_launch();
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error(cudaGetErrorString(e));
+  return 0;
+}
+
 }  // namespace md

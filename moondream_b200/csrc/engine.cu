@@ -118,7 +118,8 @@ int vision_encode(Model& m, const uint8_t* crops, int n_crops, bf16* feats, void
     // x = x + attn(ln1(x))                                      vision.py:70, layers.py:155-166
     if (layernorm(x, D, b.ln1.w, b.ln1.b, ln, D, T, D, 1e-5f, st)) return 1;
     if (gemm_rowform(ln, D, b.qkv.w, D, T, 3 * D, D, EPI_BIAS, b.qkv.b, nullptr, 0, 0, qkv, 3 * D, 0, 0, 0, st)) return 1;
-    if (vit_attention(qkv, n_crops, tok, d.vis_heads, att, st)) return 1;
+    if (g_attention_impl == 1 ? vit_attention(qkv, n_crops, tok, d.vis_heads, att, st)
+                              : vit_attention_tc(qkv, n_crops, tok, d.vis_heads, att, st)) return 1;
     if (gemm_rowform(att, D, b.proj.w, D, T, D, D, EPI_BIAS_RESIDUAL, b.proj.b, x, D, 0, x, D, 0, 0, 0, st)) return 1;
     // x = x + fc2(gelu(fc1(ln2(x))))                            vision.py:71, layers.py:129-146
     if (layernorm(x, D, b.ln2.w, b.ln2.b, ln, D, T, D, 1e-5f, st)) return 1;

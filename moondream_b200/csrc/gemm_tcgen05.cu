@@ -390,6 +390,27 @@ static cudaEvent_t profile_event() {
   return g_prof.pool[g_prof.used++];
 }
 
+// bf16 3-D tensor [d2][d1][d0] (d0 contiguous) with byte strides s1, s2; box {b0, b1, b2}.
+int make_tmap_bf16_3d(CUtensorMap* tm, const void* base, long long d0, long long d1, long long d2,
+                      long long s1_bytes, long long s2_bytes, int b0, int b1, int b2, int swizzle_bytes) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return set_error("cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
+  if ((reinterpret_cast<uintptr_t>(base) & 15) || (s1_bytes % 16) || (s2_bytes % 16))
+    return set_error("TMA operand must be 16-byte aligned with 16-byte multiple strides");
+  cuuint64_t dims[3] = {static_cast<cuuint64_t>(d0), static_cast<cuuint64_t>(d1), static_cast<cuuint64_t>(d2)};
+  cuuint64_t strides[2] = {static_cast<cuuint64_t>(s1_bytes), static_cast<cuuint64_t>(s2_bytes)};
+  cuuint32_t box[3] = {static_cast<cuuint32_t>(b0), static_cast<cuuint32_t>(b1), static_cast<cuuint32_t>(b2)};
+  cuuint32_t estr[3] = {1, 1, 1};
+  const CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                              : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                              : swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE;
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error("cuTensorMapEncodeTiled (3-D) failed");
+  return 0;
+}
+
 static int g_num_sms = 0;
 int num_sms() {
   if (!g_num_sms) {

@@ -26,6 +26,8 @@ int num_sms();
 // ---- gemm_tcgen05.cu ----
 int make_tmap_bf16_2d(CUtensorMap* tm, const void* base, long long rows, long long cols,
                       long long ld, int box_rows);
+int make_tmap_bf16_3d(CUtensorMap* tm, const void* base, long long d0, long long d1, long long d2,
+                      long long s1_bytes, long long s2_bytes, int b0, int b1, int b2, int swizzle_bytes);
 int gemm_rowform(const __nv_bfloat16* A, long long lda, const __nv_bfloat16* W, long long ldw, int M,
                  int N, int K, int mode, const __nv_bfloat16* bias, const __nv_bfloat16* res,
                  long long ldr, int res_mod, __nv_bfloat16* out, long long ldo, int remap_gin,
@@ -83,6 +85,8 @@ int prefill_attention_tc(const __nv_bfloat16* q, int n_heads, int total_tokens, 
                          const int* start_pos, int n_seqs, int max_q, int prefix_len,
                          const __nv_bfloat16* kv_pool, int n_pages, int n_layers, const int* block_tables,
                          int max_blocks, int layer, __nv_bfloat16* out, cudaStream_t stream);
+int vit_attention_tc(const __nv_bfloat16* qkv, int n_crops, int seq, int n_heads, __nv_bfloat16* out,
+                     cudaStream_t stream);
 extern int g_attention_impl;   // 0 tcgen05, 1 legacy mma.sync
 
 // ---- attention.cu ----

@@ -35,9 +35,11 @@ def test_layernorm(rows, dim):
     assert ((y != ref).float().mean().item()) < 0.02
 
 
+@pytest.mark.parametrize("impl", [0, 1], ids=["tcgen05", "mma_sync"])
 @pytest.mark.parametrize("n_crops,heads", [(1, 16), (3, 2), (2, 10)])
-def test_vit_attention(n_crops, heads):
+def test_vit_attention(n_crops, heads, impl):
     N, lib = _lib()
+    lib.md_debug_attention_impl(impl)
     seq, hd = 729, 72
     D = heads * hd
     g = torch.Generator(device="cuda").manual_seed(n_crops * 10 + heads)
@@ -46,6 +48,7 @@ def test_vit_attention(n_crops, heads):
     N.check(lib.md_vit_attention_bf16(N.ptr(qkv), n_crops, seq, heads, N.ptr(out), N.current_stream()))
     q, k, v = [t.view(n_crops, seq, heads, hd).transpose(1, 2).float() for t in qkv.chunk(3, dim=-1)]
     ref = F.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(n_crops * seq, D)
+    lib.md_debug_attention_impl(0)
     assert rel(out, ref) < 6e-3, rel(out, ref)
 
 

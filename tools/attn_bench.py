@@ -45,3 +45,29 @@ lib.md_debug_attention_impl(0)
 import subprocess
 # occupancy probe
 print("done")
+
+# ---- ViT attention: 64 crops x 16 heads x 729 x 72 ----
+n_crops, vh, seq = 64, 16, 729
+Dv = vh * 72
+qkv = torch.randn(n_crops * seq, 3 * Dv, device="cuda").bfloat16()
+vout = torch.empty(n_crops * seq, Dv, device="cuda", dtype=torch.bfloat16)
+vflops = 4.0 * vh * n_crops * seq * seq * 72
+vres = {}
+for impl in (0, 1):
+    lib.md_debug_attention_impl(impl)
+    def runv():
+        N.check(lib.md_vit_attention_bf16(N.ptr(qkv), n_crops, seq, vh, N.ptr(vout), N.current_stream()))
+    for _ in range(3):
+        runv()
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(10):
+        runv()
+    e.record()
+    torch.cuda.synchronize()
+    ms = s.elapsed_time(e) / 10
+    vres[impl] = vout.float().clone()
+    print({"vit impl": ["tcgen05", "mma.sync"][impl], "ms": ms, "tflops": vflops / ms / 1e9}, flush=True)
+print("vit rel diff", ((vres[0] - vres[1]).norm() / vres[1].norm()).item())
+lib.md_debug_attention_impl(0)
