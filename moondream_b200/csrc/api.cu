@@ -9,6 +9,7 @@ namespace md {
 static thread_local char g_err[512] = "";
 static long long g_launches = 0;
 int g_attention_impl = 0;
+int g_pdl = 1;
 
 int set_error(const char* msg) {
   strncpy(g_err, msg ? msg : "unknown error", sizeof(g_err) - 1);
@@ -107,6 +108,7 @@ int md_prefill_attention_bf16(const void* q, int n_heads, int total_tokens, cons
                                   layer, BFM(out), STREAM(stream));
 }
 void md_debug_attention_impl(int impl) { md::g_attention_impl = impl; }
+void md_debug_set_pdl(int enable) { md::g_pdl = enable; }
 
 int md_decode_attention_bf16(const void* q, int n_heads, const int* pos, int n_seqs, const md_kv* kv,
                              int layer, void* out, void* stream) {

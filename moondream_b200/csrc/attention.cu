@@ -342,6 +342,8 @@ decode_attention_kernel(const __nv_bfloat16* __restrict__ q, int n_heads, const 
                         const __nv_bfloat16* __restrict__ kv_pool, int n_pages,
                         const int* __restrict__ block_tables, int max_blocks, int layer,
                         __nv_bfloat16* __restrict__ out, long long ld_out, float scale_log2) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int head = blockIdx.x, seq = blockIdx.y;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int sub = lane & 7;            // which 16-byte chunk (8 dims) of the 64-dim row
@@ -433,11 +435,9 @@ int decode_attention(const __nv_bfloat16* q, int n_heads, const int* pos, int n_
                      int max_blocks, int layer, __nv_bfloat16* out, long long ld_out, cudaStream_t stream) {
   if (n_seqs <= 0) return set_error("decode_attention: empty batch");
   dim3 grid(n_heads, n_seqs);
-  decode_attention_kernel<<<grid, 128, 0, stream>>>(q, n_heads, pos, kv_pool, n_pages, block_tables,
-                                                    max_blocks, layer, out, ld_out,
-                                                    0.125f * 1.4426950408889634f);
   count_launch();
-  cudaError_t e = cudaGetLastError();
+  cudaError_t e = launch_k(decode_attention_kernel, grid, dim3(128), 0, stream, q, n_heads, pos, kv_pool, n_pages,
+                           block_tables, max_blocks, layer, out, ld_out, 0.125f * 1.4426950408889634f);
   if (e != cudaSuccess) return set_error(cudaGetErrorString(e));
   return 0;
 }

@@ -8,6 +8,13 @@
 
 namespace md {
 
+#define MD_LAUNCH(kernel, grid, block, smem, stream, ...)                                   \
+  do {                                                                                      \
+    count_launch();                                                                         \
+    cudaError_t e__ = launch_k(kernel, grid, block, smem, stream, __VA_ARGS__);             \
+    if (e__ != cudaSuccess) return set_error(cudaGetErrorString(e__));                      \
+  } while (0)
+
 #define MD_CHECK_LAUNCH()                                        \
   do {                                                           \
     count_launch();                                              \
@@ -26,6 +33,8 @@ __global__ void __launch_bounds__(256)
 layernorm_kernel(const __nv_bfloat16* __restrict__ x, long long ldx,
                  const __nv_bfloat16* __restrict__ w, const __nv_bfloat16* __restrict__ b,
                  __nv_bfloat16* __restrict__ y, long long ldy, int rows, int dim, float eps) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -89,8 +98,7 @@ int layernorm(const __nv_bfloat16* x, long long ldx, const __nv_bfloat16* w, con
               __nv_bfloat16* y, long long ldy, int rows, int dim, float eps, cudaStream_t stream) {
   if (rows <= 0) return set_error("layernorm: empty input");
   if (dim % 8 || dim > kLnMaxChunks * 32 * 8) return set_error("layernorm: dim must be a multiple of 8 and <= 4096");
-  layernorm_kernel<<<(rows + 7) / 8, 256, 0, stream>>>(x, ldx, w, b, y, ldy, rows, dim, eps);
-  MD_CHECK_LAUNCH();
+  MD_LAUNCH(layernorm_kernel, dim3((rows + 7) / 8), dim3(256), 0, stream, x, ldx, w, b, y, ldy, rows, dim, eps);
   return 0;
 }
 
@@ -201,6 +209,8 @@ int stitch_pool_concat(const __nv_bfloat16* feats, const int* crop_offsets, cons
 __global__ void __launch_bounds__(128)
 embed_kernel(const int* __restrict__ ids, long long id_stride, const __nv_bfloat16* __restrict__ wte,
              int dim, int vocab, __nv_bfloat16* __restrict__ out, long long ldo) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int row = blockIdx.x;
   int id = ids[row * id_stride];
   if (id < 0 || id >= vocab) id = 0;
@@ -212,8 +222,7 @@ embed_kernel(const int* __restrict__ ids, long long id_stride, const __nv_bfloat
 int embed_tokens(const int* ids, long long id_stride, int n, const __nv_bfloat16* wte, int dim,
                  int vocab, __nv_bfloat16* out, long long ldo, cudaStream_t stream) {
   if (n <= 0) return set_error("embed_tokens: empty input");
-  embed_kernel<<<n, 128, 0, stream>>>(ids, id_stride, wte, dim, vocab, out, ldo);
-  MD_CHECK_LAUNCH();
+  MD_LAUNCH(embed_kernel, dim3(n), dim3(128), 0, stream, ids, id_stride, wte, dim, vocab, out, ldo);
   return 0;
 }
 
@@ -232,6 +241,8 @@ rope_kv_write_kernel(const __nv_bfloat16* __restrict__ qkv, int n_tokens, int n_
                      const float* __restrict__ freqs, __nv_bfloat16* __restrict__ q_out,
                      __nv_bfloat16* __restrict__ kv_pool, int n_pages,
                      const int* __restrict__ block_tables, int max_blocks, int layer) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int gw = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (gw >= n_tokens * n_heads) return;
@@ -282,10 +293,8 @@ int rope_kv_write(const __nv_bfloat16* qkv, int n_tokens, int n_heads, const int
                   int layer, cudaStream_t stream) {
   if (n_tokens <= 0) return set_error("rope_kv_write: empty input");
   const int warps = n_tokens * n_heads;
-  rope_kv_write_kernel<<<(warps + 7) / 8, 256, 0, stream>>>(qkv, n_tokens, n_heads, q_offsets, start_pos,
-                                                          n_seqs, freqs, q_out, kv_pool, n_pages,
-                                                          block_tables, max_blocks, layer);
-  MD_CHECK_LAUNCH();
+  MD_LAUNCH(rope_kv_write_kernel, dim3((warps + 7) / 8), dim3(256), 0, stream, qkv, n_tokens, n_heads, q_offsets,
+            start_pos, n_seqs, freqs, q_out, kv_pool, n_pages, block_tables, max_blocks, layer);
   return 0;
 }
 
@@ -337,6 +346,8 @@ argmax_partial_kernel(const float* __restrict__ ws, int splits, int B, int V, in
                       float* __restrict__ part_best, float* __restrict__ part_second, int* __restrict__ part_idx,
                       int* __restrict__ out_ids, long long out_stride, const int* __restrict__ out_index,
                       float* __restrict__ out_margin, __nv_bfloat16* __restrict__ out_logits) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int part = blockIdx.x, b = blockIdx.y;
   const int per = (V + parts - 1) / parts;
   const int v0 = part * per, v1 = min(V, v0 + per);
@@ -373,6 +384,8 @@ __global__ void __launch_bounds__(128)
 argmax_final_kernel(const float* __restrict__ part_best, const float* __restrict__ part_second,
                     const int* __restrict__ part_idx, int B, int parts, int* __restrict__ out_ids,
                     long long out_stride, const int* __restrict__ out_index, float* __restrict__ out_margin) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int b = blockIdx.x * 4 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (b >= B) return;
@@ -405,14 +418,11 @@ int argmax_logits(const float* ws, int splits, int B, int V, const __nv_bfloat16
   float* pb = scratch;
   float* ps = scratch ? scratch + 1LL * B * kArgmaxMaxParts : nullptr;
   int* pi = scratch ? reinterpret_cast<int*>(scratch + 2LL * B * kArgmaxMaxParts) : nullptr;
-  argmax_partial_kernel<<<dim3(parts, B), 512, 0, stream>>>(ws, splits, B, V, parts, bias, bias_period, mask_id,
-                                                           pb, ps, pi, out_ids, out_stride, out_index,
-                                                           out_margin, out_logits);
-  MD_CHECK_LAUNCH();
+  MD_LAUNCH(argmax_partial_kernel, dim3(parts, B), dim3(512), 0, stream, ws, splits, B, V, parts, bias,
+            bias_period, mask_id, pb, ps, pi, out_ids, out_stride, out_index, out_margin, out_logits);
   if (parts > 1) {
-    argmax_final_kernel<<<(B + 3) / 4, 128, 0, stream>>>(pb, ps, pi, B, parts, out_ids, out_stride, out_index,
-                                                        out_margin);
-    MD_CHECK_LAUNCH();
+    MD_LAUNCH(argmax_final_kernel, dim3((B + 3) / 4), dim3(128), 0, stream, pb, ps, pi, B, parts, out_ids,
+              out_stride, out_index, out_margin);
   }
   return 0;
 }
@@ -423,6 +433,8 @@ int argmax_logits(const float* ws, int splits, int B, int V, const __nv_bfloat16
 __global__ void decode_advance_kernel(int* cur_tok, int* pos, int* step, const int* preds,
                                       const int* forced, long long stride, int batch, int eos_id,
                                       int* finished) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int s = *step;
   for (int b = threadIdx.x; b < batch; b += blockDim.x) {
     const int t = (forced ? forced : preds)[b * stride + s + 1];
@@ -436,15 +448,16 @@ __global__ void decode_advance_kernel(int* cur_tok, int* pos, int* step, const i
 
 int decode_advance(int* cur_tok, int* pos, int* step, const int* preds, const int* forced,
                    long long stride, int batch, int eos_id, int* finished, cudaStream_t stream) {
-  decode_advance_kernel<<<1, 256, 0, stream>>>(cur_tok, pos, step, preds, forced, stride, batch, eos_id,
-                                               finished);
-  MD_CHECK_LAUNCH();
+  MD_LAUNCH(decode_advance_kernel, dim3(1), dim3(256), 0, stream, cur_tok, pos, step, preds, forced, stride, batch,
+            eos_id, finished);
   return 0;
 }
 
 __global__ void __launch_bounds__(128)
 gather_rows_kernel(const __nv_bfloat16* __restrict__ src, long long ld_src, const int* __restrict__ idx,
                    int dim, __nv_bfloat16* __restrict__ out, long long ldo) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int row = blockIdx.x;
   const uint4* s = reinterpret_cast<const uint4*>(src + static_cast<long long>(idx[row]) * ld_src);
   uint4* d = reinterpret_cast<uint4*>(out + static_cast<long long>(row) * ldo);
@@ -455,8 +468,7 @@ int gather_rows(const __nv_bfloat16* src, long long ld_src, const int* idx, int 
                 __nv_bfloat16* out, long long ldo, cudaStream_t stream) {
   if (n <= 0) return set_error("gather_rows: empty input");
   if (dim % 8) return set_error("gather_rows: dim must be a multiple of 8");
-  gather_rows_kernel<<<n, 128, 0, stream>>>(src, ld_src, idx, dim, out, ldo);
-  MD_CHECK_LAUNCH();
+  MD_LAUNCH(gather_rows_kernel, dim3(n), dim3(128), 0, stream, src, ld_src, idx, dim, out, ldo);
   return 0;
 }
 
@@ -530,6 +542,8 @@ decode_qkv_mlp_epilogue_kernel(const float* __restrict__ ws, int splits, int B, 
                                __nv_bfloat16* __restrict__ hid, long long ld_hid,
                                __nv_bfloat16* __restrict__ kv_pool, int n_pages,
                                const int* __restrict__ block_tables, int max_blocks, int layer) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int unit = blockIdx.x * 4 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   const int b = blockIdx.y;
@@ -580,10 +594,8 @@ int decode_qkv_mlp_epilogue(const float* ws, int splits, int B, int D, int FF, i
   if (D % 64 || FF % 64) return set_error("decode epilogue: dims must be multiples of 64");
   const int units = (3 * D + FF) / 64;
   dim3 grid((units + 3) / 4, B);
-  decode_qkv_mlp_epilogue_kernel<<<grid, 128, 0, stream>>>(ws, splits, B, D, FF, n_heads, bias, pos, freqs,
-                                                          q_out, hid, ld_hid, kv_pool, n_pages, block_tables,
-                                                          max_blocks, layer);
-  MD_CHECK_LAUNCH();
+  MD_LAUNCH(decode_qkv_mlp_epilogue_kernel, grid, dim3(128), 0, stream, ws, splits, B, D, FF, n_heads, bias, pos,
+            freqs, q_out, hid, ld_hid, kv_pool, n_pages, block_tables, max_blocks, layer);
   return 0;
 }
 
@@ -593,6 +605,8 @@ decode_residual_ln_epilogue_kernel(const float* __restrict__ ws, int splits, int
                                    const __nv_bfloat16* __restrict__ bias_fc2, __nv_bfloat16* __restrict__ x,
                                    const __nv_bfloat16* __restrict__ ln_w, const __nv_bfloat16* __restrict__ ln_b,
                                    __nv_bfloat16* __restrict__ ln_out, float eps) {
+  pdl_launch_dependents();
+  pdl_wait();
   constexpr int kMaxChunks = 2;                        // 8-element chunks per thread: D <= 4096
   const int b = blockIdx.x;
   const int tid = threadIdx.x;
@@ -678,9 +692,8 @@ int decode_residual_ln_epilogue(const float* ws, int splits, int proj_splits, in
                                 __nv_bfloat16* x, const __nv_bfloat16* ln_w, const __nv_bfloat16* ln_b,
                                 __nv_bfloat16* ln_out, cudaStream_t stream) {
   if (D > 4096 || D % 8) return set_error("decode epilogue: dim must be a multiple of 8 and <= 4096");
-  decode_residual_ln_epilogue_kernel<<<B, 256, 0, stream>>>(ws, splits, proj_splits, B, D, bias_proj,
-                                                           bias_fc2, x, ln_w, ln_b, ln_out, 1e-5f);
-  MD_CHECK_LAUNCH();
+  MD_LAUNCH(decode_residual_ln_epilogue_kernel, dim3(B), dim3(256), 0, stream, ws, splits, proj_splits, B, D,
+            bias_proj, bias_fc2, x, ln_w, ln_b, ln_out, 1e-5f);
   return 0;
 }
 

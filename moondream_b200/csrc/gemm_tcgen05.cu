@@ -81,6 +81,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int rank = (CG == 2) ? static_cast<int>(cluster_ctarank()) : 0;
   const bool leader = rank == 0;
 
+  pdl_launch_dependents();
   if (warp == 0 && lane == 0) {
     prefetch_tensormap(&tmA);
     prefetch_tensormap(&tmB);
@@ -104,6 +105,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (CG == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_wait();                           // everything above overlapped the previous kernel's tail
 
   const int total_tiles = p.m_blocks * p.n_blocks * p.k_splits;
   const int kb_per_split = p.kb_per_split;
@@ -289,6 +291,8 @@ __global__ void splitk_epilogue_kernel(const float* __restrict__ ws, int splits,
                                        int mode, const __nv_bfloat16* __restrict__ bias,
                                        const __nv_bfloat16* __restrict__ res, long long ldr,
                                        __nv_bfloat16* __restrict__ out, long long ldo) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int n = (blockIdx.x * blockDim.x + threadIdx.x) * 2;
   const int b = blockIdx.y;
   if (n >= N) return;
@@ -442,13 +446,15 @@ static int launch_gemm(const CUtensorMap& tA, const CUtensorMap& tB, const GemmP
   cfg.blockDim = dim3(kGemmThreads);
   cfg.dynamicSmemBytes = S::kTotal;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CG;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = g_pdl ? 1 : 0;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = 2;
   cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_bf16_kernel<BN, STAGES, CG>, tA, tB, p);
   count_launch();
   if (e != cudaSuccess) return set_error(cudaGetErrorString(e));
@@ -575,9 +581,8 @@ int splitk_epilogue(const float* ws, int splits, int B, int N, int mode, const _
                     cudaStream_t stream) {
   if (N % 2) return set_error("splitk_epilogue: N must be even");
   dim3 grid((N / 2 + 127) / 128, B);
-  splitk_epilogue_kernel<<<grid, 128, 0, stream>>>(ws, splits, B, N, mode, bias, res, ldr, out, ldo);
+  cudaError_t e = launch_k(splitk_epilogue_kernel, grid, dim3(128), 0, stream, ws, splits, B, N, mode, bias, res, ldr, out, ldo);
   count_launch();
-  cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(cudaGetErrorString(e));
   return 0;
 }

@@ -23,6 +23,25 @@ long long launch_count();
 void reset_launch_count();
 int num_sms();
 
+// Launch with programmatic stream serialization (PDL) when enabled: the kernel must call pdl_wait()
+// before touching memory its predecessor produced.
+extern int g_pdl;
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                            Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = g_pdl ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // ---- gemm_tcgen05.cu ----
 int make_tmap_bf16_2d(CUtensorMap* tm, const void* base, long long rows, long long cols,
                       long long ld, int box_rows);

@@ -16,6 +16,16 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
 
 // ----------------------------------------------------------------------------------------------
+// programmatic dependent launch: a kernel may start (prologue) while its predecessor drains;
+// pdl_wait() blocks until the predecessor grid has completed and its writes are visible.
+// Both are no-ops for a kernel launched without the attribute.
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_launch_dependents() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+// ----------------------------------------------------------------------------------------------
 // mbarrier
 // ----------------------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {

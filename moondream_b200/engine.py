@@ -16,7 +16,7 @@ import torch
 
 from . import _native as N
 from .config import MoondreamConfig
-from .image_crops import overlap_crop_image
+from .image_crops import crop_tiling, overlap_crop_image
 from .synth import state_dict_spec
 
 PAGE = 64
@@ -158,6 +158,9 @@ class Engine:
         self.cfg = cfg
         self.device = torch.device(device)
         self.lib = N.lib()
+        import os as _os0
+        if _os0.environ.get("MD_PDL") is not None:          # A/B switch for profiling runs
+            self.lib.md_debug_set_pdl(int(_os0.environ["MD_PDL"]))
         prepared, self.patch_k, self.vis_ff = prepare_weights(cfg, state_dict)
         self.weights, self._owners = upload_weights(cfg, prepared, self.device)   # keeps device memory alive
         del prepared
@@ -184,6 +187,11 @@ class Engine:
         self.pages = PagePool(cfg, kv_pages, self.device)
         self._ws: Optional[torch.Tensor] = None
         self._decode_state: Dict[int, dict] = {}
+        self._stage: Optional[torch.Tensor] = None
+        import concurrent.futures
+        import os as _os
+        n_cpu = len(_os.sched_getaffinity(0)) if hasattr(_os, "sched_getaffinity") else (_os.cpu_count() or 1)
+        self._pool = concurrent.futures.ThreadPoolExecutor(max_workers=max(1, min(8, n_cpu)))
 
     def __del__(self):
         try:
@@ -294,15 +302,27 @@ class Engine:
     def encode_images(self, images: Sequence[np.ndarray], return_hidden: bool = False):
         """Host uint8 HxWx3 images -> crops (PIL Lanczos, image_crops.py:58-167) -> H2D -> encode_crops."""
         v = self.cfg.vision
-        crops, offsets, tilings = [], [0], []
-        for im in images:
-            oc = overlap_crop_image(im, overlap_margin=v.overlap_margin, max_crops=v.max_crops,
-                                    base_size=(v.crop_size, v.crop_size), patch_size=v.enc_patch_size)
-            crops.append(oc["crops"])
-            tilings.append(oc["tiling"])
-            offsets.append(offsets[-1] + oc["crops"].shape[0])
-        host = torch.from_numpy(np.concatenate(crops, axis=0)).pin_memory()
-        dev = host.to(self.device, non_blocking=True)
+        kw = dict(overlap_margin=v.overlap_margin, max_crops=v.max_crops,
+                  base_size=(v.crop_size, v.crop_size), patch_size=v.enc_patch_size)
+        tilings = [crop_tiling(im.shape, **kw) for im in images]
+        offsets = [0]
+        for th, tw in tilings:
+            offsets.append(offsets[-1] + th * tw + 1)
+        # crops are written straight into persistent pinned staging memory by a small thread pool
+        # (PIL's resize and numpy's copies release the GIL)
+        n = offsets[-1]
+        if self._stage is None or self._stage.shape[0] < n:
+            self._stage = torch.empty((max(n, 64), v.crop_size, v.crop_size, 3), dtype=torch.uint8).pin_memory()
+        stage_np = self._stage.numpy()
+
+        def work(i):
+            overlap_crop_image(images[i], out=stage_np[offsets[i]: offsets[i + 1]], **kw)
+
+        if len(images) > 1:
+            list(self._pool.map(work, range(len(images))))
+        else:
+            work(0)
+        dev = self._stage[:n].to(self.device, non_blocking=True)
         return self.encode_crops(dev, offsets, tilings, return_hidden=return_hidden)
 
     def prefix_kv_tensors(self, prefix: PrefixKV) -> List[Tuple[torch.Tensor, torch.Tensor]]:

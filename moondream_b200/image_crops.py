@@ -50,6 +50,8 @@ def select_tiling(height: int, width: int, crop_size: int, max_crops: int) -> Tu
 
 
 def _resize(image: np.ndarray, out_h: int, out_w: int) -> np.ndarray:
+    if image.shape[0] == out_h and image.shape[1] == out_w:
+        return image        # PIL (Image.resize) and vips return an unchanged copy for a same-size resize
     if HAS_VIPS:  # pragma: no cover
         vimg = pyvips.Image.new_from_array(image)
         return vimg.resize(out_w / image.shape[1], vscale=out_h / image.shape[0]).numpy()
@@ -57,21 +59,39 @@ def _resize(image: np.ndarray, out_h: int, out_w: int) -> np.ndarray:
                                                      resample=Image.Resampling.LANCZOS))
 
 
-def overlap_crop_image(image: np.ndarray, overlap_margin: int, max_crops: int,
-                       base_size: Tuple[int, int] = (378, 378), patch_size: int = 14
-                       ) -> OverlapCropOutput:
-    """Global crop (index 0) + rows*cols overlapping local crops, all `base_size`, uint8 HWC."""
+def crop_tiling(image_shape, overlap_margin: int, max_crops: int, base_size: Tuple[int, int] = (378, 378),
+                patch_size: int = 14) -> Tuple[int, int]:
+    """The (rows, cols) grid `overlap_crop_image` will use for an image of this shape."""
     margin_px = patch_size * overlap_margin
     window = (base_size[0] // patch_size - 2 * overlap_margin) * patch_size
-    rows, cols = select_tiling(image.shape[0] - 2 * margin_px, image.shape[1] - 2 * margin_px,
-                               window, max_crops)
-    crops = np.zeros((rows * cols + 1, base_size[0], base_size[1], image.shape[2]), dtype=np.uint8)
+    return select_tiling(image_shape[0] - 2 * margin_px, image_shape[1] - 2 * margin_px, window, max_crops)
+
+
+def overlap_crop_image(image: np.ndarray, overlap_margin: int, max_crops: int,
+                       base_size: Tuple[int, int] = (378, 378), patch_size: int = 14,
+                       out: np.ndarray = None) -> OverlapCropOutput:
+    """Global crop (index 0) + rows*cols overlapping local crops, all `base_size`, uint8 HWC.
+    `out` (optional, beyond the reference's signature): a preallocated uint8
+    [rows*cols + 1, H, W, C] array (e.g. a slice of pinned staging memory) to write into."""
+    margin_px = patch_size * overlap_margin
+    window = (base_size[0] // patch_size - 2 * overlap_margin) * patch_size
+    rows, cols = crop_tiling(image.shape, overlap_margin, max_crops, base_size, patch_size)
+    shape = (rows * cols + 1, base_size[0], base_size[1], image.shape[2])
+    if out is None:
+        crops = np.zeros(shape, dtype=np.uint8)
+    else:
+        if tuple(out.shape) != shape or out.dtype != np.uint8:
+            raise ValueError(f"out must be uint8 {shape}")
+        crops = out
     canvas = _resize(image, rows * window + 2 * margin_px, cols * window + 2 * margin_px)
     crops[0] = _resize(image, base_size[0], base_size[1])
     for r in range(rows):
         for c in range(cols):
             tile = canvas[r * window: r * window + base_size[0], c * window: c * window + base_size[1]]
-            crops[1 + r * cols + c, : tile.shape[0], : tile.shape[1]] = tile
+            dst = crops[1 + r * cols + c]
+            if out is not None and (tile.shape[0] < base_size[0] or tile.shape[1] < base_size[1]):
+                dst[...] = 0                      # partially covered tile: clear the staging slot first
+            dst[: tile.shape[0], : tile.shape[1]] = tile
     return {"crops": crops, "tiling": (rows, cols)}
 
 
