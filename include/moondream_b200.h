@@ -114,7 +114,8 @@ int md_prefill_attention_bf16(const void* q, int n_heads, int total_tokens, cons
                               const md_kv* kv, int layer, void* out, void* stream);
 /* Testing / A-B timing only: 0 = tcgen05 attention (default), 1 = the legacy mma.sync kernel. */
 void md_debug_attention_impl(int impl);
-/* Testing / A-B timing only: programmatic dependent launch between consecutive kernels (default on). */
+/* Testing / A-B timing only: programmatic dependent launch between consecutive kernels (default off:
+ * measured slower on the decode graph in round 1). */
 void md_debug_set_pdl(int enable);
 
 /* One-query attention for decode (text.py:46-50 with the [1,1,2048] mask of moondream.py:472-474). */
