@@ -342,7 +342,6 @@ decode_attention_kernel(const __nv_bfloat16* __restrict__ q, int n_heads, const 
                         const __nv_bfloat16* __restrict__ kv_pool, int n_pages,
                         const int* __restrict__ block_tables, int max_blocks, int layer,
                         __nv_bfloat16* __restrict__ out, long long ld_out, float scale_log2) {
-  pdl_launch_dependents();
   pdl_wait();
   const int head = blockIdx.x, seq = blockIdx.y;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;

@@ -81,7 +81,6 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int rank = (CG == 2) ? static_cast<int>(cluster_ctarank()) : 0;
   const bool leader = rank == 0;
 
-  pdl_launch_dependents();
   if (warp == 0 && lane == 0) {
     prefetch_tensormap(&tmA);
     prefetch_tensormap(&tmB);
