@@ -104,7 +104,6 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (CG == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
-  pdl_wait();                           // everything above overlapped the previous kernel's tail
 
   const int total_tiles = p.m_blocks * p.n_blocks * p.k_splits;
   const int kb_per_split = p.kb_per_split;
@@ -115,6 +114,23 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      // Swapped form: the A operand is a weight matrix, which no earlier kernel produces.  Under
+      // programmatic dependent launch this CTA may be running while its predecessor drains, so the
+      // weight tiles of the first ring of stages are requested before the dependency wait; only the
+      // activation (B) loads and everything downstream of them wait for the predecessor.
+      int prefetched = 0;
+      if (CG == 1 && p.mode == EPI_PARTIAL && unit < total_tiles) {
+        const int split = unit % p.k_splits;
+        const int m_blk = (unit / p.k_splits) / p.n_blocks;
+        const int kb0 = split * kb_per_split;
+        const int kb1 = min(p.k_blocks, kb0 + kb_per_split);
+        prefetched = min(STAGES, kb1 - kb0);
+        for (int i = 0; i < prefetched; ++i) {
+          mbar_arrive_expect_tx(&full_bar[i], S::kStageBytes);
+          tma_load_2d(smem + i * S::kStageBytes, &tmA, &full_bar[i], (kb0 + i) * BK, m_blk * BM);
+        }
+      }
+      pdl_wait();
       for (int tile = unit; tile < total_tiles; tile += n_units) {
         const int split = tile % p.k_splits;
         const int t2 = tile / p.k_splits;
@@ -125,18 +141,24 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int a_row = m_blk * (BM * CG) + rank * BM;
         const int b_row = n_blk * BN + rank * (BN / CG);
         for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * S::kStageBytes;
           uint8_t* sb = sa + S::kABytes;
-          if (CG == 2) {
-            if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * S::kStageBytes);
-            else mbar_arrive_leader(&full_bar[stage]);
-            tma_load_2d_pair(sa, &tmA, &full_bar[stage], kb * BK, a_row);
-            tma_load_2d_pair(sb, &tmB, &full_bar[stage], kb * BK, b_row);
-          } else {
-            mbar_arrive_expect_tx(&full_bar[stage], S::kStageBytes);
-            tma_load_2d(sa, &tmA, &full_bar[stage], kb * BK, a_row);
+          if (prefetched > 0) {
+            // stage already armed and its weight tile in flight: add the activation tile
+            --prefetched;
             tma_load_2d(sb, &tmB, &full_bar[stage], kb * BK, b_row);
+          } else {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            if (CG == 2) {
+              if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * S::kStageBytes);
+              else mbar_arrive_leader(&full_bar[stage]);
+              tma_load_2d_pair(sa, &tmA, &full_bar[stage], kb * BK, a_row);
+              tma_load_2d_pair(sb, &tmB, &full_bar[stage], kb * BK, b_row);
+            } else {
+              mbar_arrive_expect_tx(&full_bar[stage], S::kStageBytes);
+              tma_load_2d(sa, &tmA, &full_bar[stage], kb * BK, a_row);
+              tma_load_2d(sb, &tmB, &full_bar[stage], kb * BK, b_row);
+            }
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -145,6 +167,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   } else if (warp == 1) {
     // ------------------------------ MMA issuer (leader CTA only) ------------------------------
     if (lane == 0 && leader) {
+      pdl_wait();
       constexpr uint32_t idesc = make_idesc_bf16_f32(BM * CG, BN);
       int stage = 0;
       uint32_t phase = 0;
@@ -181,6 +204,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else if (warp >= 4) {
     // ------------------------------ epilogue ------------------------------
+    pdl_wait();                             // global reads (residual) and writes must follow the predecessor
     const int q = warp & 3;                 // TMEM lane quadrant this warp may read
     const int half = (warp - 4) >> 2;       // the two warps of a quadrant interleave 32-column chunks
     int it = 0;
