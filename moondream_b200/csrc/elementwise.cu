@@ -621,13 +621,28 @@ decode_residual_ln_epilogue_kernel(const float* __restrict__ ws, int splits, int
     float a[8], m[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) a[k] = m[k] = 0.f;
-    // all loads of a thread are independent 16-byte reads: the split loop pipelines freely
-    for (int s = 0; s < splits; ++s) {
-      const float4* src = reinterpret_cast<const float4*>(ws + (static_cast<long long>(s) * B + b) * D + d0);
-      const float4 lo = src[0], hi = src[1];
-      float* dst = s < proj_splits ? a : m;
-      dst[0] += lo.x; dst[1] += lo.y; dst[2] += lo.z; dst[3] += lo.w;
-      dst[4] += hi.x; dst[5] += hi.y; dst[6] += hi.z; dst[7] += hi.w;
+    // all loads of a thread are independent 16-byte reads: issue them in batches of four splits so the
+    // L2 round trips overlap instead of forming a chain
+    const long long sstride = static_cast<long long>(B) * D;
+    const float* base_ptr = ws + static_cast<long long>(b) * D + d0;
+    for (int s0 = 0; s0 < splits; s0 += 4) {
+      float4 lo[4], hi[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (s0 + u < splits) {
+          const float4* src = reinterpret_cast<const float4*>(base_ptr + (s0 + u) * sstride);
+          lo[u] = src[0];
+          hi[u] = src[1];
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (s0 + u < splits) {
+          float* dst = (s0 + u) < proj_splits ? a : m;
+          dst[0] += lo[u].x; dst[1] += lo[u].y; dst[2] += lo[u].z; dst[3] += lo[u].w;
+          dst[4] += hi[u].x; dst[5] += hi[u].y; dst[6] += hi[u].z; dst[7] += hi[u].w;
+        }
+      }
     }
     const uint4 bp = *reinterpret_cast<const uint4*>(bias_proj + d0);
     const uint4 bf = *reinterpret_cast<const uint4*>(bias_fc2 + d0);

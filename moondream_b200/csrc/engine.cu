@@ -271,11 +271,13 @@ int text_decode_step(Model& m, bf16* x, const int* pos, int batch, const md_kv& 
   if (layernorm(x, D, m.txt[0].ln.w, m.txt[0].ln.b, ln, D, batch, D, 1e-5f, st)) return 1;
   for (int i = 0; i < d.txt_layers; ++i) {
     const TxtBlock& b = m.txt[i];
-    // [qkv ; fc1] share the input l = ln(x) (text.py:145-157): one weight stream
-    const int s1 = gemm_swapped(b.qkv.w, D, ln, D, 3 * D + FF, batch, D, gemm_swapped_splits(3 * D + FF, D), wsf, st);
-    if (s1 < 0) return 1;
-    if (decode_qkv_mlp_epilogue(wsf, s1, batch, D, FF, H, b.qkv.b, pos, m.rope, q, xcat + D, D + FF, pool,
-                                kv.n_pages, kv.block_tables, kv.max_blocks, i, st)) return 1;
+    // [qkv ; fc1] share the input l = ln(x) (text.py:145-157): one weight stream whose epilogue applies
+    // bias, RoPE, the KV-page write and GELU directly (no split-K, no fp32 round trip)
+    DecodeEpilogue de{};
+    de.D = D; de.FF = FF; de.n_heads = H; de.bias = b.qkv.b; de.pos = pos; de.freqs = m.rope; de.q_out = q;
+    de.hid = xcat + D; de.ld_hid = D + FF; de.kv_pool = pool; de.n_pages = kv.n_pages;
+    de.block_tables = kv.block_tables; de.max_blocks = kv.max_blocks; de.layer = i;
+    if (gemm_swapped_decode(b.qkv.w, D, ln, D, 3 * D + FF, batch, D, de, st)) return 1;
     if (decode_attention(q, H, pos, batch, pool, kv.n_pages, kv.block_tables, kv.max_blocks, i, xcat, D + FF, st)) return 1;
     // proj(att) and fc2(hid) both land in the residual: one K-concatenated weight stream
     const int s2 = gemm_swapped_kb(b.proj.w, D + FF, xcat, D + FF, D, batch, D + FF, kb, wsf, st);

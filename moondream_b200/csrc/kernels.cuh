@@ -13,6 +13,7 @@ enum : int {
   EPI_BIAS_GELU = 1,       // out = bf16(gelu_tanh(bf16(acc + bias)))
   EPI_BIAS_RESIDUAL = 2,   // out = bf16(bf16(acc + bias) + residual)
   EPI_PARTIAL = 3,         // swapped form: fp32 partial sums to workspace
+  EPI_DECODE_QKV_MLP = 4,  // swapped form, no split-K: bias + RoPE + KV-page write (qkv rows), bias + GELU (fc1 rows)
 };
 
 // error plumbing: every entry point returns 0 on success; the message is kept per thread.
@@ -57,6 +58,24 @@ int gemm_profile_read(double* total_ms, double* total_flops, long long* launches
 int gemm_swapped_splits(int n_out, int K);
 int gemm_swapped(const __nv_bfloat16* W, long long ldw, const __nv_bfloat16* X, long long ldx,
                  int n_out, int batch, int K, int splits, float* ws, cudaStream_t stream);
+// Decode-step [qkv ; fc1] stream with everything downstream fused into the GEMM epilogue (text.py:30-43,
+// moondream.py:74-78, layers.py:130,137): rows < 3D are q|k|v features (bias, bf16 round, partial RoPE,
+// q -> q_out, k/v -> KV pages), rows >= 3D are fc1 features (bias, round, GELU -> hid).
+struct DecodeEpilogue {
+  int D, FF, n_heads;
+  const __nv_bfloat16* bias;      // [3D + FF]
+  const int* pos;                 // [batch]
+  const float* freqs;             // rope table [ctx][16][2]
+  __nv_bfloat16* q_out;           // [batch, D]
+  __nv_bfloat16* hid;             // [batch, *] row pitch ld_hid
+  long long ld_hid;
+  __nv_bfloat16* kv_pool;
+  int n_pages;
+  const int* block_tables;
+  int max_blocks, layer;
+};
+int gemm_swapped_decode(const __nv_bfloat16* W, long long ldw, const __nv_bfloat16* X, long long ldx,
+                        int n_out, int batch, int K, const DecodeEpilogue& epi, cudaStream_t stream);
 // same, with an explicit number of 64-wide k-blocks per split (split boundaries the caller relies on)
 int gemm_swapped_kb(const __nv_bfloat16* W, long long ldw, const __nv_bfloat16* X, long long ldx,
                     int n_out, int batch, int K, int kb_per_split, float* ws, cudaStream_t stream);
