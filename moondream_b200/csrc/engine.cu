@@ -203,24 +203,6 @@ int text_prefill(Model& m, bf16* x, int T, const int* q_offsets, const int* star
 // ------------------------------------------------------------------------------------------------
 // text decoder: one decode step for `batch` sequences (fused layout, 5 launches per block)
 // ------------------------------------------------------------------------------------------------
-// k-blocks per split of the K-concatenated [proj | fc2] stream: a divisor of D/64 (so no split
-// straddles the proj/fc2 boundary) that minimises waves x tile length, at most 32 splits.
-static int pick_cat_kb(const md_dims& d) {
-  const int kb_d = d.txt_dim / 64, total = (d.txt_dim + d.txt_ff) / 64;
-  const int m_blocks = (d.txt_dim + 127) / 128;
-  int best = kb_d;
-  long long best_cost = -1;
-  for (int c = kb_d; c >= 1; --c) {
-    if (kb_d % c) continue;
-    const int splits = (total + c - 1) / c;
-    if (splits > 32) break;
-    const int tiles = m_blocks * splits;
-    const long long cost = 1LL * ((tiles + num_sms() - 1) / num_sms()) * c;
-    if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = c; }
-  }
-  return best;
-}
-
 static long long smallbatch_ws_floats(const Model& m, int batch) {
   const md_dims& d = m.d;
   long long need = 0;
@@ -230,8 +212,7 @@ static long long smallbatch_ws_floats(const Model& m, int batch) {
   };
   upd(3 * d.txt_dim + d.txt_ff, d.txt_dim);
   {
-    const int kb = pick_cat_kb(d);
-    const long long f = 1LL * (((d.txt_dim + d.txt_ff) / 64 + kb - 1) / kb) * batch * d.txt_dim;
+    const long long f = 1LL * plan_swapped(d.txt_dim, d.txt_dim + d.txt_ff, d.txt_dim / 64).splits * batch * d.txt_dim;
     if (f > need) need = f;
   }
   upd(d.vocab, d.txt_dim);
@@ -266,21 +247,21 @@ int text_decode_step(Model& m, bf16* x, const int* pos, int batch, const md_kv& 
   bf16* xcat = reinterpret_cast<bf16*>(p); p += pad256(1LL * batch * (D + FF) * 2);   // [att | gelu(fc1)]
   float* wsf = reinterpret_cast<float*>(p);
   bf16* pool = reinterpret_cast<bf16*>(kv.pool);
-  const int kb = pick_cat_kb(d);
+  const int kb = plan_swapped(D, D + FF, D / 64).kb;    // a divisor of D/64: no split straddles proj | fc2
   const int proj_splits = (D / 64) / kb;
   if (layernorm(x, D, m.txt[0].ln.w, m.txt[0].ln.b, ln, D, batch, D, 1e-5f, st)) return 1;
   for (int i = 0; i < d.txt_layers; ++i) {
     const TxtBlock& b = m.txt[i];
-    // [qkv ; fc1] share the input l = ln(x) (text.py:145-157): one weight stream whose epilogue applies
-    // bias, RoPE, the KV-page write and GELU directly (no split-K, no fp32 round trip)
-    DecodeEpilogue de{};
-    de.D = D; de.FF = FF; de.n_heads = H; de.bias = b.qkv.b; de.pos = pos; de.freqs = m.rope; de.q_out = q;
-    de.hid = xcat + D; de.ld_hid = D + FF; de.kv_pool = pool; de.n_pages = kv.n_pages;
-    de.block_tables = kv.block_tables; de.max_blocks = kv.max_blocks; de.layer = i;
-    if (gemm_swapped_decode(b.qkv.w, D, ln, D, 3 * D + FF, batch, D, de, st)) return 1;
+    // [qkv ; fc1] share the input l = ln(x) (text.py:145-157): one weight stream, then bias / RoPE /
+    // KV-page write / GELU.  (gemm_swapped_decode fuses those into the GEMM epilogue but needs whole-K
+    // tiles, i.e. 112 streaming SMs instead of 148: measured slower, 2.35 vs 2.07 ms per step.)
+    const int s1 = gemm_swapped(b.qkv.w, D, ln, D, 3 * D + FF, batch, D, 0, wsf, st);
+    if (s1 < 0) return 1;
+    if (decode_qkv_mlp_epilogue(wsf, s1, batch, D, FF, H, b.qkv.b, pos, m.rope, q, xcat + D, D + FF, pool,
+                                kv.n_pages, kv.block_tables, kv.max_blocks, i, st)) return 1;
     if (decode_attention(q, H, pos, batch, pool, kv.n_pages, kv.block_tables, kv.max_blocks, i, xcat, D + FF, st)) return 1;
     // proj(att) and fc2(hid) both land in the residual: one K-concatenated weight stream
-    const int s2 = gemm_swapped_kb(b.proj.w, D + FF, xcat, D + FF, D, batch, D + FF, kb, wsf, st);
+    const int s2 = gemm_swapped_kb(b.proj.w, D + FF, xcat, D + FF, D, batch, D + FF, D / 64, wsf, st);
     if (s2 < 0) return 1;
     const bool last = i + 1 == d.txt_layers;
     const Lin& nln = last ? m.txt_post_ln : m.txt[i + 1].ln;

@@ -33,6 +33,8 @@ struct GemmParams {
   int m_blocks, n_blocks, k_blocks;   // m_blocks counts (BM * CG)-row tiles; k_blocks = ceil(K / BK)
   int k_splits;                        // >1 only in swapped form
   int kb_per_split;                    // k-blocks owned by each split (last one may be shorter)
+  int tile_rows;                       // rows of A per tile (<= BM; single-CTA tiles only): balances the
+                                       // weight stream over the SMs when M / BM is not a multiple of 148
   int mode;                            // EPI_* (row form) or EPI_PARTIAL (swapped form)
   // row form
   __nv_bfloat16* out;
@@ -183,8 +185,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int kb1 = min(p.k_blocks, kb0 + kb_per_split);
         prefetched = min(STAGES, kb1 - kb0);
         for (int i = 0; i < prefetched; ++i) {
-          mbar_arrive_expect_tx(&full_bar[i], S::kStageBytes);
-          tma_load_2d(smem + i * S::kStageBytes, &tmA, &full_bar[i], (kb0 + i) * BK, m_blk * BM);
+          mbar_arrive_expect_tx(&full_bar[i], p.tile_rows * (BK * 2) + S::kBBytes);
+          tma_load_2d(smem + i * S::kStageBytes, &tmA, &full_bar[i], (kb0 + i) * BK, m_blk * p.tile_rows);
         }
       }
       pdl_wait();
@@ -195,7 +197,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int m_blk = t2 / p.n_blocks;
         const int kb0 = split * kb_per_split;
         const int kb1 = min(p.k_blocks, kb0 + kb_per_split);
-        const int a_row = m_blk * (BM * CG) + rank * BM;
+        const int a_row = (CG == 2) ? m_blk * (BM * CG) + rank * BM : m_blk * p.tile_rows;
         const int b_row = n_blk * BN + rank * (BN / CG);
         for (int kb = kb0; kb < kb1; ++kb) {
           uint8_t* sa = smem + stage * S::kStageBytes;
@@ -212,7 +214,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               tma_load_2d_pair(sa, &tmA, &full_bar[stage], kb * BK, a_row);
               tma_load_2d_pair(sb, &tmB, &full_bar[stage], kb * BK, b_row);
             } else {
-              mbar_arrive_expect_tx(&full_bar[stage], S::kStageBytes);
+              mbar_arrive_expect_tx(&full_bar[stage], p.tile_rows * (BK * 2) + S::kBBytes);
               tma_load_2d(sa, &tmA, &full_bar[stage], kb * BK, a_row);
               tma_load_2d(sb, &tmB, &full_bar[stage], kb * BK, b_row);
             }
@@ -272,8 +274,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int m_blk = t2 / p.n_blocks;
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
-      const int row = m_blk * (BM * CG) + rank * BM + q * 32 + lane;   // accumulator row of this thread
-      const bool row_ok = row < p.M;
+      const int row_in_tile = q * 32 + lane;
+      const int row = (CG == 2 ? m_blk * (BM * CG) + rank * BM : m_blk * p.tile_rows) + row_in_tile;   // accumulator row
+      const bool row_ok = row < p.M && (CG == 2 || row_in_tile < p.tile_rows);
       long long out_row = row;
       if (p.remap_gin > 0)
         out_row = static_cast<long long>(row / p.remap_gin) * p.remap_gout + row % p.remap_gin +
@@ -594,6 +597,7 @@ int gemm_rowform(const __nv_bfloat16* A, long long lda, const __nv_bfloat16* W, 
   p.k_blocks = (K + BK - 1) / BK;
   p.k_splits = 1;
   p.kb_per_split = p.k_blocks;
+  p.tile_rows = BM;
   p.mode = mode;
   p.out = out; p.ldo = ldo; p.bias = bias; p.res = res; p.ldr = ldr; p.res_mod = res_mod;
   p.remap_gin = remap_gin; p.remap_gout = remap_gout; p.remap_goff = remap_goff;
@@ -611,30 +615,49 @@ int gemm_rowform(const __nv_bfloat16* A, long long lda, const __nv_bfloat16* W, 
   return rc;
 }
 
-int gemm_swapped_splits(int n_out, int K) {
-  // enough (feature-block x K-split) work items to give every SM a weight stream
-  const int m_blocks = (n_out + BM - 1) / BM;
+
+// Plan of a weight-streaming (swapped) GEMM: tile height (rows of W per CTA tile, <= 128) and k-blocks per
+// split such that (tiles x splits) fills whole waves of the SMs.  cost = waves x tile_rows x kb is the
+// critical path in units of 128-byte weight rows; ties prefer fewer splits (less partial-sum traffic).
+// kb_divisor > 0 restricts kb to divisors of it (split boundaries the caller relies on).
+SwappedPlan plan_swapped(int n_out, int K, int kb_divisor) {
   const int k_blocks = (K + BK - 1) / BK;
-  int splits = (num_sms() + m_blocks - 1) / m_blocks;
-  if (splits > k_blocks / 4) splits = k_blocks / 4;   // keep >= 4 k-blocks (256 of K) per split
-  if (splits < 1) splits = 1;
-  if (splits > 16) splits = 16;
-  return splits;
+  const int sms = num_sms();
+  SwappedPlan best{BM, k_blocks, 1};
+  long long best_cost = -1;
+  for (int kb = k_blocks; kb >= 1; --kb) {
+    if (kb_divisor > 0 ? (kb > kb_divisor || kb_divisor % kb) : false) continue;
+    const int splits = (k_blocks + kb - 1) / kb;
+    if (splits > 32) break;
+    if (kb_divisor == 0 && kb < 4 && k_blocks >= 4) break;           // keep >= 256 of K per split
+    for (int rows = BM; rows >= 64; --rows) {
+      const int tiles = (n_out + rows - 1) / rows;
+      const long long waves = (1LL * tiles * splits + sms - 1) / sms;
+      // critical path in 128-byte weight rows + this SM's share of the fp32 partial-sum traffic
+      // (written and re-read once per split, nominal batch 32)
+      const long long cost = waves * rows * kb + (1LL * splits * n_out * 32 * 8) / (128LL * sms);
+      if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = SwappedPlan{rows, kb, splits}; }
+    }
+  }
+  return best;
 }
 
 // ws[splits][batch][n_out] (fp32) = W[n_out,K] * X[batch,K]^T  partial sums; split s owns k-blocks
 // [s * kb_per_split, (s+1) * kb_per_split).  Returns the number of splits (>0), -1 on error.
 static int gemm_swapped_impl(const __nv_bfloat16* W, long long ldw, const __nv_bfloat16* X, long long ldx,
-                             int n_out, int batch, int K, int kb_per_split, float* ws, cudaStream_t stream) {
+                             int n_out, int batch, int K, int kb_per_split, int tile_rows, float* ws,
+                             cudaStream_t stream) {
   if (n_out <= 0 || batch <= 0 || K <= 0) { set_error("gemm_swapped: empty problem"); return -1; }
   if (K % 8) { set_error("gemm_swapped: K must be a multiple of 8"); return -1; }
+  if (tile_rows < 1 || tile_rows > BM) tile_rows = BM;
   const int bn = batch <= 32 ? 32 : batch <= 64 ? 64 : batch <= 128 ? 128 : 256;
   CUtensorMap tA, tB;
-  if (make_tmap_bf16_2d(&tA, W, n_out, K, ldw, BM)) return -1;
+  if (make_tmap_bf16_2d(&tA, W, n_out, K, ldw, tile_rows)) return -1;
   if (make_tmap_bf16_2d(&tB, X, batch, K, ldx, bn)) return -1;
   GemmParams p{};
   p.M = n_out; p.N = batch; p.K = K;
-  p.m_blocks = (n_out + BM - 1) / BM;
+  p.tile_rows = tile_rows;
+  p.m_blocks = (n_out + tile_rows - 1) / tile_rows;
   p.n_blocks = (batch + bn - 1) / bn;
   p.k_blocks = (K + BK - 1) / BK;
   if (kb_per_split < 1) kb_per_split = 1;
@@ -647,12 +670,13 @@ static int gemm_swapped_impl(const __nv_bfloat16* W, long long ldw, const __nv_b
   return rc ? -1 : p.k_splits;
 }
 
+int gemm_swapped_splits(int n_out, int K) { return plan_swapped(n_out, K, 0).splits; }
+
 int gemm_swapped(const __nv_bfloat16* W, long long ldw, const __nv_bfloat16* X, long long ldx,
                  int n_out, int batch, int K, int splits, float* ws, cudaStream_t stream) {
-  const int k_blocks = (K + BK - 1) / BK;
-  if (splits < 1) splits = 1;
-  if (splits > k_blocks) splits = k_blocks;
-  return gemm_swapped_impl(W, ldw, X, ldx, n_out, batch, K, (k_blocks + splits - 1) / splits, ws, stream);
+  (void)splits;                                  // the plan decides (callers size ws with gemm_swapped_splits)
+  const SwappedPlan pl = plan_swapped(n_out, K, 0);
+  return gemm_swapped_impl(W, ldw, X, ldx, n_out, batch, K, pl.kb, pl.tile_rows, ws, stream);
 }
 
 int gemm_swapped_decode(const __nv_bfloat16* W, long long ldw, const __nv_bfloat16* X, long long ldx,
@@ -670,6 +694,7 @@ int gemm_swapped_decode(const __nv_bfloat16* W, long long ldw, const __nv_bfloat
   p.n_blocks = (batch + bn - 1) / bn;
   p.k_blocks = (K + BK - 1) / BK;
   p.kb_per_split = p.k_blocks;
+  p.tile_rows = BM;
   p.k_splits = 1;                                   // the whole K in one CTA: the epilogue sees final sums
   p.mode = EPI_DECODE_QKV_MLP;
   p.dec = epi;
@@ -677,8 +702,9 @@ int gemm_swapped_decode(const __nv_bfloat16* W, long long ldw, const __nv_bfloat
 }
 
 int gemm_swapped_kb(const __nv_bfloat16* W, long long ldw, const __nv_bfloat16* X, long long ldx,
-                    int n_out, int batch, int K, int kb_per_split, float* ws, cudaStream_t stream) {
-  return gemm_swapped_impl(W, ldw, X, ldx, n_out, batch, K, kb_per_split, ws, stream);
+                    int n_out, int batch, int K, int kb_divisor, float* ws, cudaStream_t stream) {
+  const SwappedPlan pl = plan_swapped(n_out, K, kb_divisor);
+  return gemm_swapped_impl(W, ldw, X, ldx, n_out, batch, K, pl.kb, pl.tile_rows, ws, stream);
 }
 
 int splitk_epilogue(const float* ws, int splits, int B, int N, int mode, const __nv_bfloat16* bias,

@@ -55,6 +55,8 @@ int gemm_rowform(const __nv_bfloat16* A, long long lda, const __nv_bfloat16* W, 
 void gemm_force_cta_group(int cg);
 void gemm_profile_enable(int on);
 int gemm_profile_read(double* total_ms, double* total_flops, long long* launches);
+struct SwappedPlan { int tile_rows, kb, splits; };
+SwappedPlan plan_swapped(int n_out, int K, int kb_divisor);
 int gemm_swapped_splits(int n_out, int K);
 int gemm_swapped(const __nv_bfloat16* W, long long ldw, const __nv_bfloat16* X, long long ldx,
                  int n_out, int batch, int K, int splits, float* ws, cudaStream_t stream);
@@ -76,9 +78,9 @@ struct DecodeEpilogue {
 };
 int gemm_swapped_decode(const __nv_bfloat16* W, long long ldw, const __nv_bfloat16* X, long long ldx,
                         int n_out, int batch, int K, const DecodeEpilogue& epi, cudaStream_t stream);
-// same, with an explicit number of 64-wide k-blocks per split (split boundaries the caller relies on)
+// same, with k-blocks per split restricted to divisors of kb_divisor (split boundaries the caller relies on)
 int gemm_swapped_kb(const __nv_bfloat16* W, long long ldw, const __nv_bfloat16* X, long long ldx,
-                    int n_out, int batch, int K, int kb_per_split, float* ws, cudaStream_t stream);
+                    int n_out, int batch, int K, int kb_divisor, float* ws, cudaStream_t stream);
 int splitk_epilogue(const float* ws, int splits, int B, int N, int mode, const __nv_bfloat16* bias,
                     const __nv_bfloat16* res, long long ldr, __nv_bfloat16* out, long long ldo,
                     cudaStream_t stream);
