@@ -117,6 +117,9 @@ void md_debug_attention_impl(int impl);
 /* Testing / A-B timing only: programmatic dependent launch between consecutive kernels (default off:
  * measured slower on the decode graph in round 1). */
 void md_debug_set_pdl(int enable);
+/* Ablation timing only (results are garbage when non-zero): skip kernels of md_text_decode_step;
+ * bit0 [qkv;fc1] GEMM, bit1 its epilogue, bit2 attention, bit3 [proj|fc2] GEMM, bit4 residual+LN epilogue. */
+void md_debug_skip_decode_kernels(int mask);
 
 /* One-query attention for decode (text.py:46-50 with the [1,1,2048] mask of moondream.py:472-474). */
 int md_decode_attention_bf16(const void* q, int n_heads, const int* pos, int n_seqs, const md_kv* kv,

@@ -53,6 +53,7 @@ _SIGNATURES = {
     "md_prefill_attention_bf16": (c_int, [_P, c_int, c_int, _P, _P, c_int, c_int, c_int, _KV, c_int, _P, _P]),
     "md_debug_attention_impl": (None, [c_int]),
     "md_debug_set_pdl": (None, [c_int]),
+    "md_debug_skip_decode_kernels": (None, [c_int]),
     "md_decode_attention_bf16": (c_int, [_P, c_int, _P, c_int, _KV, c_int, _P, _P]),
     "md_model_num_weights": (c_int, [_DIMS]),
     "md_model_create": (c_int, [_DIMS, ctypes.POINTER(c_void_p), c_int, _P, _P, ctypes.POINTER(c_void_p)]),

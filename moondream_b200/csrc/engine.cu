@@ -234,6 +234,8 @@ static int small_linear(const bf16* x, long long ldx, const Lin& l, int batch, i
   return splitk_epilogue(ws, used, batch, n_out, mode, l.b, res, ldr, out, ldo, st);
 }
 
+int g_debug_skip = 0;   // ablation timing only: bit0 GEMM1, bit1 epilogue1, bit2 attention, bit3 GEMM2, bit4 epilogue2
+
 int text_decode_step(Model& m, bf16* x, const int* pos, int batch, const md_kv& kv, bf16* normed_out, void* ws,
                      cudaStream_t st) {
   const md_dims& d = m.d;
@@ -255,18 +257,23 @@ int text_decode_step(Model& m, bf16* x, const int* pos, int batch, const md_kv& 
     // [qkv ; fc1] share the input l = ln(x) (text.py:145-157): one weight stream, then bias / RoPE /
     // KV-page write / GELU.  (gemm_swapped_decode fuses those into the GEMM epilogue but needs whole-K
     // tiles, i.e. 112 streaming SMs instead of 148: measured slower, 2.35 vs 2.07 ms per step.)
-    const int s1 = gemm_swapped(b.qkv.w, D, ln, D, 3 * D + FF, batch, D, 0, wsf, st);
+    int s1 = plan_swapped(3 * D + FF, D, 0).splits;
+    if (!(g_debug_skip & 1)) s1 = gemm_swapped(b.qkv.w, D, ln, D, 3 * D + FF, batch, D, 0, wsf, st);
     if (s1 < 0) return 1;
-    if (decode_qkv_mlp_epilogue(wsf, s1, batch, D, FF, H, b.qkv.b, pos, m.rope, q, xcat + D, D + FF, pool,
+    if (!(g_debug_skip & 2) &&
+        decode_qkv_mlp_epilogue(wsf, s1, batch, D, FF, H, b.qkv.b, pos, m.rope, q, xcat + D, D + FF, pool,
                                 kv.n_pages, kv.block_tables, kv.max_blocks, i, st)) return 1;
-    if (decode_attention(q, H, pos, batch, pool, kv.n_pages, kv.block_tables, kv.max_blocks, i, xcat, D + FF, st)) return 1;
+    if (!(g_debug_skip & 4) &&
+        decode_attention(q, H, pos, batch, pool, kv.n_pages, kv.block_tables, kv.max_blocks, i, xcat, D + FF, st)) return 1;
     // proj(att) and fc2(hid) both land in the residual: one K-concatenated weight stream
-    const int s2 = gemm_swapped_kb(b.proj.w, D + FF, xcat, D + FF, D, batch, D + FF, D / 64, wsf, st);
+    int s2 = plan_swapped(D, D + FF, D / 64).splits;
+    if (!(g_debug_skip & 8)) s2 = gemm_swapped_kb(b.proj.w, D + FF, xcat, D + FF, D, batch, D + FF, D / 64, wsf, st);
     if (s2 < 0) return 1;
     const bool last = i + 1 == d.txt_layers;
     const Lin& nln = last ? m.txt_post_ln : m.txt[i + 1].ln;
     bf16* ln_dst = last ? (normed_out ? normed_out : ln_last) : ln;
-    if (decode_residual_ln_epilogue(wsf, s2, proj_splits, batch, D, b.proj.b, b.fc2.b, x, nln.w, nln.b, ln_dst, st)) return 1;
+    if (!(g_debug_skip & 16) &&
+        decode_residual_ln_epilogue(wsf, s2, proj_splits, batch, D, b.proj.b, b.fc2.b, x, nln.w, nln.b, ln_dst, st)) return 1;
   }
   return 0;
 }

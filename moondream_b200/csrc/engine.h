@@ -40,6 +40,7 @@ int vision_project(Model& m, const bf16* feats, const int* crop_offsets, const i
 long long text_prefill_ws_bytes(const Model& m, int T);
 int text_prefill(Model& m, bf16* x, int T, const int* q_offsets, const int* start_pos, int n_seqs,
                  int max_q, const md_kv& kv, void* ws, cudaStream_t st);
+extern int g_debug_skip;
 long long text_decode_ws_bytes(const Model& m, int batch);
 int text_decode_step(Model& m, bf16* x, const int* pos, int batch, const md_kv& kv, bf16* normed_out, void* ws,
                      cudaStream_t st);
