@@ -188,3 +188,44 @@ def test_golden_reference_fixture(tiny):
             pts = eng.generate_points(eng.encode_images([img]), [case[f"{kind}_prompt"]], size, 3)[0]
             want = [{"bins": b, "ulps": u} for b, u in zip(case[f"{kind}_bins"], case[f"{kind}_ulps"])]
             _check_objects(pts, want, f"{case['name']} {kind}")
+
+
+def test_moondream_0_5b_parity():
+    """BASELINE.json configs[0]: Moondream-0.5B, one 378x378 image, greedy caption vs the reference CPU path
+    (oracle).  Exercises vision dim 720 / 10 heads / FF 2690 (zero-padded to 2696) and text dim 1024 / 16 heads."""
+    from moondream_b200 import config as C, synth
+    from moondream_b200.engine import Engine
+    from oracle.moondream_oracle import OracleModel
+
+    cfg = C.moondream_0_5b()
+    sd = synth.synthetic_state_dict(cfg, 0)
+    eng = Engine(cfg, sd, max_batch=4)
+    orc = OracleModel(cfg, sd)
+    imgs = [synth.synthetic_image(0, 378, 378), synth.synthetic_image(1, 500, 700)]
+    prompt = cfg.tokenizer.templates["caption"]["normal"]
+    prefixes, feats, img_emb, hidden = eng.encode_images(imgs, return_hidden=True)
+    res = eng.generate(prefixes, [prompt, prompt], max_tokens=6)
+    for i, img in enumerate(imgs):
+        o_enc, o_emb, _ = orc.encode_image(img, return_embeds=True)
+        assert rel(img_emb[i], o_emb) < REL_TOL, rel(img_emb[i], o_emb)
+        gen = orc.generate(o_enc, prompt, 6)
+        _check_tokens(res.tokens[i].tolist(), gen, f"0.5B image {i}")
+    del eng
+    torch.cuda.empty_cache()
+
+
+def test_large_batch_matches_small_batch(tiny):
+    """batch 96 (three column tiles of the weight-streaming GEMM, BN = 128) gives the tokens of batch-1 runs."""
+    from moondream_b200 import config as C, synth
+    from moondream_b200.engine import Engine
+
+    cfg, sd, eng, _, _ = tiny
+    big = Engine(cfg, sd, max_batch=96)
+    imgs = [synth.synthetic_image(i % 7, 378, 378) for i in range(96)]
+    prompts = [synth.synthetic_prompt(i % 5, 3 + (i % 4), cfg.text.vocab_size) for i in range(96)]
+    res = big.generate(big.encode_images(imgs), prompts, max_tokens=10)
+    for i in (0, 17, 63, 95):
+        one = eng.generate(eng.encode_images([imgs[i]]), [prompts[i]], max_tokens=10)
+        assert torch.equal(one.tokens[0], res.tokens[i]), i
+    del big
+    torch.cuda.empty_cache()
