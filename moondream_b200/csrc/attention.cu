@@ -336,22 +336,79 @@ int prefill_attention(const __nv_bfloat16* q, int n_heads, const int* q_offsets,
 
 // ------------------------------------------------------------------------------------------------
 // decode attention: one (sequence, head) per CTA, 4 warps split the keys, 8 lanes per key row.
+// FUSED = true additionally finishes the [qkv ; fc1] weight stream of the block for this (sequence, head)
+// before attending: sums the fp32 split-K partials of its 3 x 64 q/k/v features (+ bias, bf16 round, partial
+// RoPE, K/V row -> KV page; reference text.py:30-43, moondream.py:74-78) and of a 1/H slice of the fc1
+// features (+ bias, round, GELU -> hid; layers.py:130,137).  That replaces a separate epilogue kernel.
 // ------------------------------------------------------------------------------------------------
+struct DecodeFuse {
+  const float* ws;                 // [splits][B][3D + FF]
+  int splits, B, D, FF;
+  const __nv_bfloat16* bias;       // [3D + FF]
+  const float* freqs;              // rope table
+  __nv_bfloat16* hid;              // gelu(fc1) output rows, pitch ld_hid
+  long long ld_hid;
+};
+
+template <bool FUSED>
 __global__ void __launch_bounds__(128)
 decode_attention_kernel(const __nv_bfloat16* __restrict__ q, int n_heads, const int* __restrict__ pos,
-                        const __nv_bfloat16* __restrict__ kv_pool, int n_pages,
+                        __nv_bfloat16* __restrict__ kv_pool, int n_pages,
                         const int* __restrict__ block_tables, int max_blocks, int layer,
-                        __nv_bfloat16* __restrict__ out, long long ld_out, float scale_log2) {
+                        __nv_bfloat16* __restrict__ out, long long ld_out, float scale_log2, const DecodeFuse fz) {
   pdl_wait();
   const int head = blockIdx.x, seq = blockIdx.y;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int sub = lane & 7;            // which 16-byte chunk (8 dims) of the 64-dim row
   const int rowi = lane >> 3;          // 4 key rows per warp step
-  const int kv_len = pos[seq] + 1;     // the current token's K/V was written just before this kernel
+  const int cur = pos[seq];
+  const int kv_len = cur + 1;          // the current token's K/V row is part of the context
   const int* btab = block_tables + static_cast<long long>(seq) * max_blocks;
+  const long long head_off = static_cast<long long>(head) * (kPageTokens * 64);
+  const long long v_off = static_cast<long long>(n_heads) * (kPageTokens * 64);
 
+  __shared__ float sq[64];
   float qv[8];
-  {
+  if (FUSED) {
+    const int NF = 3 * fz.D + fz.FF;
+    auto value = [&](int f) {
+      float a = 0.f;
+      for (int s = 0; s < fz.splits; ++s) a += fz.ws[(static_cast<long long>(s) * fz.B + seq) * NF + f];
+      return bf16_round(a + __bfloat162float(fz.bias[f]));
+    };
+    if (warp < 3) {                                        // warp 0: q, 1: k, 2: v of this head
+      const int f0 = warp * fz.D + head * 64;
+      float o0, o1;
+      if (warp < 2 && lane < 16) {
+        const float re = value(f0 + lane), im = value(f0 + 16 + lane);
+        const float c = fz.freqs[(cur * 16 + lane) * 2], sn = fz.freqs[(cur * 16 + lane) * 2 + 1];
+        o0 = __fsub_rn(__fmul_rn(re, c), __fmul_rn(im, sn));
+        o1 = __fadd_rn(__fmul_rn(re, sn), __fmul_rn(im, c));
+      } else {
+        o0 = value(f0 + 2 * lane);
+        o1 = value(f0 + 2 * lane + 1);
+      }
+      if (warp == 0) {
+        sq[2 * lane] = bf16_round(o0);
+        sq[2 * lane + 1] = bf16_round(o1);
+      } else {
+        const int page = btab[cur >> 6];
+        __nv_bfloat16* dst = kv_pool + ((static_cast<long long>(layer) * n_pages + page) * 2 + (warp - 1)) * v_off +
+                             head_off + (cur & 63) * 64 + 2 * lane;
+        *reinterpret_cast<uint32_t*>(dst) = pack_bf16x2(o0, o1);
+      }
+    }
+    // this CTA's slice of the fc1 features
+    const int per = fz.FF / n_heads;
+    for (int i = tid * 2; i < per; i += 256) {
+      const int f = 3 * fz.D + head * per + i;
+      const float g0 = gelu_tanh(value(f)), g1 = gelu_tanh(value(f + 1));
+      *reinterpret_cast<uint32_t*>(fz.hid + seq * fz.ld_hid + head * per + i) = pack_bf16x2(g0, g1);
+    }
+    __syncthreads();                                       // q in smem, new K/V row visible to the block
+#pragma unroll
+    for (int j = 0; j < 8; ++j) qv[j] = sq[sub * 8 + j];
+  } else {
     const uint4 qq = *reinterpret_cast<const uint4*>(q + (static_cast<long long>(seq) * n_heads + head) * 64 + sub * 8);
     const uint32_t w[4] = {qq.x, qq.y, qq.z, qq.w};
 #pragma unroll
@@ -362,8 +419,6 @@ decode_attention_kernel(const __nv_bfloat16* __restrict__ q, int n_heads, const 
 #pragma unroll
   for (int j = 0; j < 8; ++j) acc[j] = 0.f;
 
-  const long long head_off = static_cast<long long>(head) * (kPageTokens * 64);
-  const long long v_off = static_cast<long long>(n_heads) * (kPageTokens * 64);
   // each warp takes 16 consecutive keys (4 steps of 4 rows) per iteration, warps interleave
   for (int k0 = warp * 16; k0 < kv_len; k0 += 64) {
     const int page = btab[k0 >> 6];
@@ -435,8 +490,26 @@ int decode_attention(const __nv_bfloat16* q, int n_heads, const int* pos, int n_
   if (n_seqs <= 0) return set_error("decode_attention: empty batch");
   dim3 grid(n_heads, n_seqs);
   count_launch();
-  cudaError_t e = launch_k(decode_attention_kernel, grid, dim3(128), 0, stream, q, n_heads, pos, kv_pool, n_pages,
-                           block_tables, max_blocks, layer, out, ld_out, 0.125f * 1.4426950408889634f);
+  cudaError_t e = launch_k(decode_attention_kernel<false>, grid, dim3(128), 0, stream, q, n_heads, pos,
+                           const_cast<__nv_bfloat16*>(kv_pool), n_pages, block_tables, max_blocks, layer, out, ld_out,
+                           0.125f * 1.4426950408889634f, DecodeFuse{});
+  if (e != cudaSuccess) return set_error(cudaGetErrorString(e));
+  return 0;
+}
+
+// fused form: q/k/v/fc1 are finished from the split-K partials `ws` inside the kernel (see DecodeFuse)
+int decode_attention_fused(const float* ws, int splits, int D, int FF, const __nv_bfloat16* bias, const float* freqs,
+                           __nv_bfloat16* hid, long long ld_hid, int n_heads, const int* pos, int n_seqs,
+                           __nv_bfloat16* kv_pool, int n_pages, const int* block_tables, int max_blocks, int layer,
+                           __nv_bfloat16* out, long long ld_out, cudaStream_t stream) {
+  if (n_seqs <= 0) return set_error("decode_attention: empty batch");
+  if (FF % n_heads || (FF / n_heads) % 2) return set_error("decode_attention_fused: FF must split evenly over the heads");
+  DecodeFuse fz{ws, splits, n_seqs, D, FF, bias, freqs, hid, ld_hid};
+  dim3 grid(n_heads, n_seqs);
+  count_launch();
+  cudaError_t e = launch_k(decode_attention_kernel<true>, grid, dim3(128), 0, stream,
+                           static_cast<const __nv_bfloat16*>(nullptr), n_heads, pos, kv_pool, n_pages, block_tables,
+                           max_blocks, layer, out, ld_out, 0.125f * 1.4426950408889634f, fz);
   if (e != cudaSuccess) return set_error(cudaGetErrorString(e));
   return 0;
 }

@@ -260,11 +260,10 @@ int text_decode_step(Model& m, bf16* x, const int* pos, int batch, const md_kv& 
     int s1 = plan_swapped(3 * D + FF, D, 0).splits;
     if (!(g_debug_skip & 1)) s1 = gemm_swapped(b.qkv.w, D, ln, D, 3 * D + FF, batch, D, 0, wsf, st);
     if (s1 < 0) return 1;
-    if (!(g_debug_skip & 2) &&
-        decode_qkv_mlp_epilogue(wsf, s1, batch, D, FF, H, b.qkv.b, pos, m.rope, q, xcat + D, D + FF, pool,
-                                kv.n_pages, kv.block_tables, kv.max_blocks, i, st)) return 1;
+    // bias / RoPE / KV-row write / GELU of that stream happen inside the attention kernel (one launch fewer)
     if (!(g_debug_skip & 4) &&
-        decode_attention(q, H, pos, batch, pool, kv.n_pages, kv.block_tables, kv.max_blocks, i, xcat, D + FF, st)) return 1;
+        decode_attention_fused(wsf, s1, D, FF, b.qkv.b, m.rope, xcat + D, D + FF, H, pos, batch, pool, kv.n_pages,
+                               kv.block_tables, kv.max_blocks, i, xcat, D + FF, st)) return 1;
     // proj(att) and fc2(hid) both land in the residual: one K-concatenated weight stream
     int s2 = plan_swapped(D, D + FF, D / 64).splits;
     if (!(g_debug_skip & 8)) s2 = gemm_swapped_kb(b.proj.w, D + FF, xcat, D + FF, D, batch, D + FF, D / 64, wsf, st);

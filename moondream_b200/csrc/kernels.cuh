@@ -139,5 +139,9 @@ int prefill_attention(const __nv_bfloat16* q, int n_heads, const int* q_offsets,
 int decode_attention(const __nv_bfloat16* q, int n_heads, const int* pos, int n_seqs,
                      const __nv_bfloat16* kv_pool, int n_pages, const int* block_tables,
                      int max_blocks, int layer, __nv_bfloat16* out, long long ld_out, cudaStream_t stream);
+int decode_attention_fused(const float* ws, int splits, int D, int FF, const __nv_bfloat16* bias, const float* freqs,
+                           __nv_bfloat16* hid, long long ld_hid, int n_heads, const int* pos, int n_seqs,
+                           __nv_bfloat16* kv_pool, int n_pages, const int* block_tables, int max_blocks, int layer,
+                           __nv_bfloat16* out, long long ld_out, cudaStream_t stream);
 
 }  // namespace md
