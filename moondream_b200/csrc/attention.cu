@@ -356,6 +356,9 @@ decode_attention_kernel(const __nv_bfloat16* __restrict__ q, int n_heads, const 
                         __nv_bfloat16* __restrict__ kv_pool, int n_pages,
                         const int* __restrict__ block_tables, int max_blocks, int layer,
                         __nv_bfloat16* __restrict__ out, long long ld_out, float scale_log2, const DecodeFuse fz) {
+  // all CTAs of this grid are resident at once, so the trigger fires immediately: the next kernel (the
+  // [proj|fc2] weight stream) may start prefetching weights while this one is streaming K/V
+  pdl_launch_dependents();
   pdl_wait();
   const int head = blockIdx.x, seq = blockIdx.y;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
