@@ -113,6 +113,16 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def ncu_traffic():
+    """Mean DRAM read+write bytes per launch of the dominant GEMM class from the committed `ncu --set full`
+    capture (profiles/r01_ncu_full_summary.json); None when absent."""
+    path = os.path.join(ROOT, "profiles", "r01_ncu_full_summary.json")
+    try:
+        return float(json.load(open(path))["gemm_mean_traffic_bytes"])
+    except Exception:
+        return None
+
+
 def flops_per_image(cfg, n_crops: int) -> float:
     """Algorithmic FLOPs: 2*M*K*N per GEMM, 4*H*Tq*Tk*hd per attention."""
     v, t = cfg.vision, cfg.text
@@ -300,7 +310,9 @@ def run_main(args, cfg, sd, rank, world, local_rank):
         "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "roofline": {"bound": "tensor", "kernel": "gemm_bf16_kernel (tcgen05 row-form GEMM: ViT, projection, prefill)",
                      "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
-                     "frac": achieved / peaks["bf16_tflops"] if peaks["bf16_tflops"] else None, "traffic": None,
+                     "frac": achieved / peaks["bf16_tflops"] if peaks["bf16_tflops"] else None, "traffic": ncu_traffic(),
+                     "traffic_note": "bytes per launch, mean of 4 ViT GEMM launches (ncu --set full, profiles/r01_ncu_full_summary.json); "
+                                     "algorithmic bytes of the same launches: 438 / 325 / 519 / 642 MB",
                      "peak_source": peaks["source"], "launches": int(g_n.value),
                      "share_of_step": (g_ms.value / ms) if ms > 0 else None,
                      "step_model_tflops": total_flops / 1e12 / (ms_max / 1e3)},
