@@ -114,8 +114,7 @@ int md_prefill_attention_bf16(const void* q, int n_heads, int total_tokens, cons
                               const md_kv* kv, int layer, void* out, void* stream);
 /* Testing / A-B timing only: 0 = tcgen05 attention (default), 1 = the legacy mma.sync kernel. */
 void md_debug_attention_impl(int impl);
-/* Testing / A-B timing only: programmatic dependent launch between consecutive kernels (default off:
- * measured slower on the decode graph in round 1). */
+/* Testing / A-B timing only: programmatic dependent launch between consecutive kernels (default on). */
 void md_debug_set_pdl(int enable);
 /* Ablation timing only (results are garbage when non-zero): skip kernels of md_text_decode_step;
  * bit0 [qkv;fc1] GEMM, bit1 its epilogue, bit2 attention, bit3 [proj|fc2] GEMM, bit4 residual+LN epilogue. */
