@@ -182,9 +182,12 @@ int text_prefill(Model& m, bf16* x, int T, const int* q_offsets, const int* star
     const TxtBlock& b = m.txt[i];
     // l = ln(x); x = x + attn(l) + mlp(l)                       text.py:145-158
     if (layernorm(x, D, b.ln.w, b.ln.b, ln, D, T, D, 1e-5f, st)) return 1;
-    if (gemm_rowform(ln, D, b.qkv.w, D, T, 3 * D, D, EPI_BIAS, b.qkv.b, nullptr, 0, 0, qkv, 3 * D, 0, 0, 0, st)) return 1;
-    if (rope_kv_write(qkv, T, H, q_offsets, start_pos, n_seqs, m.rope, q, pool, kv.n_pages, kv.block_tables,
-                      kv.max_blocks, i, st)) return 1;
+    // QKV projection with bias, RoPE and the KV-page write in the GEMM epilogue (no qkv round trip through HBM)
+    RopeEpilogue re{};
+    re.D = D; re.n_heads = H; re.n_seqs = n_seqs; re.q_offsets = q_offsets; re.start_pos = start_pos;
+    re.freqs = m.rope; re.q_out = q; re.kv_pool = pool; re.n_pages = kv.n_pages; re.block_tables = kv.block_tables;
+    re.max_blocks = kv.max_blocks; re.layer = i;
+    if (gemm_rowform_qkv_rope(ln, D, b.qkv.w, b.qkv.ld, T, D, b.qkv.b, re, st)) return 1;
     if (g_attention_impl == 1) {
       if (prefill_attention(q, H, q_offsets, start_pos, n_seqs, max_q, d.prefix_len, pool, kv.n_pages,
                             kv.block_tables, kv.max_blocks, i, att, st)) return 1;

@@ -47,6 +47,7 @@ struct GemmParams {
   // swapped form
   float* ws;                           // [k_splits][N][M] fp32
   DecodeEpilogue dec;                  // EPI_DECODE_QKV_MLP
+  RopeEpilogue rope;                   // EPI_QKV_ROPE
 };
 
 
@@ -103,6 +104,64 @@ __device__ __forceinline__ void decode_qkv_mlp_rows(const GemmParams& p, const u
     if (write2) *reinterpret_cast<uint32_t*>(dst) = pack_bf16x2(o0, o1);
     else *dst = __float2bfloat16_rn(o0);
   }
+}
+
+// Fused epilogue of the prefill QKV projection: this thread owns token row `row` and the 32 output columns
+// col0..col0+31 = one half of one head of q, k or v.  dims 0..31 of q and k rotate (pairs (j, j+16) are
+// both in this thread), everything else passes through; q goes to q_out, k / v to the KV page of (seq, pos).
+struct RopeRow { int pos; long long kv_row; };   // kv_row: element offset of (page, token) for head 0, k plane
+__device__ __forceinline__ RopeRow rope_locate(const RopeEpilogue& e, int row) {
+  int lo = 0, hi = e.n_seqs;
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (e.q_offsets[mid] <= row) lo = mid; else hi = mid;
+  }
+  RopeRow r;
+  r.pos = e.start_pos[lo] + (row - e.q_offsets[lo]);
+  const int page = e.block_tables[static_cast<long long>(lo) * e.max_blocks + (r.pos >> 6)];
+  r.kv_row = ((static_cast<long long>(e.layer) * e.n_pages + page) * 2) * e.n_heads * (64 * 64) + (r.pos & 63) * 64;
+  return r;
+}
+__device__ __forceinline__ void rope_store_chunk(const GemmParams& p, const uint32_t (&acc)[32], int row, int col0,
+                                                 const RopeRow& rr) {
+  const RopeEpilogue& e = p.rope;
+  const int part = col0 / e.D;                            // 0 q, 1 k, 2 v
+  const int within = col0 - part * e.D;
+  const int head = within >> 6, half = (within >> 5) & 1;
+  float v[32];
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    const uint4 bq = *reinterpret_cast<const uint4*>(p.bias + col0 + g * 8);
+    const uint32_t bw[4] = {bq.x, bq.y, bq.z, bq.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      v[g * 8 + 2 * j] = bf16_round(__uint_as_float(acc[g * 8 + 2 * j]) + bf16_lo(bw[j]));
+      v[g * 8 + 2 * j + 1] = bf16_round(__uint_as_float(acc[g * 8 + 2 * j + 1]) + bf16_hi(bw[j]));
+    }
+  }
+  uint32_t o[16];
+  if (part < 2 && half == 0) {
+    const float4* tab = reinterpret_cast<const float4*>(e.freqs + static_cast<long long>(rr.pos) * 32);   // 16 x (cos, sin)
+#pragma unroll
+    for (int j = 0; j < 16; j += 2) {
+      const float4 cs = tab[j >> 1];                      // (cos_j, sin_j, cos_j+1, sin_j+1)
+      const float r0 = __fsub_rn(__fmul_rn(v[j], cs.x), __fmul_rn(v[16 + j], cs.y));
+      const float i0 = __fadd_rn(__fmul_rn(v[j], cs.y), __fmul_rn(v[16 + j], cs.x));
+      const float r1 = __fsub_rn(__fmul_rn(v[j + 1], cs.z), __fmul_rn(v[17 + j], cs.w));
+      const float i1 = __fadd_rn(__fmul_rn(v[j + 1], cs.w), __fmul_rn(v[17 + j], cs.z));
+      o[j] = pack_bf16x2(r0, i0);                         // interleaved output (re', im')
+      o[j + 1] = pack_bf16x2(r1, i1);
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) o[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+  }
+  __nv_bfloat16* dst;
+  if (part == 0) dst = e.q_out + static_cast<long long>(row) * e.D + head * 64 + half * 32;
+  else dst = e.kv_pool + rr.kv_row + (static_cast<long long>(part - 1) * e.n_heads + head) * (64 * 64) + half * 32;
+#pragma unroll
+  for (int g = 0; g < 4; ++g)
+    *reinterpret_cast<uint4*>(dst + g * 8) = make_uint4(o[4 * g], o[4 * g + 1], o[4 * g + 2], o[4 * g + 3]);
 }
 
 template <int BN, int STAGES, int CG>
@@ -285,6 +344,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const bool use_res = p.mode == EPI_BIAS_RESIDUAL && row_ok;
       const __nv_bfloat16* rbase = use_res ? p.res + static_cast<long long>(res_row) * p.ldr : nullptr;
 
+      RopeRow rr{0, 0};
+      if (p.mode == EPI_QKV_ROPE && row_ok) rr = rope_locate(p.rope, row);
       // the residual does not depend on the accumulator: fetch the first chunk before waiting for the MMAs
       uint4 rq[4], rq_next[4];
       auto load_res = [&](int cc, uint4 (&dst)[4]) {
@@ -310,6 +371,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int col0 = n_blk * BN + c * 32;
         if (p.mode == EPI_DECODE_QKV_MLP) {
           decode_qkv_mlp_rows(p, acc, row, col0, lane);
+          continue;
+        }
+        if (p.mode == EPI_QKV_ROPE) {
+          if (row_ok && col0 < p.N) rope_store_chunk(p, acc, row, col0, rr);
           continue;
         }
         if (p.mode == EPI_PARTIAL) {
@@ -677,6 +742,41 @@ int gemm_swapped(const __nv_bfloat16* W, long long ldw, const __nv_bfloat16* X, 
   (void)splits;                                  // the plan decides (callers size ws with gemm_swapped_splits)
   const SwappedPlan pl = plan_swapped(n_out, K, 0);
   return gemm_swapped_impl(W, ldw, X, ldx, n_out, batch, K, pl.kb, pl.tile_rows, ws, stream);
+}
+
+int gemm_rowform_qkv_rope(const __nv_bfloat16* A, long long lda, const __nv_bfloat16* W, long long ldw, int M,
+                          int K, const __nv_bfloat16* bias, const RopeEpilogue& epi, cudaStream_t stream) {
+  const int N = 3 * epi.D;
+  if (M <= 0 || K <= 0) return set_error("gemm_qkv_rope: empty problem");
+  if (K % 8 || epi.D % 64 || epi.D != epi.n_heads * 64 || !bias) return set_error("gemm_qkv_rope: unsupported shape");
+  const int bn = 256;                                // 4 heads per column tile; N = 3D is a multiple of 64
+  int cg = (M > BM) ? 2 : 1;
+  if (g_force_cg == 1) cg = 1;
+  CUtensorMap tA, tB;
+  if (make_tmap_bf16_2d(&tA, A, M, K, lda, BM)) return 1;
+  if (make_tmap_bf16_2d(&tB, W, N, K, ldw, bn / cg)) return 1;
+  GemmParams p{};
+  p.M = M; p.N = N; p.K = K;
+  p.m_blocks = (M + BM * cg - 1) / (BM * cg);
+  p.n_blocks = (N + bn - 1) / bn;
+  p.k_blocks = (K + BK - 1) / BK;
+  p.k_splits = 1;
+  p.kb_per_split = p.k_blocks;
+  p.tile_rows = BM;
+  p.mode = EPI_QKV_ROPE;
+  p.bias = bias;
+  p.rope = epi;
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  const bool prof = g_prof.on && cudaStreamIsCapturing(stream, &cap) == cudaSuccess &&
+                    cap == cudaStreamCaptureStatusNone;
+  if (prof) cudaEventRecord(profile_event(), stream);
+  const int rc = dispatch_gemm(bn, cg, tA, tB, p, stream);
+  if (prof) {
+    cudaEventRecord(profile_event(), stream);
+    g_prof.flops += 2.0 * M * static_cast<double>(N) * K;
+    g_prof.launches += 1;
+  }
+  return rc;
 }
 
 int gemm_swapped_decode(const __nv_bfloat16* W, long long ldw, const __nv_bfloat16* X, long long ldx,

@@ -14,6 +14,7 @@ enum : int {
   EPI_BIAS_RESIDUAL = 2,   // out = bf16(bf16(acc + bias) + residual)
   EPI_PARTIAL = 3,         // swapped form: fp32 partial sums to workspace
   EPI_DECODE_QKV_MLP = 4,  // swapped form, no split-K: bias + RoPE + KV-page write (qkv rows), bias + GELU (fc1 rows)
+  EPI_QKV_ROPE = 5,        // row form, decoder QKV projection: bias + partial RoPE, q -> q_out, k/v -> KV pages
 };
 
 // error plumbing: every entry point returns 0 on success; the message is kept per thread.
@@ -63,6 +64,22 @@ int gemm_swapped(const __nv_bfloat16* W, long long ldw, const __nv_bfloat16* X, 
 // Decode-step [qkv ; fc1] stream with everything downstream fused into the GEMM epilogue (text.py:30-43,
 // moondream.py:74-78, layers.py:130,137): rows < 3D are q|k|v features (bias, bf16 round, partial RoPE,
 // q -> q_out, k/v -> KV pages), rows >= 3D are fc1 features (bias, round, GELU -> hid).
+// Prefill QKV projection with RoPE and the KV-cache write fused into the GEMM epilogue (text.py:30-43,
+// rope.py:20-48, moondream.py:74-78): output column block -> (q|k|v, head, half-head); row -> (sequence, position).
+struct RopeEpilogue {
+  int D, n_heads, n_seqs;
+  const int* q_offsets;           // [n_seqs + 1] token rows of each sequence
+  const int* start_pos;           // [n_seqs]
+  const float* freqs;             // rope table [ctx][16][2]
+  __nv_bfloat16* q_out;           // [tokens, D]
+  __nv_bfloat16* kv_pool;
+  int n_pages;
+  const int* block_tables;
+  int max_blocks, layer;
+};
+int gemm_rowform_qkv_rope(const __nv_bfloat16* A, long long lda, const __nv_bfloat16* W, long long ldw, int M,
+                          int K, const __nv_bfloat16* bias, const RopeEpilogue& epi, cudaStream_t stream);
+
 struct DecodeEpilogue {
   int D, FF, n_heads;
   const __nv_bfloat16* bias;      // [3D + FF]
