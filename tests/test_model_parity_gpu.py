@@ -4,7 +4,7 @@ fixtures generated from the unmodified reference.
 
 Tolerances (written here on purpose):
   * integer outputs (token ids, region bins, tilings): exact, except that an argmax may differ where
-    the ORACLE's own top-1/top-2 logit margin is below NEAR_TIE_ULPS bf16 ulps of the top logit (the
+    the ORACLE's own top-1/top-2 logit margin is below NEAR_TIE_ULPS (4.5) bf16 ulps of the top logit (the
     reference rounds logits to bf16, so such decisions are ties up to rounding; its own argmax moves
     there between 1 and 8 CPU threads).  After such a legitimate flip the two sequences
     diverge, so the comparison of that sequence stops there;
@@ -22,7 +22,10 @@ import torch
 pytestmark = pytest.mark.gpu
 
 REL_TOL = 3e-2
-NEAR_TIE_ULPS = 3.0     # hidden states agree to ~1e-2 relative => logits to ~2 bf16 ulps
+# Measured on the tiny preset (85 decode steps, oracle/bf16 vs oracle/fp32): the bf16 REFERENCE's own logits sit
+# mean 1.1 / p90 1.8 / max 2.2 bf16 ulps (of the top logit) from the fp32 truth.  A margin is the difference of two
+# such logits, so two independent bf16 evaluations of the same model can disagree on a margin by ~2 x 2.2 ulps.
+NEAR_TIE_ULPS = 4.5
 GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
 
 
