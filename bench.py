@@ -229,16 +229,15 @@ def run_main(args, cfg, sd, rank, world, local_rank):
     gathered = torch.empty((world * B, NEW_TOKENS + 1), dtype=torch.int32, device=dev) if world > 1 else None
 
     def step_resident():
-        prefixes = eng.encode_crops(crops_dev, offsets, tilings)
-        res = eng.generate(prefixes, prompts, NEW_TOKENS, consume=True, stop_on_eos=False, to_host=False)
+        # ViT -> stitch/pool/project -> [BOS; image; prompt] prefill (one pass) -> first token -> decode loop
+        res = eng.caption_from_crops(crops_dev, offsets, tilings, prompts, NEW_TOKENS, to_host=False, stop_on_eos=False)
         if world > 1:   # the one collective of the path: finished token ids over NVLink
             dist.all_gather_into_tensor(gathered, res.tokens)
         return res
 
     def step_e2e():
-        prefixes = eng.encode_images(images)           # host crop -> pinned H2D -> ViT -> prefill
-        res = eng.generate(prefixes, prompts, NEW_TOKENS, consume=True, stop_on_eos=False, to_host=True)
-        return res
+        dev, offs, til = eng.stage_images(images)      # host crop (PIL) -> pinned staging -> H2D
+        return eng.caption_from_crops(dev, offs, til, prompts, NEW_TOKENS, to_host=True, stop_on_eos=False)
 
     def barrier():
         torch.cuda.synchronize()

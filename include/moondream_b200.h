@@ -168,10 +168,11 @@ int md_vision_encode(md_model* model, const uint8_t* crops, int n_crops, void* f
  * crop_offsets int32 [n_images+1] (first crop of an image is its global crop), tilings int32
  * [n_images][2].  Writes the projected rows of image i to embeds rows i*prefix_len+1 .. +grid^2
  * (row i*prefix_len is left for the BOS embedding, moondream.py:250-254); embeds is
- * [n_images*prefix_len, txt_dim] bf16. */
+ * [n_images*rows_per_image, txt_dim] bf16 with rows_per_image >= prefix_len (prefix_len when 0 is passed): a larger
+ * value leaves room after each image for prompt embeddings so image and prompt prefill in one pass. */
 long long md_vision_project_workspace_bytes(const md_model* model, int n_images);
 int md_vision_project(md_model* model, const void* feats, const int* crop_offsets, const int* tilings,
-                      int n_images, void* embeds, void* workspace, void* stream);
+                      int n_images, void* embeds, int rows_per_image, void* workspace, void* stream);
 
 /* text_encoder (text.py:12-13): out[i] = wte[ids[i * id_stride]]. */
 int md_embed_tokens(md_model* model, const int* ids, long long id_stride, int n, void* out,

@@ -61,7 +61,7 @@ _SIGNATURES = {
     "md_vision_encode_workspace_bytes": (_LL, [_P, c_int]),
     "md_vision_encode": (c_int, [_P, _P, c_int, _P, _P, _P]),
     "md_vision_project_workspace_bytes": (_LL, [_P, c_int]),
-    "md_vision_project": (c_int, [_P, _P, _P, _P, c_int, _P, _P, _P]),
+    "md_vision_project": (c_int, [_P, _P, _P, _P, c_int, _P, c_int, _P, _P]),
     "md_embed_tokens": (c_int, [_P, _P, _LL, c_int, _P, _LL, _P]),
     "md_text_prefill_workspace_bytes": (_LL, [_P, c_int]),
     "md_text_prefill": (c_int, [_P, _P, c_int, _P, _P, c_int, c_int, _KV, _P, _P]),

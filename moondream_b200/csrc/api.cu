@@ -150,10 +150,10 @@ long long md_vision_project_workspace_bytes(const md_model* model, int n_images)
   return model ? md::vision_project_ws_bytes(*model, n_images) : -1;
 }
 int md_vision_project(md_model* model, const void* feats, const int* crop_offsets, const int* tilings,
-                      int n_images, void* embeds, void* workspace, void* stream) {
+                      int n_images, void* embeds, int rows_per_image, void* workspace, void* stream) {
   NEED(model && feats && crop_offsets && tilings && embeds && workspace, "md_vision_project");
-  return md::vision_project(*model, BF(feats), crop_offsets, tilings, n_images, BFM(embeds), workspace,
-                            STREAM(stream));
+  return md::vision_project(*model, BF(feats), crop_offsets, tilings, n_images, BFM(embeds), rows_per_image,
+                            workspace, STREAM(stream));
 }
 
 int md_embed_tokens(md_model* model, const int* ids, long long id_stride, int n, void* out,

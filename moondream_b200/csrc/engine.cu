@@ -139,7 +139,7 @@ long long vision_project_ws_bytes(const Model& m, int n_images) {
 }
 
 int vision_project(Model& m, const bf16* feats, const int* crop_offsets, const int* tilings, int n_images,
-                   bf16* embeds, void* ws, cudaStream_t st) {
+                   bf16* embeds, int rows_per_image, void* ws, cudaStream_t st) {
   const md_dims& d = m.d;
   if (n_images <= 0) return set_error("md_vision_project: empty batch");
   const int tok = d.grid * d.grid;
@@ -150,9 +150,11 @@ int vision_project(Model& m, const bf16* feats, const int* crop_offsets, const i
   if (stitch_pool_concat(feats, crop_offsets, tilings, n_images, d.grid, d.margin, d.vis_dim, cat, st)) return 1;
   if (gemm_rowform(cat, 2 * d.vis_dim, m.proj_fc1.w, 2 * d.vis_dim, T, d.proj_inner, 2 * d.vis_dim,
                    EPI_BIAS_GELU, m.proj_fc1.b, nullptr, 0, 0, hid, d.proj_inner, 0, 0, 0, st)) return 1;
-  // rows of image i land at i*prefix_len + 1 .. (row i*prefix_len is the BOS embedding)
+  // rows of image i land at i*rows_per_image + 1 .. (row i*rows_per_image is the BOS embedding; rows after the
+  // image tokens may hold the prompt embeddings when image and prompt are prefilled in one pass)
+  if (rows_per_image < d.prefix_len) rows_per_image = d.prefix_len;
   return gemm_rowform(hid, d.proj_inner, m.proj_fc2.w, d.proj_inner, T, d.txt_dim, d.proj_inner, EPI_BIAS,
-                      m.proj_fc2.b, nullptr, 0, 0, embeds, d.txt_dim, tok, d.prefix_len, 1, st);
+                      m.proj_fc2.b, nullptr, 0, 0, embeds, d.txt_dim, tok, rows_per_image, 1, st);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -36,7 +36,7 @@ long long vision_encode_ws_bytes(const Model& m, int n_crops);
 int vision_encode(Model& m, const uint8_t* crops, int n_crops, bf16* feats, void* ws, cudaStream_t st);
 long long vision_project_ws_bytes(const Model& m, int n_images);
 int vision_project(Model& m, const bf16* feats, const int* crop_offsets, const int* tilings, int n_images,
-                   bf16* embeds, void* ws, cudaStream_t st);
+                   bf16* embeds, int rows_per_image, void* ws, cudaStream_t st);
 long long text_prefill_ws_bytes(const Model& m, int T);
 int text_prefill(Model& m, bf16* x, int T, const int* q_offsets, const int* start_pos, int n_seqs,
                  int max_q, const md_kv& kv, void* ws, cudaStream_t st);

@@ -231,14 +231,14 @@ class Engine:
         return feats
 
     def vision_project(self, feats: torch.Tensor, crop_offsets: Sequence[int],
-                       tilings: Sequence[Tuple[int, int]], embeds: torch.Tensor):
+                       tilings: Sequence[Tuple[int, int]], embeds: torch.Tensor, rows_per_image: int = 0):
         """reconstruct_from_crops + _vis_proj for all images; fills embeds rows 1..729 of each image."""
         n = len(tilings)
         offs = self._i32(list(crop_offsets))
         til = self._i32([list(x) for x in tilings])
         ws = self._workspace(self.lib.md_vision_project_workspace_bytes(self.model, n))
         N.check(self.lib.md_vision_project(self.model, N.ptr(feats), N.ptr(offs), N.ptr(til), n,
-                                           N.ptr(embeds), N.ptr(ws), N.current_stream()),
+                                           N.ptr(embeds), rows_per_image, N.ptr(ws), N.current_stream()),
                 "md_vision_project")
 
     # ------------------------------------------------------------------ text
@@ -301,6 +301,55 @@ class Engine:
 
     def encode_images(self, images: Sequence[np.ndarray], return_hidden: bool = False):
         """Host uint8 HxWx3 images -> crops (PIL Lanczos, image_crops.py:58-167) -> H2D -> encode_crops."""
+        # crops are written straight into persistent pinned staging memory by a small thread pool
+        # (PIL's resize and numpy's copies release the GIL)
+        dev, offsets, tilings = self.stage_images(images)
+        return self.encode_crops(dev, offsets, tilings, return_hidden=return_hidden)
+
+    def encode_crops_with_prompt(self, crops_u8: torch.Tensor, crop_offsets: Sequence[int],
+                                 tilings: Sequence[Tuple[int, int]], prompt: Sequence[Sequence[int]]):
+        """encode_image + the prompt prefill of caption()/query() in ONE decoder pass per batch:
+        rows [BOS | 729 image tokens | prompt] at positions 0..729+Tp under the same prefix-LM mask
+        (moondream.py:138-146, :254-257, :308-310).  Needs equal prompt lengths.  Returns the prefixes
+        (pos = 730 + Tp) and the last-token hidden states [n_img, dim] for the LM head."""
+        t = self.cfg.text
+        n_img = len(tilings)
+        Tp = len(prompt[0])
+        assert all(len(p) == Tp for p in prompt) and len(prompt) == n_img
+        rows = t.prefix_attn + Tp
+        feats = self.vision_encode(crops_u8)
+        embeds = torch.empty((n_img * rows, t.dim), dtype=torch.bfloat16, device=self.device)
+        self.vision_project(feats, crop_offsets, tilings, embeds, rows_per_image=rows)
+        bos = torch.full((n_img,), self.cfg.tokenizer.bos_id, dtype=torch.int32, device=self.device)
+        self.embed(bos, embeds, ldo=rows * t.dim)
+        view = embeds.view(n_img, rows, t.dim)
+        ptoks = self._i32([tok for p in prompt for tok in p])
+        pemb = torch.empty((n_img * Tp, t.dim), dtype=torch.bfloat16, device=self.device)
+        self.embed(ptoks, pemb)
+        view[:, t.prefix_attn:].copy_(pemb.view(n_img, Tp, t.dim))
+        n_pages = math.ceil(rows / PAGE)
+        prefixes = [PrefixKV(rows, self.pages.alloc(n_pages), self.pages) for _ in range(n_img)]
+        bt = torch.zeros((n_img, self.max_blocks), dtype=torch.int32)
+        for i, p in enumerate(prefixes):
+            bt[i, : len(p.pages)] = torch.tensor(p.pages, dtype=torch.int32)
+        bt = bt.to(self.device)
+        self.prefill(embeds, [i * rows for i in range(n_img + 1)], [0] * n_img, bt)
+        hidden_last = view[:, rows - 1].contiguous()
+        return prefixes, hidden_last
+
+    def caption_from_crops(self, crops_u8: torch.Tensor, crop_offsets: Sequence[int],
+                           tilings: Sequence[Tuple[int, int]], prompts: Sequence[Sequence[int]], max_tokens: int,
+                           to_host: bool = True, stop_on_eos: bool = True) -> "GenerationResult":
+        """encode + greedy generation for a batch; one fused prefill pass when the prompts have equal length."""
+        if len({len(p) for p in prompts}) == 1:
+            prefixes, hidden_last = self.encode_crops_with_prompt(crops_u8, crop_offsets, tilings, prompts)
+            return self.generate(prefixes, prompts, max_tokens, consume=True, stop_on_eos=stop_on_eos, to_host=to_host,
+                                 prefilled_hidden=hidden_last)
+        prefixes = self.encode_crops(crops_u8, crop_offsets, tilings)
+        return self.generate(prefixes, prompts, max_tokens, consume=True, stop_on_eos=stop_on_eos, to_host=to_host)
+
+    def stage_images(self, images: Sequence[np.ndarray]):
+        """host uint8 images -> crops in pinned staging memory -> device; returns (crops, offsets, tilings)"""
         v = self.cfg.vision
         kw = dict(overlap_margin=v.overlap_margin, max_crops=v.max_crops,
                   base_size=(v.crop_size, v.crop_size), patch_size=v.enc_patch_size)
@@ -308,8 +357,6 @@ class Engine:
         offsets = [0]
         for th, tw in tilings:
             offsets.append(offsets[-1] + th * tw + 1)
-        # crops are written straight into persistent pinned staging memory by a small thread pool
-        # (PIL's resize and numpy's copies release the GIL)
         n = offsets[-1]
         if self._stage is None or self._stage.shape[0] < n:
             self._stage = torch.empty((max(n, 64), v.crop_size, v.crop_size, 3), dtype=torch.uint8).pin_memory()
@@ -322,8 +369,7 @@ class Engine:
             list(self._pool.map(work, range(len(images))))
         else:
             work(0)
-        dev = self._stage[:n].to(self.device, non_blocking=True)
-        return self.encode_crops(dev, offsets, tilings, return_hidden=return_hidden)
+        return self._stage[:n].to(self.device, non_blocking=True), offsets, tilings
 
     def prefix_kv_tensors(self, prefix: PrefixKV) -> List[Tuple[torch.Tensor, torch.Tensor]]:
         """Materialise (k, v) [1, heads, pos, 64] per layer like EncodedImage.caches (moondream.py:56-59)."""
@@ -409,7 +455,8 @@ class Engine:
     def generate(self, prefixes: Sequence[PrefixKV], prompts: Sequence[Sequence[int]], max_tokens: int,
                  forced: Optional[Sequence[Sequence[int]]] = None, consume: bool = False,
                  use_graph: bool = True, stop_on_eos: bool = True,
-                 prompt_embeds: Optional[torch.Tensor] = None, to_host: bool = True) -> GenerationResult:
+                 prompt_embeds: Optional[torch.Tensor] = None, to_host: bool = True,
+                 prefilled_hidden: Optional[torch.Tensor] = None) -> GenerationResult:
         """Greedy `_generate_answer` (moondream.py:434-539) for a batch: ragged prompt prefill, first
         token from the LM head, then `max_tokens` decode steps (the reference also runs the step after
         the last emitted token).  Returns the argmax at every step; callers cut at eos."""
@@ -418,25 +465,30 @@ class Engine:
         assert len(prompts) == B
         S = max_tokens + 1
         lens = [len(p) for p in prompts]
+        if prefilled_hidden is not None:
+            lens = [0] * B              # prefixes already include the prompt; prefilled_hidden = last-token hidden states
         total = [prefixes[i].pos + lens[i] + max_tokens + 1 for i in range(B)]
         bt, owned = self._sequence_tables(prefixes, max(total), consume)
         try:
             st = self._decode_buffers(B, S)
             st["bt"].copy_(bt)
             # ---- prompt prefill (moondream.py:280-321) ----
-            q_off = [0]
-            for n in lens:
-                q_off.append(q_off[-1] + n)
-            if prompt_embeds is None:
-                flat = self._i32([tok for p in prompts for tok in p])
-                x = torch.empty((q_off[-1], t.dim), dtype=torch.bfloat16, device=self.device)
-                self.embed(flat, x)
+            if prefilled_hidden is not None:
+                st["x"].copy_(prefilled_hidden)
             else:
-                x = prompt_embeds
-            self.prefill(x, q_off, [p.pos for p in prefixes], st["bt"])
-            last = self._i32([q_off[i + 1] - 1 for i in range(B)])
-            N.check(self.lib.md_gather_rows_bf16(N.ptr(x), x.stride(0), N.ptr(last), B, t.dim, N.ptr(st["x"]),
-                                                 st["x"].stride(0), N.current_stream()), "md_gather_rows_bf16")
+                q_off = [0]
+                for n in lens:
+                    q_off.append(q_off[-1] + n)
+                if prompt_embeds is None:
+                    flat = self._i32([tok for p in prompts for tok in p])
+                    x = torch.empty((q_off[-1], t.dim), dtype=torch.bfloat16, device=self.device)
+                    self.embed(flat, x)
+                else:
+                    x = prompt_embeds
+                self.prefill(x, q_off, [p.pos for p in prefixes], st["bt"])
+                last = self._i32([q_off[i + 1] - 1 for i in range(B)])
+                N.check(self.lib.md_gather_rows_bf16(N.ptr(x), x.stride(0), N.ptr(last), B, t.dim, N.ptr(st["x"]),
+                                                     st["x"].stride(0), N.current_stream()), "md_gather_rows_bf16")
             st["step"].zero_()
             st["finished"].zero_()
             self.lm_head(st["x"], st["preds"], S, mask_id=-1, out_index=None, margins=st["margins"])

@@ -167,6 +167,31 @@ class MoondreamModel:
             out.append(seq)
         return out
 
+    def _cut(self, rows: List[List[int]], max_tokens: int) -> List[List[int]]:
+        eos = self.config.tokenizer.eos_id
+        out = []
+        for row in rows:
+            seq = []
+            for t in row[:max_tokens]:
+                if t == eos:
+                    break
+                seq.append(t)
+            out.append(seq)
+        return out
+
+    def _run_images(self, images: Sequence[Any], prompts: Sequence[Sequence[int]], max_tokens: int) -> List[List[int]]:
+        """Batched generation straight from raw images: when no image is pre-encoded the image prefix and the
+        prompt are prefilled in one decoder pass (engine.caption_from_crops); otherwise the two-step path."""
+        if any(isinstance(im, EncodedImage) for im in images):
+            return self._run(self.encode_images(images), prompts, max_tokens)
+        out: List[List[int]] = []
+        for lo in range(0, len(images), self._max_batch):
+            arrs = [_as_array(im) for im in images[lo: lo + self._max_batch]]
+            dev, offs, til = self.engine.stage_images(arrs)
+            res = self.engine.caption_from_crops(dev, offs, til, prompts[lo: lo + self._max_batch], max_tokens)
+            out += self._cut(res.tokens.tolist(), max_tokens)
+        return out
+
     def _stream_text(self, tokens: Sequence[int]):
         """Streaming detokenisation with the reference's flush rules (moondream.py:476-537)."""
         cache: List[int] = []
@@ -204,8 +229,7 @@ class MoondreamModel:
         if length not in tpl:
             raise ValueError(f"Model does not support caption length '{length}'.")
         max_tokens = self._greedy(settings)
-        enc = self.encode_images(images)
-        toks = self._run(enc, [tpl[length]] * len(enc), max_tokens)
+        toks = self._run_images(images, [tpl[length]] * len(images), max_tokens)
         return [{"caption": "".join(self._stream_text(t))} for t in toks]
 
     def caption(self, image, length: Literal["normal", "short", "long"] = "normal", stream: bool = False,
@@ -238,9 +262,8 @@ class MoondreamModel:
         if self.config.tokenizer.templates["query"] is None:
             raise NotImplementedError("Model does not support querying.")
         max_tokens = self._greedy(settings)
-        enc = self.encode_images(images)
         prompts = [self._query_prompt(q, None, False) for q in questions]
-        toks = self._run(enc, prompts, max_tokens)
+        toks = self._run_images(images, prompts, max_tokens)
         return [{"answer": "".join(self._stream_text(t))} for t in toks]
 
     def query(self, image=None, question: str = None, reasoning: bool = False,

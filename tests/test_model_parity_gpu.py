@@ -240,3 +240,20 @@ def test_large_batch_matches_small_batch(tiny):
                 break
     del big
     torch.cuda.empty_cache()
+
+
+def test_single_pass_prefill_matches_two_pass_and_oracle(tiny):
+    """[BOS; image; prompt] prefilled in one decoder pass (engine.caption_from_crops) vs the reference's two steps
+    (encode_image, then the prompt prefill of caption/query) and vs the oracle."""
+    from moondream_b200 import synth
+
+    cfg, sd, eng, orc, _ = tiny
+    imgs = [synth.synthetic_image(50 + i, *IMAGES[i % 3]) for i in range(4)]
+    prompts = [synth.synthetic_prompt(60 + i, 9, cfg.text.vocab_size) for i in range(4)]
+    dev, offs, til = eng.stage_images(imgs)
+    one = eng.caption_from_crops(dev, offs, til, prompts, 16)
+    two = eng.generate(eng.encode_images(imgs), prompts, 16)
+    for i in range(4):
+        o = orc.generate(orc.encode_image(imgs[i]), prompts[i], 16)
+        _check_tokens(one.tokens[i].tolist(), o, f"single-pass image {i}")
+        _check_tokens(two.tokens[i].tolist(), o, f"two-pass image {i}")
