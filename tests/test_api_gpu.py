@@ -1,0 +1,107 @@
+"""The drop-in `MoondreamModel` surface (reference moondream/torch/moondream.py) driven the way the reference's
+callers drive it: encode_image / caption / query / detect / point, settings keys, result shapes, exceptions."""
+import numpy as np
+import pytest
+import torch
+from PIL import Image
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def api():
+    from moondream_b200 import config as C, synth
+    from moondream_b200.moondream import MoondreamModel
+    from oracle.moondream_oracle import OracleModel
+    from oracle.reference_shim import StubTokenizer
+
+    cfg = C.tiny()
+    sd = synth.synthetic_state_dict(cfg, 0)
+    model = MoondreamModel(cfg, tokenizer=StubTokenizer(cfg.text.vocab_size), max_batch=8)
+    model.load_state_dict(sd)
+    return cfg, model, OracleModel(cfg, sd)
+
+
+def _ids(text):
+    return [int(t) for t in text.split()]
+
+
+def _agree(got, gen, what):
+    for i, (a, b) in enumerate(zip(got, gen.tokens)):
+        if a != b:
+            assert gen.margin_ulps[i] < 4.5, (what, i, a, b, gen.margin_ulps[i])
+            return
+
+
+def test_caption_query_through_the_api(api):
+    from moondream_b200 import synth
+    from moondream_b200.moondream import EncodedImage
+
+    cfg, model, orc = api
+    img = synth.synthetic_image(3, 500, 700)
+    enc = model.encode_image(Image.fromarray(img))
+    assert isinstance(enc, EncodedImage) and enc.pos == 730 and model.encode_image(enc) is enc
+    assert len(enc.caches) == cfg.text.n_layers and tuple(enc.caches[0][0].shape) == (1, cfg.text.n_heads, 730, 64)
+    settings = {"temperature": 0, "max_tokens": 10}
+    o_enc = orc.encode_image(img)
+    out = model.caption(enc, "short", settings=settings)
+    assert set(out) == {"caption"} and isinstance(out["caption"], str)
+    _agree(_ids(out["caption"]), orc.generate(o_enc, cfg.tokenizer.templates["caption"]["short"], 10), "caption")
+    chunks = list(model.caption(enc, "normal", stream=True, settings=settings)["caption"])
+    assert "".join(chunks) == model.caption(enc, "normal", settings=settings)["caption"]
+    # query: prefix + question + suffix + suffix (the reference's duplicated suffix, moondream.py:586-604)
+    q = model.query(enc, "11 12 13", settings=settings)
+    tk = cfg.tokenizer
+    prompt = tk.templates["query"]["prefix"] + [11, 12, 13] + tk.templates["query"]["suffix"] * 2
+    _agree(_ids(q["answer"]), orc.generate(o_enc, prompt, 10), "query")
+    # batch calls agree with single calls
+    many = model.caption_batch([img, synth.synthetic_image(4, 378, 378)], "short", settings=settings)
+    assert len(many) == 2 and set(many[0]) == {"caption"}
+    _agree(_ids(many[0]["caption"]), orc.generate(o_enc, cfg.tokenizer.templates["caption"]["short"], 10), "caption_batch")
+
+
+def test_detect_point_through_the_api(api):
+    from moondream_b200 import synth
+
+    cfg, model, orc = api
+    img = synth.synthetic_image(8, 800, 600)
+    enc = model.encode_image(img)
+    o_enc = orc.encode_image(img)
+    tk = cfg.tokenizer
+    det = model.detect(enc, "17 23", settings={"max_objects": 2})
+    assert set(det) == {"objects"} and all(set(o) == {"x_min", "y_min", "x_max", "y_max"} for o in det["objects"])
+    want = orc.generate_points(o_enc, tk.templates["detect"]["prefix"] + [17, 23] + tk.templates["detect"]["suffix"], True, 2)
+    if want and min(want[0]["ulps"][:4]) >= 4.5:
+        assert len(det["objects"]) >= 1
+        for k in ("x_min", "y_min", "x_max", "y_max"):
+            assert abs(det["objects"][0][k] - want[0][k]) < 1e-5
+    pts = model.point(enc, "17 23", settings={"max_objects": 2})
+    assert set(pts) == {"points"} and all(set(p) == {"x", "y"} for p in pts["points"])
+
+
+def test_error_behaviour_matches_the_reference(api):
+    from moondream_b200 import synth
+
+    cfg, model, _ = api
+    img = synth.synthetic_image(1, 378, 378)
+    with pytest.raises(ValueError):
+        model.encode_image("not an image")                       # moondream.py:237-238
+    with pytest.raises(ValueError):
+        model.query(img, None, settings={"temperature": 0})      # moondream.py:553-554
+    with pytest.raises(ValueError):
+        model.query(None, "x", spatial_refs=[(0.5, 0.5)], settings={"temperature": 0})   # :556-557
+    with pytest.raises(ValueError):
+        model.caption(img, "poetic", settings={"temperature": 0})  # :634-635
+    with pytest.raises(ValueError):
+        model.caption(img, "short")                               # default temperature 0.5: sampling not implemented
+    with pytest.raises(NotImplementedError):
+        model.caption(img, "short", settings={"temperature": 0, "variant": "foo"})
+
+
+def test_spatial_refs_query_runs(api):
+    from moondream_b200 import synth
+
+    cfg, model, _ = api
+    img = synth.synthetic_image(2, 378, 378)
+    out = model.query(img, "5 6", spatial_refs=[(0.25, 0.75), (0.1, 0.2, 0.5, 0.9)], settings={"temperature": 0, "max_tokens": 4})
+    assert isinstance(out["answer"], str) and len(_ids(out["answer"])) <= 4
