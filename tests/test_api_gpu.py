@@ -103,5 +103,5 @@ def test_spatial_refs_query_runs(api):
 
     cfg, model, _ = api
     img = synth.synthetic_image(2, 378, 378)
-    out = model.query(img, "5 6", spatial_refs=[(0.25, 0.75), (0.1, 0.2, 0.5, 0.9)], settings={"temperature": 0, "max_tokens": 4})
+    out = model.query(img, "15 16", spatial_refs=[(0.25, 0.75), (0.1, 0.2, 0.5, 0.9)], settings={"temperature": 0, "max_tokens": 4})
     assert isinstance(out["answer"], str) and len(_ids(out["answer"])) <= 4
