@@ -76,7 +76,7 @@ def stitch_crops(local: Tensor, tiling: Tuple[int, int], margin: int) -> Tensor:
     g = local.shape[1]
     inner = g - 2 * margin
     canvas = torch.zeros((inner * th + 2 * margin, inner * tw + 2 * margin, local.shape[3]),
-                         dtype=local.dtype)
+                         dtype=local.dtype, device=local.device)
     for idx in range(local.shape[0]):
         ty, tx = divmod(idx, tw)
         ys, ye = (0 if ty == 0 else margin), (g if ty == th - 1 else g - margin)
@@ -148,26 +148,29 @@ class Generation:
 
 
 class OracleModel:
-    def __init__(self, cfg, weights: Dict[str, Tensor], dtype: torch.dtype = torch.bfloat16):
+    def __init__(self, cfg, weights: Dict[str, Tensor], dtype: torch.dtype = torch.bfloat16, device="cpu"):
+        """device="cuda" runs the same eager torch ops on a GPU: the reference's torch-CUDA path used as the
+        speed comparator (tools/torch_cuda_comparator.py); parity work always uses the CPU instance."""
         self.cfg = cfg
         self.dtype = dtype
-        self.w = {k: v.to(dtype) for k, v in weights.items()}
+        self.device = torch.device(device)
+        self.w = {k: v.to(device=self.device, dtype=dtype) for k, v in weights.items()}
         t = cfg.text
         self.head_dim = t.dim // t.n_heads
-        self.rope = rope_table(self.head_dim, t.max_context)
+        self.rope = rope_table(self.head_dim, t.max_context).to(self.device)
         # moondream.py:138-146: causal mask with a bidirectional [prefix x prefix] block
         mask = torch.tril(torch.ones(1, 1, t.max_context, t.max_context, dtype=torch.bool))
         prefix = 1 + (cfg.vision.crop_size // cfg.vision.enc_patch_size) ** 2
         mask[..., :prefix, :prefix] = 1
-        self.attn_mask = mask
+        self.attn_mask = mask.to(self.device)
         self.reset_cache()
 
     # ---- KV cache (moondream.py:62-78) ----
     def reset_cache(self):
         t = self.cfg.text
         shape = (1, t.n_kv_heads, t.max_context, self.head_dim)
-        self.k_cache = [torch.zeros(shape, dtype=self.dtype) for _ in range(t.n_layers)]
-        self.v_cache = [torch.zeros(shape, dtype=self.dtype) for _ in range(t.n_layers)]
+        self.k_cache = [torch.zeros(shape, dtype=self.dtype, device=self.device) for _ in range(t.n_layers)]
+        self.v_cache = [torch.zeros(shape, dtype=self.dtype, device=self.device) for _ in range(t.n_layers)]
 
     def load_encoded(self, enc: Encoded):
         """moondream.py:620-623."""
@@ -180,7 +183,7 @@ class OracleModel:
         """vision.py:25-41: uint8 NHWC -> NCHW in `dtype`, in-place /255, -0.5, /0.5."""
         v = self.cfg.vision
         crops, tiling = overlap_crops(image, v.overlap_margin, v.max_crops, v.crop_size, v.enc_patch_size)
-        x = torch.from_numpy(np.transpose(crops, (0, 3, 1, 2))).to(dtype=self.dtype)
+        x = torch.from_numpy(np.transpose(crops, (0, 3, 1, 2))).to(device=self.device, dtype=self.dtype)
         x = x.div_(255.0).sub_(0.5).div_(0.5)
         return x, tiling
 
@@ -285,10 +288,10 @@ class OracleModel:
         """moondream.py:230-268: vision -> [BOS; image] prefill at positions 0..729 -> KV snapshot."""
         with torch.no_grad():
             img_emb = self.run_vision(image)
-            bos = self.embed(torch.tensor([[self.cfg.tokenizer.bos_id]]))
+            bos = self.embed(torch.tensor([[self.cfg.tokenizer.bos_id]], device=self.device))
             x = torch.cat([bos, img_emb[None]], dim=1)
             n = x.size(1)
-            hidden = self.text_decoder(x, self.attn_mask[:, :, 0:n, :], torch.arange(n, dtype=torch.long))
+            hidden = self.text_decoder(x, self.attn_mask[:, :, 0:n, :], torch.arange(n, dtype=torch.long, device=self.device))
             enc = Encoded(n, [(self.k_cache[i][:, :, :n, :].clone(), self.v_cache[i][:, :, :n, :].clone())
                               for i in range(self.cfg.text.n_layers)])
         if return_embeds:
@@ -298,20 +301,20 @@ class OracleModel:
     def prefill_prompt(self, prompt: Sequence[int], pos: int, embeds: Optional[Tensor] = None):
         """moondream.py:280-321 with temperature == 0: returns (logits, hidden, next_token, pos)."""
         with torch.no_grad():
-            x = self.embed(torch.tensor([list(prompt)])) if embeds is None else embeds
+            x = self.embed(torch.tensor([list(prompt)], device=self.device)) if embeds is None else embeds
             T = x.size(1)
             hidden = self.text_decoder(x, self.attn_mask[:, :, pos:pos + T, :],
-                                       torch.arange(pos, pos + T, dtype=torch.long))
+                                       torch.arange(pos, pos + T, dtype=torch.long, device=self.device))
             logits = self.lm_head(hidden)
             nxt = torch.argmax(logits, dim=-1).unsqueeze(1)
         return logits, hidden, nxt, pos + T
 
     def decode_one(self, emb: Tensor, pos: int):
         """moondream.py:183-192 + the mask/pos bookkeeping of the generator (:472-474, :514)."""
-        mask = torch.zeros(1, 1, self.cfg.text.max_context, dtype=torch.bool)
+        mask = torch.zeros(1, 1, self.cfg.text.max_context, dtype=torch.bool, device=self.device)
         mask[:, :, : pos + 1] = 1
         with torch.no_grad():
-            hidden = self.text_decoder(emb, mask, torch.tensor([pos], dtype=torch.long))
+            hidden = self.text_decoder(emb, mask, torch.tensor([pos], dtype=torch.long, device=self.device))
             logits = self.lm_head(hidden)
         return logits, hidden
 
@@ -353,7 +356,7 @@ class OracleModel:
             out.predicted.append(pred)
             out.margins.append(margin)
             out.margin_ulps.append(ulps)
-            logits, hidden = self.decode_one(self.embed(torch.tensor([[tok]])), pos)
+            logits, hidden = self.decode_one(self.embed(torch.tensor([[tok]], device=self.device)), pos)
             logits[:, tk.answer_id] = float("-inf")
             pos += 1
             pred = int(torch.argmax(logits, dim=-1).item())
