@@ -48,11 +48,11 @@ __device__ __forceinline__ float chunk_max(const uint32_t (&v)[32], bool full, i
   float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
   if (full) {
 #pragma unroll
-    for (int i = 0; i < 32; i += 4) {
-      m0 = fmaxf(m0, __uint_as_float(v[i]));
-      m1 = fmaxf(m1, __uint_as_float(v[i + 1]));
-      m2 = fmaxf(m2, __uint_as_float(v[i + 2]));
-      m3 = fmaxf(m3, __uint_as_float(v[i + 3]));
+    for (int i = 0; i < 32; i += 8) {            // max(max(m, a), b) folds into one 3-input FMNMX
+      m0 = fmaxf(fmaxf(m0, __uint_as_float(v[i])), __uint_as_float(v[i + 1]));
+      m1 = fmaxf(fmaxf(m1, __uint_as_float(v[i + 2])), __uint_as_float(v[i + 3]));
+      m2 = fmaxf(fmaxf(m2, __uint_as_float(v[i + 4])), __uint_as_float(v[i + 5]));
+      m3 = fmaxf(fmaxf(m3, __uint_as_float(v[i + 6])), __uint_as_float(v[i + 7]));
     }
   } else {
 #pragma unroll
@@ -73,16 +73,20 @@ __device__ __forceinline__ float chunk_probs(const uint32_t (&v)[32], bool full,
   uint32_t pk[16];
   float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
   if (full) {
+    const float2 sc = make_float2(scale_log2, scale_log2), nb = make_float2(-base, -base);
+    float2 s01 = make_float2(0.f, 0.f), s23 = make_float2(0.f, 0.f);
 #pragma unroll
     for (int i = 0; i < 16; i += 2) {
-      const float e0 = ex2_approx(fmaf(__uint_as_float(v[2 * i]), scale_log2, -base));
-      const float e1 = ex2_approx(fmaf(__uint_as_float(v[2 * i + 1]), scale_log2, -base));
-      const float e2 = ex2_approx(fmaf(__uint_as_float(v[2 * i + 2]), scale_log2, -base));
-      const float e3 = ex2_approx(fmaf(__uint_as_float(v[2 * i + 3]), scale_log2, -base));
-      a0 += e0; a1 += e1; a2 += e2; a3 += e3;
-      pk[i] = pack_bf16x2(e0, e1);
-      pk[i + 1] = pack_bf16x2(e2, e3);
+      const float2 x0 = ffma2(make_float2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1])), sc, nb);
+      const float2 x1 = ffma2(make_float2(__uint_as_float(v[2 * i + 2]), __uint_as_float(v[2 * i + 3])), sc, nb);
+      const float2 e0 = make_float2(ex2_approx(x0.x), ex2_approx(x0.y));
+      const float2 e1 = make_float2(ex2_approx(x1.x), ex2_approx(x1.y));
+      s01 = fadd2(s01, e0);
+      s23 = fadd2(s23, e1);
+      pk[i] = pack_bf16x2(e0.x, e0.y);
+      pk[i + 1] = pack_bf16x2(e1.x, e1.y);
     }
+    a0 = s01.x; a1 = s01.y; a2 = s23.x; a3 = s23.y;
   } else {
 #pragma unroll
     for (int i = 0; i < 16; ++i) {

@@ -524,81 +524,12 @@ namespace md {
 // ------------------------------------------------------------------------------------------------
 // Fused decode-step epilogues (one token per sequence).
 //
-// decode_qkv_mlp_epilogue: finishes the [qkv ; fc1] weight-streaming GEMM of one layer.
-//   ws [splits][B][3D + FF] fp32 partial sums.  One warp per unit of 64 features:
-//     q / k head : + bias, round to bf16 (the Linear output, text.py:30), partial RoPE (rope.py:20-48),
-//                  q -> q_out [B, D]; k -> KV page (moondream.py:74-78)
-//     v head     : + bias -> KV page
-//     fc1 unit   : + bias, round, GELU-tanh (layers.py:130,137) -> hid (row stride ld_hid)
+// (The [qkv ; fc1] stream is finished inside decode_attention_kernel<true>, attention.cu.)
 // decode_residual_ln_epilogue: finishes the K-concatenated [proj | fc2] GEMM.
 //   splits [0, proj_splits) belong to proj(att), the rest to fc2(hid); each group is summed in fixed
 //   order, biased and rounded to bf16 separately, then x = bf16(bf16(x + attn) + mlp) exactly as
 //   text.py:158 evaluates `x + l_attn + l_mlp`; finally LayerNorm (next block's ln, or post_ln).
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128)
-decode_qkv_mlp_epilogue_kernel(const float* __restrict__ ws, int splits, int B, int D, int FF, int n_heads,
-                               const __nv_bfloat16* __restrict__ bias, const int* __restrict__ pos,
-                               const float* __restrict__ freqs, __nv_bfloat16* __restrict__ q_out,
-                               __nv_bfloat16* __restrict__ hid, long long ld_hid,
-                               __nv_bfloat16* __restrict__ kv_pool, int n_pages,
-                               const int* __restrict__ block_tables, int max_blocks, int layer) {
-  pdl_launch_dependents();
-  pdl_wait();
-  const int unit = blockIdx.x * 4 + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  const int b = blockIdx.y;
-  const int NF = 3 * D + FF;
-  if (unit * 64 >= NF) return;
-  const int f0 = unit * 64;
-  auto value = [&](int f) {
-    float a = 0.f;
-    for (int s = 0; s < splits; ++s) a += ws[(static_cast<long long>(s) * B + b) * NF + f];
-    return bf16_round(a + __bfloat162float(bias[f]));
-  };
-  if (f0 >= 3 * D) {                                   // fc1 unit
-    const int f = f0 + 2 * lane;
-    const float g0 = gelu_tanh(value(f)), g1 = gelu_tanh(value(f + 1));
-    *reinterpret_cast<uint32_t*>(hid + b * ld_hid + (f - 3 * D)) = pack_bf16x2(g0, g1);
-    return;
-  }
-  const int part = f0 / D;                             // 0 q, 1 k, 2 v
-  const int head = (f0 - part * D) / 64;
-  const int p = pos[b];
-  float o0, o1;
-  if (part < 2 && lane < 16) {
-    const float re = value(f0 + lane), im = value(f0 + 16 + lane);
-    const float c = freqs[(p * 16 + lane) * 2], s = freqs[(p * 16 + lane) * 2 + 1];
-    o0 = __fsub_rn(__fmul_rn(re, c), __fmul_rn(im, s));
-    o1 = __fadd_rn(__fmul_rn(re, s), __fmul_rn(im, c));
-  } else {
-    o0 = value(f0 + 2 * lane);
-    o1 = value(f0 + 2 * lane + 1);
-  }
-  const uint32_t packed = pack_bf16x2(o0, o1);
-  if (part == 0) {
-    *reinterpret_cast<uint32_t*>(q_out + static_cast<long long>(b) * D + head * 64 + 2 * lane) = packed;
-  } else {
-    const int page = block_tables[static_cast<long long>(b) * max_blocks + (p >> 6)];
-    __nv_bfloat16* dst = kv_pool +
-        (((static_cast<long long>(layer) * n_pages + page) * 2 + (part - 1)) * n_heads + head) * (64 * 64) +
-        (p & 63) * 64 + 2 * lane;
-    *reinterpret_cast<uint32_t*>(dst) = packed;
-  }
-}
-
-int decode_qkv_mlp_epilogue(const float* ws, int splits, int B, int D, int FF, int n_heads,
-                            const __nv_bfloat16* bias, const int* pos, const float* freqs,
-                            __nv_bfloat16* q_out, __nv_bfloat16* hid, long long ld_hid,
-                            __nv_bfloat16* kv_pool, int n_pages, const int* block_tables, int max_blocks,
-                            int layer, cudaStream_t stream) {
-  if (D % 64 || FF % 64) return set_error("decode epilogue: dims must be multiples of 64");
-  const int units = (3 * D + FF) / 64;
-  dim3 grid((units + 3) / 4, B);
-  MD_LAUNCH(decode_qkv_mlp_epilogue_kernel, grid, dim3(128), 0, stream, ws, splits, B, D, FF, n_heads, bias, pos,
-            freqs, q_out, hid, ld_hid, kv_pool, n_pages, block_tables, max_blocks, layer);
-  return 0;
-}
-
 __global__ void __launch_bounds__(256)
 decode_residual_ln_epilogue_kernel(const float* __restrict__ ws, int splits, int proj_splits, int B, int D,
                                    const __nv_bfloat16* __restrict__ bias_proj,

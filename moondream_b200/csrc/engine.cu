@@ -162,9 +162,8 @@ int vision_project(Model& m, const bf16* feats, const int* crop_offsets, const i
 // ------------------------------------------------------------------------------------------------
 long long text_prefill_ws_bytes(const Model& m, int T) {
   const md_dims& d = m.d;
-  // ln | qkv | q | attn | tmp | hidden(ff)
-  return pad256(1LL * T * d.txt_dim * 2) * 4 + pad256(1LL * T * 3 * d.txt_dim * 2) +
-         pad256(1LL * T * d.txt_ff * 2) + 4096;
+  // ln | q | attn | tmp | hidden(ff)
+  return pad256(1LL * T * d.txt_dim * 2) * 4 + pad256(1LL * T * d.txt_ff * 2) + 4096;
 }
 
 int text_prefill(Model& m, bf16* x, int T, const int* q_offsets, const int* start_pos, int n_seqs,
@@ -174,7 +173,6 @@ int text_prefill(Model& m, bf16* x, int T, const int* q_offsets, const int* star
   const int D = d.txt_dim, H = d.txt_heads;
   char* p = align_up(reinterpret_cast<char*>(ws));
   bf16* ln = reinterpret_cast<bf16*>(p); p += pad256(1LL * T * D * 2);
-  bf16* qkv = reinterpret_cast<bf16*>(p); p += pad256(1LL * T * 3 * D * 2);
   bf16* q = reinterpret_cast<bf16*>(p); p += pad256(1LL * T * D * 2);
   bf16* att = reinterpret_cast<bf16*>(p); p += pad256(1LL * T * D * 2);
   bf16* tmp = reinterpret_cast<bf16*>(p); p += pad256(1LL * T * D * 2);
@@ -228,7 +226,7 @@ static long long smallbatch_ws_floats(const Model& m, int batch) {
 
 long long text_decode_ws_bytes(const Model& m, int batch) {
   const md_dims& d = m.d;
-  return pad256(1LL * batch * d.txt_dim * 2) * 3 + pad256(1LL * batch * (d.txt_dim + d.txt_ff) * 2) +
+  return pad256(1LL * batch * d.txt_dim * 2) * 2 + pad256(1LL * batch * (d.txt_dim + d.txt_ff) * 2) +
          pad256(smallbatch_ws_floats(m, batch) * 4) + 4096;
 }
 
@@ -249,7 +247,6 @@ int text_decode_step(Model& m, bf16* x, const int* pos, int batch, const md_kv& 
   const int D = d.txt_dim, FF = d.txt_ff, H = d.txt_heads;
   char* p = align_up(reinterpret_cast<char*>(ws));
   bf16* ln = reinterpret_cast<bf16*>(p); p += pad256(1LL * batch * D * 2);
-  bf16* q = reinterpret_cast<bf16*>(p); p += pad256(1LL * batch * D * 2);
   bf16* ln_last = reinterpret_cast<bf16*>(p); p += pad256(1LL * batch * D * 2);
   bf16* xcat = reinterpret_cast<bf16*>(p); p += pad256(1LL * batch * (D + FF) * 2);   // [att | gelu(fc1)]
   float* wsf = reinterpret_cast<float*>(p);
@@ -260,8 +257,8 @@ int text_decode_step(Model& m, bf16* x, const int* pos, int batch, const md_kv& 
   for (int i = 0; i < d.txt_layers; ++i) {
     const TxtBlock& b = m.txt[i];
     // [qkv ; fc1] share the input l = ln(x) (text.py:145-157): one weight stream, then bias / RoPE /
-    // KV-page write / GELU.  (gemm_swapped_decode fuses those into the GEMM epilogue but needs whole-K
-    // tiles, i.e. 112 streaming SMs instead of 148: measured slower, 2.35 vs 2.07 ms per step.)
+    // KV-page write / GELU, which the attention kernel applies for its own (sequence, head).  (Fusing them into
+    // the GEMM epilogue needs whole-K tiles, i.e. 112 streaming SMs instead of 148: measured slower, DESIGN.md.)
     int s1 = plan_swapped(3 * D + FF, D, 0).splits;
     if (!(g_debug_skip & 1)) s1 = gemm_swapped(b.qkv.w, D, ln, D, 3 * D + FF, batch, D, 0, wsf, st);
     if (s1 < 0) return 1;

@@ -46,65 +46,9 @@ struct GemmParams {
   int remap_gin, remap_gout, remap_goff;  // out row = (r / gin) * gout + r % gin + goff when gin > 0
   // swapped form
   float* ws;                           // [k_splits][N][M] fp32
-  DecodeEpilogue dec;                  // EPI_DECODE_QKV_MLP
   RopeEpilogue rope;                   // EPI_QKV_ROPE
 };
 
-
-// Fused epilogue of the decode-step [qkv ; fc1] stream: this thread owns output feature `row` for the
-// 32 batch columns col0..col0+31 (acc).  A warp covers 32 consecutive features, i.e. half a head, so
-// every branch below is warp-uniform and the RoPE partner (dim +/- 16) lives in the same warp.
-__device__ __forceinline__ void decode_qkv_mlp_rows(const GemmParams& p, const uint32_t (&acc)[32], int row,
-                                                    int col0, int lane) {
-  const DecodeEpilogue& e = p.dec;
-  const int NF = 3 * e.D + e.FF;
-  if (row >= NF) return;                                  // warp-uniform (NF is a multiple of 64)
-  const float bias = __bfloat162float(e.bias[row]);
-  if (row >= 3 * e.D) {                                   // fc1 feature: bias, round, GELU
-    const int f = row - 3 * e.D;
-#pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      const int b = col0 + j;
-      if (b < p.N) e.hid[b * e.ld_hid + f] = __float2bfloat16_rn(gelu_tanh(bf16_round(__uint_as_float(acc[j]) + bias)));
-    }
-    return;
-  }
-  const int part = row / e.D;                             // 0 q, 1 k, 2 v
-  const int within = row - part * e.D;
-  const int head = within >> 6, d = within & 63;
-  const bool rotate = part < 2 && d < 32;                 // warp-uniform
-#pragma unroll 4
-  for (int j = 0; j < 32; ++j) {
-    const int b = col0 + j;
-    const bool ok = b < p.N;                              // uniform
-    const float v = bf16_round(__uint_as_float(acc[j]) + bias);
-    const int ps = ok ? e.pos[b] : 0;
-    float o0 = v, o1 = 0.f;
-    int dim = d;
-    bool write2 = false;
-    if (rotate) {
-      const float partner = __shfl_xor_sync(0xffffffffu, v, 16);
-      if (d < 16) {
-        const float c = e.freqs[(ps * 16 + d) * 2], sn = e.freqs[(ps * 16 + d) * 2 + 1];
-        o0 = __fsub_rn(__fmul_rn(v, c), __fmul_rn(partner, sn));        // re' = re cos - im sin
-        o1 = __fadd_rn(__fmul_rn(v, sn), __fmul_rn(partner, c));        // im' = re sin + im cos
-        dim = 2 * d;
-        write2 = true;
-      }
-    }
-    if (!ok || (rotate && d >= 16)) continue;             // upper half of the rotated block only feeds its partner
-    __nv_bfloat16* dst;
-    if (part == 0) {
-      dst = e.q_out + static_cast<long long>(b) * e.D + head * 64 + dim;
-    } else {
-      const int page = e.block_tables[static_cast<long long>(b) * e.max_blocks + (ps >> 6)];
-      dst = e.kv_pool + (((static_cast<long long>(e.layer) * e.n_pages + page) * 2 + (part - 1)) * e.n_heads + head) * (64 * 64) +
-            (ps & 63) * 64 + dim;
-    }
-    if (write2) *reinterpret_cast<uint32_t*>(dst) = pack_bf16x2(o0, o1);
-    else *dst = __float2bfloat16_rn(o0);
-  }
-}
 
 // Fused epilogue of the prefill QKV projection: this thread owns token row `row` and the 32 output columns
 // col0..col0+31 = one half of one head of q, k or v.  dims 0..31 of q and k rotate (pairs (j, j+16) are
@@ -237,7 +181,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       // weight tiles of the first ring of stages are requested before the dependency wait; only the
       // activation (B) loads and everything downstream of them wait for the predecessor.
       int prefetched = 0;
-      if (CG == 1 && p.mode >= EPI_PARTIAL && unit < total_tiles) {
+      if (CG == 1 && p.mode == EPI_PARTIAL && unit < total_tiles) {
         const int split = unit % p.k_splits;
         const int m_blk = (unit / p.k_splits) / p.n_blocks;
         const int kb0 = split * kb_per_split;
@@ -369,10 +313,6 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         load_res(c + 2, rq_next);
         tmem_ld_wait();
         const int col0 = n_blk * BN + c * 32;
-        if (p.mode == EPI_DECODE_QKV_MLP) {
-          decode_qkv_mlp_rows(p, acc, row, col0, lane);
-          continue;
-        }
         if (p.mode == EPI_QKV_ROPE) {
           if (row_ok && col0 < p.N) rope_store_chunk(p, acc, row, col0, rr);
           continue;
@@ -777,28 +717,6 @@ int gemm_rowform_qkv_rope(const __nv_bfloat16* A, long long lda, const __nv_bflo
     g_prof.launches += 1;
   }
   return rc;
-}
-
-int gemm_swapped_decode(const __nv_bfloat16* W, long long ldw, const __nv_bfloat16* X, long long ldx,
-                        int n_out, int batch, int K, const DecodeEpilogue& epi, cudaStream_t stream) {
-  if (n_out <= 0 || batch <= 0 || K <= 0) return set_error("gemm_swapped_decode: empty problem");
-  if (K % 8 || epi.D % 64 || epi.FF % 64 || n_out != 3 * epi.D + epi.FF)
-    return set_error("gemm_swapped_decode: unsupported shape");
-  const int bn = batch <= 32 ? 32 : batch <= 64 ? 64 : batch <= 128 ? 128 : 256;
-  CUtensorMap tA, tB;
-  if (make_tmap_bf16_2d(&tA, W, n_out, K, ldw, BM)) return 1;
-  if (make_tmap_bf16_2d(&tB, X, batch, K, ldx, bn)) return 1;
-  GemmParams p{};
-  p.M = n_out; p.N = batch; p.K = K;
-  p.m_blocks = (n_out + BM - 1) / BM;
-  p.n_blocks = (batch + bn - 1) / bn;
-  p.k_blocks = (K + BK - 1) / BK;
-  p.kb_per_split = p.k_blocks;
-  p.tile_rows = BM;
-  p.k_splits = 1;                                   // the whole K in one CTA: the epilogue sees final sums
-  p.mode = EPI_DECODE_QKV_MLP;
-  p.dec = epi;
-  return dispatch_gemm(bn, 1, tA, tB, p, stream);
 }
 
 int gemm_swapped_kb(const __nv_bfloat16* W, long long ldw, const __nv_bfloat16* X, long long ldx,

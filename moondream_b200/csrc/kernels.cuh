@@ -13,7 +13,6 @@ enum : int {
   EPI_BIAS_GELU = 1,       // out = bf16(gelu_tanh(bf16(acc + bias)))
   EPI_BIAS_RESIDUAL = 2,   // out = bf16(bf16(acc + bias) + residual)
   EPI_PARTIAL = 3,         // swapped form: fp32 partial sums to workspace
-  EPI_DECODE_QKV_MLP = 4,  // swapped form, no split-K: bias + RoPE + KV-page write (qkv rows), bias + GELU (fc1 rows)
   EPI_QKV_ROPE = 5,        // row form, decoder QKV projection: bias + partial RoPE, q -> q_out, k/v -> KV pages
 };
 
@@ -61,9 +60,6 @@ SwappedPlan plan_swapped(int n_out, int K, int kb_divisor);
 int gemm_swapped_splits(int n_out, int K);
 int gemm_swapped(const __nv_bfloat16* W, long long ldw, const __nv_bfloat16* X, long long ldx,
                  int n_out, int batch, int K, int splits, float* ws, cudaStream_t stream);
-// Decode-step [qkv ; fc1] stream with everything downstream fused into the GEMM epilogue (text.py:30-43,
-// moondream.py:74-78, layers.py:130,137): rows < 3D are q|k|v features (bias, bf16 round, partial RoPE,
-// q -> q_out, k/v -> KV pages), rows >= 3D are fc1 features (bias, round, GELU -> hid).
 // Prefill QKV projection with RoPE and the KV-cache write fused into the GEMM epilogue (text.py:30-43,
 // rope.py:20-48, moondream.py:74-78): output column block -> (q|k|v, head, half-head); row -> (sequence, position).
 struct RopeEpilogue {
@@ -79,22 +75,6 @@ struct RopeEpilogue {
 };
 int gemm_rowform_qkv_rope(const __nv_bfloat16* A, long long lda, const __nv_bfloat16* W, long long ldw, int M,
                           int K, const __nv_bfloat16* bias, const RopeEpilogue& epi, cudaStream_t stream);
-
-struct DecodeEpilogue {
-  int D, FF, n_heads;
-  const __nv_bfloat16* bias;      // [3D + FF]
-  const int* pos;                 // [batch]
-  const float* freqs;             // rope table [ctx][16][2]
-  __nv_bfloat16* q_out;           // [batch, D]
-  __nv_bfloat16* hid;             // [batch, *] row pitch ld_hid
-  long long ld_hid;
-  __nv_bfloat16* kv_pool;
-  int n_pages;
-  const int* block_tables;
-  int max_blocks, layer;
-};
-int gemm_swapped_decode(const __nv_bfloat16* W, long long ldw, const __nv_bfloat16* X, long long ldx,
-                        int n_out, int batch, int K, const DecodeEpilogue& epi, cudaStream_t stream);
 // same, with k-blocks per split restricted to divisors of kb_divisor (split boundaries the caller relies on)
 int gemm_swapped_kb(const __nv_bfloat16* W, long long ldw, const __nv_bfloat16* X, long long ldx,
                     int n_out, int batch, int K, int kb_divisor, float* ws, cudaStream_t stream);
@@ -125,11 +105,6 @@ int decode_advance(int* cur_tok, int* pos, int* step, const int* preds, const in
 int gather_rows(const __nv_bfloat16* src, long long ld_src, const int* idx, int n, int dim,
                 __nv_bfloat16* out, long long ldo, cudaStream_t stream);
 int bins_to_values(int which, const int* bins, int n, float* out, cudaStream_t stream);
-int decode_qkv_mlp_epilogue(const float* ws, int splits, int B, int D, int FF, int n_heads,
-                            const __nv_bfloat16* bias, const int* pos, const float* freqs,
-                            __nv_bfloat16* q_out, __nv_bfloat16* hid, long long ld_hid,
-                            __nv_bfloat16* kv_pool, int n_pages, const int* block_tables, int max_blocks,
-                            int layer, cudaStream_t stream);
 int decode_residual_ln_epilogue(const float* ws, int splits, int proj_splits, int B, int D,
                                 const __nv_bfloat16* bias_proj, const __nv_bfloat16* bias_fc2,
                                 __nv_bfloat16* x, const __nv_bfloat16* ln_w, const __nv_bfloat16* ln_b,
