@@ -316,6 +316,13 @@ def run_main(args, cfg, sd, rank, world, local_rank):
                      "share_of_step": (g_ms.value / ms) if ms > 0 else None,
                      "step_model_tflops": total_flops / 1e12 / (ms_max / 1e3)},
     }
+    try:   # the reference's eager torch-CUDA path on the same GPU model (separate run, tools/torch_cuda_comparator.py)
+        comp = json.load(open(os.path.join(ROOT, "profiles", "r01_torch_cuda_comparator.json")))
+        line["comparators"] = {"reference_torch_cuda_eager_images_per_s": comp["images_per_s"],
+                               "source": "profiles/r01_torch_cuda_comparator.json (oracle port of the reference on cuda, "
+                                         "batch-1 sequential, measured in a separate run on this pool's B200)"}
+    except Exception:
+        pass
     if world == 1 and not args.no_cpu_baseline:
         threads = usable_cpus()
         val, detail = cpu_sample(cfg, sd, threads)
