@@ -33,6 +33,7 @@ struct GemmParams {
   int m_blocks, n_blocks, k_blocks;   // m_blocks counts (BM * CG)-row tiles; k_blocks = ceil(K / BK)
   int k_splits;                        // >1 only in swapped form
   int kb_per_split;                    // k-blocks owned by each split (last one may be shorter)
+  int trigger_early;                   // PDL: release dependents at kernel start (weight-streaming form, g_pdl >= 2)
   int tile_rows;                       // rows of A per tile (<= BM; single-CTA tiles only): balances the
                                        // weight stream over the SMs when M / BM is not a multiple of 148
   int mode;                            // EPI_* (row form) or EPI_PARTIAL (swapped form)
@@ -143,6 +144,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int rank = (CG == 2) ? static_cast<int>(cluster_ctarank()) : 0;
   const bool leader = rank == 0;
 
+  if (p.trigger_early) pdl_launch_dependents();
   if (warp == 0 && lane == 0) {
     prefetch_tensormap(&tmA);
     prefetch_tensormap(&tmB);
@@ -670,6 +672,7 @@ static int gemm_swapped_impl(const __nv_bfloat16* W, long long ldw, const __nv_b
   p.kb_per_split = kb_per_split;
   p.k_splits = (p.k_blocks + kb_per_split - 1) / kb_per_split;   // every split owns >= 1 k-block
   p.mode = EPI_PARTIAL;
+  p.trigger_early = g_pdl >= 2 ? 1 : 0;
   p.ws = ws;
   const int rc = dispatch_gemm(bn, 1, tA, tB, p, stream);
   return rc ? -1 : p.k_splits;
