@@ -29,6 +29,9 @@ namespace md {
 // ------------------------------------------------------------------------------------------------
 constexpr int kLnMaxChunks = 16;   // per lane, 8 elements each -> dim <= 4096
 
+// CH = 16-byte chunks per lane this instantiation keeps in registers (dim <= CH * 256): sizing it to the row
+// width instead of the 4096 maximum keeps the register count low enough for full occupancy.
+template <int CH>
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const __nv_bfloat16* __restrict__ x, long long ldx,
                  const __nv_bfloat16* __restrict__ w, const __nv_bfloat16* __restrict__ b,
@@ -40,10 +43,10 @@ layernorm_kernel(const __nv_bfloat16* __restrict__ x, long long ldx,
   if (row >= rows) return;
   const int chunks = dim >> 3;
   const __nv_bfloat16* xr = x + static_cast<long long>(row) * ldx;
-  uint4 v[kLnMaxChunks];
+  uint4 v[CH];
   float sum = 0.f;
 #pragma unroll
-  for (int i = 0; i < kLnMaxChunks; ++i) {
+  for (int i = 0; i < CH; ++i) {
     const int c = lane + i * 32;
     if (c < chunks) {
       v[i] = *reinterpret_cast<const uint4*>(xr + c * 8);
@@ -57,7 +60,7 @@ layernorm_kernel(const __nv_bfloat16* __restrict__ x, long long ldx,
   const float mean = sum / dim;
   float sq = 0.f;
 #pragma unroll
-  for (int i = 0; i < kLnMaxChunks; ++i) {
+  for (int i = 0; i < CH; ++i) {
     const int c = lane + i * 32;
     if (c < chunks) {
       const uint32_t u[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
@@ -74,7 +77,7 @@ layernorm_kernel(const __nv_bfloat16* __restrict__ x, long long ldx,
   const float shift = -rstd * mean;
   __nv_bfloat16* yr = y + static_cast<long long>(row) * ldy;
 #pragma unroll
-  for (int i = 0; i < kLnMaxChunks; ++i) {
+  for (int i = 0; i < CH; ++i) {
     const int c = lane + i * 32;
     if (c < chunks) {
       const uint4 wq = *reinterpret_cast<const uint4*>(w + c * 8);
@@ -98,7 +101,13 @@ int layernorm(const __nv_bfloat16* x, long long ldx, const __nv_bfloat16* w, con
               __nv_bfloat16* y, long long ldy, int rows, int dim, float eps, cudaStream_t stream) {
   if (rows <= 0) return set_error("layernorm: empty input");
   if (dim % 8 || dim > kLnMaxChunks * 32 * 8) return set_error("layernorm: dim must be a multiple of 8 and <= 4096");
-  MD_LAUNCH(layernorm_kernel, dim3((rows + 7) / 8), dim3(256), 0, stream, x, ldx, w, b, y, ldy, rows, dim, eps);
+  const int need = (dim / 8 + 31) / 32;             // chunks per lane
+  const dim3 grid((rows + 7) / 8), block(256);
+  if (need <= 2) MD_LAUNCH(layernorm_kernel<2>, grid, block, 0, stream, x, ldx, w, b, y, ldy, rows, dim, eps);
+  else if (need <= 4) MD_LAUNCH(layernorm_kernel<4>, grid, block, 0, stream, x, ldx, w, b, y, ldy, rows, dim, eps);
+  else if (need <= 5) MD_LAUNCH(layernorm_kernel<5>, grid, block, 0, stream, x, ldx, w, b, y, ldy, rows, dim, eps);
+  else if (need <= 8) MD_LAUNCH(layernorm_kernel<8>, grid, block, 0, stream, x, ldx, w, b, y, ldy, rows, dim, eps);
+  else MD_LAUNCH(layernorm_kernel<16>, grid, block, 0, stream, x, ldx, w, b, y, ldy, rows, dim, eps);
   return 0;
 }
 
