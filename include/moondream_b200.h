@@ -119,6 +119,12 @@ void md_debug_set_pdl(int enable);
 /* Ablation timing only (results are garbage when non-zero): skip kernels of md_text_decode_step;
  * bit0 [qkv;fc1] GEMM, bit1 its epilogue, bit2 attention, bit3 [proj|fc2] GEMM, bit4 residual+LN epilogue. */
 void md_debug_skip_decode_kernels(int mask);
+/* Profiling only: while `records` is non-NULL every CTA of the decode-step kernels (weight-stream GEMMs, decode
+ * attention, residual+LayerNorm epilogue) appends one record of 6 uint64 to records[capacity][6]:
+ * {tag << 32 | block, t_entry, t_after_dependency_wait, t_mid0, t_mid1, t_exit} in %globaltimer ns; tag bits 31..28:
+ * 1 GEMM (bits 27..24 epilogue mode, 23..0 rows), 2 decode attention, 3 residual+LN epilogue.  `count` is a
+ * device uint32 the caller zeroes.  Pass NULL to remove.  (tools/decode_timeline.py) */
+int md_debug_timeline(void* records, void* count, unsigned int capacity);
 
 /* One-query attention for decode (text.py:46-50 with the [1,1,2048] mask of moondream.py:472-474). */
 int md_decode_attention_bf16(const void* q, int n_heads, const int* pos, int n_seqs, const md_kv* kv,

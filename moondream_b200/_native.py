@@ -7,7 +7,7 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import c_char_p, c_int, c_longlong, c_void_p, c_float
+from ctypes import c_char_p, c_int, c_longlong, c_void_p, c_float, c_uint
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libmoondream_b200.so")
@@ -54,6 +54,7 @@ _SIGNATURES = {
     "md_debug_attention_impl": (None, [c_int]),
     "md_debug_set_pdl": (None, [c_int]),
     "md_debug_skip_decode_kernels": (None, [c_int]),
+    "md_debug_timeline": (c_int, [c_void_p, c_void_p, c_uint]),
     "md_decode_attention_bf16": (c_int, [_P, c_int, _P, c_int, _KV, c_int, _P, _P]),
     "md_model_num_weights": (c_int, [_DIMS]),
     "md_model_create": (c_int, [_DIMS, ctypes.POINTER(c_void_p), c_int, _P, _P, ctypes.POINTER(c_void_p)]),

@@ -350,16 +350,22 @@ struct DecodeFuse {
   long long ld_hid;
 };
 
+// 7 CTAs per SM (<= 72 registers): batch 32 x 32 heads = 1024 CTAs must all be resident on 148 SMs, a second
+// partial wave costs ~10 us per layer (measured with tools/decode_timeline.py)
 template <bool FUSED>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 7)
 decode_attention_kernel(const __nv_bfloat16* __restrict__ q, int n_heads, const int* __restrict__ pos,
                         __nv_bfloat16* __restrict__ kv_pool, int n_pages,
                         const int* __restrict__ block_tables, int max_blocks, int layer,
                         __nv_bfloat16* __restrict__ out, long long ld_out, float scale_log2, const DecodeFuse fz) {
   // all CTAs of this grid are resident at once, so the trigger fires immediately: the next kernel (the
   // [proj|fc2] weight stream) may start prefetching weights while this one is streaming K/V
+  const bool tl = tl_on() && threadIdx.x == 0;
+  __shared__ unsigned long long tl_s[4];               // debug timeline stamps (thread 0 only; smem keeps them out of registers)
+  if (tl) tl_s[0] = tl_now();
   pdl_launch_dependents();
   pdl_wait();
+  if (tl) tl_s[1] = tl_now();
   const int head = blockIdx.x, seq = blockIdx.y;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int sub = lane & 7;            // which 16-byte chunk (8 dims) of the 64-dim row
@@ -372,51 +378,90 @@ decode_attention_kernel(const __nv_bfloat16* __restrict__ q, int n_heads, const 
 
   __shared__ float sq[64];
   float qv[8];
+  // The prologue is a chain of dependent L2 round trips during which HBM would sit idle (~5 us measured,
+  // tools/decode_timeline.py), so (a) every independent load is issued before the first use of any of them
+  // and (b) the first 128 keys' K and V rows (one 128-byte line per thread and plane) are requested into L2
+  // up front: the main loop then starts on L2 hits with the stream already running.
+  auto prefetch_head = [&]() {
+    if (tid < kv_len) {
+      const int page = btab[tid >> 6];
+      const __nv_bfloat16* kp = kv_pool +
+          ((static_cast<long long>(layer) * n_pages + page) * 2) * n_heads * (kPageTokens * 64) + head_off + (tid & 63) * 64;
+      prefetch_l2(kp);
+      prefetch_l2(kp + v_off);
+    }
+  };
   if (FUSED) {
     const int NF = 3 * fz.D + fz.FF;
-    auto value = [&](int f) {
-      float a = 0.f;
-      for (int s = 0; s < fz.splits; ++s) a += fz.ws[(static_cast<long long>(s) * fz.B + seq) * NF + f];
-      return bf16_round(a + __bfloat162float(fz.bias[f]));
+    const long long sstride = static_cast<long long>(fz.B) * NF;
+    const float* ws0 = fz.ws + static_cast<long long>(seq) * NF;            // split 0 of this sequence
+    const int per = fz.FF / n_heads;
+    // features this thread finishes: (fa, fb) of q / k / v (warps 0..2) and (fh, fh + 1) of the fc1 slice
+    const bool rot = warp < 2 && lane < 16;                  // dims 0..31 of q and k rotate as pairs (j, j + 16)
+    const int f0 = warp * fz.D + head * 64;
+    const int fa = rot ? f0 + lane : f0 + 2 * lane;
+    const int fb = rot ? f0 + 16 + lane : f0 + 2 * lane + 1;
+    const int fh = 3 * fz.D + head * per + tid * 2;
+    const bool has_h = tid * 2 < per;
+    float ra = 0.f, rb = 0.f, ba = 0.f, bb = 0.f;
+    float2 rh = make_float2(0.f, 0.f);
+    uint32_t bh = 0;
+    if (warp < 3) {
+      ra = ws0[fa]; rb = ws0[fb];
+      ba = __bfloat162float(fz.bias[fa]); bb = __bfloat162float(fz.bias[fb]);
+    }
+    if (has_h) {
+      rh = *reinterpret_cast<const float2*>(ws0 + fh);
+      bh = *reinterpret_cast<const uint32_t*>(fz.bias + fh);
+    }
+    prefetch_head();                                         // first use of the position / block table
+    float cs = 0.f, sn = 0.f;
+    int new_page = 0;
+    if (rot) { cs = fz.freqs[(cur * 16 + lane) * 2]; sn = fz.freqs[(cur * 16 + lane) * 2 + 1]; }
+    if (warp == 1 || warp == 2) new_page = btab[cur >> 6];
+    // same summation order as before: split 0, 1, 2, ... then the bias, rounded to bf16 like the Linear output
+    auto finish = [&](float a, int f, float b) {
+#pragma unroll 1
+      for (int s2 = 1; s2 < fz.splits; ++s2) a += ws0[s2 * sstride + f];
+      return bf16_round(a + b);
     };
-    if (warp < 3) {                                        // warp 0: q, 1: k, 2: v of this head
-      const int f0 = warp * fz.D + head * 64;
-      float o0, o1;
-      if (warp < 2 && lane < 16) {
-        const float re = value(f0 + lane), im = value(f0 + 16 + lane);
-        const float c = fz.freqs[(cur * 16 + lane) * 2], sn = fz.freqs[(cur * 16 + lane) * 2 + 1];
-        o0 = __fsub_rn(__fmul_rn(re, c), __fmul_rn(im, sn));
-        o1 = __fadd_rn(__fmul_rn(re, sn), __fmul_rn(im, c));
-      } else {
-        o0 = value(f0 + 2 * lane);
-        o1 = value(f0 + 2 * lane + 1);
+    if (has_h) {
+      const float g0 = gelu_tanh(finish(rh.x, fh, bf16_lo(bh))), g1 = gelu_tanh(finish(rh.y, fh + 1, bf16_hi(bh)));
+      *reinterpret_cast<uint32_t*>(fz.hid + seq * fz.ld_hid + head * per + tid * 2) = pack_bf16x2(g0, g1);
+    }
+    for (int i2 = tid * 2 + 256; i2 < per; i2 += 256) {      // slices wider than 256 features
+      const int f = 3 * fz.D + head * per + i2;
+      const float g0 = gelu_tanh(finish(ws0[f], f, __bfloat162float(fz.bias[f])));
+      const float g1 = gelu_tanh(finish(ws0[f + 1], f + 1, __bfloat162float(fz.bias[f + 1])));
+      *reinterpret_cast<uint32_t*>(fz.hid + seq * fz.ld_hid + head * per + i2) = pack_bf16x2(g0, g1);
+    }
+    if (warp < 3) {                                          // warp 0: q, 1: k, 2: v of this head
+      const float va = finish(ra, fa, ba), vb = finish(rb, fb, bb);
+      float o0 = va, o1 = vb;
+      if (rot) {
+        o0 = __fsub_rn(__fmul_rn(va, cs), __fmul_rn(vb, sn));
+        o1 = __fadd_rn(__fmul_rn(va, sn), __fmul_rn(vb, cs));
       }
       if (warp == 0) {
         sq[2 * lane] = bf16_round(o0);
         sq[2 * lane + 1] = bf16_round(o1);
       } else {
-        const int page = btab[cur >> 6];
-        __nv_bfloat16* dst = kv_pool + ((static_cast<long long>(layer) * n_pages + page) * 2 + (warp - 1)) * v_off +
+        __nv_bfloat16* dst = kv_pool + ((static_cast<long long>(layer) * n_pages + new_page) * 2 + (warp - 1)) * v_off +
                              head_off + (cur & 63) * 64 + 2 * lane;
         *reinterpret_cast<uint32_t*>(dst) = pack_bf16x2(o0, o1);
       }
-    }
-    // this CTA's slice of the fc1 features
-    const int per = fz.FF / n_heads;
-    for (int i = tid * 2; i < per; i += 256) {
-      const int f = 3 * fz.D + head * per + i;
-      const float g0 = gelu_tanh(value(f)), g1 = gelu_tanh(value(f + 1));
-      *reinterpret_cast<uint32_t*>(fz.hid + seq * fz.ld_hid + head * per + i) = pack_bf16x2(g0, g1);
     }
     __syncthreads();                                       // q in smem, new K/V row visible to the block
 #pragma unroll
     for (int j = 0; j < 8; ++j) qv[j] = sq[sub * 8 + j];
   } else {
+    prefetch_head();
     const uint4 qq = *reinterpret_cast<const uint4*>(q + (static_cast<long long>(seq) * n_heads + head) * 64 + sub * 8);
     const uint32_t w[4] = {qq.x, qq.y, qq.z, qq.w};
 #pragma unroll
     for (int j = 0; j < 4; ++j) { qv[2 * j] = bf16_lo(w[j]); qv[2 * j + 1] = bf16_hi(w[j]); }
   }
+  if (tl) tl_s[2] = tl_now();
   float m = -INFINITY, l = 0.f;
   float acc[8];
 #pragma unroll
@@ -463,6 +508,7 @@ decode_attention_kernel(const __nv_bfloat16* __restrict__ q, int n_heads, const 
     }
   }
 
+  if (tl) tl_s[3] = tl_now();
   // merge the 16 partial states (4 row groups x 4 warps) that share each dim chunk
   __shared__ float sm_m[16][8], sm_l[16][8], sm_acc[16][8][8];
   const int slot = warp * 4 + rowi;
@@ -485,7 +531,10 @@ decode_attention_kernel(const __nv_bfloat16* __restrict__ q, int n_heads, const 
     }
     out[static_cast<long long>(seq) * ld_out + head * 64 + c * 8 + j] = __float2bfloat16_rn(A / L);
   }
+  if (tl) tl_emit((2u << 28) | (FUSED ? 1u : 0u), tl_s[0], tl_s[1], tl_s[2], tl_s[3], tl_now());
 }
+
+void timeline_install_attention(const Timeline& t) { timeline_install(t); }
 
 int decode_attention(const __nv_bfloat16* q, int n_heads, const int* pos, int n_seqs,
                      const __nv_bfloat16* kv_pool, int n_pages, const int* block_tables,

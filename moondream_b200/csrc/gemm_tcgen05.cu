@@ -144,6 +144,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int rank = (CG == 2) ? static_cast<int>(cluster_ctarank()) : 0;
   const bool leader = rank == 0;
 
+  __shared__ unsigned long long tl_s[5];    // debug timeline stamps (see ptx.cuh), untouched unless installed
+  const bool tl = tl_on();
+  if (tl && threadIdx.x == 0) tl_s[0] = tl_now();
   if (p.trigger_early) pdl_launch_dependents();
   if (warp == 0 && lane == 0) {
     prefetch_tensormap(&tmA);
@@ -195,6 +198,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
       }
       pdl_wait();
+      if (tl) tl_s[1] = tl_now();
       for (int tile = unit; tile < total_tiles; tile += n_units) {
         const int split = tile % p.k_splits;
         const int t2 = tile / p.k_splits;
@@ -248,6 +252,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
+          if (tl && it == 0 && kb == kb0) tl_s[2] = tl_now();          // first operands landed
           const uint32_t sa = smem_u32(smem + stage * S::kStageBytes);
           const uint32_t sb = sa + S::kABytes;
           const uint64_t da = make_desc_k_sw128(sa);
@@ -305,6 +310,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
       mbar_wait(&tmem_full[as], aphase);
       tc_fence_after();
+      if (tl && threadIdx.x == 128) tl_s[3] = tl_now();                  // (last) accumulator complete
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
                              static_cast<uint32_t>(as * BN);
 
@@ -373,6 +379,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   tc_fence_before();
   if (CG == 2) cluster_sync_all(); else __syncthreads();
+  if (tl && threadIdx.x == 0 && blockIdx.x < total_tiles * CG)
+    tl_emit((1u << 28) | (static_cast<uint32_t>(p.mode) << 24) | (static_cast<uint32_t>(p.M) & 0xFFFFFFu),
+            tl_s[0], tl_s[1], tl_s[2], tl_s[3], tl_now());
   if (warp == 2) {
     tc_fence_after();
     if (CG == 2) tmem_dealloc_pair(tmem_base, kTmemCols); else tmem_dealloc(tmem_base, kTmemCols);
@@ -557,6 +566,14 @@ static int launch_gemm(const CUtensorMap& tA, const CUtensorMap& tB, const GemmP
 
 static int g_force_cg = 0;   // 0 = auto, 1 / 2 = force (tests and A/B timing)
 void gemm_force_cta_group(int cg) { g_force_cg = cg; }
+// Installs (buf != nullptr) or removes the debug timeline buffer in every kernel translation unit.
+int timeline_install_all(unsigned long long* buf, unsigned int* count, unsigned int cap) {
+  Timeline t{buf, count, buf ? cap : 0u};
+  if (timeline_install(t) != cudaSuccess) return set_error("timeline: cudaMemcpyToSymbol failed");
+  timeline_install_attention(t);
+  timeline_install_elementwise(t);
+  return 0;
+}
 
 // bn: B-tile rows; cg: CTAs per tile
 static int dispatch_gemm(int bn, int cg, const CUtensorMap& tA, const CUtensorMap& tB, const GemmParams& p,

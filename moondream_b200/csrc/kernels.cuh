@@ -43,6 +43,12 @@ inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, siz
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
+// debug timeline (ptx.cuh): each kernel translation unit holds its own __constant__ copy
+struct Timeline;
+int timeline_install_all(unsigned long long* buf, unsigned int* count, unsigned int cap);
+void timeline_install_attention(const Timeline& t);
+void timeline_install_elementwise(const Timeline& t);
+
 // ---- gemm_tcgen05.cu ----
 int make_tmap_bf16_2d(CUtensorMap* tm, const void* base, long long rows, long long cols,
                       long long ld, int box_rows);

@@ -72,6 +72,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 // ----------------------------------------------------------------------------------------------
 // TMA
 // ----------------------------------------------------------------------------------------------
+// hint: bring the 128-byte line holding `p` into L2 (no register result, no fault on the data path)
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
 __device__ __forceinline__ void prefetch_tensormap(const CUtensorMap* tm) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tm)) : "memory");
 }
@@ -384,6 +388,32 @@ __device__ __forceinline__ float gelu_tanh(float x) {
   float e;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(t));                   // ~2 ulp
   return __fdividef(x, 1.0f + e);
+}
+
+// ---- debug timeline (md_debug_timeline) ----
+// Per-CTA %globaltimer stamps, written only while a buffer is installed (tools/decode_timeline.py): the
+// ground truth for where a decode step's time goes once PDL overlaps adjacent kernels and CUDA events
+// or ncu (which serialises launches) can no longer tell.  One __constant__ copy per translation unit.
+struct Timeline { unsigned long long* buf; unsigned int* count; unsigned int cap; };
+constexpr int kTimelineWords = 6;   // {tag << 32 | block, entry, after dependency wait, mid0, mid1, exit}
+static __constant__ Timeline c_timeline;
+__device__ __forceinline__ bool tl_on() { return c_timeline.buf != nullptr; }
+__device__ __forceinline__ unsigned long long tl_now() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void tl_emit(uint32_t tag, unsigned long long t0, unsigned long long t1,
+                                        unsigned long long t2, unsigned long long t3, unsigned long long t4) {
+  const unsigned int i = atomicAdd(c_timeline.count, 1u);
+  if (i >= c_timeline.cap) return;
+  unsigned long long* r = c_timeline.buf + static_cast<size_t>(i) * kTimelineWords;
+  const uint32_t blk = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+  r[0] = (static_cast<unsigned long long>(tag) << 32) | blk;
+  r[1] = t0; r[2] = t1; r[3] = t2; r[4] = t3; r[5] = t4;
+}
+static inline cudaError_t timeline_install(const Timeline& t) {
+  return cudaMemcpyToSymbol(c_timeline, &t, sizeof(t));
 }
 
 }  // namespace md
