@@ -550,7 +550,7 @@ decode_residual_ln_epilogue_kernel(const float* __restrict__ ws, int splits, int
   if (tl) tl0 = tl_now();
   pdl_launch_dependents();
   constexpr int kMaxChunks = 2;                        // 8-element chunks per thread: D <= 4096
-  constexpr int kBatch = 8;                            // splits fetched per round of independent loads
+  constexpr int kBatch = 10;                           // splits fetched per round of independent loads
   const int b = blockIdx.x;
   const int tid = threadIdx.x;
   const int chunks = D >> 3;

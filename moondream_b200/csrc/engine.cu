@@ -215,7 +215,8 @@ static long long smallbatch_ws_floats(const Model& m, int batch) {
   };
   upd(3 * d.txt_dim + d.txt_ff, d.txt_dim);
   {
-    const long long f = 1LL * plan_swapped(d.txt_dim, d.txt_dim + d.txt_ff, d.txt_dim / 64).splits * batch * d.txt_dim;
+    const SwappedPlan2 pl = plan_swapped_2seg(d.txt_dim, d.txt_dim + d.txt_ff, d.txt_dim);
+    const long long f = 1LL * (pl.splits_a + pl.splits_b) * batch * d.txt_dim;
     if (f > need) need = f;
   }
   upd(d.vocab, d.txt_dim);
@@ -251,8 +252,8 @@ int text_decode_step(Model& m, bf16* x, const int* pos, int batch, const md_kv& 
   bf16* xcat = reinterpret_cast<bf16*>(p); p += pad256(1LL * batch * (D + FF) * 2);   // [att | gelu(fc1)]
   float* wsf = reinterpret_cast<float*>(p);
   bf16* pool = reinterpret_cast<bf16*>(kv.pool);
-  const int kb = plan_swapped(D, D + FF, D / 64).kb;    // a divisor of D/64: no split straddles proj | fc2
-  const int proj_splits = (D / 64) / kb;
+  const SwappedPlan2 pl2 = plan_swapped_2seg(D, D + FF, D);   // no split straddles proj | fc2
+  const int proj_splits = pl2.splits_a;
   if (layernorm(x, D, m.txt[0].ln.w, m.txt[0].ln.b, ln, D, batch, D, 1e-5f, st)) return 1;
   for (int i = 0; i < d.txt_layers; ++i) {
     const TxtBlock& b = m.txt[i];
@@ -267,8 +268,8 @@ int text_decode_step(Model& m, bf16* x, const int* pos, int batch, const md_kv& 
         decode_attention_fused(wsf, s1, D, FF, b.qkv.b, m.rope, xcat + D, D + FF, H, pos, batch, pool, kv.n_pages,
                                kv.block_tables, kv.max_blocks, i, xcat, D + FF, st)) return 1;
     // proj(att) and fc2(hid) both land in the residual: one K-concatenated weight stream
-    int s2 = plan_swapped(D, D + FF, D / 64).splits;
-    if (!(g_debug_skip & 8)) s2 = gemm_swapped_kb(b.proj.w, D + FF, xcat, D + FF, D, batch, D + FF, D / 64, wsf, st);
+    int s2 = pl2.splits_a + pl2.splits_b;
+    if (!(g_debug_skip & 8)) s2 = gemm_swapped_2seg(b.proj.w, D + FF, xcat, D + FF, D, batch, D + FF, D, wsf, st);
     if (s2 < 0) return 1;
     const bool last = i + 1 == d.txt_layers;
     const Lin& nln = last ? m.txt_post_ln : m.txt[i + 1].ln;

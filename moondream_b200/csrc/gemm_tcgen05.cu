@@ -28,11 +28,20 @@ constexpr int BK = 64;
 constexpr int kEpiWarps = 8;                        // two warps per TMEM lane quadrant
 constexpr int kGemmThreads = 128 + kEpiWarps * 32;  // producer, MMA, TMEM-alloc, spare + epilogue
 
+static int g_gemm_debug = 0;            // md_debug_gemm: timing experiments only
+
 struct GemmParams {
   int M, N, K;
   int m_blocks, n_blocks, k_blocks;   // m_blocks counts (BM * CG)-row tiles; k_blocks = ceil(K / BK)
   int k_splits;                        // >1 only in swapped form
   int kb_per_split;                    // k-blocks owned by each split (last one may be shorter)
+  // optional second K segment (the K-concatenated [proj | fc2] stream, whose two halves are rounded to bf16
+  // separately and so may not share a split): splits [0, seg_splits) tile k-blocks [0, seg_kb) with
+  // kb_per_split each, the remaining splits tile [seg_kb, k_blocks) with kb_per_split2 each.
+  // Single segment: seg_splits = k_splits, seg_kb = k_blocks.
+  int seg_splits, seg_kb, kb_per_split2;
+  int debug;                           // timing experiments only (md_debug_gemm): bit0 skip the activation loads of the
+                                       // swapped form, bit1 re-read the first weight k-block (L2 instead of HBM)
   int trigger_early;                   // PDL: release dependents at kernel start (weight-streaming form, g_pdl >= 2)
   int tile_rows;                       // rows of A per tile (<= BM; single-CTA tiles only): balances the
                                        // weight stream over the SMs when M / BM is not a multiple of 148
@@ -49,6 +58,17 @@ struct GemmParams {
   float* ws;                           // [k_splits][N][M] fp32
   RopeEpilogue rope;                   // EPI_QKV_ROPE
 };
+
+// k-block range [kb0, kb1) of one split
+__device__ __forceinline__ void split_range(const GemmParams& p, int split, int& kb0, int& kb1) {
+  if (split < p.seg_splits) {
+    kb0 = split * p.kb_per_split;
+    kb1 = min(p.seg_kb, kb0 + p.kb_per_split);
+  } else {
+    kb0 = p.seg_kb + (split - p.seg_splits) * p.kb_per_split2;
+    kb1 = min(p.k_blocks, kb0 + p.kb_per_split2);
+  }
+}
 
 
 // Fused epilogue of the prefill QKV projection: this thread owns token row `row` and the 32 output columns
@@ -145,7 +165,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const bool leader = rank == 0;
 
   __shared__ unsigned long long tl_s[5];    // debug timeline stamps (see ptx.cuh), untouched unless installed
+  __shared__ unsigned long long tl_kb[2][40];   // per-k-block stamps of a few CTAs: [0] loads issued, [1] operands landed
   const bool tl = tl_on();
+  const bool tl_detail = tl && (p.debug & 8) && p.mode == EPI_PARTIAL && (blockIdx.x == 0 || blockIdx.x == 73 || blockIdx.x == gridDim.x - 1);
   if (tl && threadIdx.x == 0) tl_s[0] = tl_now();
   if (p.trigger_early) pdl_launch_dependents();
   if (warp == 0 && lane == 0) {
@@ -173,7 +195,6 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const uint32_t tmem_base = *tmem_ptr_smem;
 
   const int total_tiles = p.m_blocks * p.n_blocks * p.k_splits;
-  const int kb_per_split = p.kb_per_split;
   const int unit = blockIdx.x / CG, n_units = gridDim.x / CG;
 
   if (warp == 0) {
@@ -189,12 +210,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       if (CG == 1 && p.mode == EPI_PARTIAL && unit < total_tiles) {
         const int split = unit % p.k_splits;
         const int m_blk = (unit / p.k_splits) / p.n_blocks;
-        const int kb0 = split * kb_per_split;
-        const int kb1 = min(p.k_blocks, kb0 + kb_per_split);
+        int kb0, kb1;
+        split_range(p, split, kb0, kb1);
         prefetched = min(STAGES, kb1 - kb0);
         for (int i = 0; i < prefetched; ++i) {
-          mbar_arrive_expect_tx(&full_bar[i], p.tile_rows * (BK * 2) + S::kBBytes);
-          tma_load_2d(smem + i * S::kStageBytes, &tmA, &full_bar[i], (kb0 + i) * BK, m_blk * p.tile_rows);
+          mbar_arrive_expect_tx(&full_bar[i], p.tile_rows * (BK * 2) + ((p.debug & 1) ? 0 : S::kBBytes));
+          tma_load_2d(smem + i * S::kStageBytes, &tmA, &full_bar[i], (kb0 + ((p.debug & 2) ? 0 : i)) * BK, m_blk * p.tile_rows);
         }
       }
       pdl_wait();
@@ -204,8 +225,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int t2 = tile / p.k_splits;
         const int n_blk = t2 % p.n_blocks;
         const int m_blk = t2 / p.n_blocks;
-        const int kb0 = split * kb_per_split;
-        const int kb1 = min(p.k_blocks, kb0 + kb_per_split);
+        int kb0, kb1;
+        split_range(p, split, kb0, kb1);
         const int a_row = (CG == 2) ? m_blk * (BM * CG) + rank * BM : m_blk * p.tile_rows;
         const int b_row = n_blk * BN + rank * (BN / CG);
         for (int kb = kb0; kb < kb1; ++kb) {
@@ -214,7 +235,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           if (prefetched > 0) {
             // stage already armed and its weight tile in flight: add the activation tile
             --prefetched;
-            tma_load_2d(sb, &tmB, &full_bar[stage], kb * BK, b_row);
+            if (!(p.debug & 1)) tma_load_2d(sb, &tmB, &full_bar[stage], kb * BK, b_row);
           } else {
             mbar_wait(&empty_bar[stage], phase ^ 1);
             if (CG == 2) {
@@ -223,11 +244,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               tma_load_2d_pair(sa, &tmA, &full_bar[stage], kb * BK, a_row);
               tma_load_2d_pair(sb, &tmB, &full_bar[stage], kb * BK, b_row);
             } else {
-              mbar_arrive_expect_tx(&full_bar[stage], p.tile_rows * (BK * 2) + S::kBBytes);
-              tma_load_2d(sa, &tmA, &full_bar[stage], kb * BK, a_row);
-              tma_load_2d(sb, &tmB, &full_bar[stage], kb * BK, b_row);
+              const bool skip_b = p.mode == EPI_PARTIAL && (p.debug & 1);
+              mbar_arrive_expect_tx(&full_bar[stage], p.tile_rows * (BK * 2) + (skip_b ? 0 : S::kBBytes));
+              tma_load_2d(sa, &tmA, &full_bar[stage], ((p.mode == EPI_PARTIAL && (p.debug & 2)) ? kb0 : kb) * BK, a_row);
+              if (!skip_b) tma_load_2d(sb, &tmB, &full_bar[stage], kb * BK, b_row);
             }
           }
+          if (tl_detail && tile == unit && kb - kb0 < 40) tl_kb[0][kb - kb0] = tl_now();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -242,8 +265,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       int it = 0;
       for (int tile = unit; tile < total_tiles; tile += n_units, ++it) {
         const int split = tile % p.k_splits;
-        const int kb0 = split * kb_per_split;
-        const int kb1 = min(p.k_blocks, kb0 + kb_per_split);
+        int kb0, kb1;
+        split_range(p, split, kb0, kb1);
         const int as = it & 1;
         const uint32_t aphase = (it >> 1) & 1;
         mbar_wait(&tmem_empty[as], aphase ^ 1);
@@ -253,6 +276,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           if (tl && it == 0 && kb == kb0) tl_s[2] = tl_now();          // first operands landed
+          if (tl_detail && it == 0 && kb - kb0 < 40) tl_kb[1][kb - kb0] = tl_now();
           const uint32_t sa = smem_u32(smem + stage * S::kStageBytes);
           const uint32_t sb = sa + S::kABytes;
           const uint64_t da = make_desc_k_sw128(sa);
@@ -382,9 +406,186 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (tl && threadIdx.x == 0 && blockIdx.x < total_tiles * CG)
     tl_emit((1u << 28) | (static_cast<uint32_t>(p.mode) << 24) | (static_cast<uint32_t>(p.M) & 0xFFFFFFu),
             tl_s[0], tl_s[1], tl_s[2], tl_s[3], tl_now());
+  if (tl_detail && threadIdx.x == 0) {
+    const int n = min(40, min(p.k_blocks, p.kb_per_split));
+    for (int j = 0; j < n; ++j)
+      tl_emit((4u << 28) | (static_cast<uint32_t>(j) << 16) | (static_cast<uint32_t>(p.M) & 0xFFFFu), tl_kb[0][j], tl_kb[1][j],
+              tl_s[1], tl_s[3], 0ull);
+  }
   if (warp == 2) {
     tc_fence_after();
     if (CG == 2) tmem_dealloc_pair(tmem_base, kTmemCols); else tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// Small-batch weight stream (decode-time Linear layers, batch <= 128 rows of activations).
+//
+// ws[split][b][n] = sum_{k in split} X[b][k] * W[n][k]  (fp32 partials, finished by the consumer kernel).
+//
+// The activations are the MMA's A operand (M = 128 lanes, only `batch` of them meaningful) and the weight tile
+// is the B operand (N = tile_n rounded up to 16, up to 256 rows).  The other orientation (weights as A, the
+// `swapped` form this kernel replaces) leaves the tensor core operand-bound: every K = 16 step re-reads a full
+// 128-row A tile from shared memory at ~32 B/clk, i.e. ~600 clocks per 64-wide k-block whatever the batch,
+// which caps an SM at ~43 GB/s of weights at the power-capped 1.57 GHz clock -- below its share of HBM
+// (measured per k-block with tools/decode_timeline.py).  As the B operand the same bytes cost 2 * N clocks.
+//
+// One CTA per (weight-row tile, K split), all resident at once (the plan keeps tiles * splits <= #SMs where
+// it can).  Under programmatic dependent launch the weight tiles of the first ring of stages are requested
+// before the dependency wait (no earlier kernel writes weights); only the activation loads, and everything
+// downstream of them, wait for the predecessor.
+// ------------------------------------------------------------------------------------------------
+constexpr int kSbMaxStages = 12;
+constexpr int kSbThreads = 256;          // warp 0 TMA producer, 1 MMA issuer, 2 TMEM allocator, 4..7 epilogue
+constexpr int kSbTailPad = BM * BK * 2;  // the A descriptor spans 128 rows whatever the batch: keep it in bounds
+
+struct SmallBatchParams {
+  int batch, n_out, k_blocks;
+  int tile_n, n_mma, k_splits;
+  int kb_per_split, seg_splits, seg_kb, kb_per_split2;   // split -> k-block range, as in GemmParams
+  int stages, a_bytes, stage_bytes;    // a_bytes: activation tile (box rows * 128 B), then the weight tile
+  int tmem_cols;
+  int trigger_early;
+  float* ws;
+};
+
+__global__ void __launch_bounds__(kSbThreads, 1)
+smallbatch_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
+                       const SmallBatchParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + p.stages * p.stage_bytes + kSbTailPad);
+  uint64_t* empty_bar = full_bar + kSbMaxStages;
+  uint64_t* tmem_full = empty_bar + kSbMaxStages;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_full + 1);
+  __shared__ unsigned long long tl_s[5];    // debug timeline stamps (see ptx.cuh), untouched unless installed
+  const bool tl = tl_on();
+  if (tl && threadIdx.x == 0) tl_s[0] = tl_now();
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  if (p.trigger_early) pdl_launch_dependents();
+  if (warp == 0 && lane == 0) {
+    prefetch_tensormap(&tmX);
+    prefetch_tensormap(&tmW);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < p.stages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    mbar_init(tmem_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_ptr_smem, static_cast<uint32_t>(p.tmem_cols));
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  const int split = blockIdx.x % p.k_splits;
+  const int tile = blockIdx.x / p.k_splits;
+  int kb0, kb1;
+  if (split < p.seg_splits) {
+    kb0 = split * p.kb_per_split;
+    kb1 = min(p.seg_kb, kb0 + p.kb_per_split);
+  } else {
+    kb0 = p.seg_kb + (split - p.seg_splits) * p.kb_per_split2;
+    kb1 = min(p.k_blocks, kb0 + p.kb_per_split2);
+  }
+  const int nk = kb1 - kb0;
+  const int n0 = tile * p.tile_n;
+  const uint32_t tx_bytes = static_cast<uint32_t>(p.a_bytes + p.tile_n * (BK * 2));
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const int pre = min(p.stages, nk);
+      for (int i = 0; i < pre; ++i) {
+        mbar_arrive_expect_tx(&full_bar[i], tx_bytes);
+        tma_load_2d(smem + i * p.stage_bytes + p.a_bytes, &tmW, &full_bar[i], (kb0 + i) * BK, n0);
+      }
+      pdl_wait();
+      if (tl) tl_s[1] = tl_now();
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int j = 0; j < nk; ++j) {
+        uint8_t* sx = smem + stage * p.stage_bytes;
+        if (j >= pre) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
+          tma_load_2d(sx + p.a_bytes, &tmW, &full_bar[stage], (kb0 + j) * BK, n0);
+        }
+        tma_load_2d(sx, &tmX, &full_bar[stage], (kb0 + j) * BK, 0);
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16_f32(BM, p.n_mma);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int j = 0; j < nk; ++j) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        if (tl && j == 0) tl_s[2] = tl_now();                 // first operands landed
+        const uint32_t sx = smem_u32(smem + stage * p.stage_bytes);
+        const uint64_t da = make_desc_k_sw128(sx);
+        const uint64_t db = make_desc_k_sw128(sx + static_cast<uint32_t>(p.a_bytes));
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k)
+          umma_bf16(tmem_base, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k), idesc,
+                    (j > 0 || k > 0) ? 1u : 0u);
+        umma_commit(&empty_bar[stage]);
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+      }
+      umma_commit(tmem_full);
+    }
+  } else if (warp >= 4) {
+    // lanes of TMEM = rows of the activation tile: warp q owns batch rows 32q .. 32q+31
+    const int q = warp - 4;
+    pdl_wait();                              // ws is still being read by the predecessor's consumers
+    if (q * 32 < p.batch) {
+      const int b = q * 32 + lane;
+      mbar_wait(tmem_full, 0);
+      tc_fence_after();
+      if (tl && threadIdx.x == 128) tl_s[3] = tl_now();       // accumulator complete
+      float* dst = p.ws + (static_cast<long long>(split) * p.batch + b) * p.n_out + n0;
+      const bool vec = ((n0 | p.n_out) & 3) == 0;
+      const int n_valid = min(p.tile_n, p.n_out - n0);
+      for (int c = 0; c * 32 < n_valid; ++c) {
+        uint32_t acc[32];
+        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(c * 32), acc);
+        tmem_ld_wait();
+        if (b < p.batch) {
+          if (vec && c * 32 + 32 <= n_valid) {
+#pragma unroll
+            for (int g = 0; g < 8; ++g)
+              *reinterpret_cast<float4*>(dst + c * 32 + g * 4) =
+                  make_float4(__uint_as_float(acc[4 * g]), __uint_as_float(acc[4 * g + 1]),
+                              __uint_as_float(acc[4 * g + 2]), __uint_as_float(acc[4 * g + 3]));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (c * 32 + j < n_valid) dst[c * 32 + j] = __uint_as_float(acc[j]);
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (tl && threadIdx.x == 0)
+    tl_emit((1u << 28) | (static_cast<uint32_t>(EPI_PARTIAL) << 24) | (static_cast<uint32_t>(p.n_out) & 0xFFFFFFu),
+            tl_s[0], tl_s[1], tl_s[2], tl_s[3], tl_now());
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, static_cast<uint32_t>(p.tmem_cols));
   }
 }
 
@@ -564,6 +765,7 @@ static int launch_gemm(const CUtensorMap& tA, const CUtensorMap& tB, const GemmP
   return 0;
 }
 
+void gemm_debug_flags(int flags) { g_gemm_debug = flags; }
 static int g_force_cg = 0;   // 0 = auto, 1 / 2 = force (tests and A/B timing)
 void gemm_force_cta_group(int cg) { g_force_cg = cg; }
 // Installs (buf != nullptr) or removes the debug timeline buffer in every kernel translation unit.
@@ -621,6 +823,7 @@ int gemm_rowform(const __nv_bfloat16* A, long long lda, const __nv_bfloat16* W, 
   p.k_blocks = (K + BK - 1) / BK;
   p.k_splits = 1;
   p.kb_per_split = p.k_blocks;
+  p.seg_splits = 1; p.seg_kb = p.k_blocks; p.kb_per_split2 = p.k_blocks;
   p.tile_rows = BM;
   p.mode = mode;
   p.out = out; p.ldo = ldo; p.bias = bias; p.res = res; p.ldr = ldr; p.res_mod = res_mod;
@@ -668,12 +871,71 @@ SwappedPlan plan_swapped(int n_out, int K, int kb_divisor) {
 
 // ws[splits][batch][n_out] (fp32) = W[n_out,K] * X[batch,K]^T  partial sums; split s owns k-blocks
 // [s * kb_per_split, (s+1) * kb_per_split).  Returns the number of splits (>0), -1 on error.
+
+static int launch_smallbatch(const __nv_bfloat16* W, long long ldw, const __nv_bfloat16* X, long long ldx,
+                             int n_out, int batch, int K, int kb_per_split, int tile_n, float* ws,
+                             cudaStream_t stream, int seg_kb, int kb_per_split2) {
+  if (batch > BM) { set_error("small-batch GEMM: batch must be <= 128"); return -1; }
+  if (tile_n < 1) tile_n = BM;
+  if (tile_n > 256) tile_n = 256;
+  SmallBatchParams p{};
+  p.batch = batch; p.n_out = n_out;
+  p.k_blocks = (K + BK - 1) / BK;
+  p.tile_n = tile_n;
+  p.n_mma = (tile_n + 15) / 16 * 16;
+  const int n_tiles = (n_out + tile_n - 1) / tile_n;
+  if (kb_per_split < 1) kb_per_split = 1;
+  if (kb_per_split > p.k_blocks) kb_per_split = p.k_blocks;
+  p.kb_per_split = kb_per_split;
+  if (seg_kb > 0 && seg_kb < p.k_blocks) {
+    if (kb_per_split2 < 1) kb_per_split2 = 1;
+    p.seg_kb = seg_kb;
+    p.seg_splits = (seg_kb + kb_per_split - 1) / kb_per_split;
+    p.kb_per_split2 = kb_per_split2;
+    p.k_splits = p.seg_splits + (p.k_blocks - seg_kb + kb_per_split2 - 1) / kb_per_split2;
+  } else {
+    p.k_splits = (p.k_blocks + kb_per_split - 1) / kb_per_split;   // every split owns >= 1 k-block
+    p.seg_splits = p.k_splits; p.seg_kb = p.k_blocks; p.kb_per_split2 = kb_per_split;
+  }
+  const int a_rows = (batch + 7) / 8 * 8;
+  p.a_bytes = a_rows * BK * 2;                       // a multiple of 1024: the weight tile stays swizzle-aligned
+  p.stage_bytes = p.a_bytes + p.n_mma * BK * 2;
+  const int bar_bytes = (2 * kSbMaxStages + 1) * 8 + 16;
+  constexpr int kSbSmemMax = 227 * 1024 - 1024;      // leave room for the kernel's few static __shared__ words
+  const int budget = kSbSmemMax - 1024 - kSbTailPad - bar_bytes;
+  p.stages = budget / p.stage_bytes;
+  if (p.stages > kSbMaxStages) p.stages = kSbMaxStages;
+  if (p.stages < 2) { set_error("small-batch GEMM: tile does not fit shared memory"); return -1; }
+  p.tmem_cols = p.n_mma <= 32 ? 32 : p.n_mma <= 64 ? 64 : p.n_mma <= 128 ? 128 : 256;
+  p.trigger_early = g_pdl >= 2 ? 1 : 0;
+  p.ws = ws;
+  CUtensorMap tX, tW;
+  if (make_tmap_bf16_2d(&tX, X, batch, K, ldx, a_rows)) return -1;
+  if (make_tmap_bf16_2d(&tW, W, n_out, K, ldw, tile_n)) return -1;
+  const int smem_bytes = p.stages * p.stage_bytes + kSbTailPad + bar_bytes + 1024;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(smallbatch_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSbSmemMax);
+    if (e != cudaSuccess) { set_error(cudaGetErrorString(e)); return -1; }
+    configured = true;
+  }
+  count_launch();
+  cudaError_t e = launch_k(smallbatch_gemm_kernel, dim3(n_tiles * p.k_splits), dim3(kSbThreads),
+                           static_cast<size_t>(smem_bytes), stream, tX, tW, p);
+  if (e != cudaSuccess) { set_error(cudaGetErrorString(e)); return -1; }
+  return p.k_splits;
+}
+
+// With seg_kb > 0 the k-blocks split in two segments (see GemmParams): [0, seg_kb) in pieces of kb_per_split,
+// the rest in pieces of kb_per_split2.
 static int gemm_swapped_impl(const __nv_bfloat16* W, long long ldw, const __nv_bfloat16* X, long long ldx,
                              int n_out, int batch, int K, int kb_per_split, int tile_rows, float* ws,
-                             cudaStream_t stream) {
+                             cudaStream_t stream, int seg_kb = 0, int kb_per_split2 = 0) {
   if (n_out <= 0 || batch <= 0 || K <= 0) { set_error("gemm_swapped: empty problem"); return -1; }
   if (K % 8) { set_error("gemm_swapped: K must be a multiple of 8"); return -1; }
   if (tile_rows < 1 || tile_rows > BM) tile_rows = BM;
+  if (batch <= BM && !(g_gemm_debug & 16))
+    return launch_smallbatch(W, ldw, X, ldx, n_out, batch, K, kb_per_split, tile_rows, ws, stream, seg_kb, kb_per_split2);
   const int bn = batch <= 32 ? 32 : batch <= 64 ? 64 : batch <= 128 ? 128 : 256;
   CUtensorMap tA, tB;
   if (make_tmap_bf16_2d(&tA, W, n_out, K, ldw, tile_rows)) return -1;
@@ -687,9 +949,19 @@ static int gemm_swapped_impl(const __nv_bfloat16* W, long long ldw, const __nv_b
   if (kb_per_split < 1) kb_per_split = 1;
   if (kb_per_split > p.k_blocks) kb_per_split = p.k_blocks;
   p.kb_per_split = kb_per_split;
-  p.k_splits = (p.k_blocks + kb_per_split - 1) / kb_per_split;   // every split owns >= 1 k-block
+  if (seg_kb > 0 && seg_kb < p.k_blocks) {
+    if (kb_per_split2 < 1) kb_per_split2 = 1;
+    p.seg_kb = seg_kb;
+    p.seg_splits = (seg_kb + kb_per_split - 1) / kb_per_split;
+    p.kb_per_split2 = kb_per_split2;
+    p.k_splits = p.seg_splits + (p.k_blocks - seg_kb + kb_per_split2 - 1) / kb_per_split2;
+  } else {
+    p.k_splits = (p.k_blocks + kb_per_split - 1) / kb_per_split;   // every split owns >= 1 k-block
+    p.seg_splits = p.k_splits; p.seg_kb = p.k_blocks; p.kb_per_split2 = kb_per_split;
+  }
   p.mode = EPI_PARTIAL;
   p.trigger_early = g_pdl >= 2 ? 1 : 0;
+  p.debug = g_gemm_debug;
   p.ws = ws;
   const int rc = dispatch_gemm(bn, 1, tA, tB, p, stream);
   return rc ? -1 : p.k_splits;
@@ -722,6 +994,7 @@ int gemm_rowform_qkv_rope(const __nv_bfloat16* A, long long lda, const __nv_bflo
   p.k_blocks = (K + BK - 1) / BK;
   p.k_splits = 1;
   p.kb_per_split = p.k_blocks;
+  p.seg_splits = 1; p.seg_kb = p.k_blocks; p.kb_per_split2 = p.k_blocks;
   p.tile_rows = BM;
   p.mode = EPI_QKV_ROPE;
   p.bias = bias;
@@ -739,10 +1012,47 @@ int gemm_rowform_qkv_rope(const __nv_bfloat16* A, long long lda, const __nv_bflo
   return rc;
 }
 
-int gemm_swapped_kb(const __nv_bfloat16* W, long long ldw, const __nv_bfloat16* X, long long ldx,
-                    int n_out, int batch, int K, int kb_divisor, float* ws, cudaStream_t stream) {
-  const SwappedPlan pl = plan_swapped(n_out, K, kb_divisor);
-  return gemm_swapped_impl(W, ldw, X, ldx, n_out, batch, K, pl.kb, pl.tile_rows, ws, stream);
+// Plan for a K-concatenated weight stream [A | B] whose halves must not share a split (seg_K = width of A, a
+// multiple of 64).  One k-block of the swapped form costs a full 128-row MMA pass over the staged weight tile
+// (~0.26 us measured, tools/decode_timeline.py: the tensor core reads the A operand from shared memory at
+// ~32 B/clk, so N = 32 leaves it operand-bound) whatever tile_rows is: the plan minimises the k-blocks of the
+// longest CTA, i.e. prefers full 128-row tiles and many short splits, as long as every CTA is resident at once.
+SwappedPlan2 plan_swapped_2seg(int n_out, int K, int seg_K) {
+  const int k_blocks = (K + BK - 1) / BK;
+  const int ka = seg_K / BK, kbt = k_blocks - ka;
+  const int sms = num_sms();
+  SwappedPlan2 best{BM, 1, ka, 1, kbt};
+  long long best_cost = -1;
+  if (g_gemm_debug & 4) {                 // A/B timing: the previous plan (equal splits of seg_K, balanced tile rows)
+    const SwappedPlan old = plan_swapped(n_out, K, ka);
+    return SwappedPlan2{old.tile_rows, ka / old.kb, old.kb, (kbt + old.kb - 1) / old.kb, old.kb};
+  }
+  for (int rows = BM; rows >= 64; --rows) {
+    const int tiles = (n_out + rows - 1) / rows;
+    for (int sa = 1; sa <= ka && sa <= 8; ++sa) {
+      const int kba = (ka + sa - 1) / sa;
+      if (kba * (sa - 1) >= ka) continue;                       // a split would be empty
+      for (int sb = 1; sb <= kbt && sb <= 24; ++sb) {
+        const int kbb = (kbt + sb - 1) / sb;
+        if (kbb * (sb - 1) >= kbt) continue;
+        const long long waves = (1LL * tiles * (sa + sb) + sms - 1) / sms;
+        const int eff_rows = rows > 96 ? rows : 96;              // MMA floor in units of streamed weight rows
+        const long long cost = waves * eff_rows * (kba > kbb ? kba : kbb) +
+                               (1LL * (sa + sb) * n_out * 32 * 8) / (128LL * sms);
+        if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = SwappedPlan2{rows, sa, kba, sb, kbb}; }
+      }
+    }
+  }
+  return best;
+}
+
+// same as gemm_swapped for W = [A | B] along K with the split boundaries of plan_swapped_2seg: splits
+// [0, splits_a) hold A's partial sums, the rest B's.  Returns the number of splits, -1 on error.
+int gemm_swapped_2seg(const __nv_bfloat16* W, long long ldw, const __nv_bfloat16* X, long long ldx,
+                      int n_out, int batch, int K, int seg_K, float* ws, cudaStream_t stream) {
+  if (seg_K <= 0 || seg_K >= K || seg_K % BK) { set_error("gemm_swapped_2seg: segment boundary must be a multiple of 64 inside K"); return -1; }
+  const SwappedPlan2 pl = plan_swapped_2seg(n_out, K, seg_K);
+  return gemm_swapped_impl(W, ldw, X, ldx, n_out, batch, K, pl.kb_a, pl.tile_rows, ws, stream, seg_K / BK, pl.kb_b);
 }
 
 int splitk_epilogue(const float* ws, int splits, int B, int N, int mode, const __nv_bfloat16* bias,

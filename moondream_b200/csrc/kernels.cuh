@@ -59,6 +59,7 @@ int gemm_rowform(const __nv_bfloat16* A, long long lda, const __nv_bfloat16* W, 
                  long long ldr, int res_mod, __nv_bfloat16* out, long long ldo, int remap_gin,
                  int remap_gout, int remap_goff, cudaStream_t stream);
 void gemm_force_cta_group(int cg);
+void gemm_debug_flags(int flags);
 void gemm_profile_enable(int on);
 int gemm_profile_read(double* total_ms, double* total_flops, long long* launches);
 struct SwappedPlan { int tile_rows, kb, splits; };
@@ -81,9 +82,11 @@ struct RopeEpilogue {
 };
 int gemm_rowform_qkv_rope(const __nv_bfloat16* A, long long lda, const __nv_bfloat16* W, long long ldw, int M,
                           int K, const __nv_bfloat16* bias, const RopeEpilogue& epi, cudaStream_t stream);
-// same, with k-blocks per split restricted to divisors of kb_divisor (split boundaries the caller relies on)
-int gemm_swapped_kb(const __nv_bfloat16* W, long long ldw, const __nv_bfloat16* X, long long ldx,
-                    int n_out, int batch, int K, int kb_divisor, float* ws, cudaStream_t stream);
+// K-concatenated stream W = [A | B] (seg_K = width of A): no split straddles the boundary
+struct SwappedPlan2 { int tile_rows, splits_a, kb_a, splits_b, kb_b; };
+SwappedPlan2 plan_swapped_2seg(int n_out, int K, int seg_K);
+int gemm_swapped_2seg(const __nv_bfloat16* W, long long ldw, const __nv_bfloat16* X, long long ldx,
+                      int n_out, int batch, int K, int seg_K, float* ws, cudaStream_t stream);
 int splitk_epilogue(const float* ws, int splits, int B, int N, int mode, const __nv_bfloat16* bias,
                     const __nv_bfloat16* res, long long ldr, __nv_bfloat16* out, long long ldo,
                     cudaStream_t stream);

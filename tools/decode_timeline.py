@@ -22,6 +22,8 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--batch", type=int, default=32)
 ap.add_argument("--steps", type=int, default=6)
 ap.add_argument("--out", default="gpurun_out/decode_timeline.json")
+ap.add_argument("--gemm-debug", type=int, default=0, help="md_debug_gemm flags (timing experiments)")
+ap.add_argument("--brief", action="store_true")
 args = ap.parse_args()
 
 B = args.batch
@@ -30,6 +32,7 @@ sd = synth.synthetic_state_dict(cfg, 0)
 images = [synth.synthetic_image(i, 378, 378) for i in range(B)]
 prompts = [synth.synthetic_prompt(i, 32, cfg.text.vocab_size) for i in range(B)]
 eng = Engine(cfg, sd, max_batch=B)
+eng.lib.md_debug_gemm(args.gemm_debug)
 pre = eng.encode_images(images)
 eng.generate(pre, prompts, 8, stop_on_eos=False, to_host=False)          # capture
 for _ in range(3):                                                       # settle clocks before measuring
@@ -89,7 +92,7 @@ print(f"last decode step: {len(last)} launches, span {(last[-1]['exit_last'] - l
       f"(+ lm_head / argmax / advance outside)")
 print("times in us relative to the step's first entry; wait = dependency (griddepcontrol.wait) released")
 print(f"{'kind':6s} {'ctas':>5s} {'entry':>8s} {'wait0':>8s} {'wait1':>8s} {'mid0a':>8s} {'mid0b':>8s} {'mid1b':>8s} {'exit0':>8s} {'exit1':>8s} {'busy':>7s}")
-for d in last[4 * 10: 4 * 12]:
+for d in ([] if args.brief else last[4 * 10: 4 * 12]):
     f = lambda k: (d[k] - t0) / 1000.0  # noqa: E731
     print(f"{d['kind']:6s} {d['ctas']:5d} {f('entry_first'):8.1f} {f('wait_first'):8.1f} {f('wait_last'):8.1f} {f('mid0_first'):8.1f} "
           f"{f('mid0_last'):8.1f} {f('mid1_last'):8.1f} {f('exit_first'):8.1f} {f('exit_last'):8.1f} {d['cta_busy_mean'] / 1000:7.1f}")
@@ -120,6 +123,27 @@ for k in order:
         "wait_last_after_prev_exit_us": float(np.mean([d["gap_after_prev_exit"] for d in ds if d["gap_after_prev_exit"] is not None])) / 1000,
         "cta_busy_mean_us": float(np.mean([d["cta_busy_mean"] for d in ds])) / 1000,
     }
-    print(k, json.dumps(summary[k]))
+    print(k, json.dumps(summary[k]) if not args.brief else
+          {q: round(summary[k][q], 2) for q in ("wait_to_exit_us", "cta_busy_mean_us", "wait_last_after_prev_exit_us")})
+# per-k-block pipeline stamps of a few CTAs (kind 4): load-issue -> operands-landed latency inside the weight stream
+det = r[kind == 4]
+if len(det):
+    for rows_id, nm in ((3 * D + FF) & 0xFFFF, "gemm1"), (D & 0xFFFF, "gemm2"):
+        x = det[(det[:, 0] >> 32 & 0xFFFF) == rows_id]
+        if not len(x):
+            continue
+        # keep the records of the last launch of one CTA: same block id, latest wait stamp
+        blk = x[:, 0] & 0xFFFFFFFF
+        for b in np.unique(blk):
+            y = x[blk == b]
+            y = y[y[:, 3] == y[:, 3].max()]
+            j = (y[:, 0] >> 48) & 0xFFF
+            y = y[np.argsort(j)]
+            t_wait = y[0, 3]
+            issue = (y[:, 1] - t_wait) / 1000.0
+            full = (y[:, 2] - t_wait) / 1000.0
+            print(f"{nm} cta {b}: k-block j: loads issued / operands landed (us after the dependency wait), acc ready {(y[0, 4] - t_wait) / 1000.0:.2f}")
+            print("   issue " + " ".join(f"{v:5.2f}" for v in issue))
+            print("   full  " + " ".join(f"{v:5.2f}" for v in full))
 os.makedirs(os.path.dirname(args.out) or ".", exist_ok=True)
 json.dump({"batch": B, "summary": summary, "last_step": last}, open(args.out, "w"), indent=1)

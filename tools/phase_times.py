@@ -16,6 +16,7 @@ B = int(sys.argv[2]) if len(sys.argv) > 2 else 32
 cfg = C.preset(model)
 sd = synth.synthetic_state_dict(cfg, 0)
 eng = Engine(cfg, sd, max_batch=B)
+eng.lib.md_debug_gemm(int(os.environ.get("MD_DEBUG_GEMM", "0")))   # timing experiments (A/B of plans)
 images = [synth.synthetic_image(i, 378, 378) for i in range(B)]
 prompts = [synth.synthetic_prompt(i, 32, cfg.text.vocab_size) for i in range(B)]
 crops, offsets, tilings = [], [0], []
