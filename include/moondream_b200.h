@@ -119,9 +119,8 @@ void md_debug_set_pdl(int enable);
 /* Ablation timing only (results are garbage when non-zero): skip kernels of md_text_decode_step;
  * bit0 [qkv;fc1] GEMM, bit1 its epilogue, bit2 attention, bit3 [proj|fc2] GEMM, bit4 residual+LN epilogue. */
 void md_debug_skip_decode_kernels(int mask);
-/* Timing experiments only (results are garbage when non-zero), weight-streaming GEMM: bit0 skip the activation
- * tile loads, bit1 re-read the first weight k-block (weights from L2 instead of HBM), bit2 previous split plan of
- * the [proj | fc2] stream, bit3 per-k-block stamps in md_debug_timeline (perturbs the step). */
+/* Timing experiments only, small-batch weight stream:
+ * bit2 previous split plan of the [proj | fc2] stream (equal splits).  Other bits are ignored. */
 void md_debug_gemm(int flags);
 /* Profiling only: while `records` is non-NULL every CTA of the decode-step kernels (weight-stream GEMMs, decode
  * attention, residual+LayerNorm epilogue) appends one record of 6 uint64 to records[capacity][6]:

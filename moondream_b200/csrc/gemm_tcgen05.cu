@@ -12,10 +12,11 @@
 // Tails in M, N and K are handled by TMA out-of-bounds zero fill plus masked stores, so the
 // awkward reference shapes (K=588->592, N=4304, M=B*729) need no padded copies of activations.
 //
-// Two output forms:
-//   * row form   (activations are the M side): bf16 out[M,N] with fused epilogue.
-//   * swapped form (weights are the M side, the small decode batch is the N side, optional split-K):
-//     fp32 partial sums ws[split][n(batch)][m(feature)], finished by splitk_epilogue_kernel.
+// Two kernels:
+//   * gemm_bf16_kernel (row form, prefill / ViT sized M): bf16 out[M,N] with a fused epilogue.
+//   * smallbatch_gemm_kernel (decode sized M <= 128 per launch): one CTA per (weight-row tile, K split) streams
+//     its slice of the weight matrix once; fp32 partial sums ws[split][b][n] are finished by the consumer
+//     (splitk_epilogue_kernel, the decode attention prologue, the residual + LayerNorm epilogue, argmax).
 #include <vector>
 
 #include "kernels.cuh"
@@ -33,20 +34,7 @@ static int g_gemm_debug = 0;            // md_debug_gemm: timing experiments onl
 struct GemmParams {
   int M, N, K;
   int m_blocks, n_blocks, k_blocks;   // m_blocks counts (BM * CG)-row tiles; k_blocks = ceil(K / BK)
-  int k_splits;                        // >1 only in swapped form
-  int kb_per_split;                    // k-blocks owned by each split (last one may be shorter)
-  // optional second K segment (the K-concatenated [proj | fc2] stream, whose two halves are rounded to bf16
-  // separately and so may not share a split): splits [0, seg_splits) tile k-blocks [0, seg_kb) with
-  // kb_per_split each, the remaining splits tile [seg_kb, k_blocks) with kb_per_split2 each.
-  // Single segment: seg_splits = k_splits, seg_kb = k_blocks.
-  int seg_splits, seg_kb, kb_per_split2;
-  int debug;                           // timing experiments only (md_debug_gemm): bit0 skip the activation loads of the
-                                       // swapped form, bit1 re-read the first weight k-block (L2 instead of HBM)
-  int trigger_early;                   // PDL: release dependents at kernel start (weight-streaming form, g_pdl >= 2)
-  int tile_rows;                       // rows of A per tile (<= BM; single-CTA tiles only): balances the
-                                       // weight stream over the SMs when M / BM is not a multiple of 148
-  int mode;                            // EPI_* (row form) or EPI_PARTIAL (swapped form)
-  // row form
+  int mode;                            // EPI_BIAS / EPI_BIAS_GELU / EPI_BIAS_RESIDUAL / EPI_QKV_ROPE
   __nv_bfloat16* out;
   long long ldo;
   const __nv_bfloat16* bias;           // [N] or nullptr
@@ -54,22 +42,8 @@ struct GemmParams {
   long long ldr;
   int res_mod;                         // residual row = row % res_mod when > 0 (pos_emb broadcast)
   int remap_gin, remap_gout, remap_goff;  // out row = (r / gin) * gout + r % gin + goff when gin > 0
-  // swapped form
-  float* ws;                           // [k_splits][N][M] fp32
   RopeEpilogue rope;                   // EPI_QKV_ROPE
 };
-
-// k-block range [kb0, kb1) of one split
-__device__ __forceinline__ void split_range(const GemmParams& p, int split, int& kb0, int& kb1) {
-  if (split < p.seg_splits) {
-    kb0 = split * p.kb_per_split;
-    kb1 = min(p.seg_kb, kb0 + p.kb_per_split);
-  } else {
-    kb0 = p.seg_kb + (split - p.seg_splits) * p.kb_per_split2;
-    kb1 = min(p.k_blocks, kb0 + p.kb_per_split2);
-  }
-}
-
 
 // Fused epilogue of the prefill QKV projection: this thread owns token row `row` and the 32 output columns
 // col0..col0+31 = one half of one head of q, k or v.  dims 0..31 of q and k rotate (pairs (j, j+16) are
@@ -165,11 +139,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const bool leader = rank == 0;
 
   __shared__ unsigned long long tl_s[5];    // debug timeline stamps (see ptx.cuh), untouched unless installed
-  __shared__ unsigned long long tl_kb[2][40];   // per-k-block stamps of a few CTAs: [0] loads issued, [1] operands landed
   const bool tl = tl_on();
-  const bool tl_detail = tl && (p.debug & 8) && p.mode == EPI_PARTIAL && (blockIdx.x == 0 || blockIdx.x == 73 || blockIdx.x == gridDim.x - 1);
   if (tl && threadIdx.x == 0) tl_s[0] = tl_now();
-  if (p.trigger_early) pdl_launch_dependents();
   if (warp == 0 && lane == 0) {
     prefetch_tensormap(&tmA);
     prefetch_tensormap(&tmB);
@@ -194,7 +165,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
-  const int total_tiles = p.m_blocks * p.n_blocks * p.k_splits;
+  const int total_tiles = p.m_blocks * p.n_blocks;
   const int unit = blockIdx.x / CG, n_units = gridDim.x / CG;
 
   if (warp == 0) {
@@ -202,55 +173,27 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      // Swapped form: the A operand is a weight matrix, which no earlier kernel produces.  Under
-      // programmatic dependent launch this CTA may be running while its predecessor drains, so the
-      // weight tiles of the first ring of stages are requested before the dependency wait; only the
-      // activation (B) loads and everything downstream of them wait for the predecessor.
-      int prefetched = 0;
-      if (CG == 1 && p.mode == EPI_PARTIAL && unit < total_tiles) {
-        const int split = unit % p.k_splits;
-        const int m_blk = (unit / p.k_splits) / p.n_blocks;
-        int kb0, kb1;
-        split_range(p, split, kb0, kb1);
-        prefetched = min(STAGES, kb1 - kb0);
-        for (int i = 0; i < prefetched; ++i) {
-          mbar_arrive_expect_tx(&full_bar[i], p.tile_rows * (BK * 2) + ((p.debug & 1) ? 0 : S::kBBytes));
-          tma_load_2d(smem + i * S::kStageBytes, &tmA, &full_bar[i], (kb0 + ((p.debug & 2) ? 0 : i)) * BK, m_blk * p.tile_rows);
-        }
-      }
       pdl_wait();
       if (tl) tl_s[1] = tl_now();
       for (int tile = unit; tile < total_tiles; tile += n_units) {
-        const int split = tile % p.k_splits;
-        const int t2 = tile / p.k_splits;
-        const int n_blk = t2 % p.n_blocks;
-        const int m_blk = t2 / p.n_blocks;
-        int kb0, kb1;
-        split_range(p, split, kb0, kb1);
-        const int a_row = (CG == 2) ? m_blk * (BM * CG) + rank * BM : m_blk * p.tile_rows;
+        const int n_blk = tile % p.n_blocks;
+        const int m_blk = tile / p.n_blocks;
+        const int a_row = m_blk * (BM * CG) + rank * BM;
         const int b_row = n_blk * BN + rank * (BN / CG);
-        for (int kb = kb0; kb < kb1; ++kb) {
+        for (int kb = 0; kb < p.k_blocks; ++kb) {
           uint8_t* sa = smem + stage * S::kStageBytes;
           uint8_t* sb = sa + S::kABytes;
-          if (prefetched > 0) {
-            // stage already armed and its weight tile in flight: add the activation tile
-            --prefetched;
-            if (!(p.debug & 1)) tma_load_2d(sb, &tmB, &full_bar[stage], kb * BK, b_row);
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          if (CG == 2) {
+            if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * S::kStageBytes);
+            else mbar_arrive_leader(&full_bar[stage]);
+            tma_load_2d_pair(sa, &tmA, &full_bar[stage], kb * BK, a_row);
+            tma_load_2d_pair(sb, &tmB, &full_bar[stage], kb * BK, b_row);
           } else {
-            mbar_wait(&empty_bar[stage], phase ^ 1);
-            if (CG == 2) {
-              if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * S::kStageBytes);
-              else mbar_arrive_leader(&full_bar[stage]);
-              tma_load_2d_pair(sa, &tmA, &full_bar[stage], kb * BK, a_row);
-              tma_load_2d_pair(sb, &tmB, &full_bar[stage], kb * BK, b_row);
-            } else {
-              const bool skip_b = p.mode == EPI_PARTIAL && (p.debug & 1);
-              mbar_arrive_expect_tx(&full_bar[stage], p.tile_rows * (BK * 2) + (skip_b ? 0 : S::kBBytes));
-              tma_load_2d(sa, &tmA, &full_bar[stage], ((p.mode == EPI_PARTIAL && (p.debug & 2)) ? kb0 : kb) * BK, a_row);
-              if (!skip_b) tma_load_2d(sb, &tmB, &full_bar[stage], kb * BK, b_row);
-            }
+            mbar_arrive_expect_tx(&full_bar[stage], S::kStageBytes);
+            tma_load_2d(sa, &tmA, &full_bar[stage], kb * BK, a_row);
+            tma_load_2d(sb, &tmB, &full_bar[stage], kb * BK, b_row);
           }
-          if (tl_detail && tile == unit && kb - kb0 < 40) tl_kb[0][kb - kb0] = tl_now();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -264,19 +207,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       uint32_t phase = 0;
       int it = 0;
       for (int tile = unit; tile < total_tiles; tile += n_units, ++it) {
-        const int split = tile % p.k_splits;
-        int kb0, kb1;
-        split_range(p, split, kb0, kb1);
         const int as = it & 1;
         const uint32_t aphase = (it >> 1) & 1;
         mbar_wait(&tmem_empty[as], aphase ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(as * BN);
-        for (int kb = kb0; kb < kb1; ++kb) {
+        for (int kb = 0; kb < p.k_blocks; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          if (tl && it == 0 && kb == kb0) tl_s[2] = tl_now();          // first operands landed
-          if (tl_detail && it == 0 && kb - kb0 < 40) tl_kb[1][kb - kb0] = tl_now();
+          if (tl && it == 0 && kb == 0) tl_s[2] = tl_now();            // first operands landed
           const uint32_t sa = smem_u32(smem + stage * S::kStageBytes);
           const uint32_t sb = sa + S::kABytes;
           const uint64_t da = make_desc_k_sw128(sa);
@@ -284,7 +223,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             // advance 16 elements (32 B) along K inside the 128-byte swizzle row: +2 in 16-B units
-            const uint32_t acc = (kb > kb0 || k > 0) ? 1u : 0u;
+            const uint32_t acc = (kb > 0 || k > 0) ? 1u : 0u;
             if (CG == 2) umma_bf16_pair(tmem_d, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k), idesc, acc);
             else umma_bf16(tmem_d, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k), idesc, acc);
           }
@@ -302,15 +241,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int half = (warp - 4) >> 2;       // the two warps of a quadrant interleave 32-column chunks
     int it = 0;
     for (int tile = unit; tile < total_tiles; tile += n_units, ++it) {
-      const int split = tile % p.k_splits;
-      const int t2 = tile / p.k_splits;
-      const int n_blk = t2 % p.n_blocks;
-      const int m_blk = t2 / p.n_blocks;
+      const int n_blk = tile % p.n_blocks;
+      const int m_blk = tile / p.n_blocks;
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
-      const int row_in_tile = q * 32 + lane;
-      const int row = (CG == 2 ? m_blk * (BM * CG) + rank * BM : m_blk * p.tile_rows) + row_in_tile;   // accumulator row
-      const bool row_ok = row < p.M && (CG == 2 || row_in_tile < p.tile_rows);
+      const int row = m_blk * (BM * CG) + rank * BM + q * 32 + lane;   // accumulator row
+      const bool row_ok = row < p.M;
       long long out_row = row;
       if (p.remap_gin > 0)
         out_row = static_cast<long long>(row / p.remap_gin) * p.remap_gout + row % p.remap_gin +
@@ -347,16 +283,6 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int col0 = n_blk * BN + c * 32;
         if (p.mode == EPI_QKV_ROPE) {
           if (row_ok && col0 < p.N) rope_store_chunk(p, acc, row, col0, rr);
-          continue;
-        }
-        if (p.mode == EPI_PARTIAL) {
-          // swapped form: rows are output features (contiguous across lanes), columns are batch
-          if (row_ok) {
-            float* wsp = p.ws + (static_cast<long long>(split) * p.N) * p.M + row;
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (col0 + j < p.N) wsp[static_cast<long long>(col0 + j) * p.M] = __uint_as_float(acc[j]);
-          }
           continue;
         }
         if (row_ok && col0 < p.N) {
@@ -406,12 +332,6 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (tl && threadIdx.x == 0 && blockIdx.x < total_tiles * CG)
     tl_emit((1u << 28) | (static_cast<uint32_t>(p.mode) << 24) | (static_cast<uint32_t>(p.M) & 0xFFFFFFu),
             tl_s[0], tl_s[1], tl_s[2], tl_s[3], tl_now());
-  if (tl_detail && threadIdx.x == 0) {
-    const int n = min(40, min(p.k_blocks, p.kb_per_split));
-    for (int j = 0; j < n; ++j)
-      tl_emit((4u << 28) | (static_cast<uint32_t>(j) << 16) | (static_cast<uint32_t>(p.M) & 0xFFFFu), tl_kb[0][j], tl_kb[1][j],
-              tl_s[1], tl_s[3], 0ull);
-  }
   if (warp == 2) {
     tc_fence_after();
     if (CG == 2) tmem_dealloc_pair(tmem_base, kTmemCols); else tmem_dealloc(tmem_base, kTmemCols);
@@ -441,7 +361,7 @@ constexpr int kSbThreads = 256;          // warp 0 TMA producer, 1 MMA issuer, 2
 constexpr int kSbTailPad = BM * BK * 2;  // the A descriptor spans 128 rows whatever the batch: keep it in bounds
 
 struct SmallBatchParams {
-  int batch, n_out, k_blocks;
+  int batch, batch_total, n_out, k_blocks;   // this launch covers `batch` (<= 128) rows of a batch_total-row problem
   int tile_n, n_mma, k_splits;
   int kb_per_split, seg_splits, seg_kb, kb_per_split2;   // split -> k-block range, as in GemmParams
   int stages, a_bytes, stage_bytes;    // a_bytes: activation tile (box rows * 128 B), then the weight tile
@@ -554,7 +474,7 @@ smallbatch_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
       mbar_wait(tmem_full, 0);
       tc_fence_after();
       if (tl && threadIdx.x == 128) tl_s[3] = tl_now();       // accumulator complete
-      float* dst = p.ws + (static_cast<long long>(split) * p.batch + b) * p.n_out + n0;
+      float* dst = p.ws + (static_cast<long long>(split) * p.batch_total + b) * p.n_out + n0;
       const bool vec = ((n0 | p.n_out) & 3) == 0;
       const int n_valid = min(p.tile_n, p.n_out - n0);
       for (int c = 0; c * 32 < n_valid; ++c) {
@@ -589,7 +509,7 @@ smallbatch_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
   }
 }
 
-// Finishes a swapped-form GEMM: out[b][n] = epi( sum_s ws[s][b][n] + bias[n] ) in a fixed
+// Finishes a small-batch GEMM: out[b][n] = epi( sum_s ws[s][b][n] + bias[n] ) in a fixed
 // summation order (deterministic, unlike atomics).
 __global__ void splitk_epilogue_kernel(const float* __restrict__ ws, int splits, int B, int N,
                                        int mode, const __nv_bfloat16* __restrict__ bias,
@@ -742,7 +662,7 @@ static int launch_gemm(const CUtensorMap& tA, const CUtensorMap& tB, const GemmP
     if (e != cudaSuccess) return set_error(cudaGetErrorString(e));
     configured = true;
   }
-  const int total = p.m_blocks * p.n_blocks * p.k_splits;
+  const int total = p.m_blocks * p.n_blocks;
   const int max_units = num_sms() / CG;
   const int units = total < max_units ? total : max_units;
   cudaLaunchConfig_t cfg{};
@@ -821,14 +741,9 @@ int gemm_rowform(const __nv_bfloat16* A, long long lda, const __nv_bfloat16* W, 
   p.m_blocks = (M + BM * cg - 1) / (BM * cg);
   p.n_blocks = (N + bn - 1) / bn;
   p.k_blocks = (K + BK - 1) / BK;
-  p.k_splits = 1;
-  p.kb_per_split = p.k_blocks;
-  p.seg_splits = 1; p.seg_kb = p.k_blocks; p.kb_per_split2 = p.k_blocks;
-  p.tile_rows = BM;
   p.mode = mode;
   p.out = out; p.ldo = ldo; p.bias = bias; p.res = res; p.ldr = ldr; p.res_mod = res_mod;
   p.remap_gin = remap_gin; p.remap_gout = remap_gout; p.remap_goff = remap_goff;
-  p.ws = nullptr;
   cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
   const bool prof = g_prof.on && cudaStreamIsCapturing(stream, &cap) == cudaSuccess &&
                     cap == cudaStreamCaptureStatusNone;
@@ -843,10 +758,10 @@ int gemm_rowform(const __nv_bfloat16* A, long long lda, const __nv_bfloat16* W, 
 }
 
 
-// Plan of a weight-streaming (swapped) GEMM: tile height (rows of W per CTA tile, <= 128) and k-blocks per
-// split such that (tiles x splits) fills whole waves of the SMs.  cost = waves x tile_rows x kb is the
-// critical path in units of 128-byte weight rows; ties prefer fewer splits (less partial-sum traffic).
-// kb_divisor > 0 restricts kb to divisors of it (split boundaries the caller relies on).
+// Plan of a small-batch weight stream: tile height (rows of W per CTA, <= 128) and k-blocks per split such
+// that (tiles x splits) fills whole waves of the SMs.  cost = waves x tile_rows x kb is the critical path in
+// units of 128-byte weight rows; ties prefer fewer splits (less partial-sum traffic).
+// kb_divisor > 0 restricts kb to divisors of it.
 SwappedPlan plan_swapped(int n_out, int K, int kb_divisor) {
   const int k_blocks = (K + BK - 1) / BK;
   const int sms = num_sms();
@@ -870,16 +785,18 @@ SwappedPlan plan_swapped(int n_out, int K, int kb_divisor) {
 }
 
 // ws[splits][batch][n_out] (fp32) = W[n_out,K] * X[batch,K]^T  partial sums; split s owns k-blocks
-// [s * kb_per_split, (s+1) * kb_per_split).  Returns the number of splits (>0), -1 on error.
-
-static int launch_smallbatch(const __nv_bfloat16* W, long long ldw, const __nv_bfloat16* X, long long ldx,
+// [s * kb_per_split, (s+1) * kb_per_split).
+// With seg_kb > 0 the k-blocks split in two segments (see SmallBatchParams): [0, seg_kb) in pieces of
+// kb_per_split, the rest in pieces of kb_per_split2.  Batches above 128 rows run as consecutive 128-row launches.
+// Returns the number of splits (> 0), -1 on error.
+static int gemm_swapped_impl(const __nv_bfloat16* W, long long ldw, const __nv_bfloat16* X, long long ldx,
                              int n_out, int batch, int K, int kb_per_split, int tile_n, float* ws,
-                             cudaStream_t stream, int seg_kb, int kb_per_split2) {
-  if (batch > BM) { set_error("small-batch GEMM: batch must be <= 128"); return -1; }
-  if (tile_n < 1) tile_n = BM;
-  if (tile_n > 256) tile_n = 256;
+                             cudaStream_t stream, int seg_kb = 0, int kb_per_split2 = 0) {
+  if (n_out <= 0 || batch <= 0 || K <= 0) { set_error("small-batch GEMM: empty problem"); return -1; }
+  if (K % 8) { set_error("small-batch GEMM: K must be a multiple of 8"); return -1; }
+  if (tile_n < 1 || tile_n > 256) tile_n = BM;
   SmallBatchParams p{};
-  p.batch = batch; p.n_out = n_out;
+  p.batch_total = batch; p.n_out = n_out;
   p.k_blocks = (K + BK - 1) / BK;
   p.tile_n = tile_n;
   p.n_mma = (tile_n + 15) / 16 * 16;
@@ -897,74 +814,36 @@ static int launch_smallbatch(const __nv_bfloat16* W, long long ldw, const __nv_b
     p.k_splits = (p.k_blocks + kb_per_split - 1) / kb_per_split;   // every split owns >= 1 k-block
     p.seg_splits = p.k_splits; p.seg_kb = p.k_blocks; p.kb_per_split2 = kb_per_split;
   }
-  const int a_rows = (batch + 7) / 8 * 8;
-  p.a_bytes = a_rows * BK * 2;                       // a multiple of 1024: the weight tile stays swizzle-aligned
-  p.stage_bytes = p.a_bytes + p.n_mma * BK * 2;
-  const int bar_bytes = (2 * kSbMaxStages + 1) * 8 + 16;
-  constexpr int kSbSmemMax = 227 * 1024 - 1024;      // leave room for the kernel's few static __shared__ words
-  const int budget = kSbSmemMax - 1024 - kSbTailPad - bar_bytes;
-  p.stages = budget / p.stage_bytes;
-  if (p.stages > kSbMaxStages) p.stages = kSbMaxStages;
-  if (p.stages < 2) { set_error("small-batch GEMM: tile does not fit shared memory"); return -1; }
   p.tmem_cols = p.n_mma <= 32 ? 32 : p.n_mma <= 64 ? 64 : p.n_mma <= 128 ? 128 : 256;
   p.trigger_early = g_pdl >= 2 ? 1 : 0;
-  p.ws = ws;
-  CUtensorMap tX, tW;
-  if (make_tmap_bf16_2d(&tX, X, batch, K, ldx, a_rows)) return -1;
-  if (make_tmap_bf16_2d(&tW, W, n_out, K, ldw, tile_n)) return -1;
-  const int smem_bytes = p.stages * p.stage_bytes + kSbTailPad + bar_bytes + 1024;
+  constexpr int kSbSmemMax = 227 * 1024 - 1024;      // leave room for the kernel's few static __shared__ words
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(smallbatch_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSbSmemMax);
     if (e != cudaSuccess) { set_error(cudaGetErrorString(e)); return -1; }
     configured = true;
   }
-  count_launch();
-  cudaError_t e = launch_k(smallbatch_gemm_kernel, dim3(n_tiles * p.k_splits), dim3(kSbThreads),
-                           static_cast<size_t>(smem_bytes), stream, tX, tW, p);
-  if (e != cudaSuccess) { set_error(cudaGetErrorString(e)); return -1; }
-  return p.k_splits;
-}
-
-// With seg_kb > 0 the k-blocks split in two segments (see GemmParams): [0, seg_kb) in pieces of kb_per_split,
-// the rest in pieces of kb_per_split2.
-static int gemm_swapped_impl(const __nv_bfloat16* W, long long ldw, const __nv_bfloat16* X, long long ldx,
-                             int n_out, int batch, int K, int kb_per_split, int tile_rows, float* ws,
-                             cudaStream_t stream, int seg_kb = 0, int kb_per_split2 = 0) {
-  if (n_out <= 0 || batch <= 0 || K <= 0) { set_error("gemm_swapped: empty problem"); return -1; }
-  if (K % 8) { set_error("gemm_swapped: K must be a multiple of 8"); return -1; }
-  if (tile_rows < 1 || tile_rows > BM) tile_rows = BM;
-  if (batch <= BM && !(g_gemm_debug & 16))
-    return launch_smallbatch(W, ldw, X, ldx, n_out, batch, K, kb_per_split, tile_rows, ws, stream, seg_kb, kb_per_split2);
-  const int bn = batch <= 32 ? 32 : batch <= 64 ? 64 : batch <= 128 ? 128 : 256;
-  CUtensorMap tA, tB;
-  if (make_tmap_bf16_2d(&tA, W, n_out, K, ldw, tile_rows)) return -1;
-  if (make_tmap_bf16_2d(&tB, X, batch, K, ldx, bn)) return -1;
-  GemmParams p{};
-  p.M = n_out; p.N = batch; p.K = K;
-  p.tile_rows = tile_rows;
-  p.m_blocks = (n_out + tile_rows - 1) / tile_rows;
-  p.n_blocks = (batch + bn - 1) / bn;
-  p.k_blocks = (K + BK - 1) / BK;
-  if (kb_per_split < 1) kb_per_split = 1;
-  if (kb_per_split > p.k_blocks) kb_per_split = p.k_blocks;
-  p.kb_per_split = kb_per_split;
-  if (seg_kb > 0 && seg_kb < p.k_blocks) {
-    if (kb_per_split2 < 1) kb_per_split2 = 1;
-    p.seg_kb = seg_kb;
-    p.seg_splits = (seg_kb + kb_per_split - 1) / kb_per_split;
-    p.kb_per_split2 = kb_per_split2;
-    p.k_splits = p.seg_splits + (p.k_blocks - seg_kb + kb_per_split2 - 1) / kb_per_split2;
-  } else {
-    p.k_splits = (p.k_blocks + kb_per_split - 1) / kb_per_split;   // every split owns >= 1 k-block
-    p.seg_splits = p.k_splits; p.seg_kb = p.k_blocks; p.kb_per_split2 = kb_per_split;
+  CUtensorMap tW;
+  if (make_tmap_bf16_2d(&tW, W, n_out, K, ldw, tile_n)) return -1;
+  for (int b0 = 0; b0 < batch; b0 += BM) {
+    p.batch = batch - b0 < BM ? batch - b0 : BM;
+    const int a_rows = (p.batch + 7) / 8 * 8;
+    p.a_bytes = a_rows * BK * 2;                     // a multiple of 1024: the weight tile stays swizzle-aligned
+    p.stage_bytes = p.a_bytes + p.n_mma * BK * 2;
+    const int bar_bytes = (2 * kSbMaxStages + 1) * 8 + 16;
+    p.stages = (kSbSmemMax - 1024 - kSbTailPad - bar_bytes) / p.stage_bytes;
+    if (p.stages > kSbMaxStages) p.stages = kSbMaxStages;
+    if (p.stages < 2) { set_error("small-batch GEMM: tile does not fit shared memory"); return -1; }
+    p.ws = ws + static_cast<long long>(b0) * n_out;
+    CUtensorMap tX;
+    if (make_tmap_bf16_2d(&tX, X + static_cast<long long>(b0) * ldx, p.batch, K, ldx, a_rows)) return -1;
+    const int smem_bytes = p.stages * p.stage_bytes + kSbTailPad + bar_bytes + 1024;
+    count_launch();
+    cudaError_t e = launch_k(smallbatch_gemm_kernel, dim3(n_tiles * p.k_splits), dim3(kSbThreads),
+                             static_cast<size_t>(smem_bytes), stream, tX, tW, p);
+    if (e != cudaSuccess) { set_error(cudaGetErrorString(e)); return -1; }
   }
-  p.mode = EPI_PARTIAL;
-  p.trigger_early = g_pdl >= 2 ? 1 : 0;
-  p.debug = g_gemm_debug;
-  p.ws = ws;
-  const int rc = dispatch_gemm(bn, 1, tA, tB, p, stream);
-  return rc ? -1 : p.k_splits;
+  return p.k_splits;
 }
 
 int gemm_swapped_splits(int n_out, int K) { return plan_swapped(n_out, K, 0).splits; }
@@ -992,10 +871,6 @@ int gemm_rowform_qkv_rope(const __nv_bfloat16* A, long long lda, const __nv_bflo
   p.m_blocks = (M + BM * cg - 1) / (BM * cg);
   p.n_blocks = (N + bn - 1) / bn;
   p.k_blocks = (K + BK - 1) / BK;
-  p.k_splits = 1;
-  p.kb_per_split = p.k_blocks;
-  p.seg_splits = 1; p.seg_kb = p.k_blocks; p.kb_per_split2 = p.k_blocks;
-  p.tile_rows = BM;
   p.mode = EPI_QKV_ROPE;
   p.bias = bias;
   p.rope = epi;
@@ -1013,10 +888,10 @@ int gemm_rowform_qkv_rope(const __nv_bfloat16* A, long long lda, const __nv_bflo
 }
 
 // Plan for a K-concatenated weight stream [A | B] whose halves must not share a split (seg_K = width of A, a
-// multiple of 64).  One k-block of the swapped form costs a full 128-row MMA pass over the staged weight tile
-// (~0.26 us measured, tools/decode_timeline.py: the tensor core reads the A operand from shared memory at
-// ~32 B/clk, so N = 32 leaves it operand-bound) whatever tile_rows is: the plan minimises the k-blocks of the
-// longest CTA, i.e. prefers full 128-row tiles and many short splits, as long as every CTA is resident at once.
+// multiple of 64).  A k-block costs four M = 128 MMAs whatever the tile height (~0.3 us measured with
+// tools/decode_timeline.py: the 128-lane activation operand is re-read from shared memory every K = 16 step),
+// so the plan minimises the k-blocks of the longest CTA: full 128-row tiles and many short splits, as long as
+// every CTA is resident at once.
 SwappedPlan2 plan_swapped_2seg(int n_out, int K, int seg_K) {
   const int k_blocks = (K + BK - 1) / BK;
   const int ka = seg_K / BK, kbt = k_blocks - ka;

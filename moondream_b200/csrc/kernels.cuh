@@ -12,7 +12,7 @@ enum : int {
   EPI_BIAS = 0,            // out = bf16(acc + bias)
   EPI_BIAS_GELU = 1,       // out = bf16(gelu_tanh(bf16(acc + bias)))
   EPI_BIAS_RESIDUAL = 2,   // out = bf16(bf16(acc + bias) + residual)
-  EPI_PARTIAL = 3,         // swapped form: fp32 partial sums to workspace
+  EPI_PARTIAL = 3,         // small-batch kernel: fp32 partial sums to workspace (timeline tag only)
   EPI_QKV_ROPE = 5,        // row form, decoder QKV projection: bias + partial RoPE, q -> q_out, k/v -> KV pages
 };
 

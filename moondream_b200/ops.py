@@ -34,7 +34,8 @@ def linear(x, w, bias=None, epilogue=EPI_BIAS, residual=None, res_mod=0, out=Non
 
 
 def linear_small_batch(x, w, bias=None, epilogue=EPI_BIAS, residual=None, out=None, workspace=None):
-    """Decode-sized batch: weights stream through the M side of the MMA, split-K reduce."""
+    """Decode-sized batch: every CTA streams one (weight-row tile, K split) once; split-K partials are reduced
+    in a fixed order by the epilogue kernel."""
     _req(x), _req(w)
     B, K = x.shape
     Nout = w.shape[0]

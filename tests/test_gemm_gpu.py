@@ -94,7 +94,7 @@ def test_linear_strided_views(cta_group):
 
 
 SMALL = [(32, 6144, 2048), (32, 2048, 8192), (1, 2048, 2048), (5, 1024, 8192), (32, 51200, 2048),
-         (64, 8192, 2048), (128, 3072, 1024), (7, 1032, 264)]
+         (64, 8192, 2048), (128, 3072, 1024), (7, 1032, 264), (200, 2048, 1024)]
 
 
 @pytest.mark.parametrize("B,N,K", SMALL)

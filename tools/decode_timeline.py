@@ -125,25 +125,5 @@ for k in order:
     }
     print(k, json.dumps(summary[k]) if not args.brief else
           {q: round(summary[k][q], 2) for q in ("wait_to_exit_us", "cta_busy_mean_us", "wait_last_after_prev_exit_us")})
-# per-k-block pipeline stamps of a few CTAs (kind 4): load-issue -> operands-landed latency inside the weight stream
-det = r[kind == 4]
-if len(det):
-    for rows_id, nm in ((3 * D + FF) & 0xFFFF, "gemm1"), (D & 0xFFFF, "gemm2"):
-        x = det[(det[:, 0] >> 32 & 0xFFFF) == rows_id]
-        if not len(x):
-            continue
-        # keep the records of the last launch of one CTA: same block id, latest wait stamp
-        blk = x[:, 0] & 0xFFFFFFFF
-        for b in np.unique(blk):
-            y = x[blk == b]
-            y = y[y[:, 3] == y[:, 3].max()]
-            j = (y[:, 0] >> 48) & 0xFFF
-            y = y[np.argsort(j)]
-            t_wait = y[0, 3]
-            issue = (y[:, 1] - t_wait) / 1000.0
-            full = (y[:, 2] - t_wait) / 1000.0
-            print(f"{nm} cta {b}: k-block j: loads issued / operands landed (us after the dependency wait), acc ready {(y[0, 4] - t_wait) / 1000.0:.2f}")
-            print("   issue " + " ".join(f"{v:5.2f}" for v in issue))
-            print("   full  " + " ".join(f"{v:5.2f}" for v in full))
 os.makedirs(os.path.dirname(args.out) or ".", exist_ok=True)
 json.dump({"batch": B, "summary": summary, "last_step": last}, open(args.out, "w"), indent=1)
