@@ -219,7 +219,7 @@ def run_reference(args, cfg, sd):
         "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit_line(line)
 
 
 # --------------------------------------------------------------------------------------------
@@ -353,11 +353,31 @@ def run_main(args, cfg, sd, rank, world, local_rank):
             "value": val, "unit": "images/s", "cores": threads, "kind": "port",
             "sample": f"1 image: full encode_image + {PROMPT_LEN}-token prompt prefill + 16 of {NEW_TOKENS} decode "
                       f"steps (decode time x4); oracle port of the reference (bf16 torch CPU, sequential batch-1); {detail}"}
-    print(json.dumps(line), flush=True)
+    emit_line(line)
+
+
+_JSON_OUT = None
+
+
+def protect_stdout():
+    """stdout carries exactly one JSON line: keep a private handle on it and point fd 1 at stderr, so banners that
+    libraries write straight to fd 1 (NCCL prints its version there whatever NCCL_DEBUG_FILE says) cannot reach it."""
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit_line(line):
+    out = _JSON_OUT if _JSON_OUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 def main():
     global NEW_TOKENS
+    protect_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
