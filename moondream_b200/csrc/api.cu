@@ -55,10 +55,10 @@ int md_linear_bf16(const void* x, long long ldx, const void* w, long long ldw, i
                           res_mod, BFM(out), ldo, remap_gin, remap_gout, remap_goff, STREAM(stream));
 }
 
-int md_linear_small_batch_splits(int n_out, int K) { return md::gemm_swapped_splits(n_out, K); }
+int md_linear_small_batch_splits(int n_out, int K) { return md::gemm_smallbatch_splits(n_out, K); }
 
 long long md_linear_small_batch_workspace_bytes(int n_out, int batch, int K) {
-  return static_cast<long long>(md::gemm_swapped_splits(n_out, K)) * batch * n_out * 4;
+  return static_cast<long long>(md::gemm_smallbatch_splits(n_out, K)) * batch * n_out * 4;
 }
 
 int md_linear_small_batch_bf16(const void* x, long long ldx, const void* w, long long ldw, int batch,
@@ -67,8 +67,8 @@ int md_linear_small_batch_bf16(const void* x, long long ldx, const void* w, long
                                void* stream) {
   NEED(x && w && out && workspace, "md_linear_small_batch_bf16");
   if (epilogue < 0 || epilogue > 2) return md::set_error("md_linear_small_batch_bf16: bad epilogue");
-  const int want = md::gemm_swapped_splits(n_out, K);
-  const int used = md::gemm_swapped(BF(w), ldw, BF(x), ldx, n_out, batch, K, want,
+  const int want = md::gemm_smallbatch_splits(n_out, K);
+  const int used = md::gemm_smallbatch(BF(w), ldw, BF(x), ldx, n_out, batch, K, want,
                                     reinterpret_cast<float*>(workspace), STREAM(stream));
   if (used < 0) return 1;
   return md::splitk_epilogue(reinterpret_cast<const float*>(workspace), used, batch, n_out, epilogue,

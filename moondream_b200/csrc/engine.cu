@@ -210,12 +210,12 @@ static long long smallbatch_ws_floats(const Model& m, int batch) {
   const md_dims& d = m.d;
   long long need = 0;
   auto upd = [&](int n_out, int K) {
-    const long long f = 1LL * gemm_swapped_splits(n_out, K) * batch * n_out;
+    const long long f = 1LL * gemm_smallbatch_splits(n_out, K) * batch * n_out;
     if (f > need) need = f;
   };
   upd(3 * d.txt_dim + d.txt_ff, d.txt_dim);
   {
-    const SwappedPlan2 pl = plan_swapped_2seg(d.txt_dim, d.txt_dim + d.txt_ff, d.txt_dim);
+    const StreamPlan2 pl = plan_smallbatch_2seg(d.txt_dim, d.txt_dim + d.txt_ff, d.txt_dim);
     const long long f = 1LL * (pl.splits_a + pl.splits_b) * batch * d.txt_dim;
     if (f > need) need = f;
   }
@@ -233,7 +233,7 @@ long long text_decode_ws_bytes(const Model& m, int batch) {
 
 static int small_linear(const bf16* x, long long ldx, const Lin& l, int batch, int n_out, int K, int mode,
                         const bf16* res, long long ldr, bf16* out, long long ldo, float* ws, cudaStream_t st) {
-  const int used = gemm_swapped(l.w, l.ld, x, ldx, n_out, batch, K, gemm_swapped_splits(n_out, K), ws, st);
+  const int used = gemm_smallbatch(l.w, l.ld, x, ldx, n_out, batch, K, gemm_smallbatch_splits(n_out, K), ws, st);
   if (used < 0) return 1;
   return splitk_epilogue(ws, used, batch, n_out, mode, l.b, res, ldr, out, ldo, st);
 }
@@ -252,7 +252,7 @@ int text_decode_step(Model& m, bf16* x, const int* pos, int batch, const md_kv& 
   bf16* xcat = reinterpret_cast<bf16*>(p); p += pad256(1LL * batch * (D + FF) * 2);   // [att | gelu(fc1)]
   float* wsf = reinterpret_cast<float*>(p);
   bf16* pool = reinterpret_cast<bf16*>(kv.pool);
-  const SwappedPlan2 pl2 = plan_swapped_2seg(D, D + FF, D);   // no split straddles proj | fc2
+  const StreamPlan2 pl2 = plan_smallbatch_2seg(D, D + FF, D);   // no split straddles proj | fc2
   const int proj_splits = pl2.splits_a;
   if (layernorm(x, D, m.txt[0].ln.w, m.txt[0].ln.b, ln, D, batch, D, 1e-5f, st)) return 1;
   for (int i = 0; i < d.txt_layers; ++i) {
@@ -260,8 +260,8 @@ int text_decode_step(Model& m, bf16* x, const int* pos, int batch, const md_kv& 
     // [qkv ; fc1] share the input l = ln(x) (text.py:145-157): one weight stream, then bias / RoPE /
     // KV-page write / GELU, which the attention kernel applies for its own (sequence, head).  (Fusing them into
     // the GEMM epilogue needs whole-K tiles, i.e. 112 streaming SMs instead of 148: measured slower, DESIGN.md.)
-    int s1 = plan_swapped(3 * D + FF, D, 0).splits;
-    if (!(g_debug_skip & 1)) s1 = gemm_swapped(b.qkv.w, D, ln, D, 3 * D + FF, batch, D, 0, wsf, st);
+    int s1 = plan_smallbatch(3 * D + FF, D, 0).splits;
+    if (!(g_debug_skip & 1)) s1 = gemm_smallbatch(b.qkv.w, D, ln, D, 3 * D + FF, batch, D, 0, wsf, st);
     if (s1 < 0) return 1;
     // bias / RoPE / KV-row write / GELU of that stream happen inside the attention kernel (one launch fewer)
     if (!(g_debug_skip & 4) &&
@@ -269,7 +269,7 @@ int text_decode_step(Model& m, bf16* x, const int* pos, int batch, const md_kv& 
                                kv.block_tables, kv.max_blocks, i, xcat, D + FF, st)) return 1;
     // proj(att) and fc2(hid) both land in the residual: one K-concatenated weight stream
     int s2 = pl2.splits_a + pl2.splits_b;
-    if (!(g_debug_skip & 8)) s2 = gemm_swapped_2seg(b.proj.w, D + FF, xcat, D + FF, D, batch, D + FF, D, wsf, st);
+    if (!(g_debug_skip & 8)) s2 = gemm_smallbatch_2seg(b.proj.w, D + FF, xcat, D + FF, D, batch, D + FF, D, wsf, st);
     if (s2 < 0) return 1;
     const bool last = i + 1 == d.txt_layers;
     const Lin& nln = last ? m.txt_post_ln : m.txt[i + 1].ln;
@@ -304,8 +304,8 @@ int lm_head_argmax(Model& m, const bf16* hidden, long long ldh, int prenormed, i
     normed = ln;
     ldn = d.txt_dim;
   }
-  const int used = gemm_swapped(m.lm_head.w, d.txt_dim, normed, ldn, d.vocab, batch, d.txt_dim,
-                                gemm_swapped_splits(d.vocab, d.txt_dim), wsf, st);
+  const int used = gemm_smallbatch(m.lm_head.w, d.txt_dim, normed, ldn, d.vocab, batch, d.txt_dim,
+                                gemm_smallbatch_splits(d.vocab, d.txt_dim), wsf, st);
   if (used < 0) return 1;
   return argmax_logits(wsf, used, batch, d.vocab, m.lm_head.b, 1, mask_id, out_ids, out_stride, out_index,
                        out_margin, out_logits, scratch, st);
@@ -336,8 +336,8 @@ int region_decode(Model& m, int which, const bf16* hidden, long long ldh, int ba
   // mlp(hidden): fc1 + gelu, fc2 (region.py:46-57, 74-93)
   if (small_linear(hidden, ldh, l1, batch, d.reg_inner, d.txt_dim, EPI_BIAS_GELU, nullptr, 0, hid,
                    d.reg_inner, wsf, st)) return 1;
-  const int used = gemm_swapped(l2.w, l2.ld, hid, d.reg_inner, n_out, batch, d.reg_inner,
-                                gemm_swapped_splits(n_out, d.reg_inner), wsf, st);
+  const int used = gemm_smallbatch(l2.w, l2.ld, hid, d.reg_inner, n_out, batch, d.reg_inner,
+                                gemm_smallbatch_splits(n_out, d.reg_inner), wsf, st);
   if (used < 0) return 1;
   if (which == 0)
     return argmax_logits(wsf, used, batch, n_out, l2.b, 1, -1, out_bins, 1, nullptr, nullptr, nullptr, nullptr, st);

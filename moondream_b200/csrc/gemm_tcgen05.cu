@@ -762,10 +762,10 @@ int gemm_rowform(const __nv_bfloat16* A, long long lda, const __nv_bfloat16* W, 
 // that (tiles x splits) fills whole waves of the SMs.  cost = waves x tile_rows x kb is the critical path in
 // units of 128-byte weight rows; ties prefer fewer splits (less partial-sum traffic).
 // kb_divisor > 0 restricts kb to divisors of it.
-SwappedPlan plan_swapped(int n_out, int K, int kb_divisor) {
+StreamPlan plan_smallbatch(int n_out, int K, int kb_divisor) {
   const int k_blocks = (K + BK - 1) / BK;
   const int sms = num_sms();
-  SwappedPlan best{BM, k_blocks, 1};
+  StreamPlan best{BM, k_blocks, 1};
   long long best_cost = -1;
   for (int kb = k_blocks; kb >= 1; --kb) {
     if (kb_divisor > 0 ? (kb > kb_divisor || kb_divisor % kb) : false) continue;
@@ -778,7 +778,7 @@ SwappedPlan plan_swapped(int n_out, int K, int kb_divisor) {
       // critical path in 128-byte weight rows + this SM's share of the fp32 partial-sum traffic
       // (written and re-read once per split, nominal batch 32)
       const long long cost = waves * rows * kb + (1LL * splits * n_out * 32 * 8) / (128LL * sms);
-      if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = SwappedPlan{rows, kb, splits}; }
+      if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = StreamPlan{rows, kb, splits}; }
     }
   }
   return best;
@@ -789,7 +789,7 @@ SwappedPlan plan_swapped(int n_out, int K, int kb_divisor) {
 // With seg_kb > 0 the k-blocks split in two segments (see SmallBatchParams): [0, seg_kb) in pieces of
 // kb_per_split, the rest in pieces of kb_per_split2.  Batches above 128 rows run as consecutive 128-row launches.
 // Returns the number of splits (> 0), -1 on error.
-static int gemm_swapped_impl(const __nv_bfloat16* W, long long ldw, const __nv_bfloat16* X, long long ldx,
+static int gemm_smallbatch_impl(const __nv_bfloat16* W, long long ldw, const __nv_bfloat16* X, long long ldx,
                              int n_out, int batch, int K, int kb_per_split, int tile_n, float* ws,
                              cudaStream_t stream, int seg_kb = 0, int kb_per_split2 = 0) {
   if (n_out <= 0 || batch <= 0 || K <= 0) { set_error("small-batch GEMM: empty problem"); return -1; }
@@ -846,13 +846,13 @@ static int gemm_swapped_impl(const __nv_bfloat16* W, long long ldw, const __nv_b
   return p.k_splits;
 }
 
-int gemm_swapped_splits(int n_out, int K) { return plan_swapped(n_out, K, 0).splits; }
+int gemm_smallbatch_splits(int n_out, int K) { return plan_smallbatch(n_out, K, 0).splits; }
 
-int gemm_swapped(const __nv_bfloat16* W, long long ldw, const __nv_bfloat16* X, long long ldx,
+int gemm_smallbatch(const __nv_bfloat16* W, long long ldw, const __nv_bfloat16* X, long long ldx,
                  int n_out, int batch, int K, int splits, float* ws, cudaStream_t stream) {
-  (void)splits;                                  // the plan decides (callers size ws with gemm_swapped_splits)
-  const SwappedPlan pl = plan_swapped(n_out, K, 0);
-  return gemm_swapped_impl(W, ldw, X, ldx, n_out, batch, K, pl.kb, pl.tile_rows, ws, stream);
+  (void)splits;                                  // the plan decides (callers size ws with gemm_smallbatch_splits)
+  const StreamPlan pl = plan_smallbatch(n_out, K, 0);
+  return gemm_smallbatch_impl(W, ldw, X, ldx, n_out, batch, K, pl.kb, pl.tile_rows, ws, stream);
 }
 
 int gemm_rowform_qkv_rope(const __nv_bfloat16* A, long long lda, const __nv_bfloat16* W, long long ldw, int M,
@@ -892,15 +892,15 @@ int gemm_rowform_qkv_rope(const __nv_bfloat16* A, long long lda, const __nv_bflo
 // tools/decode_timeline.py: the 128-lane activation operand is re-read from shared memory every K = 16 step),
 // so the plan minimises the k-blocks of the longest CTA: full 128-row tiles and many short splits, as long as
 // every CTA is resident at once.
-SwappedPlan2 plan_swapped_2seg(int n_out, int K, int seg_K) {
+StreamPlan2 plan_smallbatch_2seg(int n_out, int K, int seg_K) {
   const int k_blocks = (K + BK - 1) / BK;
   const int ka = seg_K / BK, kbt = k_blocks - ka;
   const int sms = num_sms();
-  SwappedPlan2 best{BM, 1, ka, 1, kbt};
+  StreamPlan2 best{BM, 1, ka, 1, kbt};
   long long best_cost = -1;
   if (g_gemm_debug & 4) {                 // A/B timing: the previous plan (equal splits of seg_K, balanced tile rows)
-    const SwappedPlan old = plan_swapped(n_out, K, ka);
-    return SwappedPlan2{old.tile_rows, ka / old.kb, old.kb, (kbt + old.kb - 1) / old.kb, old.kb};
+    const StreamPlan old = plan_smallbatch(n_out, K, ka);
+    return StreamPlan2{old.tile_rows, ka / old.kb, old.kb, (kbt + old.kb - 1) / old.kb, old.kb};
   }
   for (int rows = BM; rows >= 64; --rows) {
     const int tiles = (n_out + rows - 1) / rows;
@@ -914,20 +914,20 @@ SwappedPlan2 plan_swapped_2seg(int n_out, int K, int seg_K) {
         const int eff_rows = rows > 96 ? rows : 96;              // MMA floor in units of streamed weight rows
         const long long cost = waves * eff_rows * (kba > kbb ? kba : kbb) +
                                (1LL * (sa + sb) * n_out * 32 * 8) / (128LL * sms);
-        if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = SwappedPlan2{rows, sa, kba, sb, kbb}; }
+        if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = StreamPlan2{rows, sa, kba, sb, kbb}; }
       }
     }
   }
   return best;
 }
 
-// same as gemm_swapped for W = [A | B] along K with the split boundaries of plan_swapped_2seg: splits
+// same as gemm_smallbatch for W = [A | B] along K with the split boundaries of plan_smallbatch_2seg: splits
 // [0, splits_a) hold A's partial sums, the rest B's.  Returns the number of splits, -1 on error.
-int gemm_swapped_2seg(const __nv_bfloat16* W, long long ldw, const __nv_bfloat16* X, long long ldx,
+int gemm_smallbatch_2seg(const __nv_bfloat16* W, long long ldw, const __nv_bfloat16* X, long long ldx,
                       int n_out, int batch, int K, int seg_K, float* ws, cudaStream_t stream) {
-  if (seg_K <= 0 || seg_K >= K || seg_K % BK) { set_error("gemm_swapped_2seg: segment boundary must be a multiple of 64 inside K"); return -1; }
-  const SwappedPlan2 pl = plan_swapped_2seg(n_out, K, seg_K);
-  return gemm_swapped_impl(W, ldw, X, ldx, n_out, batch, K, pl.kb_a, pl.tile_rows, ws, stream, seg_K / BK, pl.kb_b);
+  if (seg_K <= 0 || seg_K >= K || seg_K % BK) { set_error("gemm_smallbatch_2seg: segment boundary must be a multiple of 64 inside K"); return -1; }
+  const StreamPlan2 pl = plan_smallbatch_2seg(n_out, K, seg_K);
+  return gemm_smallbatch_impl(W, ldw, X, ldx, n_out, batch, K, pl.kb_a, pl.tile_rows, ws, stream, seg_K / BK, pl.kb_b);
 }
 
 int splitk_epilogue(const float* ws, int splits, int B, int N, int mode, const __nv_bfloat16* bias,

@@ -62,10 +62,10 @@ void gemm_force_cta_group(int cg);
 void gemm_debug_flags(int flags);
 void gemm_profile_enable(int on);
 int gemm_profile_read(double* total_ms, double* total_flops, long long* launches);
-struct SwappedPlan { int tile_rows, kb, splits; };
-SwappedPlan plan_swapped(int n_out, int K, int kb_divisor);
-int gemm_swapped_splits(int n_out, int K);
-int gemm_swapped(const __nv_bfloat16* W, long long ldw, const __nv_bfloat16* X, long long ldx,
+struct StreamPlan { int tile_rows, kb, splits; };
+StreamPlan plan_smallbatch(int n_out, int K, int kb_divisor);
+int gemm_smallbatch_splits(int n_out, int K);
+int gemm_smallbatch(const __nv_bfloat16* W, long long ldw, const __nv_bfloat16* X, long long ldx,
                  int n_out, int batch, int K, int splits, float* ws, cudaStream_t stream);
 // Prefill QKV projection with RoPE and the KV-cache write fused into the GEMM epilogue (text.py:30-43,
 // rope.py:20-48, moondream.py:74-78): output column block -> (q|k|v, head, half-head); row -> (sequence, position).
@@ -83,9 +83,9 @@ struct RopeEpilogue {
 int gemm_rowform_qkv_rope(const __nv_bfloat16* A, long long lda, const __nv_bfloat16* W, long long ldw, int M,
                           int K, const __nv_bfloat16* bias, const RopeEpilogue& epi, cudaStream_t stream);
 // K-concatenated stream W = [A | B] (seg_K = width of A): no split straddles the boundary
-struct SwappedPlan2 { int tile_rows, splits_a, kb_a, splits_b, kb_b; };
-SwappedPlan2 plan_swapped_2seg(int n_out, int K, int seg_K);
-int gemm_swapped_2seg(const __nv_bfloat16* W, long long ldw, const __nv_bfloat16* X, long long ldx,
+struct StreamPlan2 { int tile_rows, splits_a, kb_a, splits_b, kb_b; };
+StreamPlan2 plan_smallbatch_2seg(int n_out, int K, int seg_K);
+int gemm_smallbatch_2seg(const __nv_bfloat16* W, long long ldw, const __nv_bfloat16* X, long long ldx,
                       int n_out, int batch, int K, int seg_K, float* ws, cudaStream_t stream);
 int splitk_epilogue(const float* ws, int splits, int B, int N, int mode, const __nv_bfloat16* bias,
                     const __nv_bfloat16* res, long long ldr, __nv_bfloat16* out, long long ldo,
