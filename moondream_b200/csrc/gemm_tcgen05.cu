@@ -344,12 +344,16 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 //
 // ws[split][b][n] = sum_{k in split} X[b][k] * W[n][k]  (fp32 partials, finished by the consumer kernel).
 //
-// The activations are the MMA's A operand (M = 128 lanes, only `batch` of them meaningful) and the weight tile
-// is the B operand (N = tile_n rounded up to 16, up to 256 rows).  The other orientation (weights as A, the
-// `swapped` form this kernel replaces) leaves the tensor core operand-bound: every K = 16 step re-reads a full
-// 128-row A tile from shared memory at ~32 B/clk, i.e. ~600 clocks per 64-wide k-block whatever the batch,
-// which caps an SM at ~43 GB/s of weights at the power-capped 1.57 GHz clock -- below its share of HBM
-// (measured per k-block with tools/decode_timeline.py).  As the B operand the same bytes cost 2 * N clocks.
+// The activations are the MMA's A operand (M = 128 lanes, only `batch` of them meaningful: the TMA box holds the
+// real rows, the descriptor's remaining rows read whatever follows in shared memory and land in lanes that are
+// never stored) and the weight tile is the B operand (N = tile_n rounded up to 16, up to 256 rows).
+//
+// Measured per k-block with tools/decode_timeline.py: a 64-wide k-block costs ~600 clocks in either orientation
+// when the tile is narrow, because every K = 16 MMA re-reads its 128-row A operand from shared memory at
+// ~32 B/clk.  With the weights as A (the first version of this stream) that made time proportional to k-blocks
+// and independent of tile height (72-row tiles streamed at 4.3 TB/s chip-wide); as the B operand the weight
+// bytes per k-block can grow to 256 rows for the same A-operand cost, which is what the split plans exploit.
+// Halving the A-operand read (M = 64 MMAs, or the activation tile held in TMEM) is the remaining lever.
 //
 // One CTA per (weight-row tile, K split), all resident at once (the plan keeps tiles * splits <= #SMs where
 // it can).  Under programmatic dependent launch the weight tiles of the first ring of stages are requested
