@@ -9,7 +9,7 @@ from __future__ import annotations
 import ctypes
 import math
 from dataclasses import dataclass, field
-from typing import Dict, List, Optional, Sequence, Tuple
+from typing import Callable, Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
 import torch
@@ -456,10 +456,15 @@ class Engine:
                  forced: Optional[Sequence[Sequence[int]]] = None, consume: bool = False,
                  use_graph: bool = True, stop_on_eos: bool = True,
                  prompt_embeds: Optional[torch.Tensor] = None, to_host: bool = True,
-                 prefilled_hidden: Optional[torch.Tensor] = None) -> GenerationResult:
-        """Greedy `_generate_answer` (moondream.py:434-539) for a batch: ragged prompt prefill, first
+                 prefilled_hidden: Optional[torch.Tensor] = None,
+                 sampler: Optional[Callable[[torch.Tensor], torch.Tensor]] = None) -> GenerationResult:
+        """`_generate_answer` (moondream.py:434-539) for a batch: ragged prompt prefill, first
         token from the LM head, then `max_tokens` decode steps (the reference also runs the step after
-        the last emitted token).  Returns the argmax at every step; callers cut at eos."""
+        the last emitted token).  Greedy by default: returns the argmax at every step; callers cut at eos.
+        `sampler` (moondream_b200.sampling.HostSampler) switches to the reference's temperature / top-p
+        sampling (:312-318, :524-530): every step hands its bf16 logits [B, vocab] to the callable, which
+        returns the tokens to feed next; the returned tokens are then the sampled ones.  That path
+        synchronises once per token and does not use the CUDA graph."""
         t, tk = self.cfg.text, self.cfg.tokenizer
         B = len(prefixes)
         assert len(prompts) == B
@@ -491,6 +496,10 @@ class Engine:
                                                      st["x"].stride(0), N.current_stream()), "md_gather_rows_bf16")
             st["step"].zero_()
             st["finished"].zero_()
+            if sampler is not None:
+                if forced is not None:
+                    raise ValueError("generate: `forced` and `sampler` are mutually exclusive")
+                return self._generate_sampled(st, prefixes, lens, B, S, max_tokens, sampler, stop_on_eos, to_host)
             self.lm_head(st["x"], st["preds"], S, mask_id=-1, out_index=None, margins=st["margins"])
             use_forced = forced is not None
             if use_forced:
@@ -536,6 +545,47 @@ class Engine:
             for pages in owned:
                 self.pages.release(pages)
         return GenerationResult(tokens, margins, steps)
+
+    def _generate_sampled(self, st: dict, prefixes: Sequence[PrefixKV], lens: Sequence[int], B: int, S: int,
+                          max_tokens: int, sampler: Callable[[torch.Tensor], torch.Tensor], stop_on_eos: bool,
+                          to_host: bool) -> GenerationResult:
+        """Decode loop of `generate` with the next token chosen by `sampler` from each step's logits.  Uses the
+        teacher-forcing slots: step s consumes forced[:, s], its sampled successor is written to forced[:, s + 1]
+        before the bookkeeping kernel advances.  (The caller holds and releases the sequences' pages.)"""
+        tk = self.cfg.tokenizer
+        lib = self.lib
+        logits = st.get("logits")
+        if logits is None:
+            logits = st["logits"] = torch.empty((B, self.cfg.text.vocab_size), dtype=torch.bfloat16, device=self.device)
+        self.lm_head(st["x"], st["preds"], S, mask_id=-1, out_index=None, margins=st["margins"], logits=logits)
+        tok = sampler(logits).to(torch.int32)
+        done = tok.cpu() == tk.eos_id
+        st["forced"].zero_()
+        st["forced"][:, 0].copy_(tok)
+        st["cur"].copy_(st["forced"][:, 0])
+        st["pos"].copy_(self._i32([prefixes[i].pos + lens[i] for i in range(B)]))
+        kv = self._kv(st["bt"])
+        off = int(lib.md_text_decode_workspace_bytes(self.model, B))
+        steps = 0
+        for s in range(max_tokens):
+            if stop_on_eos and bool(done.all()):
+                break
+            stream = N.current_stream()
+            self.embed(st["cur"], st["x"])
+            N.check(lib.md_text_decode_step(self.model, N.ptr(st["x"]), N.ptr(st["pos"]), B, ctypes.byref(kv),
+                                            N.ptr(st["normed"]), N.ptr(st["ws"]), stream), "md_text_decode_step")
+            self.lm_head(st["normed"], st["preds"], S, mask_id=tk.answer_id, out_index=st["step"],
+                         margins=st["margins"], logits=logits, ws=st["ws"][off:], out_offset=1, prenormed=True)
+            tok = sampler(logits).to(torch.int32)                 # synchronises: device logits -> host -> token ids
+            done |= tok.cpu() == tk.eos_id
+            st["forced"][:, s + 1].copy_(tok)
+            N.check(lib.md_decode_advance(N.ptr(st["cur"]), N.ptr(st["pos"]), N.ptr(st["step"]), N.ptr(st["preds"]),
+                                          N.ptr(st["forced"]), S, B, tk.eos_id, N.ptr(st["finished"]), stream),
+                    "md_decode_advance")
+            steps += 1
+        if to_host:
+            return GenerationResult(st["forced"].to("cpu"), st["margins"].to("cpu"), steps)
+        return GenerationResult(st["forced"].clone(), st["margins"].clone(), steps)
 
     # ------------------------------------------------------------------ region head
     def region_encode(self, which: int, values: torch.Tensor) -> torch.Tensor:

@@ -11,8 +11,9 @@ Deliberate differences from the reference (documented in DESIGN.md):
   * ``settings`` without "variant" is accepted by ``encode_image`` (the reference raises KeyError at
     moondream.py:240-243); LoRA variants (lora.py) need the network and are rejected with
     NotImplementedError when requested.
-  * temperature > 0 (sampling) is "next" (SURVEY.md §8f rank 2): only greedy decoding is implemented;
-    callers must pass ``settings={"temperature": 0}`` or accept the ValueError.
+  * temperature > 0 follows the reference's softmax / top-p / multinomial arithmetic (moondream.py:270-278,
+    312-318) on the host from each step's logits (moondream_b200/sampling.py): functionally the reference's
+    default behaviour, but one synchronisation per token; the CUDA-graph path is the greedy one.
   * ``EncodedImage`` holds KV *pages* (shared, copy-on-write for the partial page) instead of
     cloned tensors; ``.caches`` materialises the reference's per-layer (k, v) view on demand.
 """
@@ -122,15 +123,20 @@ class MoondreamModel:
 
     # ------------------------------------------------------------------ settings
     @staticmethod
-    def _greedy(settings: Optional[dict]):
+    def _text_settings(settings: Optional[dict]):
+        """(max_tokens, sampler) from the reference's TextSamplingSettings (moondream.py:443-454): sampler is None
+        for temperature 0 (greedy, CUDA-graph decode), else the host nucleus sampler."""
         temperature = settings.get("temperature", DEFAULT_TEMPERATURE) if settings else DEFAULT_TEMPERATURE
-        if temperature != 0:
-            raise ValueError("only greedy decoding is implemented: pass settings={'temperature': 0} "
-                             "(nucleus sampling is listed as 'next' in DESIGN.md)")
+        top_p = settings.get("top_p", DEFAULT_TOP_P) if settings else DEFAULT_TOP_P
         if settings and settings.get("variant") is not None:
             raise NotImplementedError("LoRA variants are downloaded from the network by the reference "
                                       "(lora.py:23-40) and are not supported offline")
-        return settings.get("max_tokens", DEFAULT_MAX_TOKENS) if settings else DEFAULT_MAX_TOKENS
+        max_tokens = settings.get("max_tokens", DEFAULT_MAX_TOKENS) if settings else DEFAULT_MAX_TOKENS
+        sampler = None
+        if temperature != 0:
+            from .sampling import HostSampler
+            sampler = HostSampler(temperature, top_p)          # ValueError for a negative temperature
+        return max_tokens, sampler
 
     # ------------------------------------------------------------------ image encoding
     def encode_images(self, images: Sequence[Any]) -> List[EncodedImage]:
@@ -152,10 +158,10 @@ class MoondreamModel:
 
     # ------------------------------------------------------------------ text generation
     def _run(self, encoded: Sequence[EncodedImage], prompts: Sequence[Sequence[int]], max_tokens: int,
-             eos_id: Optional[int] = None, prompt_embeds=None) -> List[List[int]]:
+             eos_id: Optional[int] = None, prompt_embeds=None, sampler=None) -> List[List[int]]:
         eos = self.config.tokenizer.eos_id if eos_id is None else eos_id
         res = self.engine.generate([e._prefix for e in encoded], prompts, max_tokens,
-                                   prompt_embeds=prompt_embeds)
+                                   prompt_embeds=prompt_embeds, sampler=sampler)
         toks = res.tokens.tolist()
         out = []
         for row in toks:
@@ -179,11 +185,17 @@ class MoondreamModel:
             out.append(seq)
         return out
 
-    def _run_images(self, images: Sequence[Any], prompts: Sequence[Sequence[int]], max_tokens: int) -> List[List[int]]:
+    def _run_images(self, images: Sequence[Any], prompts: Sequence[Sequence[int]], max_tokens: int,
+                    sampler=None) -> List[List[int]]:
         """Batched generation straight from raw images: when no image is pre-encoded the image prefix and the
-        prompt are prefilled in one decoder pass (engine.caption_from_crops); otherwise the two-step path."""
-        if any(isinstance(im, EncodedImage) for im in images):
-            return self._run(self.encode_images(images), prompts, max_tokens)
+        prompt are prefilled in one decoder pass (engine.caption_from_crops); otherwise (and when sampling)
+        the two-step path."""
+        if sampler is not None or any(isinstance(im, EncodedImage) for im in images):
+            rows: List[List[int]] = []
+            for lo in range(0, len(images), self._max_batch):
+                rows += self._run(self.encode_images(images[lo: lo + self._max_batch]),
+                                  prompts[lo: lo + self._max_batch], max_tokens, sampler=sampler)
+            return rows
         out: List[List[int]] = []
         for lo in range(0, len(images), self._max_batch):
             arrs = [_as_array(im) for im in images[lo: lo + self._max_batch]]
@@ -228,8 +240,8 @@ class MoondreamModel:
             raise NotImplementedError("Model does not support captioning.")
         if length not in tpl:
             raise ValueError(f"Model does not support caption length '{length}'.")
-        max_tokens = self._greedy(settings)
-        toks = self._run_images(images, [tpl[length]] * len(images), max_tokens)
+        max_tokens, sampler = self._text_settings(settings)
+        toks = self._run_images(images, [tpl[length]] * len(images), max_tokens, sampler)
         return [{"caption": "".join(self._stream_text(t))} for t in toks]
 
     def caption(self, image, length: Literal["normal", "short", "long"] = "normal", stream: bool = False,
@@ -239,9 +251,9 @@ class MoondreamModel:
             raise NotImplementedError("Model does not support captioning.")
         if length not in tpl:
             raise ValueError(f"Model does not support caption length '{length}'.")
-        max_tokens = self._greedy(settings)
+        max_tokens, sampler = self._text_settings(settings)
         enc = self.encode_image(image, settings)
-        toks = self._run([enc], [tpl[length]], max_tokens)[0]
+        toks = self._run([enc], [tpl[length]], max_tokens, sampler=sampler)[0]
         if stream:
             return {"caption": self._stream_text(toks)}
         return {"caption": "".join(self._stream_text(toks))}
@@ -261,9 +273,9 @@ class MoondreamModel:
                     settings: Optional[dict] = None) -> List[Dict[str, str]]:
         if self.config.tokenizer.templates["query"] is None:
             raise NotImplementedError("Model does not support querying.")
-        max_tokens = self._greedy(settings)
+        max_tokens, sampler = self._text_settings(settings)
         prompts = [self._query_prompt(q, None, False) for q in questions]
-        toks = self._run_images(images, prompts, max_tokens)
+        toks = self._run_images(images, prompts, max_tokens, sampler)
         return [{"answer": "".join(self._stream_text(t))} for t in toks]
 
     def query(self, image=None, question: str = None, reasoning: bool = False,
@@ -281,13 +293,13 @@ class MoondreamModel:
         if image is None:
             raise NotImplementedError("text-only query (pure causal mask, moondream.py:565-574) is "
                                       "listed as 'next' in DESIGN.md")
-        max_tokens = self._greedy(settings)
+        max_tokens, sampler = self._text_settings(settings)
         enc = self.encode_image(image, settings)
         prompt = self._query_prompt(question, spatial_refs, False)
         embeds = None
         if spatial_refs:
             embeds = self._prompt_embeds_with_refs(prompt, spatial_refs)
-        toks = self._run([enc], [prompt], max_tokens, prompt_embeds=embeds)[0]
+        toks = self._run([enc], [prompt], max_tokens, prompt_embeds=embeds, sampler=sampler)[0]
         if stream:
             return {"answer": self._stream_text(toks)}
         return {"answer": "".join(self._stream_text(toks))}

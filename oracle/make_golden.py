@@ -75,6 +75,30 @@ def main():
                "torch": torch.__version__, "cases": cases},
               open(os.path.join(OUT, "tiny_reference.json"), "w"), indent=1)
 
+    # nucleus sampling (moondream.py:270-278, 312-318, 524-530): the reference's tokens under a fixed global seed
+    SAMPLING = [("single_crop", 0, 378, 378, 5, 0.5, 0.3, 1), ("single_crop_hot", 0, 378, 378, 5, 1.0, 0.9, 2),
+                ("multi_crop_hot", 1, 500, 700, 9, 2.0, 0.5, 3)]
+    sampled = []
+    for name, idx, h, w, plen, temp, top_p, seed in SAMPLING:
+        img = synth.synthetic_image(idx, h, w)
+        prompt = synth.synthetic_prompt(idx, plen, cfg.text.vocab_size)
+        with torch.inference_mode():
+            enc = ref.encode_image(Image.fromarray(img))
+        ref.load_encoded_image(enc)
+        torch.manual_seed(seed)
+        text = "".join(ref._generate_answer(torch.tensor([prompt]), enc.pos,
+                                            {"temperature": temp, "top_p": top_p, "max_tokens": 12}))
+        tokens = R.tokens_from_text(text)
+        torch.manual_seed(seed)
+        gen = orc.generate(orc.encode_image(img), prompt, 12, temperature=temp, top_p=top_p)
+        assert gen.tokens == tokens, (name, gen.tokens, tokens)
+        sampled.append({"name": name, "image_index": idx, "height": h, "width": w, "prompt": prompt,
+                        "temperature": temp, "top_p": top_p, "seed": seed, "tokens": tokens})
+        print(name, temp, top_p, tokens[:8])
+    json.dump({"generator": "oracle/make_golden.py (unmodified reference, tiny preset, torch.manual_seed(seed) before "
+                            "_generate_answer)", "torch": torch.__version__, "cases": sampled},
+              open(os.path.join(OUT, "tiny_sampling.json"), "w"), indent=1)
+
     hashes = {}
     for preset in ("tiny", "moondream-0.5b"):
         c = C.preset(preset)

@@ -331,9 +331,27 @@ class OracleModel:
         ulp = 2.0 ** (math.floor(math.log2(mag)) - 7)
         return float(top[0] - top[1]) / ulp
 
+    @staticmethod
+    def next_token(logits: Tensor, temperature: float, top_p: float) -> int:
+        """moondream.py:312-318 / :524-530: argmax at temperature 0, else softmax(logits / T) -> `_apply_top_p`
+        (:270-278: sort descending, drop tokens whose preceding mass exceeds top_p, renormalise, scatter back)
+        -> torch.multinomial on the global RNG, all in the logits' dtype."""
+        if temperature == 0:
+            return int(torch.argmax(logits, dim=-1).item())
+        p = torch.softmax(logits / temperature, dim=-1)
+        srt, idx = torch.sort(p, dim=-1, descending=True)
+        csum = torch.cumsum(srt, dim=-1)
+        srt[csum - srt > top_p] = 0.0
+        srt.div_(srt.sum(dim=-1, keepdim=True))
+        kept = torch.zeros_like(p)
+        kept.scatter_(dim=-1, index=idx, src=srt)
+        return int(torch.multinomial(kept, num_samples=1).item())
+
     def generate(self, enc: Encoded, prompt: Sequence[int], max_tokens: int,
-                 forced: Optional[Sequence[int]] = None) -> Generation:
-        """Greedy ``_generate_answer`` (moondream.py:434-539) reduced to token ids: prompt prefill,
+                 forced: Optional[Sequence[int]] = None, temperature: float = 0.0,
+                 top_p: float = 0.3) -> Generation:
+        """``_generate_answer`` (moondream.py:434-539) reduced to token ids (greedy unless temperature > 0,
+        in which case `predicted` holds the sampled tokens and the margins still describe the argmax): prompt prefill,
         then one decoder step per emitted token; ``answer_id`` is masked from the 2nd token on
         (:517), stop on eos (:481-483).  Note the reference runs the decoder once more after the
         last emitted token (its result is discarded); that trailing step is reproduced.
@@ -343,7 +361,7 @@ class OracleModel:
         logits, hidden, nxt, pos = self.prefill_prompt(prompt, enc.pos)
         out = Generation([], [], [], margin_ulps=[])
         n = 0
-        pred = int(nxt.item())
+        pred = int(nxt.item()) if temperature == 0 else self.next_token(logits, temperature, top_p)
         margin = self._margin(logits)
         ulps = self._margin_ulps(logits)
         while True:
@@ -359,7 +377,7 @@ class OracleModel:
             logits, hidden = self.decode_one(self.embed(torch.tensor([[tok]], device=self.device)), pos)
             logits[:, tk.answer_id] = float("-inf")
             pos += 1
-            pred = int(torch.argmax(logits, dim=-1).item())
+            pred = self.next_token(logits, temperature, top_p)
             margin = self._margin(logits)
             ulps = self._margin_ulps(logits)
             n += 1

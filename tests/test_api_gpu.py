@@ -93,7 +93,7 @@ def test_error_behaviour_matches_the_reference(api):
     with pytest.raises(ValueError):
         model.caption(img, "poetic", settings={"temperature": 0})  # :634-635
     with pytest.raises(ValueError):
-        model.caption(img, "short")                               # default temperature 0.5: sampling not implemented
+        model.caption(img, "short", settings={"temperature": -1.0})
     with pytest.raises(NotImplementedError):
         model.caption(img, "short", settings={"temperature": 0, "variant": "foo"})
 
@@ -105,3 +105,32 @@ def test_spatial_refs_query_runs(api):
     img = synth.synthetic_image(2, 378, 378)
     out = model.query(img, "15 16", spatial_refs=[(0.25, 0.75), (0.1, 0.2, 0.5, 0.9)], settings={"temperature": 0, "max_tokens": 4})
     assert isinstance(out["answer"], str) and len(_ids(out["answer"])) <= 4
+
+
+def test_sampling_settings(api):
+    """temperature / top_p (moondream.py:270-278, 312-318, 524-530): the default settings sample; the limit
+    that makes sampling deterministic must reproduce the greedy tokens; a seed must reproduce itself."""
+    from moondream_b200 import synth
+
+    cfg, model, orc = api
+    img = synth.synthetic_image(3, 378, 378)        # argmax margins of its first 5 caption tokens: 9..31 bf16 ulps
+    enc = model.encode_image(img)
+    tpl = cfg.tokenizer.templates["caption"]["short"]
+    gen = orc.generate(orc.encode_image(img), tpl, 5)
+    greedy = _ids(model.caption(enc, "short", settings={"temperature": 0, "max_tokens": 5})["caption"])
+    _agree(greedy, gen, "greedy")
+    # top_p -> 0 keeps only the most likely token (the one that crosses the threshold is kept)
+    nucleus = _ids(model.caption(enc, "short", settings={"temperature": 1.0, "top_p": 1e-6, "max_tokens": 5})["caption"])
+    _agree(nucleus, gen, "nucleus")
+    assert nucleus == greedy, (nucleus, greedy)
+    torch.manual_seed(7)
+    a = _ids(model.caption(enc, "short", settings={"temperature": 1.5, "top_p": 0.95, "max_tokens": 8})["caption"])
+    torch.manual_seed(7)
+    b = _ids(model.caption(enc, "short", settings={"temperature": 1.5, "top_p": 0.95, "max_tokens": 8})["caption"])
+    assert a == b and all(0 <= t < cfg.text.vocab_size for t in a), (a, b)
+    out = model.caption(img, "short", settings={"max_tokens": 6})          # reference defaults: temperature 0.5, top_p 0.3
+    assert isinstance(out["caption"], str)
+    q = model.query(enc, "15 16", settings={"temperature": 0.7, "max_tokens": 5})
+    assert isinstance(q["answer"], str) and len(_ids(q["answer"])) <= 5
+    both = model.caption_batch([enc, img], "short", settings={"temperature": 0.7, "max_tokens": 4})
+    assert len(both) == 2 and all(isinstance(o["caption"], str) for o in both)
