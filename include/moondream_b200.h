@@ -120,7 +120,8 @@ void md_debug_set_pdl(int enable);
  * bit0 [qkv;fc1] GEMM, bit1 its epilogue, bit2 attention, bit3 [proj|fc2] GEMM, bit4 residual+LN epilogue. */
 void md_debug_skip_decode_kernels(int mask);
 /* Timing experiments only, small-batch weight stream:
- * bit2 previous split plan of the [proj | fc2] stream (equal splits).  Other bits are ignored. */
+ * bit2 previous split plan of the [proj | fc2] stream (equal splits); bit6 M = 64 MMAs for batches <= 64
+ * (experimental, not yet validated on hardware).  Other bits are ignored. */
 void md_debug_gemm(int flags);
 /* Profiling only: while `records` is non-NULL every CTA of the decode-step kernels (weight-stream GEMMs, decode
  * attention, residual+LayerNorm epilogue) appends one record of 6 uint64 to records[capacity][6]:

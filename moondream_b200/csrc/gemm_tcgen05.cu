@@ -374,6 +374,10 @@ struct SmallBatchParams {
   float* ws;
 };
 
+// MROWS = 128 is the shipped form.  MROWS = 64 (batch <= 64; selected by md_debug_gemm bit 6 until it has been
+// validated on hardware) issues M = 64 MMAs: half the A-operand read per K = 16 step, accumulator rows
+// 16q .. 16q+15 in lanes 0..15 of TMEM lane quadrant q (the 1-CTA M = 64 data-path layout).
+template <int MROWS>
 __global__ void __launch_bounds__(kSbThreads, 1)
 smallbatch_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
                        const SmallBatchParams p) {
@@ -450,7 +454,7 @@ smallbatch_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      const uint32_t idesc = make_idesc_bf16_f32(BM, p.n_mma);
+      const uint32_t idesc = make_idesc_bf16_f32(MROWS, p.n_mma);
       int stage = 0;
       uint32_t phase = 0;
       for (int j = 0; j < nk; ++j) {
@@ -470,11 +474,13 @@ smallbatch_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
       umma_commit(tmem_full);
     }
   } else if (warp >= 4) {
-    // lanes of TMEM = rows of the activation tile: warp q owns batch rows 32q .. 32q+31
+    // lanes of TMEM = rows of the activation tile: warp q owns batch rows 32q .. 32q+31 (M = 128) or
+    // 16q .. 16q+15 in its first 16 lanes (M = 64)
+    constexpr int kRowsPerWarp = MROWS / 4;
     const int q = warp - 4;
     pdl_wait();                              // ws is still being read by the predecessor's consumers
-    if (q * 32 < p.batch) {
-      const int b = q * 32 + lane;
+    if (q * kRowsPerWarp < p.batch) {
+      const int b = (lane < kRowsPerWarp) ? q * kRowsPerWarp + lane : p.batch;   // surplus lanes store nothing
       mbar_wait(tmem_full, 0);
       tc_fence_after();
       if (tl && threadIdx.x == 128) tl_s[3] = tl_now();       // accumulator complete
@@ -823,9 +829,16 @@ static int gemm_smallbatch_impl(const __nv_bfloat16* W, long long ldw, const __n
   constexpr int kSbSmemMax = 227 * 1024 - 1024;      // leave room for the kernel's few static __shared__ words
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(smallbatch_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSbSmemMax);
+    cudaError_t e = cudaFuncSetAttribute(smallbatch_gemm_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSbSmemMax);
     if (e != cudaSuccess) { set_error(cudaGetErrorString(e)); return -1; }
     configured = true;
+  }
+  const bool m64 = (g_gemm_debug & 64) && batch <= 64;     // experimental until validated on hardware
+  static bool configured64 = false;
+  if (m64 && !configured64) {
+    cudaError_t e = cudaFuncSetAttribute(smallbatch_gemm_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSbSmemMax);
+    if (e != cudaSuccess) { set_error(cudaGetErrorString(e)); return -1; }
+    configured64 = true;
   }
   CUtensorMap tW;
   if (make_tmap_bf16_2d(&tW, W, n_out, K, ldw, tile_n)) return -1;
@@ -843,8 +856,10 @@ static int gemm_smallbatch_impl(const __nv_bfloat16* W, long long ldw, const __n
     if (make_tmap_bf16_2d(&tX, X + static_cast<long long>(b0) * ldx, p.batch, K, ldx, a_rows)) return -1;
     const int smem_bytes = p.stages * p.stage_bytes + kSbTailPad + bar_bytes + 1024;
     count_launch();
-    cudaError_t e = launch_k(smallbatch_gemm_kernel, dim3(n_tiles * p.k_splits), dim3(kSbThreads),
-                             static_cast<size_t>(smem_bytes), stream, tX, tW, p);
+    cudaError_t e = m64 ? launch_k(smallbatch_gemm_kernel<64>, dim3(n_tiles * p.k_splits), dim3(kSbThreads),
+                                   static_cast<size_t>(smem_bytes), stream, tX, tW, p)
+                        : launch_k(smallbatch_gemm_kernel<128>, dim3(n_tiles * p.k_splits), dim3(kSbThreads),
+                                   static_cast<size_t>(smem_bytes), stream, tX, tW, p);
     if (e != cudaSuccess) { set_error(cudaGetErrorString(e)); return -1; }
   }
   return p.k_splits;

@@ -110,3 +110,23 @@ def test_linear_small_batch(B, N, K, mode):
     y = ops.linear_small_batch(x, w, b, epilogue=mode, residual=res)
     torch.cuda.synchronize()
     _close(y, _ref(x, w, b, mode, res), f"small-batch {B}x{N}x{K} mode {mode}")
+
+
+@pytest.mark.skipif(__import__("os").environ.get("MD_EXPERIMENTAL") != "1",
+                    reason="staged experiment (M = 64 MMAs in the small-batch stream): not yet validated on hardware; "
+                           "run with MD_EXPERIMENTAL=1")
+@pytest.mark.parametrize("B,N,K", [(32, 6144, 2048), (5, 1024, 8192), (64, 8192, 2048), (17, 1032, 264)])
+def test_linear_small_batch_m64_experimental(B, N, K):
+    from moondream_b200 import _native as N_, ops
+
+    g = torch.Generator(device="cuda").manual_seed(B + N + K)
+    x = torch.randn(B, K, device="cuda", generator=g).bfloat16()
+    w = (torch.randn(N, K, device="cuda", generator=g) / K ** 0.5).bfloat16()
+    b = torch.randn(N, device="cuda", generator=g).bfloat16()
+    N_.lib().md_debug_gemm(64)
+    try:
+        y = ops.linear_small_batch(x, w, b, epilogue=0)
+        torch.cuda.synchronize()
+    finally:
+        N_.lib().md_debug_gemm(0)
+    _close(y, _ref(x, w, b, 0, None), f"small-batch M=64 {B}x{N}x{K}")
