@@ -99,6 +99,33 @@ def main():
                             "_generate_answer)", "torch": torch.__version__, "cases": sampled},
               open(os.path.join(OUT, "tiny_sampling.json"), "w"), indent=1)
 
+    # streaming detokenisation (moondream.py:476-537): the chunks the reference's generator yields for token
+    # sequences it sampled itself, with a tokenizer whose pieces hit every flush rule
+    stream_cases = []
+    img = synth.synthetic_image(0, 378, 378)
+    with torch.inference_mode():
+        enc = ref.encode_image(Image.fromarray(img))
+    stub = ref.tokenizer
+    for seed, temp in ((11, 1.0), (12, 2.0), (13, 3.0), (14, 0.0)):
+        prompt = synth.synthetic_prompt(seed, 4, cfg.text.vocab_size)
+        settings = {"temperature": temp, "top_p": 0.95, "max_tokens": 40}
+        ref.load_encoded_image(enc)
+        torch.manual_seed(seed)
+        tokens = R.tokens_from_text("".join(ref._generate_answer(torch.tensor([prompt]), enc.pos, settings)))
+        ref.tokenizer = R.PieceTokenizer()
+        try:
+            ref.load_encoded_image(enc)
+            torch.manual_seed(seed)
+            chunks = list(ref._generate_answer(torch.tensor([prompt]), enc.pos, settings))
+        finally:
+            ref.tokenizer = stub
+        assert "".join(chunks) == R.PieceTokenizer().decode(tokens)
+        stream_cases.append({"seed": seed, "temperature": temp, "tokens": tokens, "chunks": chunks})
+        print("stream", seed, len(tokens), len(chunks))
+    json.dump({"generator": "oracle/make_golden.py (unmodified reference generator, oracle.reference_shim.PieceTokenizer)",
+               "pieces": R.PieceTokenizer.PIECES, "cases": stream_cases},
+              open(os.path.join(OUT, "streaming.json"), "w"), indent=1, ensure_ascii=True)
+
     hashes = {}
     for preset in ("tiny", "moondream-0.5b"):
         c = C.preset(preset)

@@ -49,6 +49,23 @@ class StubTokenizer:
         return "".join(f"{int(i)} " for i in ids)
 
 
+class PieceTokenizer:
+    """A tokenizer whose pieces exercise every flush rule of the reference's streaming detokeniser
+    (moondream.py:476-537): words with leading spaces, bare suffixes, newlines, CJK characters, punctuation."""
+
+    PIECES = [" the", " cat", "s", " sat", "\n", "\u6f22", "\u5b57", " on", ",", " a", " mat", ".", "\n\n",
+              " \u65e5\u672c", "\u00e9", " ", "ing", " x\n", "\u3400", " end"]
+
+    def __init__(self, pieces=None):
+        self.pieces = list(pieces) if pieces is not None else list(self.PIECES)
+
+    def encode(self, text: str):
+        return _Enc([sum(text.encode()) % len(self.pieces)])
+
+    def decode(self, ids: List[int]) -> str:
+        return "".join(self.pieces[int(i) % len(self.pieces)] for i in ids)
+
+
 def load_reference_model(cfg, state_dict: Dict[str, torch.Tensor]):
     """Construct the reference MoondreamModel (CPU, bf16) with `state_dict` loaded."""
     if not reference_available():
