@@ -126,6 +126,39 @@ def main():
                "pieces": R.PieceTokenizer.PIECES, "cases": stream_cases},
               open(os.path.join(OUT, "streaming.json"), "w"), indent=1, ensure_ascii=True)
 
+    # prompt assembly (moondream.py:541-604 query incl. spatial refs and the duplicated suffix, :625-651 caption,
+    # :735-829 detect / point): the token ids the reference actually hands to its prefill
+    seen = []
+    orig_prefill = ref._prefill_prompt
+
+    def recording_prefill(prompt_tokens, pos, *a, **k):
+        seen.append((prompt_tokens.flatten().tolist(), int(pos)))
+        return orig_prefill(prompt_tokens, pos, *a, **k)
+
+    ref._prefill_prompt = recording_prefill
+    prompt_cases = []
+    try:
+        greedy = {"temperature": 0, "max_tokens": 1}
+        calls = [("caption_short", lambda: ref.caption(enc, "short", settings=greedy), {"length": "short"}),
+                 ("caption_normal", lambda: ref.caption(enc, "normal", settings=greedy), {"length": "normal"}),
+                 ("query", lambda: ref.query(enc, "11 12 13", settings=greedy), {"question": "11 12 13"}),
+                 ("query_refs", lambda: ref.query(enc, "15 16", spatial_refs=[(0.25, 0.75), (0.1, 0.2, 0.5, 0.9)],
+                                                  settings=greedy),
+                  {"question": "15 16", "spatial_refs": [[0.25, 0.75], [0.1, 0.2, 0.5, 0.9]]}),
+                 ("detect", lambda: ref.detect(enc, "17 23", settings={"max_objects": 1}), {"object": "17 23"}),
+                 ("point", lambda: ref.point(enc, "17 23", settings={"max_objects": 1}), {"object": "17 23"})]
+        for name, call, args in calls:
+            seen.clear()
+            call()
+            assert len(seen) == 1, (name, len(seen))
+            prompt_cases.append({"name": name, "args": args, "prompt": seen[0][0], "pos": seen[0][1]})
+            print("prompt", name, seen[0][0])
+    finally:
+        ref._prefill_prompt = orig_prefill
+    json.dump({"generator": "oracle/make_golden.py (prompt tokens the unmodified reference passes to _prefill_prompt; "
+                            "StubTokenizer)", "cases": prompt_cases},
+              open(os.path.join(OUT, "prompts.json"), "w"), indent=1)
+
     hashes = {}
     for preset in ("tiny", "moondream-0.5b"):
         c = C.preset(preset)
