@@ -102,3 +102,46 @@ def test_prepare_weights_pads_for_tma_without_changing_values():
     assert f1.shape == (2696, 720) and b1.shape == (2696,) and f2.shape == (720, 2696)
     assert f1[2690:].abs().max() == 0 and b1[2690:].abs().max() == 0 and f2[:, 2690:].abs().max() == 0
     assert torch.equal(f2[:, :2690], sd["vision.blocks.0.mlp.fc2.weight"])
+
+
+@pytest.mark.parametrize("layout,fmt", [("legacy", "safetensors"), ("legacy_orig_mod", "pt"), ("model_prefixed", "safetensors"),
+                                        ("canonical", "pt")])
+def test_loader_agrees_with_the_reference_loader(tmp_path, layout, fmt):
+    """Build container only: the same file goes through the unmodified reference's `load_weights_into_model`
+    (weights.py:120-171) into the reference model and through ours; every parameter must come out identical, which pins
+    the legacy key map (and the transposed region feature tensors) to the reference rather than to this repo's reading of it."""
+    from oracle import reference_shim as R
+
+    if not R.reference_available():
+        pytest.skip("/root/reference is not present on this box")
+    import sys
+
+    from safetensors.torch import save_file
+
+    cfg = C.tiny()
+    sd = synth.synthetic_state_dict(cfg, 2)
+    if layout == "canonical":
+        tensors = dict(sd)
+    elif layout == "model_prefixed":
+        tensors = {"model." + k: v for k, v in sd.items()}
+    else:
+        tensors = _legacy_dict(cfg, sd)
+        if layout == "legacy_orig_mod":
+            tensors = {k.replace("text_model.", "text_model._orig_mod.", 1): v for k, v in tensors.items()}
+    path = str(tmp_path / ("w." + ("safetensors" if fmt == "safetensors" else "pt")))
+    if fmt == "safetensors":
+        save_file({k: v.contiguous() for k, v in tensors.items()}, path)
+    else:
+        torch.save(tensors, path)
+
+    ref = R.load_reference_model(cfg, synth.synthetic_state_dict(cfg, 5))      # different weights: must be overwritten
+    sys.path.insert(0, R.REFERENCE_ROOT)
+    from moondream.torch.weights import load_weights_into_model as ref_load
+
+    ref_load(path, ref)
+    theirs = {k: v for k, v in ref.state_dict().items() if "kv_cache" not in k}
+    ours = W.load_state_dict_from_file(path, cfg)
+    assert set(ours) == set(sd)
+    for k in sd:
+        assert k in theirs, k
+        assert torch.equal(theirs[k], sd[k]) and torch.equal(ours[k], sd[k]), k
