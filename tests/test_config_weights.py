@@ -22,6 +22,25 @@ def test_config_defaults_match_reference_values():
     c.validate()
 
 
+def test_config_dict_equals_the_reference_config_dict():
+    """Build container only: `MoondreamConfig().to_dict()` (config.py:75-94) key for key, and a dict produced by the
+    reference's config loads into ours (the `from_dict` a maintainer would feed with the reference's config JSONs)."""
+    from oracle import reference_shim as R
+
+    if not R.reference_available():
+        pytest.skip("/root/reference is not present on this box")
+    import sys
+
+    sys.path.insert(0, R.REFERENCE_ROOT)
+    from moondream.torch.config import MoondreamConfig as RefConfig
+
+    ref = RefConfig().to_dict()
+    assert C.MoondreamConfig().to_dict() == ref
+    assert C.MoondreamConfig.from_dict(json.loads(json.dumps(ref))) == C.MoondreamConfig()
+    small = C.moondream_0_5b().to_dict()
+    assert RefConfig.from_dict(small).to_dict() == small
+
+
 def test_config_dict_round_trip_and_partial_dict():
     c = C.moondream_0_5b()
     d = json.loads(json.dumps(c.to_dict()))
