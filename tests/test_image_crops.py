@@ -65,3 +65,40 @@ def test_select_tiling_properties():
         h, w = int(rng.integers(1, 4000)), int(rng.integers(1, 4000))
         th, tw = select_tiling(h, w, 266, 12)
         assert th >= 1 and tw >= 1 and th * tw <= 12
+
+
+def test_random_sizes_against_the_oracle_and_the_reference():
+    """Ragged sizes, extreme aspect ratios and every max_crops: product == oracle restatement bit for bit, and, in the
+    build container, == the unmodified reference (`image_crops.py:58-167`, PIL-Lanczos branch); margins other than the
+    default too.  Reconstruction of per-crop index maps must tile the stitched grid without holes."""
+    from moondream_b200 import synth
+    from oracle import reference_shim as R
+    from oracle.moondream_oracle import overlap_crops
+
+    ref_crop = None
+    if R.reference_available():
+        import sys
+
+        sys.path.insert(0, R.REFERENCE_ROOT)
+        from moondream.torch.image_crops import overlap_crop_image as ref_crop
+    rng = np.random.default_rng(123)
+    sizes = [(1, 1), (1, 900), (900, 1), (377, 379), (379, 377), (266, 267), (1200, 90)]
+    sizes += [(int(rng.integers(2, 1100)), int(rng.integers(2, 1100))) for _ in range(14)]
+    for n, (h, w) in enumerate(sizes):
+        max_crops = int(rng.integers(1, 13))
+        margin = 4 if n % 3 else int(rng.integers(1, 7))
+        img = synth.synthetic_image(1000 + n, h, w)
+        out = overlap_crop_image(img, overlap_margin=margin, max_crops=max_crops)
+        th, tw = out["tiling"]
+        assert out["crops"].dtype == np.uint8 and out["crops"].shape == (1 + th * tw, 378, 378, 3) and th * tw <= max_crops
+        mine, tiling = overlap_crops(img, margin, max_crops)
+        assert tuple(tiling) == (th, tw) and np.array_equal(mine, out["crops"]), (h, w, max_crops, margin)
+        if ref_crop is not None:
+            theirs = ref_crop(img, overlap_margin=margin, max_crops=max_crops)
+            assert tuple(theirs["tiling"]) == (th, tw) and np.array_equal(theirs["crops"], out["crops"]), (h, w)
+        # stitching per-crop constant maps: every output cell is owned by exactly one crop (no holes, no NaNs)
+        grid = 27
+        feats = [torch.full((grid, grid, 1), float(i)) for i in range(th * tw)]
+        rec = reconstruct_from_crops(feats, (th, tw), patch_size=1, overlap_margin=margin)
+        assert rec.shape[:2] == (th * (grid - 2 * margin) + 2 * margin, tw * (grid - 2 * margin) + 2 * margin)
+        assert set(rec.unique().tolist()) == set(float(i) for i in range(th * tw))
