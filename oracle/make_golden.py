@@ -159,6 +159,45 @@ def main():
                             "StubTokenizer)", "cases": prompt_cases},
               open(os.path.join(OUT, "prompts.json"), "w"), indent=1)
 
+    # query with spatial references (moondream.py:293-301, region.py:96-136): the reference's answer tokens, plus the
+    # rows of the prompt embedding its region encoders produced (taken from the oracle after asserting bit equality
+    # of the prefill logits with the reference's)
+    tk = cfg.tokenizer
+    ref_cases = []
+    img = synth.synthetic_image(2, 500, 700)
+    with torch.inference_mode():
+        enc = ref.encode_image(Image.fromarray(img))
+    o_enc = orc.encode_image(img)
+    got = []
+    orig_prefill = ref._prefill_prompt
+
+    def capture(prompt_tokens, pos, *a, **k):
+        out = orig_prefill(prompt_tokens, pos, *a, **k)
+        got.append((prompt_tokens.flatten().tolist(), out[0].clone()))
+        return out
+
+    ref._prefill_prompt = capture
+    try:
+        for refs in ([(0.25, 0.75)], [(0.1, 0.2, 0.5, 0.9)], [(0.25, 0.75), (0.1, 0.2, 0.5, 0.9), (0.6, 0.6)]):
+            got.clear()
+            text = ref.query(enc, "15 16", spatial_refs=refs, settings={"temperature": 0, "max_tokens": 8})["answer"]
+            prompt, ref_logits = got[0]
+            emb = orc.spatial_prompt_embeds(prompt, refs)
+            orc.load_encoded(o_enc)
+            assert torch.equal(orc.prefill_prompt(prompt, o_enc.pos, emb)[0], ref_logits)
+            gen = orc.generate(o_enc, prompt, 8, spatial_refs=refs)
+            assert gen.tokens == R.tokens_from_text(text)
+            rows = [i for i, t in enumerate(prompt) if t in (tk.coord_id, tk.size_id)]
+            ref_cases.append({"spatial_refs": [list(r) for r in refs], "question": "15 16", "prompt": prompt,
+                              "tokens": gen.tokens, "margin_ulps": gen.margin_ulps, "rows": rows,
+                              "row_embeds": emb[0, rows].float().tolist()})
+            print("refs", refs, gen.tokens[:4])
+    finally:
+        ref._prefill_prompt = orig_prefill
+    json.dump({"generator": "oracle/make_golden.py (unmodified reference query(spatial_refs=...); embedding rows from the "
+                            "oracle after bit-equality of the prefill logits)", "image": [2, 500, 700], "cases": ref_cases},
+              open(os.path.join(OUT, "tiny_spatial_refs.json"), "w"), indent=1)
+
     hashes = {}
     for preset in ("tiny", "moondream-0.5b"):
         c = C.preset(preset)

@@ -298,6 +298,27 @@ class OracleModel:
             return enc, img_emb, hidden
         return enc
 
+    def spatial_prompt_embeds(self, prompt: Sequence[int], spatial_refs) -> Tensor:
+        """Prompt embedding with the coord / size placeholder tokens replaced by region encodings
+        (moondream.py:293-301 over region.py:96-136 `encode_spatial_refs`): a point contributes (x, y), a box its
+        centre (x_c, y_c) and its (width, height); coordinates are encoded one scalar at a time, sizes as pairs."""
+        tk = self.cfg.tokenizer
+        coords, sizes = [], []
+        for ref in spatial_refs:
+            if len(ref) == 2:
+                coords += [ref[0], ref[1]]
+            else:
+                coords += [(ref[0] + ref[2]) / 2, (ref[1] + ref[3]) / 2]
+                sizes.append([ref[2] - ref[0], ref[3] - ref[1]])
+        ids = torch.tensor([list(prompt)], device=self.device)
+        with torch.no_grad():
+            x = self.embed(ids)
+            c = torch.tensor(coords, device=self.device, dtype=self.dtype).view(-1, 1)
+            x[ids == tk.coord_id] = self.encode_coordinate(c)
+            if sizes:
+                x[ids == tk.size_id] = self.encode_size(torch.tensor(sizes, device=self.device, dtype=self.dtype))
+        return x
+
     def prefill_prompt(self, prompt: Sequence[int], pos: int, embeds: Optional[Tensor] = None):
         """moondream.py:280-321 with temperature == 0: returns (logits, hidden, next_token, pos)."""
         with torch.no_grad():
@@ -349,7 +370,7 @@ class OracleModel:
 
     def generate(self, enc: Encoded, prompt: Sequence[int], max_tokens: int,
                  forced: Optional[Sequence[int]] = None, temperature: float = 0.0,
-                 top_p: float = 0.3) -> Generation:
+                 top_p: float = 0.3, spatial_refs=None) -> Generation:
         """``_generate_answer`` (moondream.py:434-539) reduced to token ids (greedy unless temperature > 0,
         in which case `predicted` holds the sampled tokens and the margins still describe the argmax): prompt prefill,
         then one decoder step per emitted token; ``answer_id`` is masked from the 2nd token on
@@ -358,7 +379,8 @@ class OracleModel:
         `forced`: teacher forcing — feed these tokens instead of the argmax (records the argmax)."""
         tk = self.cfg.tokenizer
         self.load_encoded(enc)
-        logits, hidden, nxt, pos = self.prefill_prompt(prompt, enc.pos)
+        embeds = self.spatial_prompt_embeds(prompt, spatial_refs) if spatial_refs else None
+        logits, hidden, nxt, pos = self.prefill_prompt(prompt, enc.pos, embeds)
         out = Generation([], [], [], margin_ulps=[])
         n = 0
         pred = int(nxt.item()) if temperature == 0 else self.next_token(logits, temperature, top_p)

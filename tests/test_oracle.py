@@ -82,3 +82,66 @@ def test_oracle_is_bit_identical_to_reference(tiny):
     text = ref.caption(enc, "short", settings={"temperature": 0, "max_tokens": 10})["caption"]
     gen = orc.generate(o_enc, cfg.tokenizer.templates["caption"]["short"], 10)
     assert R.tokens_from_text(text) == gen.tokens
+
+
+@pytest.mark.skipif(not R.reference_available(), reason="/root/reference only exists in the build container")
+def test_oracle_spatial_refs_and_sampling_are_bit_identical_to_reference(tiny):
+    """query(spatial_refs=...) (moondream.py:293-301, region.py:96-136): logits and hidden states of the prompt prefill
+    with point and box references, then the greedy tokens; and seeded nucleus sampling (moondream.py:270-278)."""
+    from PIL import Image
+
+    cfg, sd, orc = tiny
+    tk = cfg.tokenizer
+    ref = R.load_reference_model(cfg, sd)
+    img = synth.synthetic_image(2, 500, 700)
+    with torch.inference_mode():
+        enc = ref.encode_image(Image.fromarray(img))
+    o_enc = orc.encode_image(img)
+    seen = []
+    orig = ref._prefill_prompt
+
+    def recording(prompt_tokens, pos, *a, **k):
+        out = orig(prompt_tokens, pos, *a, **k)
+        seen.append((prompt_tokens.flatten().tolist(), out[0].clone(), out[1].clone()))
+        return out
+
+    ref._prefill_prompt = recording
+    try:
+        for refs in ([(0.25, 0.75)], [(0.1, 0.2, 0.5, 0.9)], [(0.25, 0.75), (0.1, 0.2, 0.5, 0.9), (0.6, 0.6)]):
+            seen.clear()
+            text = ref.query(enc, "15 16", spatial_refs=refs, settings={"temperature": 0, "max_tokens": 8})["answer"]
+            prompt, ref_logits, ref_hidden = seen[0]
+            assert prompt.count(tk.coord_id) == 2 * len(refs) and prompt.count(tk.size_id) == sum(len(r) == 4 for r in refs)
+            orc.load_encoded(o_enc)
+            logits, hidden, _, _ = orc.prefill_prompt(prompt, o_enc.pos, orc.spatial_prompt_embeds(prompt, refs))
+            assert torch.equal(logits, ref_logits) and torch.equal(hidden, ref_hidden)
+            plain = orc.prefill_prompt(prompt, o_enc.pos)[0]
+            assert not torch.equal(plain, ref_logits)                      # the references really enter the prompt
+            assert orc.generate(o_enc, prompt, 8, spatial_refs=refs).tokens == R.tokens_from_text(text)
+    finally:
+        ref._prefill_prompt = orig
+    prompt = synth.synthetic_prompt(3, 6, cfg.text.vocab_size)
+    for seed, temp, top_p in ((5, 0.5, 0.3), (6, 1.5, 0.9)):
+        ref.load_encoded_image(enc)
+        torch.manual_seed(seed)
+        text = "".join(ref._generate_answer(torch.tensor([prompt]), enc.pos,
+                                            {"temperature": temp, "top_p": top_p, "max_tokens": 10}))
+        torch.manual_seed(seed)
+        assert orc.generate(o_enc, prompt, 10, temperature=temp, top_p=top_p).tokens == R.tokens_from_text(text)
+
+
+def test_oracle_reproduces_spatial_ref_golden(tiny):
+    """tests/golden/tiny_spatial_refs.json (the reference's query(spatial_refs=...) answers; embedding rows taken after
+    bit-equality of the prefill logits with the reference)."""
+    import json
+    import os
+
+    cfg, sd, orc = tiny
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "tiny_spatial_refs.json")))
+    idx, h, w = gold["image"]
+    o_enc = orc.encode_image(synth.synthetic_image(idx, h, w))
+    for c in gold["cases"]:
+        refs = [tuple(r) for r in c["spatial_refs"]]
+        emb = orc.spatial_prompt_embeds(c["prompt"], refs)
+        assert torch.equal(emb[0, c["rows"]].float(), torch.tensor(c["row_embeds"]))
+        assert orc.generate(o_enc, c["prompt"], len(c["tokens"]), spatial_refs=refs).tokens == c["tokens"]
