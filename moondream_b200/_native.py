@@ -7,7 +7,7 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import c_char_p, c_int, c_longlong, c_void_p, c_float, c_uint
+from ctypes import c_char_p, c_int, c_longlong, c_void_p, c_uint
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libmoondream_b200.so")

@@ -26,7 +26,6 @@ import torch
 
 from .config import MoondreamConfig
 from .engine import Engine, PrefixKV
-from . import _native as N
 
 try:
     from PIL import Image

@@ -42,7 +42,6 @@ for impl in (0, 1):
     print({"impl": ["tcgen05", "mma.sync"][impl], "ms": ms, "tflops": flops / ms / 1e9}, flush=True)
 print("rel diff", ((res[0] - res[1]).norm() / res[1].norm()).item())
 lib.md_debug_attention_impl(0)
-import subprocess
 # occupancy probe
 print("done")
 
