@@ -1,0 +1,32 @@
+#!/usr/bin/env bash
+# First GPU call after a round that ended with staged, unvalidated work:
+#   gpurun --timeout 900 -- 'bash tools/staged_checks.sh'
+# 1. the env-gated tests, 2. the M = 64 small-batch stream against the shipped M = 128 one in one box.
+set -u
+mkdir -p gpurun_out
+echo "== staged tests"
+MD_EXPERIMENTAL=1 timeout 300 python -m pytest tests -q -m gpu -k "experimental or spatial_refs_match" --tb=short 2>&1 | tail -15
+echo "== decode timeline, M = 128 (shipped) / M = 64 (md_debug_gemm bit 6), twice each"
+for f in 0 64 0 64; do
+  echo "-- gemm-debug $f"
+  timeout 200 python tools/decode_timeline.py --brief --gemm-debug $f --out gpurun_out/decode_timeline_dbg$f.json 2>&1 |
+    grep -E "Error|error|layer period|^gemm[12] |^attn |^epi "
+done
+echo "== parity of the whole model with M = 64 forced"
+timeout 300 python - <<'PY'
+import torch
+from moondream_b200 import _native as N, config as C, synth
+from moondream_b200.engine import Engine
+from oracle.moondream_oracle import OracleModel
+cfg = C.tiny(); sd = synth.synthetic_state_dict(cfg, 0)
+N.lib().md_debug_gemm(64)
+eng = Engine(cfg, sd, max_batch=4); orc = OracleModel(cfg, sd)
+imgs = [synth.synthetic_image(i, 378, 378) for i in range(3)]
+prompts = [synth.synthetic_prompt(i, 6, cfg.text.vocab_size) for i in range(3)]
+res = eng.generate(eng.encode_images(imgs), prompts, 12, stop_on_eos=False)
+for i in range(3):
+    gen = orc.generate(orc.encode_image(imgs[i]), prompts[i], 12)
+    got = res.tokens[i, :len(gen.tokens)].tolist()
+    bad = [(j, a, b, gen.margin_ulps[j]) for j, (a, b) in enumerate(zip(got, gen.tokens)) if a != b][:1]
+    print(i, "ok" if not bad else ("first mismatch", bad[0]))
+PY
