@@ -123,6 +123,9 @@ void md_debug_skip_decode_kernels(int mask);
  * bit2 previous split plan of the [proj | fc2] stream (equal splits); bit6 M = 64 MMAs for batches <= 64
  * (experimental, not yet validated on hardware).  Other bits are ignored. */
 void md_debug_gemm(int flags);
+/* Experiments only: cap the persistent row-form GEMM's grid at `sms` SMs (0 = all, the default), leaving the others
+ * to kernels of a concurrent stream (encode / decode overlap). */
+void md_debug_gemm_sm_cap(int sms);
 /* Profiling only: while `records` is non-NULL every CTA of the decode-step kernels (weight-stream GEMMs, decode
  * attention, residual+LayerNorm epilogue) appends one record of 6 uint64 to records[capacity][6]:
  * {tag << 32 | block, t_entry, t_after_dependency_wait, t_mid0, t_mid1, t_exit} in %globaltimer ns; tag bits 31..28:

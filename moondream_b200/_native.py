@@ -55,6 +55,7 @@ _SIGNATURES = {
     "md_debug_set_pdl": (None, [c_int]),
     "md_debug_skip_decode_kernels": (None, [c_int]),
     "md_debug_gemm": (None, [c_int]),
+    "md_debug_gemm_sm_cap": (None, [c_int]),
     "md_debug_timeline": (c_int, [c_void_p, c_void_p, c_uint]),
     "md_decode_attention_bf16": (c_int, [_P, c_int, _P, c_int, _KV, c_int, _P, _P]),
     "md_model_num_weights": (c_int, [_DIMS]),

@@ -112,6 +112,7 @@ void md_debug_attention_impl(int impl) { md::g_attention_impl = impl; }
 void md_debug_set_pdl(int enable) { md::g_pdl = enable; }
 void md_debug_skip_decode_kernels(int mask) { md::g_debug_skip = mask; }
 void md_debug_gemm(int flags) { md::gemm_debug_flags(flags); }
+void md_debug_gemm_sm_cap(int sms) { md::gemm_debug_sm_cap(sms); }
 int md_debug_timeline(void* records, void* count, unsigned int capacity) {
   return md::timeline_install_all(static_cast<unsigned long long*>(records), static_cast<unsigned int*>(count), capacity);
 }

@@ -30,6 +30,7 @@ constexpr int kEpiWarps = 8;                        // two warps per TMEM lane q
 constexpr int kGemmThreads = 128 + kEpiWarps * 32;  // producer, MMA, TMEM-alloc, spare + epilogue
 
 static int g_gemm_debug = 0;            // md_debug_gemm: timing experiments only
+static int g_gemm_sm_cap = 0;           // md_debug_gemm_sm_cap: 0 = every SM (default)
 
 struct GemmParams {
   int M, N, K;
@@ -673,7 +674,9 @@ static int launch_gemm(const CUtensorMap& tA, const CUtensorMap& tB, const GemmP
     configured = true;
   }
   const int total = p.m_blocks * p.n_blocks;
-  const int max_units = num_sms() / CG;
+  int max_units = num_sms() / CG;
+  if (g_gemm_sm_cap > 0 && g_gemm_sm_cap / CG < max_units)      // experiments: leave SMs to a concurrent stream
+    max_units = g_gemm_sm_cap / CG > 0 ? g_gemm_sm_cap / CG : 1;
   const int units = total < max_units ? total : max_units;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(units * CG);
@@ -696,6 +699,7 @@ static int launch_gemm(const CUtensorMap& tA, const CUtensorMap& tB, const GemmP
 }
 
 void gemm_debug_flags(int flags) { g_gemm_debug = flags; }
+void gemm_debug_sm_cap(int sms) { g_gemm_sm_cap = sms < 0 ? 0 : sms; }
 static int g_force_cg = 0;   // 0 = auto, 1 / 2 = force (tests and A/B timing)
 void gemm_force_cta_group(int cg) { g_force_cg = cg; }
 // Installs (buf != nullptr) or removes the debug timeline buffer in every kernel translation unit.

@@ -60,6 +60,7 @@ int gemm_rowform(const __nv_bfloat16* A, long long lda, const __nv_bfloat16* W, 
                  int remap_gout, int remap_goff, cudaStream_t stream);
 void gemm_force_cta_group(int cg);
 void gemm_debug_flags(int flags);
+void gemm_debug_sm_cap(int sms);
 void gemm_profile_enable(int on);
 int gemm_profile_read(double* total_ms, double* total_flops, long long* launches);
 struct StreamPlan { int tile_rows, kb, splits; };
