@@ -30,3 +30,5 @@ for i in range(3):
     bad = [(j, a, b, gen.margin_ulps[j]) for j, (a, b) in enumerate(zip(got, gen.tokens)) if a != b][:1]
     print(i, "ok" if not bad else ("first mismatch", bad[0]))
 PY
+echo "== encode / decode overlap probe (DESIGN.md section 9, 1b)"
+timeout 400 python tools/overlap_probe.py --batches 6 2>&1 | tail -8
