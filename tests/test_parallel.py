@@ -48,10 +48,21 @@ def _worker(rank, world, port, n_items, T):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("n_items", [8, 7])
-def test_two_rank_gloo_allgather(n_items):
+def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
     port = s.getsockname()[1]
     s.close()
-    mp.spawn(_worker, args=(2, port, n_items, 5), nprocs=2, join=True)
+    return port
+
+
+@pytest.mark.parametrize("n_items", [8, 7])
+def test_two_rank_gloo_allgather(n_items):
+    mp.spawn(_worker, args=(2, _free_port(), n_items, 5), nprocs=2, join=True)
+
+
+@pytest.mark.parametrize("world,n_items", [(4, 10), (3, 2)])
+def test_wider_worlds_with_ragged_and_empty_shards(world, n_items):
+    """The 4- and 8-GPU runs use the same code as the 2-GPU one; cover a remainder (10 items on 4 ranks) and ranks
+    that own nothing (2 items on 3 ranks) on CPU."""
+    mp.spawn(_worker, args=(world, _free_port(), n_items, 3), nprocs=world, join=True)
