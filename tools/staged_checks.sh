@@ -32,3 +32,8 @@ for i in range(3):
 PY
 echo "== encode / decode overlap probe (DESIGN.md section 9, 1b)"
 timeout 400 python tools/overlap_probe.py --batches 6 2>&1 | tail -8
+echo "== compute-sanitizer (SURVEY.md section 5: memcheck / racecheck on the hand-written kernels; bounded subsets)"
+timeout 400 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gemm_gpu.py -q -m gpu \
+  -k "small_batch and (32-6144 or 7-1032)" -p no:cacheprovider 2>&1 | tail -4
+timeout 400 compute-sanitizer --tool racecheck --error-exitcode 9 python -m pytest tests/test_kernels_gpu.py -q -m gpu \
+  -k "decode_attention or layernorm" -p no:cacheprovider 2>&1 | tail -4
