@@ -288,12 +288,11 @@ flash_attention_kernel(const FlashParams p) {
 template <int HD, int DP, bool PAGED>
 static int launch_flash(const FlashParams& p, dim3 grid, cudaStream_t stream) {
   constexpr int smem = (64 + 4 * 64) * (DP + 8) * 2;
-  static bool configured = false;
-  if (!configured) {
+  static DeviceOnce configured;
+  if (configured.first()) {
     cudaError_t e = cudaFuncSetAttribute(flash_attention_kernel<HD, DP, PAGED>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return set_error(cudaGetErrorString(e));
-    configured = true;
   }
   flash_attention_kernel<HD, DP, PAGED><<<grid, 128, smem, stream>>>(p);
   count_launch();

@@ -360,8 +360,8 @@ int prefill_attention_tc(const __nv_bfloat16* q, int n_heads, int total_tokens, 
   const long long pool_rows = static_cast<long long>(n_layers) * n_pages * 2 * n_heads * 64;
   if (pool_rows >= (1LL << 31)) return set_error("prefill_attention: KV pool too large for 32-bit TMA coordinates");
   if (make_tmap_bf16_2d(&tKV, kv_pool, pool_rows, 64, 64, 64)) return 1;
-  static bool configured = false;
-  if (!configured) {
+  static DeviceOnce configured;
+  if (configured.first()) {
     cudaError_t e = cudaFuncSetAttribute(fa_tc_prefill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          fa::kSmemTotal);
     if (e != cudaSuccess) return set_error(cudaGetErrorString(e));
@@ -369,7 +369,6 @@ int prefill_attention_tc(const __nv_bfloat16* q, int n_heads, int total_tokens, 
     e = cudaFuncSetAttribute(fa_tc_prefill_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
                              cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return set_error(cudaGetErrorString(e));
-    configured = true;
   }
   FaTcParams p{};
   p.q_offsets = q_offsets; p.start_pos = start_pos; p.block_tables = block_tables;
@@ -646,14 +645,13 @@ int vit_attention_tc(const __nv_bfloat16* qkv, int n_crops, int seq, int n_heads
   // view [token][3*H heads][72]: reading dims 64..79 of a head zero-fills 72..79
   if (make_tmap_bf16_3d(&t64, qkv, 72, 3LL * n_heads, T, 144, 3 * D * 2, 64, 1, 128, 128)) return 1;
   if (make_tmap_bf16_3d(&t16, qkv, 72, 3LL * n_heads, T, 144, 3 * D * 2, 16, 1, 128, 32)) return 1;
-  static bool configured = false;
-  if (!configured) {
+  static DeviceOnce configured;
+  if (configured.first()) {
     cudaError_t e = cudaFuncSetAttribute(fa_tc_vit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, fv::kSmemTotal);
     if (e != cudaSuccess) return set_error(cudaGetErrorString(e));
     e = cudaFuncSetAttribute(fa_tc_vit_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
                              cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return set_error(cudaGetErrorString(e));
-    configured = true;
   }
   FaVitParams p{};
   p.seq = seq; p.n_heads = n_heads; p.out = out;

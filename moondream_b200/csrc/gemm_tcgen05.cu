@@ -666,12 +666,11 @@ static int launch_gemm(const CUtensorMap& tA, const CUtensorMap& tB, const GemmP
                        cudaStream_t stream) {
   using S = GemmSmem<BN, STAGES, CG>;
   static_assert(S::kTotal <= 227 * 1024, "shared memory budget");
-  static bool configured = false;
-  if (!configured) {
+  static DeviceOnce configured;
+  if (configured.first()) {
     cudaError_t e = cudaFuncSetAttribute(gemm_bf16_kernel<BN, STAGES, CG>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal);
     if (e != cudaSuccess) return set_error(cudaGetErrorString(e));
-    configured = true;
   }
   const int total = p.m_blocks * p.n_blocks;
   int max_units = num_sms() / CG;
@@ -831,18 +830,16 @@ static int gemm_smallbatch_impl(const __nv_bfloat16* W, long long ldw, const __n
   p.tmem_cols = p.n_mma <= 32 ? 32 : p.n_mma <= 64 ? 64 : p.n_mma <= 128 ? 128 : 256;
   p.trigger_early = g_pdl >= 2 ? 1 : 0;
   constexpr int kSbSmemMax = 227 * 1024 - 1024;      // leave room for the kernel's few static __shared__ words
-  static bool configured = false;
-  if (!configured) {
+  static DeviceOnce configured;
+  if (configured.first()) {
     cudaError_t e = cudaFuncSetAttribute(smallbatch_gemm_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSbSmemMax);
     if (e != cudaSuccess) { set_error(cudaGetErrorString(e)); return -1; }
-    configured = true;
   }
   const bool m64 = (g_gemm_debug & 64) && batch <= 64;     // experimental until validated on hardware
-  static bool configured64 = false;
-  if (m64 && !configured64) {
+  static DeviceOnce configured64;
+  if (m64 && configured64.first()) {
     cudaError_t e = cudaFuncSetAttribute(smallbatch_gemm_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSbSmemMax);
     if (e != cudaSuccess) { set_error(cudaGetErrorString(e)); return -1; }
-    configured64 = true;
   }
   CUtensorMap tW;
   if (make_tmap_bf16_2d(&tW, W, n_out, K, ldw, tile_n)) return -1;

@@ -24,6 +24,19 @@ long long launch_count();
 void reset_launch_count();
 int num_sms();
 
+// cudaFuncSetAttribute is per device: one flag per (call site, device), so a second model on another GPU of the
+// same process configures its kernels too.
+struct DeviceOnce {
+  bool done[64] = {};
+  bool first() {
+    int d = 0;
+    if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= 64) return true;
+    if (done[d]) return false;
+    done[d] = true;
+    return true;
+  }
+};
+
 // Launch with programmatic stream serialization (PDL) when enabled: the kernel must call pdl_wait()
 // before touching memory its predecessor produced.
 extern int g_pdl;

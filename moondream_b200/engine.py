@@ -22,6 +22,19 @@ from .synth import state_dict_spec
 PAGE = 64
 
 
+def _on_device(fn):
+    """Run a public Engine method with the engine's GPU as the current device, so allocations, the current
+    stream and every native launch land on it even when the caller's current device is another GPU."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapped(self, *a, **k):
+        with torch.cuda.device(self.device):
+            return fn(self, *a, **k)
+
+    return wrapped
+
+
 def _round_up(x: int, m: int) -> int:
     return (x + m - 1) // m * m
 
@@ -150,6 +163,8 @@ class GenerationResult:
 
 
 class Engine:
+    _MAX_DECODE_STATES = 4
+
     def __init__(self, cfg: MoondreamConfig, state_dict: Dict[str, torch.Tensor], device="cuda",
                  kv_pages: Optional[int] = None, max_batch: int = 32):
         cfg.validate()
@@ -157,7 +172,15 @@ class Engine:
             raise N.NativeError("moondream_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
         self.cfg = cfg
         self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise N.NativeError(f"moondream_b200 runs on CUDA devices only, got {self.device}")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
         self.lib = N.lib()
+        with torch.cuda.device(self.device):
+            self._init(cfg, state_dict, kv_pages, max_batch)
+
+    def _init(self, cfg, state_dict, kv_pages, max_batch):
         import os as _os0
         if _os0.environ.get("MD_PDL") is not None:          # A/B switch for profiling runs
             self.lib.md_debug_set_pdl(int(_os0.environ["MD_PDL"]))
@@ -216,7 +239,19 @@ class Engine:
     def _i32(self, values) -> torch.Tensor:
         return torch.tensor(values, dtype=torch.int32).to(self.device, non_blocking=True)
 
+    def replace_weight(self, key: str, tensor: torch.Tensor):
+        """Overwrite one canonical tensor in place on the device (same shape; the decoder's fused [qkv;fc1] /
+        [proj|fc2] buffers are views, so they follow).  Tests use it to try another LM head on a loaded model."""
+        keys = [k for k, _, _ in state_dict_spec(self.cfg)]
+        w = self.weights[keys.index(key)]
+        if tuple(w.shape) != tuple(tensor.shape):
+            raise ValueError(f"{key}: expected {tuple(w.shape)}, got {tuple(tensor.shape)}")
+        with torch.cuda.device(self.device):
+            w.copy_(tensor.to(torch.bfloat16))
+            torch.cuda.current_stream().synchronize()
+
     # ------------------------------------------------------------------ vision
+    @_on_device
     def vision_encode(self, crops_u8: torch.Tensor) -> torch.Tensor:
         """_vis_enc: uint8 NHWC crops on device -> bf16 [n_crops * 729, enc_dim]."""
         v = self.cfg.vision
@@ -230,6 +265,7 @@ class Engine:
                                           N.current_stream()), "md_vision_encode")
         return feats
 
+    @_on_device
     def vision_project(self, feats: torch.Tensor, crop_offsets: Sequence[int],
                        tilings: Sequence[Tuple[int, int]], embeds: torch.Tensor, rows_per_image: int = 0):
         """reconstruct_from_crops + _vis_proj for all images; fills embeds rows 1..729 of each image."""
@@ -242,6 +278,7 @@ class Engine:
                 "md_vision_project")
 
     # ------------------------------------------------------------------ text
+    @_on_device
     def embed(self, ids: torch.Tensor, out: torch.Tensor, id_stride: int = 1, n: Optional[int] = None,
               ldo: Optional[int] = None):
         n = ids.numel() if n is None else n
@@ -249,6 +286,7 @@ class Engine:
                                          out.stride(0) if ldo is None else ldo, N.current_stream()),
                 "md_embed_tokens")
 
+    @_on_device
     def prefill(self, x: torch.Tensor, q_offsets: Sequence[int], start_pos: Sequence[int],
                 block_tables: torch.Tensor):
         """_prefill over a ragged batch, in place on x [total_tokens, dim]."""
@@ -262,6 +300,7 @@ class Engine:
         N.check(self.lib.md_text_prefill(self.model, N.ptr(x), T, N.ptr(qo), N.ptr(sp), n_seqs, max_q,
                                          ctypes.byref(kv), N.ptr(ws), N.current_stream()), "md_text_prefill")
 
+    @_on_device
     def lm_head(self, hidden: torch.Tensor, out_ids: torch.Tensor, out_stride: int, mask_id: int = -1,
                 out_index: Optional[torch.Tensor] = None, margins: Optional[torch.Tensor] = None,
                 logits: Optional[torch.Tensor] = None, ws: Optional[torch.Tensor] = None,
@@ -276,6 +315,7 @@ class Engine:
                                            N.current_stream()), "md_lm_head_argmax")
 
     # ------------------------------------------------------------------ image encoding
+    @_on_device
     def encode_crops(self, crops_u8: torch.Tensor, crop_offsets: Sequence[int],
                      tilings: Sequence[Tuple[int, int]], return_hidden: bool = False):
         """encode_image (moondream.py:230-268) for a batch whose crops are already on the device:
@@ -299,6 +339,7 @@ class Engine:
             return prefixes, feats, img_emb, embeds
         return prefixes
 
+    @_on_device
     def encode_images(self, images: Sequence[np.ndarray], return_hidden: bool = False):
         """Host uint8 HxWx3 images -> crops (PIL Lanczos, image_crops.py:58-167) -> H2D -> encode_crops."""
         # crops are written straight into persistent pinned staging memory by a small thread pool
@@ -306,6 +347,7 @@ class Engine:
         dev, offsets, tilings = self.stage_images(images)
         return self.encode_crops(dev, offsets, tilings, return_hidden=return_hidden)
 
+    @_on_device
     def encode_crops_with_prompt(self, crops_u8: torch.Tensor, crop_offsets: Sequence[int],
                                  tilings: Sequence[Tuple[int, int]], prompt: Sequence[Sequence[int]]):
         """encode_image + the prompt prefill of caption()/query() in ONE decoder pass per batch:
@@ -337,6 +379,7 @@ class Engine:
         hidden_last = view[:, rows - 1].contiguous()
         return prefixes, hidden_last
 
+    @_on_device
     def caption_from_crops(self, crops_u8: torch.Tensor, crop_offsets: Sequence[int],
                            tilings: Sequence[Tuple[int, int]], prompts: Sequence[Sequence[int]], max_tokens: int,
                            to_host: bool = True, stop_on_eos: bool = True) -> "GenerationResult":
@@ -348,6 +391,7 @@ class Engine:
         prefixes = self.encode_crops(crops_u8, crop_offsets, tilings)
         return self.generate(prefixes, prompts, max_tokens, consume=True, stop_on_eos=stop_on_eos, to_host=to_host)
 
+    @_on_device
     def stage_images(self, images: Sequence[np.ndarray]):
         """host uint8 images -> crops in pinned staging memory -> device; returns (crops, offsets, tilings)"""
         v = self.cfg.vision
@@ -371,6 +415,7 @@ class Engine:
             work(0)
         return self._stage[:n].to(self.device, non_blocking=True), offsets, tilings
 
+    @_on_device
     def prefix_kv_tensors(self, prefix: PrefixKV) -> List[Tuple[torch.Tensor, torch.Tensor]]:
         """Materialise (k, v) [1, heads, pos, 64] per layer like EncodedImage.caches (moondream.py:56-59)."""
         pg = torch.tensor(prefix.pages, dtype=torch.long, device=self.device)
@@ -383,42 +428,64 @@ class Engine:
     def _sequence_tables(self, prefixes: Sequence[PrefixKV], total_len: int, consume: bool):
         """Block tables for sequences that continue `prefixes`.  Full prefix pages are shared; the
         partially filled last prefix page is copied (copy-on-write) unless `consume` hands the
-        prefix's pages over to the sequence."""
+        prefix's pages over to the sequence.  All-or-nothing: the pages the whole batch needs are counted
+        before anything is taken, and a failure part-way gives back what was taken and leaves the prefixes'
+        ownership untouched."""
         n_blocks = math.ceil(total_len / PAGE)
         if n_blocks > self.max_blocks:
             raise ValueError(f"sequence of {total_len} tokens exceeds max_context {self.cfg.text.max_context}")
+        need = sum(max(0, n_blocks - (len(p.pages) if consume else p.pos // PAGE)) for p in prefixes)
+        if need > self.pages.free_pages:
+            raise N.NativeError(f"KV pool exhausted: this batch needs {need} more pages, {self.pages.free_pages} free "
+                                f"(raise kv_pages when constructing the model, or release EncodedImages)")
         bt = torch.zeros((len(prefixes), self.max_blocks), dtype=torch.int32)
         owned: List[List[int]] = []
+        taken: List[int] = []
+        consumed: List[PrefixKV] = []
         copies_src, copies_dst = [], []
-        for i, p in enumerate(prefixes):
-            full = p.pos // PAGE
-            if consume:
-                pages = list(p.pages)
-                p._released = True                      # ownership moves to the sequence
-                fresh = self.pages.alloc(n_blocks - len(pages))
-                own = pages + fresh
-                table = own
-            else:
-                fresh = self.pages.alloc(n_blocks - full)
-                if p.pos % PAGE:
-                    copies_src.append(p.pages[full])
-                    copies_dst.append(fresh[0])
-                own = fresh
-                table = list(p.pages[:full]) + fresh
-            bt[i, : len(table)] = torch.tensor(table, dtype=torch.int32)
-            owned.append(own)
+        try:
+            for i, p in enumerate(prefixes):
+                full = p.pos // PAGE
+                if consume:
+                    if p._released:
+                        raise ValueError("this encoded image's KV pages were already handed to a sequence")
+                    pages = list(p.pages)
+                    fresh = self.pages.alloc(max(0, n_blocks - len(pages)))
+                    taken += fresh
+                    p._released = True                      # ownership moves to the sequence
+                    consumed.append(p)
+                    own = pages + fresh
+                    table = own
+                else:
+                    fresh = self.pages.alloc(max(0, n_blocks - full))
+                    taken += fresh
+                    if p.pos % PAGE and fresh:
+                        copies_src.append(p.pages[full])
+                        copies_dst.append(fresh[0])
+                    own = fresh
+                    table = list(p.pages[:full]) + fresh
+                bt[i, : len(table)] = torch.tensor(table, dtype=torch.int32)
+                owned.append(own)
+        except Exception:
+            self.pages.release(taken)
+            for p in consumed:
+                p._released = False
+            raise
         if copies_src:
             src = torch.tensor(copies_src, dtype=torch.long, device=self.device)
             dst = torch.tensor(copies_dst, dtype=torch.long, device=self.device)
             self.pages.pool[:, dst] = self.pages.pool[:, src]
         return bt.to(self.device), owned
 
-    def _decode_buffers(self, B: int, S: int) -> dict:
-        key = (B, S)
-        st = self._decode_state.get(key)
+    def _decode_buffers(self, B: int) -> dict:
+        """Per-batch-size decode state (buffers, workspaces, captured graphs).  The per-step outputs use a fixed
+        row stride of max_context + 1 slots, so one set of buffers and graphs serves every max_tokens; at most
+        `_MAX_DECODE_STATES` batch sizes stay cached (least recently used goes first)."""
+        st = self._decode_state.pop(B, None)
         if st is None:
             t = self.cfg.text
             dev = self.device
+            S = t.max_context + 1
             st = {
                 "x": torch.empty((B, t.dim), dtype=torch.bfloat16, device=dev),
                 "normed": torch.empty((B, t.dim), dtype=torch.bfloat16, device=dev),
@@ -434,8 +501,11 @@ class Engine:
                                   int(self.lib.md_lm_head_workspace_bytes(self.model, B)),
                                   dtype=torch.uint8, device=dev),
                 "graphs": {},
+                "S": S,
             }
-            self._decode_state[key] = st
+            while len(self._decode_state) >= self._MAX_DECODE_STATES:
+                self._decode_state.pop(next(iter(self._decode_state)))
+        self._decode_state[B] = st          # most recently used last
         return st
 
     def _decode_step_launch(self, st: dict, B: int, S: int, use_forced: bool, mask_id: int):
@@ -452,6 +522,7 @@ class Engine:
                                       N.ptr(st["forced"]) if use_forced else None, S, B,
                                       self.cfg.tokenizer.eos_id, N.ptr(st["finished"]), s), "md_decode_advance")
 
+    @_on_device
     def generate(self, prefixes: Sequence[PrefixKV], prompts: Sequence[Sequence[int]], max_tokens: int,
                  forced: Optional[Sequence[Sequence[int]]] = None, consume: bool = False,
                  use_graph: bool = True, stop_on_eos: bool = True,
@@ -468,14 +539,17 @@ class Engine:
         t, tk = self.cfg.text, self.cfg.tokenizer
         B = len(prefixes)
         assert len(prompts) == B
-        S = max_tokens + 1
+        n_out = max_tokens + 1              # slots the caller gets back: the first token + one per decode step
         lens = [len(p) for p in prompts]
         if prefilled_hidden is not None:
             lens = [0] * B              # prefixes already include the prompt; prefilled_hidden = last-token hidden states
         total = [prefixes[i].pos + lens[i] + max_tokens + 1 for i in range(B)]
         bt, owned = self._sequence_tables(prefixes, max(total), consume)
         try:
-            st = self._decode_buffers(B, S)
+            st = self._decode_buffers(B)
+            S = st["S"]                     # row stride of preds / forced / margins (fixed, >= n_out)
+            if n_out > S:
+                raise ValueError(f"max_tokens {max_tokens} exceeds max_context {t.max_context}")
             st["bt"].copy_(bt)
             # ---- prompt prefill (moondream.py:280-321) ----
             if prefilled_hidden is not None:
@@ -503,10 +577,10 @@ class Engine:
             self.lm_head(st["x"], st["preds"], S, mask_id=-1, out_index=None, margins=st["margins"])
             use_forced = forced is not None
             if use_forced:
-                f = torch.zeros((B, S), dtype=torch.int32)
+                f = torch.zeros((B, n_out), dtype=torch.int32)
                 for i, row in enumerate(forced):
-                    f[i, : min(len(row), S)] = torch.tensor(list(row)[:S], dtype=torch.int32)
-                st["forced"].copy_(f.to(self.device))
+                    f[i, : min(len(row), n_out)] = torch.tensor(list(row)[:n_out], dtype=torch.int32)
+                st["forced"][:, :n_out].copy_(f.to(self.device))
                 st["cur"].copy_(st["forced"][:, 0])
             else:
                 st["cur"].copy_(st["preds"][:, 0])
@@ -514,7 +588,7 @@ class Engine:
             # ---- decode loop (moondream.py:481-530), one graph replay per token ----
             gkey = (use_forced, tk.answer_id)
             graph = st["graphs"].get(gkey) if use_graph else None
-            if use_graph and graph is None:
+            if use_graph and graph is None and max_tokens > 0:
                 self._decode_step_launch(st, B, S, use_forced, tk.answer_id)   # warm-up (also validates)
                 torch.cuda.synchronize()
                 # rewind the state the warm-up step advanced
@@ -537,10 +611,11 @@ class Engine:
                 if stop_on_eos and not use_forced and (s % 16 == 15) and bool(st["finished"].all().item()):
                     break
             if to_host:
-                tokens = st["preds"].to("cpu")          # the one device->host read of the call
-                margins = st["margins"].to("cpu")
+                tokens = st["preds"][:, :n_out].to("cpu")          # the one device->host read of the call
+                margins = st["margins"][:, :n_out].to("cpu")
             else:
-                tokens, margins = st["preds"].clone(), st["margins"].clone()
+                tokens = st["preds"][:, :n_out].clone(memory_format=torch.contiguous_format)
+                margins = st["margins"][:, :n_out].clone(memory_format=torch.contiguous_format)
         finally:
             for pages in owned:
                 self.pages.release(pages)
@@ -583,11 +658,14 @@ class Engine:
                                           N.ptr(st["forced"]), S, B, tk.eos_id, N.ptr(st["finished"]), stream),
                     "md_decode_advance")
             steps += 1
+        n_out = max_tokens + 1
         if to_host:
-            return GenerationResult(st["forced"].to("cpu"), st["margins"].to("cpu"), steps)
-        return GenerationResult(st["forced"].clone(), st["margins"].clone(), steps)
+            return GenerationResult(st["forced"][:, :n_out].to("cpu"), st["margins"][:, :n_out].to("cpu"), steps)
+        return GenerationResult(st["forced"][:, :n_out].clone(memory_format=torch.contiguous_format),
+                                st["margins"][:, :n_out].clone(memory_format=torch.contiguous_format), steps)
 
     # ------------------------------------------------------------------ region head
+    @_on_device
     def region_encode(self, which: int, values: torch.Tensor) -> torch.Tensor:
         """encode_coordinate / encode_size (region.py:32-43, 60-71): values fp32 [B, 1|2] -> bf16 [B, dim]."""
         values = values.to(self.device, dtype=torch.float32).contiguous()
@@ -598,6 +676,7 @@ class Engine:
                                           N.ptr(ws), N.current_stream()), "md_region_encode")
         return out
 
+    @_on_device
     def region_decode(self, which: int, hidden: torch.Tensor) -> torch.Tensor:
         """argmax bins of decode_coordinate / decode_size (region.py:46-57, 74-93): int32 [B] / [B, 2]."""
         B = hidden.shape[0]
@@ -613,6 +692,7 @@ class Engine:
                                                   N.current_stream()), "md_region_bins_to_values")
         return out
 
+    @_on_device
     def generate_points(self, prefixes: Sequence[PrefixKV], prompts: Sequence[Sequence[int]],
                         include_size: bool, max_objects: int) -> List[List[dict]]:
         """detect / point (moondream.py:735-829 -> _generate_points :653-733) for a batch in lock-step:

@@ -91,9 +91,10 @@ def param_count(cfg: MoondreamConfig) -> int:
     return sum(int(np.prod(s)) for _, s, _ in state_dict_spec(cfg))
 
 
-def synthetic_state_dict(cfg: MoondreamConfig, seed: int = 0, head_gain: float = 4.0
-                         ) -> Dict[str, torch.Tensor]:
-    """bf16 CPU tensors in the canonical layout."""
+def synthetic_state_dict(cfg: MoondreamConfig, seed: int = 0, head_gain: float = 4.0,
+                         head_peak: float = 0.0) -> Dict[str, torch.Tensor]:
+    """bf16 CPU tensors in the canonical layout.  `head_peak` > 0 adds the wide-margin component of
+    `peaked_lm_head` to the LM head (see there); 0 keeps the plain Gaussian head."""
     gen = torch.Generator(device="cpu").manual_seed(seed)
     sd: Dict[str, torch.Tensor] = {}
     for key, shape, kind in state_dict_spec(cfg):
@@ -115,7 +116,25 @@ def synthetic_state_dict(cfg: MoondreamConfig, seed: int = 0, head_gain: float =
             x.mul_(3.0)
         sd[key] = x.to(torch.bfloat16)
     sd["text.lm_head.bias"][cfg.tokenizer.eos_id] = -3.0e4
+    if head_peak:
+        sd["text.lm_head.weight"] = peaked_lm_head(sd, head_peak, seed)
     return sd
+
+
+def peaked_lm_head(sd: Dict[str, torch.Tensor], peak: float, seed: int = 0) -> torch.Tensor:
+    """Wide-margin LM head ("tied lm_head"): the Gaussian head plus `peak` times a
+    row-permuted, row-normalised copy of the token embedding, head[perm[t]] += peak * wte[t] / |wte[t]|.
+    A plain Gaussian head gives top-1/top-2 margins of 1..10 bf16 ulps (about half of all greedy decisions are ties
+    up to bf16 rounding, so strict token equality between two bf16 implementations cannot hold); the tied
+    component makes the token that follows t under the fixed permutation stand out by tens of ulps.  Around
+    peak = 2..3 the sequence still depends on the image and the context (the Gaussian part overrides the chain at
+    some steps, and those steps are the remaining near-ties); from peak = 6 on every margin is > 40 ulps and the
+    sequence is a function of the prompt's last token only (a strict end-to-end plumbing check)."""
+    wte = sd["text.wte"].float()
+    perm = torch.randperm(wte.shape[0], generator=torch.Generator(device="cpu").manual_seed(1_000_003 + seed))
+    tied = torch.empty_like(wte)
+    tied[perm] = wte / wte.norm(dim=1, keepdim=True)
+    return (sd["text.lm_head.weight"].float() + peak * tied).to(torch.bfloat16)
 
 
 def tensor_hash(t: torch.Tensor) -> str:

@@ -136,8 +136,6 @@ def test_sampling_settings(api):
     assert len(both) == 2 and all(isinstance(o["caption"], str) for o in both)
 
 
-@pytest.mark.skipif(__import__("os").environ.get("MD_EXPERIMENTAL") != "1",
-                    reason="staged after the round's GPU budget was spent: not yet run on hardware (MD_EXPERIMENTAL=1)")
 def test_spatial_refs_match_the_reference_golden(api):
     """query(spatial_refs=...) against tests/golden/tiny_spatial_refs.json: the rows of the prompt embedding that carry
     the region encodings (placement and values) and the answer tokens."""
