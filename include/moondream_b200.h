@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define MD_ABI_VERSION 1
+#define MD_ABI_VERSION 2
 
 /* epilogue selectors for the linear entry points */
 #define MD_EPI_BIAS 0          /* y = bf16(x W^T + b)                        layers.py:34-35   */
@@ -89,7 +89,7 @@ int md_layernorm_bf16(const void* x, long long ldx, const void* w, const void* b
  */
 int md_vit_attention_bf16(const void* qkv, int n_crops, int seq, int n_heads, void* out, void* stream);
 
-/* Paged KV cache handle: pool bf16 [layers][n_pages][2][heads][64 tokens][64 dims];
+/* Paged KV cache handle: pool bf16 [layers][n_pages][2][kv_heads][64 tokens][64 dims];
  * block_tables int32 [n_seqs][max_blocks] (page of positions 64*i..64*i+63 of each sequence). */
 typedef struct md_kv {
   void* pool;
@@ -97,11 +97,15 @@ typedef struct md_kv {
   const int* block_tables;
   int max_blocks;
   int n_layers;            /* layers in the pool (bounds the TMA view of the pool) */
+  int n_kv_heads;          /* heads in the pool; 0 = as many as query heads.  Fewer = grouped-query attention
+                            * (text.py:49 enable_gqa): query head h reads KV head h / (n_heads / n_kv_heads) */
 } md_kv;
 
 /* Partial RoPE (first 32 of 64 dims, split-half in / interleaved out, rope.py:20-48) on q and k of
  * fused qkv [tokens, 3*H*64]; q -> q_out [tokens, H*64]; k, v -> KV pages (moondream.py:74-78).
  * q_offsets == NULL means one token per sequence at position start_pos[seq] (decode). */
+/* (multi-head layout only: kv->n_kv_heads must be 0 or n_heads; grouped-query models go through the model-level
+ * entry points, whose QKV epilogues handle the narrower k / v column blocks) */
 int md_rope_kv_write_bf16(const void* qkv, int n_tokens, int n_heads, const int* q_offsets,
                           const int* start_pos, int n_seqs, const float* rope_table, void* q_out,
                           const md_kv* kv, int layer, void* stream);
@@ -120,8 +124,8 @@ void md_debug_set_pdl(int enable);
  * bit0 [qkv;fc1] GEMM, bit1 its epilogue, bit2 attention, bit3 [proj|fc2] GEMM, bit4 residual+LN epilogue. */
 void md_debug_skip_decode_kernels(int mask);
 /* Timing experiments only, small-batch weight stream:
- * bit2 previous split plan of the [proj | fc2] stream (equal splits); bit6 M = 64 MMAs for batches <= 64
- * (experimental, not yet validated on hardware).  Other bits are ignored. */
+ * bit2 previous split plan of the [proj | fc2] stream (equal splits); bit6 forces M = 128 MMAs for batches <= 64
+ * (the default there is M = 64).  Other bits are ignored. */
 void md_debug_gemm(int flags);
 /* Experiments only: cap the persistent row-form GEMM's grid at `sms` SMs (0 = all, the default), leaving the others
  * to kernels of a concurrent stream (encode / decode overlap). */
@@ -153,6 +157,9 @@ typedef struct md_dims {
    * W2 = [proj.weight | fc2.weight]  ([D, D + FF], row pitch D + FF).  md_model_create checks the
    * pointer relationships.  md_text_decode_step requires it (one weight stream per pair). */
   int txt_fused;
+  /* KV heads of the decoder (TextConfig.n_kv_heads, config.py:13); 0 = txt_heads.  qkv.weight then has
+   * txt_dim + 2 * txt_kv_heads * 64 rows (text.py:36-38) and the KV pool txt_kv_heads heads. */
+  int txt_kv_heads;
 } md_dims;
 
 typedef struct md_model md_model;
@@ -187,17 +194,26 @@ long long md_vision_project_workspace_bytes(const md_model* model, int n_images)
 int md_vision_project(md_model* model, const void* feats, const int* crop_offsets, const int* tilings,
                       int n_images, void* embeds, int rows_per_image, void* workspace, void* stream);
 
+/* `_vis_proj(g, r)` with the reference's own signature (moondream.py:171-172, vision.py:77-89) for one image:
+ * global_feats bf16 [grid^2, vis_dim], stitched bf16 [height, width, vis_dim] (reconstruct_from_crops' output)
+ * -> out bf16 [grid^2, txt_dim].  Workspace: md_vision_project_workspace_bytes(model, 1). */
+int md_vision_project_stitched(md_model* model, const void* global_feats, const void* stitched, int height, int width,
+                               void* out, void* workspace, void* stream);
+
 /* text_encoder (text.py:12-13): out[i] = wte[ids[i * id_stride]]. */
 int md_embed_tokens(md_model* model, const int* ids, long long id_stride, int n, void* out,
                     long long ldo, void* stream);
 
 /* _prefill (text.py:128-160) over a ragged batch: x [total_tokens, txt_dim] embeddings in, hidden
  * states out (in place); sequence s owns rows q_offsets[s]..q_offsets[s+1] at positions
- * start_pos[s]...; K/V are written to the pages. */
+ * start_pos[s]...; K/V are written to the pages.
+ * prefix_len: positions < prefix_len attend bidirectionally among themselves (the image prefix of
+ * moondream.py:143-145); -1 = the model's (730); 0 = pure causal, which is the mask the reference builds for
+ * a text-only query (moondream.py:565-574). */
 long long md_text_prefill_workspace_bytes(const md_model* model, int total_tokens);
 int md_text_prefill(md_model* model, void* x, int total_tokens, const int* q_offsets,
-                    const int* start_pos, int n_seqs, int max_q, const md_kv* kv, void* workspace,
-                    void* stream);
+                    const int* start_pos, int n_seqs, int max_q, int prefix_len, const md_kv* kv,
+                    void* workspace, void* stream);
 
 /* _decode_one_tok's decoder half (text.py:128-160 with T=1) for `batch` sequences:
  * x [batch, txt_dim] embeddings in, hidden out (in place); pos int32 [batch] (device).
@@ -211,13 +227,35 @@ int md_text_decode_step(md_model* model, void* x, const int* pos, int batch, con
 
 /* lm_head + greedy argmax (text.py:163-167, moondream.py:313-314,517-524): hidden rows
  * [batch] x txt_dim (stride ld_hidden).  Token ids go to out_ids[b * out_stride + *out_index]
- * (out_index: device int or NULL = 0); mask_id >= 0 is excluded (answer_id, moondream.py:517).
+ * (out_index: device int or NULL = 0); mask_id / mask_id2 >= 0 are excluded (answer_id in
+ * _generate_answer, moondream.py:517; eos_id and size_id in _generate_reasoning, :395-396).
  * prenormed != 0: `hidden` already holds post_ln(hidden) (from md_text_decode_step's normed_out).
  * Optional: out_margin (same addressing, top1 - top2 of the bf16 logits), out_logits bf16 [batch, vocab]. */
 long long md_lm_head_workspace_bytes(const md_model* model, int batch);
 int md_lm_head_argmax(md_model* model, const void* hidden, long long ld_hidden, int prenormed, int batch,
-                      int mask_id, int* out_ids, long long out_stride, const int* out_index,
+                      int mask_id, int mask_id2, int* out_ids, long long out_stride, const int* out_index,
                       float* out_margin, void* out_logits, void* workspace, void* stream);
+
+/* Temperature / top-p sampling on the device (moondream.py:270-278 `_apply_top_p`, :312-318, :524-530), one CTA per
+ * sequence, no sort: probs = softmax(logits / temperature) rounded like the reference's bf16 tensors; the kept set
+ * is the prefix of (probability descending, index ascending) order whose preceding mass, in the reference's bf16
+ * arithmetic, does not exceed top_p (found through a histogram of probability values); the kept probabilities are
+ * renormalised and one token is drawn by inverse CDF in index order from a uniform u: uniforms[b] when given
+ * (tests), else Philox4x32-10 keyed by *seed with counter (b, *step + out_offset), so CUDA-graph replays draw fresh
+ * numbers as the device-side step advances.  logits bf16 [batch, vocab] (md_lm_head_argmax's out_logits, masks
+ * already applied); scratch bf16 [batch, vocab]; when keep_probs != 0 scratch returns the reference's `next_probs`.
+ * The token goes to out_ids[b * out_stride + *step + out_offset] (step NULL = 0). */
+int md_sample_top_p(const void* logits, int batch, int vocab, float temperature, float top_p,
+                    const unsigned long long* seed, const int* step, const float* uniforms, void* scratch,
+                    int keep_probs, int* out_ids, long long out_stride, int out_offset, void* stream);
+
+/* text_encoder with substitution (moondream.py:381-391): out[i] = ids[i*id_stride] == sel_id ? alt[i] : wte[id]. */
+int md_embed_tokens_select(md_model* model, const int* ids, long long id_stride, int n, int sel_id,
+                           const void* alt, long long ld_alt, void* out, long long ldo, void* stream);
+
+/* dst[i * stride + *index + offset] = src[i] (per-step record of decoded coordinates; index NULL = 0). */
+int md_store_column_f32(const float* src, int n, float* dst, long long stride, const int* index, int offset,
+                        void* stream);
 
 /* Decode-loop bookkeeping on the device (the generator loop of moondream.py:481-530 without the
  * per-token .item() sync): cur_tok[b] = (forced ? forced : preds)[b*stride + step+1]; pos[b] += 1;
@@ -238,8 +276,9 @@ int md_region_decode(md_model* model, int which, const void* hidden, long long l
  * (region.py:32-43, 60-71 incl. fourier_features :12-29). */
 int md_region_encode(md_model* model, int which, const float* values, int batch, void* out,
                      long long ldo, void* workspace, void* stream);
-/* bins -> values (moondream.py:673,683,701-702): coord = bin / 1024; size = 2^(bin/1023*10 - 10). */
-int md_region_bins_to_values(int which, const int* bins, int n, float* out, void* stream);
+/* bins -> values (moondream.py:673,683,701-702): coord = bin / n_bins (n_bins = coord_out_dim, the size of the
+ * logits' last dimension); size = 2^(bin/1023*10 - 10) (the reference hard-codes 1023). */
+int md_region_bins_to_values(int which, const int* bins, int n, int n_bins, float* out, void* stream);
 
 #ifdef __cplusplus
 }

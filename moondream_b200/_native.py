@@ -16,14 +16,14 @@ _lib = None
 
 class md_kv(ctypes.Structure):
     _fields_ = [("pool", c_void_p), ("n_pages", c_int), ("block_tables", c_void_p), ("max_blocks", c_int),
-                ("n_layers", c_int)]
+                ("n_layers", c_int), ("n_kv_heads", c_int)]
 
 
 class md_dims(ctypes.Structure):
     _fields_ = [(n, c_int) for n in (
         "vis_dim", "vis_ff", "vis_layers", "vis_heads", "crop", "patch", "patch_k", "grid", "margin",
         "proj_inner", "txt_dim", "txt_ff", "txt_layers", "txt_heads", "vocab", "max_context",
-        "prefix_len", "reg_inner", "coord_feat", "coord_out", "size_feat", "size_out", "txt_fused")]
+        "prefix_len", "reg_inner", "coord_feat", "coord_out", "size_feat", "size_out", "txt_fused", "txt_kv_heads")]
 
 
 _P = c_void_p
@@ -65,19 +65,24 @@ _SIGNATURES = {
     "md_vision_encode": (c_int, [_P, _P, c_int, _P, _P, _P]),
     "md_vision_project_workspace_bytes": (_LL, [_P, c_int]),
     "md_vision_project": (c_int, [_P, _P, _P, _P, c_int, _P, c_int, _P, _P]),
+    "md_vision_project_stitched": (c_int, [_P, _P, _P, c_int, c_int, _P, _P, _P]),
     "md_embed_tokens": (c_int, [_P, _P, _LL, c_int, _P, _LL, _P]),
     "md_text_prefill_workspace_bytes": (_LL, [_P, c_int]),
-    "md_text_prefill": (c_int, [_P, _P, c_int, _P, _P, c_int, c_int, _KV, _P, _P]),
+    "md_text_prefill": (c_int, [_P, _P, c_int, _P, _P, c_int, c_int, c_int, _KV, _P, _P]),
     "md_text_decode_workspace_bytes": (_LL, [_P, c_int]),
     "md_text_decode_step": (c_int, [_P, _P, _P, c_int, _KV, _P, _P, _P]),
     "md_lm_head_workspace_bytes": (_LL, [_P, c_int]),
-    "md_lm_head_argmax": (c_int, [_P, _P, _LL, c_int, c_int, c_int, _P, _LL, _P, _P, _P, _P, _P]),
+    "md_lm_head_argmax": (c_int, [_P, _P, _LL, c_int, c_int, c_int, c_int, _P, _LL, _P, _P, _P, _P, _P]),
+    "md_sample_top_p": (c_int, [_P, c_int, c_int, ctypes.c_float, ctypes.c_float, _P, _P, _P, _P, c_int, _P, _LL,
+                                c_int, _P]),
+    "md_embed_tokens_select": (c_int, [_P, _P, _LL, c_int, c_int, _P, _LL, _P, _LL, _P]),
+    "md_store_column_f32": (c_int, [_P, c_int, _P, _LL, _P, c_int, _P]),
     "md_decode_advance": (c_int, [_P, _P, _P, _P, _P, _LL, c_int, c_int, _P, _P]),
     "md_gather_rows_bf16": (c_int, [_P, _LL, _P, c_int, c_int, _P, _LL, _P]),
     "md_region_workspace_bytes": (_LL, [_P, c_int]),
     "md_region_decode": (c_int, [_P, c_int, _P, _LL, c_int, _P, _P, _P]),
     "md_region_encode": (c_int, [_P, c_int, _P, c_int, _P, _LL, _P, _P]),
-    "md_region_bins_to_values": (c_int, [c_int, _P, c_int, _P, _P]),
+    "md_region_bins_to_values": (c_int, [c_int, _P, c_int, c_int, _P, _P]),
 }
 
 

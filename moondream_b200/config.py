@@ -130,9 +130,13 @@ class MoondreamConfig:
         t, v, r = self.text, self.vision, self.region
         if t.dim % t.n_heads or t.head_dim != 64:
             raise ValueError("text head_dim must be 64 (partial RoPE over 32 dims, rope.py:20-48)")
-        if t.n_kv_heads != t.n_heads:
-            raise ValueError("only n_kv_heads == n_heads is shipped by the reference configs "
-                             "(config.py:12-13); set text.n_kv_heads explicitly for the 0.5B")
+        if t.n_kv_heads <= 0 or t.n_heads % t.n_kv_heads:
+            raise ValueError("text.n_heads must be a multiple of text.n_kv_heads (grouped-query attention, "
+                             "text.py:49); the 0.5B JSON omits n_kv_heads and the reference default of 32 does not "
+                             "divide its 16 heads: set it explicitly")
+        if t.ff_dim % (2 * t.n_heads):
+            raise ValueError("text.ff_dim must be a multiple of 2 * n_heads (the fused decode attention finishes an "
+                             "equal, even slice of the fc1 features per head)")
         if v.enc_dim % v.enc_n_heads or v.head_dim != 72:
             raise ValueError("vision head_dim must be 72")
         if v.crop_size % v.enc_patch_size:
@@ -185,7 +189,18 @@ def tiny() -> MoondreamConfig:
     )
 
 
-PRESETS = {"moondream-2b": moondream_2b, "moondream-0.5b": moondream_0_5b, "tiny": tiny}
+def tiny_gqa() -> MoondreamConfig:
+    """`tiny` with grouped-query attention in the decoder: 4 query heads share 2 KV heads (text.py:36-38,49)."""
+    base = tiny()
+    return MoondreamConfig(
+        text=TextConfig(dim=256, ff_dim=512, n_layers=4, vocab_size=2048, n_heads=4, n_kv_heads=2),
+        vision=dataclasses.replace(base.vision, proj_out_dim=256),
+        region=RegionConfig(dim=256, inner_dim=512),
+        tokenizer=base.tokenizer,
+    )
+
+
+PRESETS = {"moondream-2b": moondream_2b, "moondream-0.5b": moondream_0_5b, "tiny": tiny, "tiny-gqa": tiny_gqa}
 
 
 def preset(name: str) -> MoondreamConfig:

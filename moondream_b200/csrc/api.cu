@@ -91,6 +91,7 @@ int md_rope_kv_write_bf16(const void* qkv, int n_tokens, int n_heads, const int*
                           const int* start_pos, int n_seqs, const float* rope_table, void* q_out,
                           const md_kv* kv, int layer, void* stream) {
   NEED(qkv && start_pos && rope_table && q_out && kv && kv->pool && kv->block_tables, "md_rope_kv_write_bf16");
+  if (kv->n_kv_heads && kv->n_kv_heads != n_heads) return md::set_error("md_rope_kv_write_bf16: multi-head layout only");
   return md::rope_kv_write(BF(qkv), n_tokens, n_heads, q_offsets, start_pos, n_seqs, rope_table,
                            BFM(q_out), BFM(kv->pool), kv->n_pages, kv->block_tables, kv->max_blocks,
                            layer, STREAM(stream));
@@ -100,11 +101,13 @@ int md_prefill_attention_bf16(const void* q, int n_heads, int total_tokens, cons
                               const int* start_pos, int n_seqs, int max_q, int prefix_len,
                               const md_kv* kv, int layer, void* out, void* stream) {
   NEED(q && q_offsets && start_pos && kv && kv->pool && kv->block_tables && out, "md_prefill_attention_bf16");
+  if (md::g_attention_impl == 1 && kv->n_kv_heads && kv->n_kv_heads != n_heads)
+    return md::set_error("md_prefill_attention_bf16: the legacy mma.sync attention has no grouped-query path");
   if (md::g_attention_impl == 1)
     return md::prefill_attention(BF(q), n_heads, q_offsets, start_pos, n_seqs, max_q, prefix_len,
                                  BF(kv->pool), kv->n_pages, kv->block_tables, kv->max_blocks, layer,
                                  BFM(out), STREAM(stream));
-  return md::prefill_attention_tc(BF(q), n_heads, total_tokens, q_offsets, start_pos, n_seqs, max_q, prefix_len,
+  return md::prefill_attention_tc(BF(q), n_heads, kv->n_kv_heads, total_tokens, q_offsets, start_pos, n_seqs, max_q, prefix_len,
                                   BF(kv->pool), kv->n_pages, kv->n_layers, kv->block_tables, kv->max_blocks,
                                   layer, BFM(out), STREAM(stream));
 }
@@ -120,7 +123,7 @@ int md_debug_timeline(void* records, void* count, unsigned int capacity) {
 int md_decode_attention_bf16(const void* q, int n_heads, const int* pos, int n_seqs, const md_kv* kv,
                              int layer, void* out, void* stream) {
   NEED(q && pos && kv && kv->pool && kv->block_tables && out, "md_decode_attention_bf16");
-  return md::decode_attention(BF(q), n_heads, pos, n_seqs, BF(kv->pool), kv->n_pages, kv->block_tables,
+  return md::decode_attention(BF(q), n_heads, kv->n_kv_heads, pos, n_seqs, BF(kv->pool), kv->n_pages, kv->block_tables,
                               kv->max_blocks, layer, BFM(out), static_cast<long long>(n_heads) * 64,
                               STREAM(stream));
 }
@@ -161,6 +164,13 @@ int md_vision_project(md_model* model, const void* feats, const int* crop_offset
                             workspace, STREAM(stream));
 }
 
+int md_vision_project_stitched(md_model* model, const void* global_feats, const void* stitched, int height, int width,
+                               void* out, void* workspace, void* stream) {
+  NEED(model && global_feats && stitched && out && workspace, "md_vision_project_stitched");
+  return md::vision_project_stitched(*model, BF(global_feats), BF(stitched), height, width, BFM(out), workspace,
+                                     STREAM(stream));
+}
+
 int md_embed_tokens(md_model* model, const int* ids, long long id_stride, int n, void* out,
                     long long ldo, void* stream) {
   NEED(model && ids && out, "md_embed_tokens");
@@ -172,11 +182,11 @@ long long md_text_prefill_workspace_bytes(const md_model* model, int total_token
   return model ? md::text_prefill_ws_bytes(*model, total_tokens) : -1;
 }
 int md_text_prefill(md_model* model, void* x, int total_tokens, const int* q_offsets,
-                    const int* start_pos, int n_seqs, int max_q, const md_kv* kv, void* workspace,
-                    void* stream) {
+                    const int* start_pos, int n_seqs, int max_q, int prefix_len, const md_kv* kv,
+                    void* workspace, void* stream) {
   NEED(model && x && q_offsets && start_pos && kv && kv->pool && kv->block_tables && workspace, "md_text_prefill");
-  return md::text_prefill(*model, BFM(x), total_tokens, q_offsets, start_pos, n_seqs, max_q, *kv, workspace,
-                          STREAM(stream));
+  return md::text_prefill(*model, BFM(x), total_tokens, q_offsets, start_pos, n_seqs, max_q, prefix_len, *kv,
+                          workspace, STREAM(stream));
 }
 
 long long md_text_decode_workspace_bytes(const md_model* model, int batch) {
@@ -192,11 +202,32 @@ long long md_lm_head_workspace_bytes(const md_model* model, int batch) {
   return model ? md::lm_head_ws_bytes(*model, batch) : -1;
 }
 int md_lm_head_argmax(md_model* model, const void* hidden, long long ld_hidden, int prenormed, int batch,
-                      int mask_id, int* out_ids, long long out_stride, const int* out_index,
+                      int mask_id, int mask_id2, int* out_ids, long long out_stride, const int* out_index,
                       float* out_margin, void* out_logits, void* workspace, void* stream) {
   NEED(model && hidden && out_ids && workspace, "md_lm_head_argmax");
-  return md::lm_head_argmax(*model, BF(hidden), ld_hidden, prenormed, batch, mask_id, out_ids, out_stride,
+  return md::lm_head_argmax(*model, BF(hidden), ld_hidden, prenormed, batch, mask_id, mask_id2, out_ids, out_stride,
                             out_index, out_margin, BFM(out_logits), workspace, STREAM(stream));
+}
+
+int md_sample_top_p(const void* logits, int batch, int vocab, float temperature, float top_p,
+                    const unsigned long long* seed, const int* step, const float* uniforms, void* scratch,
+                    int keep_probs, int* out_ids, long long out_stride, int out_offset, void* stream) {
+  NEED(logits && scratch && out_ids, "md_sample_top_p");
+  return md::sample_top_p(BF(logits), batch, vocab, temperature, top_p, seed, step, uniforms, BFM(scratch), keep_probs,
+                          out_ids, out_stride, out_offset, STREAM(stream));
+}
+
+int md_embed_tokens_select(md_model* model, const int* ids, long long id_stride, int n, int sel_id,
+                           const void* alt, long long ld_alt, void* out, long long ldo, void* stream) {
+  NEED(model && ids && out, "md_embed_tokens_select");
+  return md::embed_select(ids, id_stride, n, model->wte, model->d.txt_dim, model->d.vocab, sel_id, BF(alt), ld_alt,
+                          BFM(out), ldo, STREAM(stream));
+}
+
+int md_store_column_f32(const float* src, int n, float* dst, long long stride, const int* index, int offset,
+                        void* stream) {
+  NEED(src && dst, "md_store_column_f32");
+  return md::store_column_f32(src, n, dst, stride, index, offset, STREAM(stream));
 }
 
 int md_decode_advance(int* cur_tok, int* pos, int* step, const int* preds, const int* forced,
@@ -227,9 +258,9 @@ int md_region_encode(md_model* model, int which, const float* values, int batch,
   if (which != 0 && which != 1) return md::set_error("md_region_encode: which must be 0 or 1");
   return md::region_encode(*model, which, values, batch, BFM(out), ldo, workspace, STREAM(stream));
 }
-int md_region_bins_to_values(int which, const int* bins, int n, float* out, void* stream) {
+int md_region_bins_to_values(int which, const int* bins, int n, int n_bins, float* out, void* stream) {
   NEED(bins && out, "md_region_bins_to_values");
-  return md::bins_to_values(which, bins, n, out, STREAM(stream));
+  return md::bins_to_values(which, bins, n, n_bins, out, STREAM(stream));
 }
 
 }  // extern "C"

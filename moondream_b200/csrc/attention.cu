@@ -353,7 +353,7 @@ struct DecodeFuse {
 // partial wave costs ~10 us per layer (measured with tools/decode_timeline.py)
 template <bool FUSED>
 __global__ void __launch_bounds__(128, 7)
-decode_attention_kernel(const __nv_bfloat16* __restrict__ q, int n_heads, const int* __restrict__ pos,
+decode_attention_kernel(const __nv_bfloat16* __restrict__ q, int n_heads, int n_kv_heads, const int* __restrict__ pos,
                         __nv_bfloat16* __restrict__ kv_pool, int n_pages,
                         const int* __restrict__ block_tables, int max_blocks, int layer,
                         __nv_bfloat16* __restrict__ out, long long ld_out, float scale_log2, const DecodeFuse fz) {
@@ -372,8 +372,13 @@ decode_attention_kernel(const __nv_bfloat16* __restrict__ q, int n_heads, const 
   const int cur = pos[seq];
   const int kv_len = cur + 1;          // the current token's K/V row is part of the context
   const int* btab = block_tables + static_cast<long long>(seq) * max_blocks;
-  const long long head_off = static_cast<long long>(head) * (kPageTokens * 64);
-  const long long v_off = static_cast<long long>(n_heads) * (kPageTokens * 64);
+  // grouped-query attention (text.py:49 enable_gqa): query head h reads KV head h / (H / KVH).  The G query heads
+  // of a group are neighbouring CTAs, so the group's K/V rows come from HBM once and from L2 for the others.
+  // (The fused prologue writes the new K/V row of its own head and therefore needs KVH == H; engine.cu routes
+  // grouped models through decode_qkv_finish + the plain kernel.)
+  const int kv_head = FUSED ? head : head / (n_heads / n_kv_heads);
+  const long long head_off = static_cast<long long>(kv_head) * (kPageTokens * 64);
+  const long long v_off = static_cast<long long>(n_kv_heads) * (kPageTokens * 64);
 
   __shared__ float sq[64];
   float qv[8];
@@ -385,7 +390,7 @@ decode_attention_kernel(const __nv_bfloat16* __restrict__ q, int n_heads, const 
     if (tid < kv_len) {
       const int page = btab[tid >> 6];
       const __nv_bfloat16* kp = kv_pool +
-          ((static_cast<long long>(layer) * n_pages + page) * 2) * n_heads * (kPageTokens * 64) + head_off + (tid & 63) * 64;
+          ((static_cast<long long>(layer) * n_pages + page) * 2) * n_kv_heads * (kPageTokens * 64) + head_off + (tid & 63) * 64;
       prefetch_l2(kp);
       prefetch_l2(kp + v_off);
     }
@@ -470,7 +475,7 @@ decode_attention_kernel(const __nv_bfloat16* __restrict__ q, int n_heads, const 
   for (int k0 = warp * 16; k0 < kv_len; k0 += 64) {
     const int page = btab[k0 >> 6];
     const __nv_bfloat16* kp = kv_pool +
-        ((static_cast<long long>(layer) * n_pages + page) * 2) * n_heads * (kPageTokens * 64) + head_off;
+        ((static_cast<long long>(layer) * n_pages + page) * 2) * n_kv_heads * (kPageTokens * 64) + head_off;
     uint4 kq[4], vq[4];
 #pragma unroll
     for (int st = 0; st < 4; ++st) {
@@ -535,13 +540,15 @@ decode_attention_kernel(const __nv_bfloat16* __restrict__ q, int n_heads, const 
 
 void timeline_install_attention(const Timeline& t) { timeline_install(t); }
 
-int decode_attention(const __nv_bfloat16* q, int n_heads, const int* pos, int n_seqs,
+int decode_attention(const __nv_bfloat16* q, int n_heads, int n_kv_heads, const int* pos, int n_seqs,
                      const __nv_bfloat16* kv_pool, int n_pages, const int* block_tables,
                      int max_blocks, int layer, __nv_bfloat16* out, long long ld_out, cudaStream_t stream) {
   if (n_seqs <= 0) return set_error("decode_attention: empty batch");
+  if (n_kv_heads <= 0) n_kv_heads = n_heads;
+  if (n_heads % n_kv_heads) return set_error("decode_attention: n_heads must be a multiple of n_kv_heads");
   dim3 grid(n_heads, n_seqs);
   count_launch();
-  cudaError_t e = launch_k(decode_attention_kernel<false>, grid, dim3(128), 0, stream, q, n_heads, pos,
+  cudaError_t e = launch_k(decode_attention_kernel<false>, grid, dim3(128), 0, stream, q, n_heads, n_kv_heads, pos,
                            const_cast<__nv_bfloat16*>(kv_pool), n_pages, block_tables, max_blocks, layer, out, ld_out,
                            0.125f * 1.4426950408889634f, DecodeFuse{});
   if (e != cudaSuccess) return set_error(cudaGetErrorString(e));
@@ -559,8 +566,82 @@ int decode_attention_fused(const float* ws, int splits, int D, int FF, const __n
   dim3 grid(n_heads, n_seqs);
   count_launch();
   cudaError_t e = launch_k(decode_attention_kernel<true>, grid, dim3(128), 0, stream,
-                           static_cast<const __nv_bfloat16*>(nullptr), n_heads, pos, kv_pool, n_pages, block_tables,
+                           static_cast<const __nv_bfloat16*>(nullptr), n_heads, n_heads, pos, kv_pool, n_pages, block_tables,
                            max_blocks, layer, out, ld_out, 0.125f * 1.4426950408889634f, fz);
+  if (e != cudaSuccess) return set_error(cudaGetErrorString(e));
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Grouped-query models (n_kv_heads < n_heads): finish the [qkv ; fc1] weight stream in a separate small kernel —
+// split-K sum in fixed order + bias + bf16 rounding (the Linear outputs, text.py:30 / layers.py:130), partial RoPE on
+// q and k (rope.py:20-48), the new K/V row into its page (moondream.py:74-78), GELU on the fc1 slice — then run the
+// plain decode attention.  Columns of the stream: q [0, D) | k [D, D + KVW) | v [.., D + 2 KVW) | fc1 [.., + FF).
+// One CTA per sequence; a thread owns one rotation pair (j, j + 16) or two neighbouring pass-through features.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+decode_qkv_finish_kernel(const float* __restrict__ ws, int splits, int B, int D, int n_kv_heads, int FF,
+                         const __nv_bfloat16* __restrict__ bias, const float* __restrict__ freqs,
+                         const int* __restrict__ pos, __nv_bfloat16* __restrict__ q_out,
+                         __nv_bfloat16* __restrict__ kv_pool, int n_pages, const int* __restrict__ block_tables,
+                         int max_blocks, int layer, __nv_bfloat16* __restrict__ hid, long long ld_hid) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int seq = blockIdx.x;
+  const int kvw = n_kv_heads * 64;
+  const int NF = D + 2 * kvw + FF;
+  const long long sstride = static_cast<long long>(B) * NF;
+  const float* ws0 = ws + static_cast<long long>(seq) * NF;
+  const int cur = pos[seq];
+  const int page = block_tables[static_cast<long long>(seq) * max_blocks + (cur >> 6)];
+  __nv_bfloat16* krow = kv_pool + ((static_cast<long long>(layer) * n_pages + page) * 2) * n_kv_heads * (kPageTokens * 64) +
+                        (cur & 63) * 64;
+  const long long v_off = static_cast<long long>(n_kv_heads) * (kPageTokens * 64);
+  auto lin = [&](int f) {
+    float a = ws0[f];
+    for (int s2 = 1; s2 < splits; ++s2) a += ws0[s2 * sstride + f];
+    return bf16_round(a + __bfloat162float(bias[f]));
+  };
+  // q and k heads: 32 work items per head = 16 rotation pairs + 16 pass-through pairs
+  const int qk_heads = D / 64 + n_kv_heads;
+  for (int w = threadIdx.x; w < qk_heads * 32; w += blockDim.x) {
+    const int h = w >> 5, i = w & 31;
+    const bool is_q = h < D / 64;
+    const int base = is_q ? h * 64 : D + (h - D / 64) * 64;
+    __nv_bfloat16* dst = is_q ? q_out + static_cast<long long>(seq) * D + h * 64
+                              : krow + static_cast<long long>(h - D / 64) * (kPageTokens * 64);
+    if (i < 16) {
+      const float re = lin(base + i), im = lin(base + 16 + i);
+      const float cs = freqs[(cur * 16 + i) * 2], sn = freqs[(cur * 16 + i) * 2 + 1];
+      const float o0 = __fsub_rn(__fmul_rn(re, cs), __fmul_rn(im, sn));
+      const float o1 = __fadd_rn(__fmul_rn(re, sn), __fmul_rn(im, cs));
+      *reinterpret_cast<uint32_t*>(dst + 2 * i) = pack_bf16x2(o0, o1);          // interleaved (re', im')
+    } else {
+      const int d = 32 + 2 * (i - 16);
+      *reinterpret_cast<uint32_t*>(dst + d) = pack_bf16x2(lin(base + d), lin(base + d + 1));
+    }
+  }
+  for (int w = threadIdx.x; w < kvw / 2; w += blockDim.x) {                       // v rows
+    const int h = (2 * w) >> 6, d = (2 * w) & 63;
+    const int f = D + kvw + 2 * w;
+    *reinterpret_cast<uint32_t*>(krow + v_off + static_cast<long long>(h) * (kPageTokens * 64) + d) =
+        pack_bf16x2(lin(f), lin(f + 1));
+  }
+  for (int w = threadIdx.x; w < FF / 2; w += blockDim.x) {                        // gelu(fc1)
+    const int f = D + 2 * kvw + 2 * w;
+    *reinterpret_cast<uint32_t*>(hid + seq * ld_hid + 2 * w) = pack_bf16x2(gelu_tanh(lin(f)), gelu_tanh(lin(f + 1)));
+  }
+}
+
+int decode_qkv_finish(const float* ws, int splits, int B, int D, int n_kv_heads, int FF, const __nv_bfloat16* bias,
+                      const float* freqs, const int* pos, __nv_bfloat16* q_out, __nv_bfloat16* kv_pool, int n_pages,
+                      const int* block_tables, int max_blocks, int layer, __nv_bfloat16* hid, long long ld_hid,
+                      cudaStream_t stream) {
+  if (B <= 0) return set_error("decode_qkv_finish: empty batch");
+  if (D % 64 || FF % 2 || n_kv_heads <= 0) return set_error("decode_qkv_finish: unsupported shape");
+  count_launch();
+  cudaError_t e = launch_k(decode_qkv_finish_kernel, dim3(B), dim3(256), 0, stream, ws, splits, B, D, n_kv_heads, FF, bias,
+                           freqs, pos, q_out, kv_pool, n_pages, block_tables, max_blocks, layer, hid, ld_hid);
   if (e != cudaSuccess) return set_error(cudaGetErrorString(e));
   return 0;
 }

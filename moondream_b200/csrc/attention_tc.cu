@@ -113,7 +113,7 @@ struct FaTcParams {
   const int* q_offsets;     // [n_seqs + 1]
   const int* start_pos;     // [n_seqs]
   const int* block_tables;  // [n_seqs][max_blocks]
-  int max_blocks, n_heads, layer, n_pages, prefix_len;
+  int max_blocks, n_heads, n_kv_heads, layer, n_pages, prefix_len;
   __nv_bfloat16* out;       // [T_total, n_heads * 64]
   float scale_log2;
 };
@@ -181,7 +181,8 @@ fa_tc_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     if (lane == 0) {
       mbar_arrive_expect_tx(q_full, kQBytes);
       tma_load_2d(sQ, &tmQ, q_full, head * HD, q_off + q0);
-      const long long page_rows = 2LL * p.n_heads * 64;                 // rows of one page (k then v)
+      const long long page_rows = 2LL * p.n_kv_heads * 64;              // rows of one page (k then v)
+      const int kv_head = head / (p.n_heads / p.n_kv_heads);           // grouped-query attention (text.py:49)
       for (int j = 0; j < n_tiles; ++j) {
         const int st = j & 1;
         const uint32_t u = static_cast<uint32_t>(j >> 1);
@@ -191,10 +192,10 @@ fa_tc_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         for (int h2 = 0; h2 < 2; ++h2) {
           const int blk = min(2 * j + h2, p.max_blocks - 1);
           const long long row_k = (static_cast<long long>(p.layer) * p.n_pages + btab[blk]) * page_rows +
-                                  static_cast<long long>(head) * 64;
+                                  static_cast<long long>(kv_head) * 64;
           tma_load_2d(sK + st * kKVBytes + h2 * (kKVBytes / 2), &tmKV, &kv_full[st], 0, static_cast<int32_t>(row_k));
           tma_load_2d(sV + st * kKVBytes + h2 * (kKVBytes / 2), &tmKV, &kv_full[st], 0,
-                      static_cast<int32_t>(row_k + static_cast<long long>(p.n_heads) * 64));
+                      static_cast<int32_t>(row_k + static_cast<long long>(p.n_kv_heads) * 64));
         }
       }
     }
@@ -349,15 +350,17 @@ fa_tc_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   }
 }
 
-int prefill_attention_tc(const __nv_bfloat16* q, int n_heads, int total_tokens, const int* q_offsets,
+int prefill_attention_tc(const __nv_bfloat16* q, int n_heads, int n_kv_heads, int total_tokens, const int* q_offsets,
                          const int* start_pos, int n_seqs, int max_q, int prefix_len,
                          const __nv_bfloat16* kv_pool, int n_pages, int n_layers, const int* block_tables,
                          int max_blocks, int layer, __nv_bfloat16* out, cudaStream_t stream) {
   if (n_seqs <= 0 || max_q <= 0) return set_error("prefill_attention: empty batch");
+  if (n_kv_heads <= 0) n_kv_heads = n_heads;
+  if (n_heads % n_kv_heads) return set_error("prefill_attention: n_heads must be a multiple of n_kv_heads");
   CUtensorMap tQ, tKV;
   if (make_tmap_bf16_2d(&tQ, q, total_tokens, static_cast<long long>(n_heads) * 64,
                         static_cast<long long>(n_heads) * 64, fa::BM)) return 1;
-  const long long pool_rows = static_cast<long long>(n_layers) * n_pages * 2 * n_heads * 64;
+  const long long pool_rows = static_cast<long long>(n_layers) * n_pages * 2 * n_kv_heads * 64;
   if (pool_rows >= (1LL << 31)) return set_error("prefill_attention: KV pool too large for 32-bit TMA coordinates");
   if (make_tmap_bf16_2d(&tKV, kv_pool, pool_rows, 64, 64, 64)) return 1;
   static DeviceOnce configured;
@@ -372,7 +375,7 @@ int prefill_attention_tc(const __nv_bfloat16* q, int n_heads, int total_tokens, 
   }
   FaTcParams p{};
   p.q_offsets = q_offsets; p.start_pos = start_pos; p.block_tables = block_tables;
-  p.max_blocks = max_blocks; p.n_heads = n_heads; p.layer = layer; p.n_pages = n_pages;
+  p.max_blocks = max_blocks; p.n_heads = n_heads; p.n_kv_heads = n_kv_heads; p.layer = layer; p.n_pages = n_pages;
   p.prefix_len = prefix_len; p.out = out;
   p.scale_log2 = 0.125f * 1.4426950408889634f;
   dim3 grid((max_q + fa::BM - 1) / fa::BM, n_heads, n_seqs);

@@ -200,6 +200,40 @@ stitch_pool_concat_kernel(const __nv_bfloat16* __restrict__ feats, const int* __
   (void)inv;
 }
 
+// The same pooling + concat for an ALREADY stitched map (the reference's `_vis_proj(g, r)` seam, vision.py:77-89):
+// global [g*g, dim], stitched [H, W, dim] -> out [g*g, 2*dim].
+__global__ void __launch_bounds__(256)
+pool_concat_kernel(const __nv_bfloat16* __restrict__ global_feats, const __nv_bfloat16* __restrict__ stitched,
+                   int H, int W, int g, int dim, __nv_bfloat16* __restrict__ out) {
+  const int cell = blockIdx.x;
+  const int oy = cell / g, ox = cell % g;
+  const int y0 = (oy * H) / g, y1 = ((oy + 1) * H + g - 1) / g;
+  const int x0 = (ox * W) / g, x1 = ((ox + 1) * W + g - 1) / g;
+  const float cnt = static_cast<float>((y1 - y0) * (x1 - x0));
+  __nv_bfloat16* o = out + static_cast<long long>(cell) * (2 * dim);
+  const __nv_bfloat16* gsrc = global_feats + static_cast<long long>(cell) * dim;
+  for (int d = threadIdx.x * 2; d < dim; d += blockDim.x * 2) {
+    *reinterpret_cast<uint32_t*>(o + d) = *reinterpret_cast<const uint32_t*>(gsrc + d);
+    float a0 = 0.f, a1 = 0.f;
+    for (int y = y0; y < y1; ++y)
+      for (int x = x0; x < x1; ++x) {
+        const uint32_t u = *reinterpret_cast<const uint32_t*>(stitched + (static_cast<long long>(y) * W + x) * dim + d);
+        a0 += bf16_lo(u);
+        a1 += bf16_hi(u);
+      }
+    *reinterpret_cast<uint32_t*>(o + dim + d) = pack_bf16x2(a0 / cnt, a1 / cnt);
+  }
+}
+
+int pool_concat(const __nv_bfloat16* global_feats, const __nv_bfloat16* stitched, int H, int W, int grid, int dim,
+                __nv_bfloat16* out, cudaStream_t stream) {
+  if (H <= 0 || W <= 0) return set_error("pool_concat: empty map");
+  if (dim % 2) return set_error("pool_concat: dim must be even");
+  pool_concat_kernel<<<grid * grid, 256, 0, stream>>>(global_feats, stitched, H, W, grid, dim, out);
+  MD_CHECK_LAUNCH();
+  return 0;
+}
+
 int stitch_pool_concat(const __nv_bfloat16* feats, const int* crop_offsets, const int* tilings,
                        int n_images, int grid, int margin, int dim, __nv_bfloat16* out,
                        cudaStream_t stream) {
@@ -311,7 +345,8 @@ int rope_kv_write(const __nv_bfloat16* qkv, int n_tokens, int n_heads, const int
 // greedy argmax over logits (reference text.py:163-167 + moondream.py:313-314,517-524).
 // logits arrive as fp32 partial sums [splits][B][V] from the small-batch GEMM; the reference's
 // logits are bf16, so values are rounded to bf16 before comparing and ties go to the lowest index
-// (torch.argmax).  `mask_id` >= 0 is forced to -inf (answer_id from the 2nd generated token on).
+// (torch.argmax).  `mask_id` / `mask_id2` >= 0 are forced to -inf (answer_id from the 2nd generated token on,
+// moondream.py:517; eos_id and size_id inside _generate_reasoning, :395-396).
 // Optionally writes the top1 - top2 margin and the bf16-rounded logits.
 // ------------------------------------------------------------------------------------------------
 struct ArgTop {
@@ -351,7 +386,7 @@ __device__ __forceinline__ ArgTop argtop_block_reduce(ArgTop t, float* sb, float
 // stage 1: block (part, b) scans vocabulary slice `part` of row b.  parts == 1 writes the result directly.
 __global__ void __launch_bounds__(512)
 argmax_partial_kernel(const float* __restrict__ ws, int splits, int B, int V, int parts,
-                      const __nv_bfloat16* __restrict__ bias, int bias_period, int mask_id,
+                      const __nv_bfloat16* __restrict__ bias, int bias_period, int mask_id, int mask_id2,
                       float* __restrict__ part_best, float* __restrict__ part_second, int* __restrict__ part_idx,
                       int* __restrict__ out_ids, long long out_stride, const int* __restrict__ out_index,
                       float* __restrict__ out_margin, __nv_bfloat16* __restrict__ out_logits) {
@@ -367,7 +402,7 @@ argmax_partial_kernel(const float* __restrict__ ws, int splits, int B, int V, in
     for (int s = 0; s < splits; ++s) a += ws[(static_cast<long long>(s) * B + b) * V + v];
     if (brow) a += __bfloat162float(brow[v]);
     a = bf16_round(a);
-    if (v == mask_id) a = -INFINITY;
+    if (v == mask_id || v == mask_id2) a = -INFINITY;
     if (out_logits) out_logits[static_cast<long long>(b) * V + v] = __float2bfloat16_rn(a);
     if (a > t.best) { t.second = t.best; t.best = a; t.idx = v; }
     else if (a > t.second) t.second = a;
@@ -418,7 +453,7 @@ constexpr int kArgmaxMaxParts = 16;
 long long argmax_scratch_floats(int B) { return 3LL * B * kArgmaxMaxParts; }
 
 int argmax_logits(const float* ws, int splits, int B, int V, const __nv_bfloat16* bias, int bias_period,
-                  int mask_id, int* out_ids, long long out_stride, const int* out_index,
+                  int mask_id, int mask_id2, int* out_ids, long long out_stride, const int* out_index,
                   float* out_margin, __nv_bfloat16* out_logits, float* scratch, cudaStream_t stream) {
   if (B <= 0 || V <= 0) return set_error("argmax_logits: empty input");
   if (bias_period < 1) bias_period = 1;
@@ -428,7 +463,7 @@ int argmax_logits(const float* ws, int splits, int B, int V, const __nv_bfloat16
   float* ps = scratch ? scratch + 1LL * B * kArgmaxMaxParts : nullptr;
   int* pi = scratch ? reinterpret_cast<int*>(scratch + 2LL * B * kArgmaxMaxParts) : nullptr;
   MD_LAUNCH(argmax_partial_kernel, dim3(parts, B), dim3(512), 0, stream, ws, splits, B, V, parts, bias,
-            bias_period, mask_id, pb, ps, pi, out_ids, out_stride, out_index, out_margin, out_logits);
+            bias_period, mask_id, mask_id2, pb, ps, pi, out_ids, out_stride, out_index, out_margin, out_logits);
   if (parts > 1) {
     MD_LAUNCH(argmax_final_kernel, dim3((B + 3) / 4), dim3(128), 0, stream, pb, ps, pi, B, parts, out_ids,
               out_stride, out_index, out_margin);
@@ -481,18 +516,20 @@ int gather_rows(const __nv_bfloat16* src, long long ld_src, const int* idx, int 
   return 0;
 }
 
-__global__ void bins_to_values_kernel(int which, const int* bins, int n, float* out) {
+__global__ void bins_to_values_kernel(int which, const int* bins, int n, int n_bins, float* out) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const float b = static_cast<float>(bins[i]);
-  if (which == 0) out[i] = b / 1024.0f;
+  if (which == 0) out[i] = __fdiv_rn(b, static_cast<float>(n_bins));     // argmax / logits.size(-1), moondream.py:673
   else out[i] = exp2f(__fsub_rn(__fmul_rn(__fdiv_rn(b, 1023.0f), 10.0f), 10.0f));
 }
 
-int bins_to_values(int which, const int* bins, int n, float* out, cudaStream_t stream) {
+int bins_to_values(int which, const int* bins, int n, int n_bins, float* out, cudaStream_t stream) {
   if (n <= 0) return set_error("bins_to_values: empty input");
-  bins_to_values_kernel<<<(n + 127) / 128, 128, 0, stream>>>(which, bins, n, out);
-  MD_CHECK_LAUNCH();
+  if (n_bins <= 0) return set_error("bins_to_values: n_bins must be positive");
+  MD_LAUNCH(bins_to_values_kernel, dim3((n + 127) / 128), dim3(128), 0, stream, which, bins, n, n_bins, out);
   return 0;
 }
 

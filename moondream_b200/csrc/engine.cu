@@ -22,6 +22,8 @@ int model_create(const md_dims& d, const void* const* w, int n, const void* lut,
   if (n != model_num_weights(d)) return set_error("md_model_create: wrong number of weight tensors");
   if (d.vis_dim != d.vis_heads * 72) return set_error("md_model_create: vision head_dim must be 72");
   if (d.txt_dim != d.txt_heads * 64) return set_error("md_model_create: text head_dim must be 64");
+  if (d.txt_kv_heads < 0 || (d.txt_kv_heads > 0 && d.txt_heads % d.txt_kv_heads))
+    return set_error("md_model_create: txt_heads must be a multiple of txt_kv_heads");
   if (d.patch_k % 8 || d.vis_ff % 8 || d.vis_dim % 8 || d.txt_dim % 8 || d.txt_ff % 8 || d.vocab % 8 ||
       d.proj_inner % 8 || d.reg_inner % 8)
     return set_error("md_model_create: every GEMM dimension must be a multiple of 8 (pad when preparing)");
@@ -33,6 +35,7 @@ int model_create(const md_dims& d, const void* const* w, int n, const void* lut,
   Model* m = new (std::nothrow) Model();
   if (!m) return set_error("md_model_create: out of host memory");
   m->d = d;
+  if (m->d.txt_kv_heads == 0) m->d.txt_kv_heads = d.txt_heads;      // 0 = multi-head attention
   m->lut = reinterpret_cast<const bf16*>(lut);
   m->rope = rope;
   int k = 0;
@@ -66,11 +69,12 @@ int model_create(const md_dims& d, const void* const* w, int n, const void* lut,
   m->coord_enc.ld = d.coord_feat; m->coord_dec1.ld = d.txt_dim; m->coord_dec2.ld = d.reg_inner;
   m->size_enc.ld = d.size_feat; m->size_dec1.ld = d.txt_dim; m->size_dec2.ld = d.reg_inner;
   const long long D = d.txt_dim, FF = d.txt_ff;
+  const long long QKV = D + 2LL * m->d.txt_kv_heads * 64;            // rows of qkv.weight (text.py:36-38)
   for (auto& b : m->txt) {
     b.qkv.ld = D; b.fc1.ld = D;
     if (d.txt_fused) {
       // ... except the fused decode layout: W1 = [qkv ; fc1] rows, W2 = [proj | fc2] columns
-      if (b.fc1.w != b.qkv.w + 3 * D * D || b.fc1.b != b.qkv.b + 3 * D || b.fc2.w != b.proj.w + D) {
+      if (b.fc1.w != b.qkv.w + QKV * D || b.fc1.b != b.qkv.b + QKV || b.fc2.w != b.proj.w + D) {
         delete m;
         return set_error("md_model_create: txt_fused is set but the decoder weights are not views of "
                          "[qkv;fc1] / [proj|fc2] buffers");
@@ -157,6 +161,22 @@ int vision_project(Model& m, const bf16* feats, const int* crop_offsets, const i
                       m.proj_fc2.b, nullptr, 0, 0, embeds, d.txt_dim, tok, rows_per_image, 1, st);
 }
 
+// `_vis_proj(g, r)` itself (vision.py:77-89) for ONE image whose local features are already stitched: the seam adapter's
+// entry point (moondream_b200/seam.py); the batched product path is vision_project above.
+int vision_project_stitched(Model& m, const bf16* global_feats, const bf16* stitched, int H, int W, bf16* out, void* ws,
+                            cudaStream_t st) {
+  const md_dims& d = m.d;
+  const int T = d.grid * d.grid;
+  char* p = align_up(reinterpret_cast<char*>(ws));
+  bf16* cat = reinterpret_cast<bf16*>(p); p += pad256(1LL * T * 2 * d.vis_dim * 2);
+  bf16* hid = reinterpret_cast<bf16*>(p);
+  if (pool_concat(global_feats, stitched, H, W, d.grid, d.vis_dim, cat, st)) return 1;
+  if (gemm_rowform(cat, 2 * d.vis_dim, m.proj_fc1.w, 2 * d.vis_dim, T, d.proj_inner, 2 * d.vis_dim,
+                   EPI_BIAS_GELU, m.proj_fc1.b, nullptr, 0, 0, hid, d.proj_inner, 0, 0, 0, st)) return 1;
+  return gemm_rowform(hid, d.proj_inner, m.proj_fc2.w, d.proj_inner, T, d.txt_dim, d.proj_inner, EPI_BIAS,
+                      m.proj_fc2.b, nullptr, 0, 0, out, d.txt_dim, 0, 0, 0, st);
+}
+
 // ------------------------------------------------------------------------------------------------
 // text decoder: prefill
 // ------------------------------------------------------------------------------------------------
@@ -167,10 +187,12 @@ long long text_prefill_ws_bytes(const Model& m, int T) {
 }
 
 int text_prefill(Model& m, bf16* x, int T, const int* q_offsets, const int* start_pos, int n_seqs,
-                 int max_q, const md_kv& kv, void* ws, cudaStream_t st) {
+                 int max_q, int prefix_len, const md_kv& kv, void* ws, cudaStream_t st) {
   const md_dims& d = m.d;
   if (T <= 0 || n_seqs <= 0) return set_error("md_text_prefill: empty batch");
-  const int D = d.txt_dim, H = d.txt_heads;
+  if (prefix_len < 0) prefix_len = d.prefix_len;     // 0: pure causal mask (text-only query, moondream.py:565-574)
+  const int D = d.txt_dim, H = d.txt_heads, KVH = d.txt_kv_heads;
+  if (kv.n_kv_heads && kv.n_kv_heads != KVH) return set_error("md_text_prefill: the KV pool's head count differs from the model's");
   char* p = align_up(reinterpret_cast<char*>(ws));
   bf16* ln = reinterpret_cast<bf16*>(p); p += pad256(1LL * T * D * 2);
   bf16* q = reinterpret_cast<bf16*>(p); p += pad256(1LL * T * D * 2);
@@ -184,15 +206,16 @@ int text_prefill(Model& m, bf16* x, int T, const int* q_offsets, const int* star
     if (layernorm(x, D, b.ln.w, b.ln.b, ln, D, T, D, 1e-5f, st)) return 1;
     // QKV projection with bias, RoPE and the KV-page write in the GEMM epilogue (no qkv round trip through HBM)
     RopeEpilogue re{};
-    re.D = D; re.n_heads = H; re.n_seqs = n_seqs; re.q_offsets = q_offsets; re.start_pos = start_pos;
+    re.D = D; re.n_heads = H; re.n_kv_heads = KVH; re.n_seqs = n_seqs; re.q_offsets = q_offsets; re.start_pos = start_pos;
     re.freqs = m.rope; re.q_out = q; re.kv_pool = pool; re.n_pages = kv.n_pages; re.block_tables = kv.block_tables;
     re.max_blocks = kv.max_blocks; re.layer = i;
     if (gemm_rowform_qkv_rope(ln, D, b.qkv.w, b.qkv.ld, T, D, b.qkv.b, re, st)) return 1;
     if (g_attention_impl == 1) {
-      if (prefill_attention(q, H, q_offsets, start_pos, n_seqs, max_q, d.prefix_len, pool, kv.n_pages,
+      if (KVH != H) return set_error("md_text_prefill: the legacy mma.sync attention has no grouped-query path");
+      if (prefill_attention(q, H, q_offsets, start_pos, n_seqs, max_q, prefix_len, pool, kv.n_pages,
                             kv.block_tables, kv.max_blocks, i, att, st)) return 1;
     } else {
-      if (prefill_attention_tc(q, H, T, q_offsets, start_pos, n_seqs, max_q, d.prefix_len, pool, kv.n_pages,
+      if (prefill_attention_tc(q, H, KVH, T, q_offsets, start_pos, n_seqs, max_q, prefix_len, pool, kv.n_pages,
                                kv.n_layers, kv.block_tables, kv.max_blocks, i, att, st)) return 1;
     }
     // tmp = bf16(x + bf16(proj(att)))  -- the reference adds l_attn first, then l_mlp (text.py:158)
@@ -213,7 +236,7 @@ static long long smallbatch_ws_floats(const Model& m, int batch) {
     const long long f = 1LL * gemm_smallbatch_splits(n_out, K) * batch * n_out;
     if (f > need) need = f;
   };
-  upd(3 * d.txt_dim + d.txt_ff, d.txt_dim);
+  upd(d.txt_dim + 2 * d.txt_kv_heads * 64 + d.txt_ff, d.txt_dim);
   {
     const StreamPlan2 pl = plan_smallbatch_2seg(d.txt_dim, d.txt_dim + d.txt_ff, d.txt_dim);
     const long long f = 1LL * (pl.splits_a + pl.splits_b) * batch * d.txt_dim;
@@ -227,7 +250,7 @@ static long long smallbatch_ws_floats(const Model& m, int batch) {
 
 long long text_decode_ws_bytes(const Model& m, int batch) {
   const md_dims& d = m.d;
-  return pad256(1LL * batch * d.txt_dim * 2) * 2 + pad256(1LL * batch * (d.txt_dim + d.txt_ff) * 2) +
+  return pad256(1LL * batch * d.txt_dim * 2) * 3 + pad256(1LL * batch * (d.txt_dim + d.txt_ff) * 2) +
          pad256(smallbatch_ws_floats(m, batch) * 4) + 4096;
 }
 
@@ -245,10 +268,13 @@ int text_decode_step(Model& m, bf16* x, const int* pos, int batch, const md_kv& 
   const md_dims& d = m.d;
   if (batch <= 0) return set_error("md_text_decode_step: empty batch");
   if (!d.txt_fused) return set_error("md_text_decode_step: the model was created without the fused decode layout");
-  const int D = d.txt_dim, FF = d.txt_ff, H = d.txt_heads;
+  const int D = d.txt_dim, FF = d.txt_ff, H = d.txt_heads, KVH = d.txt_kv_heads;
+  const int QKV = D + 2 * KVH * 64;
+  if (kv.n_kv_heads && kv.n_kv_heads != KVH) return set_error("md_text_decode_step: the KV pool's head count differs from the model's");
   char* p = align_up(reinterpret_cast<char*>(ws));
   bf16* ln = reinterpret_cast<bf16*>(p); p += pad256(1LL * batch * D * 2);
   bf16* ln_last = reinterpret_cast<bf16*>(p); p += pad256(1LL * batch * D * 2);
+  bf16* qbuf = reinterpret_cast<bf16*>(p); p += pad256(1LL * batch * D * 2);          // grouped-query path only
   bf16* xcat = reinterpret_cast<bf16*>(p); p += pad256(1LL * batch * (D + FF) * 2);   // [att | gelu(fc1)]
   float* wsf = reinterpret_cast<float*>(p);
   bf16* pool = reinterpret_cast<bf16*>(kv.pool);
@@ -260,13 +286,22 @@ int text_decode_step(Model& m, bf16* x, const int* pos, int batch, const md_kv& 
     // [qkv ; fc1] share the input l = ln(x) (text.py:145-157): one weight stream, then bias / RoPE /
     // KV-page write / GELU, which the attention kernel applies for its own (sequence, head).  (Fusing them into
     // the GEMM epilogue needs whole-K tiles, i.e. 112 streaming SMs instead of 148: measured slower, DESIGN.md.)
-    int s1 = plan_smallbatch(3 * D + FF, D, 0).splits;
-    if (!(g_debug_skip & 1)) s1 = gemm_smallbatch(b.qkv.w, D, ln, D, 3 * D + FF, batch, D, 0, wsf, st);
+    int s1 = plan_smallbatch(QKV + FF, D, 0).splits;
+    if (!(g_debug_skip & 1)) s1 = gemm_smallbatch(b.qkv.w, D, ln, D, QKV + FF, batch, D, 0, wsf, st);
     if (s1 < 0) return 1;
-    // bias / RoPE / KV-row write / GELU of that stream happen inside the attention kernel (one launch fewer)
-    if (!(g_debug_skip & 4) &&
-        decode_attention_fused(wsf, s1, D, FF, b.qkv.b, m.rope, xcat + D, D + FF, H, pos, batch, pool, kv.n_pages,
-                               kv.block_tables, kv.max_blocks, i, xcat, D + FF, st)) return 1;
+    if (KVH == H) {
+      // bias / RoPE / KV-row write / GELU of that stream happen inside the attention kernel (one launch fewer)
+      if (!(g_debug_skip & 4) &&
+          decode_attention_fused(wsf, s1, D, FF, b.qkv.b, m.rope, xcat + D, D + FF, H, pos, batch, pool, kv.n_pages,
+                                 kv.block_tables, kv.max_blocks, i, xcat, D + FF, st)) return 1;
+    } else {
+      // grouped-query attention: the G query heads of a group share one new K/V row, so the stream is finished by
+      // its own small kernel and the plain paged kernel reads KV head h / G
+      if (decode_qkv_finish(wsf, s1, batch, D, KVH, FF, b.qkv.b, m.rope, pos, qbuf, pool, kv.n_pages, kv.block_tables,
+                            kv.max_blocks, i, xcat + D, D + FF, st)) return 1;
+      if (decode_attention(qbuf, H, KVH, pos, batch, pool, kv.n_pages, kv.block_tables, kv.max_blocks, i, xcat,
+                           D + FF, st)) return 1;
+    }
     // proj(att) and fc2(hid) both land in the residual: one K-concatenated weight stream
     int s2 = pl2.splits_a + pl2.splits_b;
     if (!(g_debug_skip & 8)) s2 = gemm_smallbatch_2seg(b.proj.w, D + FF, xcat, D + FF, D, batch, D + FF, D, wsf, st);
@@ -288,7 +323,7 @@ long long lm_head_ws_bytes(const Model& m, int batch) {
          pad256(argmax_scratch_floats(batch) * 4) + 4096;
 }
 
-int lm_head_argmax(Model& m, const bf16* hidden, long long ldh, int prenormed, int batch, int mask_id,
+int lm_head_argmax(Model& m, const bf16* hidden, long long ldh, int prenormed, int batch, int mask_id, int mask_id2,
                    int* out_ids, long long out_stride, const int* out_index, float* out_margin,
                    bf16* out_logits, void* ws, cudaStream_t st) {
   const md_dims& d = m.d;
@@ -307,7 +342,7 @@ int lm_head_argmax(Model& m, const bf16* hidden, long long ldh, int prenormed, i
   const int used = gemm_smallbatch(m.lm_head.w, d.txt_dim, normed, ldn, d.vocab, batch, d.txt_dim,
                                 gemm_smallbatch_splits(d.vocab, d.txt_dim), wsf, st);
   if (used < 0) return 1;
-  return argmax_logits(wsf, used, batch, d.vocab, m.lm_head.b, 1, mask_id, out_ids, out_stride, out_index,
+  return argmax_logits(wsf, used, batch, d.vocab, m.lm_head.b, 1, mask_id, mask_id2, out_ids, out_stride, out_index,
                        out_margin, out_logits, scratch, st);
 }
 
@@ -340,9 +375,9 @@ int region_decode(Model& m, int which, const bf16* hidden, long long ldh, int ba
                                 gemm_smallbatch_splits(n_out, d.reg_inner), wsf, st);
   if (used < 0) return 1;
   if (which == 0)
-    return argmax_logits(wsf, used, batch, n_out, l2.b, 1, -1, out_bins, 1, nullptr, nullptr, nullptr, nullptr, st);
+    return argmax_logits(wsf, used, batch, n_out, l2.b, 1, -1, -1, out_bins, 1, nullptr, nullptr, nullptr, nullptr, st);
   // size logits are viewed as (2, -1): rows 2b (width bins) and 2b+1 (height bins)
-  return argmax_logits(wsf, used, 2 * batch, n_out / 2, l2.b, 2, -1, out_bins, 1, nullptr, nullptr, nullptr, nullptr, st);
+  return argmax_logits(wsf, used, 2 * batch, n_out / 2, l2.b, 2, -1, -1, out_bins, 1, nullptr, nullptr, nullptr, nullptr, st);
 }
 
 int region_encode(Model& m, int which, const float* values, int batch, bf16* out, long long ldo, void* ws,

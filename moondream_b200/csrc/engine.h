@@ -37,15 +37,18 @@ int vision_encode(Model& m, const uint8_t* crops, int n_crops, bf16* feats, void
 long long vision_project_ws_bytes(const Model& m, int n_images);
 int vision_project(Model& m, const bf16* feats, const int* crop_offsets, const int* tilings, int n_images,
                    bf16* embeds, int rows_per_image, void* ws, cudaStream_t st);
+int vision_project_stitched(Model& m, const bf16* global_feats, const bf16* stitched, int H, int W, bf16* out, void* ws,
+                            cudaStream_t st);
 long long text_prefill_ws_bytes(const Model& m, int T);
 int text_prefill(Model& m, bf16* x, int T, const int* q_offsets, const int* start_pos, int n_seqs,
-                 int max_q, const md_kv& kv, void* ws, cudaStream_t st);
+                 int max_q, int prefix_len, const md_kv& kv, void* ws, cudaStream_t st);
 extern int g_debug_skip;
 long long text_decode_ws_bytes(const Model& m, int batch);
 int text_decode_step(Model& m, bf16* x, const int* pos, int batch, const md_kv& kv, bf16* normed_out, void* ws,
                      cudaStream_t st);
 long long lm_head_ws_bytes(const Model& m, int batch);
-int lm_head_argmax(Model& m, const bf16* hidden, long long ldh, int prenormed, int batch, int mask_id, int* out_ids,
+int lm_head_argmax(Model& m, const bf16* hidden, long long ldh, int prenormed, int batch, int mask_id, int mask_id2,
+                   int* out_ids,
                    long long out_stride, const int* out_index, float* out_margin, bf16* out_logits,
                    void* ws, cudaStream_t st);
 long long region_ws_bytes(const Model& m, int batch);

@@ -59,14 +59,16 @@ __device__ __forceinline__ RopeRow rope_locate(const RopeEpilogue& e, int row) {
   RopeRow r;
   r.pos = e.start_pos[lo] + (row - e.q_offsets[lo]);
   const int page = e.block_tables[static_cast<long long>(lo) * e.max_blocks + (r.pos >> 6)];
-  r.kv_row = ((static_cast<long long>(e.layer) * e.n_pages + page) * 2) * e.n_heads * (64 * 64) + (r.pos & 63) * 64;
+  r.kv_row = ((static_cast<long long>(e.layer) * e.n_pages + page) * 2) * e.n_kv_heads * (64 * 64) + (r.pos & 63) * 64;
   return r;
 }
 __device__ __forceinline__ void rope_store_chunk(const GemmParams& p, const uint32_t (&acc)[32], int row, int col0,
                                                  const RopeRow& rr) {
   const RopeEpilogue& e = p.rope;
-  const int part = col0 / e.D;                            // 0 q, 1 k, 2 v
-  const int within = col0 - part * e.D;
+  // columns: q [0, D) | k [D, D + KVW) | v [D + KVW, D + 2 KVW), KVW = n_kv_heads * 64 (text.py:36-38)
+  const int kvw = e.n_kv_heads * 64;
+  const int part = col0 < e.D ? 0 : (col0 < e.D + kvw ? 1 : 2);
+  const int within = col0 - (part == 0 ? 0 : e.D + (part - 1) * kvw);
   const int head = within >> 6, half = (within >> 5) & 1;
   float v[32];
 #pragma unroll
@@ -98,7 +100,7 @@ __device__ __forceinline__ void rope_store_chunk(const GemmParams& p, const uint
   }
   __nv_bfloat16* dst;
   if (part == 0) dst = e.q_out + static_cast<long long>(row) * e.D + head * 64 + half * 32;
-  else dst = e.kv_pool + rr.kv_row + (static_cast<long long>(part - 1) * e.n_heads + head) * (64 * 64) + half * 32;
+  else dst = e.kv_pool + rr.kv_row + (static_cast<long long>(part - 1) * e.n_kv_heads + head) * (64 * 64) + half * 32;
 #pragma unroll
   for (int g = 0; g < 4; ++g)
     *reinterpret_cast<uint4*>(dst + g * 8) = make_uint4(o[4 * g], o[4 * g + 1], o[4 * g + 2], o[4 * g + 3]);
@@ -835,7 +837,10 @@ static int gemm_smallbatch_impl(const __nv_bfloat16* W, long long ldw, const __n
     cudaError_t e = cudaFuncSetAttribute(smallbatch_gemm_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSbSmemMax);
     if (e != cudaSuccess) { set_error(cudaGetErrorString(e)); return -1; }
   }
-  const bool m64 = (g_gemm_debug & 64) && batch <= 64;     // experimental until validated on hardware
+  // batches <= 64 use M = 64 MMAs: half the activation-operand shared-memory read per k-block, which is what bounds
+  // the stream (decode layer period 78.1 -> 70.7 us, tools/decode_timeline.py, profiles/r02_decode_timeline_m64.json);
+  // md_debug_gemm bit 6 forces the M = 128 instantiation for A/B runs.
+  const bool m64 = !(g_gemm_debug & 64) && batch <= 64;
   static DeviceOnce configured64;
   if (m64 && configured64.first()) {
     cudaError_t e = cudaFuncSetAttribute(smallbatch_gemm_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSbSmemMax);
@@ -877,9 +882,10 @@ int gemm_smallbatch(const __nv_bfloat16* W, long long ldw, const __nv_bfloat16* 
 
 int gemm_rowform_qkv_rope(const __nv_bfloat16* A, long long lda, const __nv_bfloat16* W, long long ldw, int M,
                           int K, const __nv_bfloat16* bias, const RopeEpilogue& epi, cudaStream_t stream) {
-  const int N = 3 * epi.D;
+  const int N = epi.D + 2 * epi.n_kv_heads * 64;
   if (M <= 0 || K <= 0) return set_error("gemm_qkv_rope: empty problem");
-  if (K % 8 || epi.D % 64 || epi.D != epi.n_heads * 64 || !bias) return set_error("gemm_qkv_rope: unsupported shape");
+  if (K % 8 || epi.D % 64 || epi.D != epi.n_heads * 64 || epi.n_kv_heads <= 0 || epi.n_heads % epi.n_kv_heads || !bias)
+    return set_error("gemm_qkv_rope: unsupported shape");
   const int bn = 256;                                // 4 heads per column tile; N = 3D is a multiple of 64
   int cg = (M > BM) ? 2 : 1;
   if (g_force_cg == 1) cg = 1;

@@ -84,7 +84,7 @@ int gemm_smallbatch(const __nv_bfloat16* W, long long ldw, const __nv_bfloat16* 
 // Prefill QKV projection with RoPE and the KV-cache write fused into the GEMM epilogue (text.py:30-43,
 // rope.py:20-48, moondream.py:74-78): output column block -> (q|k|v, head, half-head); row -> (sequence, position).
 struct RopeEpilogue {
-  int D, n_heads, n_seqs;
+  int D, n_heads, n_kv_heads, n_seqs;   // n_kv_heads < n_heads: grouped-query attention (text.py:49 enable_gqa)
   const int* q_offsets;           // [n_seqs + 1] token rows of each sequence
   const int* start_pos;           // [n_seqs]
   const float* freqs;             // rope table [ctx][16][2]
@@ -113,6 +113,8 @@ int patchify(const uint8_t* crops, int n_crops, int crop, int patch, int k_pad,
 int stitch_pool_concat(const __nv_bfloat16* feats, const int* crop_offsets, const int* tilings,
                        int n_images, int grid, int margin, int dim, __nv_bfloat16* out,
                        cudaStream_t stream);
+int pool_concat(const __nv_bfloat16* global_feats, const __nv_bfloat16* stitched, int H, int W, int grid, int dim,
+                __nv_bfloat16* out, cudaStream_t stream);
 int embed_tokens(const int* ids, long long id_stride, int n, const __nv_bfloat16* wte, int dim,
                  int vocab, __nv_bfloat16* out, long long ldo, cudaStream_t stream);
 int rope_kv_write(const __nv_bfloat16* qkv, int n_tokens, int n_heads, const int* q_offsets,
@@ -120,14 +122,14 @@ int rope_kv_write(const __nv_bfloat16* qkv, int n_tokens, int n_heads, const int
                   __nv_bfloat16* kv_pool, int n_pages, const int* block_tables, int max_blocks,
                   int layer, cudaStream_t stream);
 int argmax_logits(const float* ws, int splits, int B, int V, const __nv_bfloat16* bias, int bias_period,
-                  int mask_id, int* out_ids, long long out_stride, const int* out_index,
+                  int mask_id, int mask_id2, int* out_ids, long long out_stride, const int* out_index,
                   float* out_margin, __nv_bfloat16* out_logits, float* scratch, cudaStream_t stream);
 long long argmax_scratch_floats(int B);
 int decode_advance(int* cur_tok, int* pos, int* step, const int* preds, const int* forced,
                    long long stride, int batch, int eos_id, int* finished, cudaStream_t stream);
 int gather_rows(const __nv_bfloat16* src, long long ld_src, const int* idx, int n, int dim,
                 __nv_bfloat16* out, long long ldo, cudaStream_t stream);
-int bins_to_values(int which, const int* bins, int n, float* out, cudaStream_t stream);
+int bins_to_values(int which, const int* bins, int n, int n_bins, float* out, cudaStream_t stream);
 int decode_residual_ln_epilogue(const float* ws, int splits, int proj_splits, int B, int D,
                                 const __nv_bfloat16* bias_proj, const __nv_bfloat16* bias_fc2,
                                 __nv_bfloat16* x, const __nv_bfloat16* ln_w, const __nv_bfloat16* ln_b,
@@ -136,7 +138,7 @@ int fourier_features(const float* x, int B, int n_in, const __nv_bfloat16* w, in
                      __nv_bfloat16* out, long long ldo, cudaStream_t stream);
 
 // ---- attention_tc.cu ----
-int prefill_attention_tc(const __nv_bfloat16* q, int n_heads, int total_tokens, const int* q_offsets,
+int prefill_attention_tc(const __nv_bfloat16* q, int n_heads, int n_kv_heads, int total_tokens, const int* q_offsets,
                          const int* start_pos, int n_seqs, int max_q, int prefix_len,
                          const __nv_bfloat16* kv_pool, int n_pages, int n_layers, const int* block_tables,
                          int max_blocks, int layer, __nv_bfloat16* out, cudaStream_t stream);
@@ -151,12 +153,25 @@ int prefill_attention(const __nv_bfloat16* q, int n_heads, const int* q_offsets,
                       int n_seqs, int max_q, int prefix_len, const __nv_bfloat16* kv_pool, int n_pages,
                       const int* block_tables, int max_blocks, int layer, __nv_bfloat16* out,
                       cudaStream_t stream);
-int decode_attention(const __nv_bfloat16* q, int n_heads, const int* pos, int n_seqs,
+int decode_attention(const __nv_bfloat16* q, int n_heads, int n_kv_heads, const int* pos, int n_seqs,
                      const __nv_bfloat16* kv_pool, int n_pages, const int* block_tables,
                      int max_blocks, int layer, __nv_bfloat16* out, long long ld_out, cudaStream_t stream);
 int decode_attention_fused(const float* ws, int splits, int D, int FF, const __nv_bfloat16* bias, const float* freqs,
                            __nv_bfloat16* hid, long long ld_hid, int n_heads, const int* pos, int n_seqs,
                            __nv_bfloat16* kv_pool, int n_pages, const int* block_tables, int max_blocks, int layer,
                            __nv_bfloat16* out, long long ld_out, cudaStream_t stream);
+int decode_qkv_finish(const float* ws, int splits, int B, int D, int n_kv_heads, int FF, const __nv_bfloat16* bias,
+                      const float* freqs, const int* pos, __nv_bfloat16* q_out, __nv_bfloat16* kv_pool, int n_pages,
+                      const int* block_tables, int max_blocks, int layer, __nv_bfloat16* hid, long long ld_hid,
+                      cudaStream_t stream);
+
+// ---- sampling.cu ----
+int sample_top_p(const __nv_bfloat16* logits, int B, int V, float temperature, float top_p,
+                 const unsigned long long* seed, const int* step, const float* uniforms, __nv_bfloat16* scratch,
+                 int keep_probs, int* out_ids, long long out_stride, int out_offset, cudaStream_t stream);
+int embed_select(const int* ids, long long id_stride, int n, const __nv_bfloat16* wte, int dim, int vocab, int sel_id,
+                 const __nv_bfloat16* alt, long long ld_alt, __nv_bfloat16* out, long long ldo, cudaStream_t stream);
+int store_column_f32(const float* src, int n, float* dst, long long stride, const int* index, int offset,
+                     cudaStream_t stream);
 
 }  // namespace md

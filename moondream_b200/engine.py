@@ -92,16 +92,17 @@ def upload_weights(cfg: MoondreamConfig, prepared: List[torch.Tensor], device) -
     dev: List[Optional[torch.Tensor]] = [None] * len(keys)
     owners = []
     D = cfg.text.dim
+    Q = D + 2 * cfg.text.n_kv_heads * cfg.text.head_dim          # rows of qkv.weight (text.py:36-38)
     for i in range(cfg.text.n_layers):
         p = f"text.blocks.{i}."
         w1 = torch.cat([prepared[idx[p + "attn.qkv.weight"]], prepared[idx[p + "mlp.fc1.weight"]]], 0).to(device)
         b1 = torch.cat([prepared[idx[p + "attn.qkv.bias"]], prepared[idx[p + "mlp.fc1.bias"]]], 0).to(device)
         w2 = torch.cat([prepared[idx[p + "attn.proj.weight"]], prepared[idx[p + "mlp.fc2.weight"]]], 1).to(device)
         owners += [w1, b1, w2]
-        dev[idx[p + "attn.qkv.weight"]] = w1[: 3 * D]
-        dev[idx[p + "mlp.fc1.weight"]] = w1[3 * D:]
-        dev[idx[p + "attn.qkv.bias"]] = b1[: 3 * D]
-        dev[idx[p + "mlp.fc1.bias"]] = b1[3 * D:]
+        dev[idx[p + "attn.qkv.weight"]] = w1[:Q]
+        dev[idx[p + "mlp.fc1.weight"]] = w1[Q:]
+        dev[idx[p + "attn.qkv.bias"]] = b1[:Q]
+        dev[idx[p + "mlp.fc1.bias"]] = b1[Q:]
         dev[idx[p + "attn.proj.weight"]] = w2[:, :D]
         dev[idx[p + "mlp.fc2.weight"]] = w2[:, D:]
     for i, t in enumerate(prepared):
@@ -111,13 +112,13 @@ def upload_weights(cfg: MoondreamConfig, prepared: List[torch.Tensor], device) -
 
 
 class PagePool:
-    """KV pages: bf16 [layers, n_pages, 2, heads, 64, 64]; a free list hands out page ids."""
+    """KV pages: bf16 [layers, n_pages, 2, kv_heads, 64, 64]; a free list hands out page ids."""
 
     def __init__(self, cfg: MoondreamConfig, n_pages: int, device):
         t = cfg.text
         self.n_pages = n_pages
         # zeros, not empty: masked / not-yet-written slots still flow through P.V as 0 * v and must be finite
-        self.pool = torch.zeros((t.n_layers, n_pages, 2, t.n_heads, PAGE, 64), dtype=torch.bfloat16,
+        self.pool = torch.zeros((t.n_layers, n_pages, 2, t.n_kv_heads, PAGE, 64), dtype=torch.bfloat16,
                                 device=device)
         self._free = list(range(n_pages - 1, -1, -1))
 
@@ -153,6 +154,22 @@ class PrefixKV:
             self.release()
         except Exception:
             pass
+
+
+@dataclass(frozen=True)
+class DecodeMode:
+    """What one captured decode step does; also the key of the CUDA-graph cache."""
+    forced: bool            # teacher forcing: feed forced[:, step + 1] instead of the prediction
+    temperature: float      # 0 = greedy argmax; > 0 = on-device top-p sampling
+    top_p: float
+    reasoning: bool         # coord_id tokens are fed as region-encoded coordinates (moondream.py:381-391)
+    mask_id: int            # ids excluded by the LM head at decode steps (-1 = none)
+    mask_id2: int
+    eos_id: int             # sets finished[b]
+
+    @property
+    def sampled(self) -> bool:
+        return self.temperature > 0.0
 
 
 @dataclass
@@ -196,7 +213,8 @@ class Engine:
             margin=v.overlap_margin, proj_inner=v.proj_inner_dim, txt_dim=t.dim, txt_ff=t.ff_dim,
             txt_layers=t.n_layers, txt_heads=t.n_heads, vocab=t.vocab_size, max_context=t.max_context,
             prefix_len=t.prefix_attn, reg_inner=r.inner_dim, coord_feat=r.coord_feat_dim,
-            coord_out=r.coord_out_dim, size_feat=r.size_feat_dim, size_out=r.size_out_dim, txt_fused=1)
+            coord_out=r.coord_out_dim, size_feat=r.size_feat_dim, size_out=r.size_out_dim, txt_fused=1,
+            txt_kv_heads=t.n_kv_heads)
         n = self.lib.md_model_num_weights(ctypes.byref(self.dims))
         assert n == len(self.weights), (n, len(self.weights))
         arr = (ctypes.c_void_p * n)(*[w.data_ptr() for w in self.weights])
@@ -234,7 +252,7 @@ class Engine:
     def _kv(self, block_tables: torch.Tensor) -> N.md_kv:
         return N.md_kv(pool=self.pages.pool.data_ptr(), n_pages=self.pages.n_pages,
                        block_tables=block_tables.data_ptr(), max_blocks=block_tables.shape[1],
-                       n_layers=self.cfg.text.n_layers)
+                       n_layers=self.cfg.text.n_layers, n_kv_heads=self.cfg.text.n_kv_heads)
 
     def _i32(self, values) -> torch.Tensor:
         return torch.tensor(values, dtype=torch.int32).to(self.device, non_blocking=True)
@@ -288,8 +306,9 @@ class Engine:
 
     @_on_device
     def prefill(self, x: torch.Tensor, q_offsets: Sequence[int], start_pos: Sequence[int],
-                block_tables: torch.Tensor):
-        """_prefill over a ragged batch, in place on x [total_tokens, dim]."""
+                block_tables: torch.Tensor, prefix_len: int = -1):
+        """_prefill over a ragged batch, in place on x [total_tokens, dim].  prefix_len: -1 = the model's 730-token
+        bidirectional image prefix (moondream.py:143-145), 0 = pure causal (text-only query, :565-574)."""
         T = x.shape[0]
         n_seqs = len(start_pos)
         assert q_offsets[-1] == T and len(q_offsets) == n_seqs + 1
@@ -297,20 +316,21 @@ class Engine:
         qo, sp = self._i32(list(q_offsets)), self._i32(list(start_pos))
         ws = self._workspace(self.lib.md_text_prefill_workspace_bytes(self.model, T))
         kv = self._kv(block_tables)
-        N.check(self.lib.md_text_prefill(self.model, N.ptr(x), T, N.ptr(qo), N.ptr(sp), n_seqs, max_q,
+        N.check(self.lib.md_text_prefill(self.model, N.ptr(x), T, N.ptr(qo), N.ptr(sp), n_seqs, max_q, prefix_len,
                                          ctypes.byref(kv), N.ptr(ws), N.current_stream()), "md_text_prefill")
 
     @_on_device
     def lm_head(self, hidden: torch.Tensor, out_ids: torch.Tensor, out_stride: int, mask_id: int = -1,
                 out_index: Optional[torch.Tensor] = None, margins: Optional[torch.Tensor] = None,
                 logits: Optional[torch.Tensor] = None, ws: Optional[torch.Tensor] = None,
-                out_offset: int = 0, prenormed: bool = False):
+                out_offset: int = 0, prenormed: bool = False, mask_id2: int = -1):
         B = hidden.shape[0]
         if ws is None:
             ws = self._workspace(self.lib.md_lm_head_workspace_bytes(self.model, B))
         ids_ptr = ctypes.c_void_p(out_ids.data_ptr() + 4 * out_offset)
         mar_ptr = None if margins is None else ctypes.c_void_p(margins.data_ptr() + 4 * out_offset)
-        N.check(self.lib.md_lm_head_argmax(self.model, N.ptr(hidden), hidden.stride(0), int(prenormed), B, mask_id, ids_ptr,
+        N.check(self.lib.md_lm_head_argmax(self.model, N.ptr(hidden), hidden.stride(0), int(prenormed), B, mask_id, mask_id2,
+                                           ids_ptr,
                                            out_stride, N.ptr(out_index), mar_ptr, N.ptr(logits), N.ptr(ws),
                                            N.current_stream()), "md_lm_head_argmax")
 
@@ -382,14 +402,16 @@ class Engine:
     @_on_device
     def caption_from_crops(self, crops_u8: torch.Tensor, crop_offsets: Sequence[int],
                            tilings: Sequence[Tuple[int, int]], prompts: Sequence[Sequence[int]], max_tokens: int,
-                           to_host: bool = True, stop_on_eos: bool = True) -> "GenerationResult":
-        """encode + greedy generation for a batch; one fused prefill pass when the prompts have equal length."""
+                           to_host: bool = True, stop_on_eos: bool = True, **gen_kw) -> "GenerationResult":
+        """encode + generation for a batch; one fused prefill pass when the prompts have equal length.
+        `gen_kw`: temperature / top_p / seed of `generate`."""
         if len({len(p) for p in prompts}) == 1:
             prefixes, hidden_last = self.encode_crops_with_prompt(crops_u8, crop_offsets, tilings, prompts)
             return self.generate(prefixes, prompts, max_tokens, consume=True, stop_on_eos=stop_on_eos, to_host=to_host,
-                                 prefilled_hidden=hidden_last)
+                                 prefilled_hidden=hidden_last, **gen_kw)
         prefixes = self.encode_crops(crops_u8, crop_offsets, tilings)
-        return self.generate(prefixes, prompts, max_tokens, consume=True, stop_on_eos=stop_on_eos, to_host=to_host)
+        return self.generate(prefixes, prompts, max_tokens, consume=True, stop_on_eos=stop_on_eos, to_host=to_host,
+                             **gen_kw)
 
     @_on_device
     def stage_images(self, images: Sequence[np.ndarray]):
@@ -419,7 +441,7 @@ class Engine:
     def prefix_kv_tensors(self, prefix: PrefixKV) -> List[Tuple[torch.Tensor, torch.Tensor]]:
         """Materialise (k, v) [1, heads, pos, 64] per layer like EncodedImage.caches (moondream.py:56-59)."""
         pg = torch.tensor(prefix.pages, dtype=torch.long, device=self.device)
-        blk = self.pages.pool[:, pg]                       # [L, P, 2, H, 64, 64]
+        blk = self.pages.pool[:, pg]                       # [L, P, 2, KVH, 64, 64]
         L, P, _, H, _, _ = blk.shape
         kv = blk.permute(0, 2, 3, 1, 4, 5).reshape(L, 2, H, P * PAGE, 64)[:, :, :, : prefix.pos]
         return [(kv[i, 0].unsqueeze(0).clone(), kv[i, 1].unsqueeze(0).clone()) for i in range(L)]
@@ -492,6 +514,7 @@ class Engine:
                 "pos": torch.zeros(B, dtype=torch.int32, device=dev),
                 "cur": torch.zeros(B, dtype=torch.int32, device=dev),
                 "step": torch.zeros(1, dtype=torch.int32, device=dev),
+                "seed": torch.zeros(1, dtype=torch.int64, device=dev),
                 "preds": torch.zeros((B, S), dtype=torch.int32, device=dev),
                 "forced": torch.zeros((B, S), dtype=torch.int32, device=dev),
                 "margins": torch.zeros((B, S), dtype=torch.float32, device=dev),
@@ -508,19 +531,161 @@ class Engine:
         self._decode_state[B] = st          # most recently used last
         return st
 
-    def _decode_step_launch(self, st: dict, B: int, S: int, use_forced: bool, mask_id: int):
-        """embed(cur) -> 24 blocks -> lm_head + argmax -> bookkeeping; graph-capturable."""
+    def _sampling_buffers(self, st: dict, B: int):
+        if "logits" not in st:
+            V = self.cfg.text.vocab_size
+            st["logits"] = torch.empty((B, V), dtype=torch.bfloat16, device=self.device)
+            st["probs"] = torch.empty((B, V), dtype=torch.bfloat16, device=self.device)
+
+    def _reasoning_buffers(self, st: dict, B: int):
+        if "coords" not in st:
+            dev = self.device
+            st["coords"] = torch.zeros((B, st["S"]), dtype=torch.float32, device=dev)
+            st["coord_bins"] = torch.zeros((B,), dtype=torch.int32, device=dev)
+            st["coord_vals"] = torch.zeros((B, 1), dtype=torch.float32, device=dev)
+            st["coord_emb"] = torch.empty((B, self.cfg.text.dim), dtype=torch.bfloat16, device=dev)
+            st["region_ws"] = torch.empty(int(self.lib.md_region_workspace_bytes(self.model, B)), dtype=torch.uint8,
+                                          device=dev)
+
+    def sample_tokens(self, logits: torch.Tensor, temperature: float, top_p: float, out_ids: torch.Tensor,
+                      out_stride: int, out_offset: int = 0, step: Optional[torch.Tensor] = None,
+                      seed: Optional[torch.Tensor] = None, uniforms: Optional[torch.Tensor] = None,
+                      scratch: Optional[torch.Tensor] = None, keep_probs: bool = False):
+        """softmax(logits / T) -> _apply_top_p -> one draw per row, on the device (moondream.py:270-278, 312-318)."""
+        B, V = logits.shape
+        if scratch is None:
+            scratch = torch.empty((B, V), dtype=torch.bfloat16, device=self.device)
+        N.check(self.lib.md_sample_top_p(N.ptr(logits), B, V, float(temperature), float(top_p), N.ptr(seed), N.ptr(step),
+                                         N.ptr(uniforms), N.ptr(scratch), int(keep_probs), N.ptr(out_ids), out_stride,
+                                         out_offset, N.current_stream()), "md_sample_top_p")
+        return scratch
+
+    def _decode_step_launch(self, st: dict, B: int, mode: "DecodeMode"):
+        """One decode step for the whole batch, graph-capturable: [coordinate interleave ->] embed(cur) -> decoder
+        blocks -> lm_head (+ masks) -> argmax [-> top-p sample] -> bookkeeping.  No host involvement."""
         lib, s = self.lib, N.current_stream()
+        S = st["S"]
         kv = self._kv(st["bt"])
-        self.embed(st["cur"], st["x"])
+        tk = self.cfg.tokenizer
+        if mode.reasoning:
+            # _generate_reasoning (moondream.py:381-391): a coord_id token is fed as encode_coordinate(argmax of
+            # decode_coordinate(last hidden)) instead of its embedding.  Computed for every row (50 MB of region
+            # weights, ~1 % of a step), used by the rows whose current token is coord_id.
+            N.check(lib.md_region_decode(self.model, 0, N.ptr(st["x"]), st["x"].stride(0), B, N.ptr(st["coord_bins"]),
+                                         N.ptr(st["region_ws"]), s), "md_region_decode")
+            N.check(lib.md_region_bins_to_values(0, N.ptr(st["coord_bins"]), B, self.cfg.region.coord_out_dim,
+                                                 N.ptr(st["coord_vals"]), s), "md_region_bins_to_values")
+            N.check(lib.md_store_column_f32(N.ptr(st["coord_vals"]), B, N.ptr(st["coords"]), S, N.ptr(st["step"]), 0, s),
+                    "md_store_column_f32")
+            N.check(lib.md_region_encode(self.model, 0, N.ptr(st["coord_vals"]), B, N.ptr(st["coord_emb"]),
+                                         st["coord_emb"].stride(0), N.ptr(st["region_ws"]), s), "md_region_encode")
+            N.check(lib.md_embed_tokens_select(self.model, N.ptr(st["cur"]), 1, B, tk.coord_id, N.ptr(st["coord_emb"]),
+                                               st["coord_emb"].stride(0), N.ptr(st["x"]), st["x"].stride(0), s),
+                    "md_embed_tokens_select")
+        else:
+            self.embed(st["cur"], st["x"])
         N.check(lib.md_text_decode_step(self.model, N.ptr(st["x"]), N.ptr(st["pos"]), B, ctypes.byref(kv),
                                         N.ptr(st["normed"]), N.ptr(st["ws"]), s), "md_text_decode_step")
         off = int(lib.md_text_decode_workspace_bytes(self.model, B))
-        self.lm_head(st["normed"], st["preds"], S, mask_id=mask_id, out_index=st["step"], margins=st["margins"],
-                     ws=st["ws"][off:], out_offset=1, prenormed=True)
+        self.lm_head(st["normed"], st["preds"], S, mask_id=mode.mask_id, mask_id2=mode.mask_id2, out_index=st["step"],
+                     margins=st["margins"], logits=st["logits"] if mode.sampled else None, ws=st["ws"][off:],
+                     out_offset=1, prenormed=True)
+        if mode.sampled:       # the sampled token replaces the argmax in the slot the bookkeeping reads
+            self.sample_tokens(st["logits"], mode.temperature, mode.top_p, st["preds"], S, out_offset=1, step=st["step"],
+                               seed=st["seed"], scratch=st["probs"])
         N.check(lib.md_decode_advance(N.ptr(st["cur"]), N.ptr(st["pos"]), N.ptr(st["step"]), N.ptr(st["preds"]),
-                                      N.ptr(st["forced"]) if use_forced else None, S, B,
-                                      self.cfg.tokenizer.eos_id, N.ptr(st["finished"]), s), "md_decode_advance")
+                                      N.ptr(st["forced"]) if mode.forced else None, S, B,
+                                      mode.eos_id, N.ptr(st["finished"]), s), "md_decode_advance")
+
+    def decode_mode(self, forced: bool = False, temperature: float = 0.0, top_p: float = 1.0,
+                    reasoning: bool = False) -> "DecodeMode":
+        tk = self.cfg.tokenizer
+        if reasoning:      # moondream.py:344 eos = answer_id; :395-396 mask eos_id and size_id
+            return DecodeMode(forced, float(temperature), float(top_p), True, tk.eos_id, tk.size_id, tk.answer_id)
+        return DecodeMode(forced, float(temperature), float(top_p), False, tk.answer_id, -1, tk.eos_id)   # :517
+
+    def _prefill_phase(self, st: dict, prompts, start_pos: Sequence[int], prompt_embeds, prefix_len: int):
+        """_prefill_prompt (moondream.py:280-321) for the batch: ragged prompt prefill at `start_pos`, last rows ->
+        st["x"].  Returns the prompt lengths."""
+        t = self.cfg.text
+        B = len(start_pos)
+        lens = [len(p) for p in prompts]
+        q_off = [0]
+        for n in lens:
+            q_off.append(q_off[-1] + n)
+        if prompt_embeds is None:
+            flat = self._i32([tok for p in prompts for tok in p])
+            x = torch.empty((q_off[-1], t.dim), dtype=torch.bfloat16, device=self.device)
+            self.embed(flat, x)
+        else:
+            x = prompt_embeds
+        self.prefill(x, q_off, list(start_pos), st["bt"], prefix_len=prefix_len)
+        last = self._i32([q_off[i + 1] - 1 for i in range(B)])
+        N.check(self.lib.md_gather_rows_bf16(N.ptr(x), x.stride(0), N.ptr(last), B, t.dim, N.ptr(st["x"]),
+                                             st["x"].stride(0), N.current_stream()), "md_gather_rows_bf16")
+        return lens
+
+    def _decode_phase(self, st: dict, B: int, pos0: Sequence[int], max_tokens: int, mode: "DecodeMode",
+                      forced=None, use_graph: bool = True, stop_on_eos: bool = True, chunk: int = 0,
+                      seed: Optional[int] = None):
+        """First token from st["x"] (the prefill's last hidden rows), then `max_tokens` decode steps.  A generator:
+        yields (lo, hi) after every `chunk` steps (0 = only once, at the end) so a caller can read preds[:, lo:hi]
+        while the loop is still running (streaming); the final yield covers the remainder."""
+        S, n_out = st["S"], max_tokens + 1
+        if n_out > S:
+            raise ValueError(f"max_tokens {max_tokens} exceeds max_context {self.cfg.text.max_context}")
+        st["step"].zero_()
+        st["finished"].zero_()
+        if mode.sampled:
+            self._sampling_buffers(st, B)
+            if seed is None:
+                seed = int(torch.randint(0, 2 ** 62, (1,)).item())     # torch's global RNG, like the reference's multinomial
+            st["seed"].fill_(seed)
+        if mode.reasoning:
+            self._reasoning_buffers(st, B)
+        # first token: no ids are masked at the prefill (moondream.py:312-318)
+        self.lm_head(st["x"], st["preds"], S, mask_id=-1, out_index=None, margins=st["margins"],
+                     logits=st["logits"] if mode.sampled else None)
+        if mode.sampled:
+            self.sample_tokens(st["logits"], mode.temperature, mode.top_p, st["preds"], S, out_offset=0, step=None,
+                               seed=st["seed"], scratch=st["probs"])
+        if mode.forced:
+            f = torch.zeros((B, n_out), dtype=torch.int32)
+            for i, row in enumerate(forced):
+                f[i, : min(len(row), n_out)] = torch.tensor(list(row)[:n_out], dtype=torch.int32)
+            st["forced"][:, :n_out].copy_(f.to(self.device))
+            st["cur"].copy_(st["forced"][:, 0])
+        else:
+            st["cur"].copy_(st["preds"][:, 0])
+        st["pos"].copy_(self._i32(list(pos0)))
+        graph = st["graphs"].get(mode) if use_graph else None
+        if use_graph and graph is None and max_tokens > 0:
+            self._decode_step_launch(st, B, mode)           # warm-up (also validates)
+            torch.cuda.synchronize()
+            # rewind the state the warm-up step advanced
+            st["step"].zero_()
+            st["pos"].sub_(1)
+            st["cur"].copy_(st["forced"][:, 0] if mode.forced else st["preds"][:, 0])
+            st["finished"].zero_()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                self._decode_step_launch(st, B, mode)
+            st["graphs"][mode] = graph                      # capture does not execute; state is still at step 0
+        lo = 0
+        steps = 0
+        for s in range(max_tokens):
+            if graph is not None:
+                graph.replay()
+            else:
+                self._decode_step_launch(st, B, mode)
+            steps += 1
+            if chunk and steps % chunk == 0:
+                yield lo, steps                             # slots [lo, steps) are final once this step is queued
+                lo = steps
+            if stop_on_eos and not mode.forced and (s % 16 == 15) and bool(st["finished"].all().item()):
+                break
+        st["steps_run"] = steps
+        yield lo, steps + 1
 
     @_on_device
     def generate(self, prefixes: Sequence[PrefixKV], prompts: Sequence[Sequence[int]], max_tokens: int,
@@ -528,15 +693,18 @@ class Engine:
                  use_graph: bool = True, stop_on_eos: bool = True,
                  prompt_embeds: Optional[torch.Tensor] = None, to_host: bool = True,
                  prefilled_hidden: Optional[torch.Tensor] = None,
-                 sampler: Optional[Callable[[torch.Tensor], torch.Tensor]] = None) -> GenerationResult:
+                 sampler: Optional[Callable[[torch.Tensor], torch.Tensor]] = None,
+                 temperature: float = 0.0, top_p: float = 1.0, seed: Optional[int] = None,
+                 prefix_len: int = -1) -> GenerationResult:
         """`_generate_answer` (moondream.py:434-539) for a batch: ragged prompt prefill, first
         token from the LM head, then `max_tokens` decode steps (the reference also runs the step after
-        the last emitted token).  Greedy by default: returns the argmax at every step; callers cut at eos.
-        `sampler` (moondream_b200.sampling.HostSampler) switches to the reference's temperature / top-p
-        sampling (:312-318, :524-530): every step hands its bf16 logits [B, vocab] to the callable, which
-        returns the tokens to feed next; the returned tokens are then the sampled ones.  That path
-        synchronises once per token and does not use the CUDA graph."""
-        t, tk = self.cfg.text, self.cfg.tokenizer
+        the last emitted token), all inside one CUDA graph per step with no per-token host sync.
+        temperature 0: greedy, returns the argmax at every step; callers cut at eos.
+        temperature > 0: the reference's softmax / top-p / multinomial on the device (md_sample_top_p), still inside
+        the graph; the returned tokens are the sampled ones.
+        `sampler` (moondream_b200.sampling.HostSampler) is the host-side restatement of the same arithmetic with torch
+        CPU ops (bit-equal to the oracle, one synchronisation per token) kept for parity tests.
+        prefix_len 0 = pure causal mask (text-only query, moondream.py:565-574)."""
         B = len(prefixes)
         assert len(prompts) == B
         n_out = max_tokens + 1              # slots the caller gets back: the first token + one per decode step
@@ -548,68 +716,20 @@ class Engine:
         try:
             st = self._decode_buffers(B)
             S = st["S"]                     # row stride of preds / forced / margins (fixed, >= n_out)
-            if n_out > S:
-                raise ValueError(f"max_tokens {max_tokens} exceeds max_context {t.max_context}")
             st["bt"].copy_(bt)
-            # ---- prompt prefill (moondream.py:280-321) ----
             if prefilled_hidden is not None:
                 st["x"].copy_(prefilled_hidden)
             else:
-                q_off = [0]
-                for n in lens:
-                    q_off.append(q_off[-1] + n)
-                if prompt_embeds is None:
-                    flat = self._i32([tok for p in prompts for tok in p])
-                    x = torch.empty((q_off[-1], t.dim), dtype=torch.bfloat16, device=self.device)
-                    self.embed(flat, x)
-                else:
-                    x = prompt_embeds
-                self.prefill(x, q_off, [p.pos for p in prefixes], st["bt"])
-                last = self._i32([q_off[i + 1] - 1 for i in range(B)])
-                N.check(self.lib.md_gather_rows_bf16(N.ptr(x), x.stride(0), N.ptr(last), B, t.dim, N.ptr(st["x"]),
-                                                     st["x"].stride(0), N.current_stream()), "md_gather_rows_bf16")
-            st["step"].zero_()
-            st["finished"].zero_()
+                self._prefill_phase(st, prompts, [p.pos for p in prefixes], prompt_embeds, prefix_len)
+            pos0 = [prefixes[i].pos + lens[i] for i in range(B)]
             if sampler is not None:
                 if forced is not None:
                     raise ValueError("generate: `forced` and `sampler` are mutually exclusive")
-                return self._generate_sampled(st, prefixes, lens, B, S, max_tokens, sampler, stop_on_eos, to_host)
-            self.lm_head(st["x"], st["preds"], S, mask_id=-1, out_index=None, margins=st["margins"])
-            use_forced = forced is not None
-            if use_forced:
-                f = torch.zeros((B, n_out), dtype=torch.int32)
-                for i, row in enumerate(forced):
-                    f[i, : min(len(row), n_out)] = torch.tensor(list(row)[:n_out], dtype=torch.int32)
-                st["forced"][:, :n_out].copy_(f.to(self.device))
-                st["cur"].copy_(st["forced"][:, 0])
-            else:
-                st["cur"].copy_(st["preds"][:, 0])
-            st["pos"].copy_(self._i32([prefixes[i].pos + lens[i] for i in range(B)]))
-            # ---- decode loop (moondream.py:481-530), one graph replay per token ----
-            gkey = (use_forced, tk.answer_id)
-            graph = st["graphs"].get(gkey) if use_graph else None
-            if use_graph and graph is None and max_tokens > 0:
-                self._decode_step_launch(st, B, S, use_forced, tk.answer_id)   # warm-up (also validates)
-                torch.cuda.synchronize()
-                # rewind the state the warm-up step advanced
-                st["step"].zero_()
-                st["pos"].sub_(1)
-                st["cur"].copy_(st["forced"][:, 0] if use_forced else st["preds"][:, 0])
-                st["finished"].zero_()
-                graph = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(graph):
-                    self._decode_step_launch(st, B, S, use_forced, tk.answer_id)
-                st["graphs"][gkey] = graph
-                # capture does not execute; state is still at step 0
-            steps = 0
-            for s in range(max_tokens):
-                if graph is not None:
-                    graph.replay()
-                else:
-                    self._decode_step_launch(st, B, S, use_forced, tk.answer_id)
-                steps += 1
-                if stop_on_eos and not use_forced and (s % 16 == 15) and bool(st["finished"].all().item()):
-                    break
+                return self._generate_sampled(st, pos0, B, S, max_tokens, sampler, stop_on_eos, to_host)
+            mode = self.decode_mode(forced is not None, temperature, top_p)
+            for _ in self._decode_phase(st, B, pos0, max_tokens, mode, forced, use_graph, stop_on_eos, seed=seed):
+                pass
+            steps = st["steps_run"]
             if to_host:
                 tokens = st["preds"][:, :n_out].to("cpu")          # the one device->host read of the call
                 margins = st["margins"][:, :n_out].to("cpu")
@@ -621,24 +741,114 @@ class Engine:
                 self.pages.release(pages)
         return GenerationResult(tokens, margins, steps)
 
-    def _generate_sampled(self, st: dict, prefixes: Sequence[PrefixKV], lens: Sequence[int], B: int, S: int,
+    @_on_device
+    def generate_stream(self, prefixes: Sequence[PrefixKV], prompts: Sequence[Sequence[int]], max_tokens: int,
+                        chunk: int = 8, temperature: float = 0.0, top_p: float = 1.0, seed: Optional[int] = None,
+                        prompt_embeds: Optional[torch.Tensor] = None, prefix_len: int = -1, eos_id: Optional[int] = None):
+        """Streaming form of `generate` (the generator of moondream.py:470-537): yields int32 [B, k] host tensors of
+        newly decoded tokens every `chunk` graph replays while later steps are still being queued, and stops once every
+        sequence has produced `eos_id`.  Closing the generator early (a consumer's `break`) releases the pages."""
+        B = len(prefixes)
+        eos = self.cfg.tokenizer.eos_id if eos_id is None else eos_id
+        lens = [len(p) for p in prompts]
+        total = [prefixes[i].pos + lens[i] + max_tokens + 1 for i in range(B)]
+        bt, owned = self._sequence_tables(prefixes, max(total), consume=False)
+        try:
+            with torch.cuda.device(self.device):
+                st = self._decode_buffers(B)
+                st["bt"].copy_(bt)
+                self._prefill_phase(st, prompts, [p.pos for p in prefixes], prompt_embeds, prefix_len)
+                pos0 = [prefixes[i].pos + lens[i] for i in range(B)]
+                mode = self.decode_mode(False, temperature, top_p)
+                done = torch.zeros(B, dtype=torch.bool)
+                for lo, hi in self._decode_phase(st, B, pos0, max_tokens, mode, None, True, False, chunk=chunk, seed=seed):
+                    hi = min(hi, max_tokens)
+                    if hi <= lo:
+                        continue
+                    part = st["preds"][:, lo:hi].to("cpu")          # synchronises on the steps queued so far only
+                    yield part
+                    done |= (part == eos).any(dim=1)
+                    if bool(done.all()):
+                        break
+        finally:
+            for pages in owned:
+                self.pages.release(pages)
+
+    @_on_device
+    def generate_reasoning(self, prefixes: Sequence[PrefixKV], prompts: Sequence[Sequence[int]],
+                           answer_prompt: Sequence[int], max_tokens: int, temperature: float = 0.0, top_p: float = 1.0,
+                           seed: Optional[int] = None, prompt_embeds: Optional[torch.Tensor] = None,
+                           prefix_len: int = -1):
+        """query(reasoning=True) (moondream.py:576-596 over _generate_reasoning :323-432): phase 1 decodes the chain
+        of thought until answer_id with eos_id / size_id masked, feeding region-encoded coordinates for coord_id
+        tokens (on the device, inside the graph); phase 2 prefills `answer_prompt` at each sequence's own position
+        and decodes the answer (_generate_answer).  Returns per sequence (reasoning_tokens, coords, answer_tokens):
+        coords[j] is the coordinate decoded for reasoning token j when that token is coord_id."""
+        t, tk = self.cfg.text, self.cfg.tokenizer
+        B = len(prefixes)
+        lens = [len(p) for p in prompts]
+        total = max(prefixes[i].pos + lens[i] for i in range(B)) + 2 * (max_tokens + 1) + len(answer_prompt)
+        total = min(total, t.max_context)
+        budget = total - max(prefixes[i].pos + lens[i] for i in range(B)) - len(answer_prompt) - 2
+        if budget < 2:
+            raise ValueError("the prompt leaves no room for generation within max_context")
+        max_tokens = min(max_tokens, budget // 2)
+        bt, owned = self._sequence_tables(prefixes, total, consume=False)
+        try:
+            st = self._decode_buffers(B)
+            st["bt"].copy_(bt)
+            self._prefill_phase(st, prompts, [p.pos for p in prefixes], prompt_embeds, prefix_len)
+            pos0 = [prefixes[i].pos + lens[i] for i in range(B)]
+            mode = self.decode_mode(False, temperature, top_p, reasoning=True)
+            for _ in self._decode_phase(st, B, pos0, max_tokens, mode, None, True, True, seed=seed):
+                pass
+            toks = st["preds"][:, : max_tokens + 1].to("cpu")
+            coords = st["coords"][:, : max_tokens + 1].to("cpu")
+            out_r, out_c, pos1 = [], [], []
+            for b in range(B):
+                row = toks[b].tolist()
+                n = next((j for j, v in enumerate(row[:max_tokens]) if v == tk.answer_id), max_tokens)
+                out_r.append(row[:n])
+                out_c.append(coords[b, :n].tolist())
+                pos1.append(pos0[b] + n)          # every emitted token went through the decoder (moondream.py:398)
+            # phase 2: _generate_answer with prompt = answer_prompt at each sequence's position
+            self._prefill_phase(st, [list(answer_prompt)] * B, pos1, None, prefix_len)
+            pos2 = [p + len(answer_prompt) for p in pos1]
+            mode2 = self.decode_mode(False, temperature, top_p)
+            for _ in self._decode_phase(st, B, pos2, max_tokens, mode2, None, True, True,
+                                        seed=None if seed is None else seed + 1):
+                pass
+            ans = st["preds"][:, : max_tokens + 1].to("cpu")
+            out_a = []
+            for b in range(B):
+                row = ans[b].tolist()[:max_tokens]
+                n = next((j for j, v in enumerate(row) if v == tk.eos_id), len(row))
+                out_a.append(row[:n])
+        finally:
+            for pages in owned:
+                self.pages.release(pages)
+        return [(out_r[b], out_c[b], out_a[b]) for b in range(B)]
+
+    def _generate_sampled(self, st: dict, pos0: Sequence[int], B: int, S: int,
                           max_tokens: int, sampler: Callable[[torch.Tensor], torch.Tensor], stop_on_eos: bool,
                           to_host: bool) -> GenerationResult:
-        """Decode loop of `generate` with the next token chosen by `sampler` from each step's logits.  Uses the
-        teacher-forcing slots: step s consumes forced[:, s], its sampled successor is written to forced[:, s + 1]
-        before the bookkeeping kernel advances.  (The caller holds and releases the sequences' pages.)"""
+        """Decode loop of `generate` with the next token chosen on the HOST by `sampler` from each step's logits (the
+        torch-CPU restatement of the reference's sampler; parity tests).  Uses the teacher-forcing slots: step s
+        consumes forced[:, s], its sampled successor is written to forced[:, s + 1] before the bookkeeping kernel
+        advances.  (The caller holds and releases the sequences' pages.)"""
         tk = self.cfg.tokenizer
         lib = self.lib
-        logits = st.get("logits")
-        if logits is None:
-            logits = st["logits"] = torch.empty((B, self.cfg.text.vocab_size), dtype=torch.bfloat16, device=self.device)
+        self._sampling_buffers(st, B)
+        logits = st["logits"]
+        st["step"].zero_()
+        st["finished"].zero_()
         self.lm_head(st["x"], st["preds"], S, mask_id=-1, out_index=None, margins=st["margins"], logits=logits)
         tok = sampler(logits).to(torch.int32)
         done = tok.cpu() == tk.eos_id
         st["forced"].zero_()
         st["forced"][:, 0].copy_(tok)
         st["cur"].copy_(st["forced"][:, 0])
-        st["pos"].copy_(self._i32([prefixes[i].pos + lens[i] for i in range(B)]))
+        st["pos"].copy_(self._i32(list(pos0)))
         kv = self._kv(st["bt"])
         off = int(lib.md_text_decode_workspace_bytes(self.model, B))
         steps = 0
@@ -688,8 +898,8 @@ class Engine:
 
     def _bins_to_values(self, which: int, bins: torch.Tensor) -> torch.Tensor:
         out = torch.empty(bins.shape, dtype=torch.float32, device=self.device)
-        N.check(self.lib.md_region_bins_to_values(which, N.ptr(bins), bins.numel(), N.ptr(out),
-                                                  N.current_stream()), "md_region_bins_to_values")
+        N.check(self.lib.md_region_bins_to_values(which, N.ptr(bins), bins.numel(), self.cfg.region.coord_out_dim,
+                                                  N.ptr(out), N.current_stream()), "md_region_bins_to_values")
         return out
 
     @_on_device

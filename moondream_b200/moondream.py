@@ -11,9 +11,11 @@ Deliberate differences from the reference (documented in DESIGN.md):
   * ``settings`` without "variant" is accepted by ``encode_image`` (the reference raises KeyError at
     moondream.py:240-243); LoRA variants (lora.py) need the network and are rejected with
     NotImplementedError when requested.
-  * temperature > 0 follows the reference's softmax / top-p / multinomial arithmetic (moondream.py:270-278,
-    312-318) on the host from each step's logits (moondream_b200/sampling.py): functionally the reference's
-    default behaviour, but one synchronisation per token; the CUDA-graph path is the greedy one.
+  * temperature > 0 (the reference's default 0.5 / top_p 0.3) follows the reference's softmax / top-p arithmetic
+    (moondream.py:270-278, 312-318) ON THE DEVICE inside the decode graph (csrc/sampling.cu); the draw is an inverse
+    CDF over the kept probabilities from a Philox stream seeded from torch's global RNG (the reference's
+    torch.multinomial consumes that RNG differently, so tokens agree in distribution, not draw by draw).
+    `settings["host_sampler"] = True` selects the host restatement with torch CPU ops (parity tests).
   * ``EncodedImage`` holds KV *pages* (shared, copy-on-write for the partial page) instead of
     cloned tensors; ``.caches`` materialises the reference's per-layer (k, v) view on demand.
 """
@@ -96,10 +98,32 @@ class MoondreamModel:
                                "moondream_b200.weights.load_weights_into_model(path, model)")
         return self._engine
 
+    # the reference's four swap seams (moondream.py:168-192), batch-1 tensor signatures, on the native engine
+    @property
+    def seam(self):
+        if getattr(self, "_seam", None) is None:
+            from .seam import SeamAdapter
+
+            self._seam = SeamAdapter(self.engine)
+        return self._seam
+
+    def _vis_enc(self, x: torch.Tensor):
+        return self.seam._vis_enc(x)
+
+    def _vis_proj(self, g: torch.Tensor, r: torch.Tensor):
+        return self.seam._vis_proj(g, r)
+
+    def _prefill(self, x: torch.Tensor, attn_mask: torch.Tensor, pos_ids: torch.Tensor, lora=None):
+        return self.seam._prefill(x, attn_mask, pos_ids, lora)
+
+    def _decode_one_tok(self, x: torch.Tensor, attn_mask: torch.Tensor, pos_ids: torch.Tensor, lora=None):
+        return self.seam._decode_one_tok(x, attn_mask, pos_ids, lora)
+
     def load_state_dict(self, state_dict: Dict[str, torch.Tensor], strict: bool = False):
         sd = {k.replace("model.", "", 1) if k.startswith("model.") else k: v for k, v in state_dict.items()}
         self._engine = Engine(self.config, sd, device=self._device, kv_pages=self._kv_pages,
                               max_batch=self._max_batch)
+        self._seam = None
         return [], []
 
     def to(self, *a, **k):
@@ -123,19 +147,27 @@ class MoondreamModel:
     # ------------------------------------------------------------------ settings
     @staticmethod
     def _text_settings(settings: Optional[dict]):
-        """(max_tokens, sampler) from the reference's TextSamplingSettings (moondream.py:443-454): sampler is None
-        for temperature 0 (greedy, CUDA-graph decode), else the host nucleus sampler."""
+        """(max_tokens, sampling) from the reference's TextSamplingSettings (moondream.py:443-454).  `sampling` is the
+        keyword set Engine.generate takes: empty for temperature 0 (greedy), temperature / top_p for on-device
+        sampling, or a HostSampler when settings["host_sampler"] asks for the torch-CPU restatement."""
         temperature = settings.get("temperature", DEFAULT_TEMPERATURE) if settings else DEFAULT_TEMPERATURE
         top_p = settings.get("top_p", DEFAULT_TOP_P) if settings else DEFAULT_TOP_P
         if settings and settings.get("variant") is not None:
             raise NotImplementedError("LoRA variants are downloaded from the network by the reference "
                                       "(lora.py:23-40) and are not supported offline")
         max_tokens = settings.get("max_tokens", DEFAULT_MAX_TOKENS) if settings else DEFAULT_MAX_TOKENS
-        sampler = None
+        if temperature < 0:
+            raise ValueError("temperature must be >= 0")
+        sampling: Dict[str, Any] = {}
         if temperature != 0:
-            from .sampling import HostSampler
-            sampler = HostSampler(temperature, top_p)          # ValueError for a negative temperature
-        return max_tokens, sampler
+            if settings and settings.get("host_sampler"):
+                from .sampling import HostSampler
+                sampling["sampler"] = HostSampler(temperature, top_p)
+            else:
+                sampling.update(temperature=float(temperature), top_p=float(top_p))
+                if settings and settings.get("seed") is not None:
+                    sampling["seed"] = int(settings["seed"])
+        return max_tokens, sampling
 
     # ------------------------------------------------------------------ image encoding
     def encode_images(self, images: Sequence[Any]) -> List[EncodedImage]:
@@ -157,10 +189,11 @@ class MoondreamModel:
 
     # ------------------------------------------------------------------ text generation
     def _run(self, encoded: Sequence[EncodedImage], prompts: Sequence[Sequence[int]], max_tokens: int,
-             eos_id: Optional[int] = None, prompt_embeds=None, sampler=None) -> List[List[int]]:
+             eos_id: Optional[int] = None, prompt_embeds=None, sampling: Optional[dict] = None,
+             prefix_len: int = -1) -> List[List[int]]:
         eos = self.config.tokenizer.eos_id if eos_id is None else eos_id
         res = self.engine.generate([e._prefix for e in encoded], prompts, max_tokens,
-                                   prompt_embeds=prompt_embeds, sampler=sampler)
+                                   prompt_embeds=prompt_embeds, prefix_len=prefix_len, **(sampling or {}))
         toks = res.tokens.tolist()
         out = []
         for row in toks:
@@ -185,15 +218,15 @@ class MoondreamModel:
         return out
 
     def _run_images(self, images: Sequence[Any], prompts: Sequence[Sequence[int]], max_tokens: int,
-                    sampler=None) -> List[List[int]]:
+                    sampling: Optional[dict] = None) -> List[List[int]]:
         """Batched generation straight from raw images: when no image is pre-encoded the image prefix and the
         prompt are prefilled in one decoder pass (engine.caption_from_crops); otherwise (and when sampling)
         the two-step path."""
-        if sampler is not None or any(isinstance(im, EncodedImage) for im in images):
+        if sampling or any(isinstance(im, EncodedImage) for im in images):
             rows: List[List[int]] = []
             for lo in range(0, len(images), self._max_batch):
                 rows += self._run(self.encode_images(images[lo: lo + self._max_batch]),
-                                  prompts[lo: lo + self._max_batch], max_tokens, sampler=sampler)
+                                  prompts[lo: lo + self._max_batch], max_tokens, sampling=sampling)
             return rows
         out: List[List[int]] = []
         for lo in range(0, len(images), self._max_batch):
@@ -205,32 +238,14 @@ class MoondreamModel:
 
     def _stream_text(self, tokens: Sequence[int]):
         """Streaming detokenisation with the reference's flush rules (moondream.py:476-537)."""
-        cache: List[int] = []
-        print_len = 0
+        dec = _StreamDecoder(self.tokenizer)
         for tok in tokens:
-            cache.append(tok)
-            text = self.tokenizer.decode(cache)
-            if text.endswith("\n"):
-                chunk = text[print_len:]
-                cache, print_len = [], 0
-                if chunk:
-                    yield chunk
-            elif len(text) > 0 and _is_cjk_char(ord(text[-1])):
-                chunk = text[print_len:]
-                print_len += len(chunk)
-                if chunk:
-                    yield chunk
-            else:
-                sp = text.rfind(" ", print_len)
-                if sp >= print_len:
-                    chunk = text[print_len: sp + 1]
-                    print_len += len(chunk)
-                    if chunk:
-                        yield chunk
-        if cache:
-            chunk = self.tokenizer.decode(cache)[print_len:]
-            if chunk:
-                yield chunk
+            out = dec.push(tok)
+            if out:
+                yield out
+        out = dec.flush()
+        if out:
+            yield out
 
     def caption_batch(self, images: Sequence[Any], length: str = "normal",
                       settings: Optional[dict] = None) -> List[Dict[str, str]]:
@@ -239,8 +254,8 @@ class MoondreamModel:
             raise NotImplementedError("Model does not support captioning.")
         if length not in tpl:
             raise ValueError(f"Model does not support caption length '{length}'.")
-        max_tokens, sampler = self._text_settings(settings)
-        toks = self._run_images(images, [tpl[length]] * len(images), max_tokens, sampler)
+        max_tokens, sampling = self._text_settings(settings)
+        toks = self._run_images(images, [tpl[length]] * len(images), max_tokens, sampling)
         return [{"caption": "".join(self._stream_text(t))} for t in toks]
 
     def caption(self, image, length: Literal["normal", "short", "long"] = "normal", stream: bool = False,
@@ -250,58 +265,122 @@ class MoondreamModel:
             raise NotImplementedError("Model does not support captioning.")
         if length not in tpl:
             raise ValueError(f"Model does not support caption length '{length}'.")
-        max_tokens, sampler = self._text_settings(settings)
+        max_tokens, sampling = self._text_settings(settings)
         enc = self.encode_image(image, settings)
-        toks = self._run([enc], [tpl[length]], max_tokens, sampler=sampler)[0]
         if stream:
-            return {"caption": self._stream_text(toks)}
+            return {"caption": self._stream_generate(enc, tpl[length], max_tokens, sampling)}
+        toks = self._run([enc], [tpl[length]], max_tokens, sampling=sampling)[0]
         return {"caption": "".join(self._stream_text(toks))}
 
-    def _query_prompt(self, question: str, spatial_refs: Optional[SpatialRefs], with_bos: bool) -> List[int]:
+    def _query_prompt(self, question: str, spatial_refs: Optional[SpatialRefs], with_bos: bool,
+                      reasoning: bool = False) -> List[int]:
         tk = self.config.tokenizer
         toks = ([tk.bos_id] if with_bos else []) + list(tk.templates["query"]["prefix"])
         if spatial_refs:
             for ref in spatial_refs:
                 toks += [tk.coord_id, tk.coord_id] if len(ref) == 2 else [tk.coord_id, tk.coord_id, tk.size_id]
         toks += self.tokenizer.encode(question).ids + list(tk.templates["query"]["suffix"])
-        # the reference appends the suffix a second time when reasoning is off (moondream.py:586-604)
-        toks += list(tk.templates["query"]["suffix"])
+        if reasoning:
+            toks += [tk.thinking_id]                   # moondream.py:586-587
+        else:
+            # the reference appends the suffix a second time when reasoning is off (moondream.py:597-598)
+            toks += list(tk.templates["query"]["suffix"])
         return toks
 
     def query_batch(self, images: Sequence[Any], questions: Sequence[str],
                     settings: Optional[dict] = None) -> List[Dict[str, str]]:
         if self.config.tokenizer.templates["query"] is None:
             raise NotImplementedError("Model does not support querying.")
-        max_tokens, sampler = self._text_settings(settings)
+        max_tokens, sampling = self._text_settings(settings)
         prompts = [self._query_prompt(q, None, False) for q in questions]
-        toks = self._run_images(images, prompts, max_tokens, sampler)
+        toks = self._run_images(images, prompts, max_tokens, sampling)
         return [{"answer": "".join(self._stream_text(t))} for t in toks]
 
     def query(self, image=None, question: str = None, reasoning: bool = False,
               spatial_refs: Optional[SpatialRefs] = None, stream: bool = False,
               settings: Optional[dict] = None):
+        """moondream.py:541-618.  image=None is the text-only query (BOS + prompt at position 0 under a pure causal
+        mask, :565-574); reasoning=True decodes the grounded chain of thought first (:576-596)."""
         if self.config.tokenizer.templates["query"] is None:
             raise NotImplementedError("Model does not support querying.")
         if question is None:
             raise ValueError("question must be provided.")
         if spatial_refs and image is None:
             raise ValueError("spatial_refs can only be used with an image.")
+        max_tokens, sampling = self._text_settings(settings)
+        if image is not None:
+            enc = self.encode_image(image, settings)
+            prefix_len = -1
+        else:
+            enc = EncodedImage(PrefixKV(0, [], self.engine.pages), self.engine)      # nothing cached: position 0
+            prefix_len = 0
+        prompt = self._query_prompt(question, spatial_refs, with_bos=image is None, reasoning=reasoning)
+        embeds = self._prompt_embeds_with_refs(prompt, spatial_refs) if spatial_refs else None
         if reasoning:
-            raise NotImplementedError("reasoning=True (grounded chain of thought, moondream.py:323-432) "
-                                      "is listed as 'next' in DESIGN.md")
-        if image is None:
-            raise NotImplementedError("text-only query (pure causal mask, moondream.py:565-574) is "
-                                      "listed as 'next' in DESIGN.md")
-        max_tokens, sampler = self._text_settings(settings)
-        enc = self.encode_image(image, settings)
-        prompt = self._query_prompt(question, spatial_refs, False)
-        embeds = None
-        if spatial_refs:
-            embeds = self._prompt_embeds_with_refs(prompt, spatial_refs)
-        toks = self._run([enc], [prompt], max_tokens, prompt_embeds=embeds, sampler=sampler)[0]
+            if "sampler" in sampling:
+                raise NotImplementedError("reasoning runs on the device; the host sampler is a parity-test path")
+            tk = self.config.tokenizer
+            r_toks, coords, a_toks = self.engine.generate_reasoning(
+                [enc._prefix], [prompt], tk.templates["query"]["suffix"], max_tokens, prompt_embeds=embeds,
+                prefix_len=prefix_len, **sampling)[0]
+            text, grounding = self._reasoning_result(r_toks, coords)
+            answer = self._stream_text(a_toks) if stream else "".join(self._stream_text(a_toks))
+            return {"reasoning": {"text": text, "grounding": grounding}, "answer": answer}
         if stream:
-            return {"answer": self._stream_text(toks)}
+            return {"answer": self._stream_generate(enc, prompt, max_tokens, sampling, embeds, prefix_len)}
+        toks = self._run([enc], [prompt], max_tokens, prompt_embeds=embeds, sampling=sampling, prefix_len=prefix_len)[0]
         return {"answer": "".join(self._stream_text(toks))}
+
+    def _reasoning_result(self, tokens: Sequence[int], coords: Sequence[float]):
+        """Text + grounding of _generate_reasoning (moondream.py:363-432): a new chunk starts at every
+        start_ground_points / end_ground token; a chunk with >= 2 coordinates grounds its text span."""
+        tk = self.config.tokenizer
+        text_chunks: List[List[int]] = [[]]
+        ground_chunks: List[List[float]] = [[]]
+        for tok, c in zip(tokens, coords):
+            if tok == tk.start_ground_points_id or tok == tk.end_ground_id:
+                text_chunks.append([])
+                ground_chunks.append([])
+            text_chunks[-1].append(tok)
+            if tok == tk.coord_id:
+                ground_chunks[-1].append(float(c))
+        texts = [self.tokenizer.decode(ch) for ch in text_chunks]
+        grounding, start = [], 0
+        for txt, g in zip(texts, ground_chunks):
+            if len(g) > 1:
+                pts = [(g[i], g[i + 1]) for i in range(0, len(g) - (len(g) % 2), 2)]
+                grounding.append({"start_idx": start, "end_idx": start + len(txt), "points": pts})
+            start += len(txt)
+        return "".join(texts), grounding
+
+    def _stream_generate(self, enc: EncodedImage, prompt: Sequence[int], max_tokens: int, sampling: dict,
+                         prompt_embeds=None, prefix_len: int = -1, chunk: int = 8):
+        """The streaming generator of moondream.py:470-537: text chunks are yielded while the decode loop is still
+        running (every `chunk` graph replays), and closing the generator stops the loop and frees the pages."""
+        if "sampler" in sampling:                 # host restatement: decode first, then detokenise
+            yield from self._stream_text(self._run([enc], [prompt], max_tokens, prompt_embeds=prompt_embeds,
+                                                   sampling=sampling, prefix_len=prefix_len)[0])
+            return
+        eos = self.config.tokenizer.eos_id
+        dec = _StreamDecoder(self.tokenizer)
+        gen = self.engine.generate_stream([enc._prefix], [prompt], max_tokens, chunk=chunk, prompt_embeds=prompt_embeds,
+                                          prefix_len=prefix_len, **sampling)
+        try:
+            for part in gen:
+                for tok in part[0].tolist():
+                    if tok == eos:
+                        out = dec.flush()
+                        if out:
+                            yield out
+                        return
+                    out = dec.push(tok)
+                    if out:
+                        yield out
+            out = dec.flush()
+            if out:
+                yield out
+        finally:
+            gen.close()
 
     def _prompt_embeds_with_refs(self, prompt: List[int], spatial_refs: SpatialRefs) -> torch.Tensor:
         """Substitute region encodings for coord/size placeholder tokens (moondream.py:293-301,
@@ -359,6 +438,41 @@ class MoondreamModel:
     def detect_gaze(self, image, eye=None, face=None, unstable_settings: Dict[str, Any] = {}):
         raise NotImplementedError("detect_gaze (moondream.py:831-973) is out of the hot path's scope "
                                   "(SURVEY.md §8a lists detect/point; gaze is an application of point)")
+
+
+class _StreamDecoder:
+    """Token-at-a-time detokeniser with the reference's flush rules (moondream.py:476-510, 531-537): text is released
+    after a newline (cache reset), after a CJK character, or up to the last space."""
+
+    def __init__(self, tokenizer):
+        self.tokenizer = tokenizer
+        self.cache: List[int] = []
+        self.print_len = 0
+
+    def push(self, tok: int) -> str:
+        self.cache.append(tok)
+        text = self.tokenizer.decode(self.cache)
+        if text.endswith("\n"):
+            chunk = text[self.print_len:]
+            self.cache, self.print_len = [], 0
+            return chunk
+        if len(text) > 0 and _is_cjk_char(ord(text[-1])):
+            chunk = text[self.print_len:]
+            self.print_len += len(chunk)
+            return chunk
+        sp = text.rfind(" ", self.print_len)
+        if sp >= self.print_len:
+            chunk = text[self.print_len: sp + 1]
+            self.print_len += len(chunk)
+            return chunk
+        return ""
+
+    def flush(self) -> str:
+        if not self.cache:
+            return ""
+        chunk = self.tokenizer.decode(self.cache)[self.print_len:]
+        self.cache, self.print_len = [], 0
+        return chunk
 
 
 def _is_cjk_char(cp: int) -> bool:

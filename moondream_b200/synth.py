@@ -137,6 +137,20 @@ def peaked_lm_head(sd: Dict[str, torch.Tensor], peak: float, seed: int = 0) -> t
     return (sd["text.lm_head.weight"].float() + peak * tied).to(torch.bfloat16)
 
 
+def special_token_bias(sd: Dict[str, torch.Tensor], cfg: MoondreamConfig, answer: float, coord: float,
+                       ground: float) -> torch.Tensor:
+    """lm_head.bias with the control tokens of the grounded chain of thought lifted (answer_id, coord_id,
+    start_ground_points_id / end_ground_id): a random network never emits them on its own, and the reasoning tests need
+    sequences that interleave coordinates, close grounding spans and terminate (moondream.py:363-432)."""
+    tk = cfg.tokenizer
+    b = sd["text.lm_head.bias"].clone().float()
+    b[tk.answer_id] += answer
+    b[tk.coord_id] += coord
+    b[tk.start_ground_points_id] += ground
+    b[tk.end_ground_id] += ground
+    return b.to(torch.bfloat16)
+
+
 def tensor_hash(t: torch.Tensor) -> str:
     return hashlib.sha256(t.contiguous().view(torch.uint8).numpy().tobytes()).hexdigest()[:16]
 

@@ -319,12 +319,21 @@ class OracleModel:
                 x[ids == tk.size_id] = self.encode_size(torch.tensor(sizes, device=self.device, dtype=self.dtype))
         return x
 
-    def prefill_prompt(self, prompt: Sequence[int], pos: int, embeds: Optional[Tensor] = None):
-        """moondream.py:280-321 with temperature == 0: returns (logits, hidden, next_token, pos)."""
+    def causal_mask(self) -> Tensor:
+        """The mask query() builds for a text-only question (moondream.py:571-574): plain lower-triangular."""
+        if getattr(self, "_causal", None) is None:
+            n = self.cfg.text.max_context
+            self._causal = torch.tril(torch.ones(1, 1, n, n, dtype=torch.bool)).to(self.device)
+        return self._causal
+
+    def prefill_prompt(self, prompt: Sequence[int], pos: int, embeds: Optional[Tensor] = None, causal: bool = False):
+        """moondream.py:280-321 with temperature == 0: returns (logits, hidden, next_token, pos).
+        `causal`: use the text-only query's mask instead of the prefix-LM one (:305-308)."""
         with torch.no_grad():
             x = self.embed(torch.tensor([list(prompt)], device=self.device)) if embeds is None else embeds
             T = x.size(1)
-            hidden = self.text_decoder(x, self.attn_mask[:, :, pos:pos + T, :],
+            mask = self.causal_mask() if causal else self.attn_mask
+            hidden = self.text_decoder(x, mask[:, :, pos:pos + T, :],
                                        torch.arange(pos, pos + T, dtype=torch.long, device=self.device))
             logits = self.lm_head(hidden)
             nxt = torch.argmax(logits, dim=-1).unsqueeze(1)
@@ -368,9 +377,9 @@ class OracleModel:
         kept.scatter_(dim=-1, index=idx, src=srt)
         return int(torch.multinomial(kept, num_samples=1).item())
 
-    def generate(self, enc: Encoded, prompt: Sequence[int], max_tokens: int,
+    def generate(self, enc: Optional[Encoded], prompt: Sequence[int], max_tokens: int,
                  forced: Optional[Sequence[int]] = None, temperature: float = 0.0,
-                 top_p: float = 0.3, spatial_refs=None) -> Generation:
+                 top_p: float = 0.3, spatial_refs=None, pos: Optional[int] = None) -> Generation:
         """``_generate_answer`` (moondream.py:434-539) reduced to token ids (greedy unless temperature > 0,
         in which case `predicted` holds the sampled tokens and the margins still describe the argmax): prompt prefill,
         then one decoder step per emitted token; ``answer_id`` is masked from the 2nd token on
@@ -378,9 +387,19 @@ class OracleModel:
         last emitted token (its result is discarded); that trailing step is reproduced.
         `forced`: teacher forcing — feed these tokens instead of the argmax (records the argmax)."""
         tk = self.cfg.tokenizer
-        self.load_encoded(enc)
+        causal = False
+        if enc is None and pos is None:        # text-only query (moondream.py:565-574): fresh caches, position 0, causal mask
+            self.reset_cache()
+            start, causal = 0, True
+        elif enc is None:                      # continue in the current cache (the answer phase after reasoning)
+            start = pos
+            causal = getattr(self, "_text_only", False)
+        else:
+            self.load_encoded(enc)
+            start = enc.pos
+        self._text_only = causal
         embeds = self.spatial_prompt_embeds(prompt, spatial_refs) if spatial_refs else None
-        logits, hidden, nxt, pos = self.prefill_prompt(prompt, enc.pos, embeds)
+        logits, hidden, nxt, pos = self.prefill_prompt(prompt, start, embeds, causal=causal)
         out = Generation([], [], [], margin_ulps=[])
         n = 0
         pred = int(nxt.item()) if temperature == 0 else self.next_token(logits, temperature, top_p)
@@ -404,6 +423,54 @@ class OracleModel:
             ulps = self._margin_ulps(logits)
             n += 1
         out.last_hidden = hidden
+        return out
+
+    def generate_reasoning(self, enc: Optional[Encoded], prompt: Sequence[int], max_tokens: int,
+                           temperature: float = 0.0, top_p: float = 0.3, spatial_refs=None) -> dict:
+        """``_generate_reasoning`` (moondream.py:323-432) reduced to ids: the chain of thought ends at answer_id;
+        eos_id and size_id are masked from the 2nd token on (:395-396); a coord_id token is fed to the decoder as
+        encode_coordinate(argmax(decode_coordinate(last hidden)) / bins) (:381-391) and its value recorded.
+        Returns {"pos", "tokens", "coords" (one per token, None unless coord_id), "margin_ulps" (token decisions),
+        "coord_ulps" (coordinate decisions)}.  enc None = text-only (fresh caches, causal mask)."""
+        tk = self.cfg.tokenizer
+        causal = enc is None
+        if causal:
+            self.reset_cache()
+            start = 0
+        else:
+            self.load_encoded(enc)
+            start = enc.pos
+        self._text_only = causal
+        embeds = self.spatial_prompt_embeds(prompt, spatial_refs) if spatial_refs else None
+        logits, hidden, _, pos = self.prefill_prompt(prompt, start, embeds, causal=causal)
+        hidden = hidden[:, -1:, :]
+        nxt = self.next_token(logits, temperature, top_p)
+        ulps = self._margin_ulps(logits)
+        out = {"tokens": [], "coords": [], "margin_ulps": [], "coord_ulps": []}
+        n = 0
+        with torch.no_grad():
+            while nxt != tk.answer_id and n < max_tokens:
+                out["tokens"].append(nxt)
+                out["margin_ulps"].append(ulps)
+                if nxt == tk.coord_id:
+                    cl = self.decode_coordinate(hidden)
+                    coord = torch.argmax(cl, dim=-1) / cl.size(-1)
+                    out["coords"].append(float(coord.item()))
+                    out["coord_ulps"].append(self._margin_ulps(cl))
+                    emb = self.encode_coordinate(coord.to(dtype=cl.dtype)).unsqueeze(0)
+                else:
+                    out["coords"].append(None)
+                    out["coord_ulps"].append(None)
+                    emb = self.embed(torch.tensor([[nxt]], device=self.device))
+                logits, hidden = self.decode_one(emb, pos)
+                logits[:, tk.eos_id] = float("-inf")
+                logits[:, tk.size_id] = float("-inf")
+                pos += 1
+                nxt = self.next_token(logits, temperature, top_p)
+                ulps = self._margin_ulps(logits)
+                n += 1
+        out["pos"] = pos
+        out["end_margin_ulps"] = ulps          # the decision that ended the chain (or would have continued it)
         return out
 
     def generate_points(self, enc: Encoded, prompt: Sequence[int], include_size: bool,

@@ -44,7 +44,12 @@ class SeamOracle(OracleModel):
         return self.lm_head(hidden), hidden
 
     def compile(self, backend: str = "inductor"):
-        """moondream.py:194-204.  (`backend` other than inductor only to check graph capture on a box without a GPU.)"""
+        """moondream.py:194-204.  (`backend` other than inductor only to check graph capture on a box without a GPU.)
+        The reference's weights are nn.Parameters and its KV caches module buffers, i.e. static addresses for
+        Inductor's CUDA graphs; this port holds them in plain containers, so they are marked static explicitly —
+        otherwise "reduce-overhead" either skips the graphs (mutated cache inputs) or copies every weight per replay."""
+        for t in list(self.w.values()) + self.k_cache + self.v_cache + [self.rope, self.attn_mask]:
+            torch._dynamo.mark_static_address(t)
         self._vis_enc = torch.compile(self.vision_encoder, fullgraph=True, backend=backend)
         self._prefill = torch.compile(self.text_decoder, fullgraph=True, backend=backend)
         if backend == "inductor":

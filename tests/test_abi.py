@@ -31,15 +31,15 @@ def test_binding_table_matches_header():
 
     assert N.exported_symbols() == _header_functions()
     lib = N.lib()
-    assert lib.md_abi_version() == 1
+    assert lib.md_abi_version() == 2
     assert lib.md_linear_small_batch_splits(2048, 8192) >= 1
 
 
 def test_struct_layouts():
     from moondream_b200 import _native as N
 
-    assert ctypes.sizeof(N.md_dims) == 23 * 4
-    assert ctypes.sizeof(N.md_kv) == 32          # ptr, int(+pad), ptr, int, int
+    assert ctypes.sizeof(N.md_dims) == 24 * 4
+    assert ctypes.sizeof(N.md_kv) == 40          # ptr, int(+pad), ptr, int, int, int(+pad)
 
 
 def test_errors_are_reported_not_crashed():

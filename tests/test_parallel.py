@@ -66,3 +66,64 @@ def test_wider_worlds_with_ragged_and_empty_shards(world, n_items):
     """The 4- and 8-GPU runs use the same code as the 2-GPU one; cover a remainder (10 items on 4 ranks) and ranks
     that own nothing (2 items on 3 ranks) on CPU."""
     mp.spawn(_worker, args=(world, _free_port(), n_items, 3), nprocs=world, join=True)
+
+
+class _StubEngine:
+    """CPU stand-in with the methods ShardedEngine needs: a sequence's "tokens" encode which image and prompt it saw."""
+
+    def __init__(self):
+        from moondream_b200 import config as C
+
+        self.cfg = C.tiny()
+        self.device = torch.device("cpu")
+
+    def stage_images(self, images):
+        return images, None, None
+
+    def caption_from_crops(self, crops, offs, til, prompts, max_tokens, to_host=False, **kw):
+        rows = [[int(im[0, 0, 0]), int(im.shape[0]), len(p)] + [0] * (max_tokens - 2) for im, p in zip(crops, prompts)]
+        return type("R", (), {"tokens": torch.tensor(rows, dtype=torch.int32)})()
+
+    def encode_images(self, images):
+        return images
+
+    def generate_points(self, enc, prompts, include_size, max_objects):
+        return [[{"x_min": float(im[0, 0, 0]), "y_min": float(k), "x_max": 1.0, "y_max": 2.0} for k in range(int(im[0, 0, 0]) % 3)]
+                for im in enc]
+
+
+def _sharded_worker(rank, world, port):
+    import numpy as np
+
+    from moondream_b200.parallel import ShardedEngine
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        sizes = [(378, 378), (800, 600), (378, 378), (1200, 900), (500, 700), (300, 200), (378, 378)]
+        images = []
+        for i, (h, w) in enumerate(sizes):
+            im = np.zeros((h, w, 3), dtype=np.uint8)
+            im[0, 0, 0] = 10 + i
+            images.append(im)
+        prompts = [[1] * (i + 1) for i in range(len(images))]
+        se = ShardedEngine(_StubEngine())
+        parts = se.plan(images)
+        assert sorted(i for p in parts for i in p) == list(range(len(images)))
+        toks = se.caption_tokens(images, prompts, 4)
+        want = torch.tensor([[10 + i, h, i + 1, 0, 0] for i, (h, w) in enumerate(sizes)], dtype=torch.int32)
+        assert torch.equal(toks, want), (rank, toks, want)          # request order on every rank
+        vals, cnt = se.detect_boxes(images, prompts, 3)
+        assert cnt.tolist() == [(10 + i) % 3 for i in range(len(images))]
+        for i in range(len(images)):
+            for k in range(int(cnt[i])):
+                assert vals[i, k].tolist() == [10.0 + i, float(k), 1.0, 2.0]
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_engine_returns_request_order_on_every_rank(world):
+    """ShardedEngine (the N > 1 product path, also what bench.py drives): LPT plan by crop count, local generation,
+    one all-gather, rows back in request order — with ragged shards."""
+    mp.spawn(_sharded_worker, args=(world, _free_port()), nprocs=world, join=True)

@@ -35,6 +35,11 @@ def cpu_stat():
 
 def child():
     sys.path.insert(0, ROOT)
+    placement = "unpinned"
+    if os.environ.get("PROBE_PIN"):
+        import bench                       # pins to one NUMA node at import (bench.pin_to_numa_node)
+
+        placement = bench.CPU_PLACEMENT
     import torch
 
     from moondream_b200 import config as C, synth
@@ -44,6 +49,8 @@ def child():
     torch.set_num_threads(threads)
     cfg = C.preset("moondream-2b")
     sd = torch.load(CACHE, mmap=True)
+    if os.environ.get("PROBE_COPY"):       # private copies, first-touched by this process (like bench.py's own weights)
+        sd = {k: v.clone() for k, v in sd.items()}
     orc = OracleModel(cfg, sd)
     img = synth.synthetic_image(0, 378, 378)
     prompt = synth.synthetic_prompt(0, 32, cfg.text.vocab_size)
@@ -68,7 +75,8 @@ def child():
                     "throttled_ms": (s1.get("throttled_usec", 0) - s0.get("throttled_usec", 0)) / 1e3,
                     "cpu_s_used": (s1.get("usage_usec", 0) - s0.get("usage_usec", 0)) / 1e6,
                     "wall_s": round(t3 - t0, 2)})
-    print("PROBE " + json.dumps({"threads": threads, "torch_threads": torch.get_num_threads(), "runs": out}))
+    print("PROBE " + json.dumps({"threads": threads, "torch_threads": torch.get_num_threads(), "placement": placement,
+                                 "runs": out}))
 
 
 def main():
@@ -88,6 +96,10 @@ def main():
     if not os.path.exists(CACHE):
         torch.save(synth.synthetic_state_dict(C.preset("moondream-2b"), 0), CACHE)
     cases = [
+        ("private weights, pinned to one NUMA node", {"OMP_NUM_THREADS": str(n), "PROBE_PIN": "1", "PROBE_COPY": "1"}, n),
+        ("private weights, unpinned", {"OMP_NUM_THREADS": str(n), "PROBE_COPY": "1"}, n),
+        ("private weights, pinned (second process)", {"OMP_NUM_THREADS": str(n), "PROBE_PIN": "1", "PROBE_COPY": "1"}, n),
+        ("private weights, unpinned (second process)", {"OMP_NUM_THREADS": str(n), "PROBE_COPY": "1"}, n),
         ("omp=usable (round-1 reference arm)", {"OMP_NUM_THREADS": str(n), "MKL_NUM_THREADS": str(n)}, n),
         ("omp=usable, passive wait", {"OMP_NUM_THREADS": str(n), "OMP_WAIT_POLICY": "passive"}, n),
         ("omp=usable, GOMP_SPINCOUNT=0", {"OMP_NUM_THREADS": str(n), "GOMP_SPINCOUNT": "0"}, n),
@@ -97,9 +109,12 @@ def main():
         ("omp unset, set_num_threads(usable)", {}, n),
     ]
     results = []
+    if os.environ.get("PROBE_ONLY"):
+        cases = cases[: int(os.environ["PROBE_ONLY"])]
     for name, env, threads in cases:
         e = dict(os.environ)
-        for k in ("OMP_NUM_THREADS", "MKL_NUM_THREADS", "OMP_WAIT_POLICY", "GOMP_SPINCOUNT", "KMP_BLOCKTIME"):
+        for k in ("OMP_NUM_THREADS", "MKL_NUM_THREADS", "OMP_WAIT_POLICY", "GOMP_SPINCOUNT", "KMP_BLOCKTIME",
+                  "PROBE_PIN", "PROBE_COPY"):
             e.pop(k, None)
         e.update(env)
         e["PROBE_CHILD"] = "1"
