@@ -124,7 +124,8 @@ void md_debug_set_pdl(int enable);
  * bit0 [qkv;fc1] GEMM, bit1 its epilogue, bit2 attention, bit3 [proj|fc2] GEMM, bit4 residual+LN epilogue. */
 void md_debug_skip_decode_kernels(int mask);
 /* Timing experiments only, small-batch weight stream:
- * bit2 previous split plan of the [proj | fc2] stream (equal splits); bit6 forces M = 128 MMAs for batches <= 64
+ * bit2 previous split plan of the [proj | fc2] stream (equal splits); bit3 plans single-segment streams with the
+ * operand-read cost model (weight tiles up to 256 rows + K splits); bit6 forces M = 128 MMAs for batches <= 64
  * (the default there is M = 64).  Other bits are ignored. */
 void md_debug_gemm(int flags);
 /* Experiments only: cap the persistent row-form GEMM's grid at `sms` SMs (0 = all, the default), leaving the others

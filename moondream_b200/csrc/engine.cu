@@ -286,7 +286,7 @@ int text_decode_step(Model& m, bf16* x, const int* pos, int batch, const md_kv& 
     // [qkv ; fc1] share the input l = ln(x) (text.py:145-157): one weight stream, then bias / RoPE /
     // KV-page write / GELU, which the attention kernel applies for its own (sequence, head).  (Fusing them into
     // the GEMM epilogue needs whole-K tiles, i.e. 112 streaming SMs instead of 148: measured slower, DESIGN.md.)
-    int s1 = plan_smallbatch(QKV + FF, D, 0).splits;
+    int s1 = gemm_smallbatch_splits(QKV + FF, D);
     if (!(g_debug_skip & 1)) s1 = gemm_smallbatch(b.qkv.w, D, ln, D, QKV + FF, batch, D, 0, wsf, st);
     if (s1 < 0) return 1;
     if (KVH == H) {

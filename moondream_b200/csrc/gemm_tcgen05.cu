@@ -777,7 +777,41 @@ int gemm_rowform(const __nv_bfloat16* A, long long lda, const __nv_bfloat16* W, 
 // that (tiles x splits) fills whole waves of the SMs.  cost = waves x tile_rows x kb is the critical path in
 // units of 128-byte weight rows; ties prefer fewer splits (less partial-sum traffic).
 // kb_divisor > 0 restricts kb to divisors of it.
-StreamPlan plan_smallbatch(int n_out, int K, int kb_divisor) {
+// Operand-read model of the stream (md_debug_gemm bit 3): an SS-mode K = 16 MMA fetches its A
+// (activation lanes) and B (weight rows) operands from shared memory at ~32 B/clk, one after the other, so a 64-wide
+// k-block of a tile costs 4 * (m_rows + rows16) clocks and weights enter the tensor core at 32 * rows / (m_rows + rows)
+// B/clk per SM.  That explains the measured streams (97-row tiles with M = 128 lanes: 14 of 32 B/clk = 4 TB/s
+// chip-wide; 194 x 2 splits: 10.8 us mean) and says the stream turns HBM-bound (23 B/clk per SM) once
+// rows >= 2.6 * m_rows: tiles up to 256 rows, paid for with K splits.  cost in clocks.
+static StreamPlan plan_smallbatch_wide(int n_out, int K, int m_rows) {
+  const int k_blocks = (K + BK - 1) / BK;
+  const int sms = num_sms();
+  const double hbm_b_per_clk = 3400.0, sm_b_per_clk = 34.0;       // ~6.5 TB/s at ~1.9 GHz; per-SM streaming ceiling
+  StreamPlan best{BM, k_blocks, 1};
+  double best_cost = -1.0;
+  for (int splits = 1; splits <= 8 && splits <= k_blocks; ++splits) {
+    const int kb = (k_blocks + splits - 1) / splits;
+    if (kb * (splits - 1) >= k_blocks) continue;                  // a split would be empty
+    if (kb < 4 && k_blocks >= 4) break;
+    for (int rows = 256; rows >= 64; --rows) {
+      const int tiles = (n_out + rows - 1) / rows;
+      const long long ctas = 1LL * tiles * splits;
+      const long long waves = (ctas + sms - 1) / sms;
+      const int rows16 = (rows + 15) / 16 * 16;
+      const double t_op = 4.0 * kb * (m_rows + rows16);
+      const double t_sm = 128.0 * rows * kb / sm_b_per_clk;
+      const double t_hbm = 128.0 * n_out * k_blocks / hbm_b_per_clk;
+      double cost = waves * (t_op > t_sm ? t_op : t_sm);
+      if (cost < t_hbm) cost = t_hbm;
+      cost += 8.0 * splits * n_out * 32 / hbm_b_per_clk + 150.0 * splits;   // fp32 partials written + re-read (L2)
+      if (best_cost < 0 || cost < best_cost - 1e-9) { best_cost = cost; best = StreamPlan{rows, kb, splits}; }
+    }
+  }
+  return best;
+}
+
+StreamPlan plan_smallbatch(int n_out, int K, int kb_divisor, int m_rows) {
+  if ((g_gemm_debug & 8) && kb_divisor == 0) return plan_smallbatch_wide(n_out, K, m_rows);
   const int k_blocks = (K + BK - 1) / BK;
   const int sms = num_sms();
   StreamPlan best{BM, k_blocks, 1};
@@ -871,12 +905,23 @@ static int gemm_smallbatch_impl(const __nv_bfloat16* W, long long ldw, const __n
   return p.k_splits;
 }
 
-int gemm_smallbatch_splits(int n_out, int K) { return plan_smallbatch(n_out, K, 0).splits; }
+// upper bound over the plans a launch may pick (callers size their partial-sum workspace with it)
+int gemm_smallbatch_splits(int n_out, int K) {
+  int s = plan_smallbatch(n_out, K, 0, 128).splits;
+  const int saved = g_gemm_debug;
+  for (int m : {64, 128}) {
+    g_gemm_debug = saved | 8;
+    const int w = plan_smallbatch(n_out, K, 0, m).splits;
+    if (w > s) s = w;
+  }
+  g_gemm_debug = saved;
+  return s;
+}
 
 int gemm_smallbatch(const __nv_bfloat16* W, long long ldw, const __nv_bfloat16* X, long long ldx,
                  int n_out, int batch, int K, int splits, float* ws, cudaStream_t stream) {
   (void)splits;                                  // the plan decides (callers size ws with gemm_smallbatch_splits)
-  const StreamPlan pl = plan_smallbatch(n_out, K, 0);
+  const StreamPlan pl = plan_smallbatch(n_out, K, 0, (!(g_gemm_debug & 64) && batch <= 64) ? 64 : 128);
   return gemm_smallbatch_impl(W, ldw, X, ldx, n_out, batch, K, pl.kb, pl.tile_rows, ws, stream);
 }
 

@@ -77,7 +77,7 @@ void gemm_debug_sm_cap(int sms);
 void gemm_profile_enable(int on);
 int gemm_profile_read(double* total_ms, double* total_flops, long long* launches);
 struct StreamPlan { int tile_rows, kb, splits; };
-StreamPlan plan_smallbatch(int n_out, int K, int kb_divisor);
+StreamPlan plan_smallbatch(int n_out, int K, int kb_divisor, int m_rows = 128);
 int gemm_smallbatch_splits(int n_out, int K);
 int gemm_smallbatch(const __nv_bfloat16* W, long long ldw, const __nv_bfloat16* X, long long ldx,
                  int n_out, int batch, int K, int splits, float* ws, cudaStream_t stream);

@@ -27,7 +27,11 @@ done
 echo "== [4] CPU arm probe: pinned vs unpinned"
 PROBE_ONLY=4 timeout 500 python tools/cpu_arm_probe.py 2>&1 | tail -5 | cut -c1-420
 echo "== [5] decode timeline (default = M 64) and phase times"
-timeout 200 python tools/decode_timeline.py --brief --out $O/c2_decode_timeline.json 2>&1 | grep -E "Error|error|layer period|^gemm[12] |^attn |^epi "
+for f in 0 8 0 8; do
+  echo "-- gemm-debug $f (bit 3 = operand-read-model plan: wide weight tiles + K splits)"
+  timeout 200 python tools/decode_timeline.py --brief --gemm-debug $f --out $O/c2_decode_timeline_dbg$f.json 2>&1 | grep -E "Error|error|layer period|^gemm[12] |^attn |^epi "
+done
+MD_DEBUG_GEMM=8 timeout 200 python tools/phase_times.py 2>&1 | grep decode_ms
 timeout 200 python tools/phase_times.py 2>&1 | tail -9
 echo "== [6] compute-sanitizer memcheck on the new kernels (bounded)"
 timeout 420 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_features_gpu.py -q -m gpu \
