@@ -79,6 +79,20 @@ int md_linear_small_batch_bf16(const void* x, long long ldx, const void* w, long
                                int n_out, int K, int epilogue, const void* bias, const void* residual,
                                long long ldr, void* out, long long ldo, void* workspace, void* stream);
 
+/*
+ * Image preprocessing on the device: the resize of overlap_crop_image (image_crops.py:124-150, PIL branch) as the two
+ * passes of Pillow's 8-bit resampler (libImaging/Resample.c).  One call = one pass over a uint8 HWC image with 3
+ * channels: axis 1 resizes the width (in_w -> out_size), axis 0 the height.  bounds int32 [out_size][2] = (first
+ * source index, taps), coeffs int32 [out_size][ksize] = Pillow's 22-bit fixed-point Lanczos-3 weights
+ * (moondream_b200/resample.py computes them with Pillow's expressions); out = clamp((2^21 + sum src * coeff) >> 22).
+ * Bit-exact against PIL.Image.resize(..., LANCZOS).  md_extract_windows_u8 cuts the rows x cols overlapping
+ * crop x crop windows (stride = crop - 2 * margin pixels, image_crops.py:152-165) out of the resized canvas.
+ */
+int md_resample_u8(const uint8_t* src, int in_h, int in_w, int axis, const int* bounds, const int* coeffs, int ksize,
+                   int out_size, uint8_t* dst, void* stream);
+int md_extract_windows_u8(const uint8_t* canvas, int h, int w, int rows, int cols, int stride, int crop, uint8_t* crops,
+                          void* stream);
+
 /* y = LayerNorm(x) * w + b, eps 1e-5, fp32 statistics (layers.py:118-119). dim % 8 == 0, <= 4096. */
 int md_layernorm_bf16(const void* x, long long ldx, const void* w, const void* b, void* y,
                       long long ldy, int rows, int dim, void* stream);
@@ -215,6 +229,16 @@ long long md_text_prefill_workspace_bytes(const md_model* model, int total_token
 int md_text_prefill(md_model* model, void* x, int total_tokens, const int* q_offsets,
                     const int* start_pos, int n_seqs, int max_q, int prefix_len, const md_kv* kv,
                     void* workspace, void* stream);
+
+/* _prefill under a LoRA variant (settings["variant"], lora.py:55-79): text.py:31-32,54-56 and layers.py:131-143 add
+ * `B (A x)` to every Linear of a decoder block.  lora: HOST array of 8 * txt_layers device pointers, per block
+ * (A_qkv [r, D], B_qkv [3D, r], A_proj [r, D], B_proj [D, r], A_fc1 [r, D], B_fc1 [FF, r], A_fc2 [r, FF], B_fc2 [D, r]),
+ * bf16, row-major; rank r a multiple of 8.  Same arguments and cache behaviour as md_text_prefill otherwise; one row
+ * per sequence (q_offsets = 0, 1, 2, ...) makes it the decode step under a variant. */
+long long md_text_prefill_lora_workspace_bytes(const md_model* model, int total_tokens, int rank);
+int md_text_prefill_lora(md_model* model, void* x, int total_tokens, const int* q_offsets, const int* start_pos,
+                         int n_seqs, int max_q, int prefix_len, const md_kv* kv, const void* const* lora, int rank,
+                         void* workspace, void* stream);
 
 /* _decode_one_tok's decoder half (text.py:128-160 with T=1) for `batch` sequences:
  * x [batch, txt_dim] embeddings in, hidden out (in place); pos int32 [batch] (device).

@@ -47,6 +47,8 @@ _SIGNATURES = {
     "md_linear_small_batch_workspace_bytes": (_LL, [c_int, c_int, c_int]),
     "md_linear_small_batch_bf16": (c_int, [_P, _LL, _P, _LL, c_int, c_int, c_int, c_int, _P, _P, _LL, _P,
                                            _LL, _P, _P]),
+    "md_resample_u8": (c_int, [_P, c_int, c_int, c_int, _P, _P, c_int, c_int, _P, _P]),
+    "md_extract_windows_u8": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P]),
     "md_layernorm_bf16": (c_int, [_P, _LL, _P, _P, _P, _LL, c_int, c_int, _P]),
     "md_vit_attention_bf16": (c_int, [_P, c_int, c_int, c_int, _P, _P]),
     "md_rope_kv_write_bf16": (c_int, [_P, c_int, c_int, _P, _P, c_int, _P, _P, _KV, c_int, _P]),
@@ -69,6 +71,9 @@ _SIGNATURES = {
     "md_embed_tokens": (c_int, [_P, _P, _LL, c_int, _P, _LL, _P]),
     "md_text_prefill_workspace_bytes": (_LL, [_P, c_int]),
     "md_text_prefill": (c_int, [_P, _P, c_int, _P, _P, c_int, c_int, c_int, _KV, _P, _P]),
+    "md_text_prefill_lora_workspace_bytes": (_LL, [_P, c_int, c_int]),
+    "md_text_prefill_lora": (c_int, [_P, _P, c_int, _P, _P, c_int, c_int, c_int, _KV, ctypes.POINTER(c_void_p), c_int,
+                                     _P, _P]),
     "md_text_decode_workspace_bytes": (_LL, [_P, c_int]),
     "md_text_decode_step": (c_int, [_P, _P, _P, c_int, _KV, _P, _P, _P]),
     "md_lm_head_workspace_bytes": (_LL, [_P, c_int]),

@@ -75,6 +75,18 @@ int md_linear_small_batch_bf16(const void* x, long long ldx, const void* w, long
                              BF(bias), BF(residual), ldr, BFM(out), ldo, STREAM(stream));
 }
 
+int md_resample_u8(const uint8_t* src, int in_h, int in_w, int axis, const int* bounds, const int* coeffs, int ksize,
+                   int out_size, uint8_t* dst, void* stream) {
+  NEED(src && bounds && coeffs && dst, "md_resample_u8");
+  return md::resample_u8(src, in_h, in_w, axis, bounds, coeffs, ksize, out_size, dst, STREAM(stream));
+}
+
+int md_extract_windows_u8(const uint8_t* canvas, int h, int w, int rows, int cols, int stride, int crop, uint8_t* crops,
+                          void* stream) {
+  NEED(canvas && crops, "md_extract_windows_u8");
+  return md::extract_windows_u8(canvas, h, w, rows, cols, stride, crop, crops, STREAM(stream));
+}
+
 int md_layernorm_bf16(const void* x, long long ldx, const void* w, const void* b, void* y,
                       long long ldy, int rows, int dim, void* stream) {
   NEED(x && w && b && y, "md_layernorm_bf16");
@@ -187,6 +199,17 @@ int md_text_prefill(md_model* model, void* x, int total_tokens, const int* q_off
   NEED(model && x && q_offsets && start_pos && kv && kv->pool && kv->block_tables && workspace, "md_text_prefill");
   return md::text_prefill(*model, BFM(x), total_tokens, q_offsets, start_pos, n_seqs, max_q, prefix_len, *kv,
                           workspace, STREAM(stream));
+}
+
+long long md_text_prefill_lora_workspace_bytes(const md_model* model, int total_tokens, int rank) {
+  return model ? md::text_prefill_lora_ws_bytes(*model, total_tokens, rank) : -1;
+}
+int md_text_prefill_lora(md_model* model, void* x, int total_tokens, const int* q_offsets, const int* start_pos,
+                         int n_seqs, int max_q, int prefix_len, const md_kv* kv, const void* const* lora, int rank,
+                         void* workspace, void* stream) {
+  NEED(model && x && q_offsets && start_pos && kv && kv->pool && kv->block_tables && lora && workspace, "md_text_prefill_lora");
+  return md::text_prefill_lora(*model, BFM(x), total_tokens, q_offsets, start_pos, n_seqs, max_q, prefix_len, *kv, lora,
+                               rank, workspace, STREAM(stream));
 }
 
 long long md_text_decode_workspace_bytes(const md_model* model, int batch) {

@@ -696,6 +696,54 @@ decode_residual_ln_epilogue_kernel(const float* __restrict__ ws, int splits, int
 
 void timeline_install_elementwise(const Timeline& t) { timeline_install(t); }
 
+// ------------------------------------------------------------------------------------------------
+// Elementwise pieces of the LoRA path (the GEMM epilogues take ONE residual; a LoRA block needs two sums):
+//   gelu_rows:  y = bf16(gelu_tanh(x))                                  layers.py:137 after `x0 + x1`
+//   add3_rows:  y = bf16(bf16(x + a) + b)                               text.py:158 `x + l_attn + l_mlp`
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+gelu_rows_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, long long n8) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n8) return;
+  const uint4 v = reinterpret_cast<const uint4*>(x)[i];
+  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+  uint32_t o[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) o[j] = pack_bf16x2(gelu_tanh(bf16_lo(w[j])), gelu_tanh(bf16_hi(w[j])));
+  reinterpret_cast<uint4*>(y)[i] = make_uint4(o[0], o[1], o[2], o[3]);
+}
+
+__global__ void __launch_bounds__(256)
+add3_rows_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ a,
+                 const __nv_bfloat16* __restrict__ b, __nv_bfloat16* __restrict__ y, long long n8) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n8) return;
+  const uint4 xv = reinterpret_cast<const uint4*>(x)[i], av = reinterpret_cast<const uint4*>(a)[i],
+              bv = reinterpret_cast<const uint4*>(b)[i];
+  const uint32_t xw[4] = {xv.x, xv.y, xv.z, xv.w}, aw[4] = {av.x, av.y, av.z, av.w}, bw[4] = {bv.x, bv.y, bv.z, bv.w};
+  uint32_t o[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    o[j] = pack_bf16x2(bf16_round(bf16_lo(xw[j]) + bf16_lo(aw[j])) + bf16_lo(bw[j]),
+                       bf16_round(bf16_hi(xw[j]) + bf16_hi(aw[j])) + bf16_hi(bw[j]));
+  reinterpret_cast<uint4*>(y)[i] = make_uint4(o[0], o[1], o[2], o[3]);
+}
+
+int gelu_rows(const __nv_bfloat16* x, __nv_bfloat16* y, long long n, cudaStream_t stream) {
+  if (n <= 0 || n % 8) return set_error("gelu_rows: element count must be a positive multiple of 8");
+  gelu_rows_kernel<<<static_cast<unsigned>((n / 8 + 255) / 256), 256, 0, stream>>>(x, y, n / 8);
+  MD_CHECK_LAUNCH();
+  return 0;
+}
+
+int add3_rows(const __nv_bfloat16* x, const __nv_bfloat16* a, const __nv_bfloat16* b, __nv_bfloat16* y, long long n,
+              cudaStream_t stream) {
+  if (n <= 0 || n % 8) return set_error("add3_rows: element count must be a positive multiple of 8");
+  add3_rows_kernel<<<static_cast<unsigned>((n / 8 + 255) / 256), 256, 0, stream>>>(x, a, b, y, n / 8);
+  MD_CHECK_LAUNCH();
+  return 0;
+}
+
 int decode_residual_ln_epilogue(const float* ws, int splits, int proj_splits, int B, int D,
                                 const __nv_bfloat16* bias_proj, const __nv_bfloat16* bias_fc2,
                                 __nv_bfloat16* x, const __nv_bfloat16* ln_w, const __nv_bfloat16* ln_b,

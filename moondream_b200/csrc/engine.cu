@@ -227,6 +227,79 @@ int text_prefill(Model& m, bf16* x, int T, const int* q_offsets, const int* star
 }
 
 // ------------------------------------------------------------------------------------------------
+// text decoder with a LoRA variant (lora.py:55-79; text.py:31-32,54-56; layers.py:131-143): every Linear of a block
+// gets `+ B (A x)` with the reference's roundings — the adapter product is a bf16 tensor added to the bf16 Linear
+// output — and, as in the reference, the proj adapters are fed the block INPUT.  Composition of the existing
+// kernels: two skinny row-form GEMMs per adapter (rank r in K, then in N), the main GEMM with the adapter product as
+// its epilogue residual, RoPE + KV write as its own kernel (the fused QKV epilogue has no residual slot), and two
+// small elementwise kernels where a block needs a second sum.  The same entry point serves decode under a variant
+// (one row per sequence): variants are the rare path, the fused weight-stream step stays adapter-free.
+// ------------------------------------------------------------------------------------------------
+long long text_prefill_lora_ws_bytes(const Model& m, int T, int rank) {
+  const md_dims& d = m.d;
+  const long long wide = d.txt_ff > 3 * d.txt_dim ? d.txt_ff : 3 * d.txt_dim;
+  // ln | q | att | attn_out | mlp_out | t | u | qkv | pre | hid
+  return pad256(1LL * T * d.txt_dim * 2) * 5 + pad256(1LL * T * rank * 2) + pad256(1LL * T * wide * 2) +
+         pad256(1LL * T * 3 * d.txt_dim * 2) + pad256(1LL * T * d.txt_ff * 2) * 2 + 4096;
+}
+
+int text_prefill_lora(Model& m, bf16* x, int T, const int* q_offsets, const int* start_pos, int n_seqs, int max_q,
+                      int prefix_len, const md_kv& kv, const void* const* lora, int rank, void* ws, cudaStream_t st) {
+  const md_dims& d = m.d;
+  if (T <= 0 || n_seqs <= 0) return set_error("md_text_prefill_lora: empty batch");
+  if (rank <= 0 || rank % 8) return set_error("md_text_prefill_lora: the adapter rank must be a positive multiple of 8");
+  if (d.txt_kv_heads != d.txt_heads) return set_error("md_text_prefill_lora: grouped-query models are not supported with variants");
+  if (prefix_len < 0) prefix_len = d.prefix_len;
+  const int D = d.txt_dim, H = d.txt_heads, FF = d.txt_ff;
+  const long long wide = FF > 3 * D ? FF : 3 * D;
+  char* p = align_up(reinterpret_cast<char*>(ws));
+  bf16* ln = reinterpret_cast<bf16*>(p); p += pad256(1LL * T * D * 2);
+  bf16* q = reinterpret_cast<bf16*>(p); p += pad256(1LL * T * D * 2);
+  bf16* att = reinterpret_cast<bf16*>(p); p += pad256(1LL * T * D * 2);
+  bf16* attn_out = reinterpret_cast<bf16*>(p); p += pad256(1LL * T * D * 2);
+  bf16* mlp_out = reinterpret_cast<bf16*>(p); p += pad256(1LL * T * D * 2);
+  bf16* t = reinterpret_cast<bf16*>(p); p += pad256(1LL * T * rank * 2);
+  bf16* u = reinterpret_cast<bf16*>(p); p += pad256(1LL * T * wide * 2);
+  bf16* qkv = reinterpret_cast<bf16*>(p); p += pad256(1LL * T * 3 * D * 2);
+  bf16* pre = reinterpret_cast<bf16*>(p); p += pad256(1LL * T * FF * 2);
+  bf16* hid = reinterpret_cast<bf16*>(p);
+  bf16* pool = reinterpret_cast<bf16*>(kv.pool);
+  // u = bf16(B bf16(A in)):  in [T, K] -> t [T, rank] -> u [T, N]
+  auto adapter = [&](const bf16* in, int K, const void* A, const void* B, int N) -> int {
+    if (gemm_rowform(in, K, reinterpret_cast<const bf16*>(A), K, T, rank, K, EPI_BIAS, nullptr, nullptr, 0, 0, t, rank,
+                     0, 0, 0, st)) return 1;
+    return gemm_rowform(t, rank, reinterpret_cast<const bf16*>(B), rank, T, N, rank, EPI_BIAS, nullptr, nullptr, 0, 0, u, N,
+                        0, 0, 0, st);
+  };
+  for (int i = 0; i < d.txt_layers; ++i) {
+    const TxtBlock& b = m.txt[i];
+    const void* const* L = lora + 8 * i;            // A/B of qkv, proj, fc1, fc2
+    for (int j = 0; j < 8; ++j)
+      if (!L[j] || (reinterpret_cast<uintptr_t>(L[j]) & 15)) return set_error("md_text_prefill_lora: null or unaligned adapter tensor");
+    if (layernorm(x, D, b.ln.w, b.ln.b, ln, D, T, D, 1e-5f, st)) return 1;
+    // qkv = bf16(bf16(qkv(l) + bias) + u)                                  text.py:30-32
+    if (adapter(ln, D, L[0], L[1], 3 * D)) return 1;
+    if (gemm_rowform(ln, D, b.qkv.w, b.qkv.ld, T, 3 * D, D, EPI_BIAS_RESIDUAL, b.qkv.b, u, 3 * D, 0, qkv, 3 * D, 0, 0, 0, st)) return 1;
+    if (rope_kv_write(qkv, T, H, q_offsets, start_pos, n_seqs, m.rope, q, pool, kv.n_pages, kv.block_tables,
+                      kv.max_blocks, i, st)) return 1;
+    if (prefill_attention_tc(q, H, H, T, q_offsets, start_pos, n_seqs, max_q, prefix_len, pool, kv.n_pages, kv.n_layers,
+                             kv.block_tables, kv.max_blocks, i, att, st)) return 1;
+    // l_attn = bf16(bf16(proj(att) + bias) + bf16(B_p bf16(A_p l)))         text.py:53-56 (x there is the block input)
+    if (adapter(ln, D, L[2], L[3], D)) return 1;
+    if (gemm_rowform(att, D, b.proj.w, b.proj.ld, T, D, D, EPI_BIAS_RESIDUAL, b.proj.b, u, D, 0, attn_out, D, 0, 0, 0, st)) return 1;
+    // mlp: x0 + x1, gelu, x0 + x1                                            layers.py:130-143
+    if (adapter(ln, D, L[4], L[5], FF)) return 1;
+    if (gemm_rowform(ln, D, b.fc1.w, b.fc1.ld, T, FF, D, EPI_BIAS_RESIDUAL, b.fc1.b, u, FF, 0, pre, FF, 0, 0, 0, st)) return 1;
+    if (gelu_rows(pre, hid, 1LL * T * FF, st)) return 1;
+    if (adapter(hid, FF, L[6], L[7], D)) return 1;
+    if (gemm_rowform(hid, FF, b.fc2.w, b.fc2.ld, T, D, FF, EPI_BIAS_RESIDUAL, b.fc2.b, u, D, 0, mlp_out, D, 0, 0, 0, st)) return 1;
+    // x = bf16(bf16(x + l_attn) + l_mlp)                                     text.py:158
+    if (add3_rows(x, attn_out, mlp_out, x, 1LL * T * D, st)) return 1;
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
 // text decoder: one decode step for `batch` sequences (fused layout, 5 launches per block)
 // ------------------------------------------------------------------------------------------------
 static long long smallbatch_ws_floats(const Model& m, int batch) {

@@ -42,6 +42,9 @@ int vision_project_stitched(Model& m, const bf16* global_feats, const bf16* stit
 long long text_prefill_ws_bytes(const Model& m, int T);
 int text_prefill(Model& m, bf16* x, int T, const int* q_offsets, const int* start_pos, int n_seqs,
                  int max_q, int prefix_len, const md_kv& kv, void* ws, cudaStream_t st);
+long long text_prefill_lora_ws_bytes(const Model& m, int T, int rank);
+int text_prefill_lora(Model& m, bf16* x, int T, const int* q_offsets, const int* start_pos, int n_seqs, int max_q,
+                      int prefix_len, const md_kv& kv, const void* const* lora, int rank, void* ws, cudaStream_t st);
 extern int g_debug_skip;
 long long text_decode_ws_bytes(const Model& m, int batch);
 int text_decode_step(Model& m, bf16* x, const int* pos, int batch, const md_kv& kv, bf16* normed_out, void* ws,

@@ -113,6 +113,9 @@ int patchify(const uint8_t* crops, int n_crops, int crop, int patch, int k_pad,
 int stitch_pool_concat(const __nv_bfloat16* feats, const int* crop_offsets, const int* tilings,
                        int n_images, int grid, int margin, int dim, __nv_bfloat16* out,
                        cudaStream_t stream);
+int gelu_rows(const __nv_bfloat16* x, __nv_bfloat16* y, long long n, cudaStream_t stream);
+int add3_rows(const __nv_bfloat16* x, const __nv_bfloat16* a, const __nv_bfloat16* b, __nv_bfloat16* y, long long n,
+              cudaStream_t stream);
 int pool_concat(const __nv_bfloat16* global_feats, const __nv_bfloat16* stitched, int H, int W, int grid, int dim,
                 __nv_bfloat16* out, cudaStream_t stream);
 int embed_tokens(const int* ids, long long id_stride, int n, const __nv_bfloat16* wte, int dim,
@@ -164,6 +167,12 @@ int decode_qkv_finish(const float* ws, int splits, int B, int D, int n_kv_heads,
                       const float* freqs, const int* pos, __nv_bfloat16* q_out, __nv_bfloat16* kv_pool, int n_pages,
                       const int* block_tables, int max_blocks, int layer, __nv_bfloat16* hid, long long ld_hid,
                       cudaStream_t stream);
+
+// ---- preprocess.cu ----
+int resample_u8(const uint8_t* src, int in_h, int in_w, int axis, const int* bounds, const int* coeffs, int ksize,
+                int out_size, uint8_t* dst, cudaStream_t stream);
+int extract_windows_u8(const uint8_t* canvas, int h, int w, int rows, int cols, int stride, int crop, uint8_t* crops,
+                       cudaStream_t stream);
 
 // ---- sampling.cu ----
 int sample_top_p(const __nv_bfloat16* logits, int B, int V, float temperature, float top_p,

@@ -179,6 +179,38 @@ class GenerationResult:
     steps: int
 
 
+class LoraVariant:
+    """A LoRA variant on the device (the reference's `variant_state_dict` tree, lora.py:55-79): per decoder block the
+    (A, B) pairs of attn.qkv / attn.proj / mlp.fc1 / mlp.fc2, bf16, plus the host pointer table the C-ABI takes."""
+
+    ORDER = (("attn", "qkv"), ("attn", "proj"), ("mlp", "fc1"), ("mlp", "fc2"))
+
+    def __init__(self, cfg: MoondreamConfig, tree: dict, device):
+        t = cfg.text
+        blocks = tree["text"]["blocks"] if "text" in tree else tree["blocks"]
+        self.tensors: List[torch.Tensor] = []
+        ranks = set()
+        qkv_rows = t.dim + 2 * t.n_kv_heads * t.head_dim
+        want = {("attn", "qkv"): (t.dim, qkv_rows), ("attn", "proj"): (t.dim, t.dim),
+                ("mlp", "fc1"): (t.dim, t.ff_dim), ("mlp", "fc2"): (t.ff_dim, t.dim)}
+        for i in range(t.n_layers):
+            blk = blocks[str(i)]
+            for group, name in self.ORDER:
+                ab = blk[group][name]
+                a = ab["A"].to(device=device, dtype=torch.bfloat16).contiguous()
+                b = ab["B"].to(device=device, dtype=torch.bfloat16).contiguous()
+                fin, fout = want[(group, name)]
+                if a.dim() != 2 or b.dim() != 2 or a.shape[1] != fin or b.shape[0] != fout or b.shape[1] != a.shape[0]:
+                    raise ValueError(f"variant block {i} {group}.{name}: A {tuple(a.shape)} / B {tuple(b.shape)} do not fit "
+                                     f"a Linear {fin} -> {fout}")
+                ranks.add(int(a.shape[0]))
+                self.tensors += [a, b]
+        if len(ranks) != 1 or next(iter(ranks)) % 8:
+            raise ValueError(f"the adapters must share one rank that is a multiple of 8, got {sorted(ranks)}")
+        self.rank = next(iter(ranks))
+        self.table = (ctypes.c_void_p * len(self.tensors))(*[x.data_ptr() for x in self.tensors])
+
+
 class Engine:
     _MAX_DECODE_STATES = 4
 
@@ -229,6 +261,10 @@ class Engine:
         self._ws: Optional[torch.Tensor] = None
         self._decode_state: Dict[int, dict] = {}
         self._stage: Optional[torch.Tensor] = None
+        self._raw_stage: Optional[torch.Tensor] = None
+        self._stage_evt = None
+        self._coeffs: Dict[Tuple[int, int], tuple] = {}
+        self.preprocess = "device"          # stage_images: resize / crop on the GPU (bit-exact with PIL); "host" = PIL
         import concurrent.futures
         import os as _os
         n_cpu = len(_os.sched_getaffinity(0)) if hasattr(_os, "sched_getaffinity") else (_os.cpu_count() or 1)
@@ -304,9 +340,19 @@ class Engine:
                                          out.stride(0) if ldo is None else ldo, N.current_stream()),
                 "md_embed_tokens")
 
+    def load_lora(self, variant) -> "LoraVariant":
+        """dict tree (or the flat dotted-key state dict of a variant file) -> LoraVariant on this engine's device."""
+        if isinstance(variant, LoraVariant):
+            return variant
+        if variant and not any(isinstance(v, dict) for v in variant.values()):
+            from .synth import nest_lora
+
+            variant = nest_lora(variant)
+        return LoraVariant(self.cfg, variant, self.device)
+
     @_on_device
     def prefill(self, x: torch.Tensor, q_offsets: Sequence[int], start_pos: Sequence[int],
-                block_tables: torch.Tensor, prefix_len: int = -1):
+                block_tables: torch.Tensor, prefix_len: int = -1, lora: Optional["LoraVariant"] = None):
         """_prefill over a ragged batch, in place on x [total_tokens, dim].  prefix_len: -1 = the model's 730-token
         bidirectional image prefix (moondream.py:143-145), 0 = pure causal (text-only query, :565-574)."""
         T = x.shape[0]
@@ -314,8 +360,14 @@ class Engine:
         assert q_offsets[-1] == T and len(q_offsets) == n_seqs + 1
         max_q = max(q_offsets[i + 1] - q_offsets[i] for i in range(n_seqs))
         qo, sp = self._i32(list(q_offsets)), self._i32(list(start_pos))
-        ws = self._workspace(self.lib.md_text_prefill_workspace_bytes(self.model, T))
         kv = self._kv(block_tables)
+        if lora is not None:
+            ws = self._workspace(self.lib.md_text_prefill_lora_workspace_bytes(self.model, T, lora.rank))
+            N.check(self.lib.md_text_prefill_lora(self.model, N.ptr(x), T, N.ptr(qo), N.ptr(sp), n_seqs, max_q, prefix_len,
+                                                  ctypes.byref(kv), lora.table, lora.rank, N.ptr(ws), N.current_stream()),
+                    "md_text_prefill_lora")
+            return
+        ws = self._workspace(self.lib.md_text_prefill_workspace_bytes(self.model, T))
         N.check(self.lib.md_text_prefill(self.model, N.ptr(x), T, N.ptr(qo), N.ptr(sp), n_seqs, max_q, prefix_len,
                                          ctypes.byref(kv), N.ptr(ws), N.current_stream()), "md_text_prefill")
 
@@ -337,7 +389,8 @@ class Engine:
     # ------------------------------------------------------------------ image encoding
     @_on_device
     def encode_crops(self, crops_u8: torch.Tensor, crop_offsets: Sequence[int],
-                     tilings: Sequence[Tuple[int, int]], return_hidden: bool = False):
+                     tilings: Sequence[Tuple[int, int]], return_hidden: bool = False,
+                     lora: Optional["LoraVariant"] = None):
         """encode_image (moondream.py:230-268) for a batch whose crops are already on the device:
         ViT -> stitch/pool/project -> [BOS; image] prefill at positions 0..729 into fresh KV pages."""
         t = self.cfg.text
@@ -354,18 +407,19 @@ class Engine:
         for i, p in enumerate(prefixes):
             bt[i, : len(p.pages)] = torch.tensor(p.pages, dtype=torch.int32)
         bt = bt.to(self.device)
-        self.prefill(embeds, [i * t.prefix_attn for i in range(n_img + 1)], [0] * n_img, bt)
+        self.prefill(embeds, [i * t.prefix_attn for i in range(n_img + 1)], [0] * n_img, bt, lora=lora)
         if return_hidden:
             return prefixes, feats, img_emb, embeds
         return prefixes
 
     @_on_device
-    def encode_images(self, images: Sequence[np.ndarray], return_hidden: bool = False):
+    def encode_images(self, images: Sequence[np.ndarray], return_hidden: bool = False,
+                      lora: Optional["LoraVariant"] = None):
         """Host uint8 HxWx3 images -> crops (PIL Lanczos, image_crops.py:58-167) -> H2D -> encode_crops."""
         # crops are written straight into persistent pinned staging memory by a small thread pool
         # (PIL's resize and numpy's copies release the GIL)
         dev, offsets, tilings = self.stage_images(images)
-        return self.encode_crops(dev, offsets, tilings, return_hidden=return_hidden)
+        return self.encode_crops(dev, offsets, tilings, return_hidden=return_hidden, lora=lora)
 
     @_on_device
     def encode_crops_with_prompt(self, crops_u8: torch.Tensor, crop_offsets: Sequence[int],
@@ -414,9 +468,16 @@ class Engine:
                              **gen_kw)
 
     @_on_device
-    def stage_images(self, images: Sequence[np.ndarray]):
-        """host uint8 images -> crops in pinned staging memory -> device; returns (crops, offsets, tilings)"""
+    def stage_images(self, images: Sequence[np.ndarray], preprocess: Optional[str] = None):
+        """host uint8 images -> crops on the device; returns (crops, offsets, tilings).
+        preprocess "device" (default): images that need a real resize are uploaded raw and resized / cropped by the
+        CUDA kernels of csrc/preprocess.cu (bit-exact with PIL's Lanczos, tests/test_resample.py); images that already
+        have the crop geometry (378 x 378) are plain copies and take the host staging path.
+        preprocess "host": the reference's way for every image — PIL on host threads into pinned staging, then H2D."""
         v = self.cfg.vision
+        mode = preprocess or self.preprocess
+        if mode not in ("device", "host"):
+            raise ValueError("preprocess must be 'device' or 'host'")
         kw = dict(overlap_margin=v.overlap_margin, max_crops=v.max_crops,
                   base_size=(v.crop_size, v.crop_size), patch_size=v.enc_patch_size)
         tilings = [crop_tiling(im.shape, **kw) for im in images]
@@ -424,6 +485,18 @@ class Engine:
         for th, tw in tilings:
             offsets.append(offsets[-1] + th * tw + 1)
         n = offsets[-1]
+        window = v.crop_size - 2 * v.overlap_margin * v.enc_patch_size
+        margin2 = 2 * v.overlap_margin * v.enc_patch_size
+
+        def needs_resize(i):
+            th, tw = tilings[i]
+            h, w = images[i].shape[:2]
+            return (h, w) != (v.crop_size, v.crop_size) or (th * window + margin2, tw * window + margin2) != (h, w)
+
+        if self._stage_evt is not None:
+            self._stage_evt.synchronize()       # the previous call's async H2D copies have left the pinned buffers
+        on_device = [i for i in range(len(images)) if mode == "device" and needs_resize(i)]
+        on_host = [i for i in range(len(images)) if i not in set(on_device)]
         if self._stage is None or self._stage.shape[0] < n:
             self._stage = torch.empty((max(n, 64), v.crop_size, v.crop_size, 3), dtype=torch.uint8).pin_memory()
         stage_np = self._stage.numpy()
@@ -431,11 +504,81 @@ class Engine:
         def work(i):
             overlap_crop_image(images[i], out=stage_np[offsets[i]: offsets[i + 1]], **kw)
 
-        if len(images) > 1:
-            list(self._pool.map(work, range(len(images))))
-        else:
-            work(0)
-        return self._stage[:n].to(self.device, non_blocking=True), offsets, tilings
+        if len(on_host) > 1:
+            list(self._pool.map(work, on_host))
+        elif on_host:
+            work(on_host[0])
+        crops = self._stage[:n].to(self.device, non_blocking=True)
+        if on_device:
+            self._preprocess_on_device(images, on_device, tilings, offsets, crops)
+        self._stage_evt = torch.cuda.Event()
+        self._stage_evt.record()
+        return crops, offsets, tilings
+
+    def _coeff_tables(self, in_size: int, out_size: int):
+        """Pillow's fixed-point Lanczos tables for one (source, target) length on the device (cached)."""
+        from .resample import lanczos_coeffs
+
+        key = (in_size, out_size)
+        hit = self._coeffs.pop(key, None)
+        if hit is None:
+            bounds, kk = lanczos_coeffs(in_size, out_size)
+            hit = (torch.from_numpy(bounds).to(self.device), torch.from_numpy(kk).to(self.device), int(kk.shape[1]))
+            while len(self._coeffs) >= 64:
+                self._coeffs.pop(next(iter(self._coeffs)))
+        self._coeffs[key] = hit
+        return hit
+
+    def _resample(self, src: torch.Tensor, axis: int, out_size: int, dst: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """one pass of PIL's resize on a uint8 [H, W, 3] device image (axis 1 = width, 0 = height)"""
+        h, w = int(src.shape[0]), int(src.shape[1])
+        bounds, kk, ksize = self._coeff_tables(w if axis == 1 else h, out_size)
+        shape = (h, out_size, 3) if axis == 1 else (out_size, w, 3)
+        if dst is None:
+            dst = torch.empty(shape, dtype=torch.uint8, device=self.device)
+        N.check(self.lib.md_resample_u8(N.ptr(src), h, w, axis, N.ptr(bounds), N.ptr(kk), ksize, out_size, N.ptr(dst),
+                                        N.current_stream()), "md_resample_u8")
+        return dst
+
+    def resize_lanczos(self, image: torch.Tensor, out_h: int, out_w: int) -> torch.Tensor:
+        """PIL.Image.resize((out_w, out_h), LANCZOS) of a uint8 [H, W, 3] device image, bit for bit: horizontal pass
+        first, then vertical (libImaging/Resample.c ImagingResampleInner); a pass whose length does not change is
+        skipped, as in Pillow."""
+        cur = image.contiguous()
+        if int(cur.shape[1]) != out_w:
+            cur = self._resample(cur, 1, out_w)
+        if int(cur.shape[0]) != out_h:
+            cur = self._resample(cur, 0, out_h)
+        return cur
+
+    def _preprocess_on_device(self, images, which, tilings, offsets, crops: torch.Tensor):
+        """overlap_crop_image (image_crops.py:58-167) for images[which] on the device, written into `crops`."""
+        v = self.cfg.vision
+        S = v.crop_size
+        window = S - 2 * v.overlap_margin * v.enc_patch_size
+        margin2 = 2 * v.overlap_margin * v.enc_patch_size
+        total = sum(int(images[i].size) for i in which)
+        if self._raw_stage is None or self._raw_stage.numel() < total:
+            self._raw_stage = torch.empty(max(total, 1 << 22), dtype=torch.uint8).pin_memory()
+        raw_np = self._raw_stage.numpy()
+        at = 0
+        spans = []
+        for i in which:
+            im = np.ascontiguousarray(images[i])
+            raw_np[at: at + im.size] = im.reshape(-1)
+            spans.append((at, im.shape[0], im.shape[1]))
+            at += im.size
+        raw = self._raw_stage[:total].to(self.device, non_blocking=True)
+        for i, (lo, h, w) in zip(which, spans):
+            th, tw = tilings[i]
+            img = raw[lo: lo + h * w * 3].view(h, w, 3)
+            o = offsets[i]
+            g = self.resize_lanczos(img, S, S)                                   # global crop (image_crops.py:146-149)
+            crops[o].copy_(g)
+            canvas = self.resize_lanczos(img, th * window + margin2, tw * window + margin2)
+            N.check(self.lib.md_extract_windows_u8(N.ptr(canvas), int(canvas.shape[0]), int(canvas.shape[1]), th, tw,
+                                                   window, S, N.ptr(crops[o + 1]), N.current_stream()),
+                    "md_extract_windows_u8")
 
     @_on_device
     def prefix_kv_tensors(self, prefix: PrefixKV) -> List[Tuple[torch.Tensor, torch.Tensor]]:
@@ -604,7 +747,8 @@ class Engine:
             return DecodeMode(forced, float(temperature), float(top_p), True, tk.eos_id, tk.size_id, tk.answer_id)
         return DecodeMode(forced, float(temperature), float(top_p), False, tk.answer_id, -1, tk.eos_id)   # :517
 
-    def _prefill_phase(self, st: dict, prompts, start_pos: Sequence[int], prompt_embeds, prefix_len: int):
+    def _prefill_phase(self, st: dict, prompts, start_pos: Sequence[int], prompt_embeds, prefix_len: int,
+                       lora: Optional["LoraVariant"] = None):
         """_prefill_prompt (moondream.py:280-321) for the batch: ragged prompt prefill at `start_pos`, last rows ->
         st["x"].  Returns the prompt lengths."""
         t = self.cfg.text
@@ -619,7 +763,7 @@ class Engine:
             self.embed(flat, x)
         else:
             x = prompt_embeds
-        self.prefill(x, q_off, list(start_pos), st["bt"], prefix_len=prefix_len)
+        self.prefill(x, q_off, list(start_pos), st["bt"], prefix_len=prefix_len, lora=lora)
         last = self._i32([q_off[i + 1] - 1 for i in range(B)])
         N.check(self.lib.md_gather_rows_bf16(N.ptr(x), x.stride(0), N.ptr(last), B, t.dim, N.ptr(st["x"]),
                                              st["x"].stride(0), N.current_stream()), "md_gather_rows_bf16")
@@ -695,7 +839,7 @@ class Engine:
                  prefilled_hidden: Optional[torch.Tensor] = None,
                  sampler: Optional[Callable[[torch.Tensor], torch.Tensor]] = None,
                  temperature: float = 0.0, top_p: float = 1.0, seed: Optional[int] = None,
-                 prefix_len: int = -1) -> GenerationResult:
+                 prefix_len: int = -1, lora: Optional["LoraVariant"] = None) -> GenerationResult:
         """`_generate_answer` (moondream.py:434-539) for a batch: ragged prompt prefill, first
         token from the LM head, then `max_tokens` decode steps (the reference also runs the step after
         the last emitted token), all inside one CUDA graph per step with no per-token host sync.
@@ -720,8 +864,13 @@ class Engine:
             if prefilled_hidden is not None:
                 st["x"].copy_(prefilled_hidden)
             else:
-                self._prefill_phase(st, prompts, [p.pos for p in prefixes], prompt_embeds, prefix_len)
+                self._prefill_phase(st, prompts, [p.pos for p in prefixes], prompt_embeds, prefix_len, lora)
             pos0 = [prefixes[i].pos + lens[i] for i in range(B)]
+            if lora is not None:
+                if forced is not None or sampler is not None:
+                    raise ValueError("generate: `forced` / `sampler` are not combined with a LoRA variant")
+                return self._generate_lora(st, pos0, B, max_tokens, lora, temperature, top_p, seed, stop_on_eos, to_host,
+                                           prefix_len)
             if sampler is not None:
                 if forced is not None:
                     raise ValueError("generate: `forced` and `sampler` are mutually exclusive")
@@ -829,6 +978,48 @@ class Engine:
                 self.pages.release(pages)
         return [(out_r[b], out_c[b], out_a[b]) for b in range(B)]
 
+    def _generate_lora(self, st: dict, pos0: Sequence[int], B: int, max_tokens: int, lora: "LoraVariant",
+                       temperature: float, top_p: float, seed: Optional[int], stop_on_eos: bool, to_host: bool,
+                       prefix_len: int) -> GenerationResult:
+        """Decode loop under a LoRA variant (settings["variant"]): each step is md_text_prefill_lora over one row per
+        sequence (the fused weight-stream step has no adapter slots).  Eager launches, positions known on the host;
+        the token choice (argmax or on-device top-p sampling) and the bookkeeping are the usual kernels."""
+        tk = self.cfg.tokenizer
+        S, n_out = st["S"], max_tokens + 1
+        sampled = temperature > 0
+        st["step"].zero_()
+        st["finished"].zero_()
+        if sampled:
+            self._sampling_buffers(st, B)
+            st["seed"].fill_(int(torch.randint(0, 2 ** 62, (1,)).item()) if seed is None else seed)
+        self.lm_head(st["x"], st["preds"], S, mask_id=-1, out_index=None, margins=st["margins"],
+                     logits=st["logits"] if sampled else None)
+        if sampled:
+            self.sample_tokens(st["logits"], temperature, top_p, st["preds"], S, out_offset=0, step=None, seed=st["seed"],
+                               scratch=st["probs"])
+        st["cur"].copy_(st["preds"][:, 0])
+        st["pos"].copy_(self._i32(list(pos0)))
+        rows = list(range(B + 1))
+        steps = 0
+        for s in range(max_tokens):
+            self.embed(st["cur"], st["x"])
+            self.prefill(st["x"], rows, [p + s for p in pos0], st["bt"], prefix_len=prefix_len, lora=lora)
+            self.lm_head(st["x"], st["preds"], S, mask_id=tk.answer_id, out_index=st["step"], margins=st["margins"],
+                         logits=st["logits"] if sampled else None, out_offset=1)
+            if sampled:
+                self.sample_tokens(st["logits"], temperature, top_p, st["preds"], S, out_offset=1, step=st["step"],
+                                   seed=st["seed"], scratch=st["probs"])
+            N.check(self.lib.md_decode_advance(N.ptr(st["cur"]), N.ptr(st["pos"]), N.ptr(st["step"]), N.ptr(st["preds"]),
+                                               None, S, B, tk.eos_id, N.ptr(st["finished"]), N.current_stream()),
+                    "md_decode_advance")
+            steps += 1
+            if stop_on_eos and (s % 16 == 15) and bool(st["finished"].all().item()):
+                break
+        if to_host:
+            return GenerationResult(st["preds"][:, :n_out].to("cpu"), st["margins"][:, :n_out].to("cpu"), steps)
+        return GenerationResult(st["preds"][:, :n_out].clone(memory_format=torch.contiguous_format),
+                                st["margins"][:, :n_out].clone(memory_format=torch.contiguous_format), steps)
+
     def _generate_sampled(self, st: dict, pos0: Sequence[int], B: int, S: int,
                           max_tokens: int, sampler: Callable[[torch.Tensor], torch.Tensor], stop_on_eos: bool,
                           to_host: bool) -> GenerationResult:
@@ -904,7 +1095,7 @@ class Engine:
 
     @_on_device
     def generate_points(self, prefixes: Sequence[PrefixKV], prompts: Sequence[Sequence[int]],
-                        include_size: bool, max_objects: int) -> List[List[dict]]:
+                        include_size: bool, max_objects: int, lora: Optional["LoraVariant"] = None) -> List[List[dict]]:
         """detect / point (moondream.py:735-829 -> _generate_points :653-733) for a batch in lock-step:
         every sequence walks x -> y -> (size) -> next-token together; finished ones are masked on the
         host.  One host sync per object instead of the reference's ~5 .item() calls."""
@@ -922,7 +1113,7 @@ class Engine:
             flat = self._i32([tok for p in prompts for tok in p])
             x = torch.empty((q_off[-1], t.dim), dtype=torch.bfloat16, device=self.device)
             self.embed(flat, x)
-            self.prefill(x, q_off, [p.pos for p in prefixes], bt)
+            self.prefill(x, q_off, [p.pos for p in prefixes], bt, lora=lora)
             last = self._i32([q_off[i + 1] - 1 for i in range(B)])
             hidden = torch.empty((B, t.dim), dtype=torch.bfloat16, device=self.device)
             N.check(self.lib.md_gather_rows_bf16(N.ptr(x), x.stride(0), N.ptr(last), B, t.dim, N.ptr(hidden),
@@ -934,10 +1125,17 @@ class Engine:
                              device=self.device)
             kv = self._kv(bt)
 
+            host_pos = [prefixes[i].pos + lens[i] for i in range(B)]
+
             def step(emb):
-                N.check(self.lib.md_text_decode_step(self.model, N.ptr(emb), N.ptr(pos), B, ctypes.byref(kv),
-                                                     None, N.ptr(ws), N.current_stream()), "md_text_decode_step")
+                if lora is not None:       # a variant: the adapter-aware decoder over one row per sequence
+                    self.prefill(emb, list(range(B + 1)), list(host_pos), bt, lora=lora)
+                else:
+                    N.check(self.lib.md_text_decode_step(self.model, N.ptr(emb), N.ptr(pos), B, ctypes.byref(kv),
+                                                         None, N.ptr(ws), N.current_stream()), "md_text_decode_step")
                 pos.add_(1)
+                for b_ in range(B):
+                    host_pos[b_] += 1
                 return emb
 
             active = [True] * B

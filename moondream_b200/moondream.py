@@ -9,8 +9,8 @@ Python: crop geometry (PIL), tokenizer, prompt templates, result shaping, stream
 
 Deliberate differences from the reference (documented in DESIGN.md):
   * ``settings`` without "variant" is accepted by ``encode_image`` (the reference raises KeyError at
-    moondream.py:240-243); LoRA variants (lora.py) need the network and are rejected with
-    NotImplementedError when requested.
+    moondream.py:240-243); LoRA variants (lora.py) are read from the reference's local cache layout or a given
+    file — a variant that is not cached raises instead of being downloaded (this build never uses the network).
   * temperature > 0 (the reference's default 0.5 / top_p 0.3) follows the reference's softmax / top-p arithmetic
     (moondream.py:270-278, 312-318) ON THE DEVICE inside the decode graph (csrc/sampling.cu); the draw is an inverse
     CDF over the kept probabilities from a Philox stream seeded from torch's global RNG (the reference's
@@ -76,6 +76,7 @@ class MoondreamModel:
         self._tokenizer = tokenizer
         self._max_batch = max_batch
         self._kv_pages = kv_pages
+        self._variants: Dict[str, Any] = {}
         self._engine: Optional[Engine] = None
 
     # ------------------------------------------------------------------ plumbing
@@ -152,9 +153,6 @@ class MoondreamModel:
         sampling, or a HostSampler when settings["host_sampler"] asks for the torch-CPU restatement."""
         temperature = settings.get("temperature", DEFAULT_TEMPERATURE) if settings else DEFAULT_TEMPERATURE
         top_p = settings.get("top_p", DEFAULT_TOP_P) if settings else DEFAULT_TOP_P
-        if settings and settings.get("variant") is not None:
-            raise NotImplementedError("LoRA variants are downloaded from the network by the reference "
-                                      "(lora.py:23-40) and are not supported offline")
         max_tokens = settings.get("max_tokens", DEFAULT_MAX_TOKENS) if settings else DEFAULT_MAX_TOKENS
         if temperature < 0:
             raise ValueError("temperature must be >= 0")
@@ -169,31 +167,72 @@ class MoondreamModel:
                     sampling["seed"] = int(settings["seed"])
         return max_tokens, sampling
 
+    # ------------------------------------------------------------------ LoRA variants
+    def _lora(self, settings: Optional[dict]):
+        """settings["variant"] -> LoraVariant on the device (lora.py:55-79 `variant_state_dict`): a variant id is looked
+        up in the reference's cache layout ($HF_HUB_CACHE | $HF_HOME/hub | ~/.cache/huggingface/hub)/md_variants/<id>/
+        final.pt (lora.py:11-29); a path to such a file, a state dict or a loaded LoraVariant are accepted too.  The
+        reference downloads a missing variant from api.moondream.ai (lora.py:31-40); this build never touches the
+        network and raises instead."""
+        import os
+
+        from .engine import LoraVariant
+
+        v = settings.get("variant") if settings else None
+        if v is None:
+            return None
+        if isinstance(v, LoraVariant):
+            return v
+        if isinstance(v, dict):
+            return self.engine.load_lora(v)
+        key = str(v)
+        if key not in self._variants:
+            path = key
+            if not os.path.isfile(path):
+                hub = os.environ.get("HF_HUB_CACHE")
+                if hub is None:
+                    home = os.environ.get("HF_HOME")
+                    hub = os.path.join(home, "hub") if home is not None else os.path.expanduser("~/.cache/huggingface/hub")
+                path = os.path.join(hub, "md_variants", key, "final.pt")
+            if not os.path.isfile(path):
+                raise RuntimeError(f"variant {key!r} is not in the local cache ({path}); the reference would download it "
+                                   f"(lora.py:31-40), this build is offline")
+            flat = torch.load(path, map_location="cpu", weights_only=True)
+            renamed = {}
+            for k, t in flat.items():                      # lora.py:64-76
+                for old, new in (("text_model.transformer.h", "text.blocks"), (".mixer", ".attn"), (".out_proj", ".proj"),
+                                 (".Wqkv", ".qkv"), (".parametrizations.weight.0", "")):
+                    if old in k:
+                        k = k.replace(old, new)
+                renamed[k] = t
+            self._variants[key] = self.engine.load_lora(renamed)
+        return self._variants[key]
+
     # ------------------------------------------------------------------ image encoding
-    def encode_images(self, images: Sequence[Any]) -> List[EncodedImage]:
+    def encode_images(self, images: Sequence[Any], settings: Optional[dict] = None) -> List[EncodedImage]:
+        lora = self._lora(settings)
         todo = [(i, _as_array(im)) for i, im in enumerate(images) if not isinstance(im, EncodedImage)]
         out: List[Optional[EncodedImage]] = [im if isinstance(im, EncodedImage) else None for im in images]
         for lo in range(0, len(todo), self._max_batch):
             chunk = todo[lo: lo + self._max_batch]
-            prefixes = self.engine.encode_images([a for _, a in chunk])
+            prefixes = self.engine.encode_images([a for _, a in chunk], lora=lora)
             for (i, _), p in zip(chunk, prefixes):
                 out[i] = EncodedImage(p, self.engine)
         return out  # type: ignore[return-value]
 
     def encode_image(self, image, settings: Optional[dict] = None) -> EncodedImage:
+        """moondream.py:230-268; under settings["variant"] the image prefill runs with the adapters (:240-257)."""
         if isinstance(image, EncodedImage):
             return image
-        if settings and settings.get("variant") is not None:
-            raise NotImplementedError("LoRA variants are not supported offline")
-        return self.encode_images([image])[0]
+        return self.encode_images([image], settings)[0]
 
     # ------------------------------------------------------------------ text generation
     def _run(self, encoded: Sequence[EncodedImage], prompts: Sequence[Sequence[int]], max_tokens: int,
              eos_id: Optional[int] = None, prompt_embeds=None, sampling: Optional[dict] = None,
-             prefix_len: int = -1) -> List[List[int]]:
+             prefix_len: int = -1, lora=None) -> List[List[int]]:
         eos = self.config.tokenizer.eos_id if eos_id is None else eos_id
         res = self.engine.generate([e._prefix for e in encoded], prompts, max_tokens,
-                                   prompt_embeds=prompt_embeds, prefix_len=prefix_len, **(sampling or {}))
+                                   prompt_embeds=prompt_embeds, prefix_len=prefix_len, lora=lora, **(sampling or {}))
         toks = res.tokens.tolist()
         out = []
         for row in toks:
@@ -218,15 +257,16 @@ class MoondreamModel:
         return out
 
     def _run_images(self, images: Sequence[Any], prompts: Sequence[Sequence[int]], max_tokens: int,
-                    sampling: Optional[dict] = None) -> List[List[int]]:
+                    sampling: Optional[dict] = None, settings: Optional[dict] = None) -> List[List[int]]:
         """Batched generation straight from raw images: when no image is pre-encoded the image prefix and the
         prompt are prefilled in one decoder pass (engine.caption_from_crops); otherwise (and when sampling)
         the two-step path."""
-        if sampling or any(isinstance(im, EncodedImage) for im in images):
+        lora = self._lora(settings)
+        if sampling or lora is not None or any(isinstance(im, EncodedImage) for im in images):
             rows: List[List[int]] = []
             for lo in range(0, len(images), self._max_batch):
-                rows += self._run(self.encode_images(images[lo: lo + self._max_batch]),
-                                  prompts[lo: lo + self._max_batch], max_tokens, sampling=sampling)
+                rows += self._run(self.encode_images(images[lo: lo + self._max_batch], settings),
+                                  prompts[lo: lo + self._max_batch], max_tokens, sampling=sampling, lora=lora)
             return rows
         out: List[List[int]] = []
         for lo in range(0, len(images), self._max_batch):
@@ -255,7 +295,7 @@ class MoondreamModel:
         if length not in tpl:
             raise ValueError(f"Model does not support caption length '{length}'.")
         max_tokens, sampling = self._text_settings(settings)
-        toks = self._run_images(images, [tpl[length]] * len(images), max_tokens, sampling)
+        toks = self._run_images(images, [tpl[length]] * len(images), max_tokens, sampling, settings)
         return [{"caption": "".join(self._stream_text(t))} for t in toks]
 
     def caption(self, image, length: Literal["normal", "short", "long"] = "normal", stream: bool = False,
@@ -267,9 +307,12 @@ class MoondreamModel:
             raise ValueError(f"Model does not support caption length '{length}'.")
         max_tokens, sampling = self._text_settings(settings)
         enc = self.encode_image(image, settings)
-        if stream:
+        lora = self._lora(settings)
+        if stream and lora is None:
             return {"caption": self._stream_generate(enc, tpl[length], max_tokens, sampling)}
-        toks = self._run([enc], [tpl[length]], max_tokens, sampling=sampling)[0]
+        toks = self._run([enc], [tpl[length]], max_tokens, sampling=sampling, lora=lora)[0]
+        if stream:
+            return {"caption": self._stream_text(toks)}
         return {"caption": "".join(self._stream_text(toks))}
 
     def _query_prompt(self, question: str, spatial_refs: Optional[SpatialRefs], with_bos: bool,
@@ -293,7 +336,7 @@ class MoondreamModel:
             raise NotImplementedError("Model does not support querying.")
         max_tokens, sampling = self._text_settings(settings)
         prompts = [self._query_prompt(q, None, False) for q in questions]
-        toks = self._run_images(images, prompts, max_tokens, sampling)
+        toks = self._run_images(images, prompts, max_tokens, sampling, settings)
         return [{"answer": "".join(self._stream_text(t))} for t in toks]
 
     def query(self, image=None, question: str = None, reasoning: bool = False,
@@ -316,9 +359,13 @@ class MoondreamModel:
             prefix_len = 0
         prompt = self._query_prompt(question, spatial_refs, with_bos=image is None, reasoning=reasoning)
         embeds = self._prompt_embeds_with_refs(prompt, spatial_refs) if spatial_refs else None
+        lora = self._lora(settings)
         if reasoning:
             if "sampler" in sampling:
                 raise NotImplementedError("reasoning runs on the device; the host sampler is a parity-test path")
+            if lora is not None:
+                raise NotImplementedError("reasoning under a LoRA variant is not implemented (the variant path decodes "
+                                          "eagerly; the reasoning loop is a captured graph)")
             tk = self.config.tokenizer
             r_toks, coords, a_toks = self.engine.generate_reasoning(
                 [enc._prefix], [prompt], tk.templates["query"]["suffix"], max_tokens, prompt_embeds=embeds,
@@ -326,9 +373,12 @@ class MoondreamModel:
             text, grounding = self._reasoning_result(r_toks, coords)
             answer = self._stream_text(a_toks) if stream else "".join(self._stream_text(a_toks))
             return {"reasoning": {"text": text, "grounding": grounding}, "answer": answer}
-        if stream:
+        if stream and lora is None:
             return {"answer": self._stream_generate(enc, prompt, max_tokens, sampling, embeds, prefix_len)}
-        toks = self._run([enc], [prompt], max_tokens, prompt_embeds=embeds, sampling=sampling, prefix_len=prefix_len)[0]
+        toks = self._run([enc], [prompt], max_tokens, prompt_embeds=embeds, sampling=sampling, prefix_len=prefix_len,
+                         lora=lora)[0]
+        if stream:
+            return {"answer": self._stream_text(toks)}
         return {"answer": "".join(self._stream_text(toks))}
 
     def _reasoning_result(self, tokens: Sequence[int], coords: Sequence[float]):
@@ -414,26 +464,26 @@ class MoondreamModel:
         if self.config.tokenizer.templates["detect"] is None:
             raise NotImplementedError("Model does not support object detection.")
         max_objects = settings.get("max_objects", DEFAULT_MAX_OBJECTS) if settings else DEFAULT_MAX_OBJECTS
-        enc = self.encode_images(images)
+        enc = self.encode_images(images, settings)
         res = self.engine.generate_points([e._prefix for e in enc], self._object_prompts("detect", objects),
-                                          include_size=True, max_objects=max_objects)
+                                          include_size=True, max_objects=max_objects, lora=self._lora(settings))
         return [{"objects": [{k: o[k] for k in ("x_min", "y_min", "x_max", "y_max")} for o in r]} for r in res]
 
     def detect(self, image, object: str, settings: Optional[dict] = None):
-        return self.detect_batch([self.encode_image(image, None)], [object], settings)[0]
+        return self.detect_batch([self.encode_image(image, settings)], [object], settings)[0]
 
     def point_batch(self, images: Sequence[Any], objects: Sequence[str],
                     settings: Optional[dict] = None) -> List[Dict[str, list]]:
         if self.config.tokenizer.templates["point"] is None:
             raise NotImplementedError("Model does not support pointing.")
         max_objects = settings.get("max_objects", DEFAULT_MAX_OBJECTS) if settings else DEFAULT_MAX_OBJECTS
-        enc = self.encode_images(images)
+        enc = self.encode_images(images, settings)
         res = self.engine.generate_points([e._prefix for e in enc], self._object_prompts("point", objects),
-                                          include_size=False, max_objects=max_objects)
+                                          include_size=False, max_objects=max_objects, lora=self._lora(settings))
         return [{"points": [{"x": o["x"], "y": o["y"]} for o in r]} for r in res]
 
     def point(self, image, object: str, settings: Optional[dict] = None):
-        return self.point_batch([self.encode_image(image, None)], [object], settings)[0]
+        return self.point_batch([self.encode_image(image, settings)], [object], settings)[0]
 
     def detect_gaze(self, image, eye=None, face=None, unstable_settings: Dict[str, Any] = {}):
         raise NotImplementedError("detect_gaze (moondream.py:831-973) is out of the hot path's scope "

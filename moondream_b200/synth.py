@@ -151,6 +151,36 @@ def special_token_bias(sd: Dict[str, torch.Tensor], cfg: MoondreamConfig, answer
     return b.to(torch.bfloat16)
 
 
+def synthetic_lora(cfg: MoondreamConfig, rank: int = 8, seed: int = 0, gain: float = 0.5) -> Dict[str, torch.Tensor]:
+    """A seeded LoRA variant in the flat key layout the reference's `variant_state_dict` produces after its renames
+    (lora.py:64-79): text.blocks.{i}.attn.{qkv,proj}.{A,B} and text.blocks.{i}.mlp.{fc1,fc2}.{A,B}, A [rank, in],
+    B [out, rank], bf16.  `gain` scales B so that the adapters move the logits visibly."""
+    gen = torch.Generator(device="cpu").manual_seed(7_000_003 + seed)
+    t = cfg.text
+    qkv = int(t.dim * (1 + 2 * t.n_kv_heads / t.n_heads))
+    shapes = {"attn.qkv": (t.dim, qkv), "attn.proj": (t.dim, t.dim), "mlp.fc1": (t.dim, t.ff_dim), "mlp.fc2": (t.ff_dim, t.dim)}
+    out: Dict[str, torch.Tensor] = {}
+    for i in range(t.n_layers):
+        for name, (fin, fout) in shapes.items():
+            a = torch.empty((rank, fin), dtype=torch.float32).normal_(0.0, 1.0, generator=gen) / fin ** 0.5
+            b = torch.empty((fout, rank), dtype=torch.float32).normal_(0.0, 1.0, generator=gen) * (gain / rank ** 0.5)
+            out[f"text.blocks.{i}.{name}.A"] = a.to(torch.bfloat16)
+            out[f"text.blocks.{i}.{name}.B"] = b.to(torch.bfloat16)
+    return out
+
+
+def nest_lora(flat: Dict[str, torch.Tensor]) -> dict:
+    """lora.py:43-52 `nest`: flat dotted keys -> nested dicts."""
+    tree: dict = {}
+    for k, v in flat.items():
+        parts = k.split(".")
+        d = tree
+        for p_ in parts[:-1]:
+            d = d.setdefault(p_, {})
+        d[parts[-1]] = v
+    return tree
+
+
 def tensor_hash(t: torch.Tensor) -> str:
     return hashlib.sha256(t.contiguous().view(torch.uint8).numpy().tobytes()).hexdigest()[:16]
 

@@ -7,6 +7,7 @@
   tests/golden/tiny_text_only.json  query(image=None) (moondream.py:565-574): pure causal mask, BOS + prompt at 0
   tests/golden/tiny_gqa.json        grouped-query decoder (n_heads 4, n_kv_heads 2; text.py:36-38,49): tokens + KV probe
   tests/golden/top_p.json           _apply_top_p (moondream.py:270-278) on model logits: kept ids and probabilities
+  tests/golden/tiny_lora.json       settings["variant"]: a synthetic rank-8 LoRA through lora.py / text.py:31-56 / layers.py:131-143
 The oracle restatement is asserted equal to the reference on the way and contributes the margins.
 """
 from __future__ import annotations
@@ -145,6 +146,44 @@ def main():
         print("gqa", idx, tokens[:8])
     json.dump({"generator": "oracle/make_golden_r2.py (unmodified reference, config tiny-gqa: 4 query heads, 2 KV heads)",
                "cases": gcases}, open(os.path.join(OUT, "tiny_gqa.json"), "w"), indent=1)
+
+    # ---------------- LoRA variant (settings["variant"], lora.py) ----------------
+    import tempfile
+
+    flat = synth.synthetic_lora(cfg, rank=8, seed=0)
+    tmp = tempfile.mkdtemp()
+    os.environ["HF_HUB_CACHE"] = tmp
+    os.makedirs(os.path.join(tmp, "md_variants", "synthetic-r8"))
+    torch.save(flat, os.path.join(tmp, "md_variants", "synthetic-r8", "final.pt"))
+    ref = R.load_reference_model(cfg, sd)
+    orc = OracleModel(cfg, sd)
+    orc.lora = synth.nest_lora(flat)
+    lcases = []
+    for idx, h, w, plen, ntok in ((0, 378, 378, 6, 12), (1, 500, 700, 9, 12)):
+        img = synth.synthetic_image(idx, h, w)
+        prompt = synth.synthetic_prompt(idx, plen, cfg.text.vocab_size)
+        settings = {"temperature": 0, "max_tokens": ntok, "variant": "synthetic-r8"}
+        with torch.inference_mode():
+            enc = ref.encode_image(Image.fromarray(img), settings)
+        ref.load_encoded_image(enc)
+        tokens = R.tokens_from_text("".join(ref._generate_answer(torch.tensor([prompt]), enc.pos, settings)))
+        o_enc = orc.encode_image(img)
+        assert all(torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) for a, b in zip(enc.caches, o_enc.caches))
+        gen = orc.generate(o_enc, prompt, ntok)
+        assert gen.tokens == tokens, (gen.tokens, tokens)
+        det = ref.detect(enc, "17 23", settings={"max_objects": 2, "variant": "synthetic-r8"})["objects"]
+        dprompt = tk.templates["detect"]["prefix"] + [17, 23] + tk.templates["detect"]["suffix"]
+        o_det = orc.generate_points(o_enc, dprompt, True, 2)
+        assert [{k: o[k] for k in d} for o, d in zip(o_det, det)] == det and len(o_det) == len(det)
+        lcases.append({"image_index": idx, "height": h, "width": w, "prompt": prompt, "tokens": tokens,
+                       "margin_ulps": gen.margin_ulps, "detect_prompt": dprompt, "detect_boxes": det,
+                       "detect_bins": [o["bins"] for o in o_det], "detect_ulps": [o["ulps"] for o in o_det],
+                       "kv_abs_mean_first_last": [float(enc.caches[i][0].float().abs().mean()) for i in (0, cfg.text.n_layers - 1)]})
+        print("lora", idx, tokens[:8], det[:1])
+    orc.lora = None
+    json.dump({"generator": "oracle/make_golden_r2.py (unmodified reference with settings['variant'] = a synthetic rank-8 "
+                            "LoRA, synth.synthetic_lora(cfg, 8, 0), placed in the reference's variant cache layout)",
+               "rank": 8, "seed": 0, "cases": lcases}, open(os.path.join(OUT, "tiny_lora.json"), "w"), indent=1)
 
     # ---------------- _apply_top_p on model logits ----------------
     pcases = []

@@ -100,9 +100,21 @@ def _ln(x: Tensor, w: Dict[str, Tensor], prefix: str) -> Tensor:
     return F.layer_norm(x, b.shape, w[prefix + ".weight"], b)
 
 
-def _mlp(x: Tensor, w: Dict[str, Tensor], prefix: str) -> Tensor:
-    """layers.py:129-146 without LoRA: fc2(gelu_tanh(fc1 x))."""
-    return _lin(F.gelu(_lin(x, w, prefix + ".fc1"), approximate="tanh"), w, prefix + ".fc2")
+def _adapter(x: Tensor, ab: Dict[str, Tensor]) -> Tensor:
+    """the LoRA side path F.linear(F.linear(x, A), B) (text.py:31-32,54-56, layers.py:133,141)"""
+    return F.linear(F.linear(x, ab["A"]), ab["B"])
+
+
+def _mlp(x: Tensor, w: Dict[str, Tensor], prefix: str, lora: Optional[dict] = None) -> Tensor:
+    """layers.py:129-146: fc2(gelu_tanh(fc1 x)), each Linear optionally followed by `+ B(A x)` of a LoRA variant."""
+    h = _lin(x, w, prefix + ".fc1")
+    if lora is not None:
+        h = h + _adapter(x, lora["fc1"])
+    h = F.gelu(h, approximate="tanh")
+    y = _lin(h, w, prefix + ".fc2")
+    if lora is not None:
+        y = y + _adapter(h, lora["fc2"])
+    return y
 
 
 def rope_table(head_dim: int, max_context: int, theta: float = 10000.0) -> Tensor:
@@ -163,6 +175,7 @@ class OracleModel:
         prefix = 1 + (cfg.vision.crop_size // cfg.vision.enc_patch_size) ** 2
         mask[..., :prefix, :prefix] = 1
         self.attn_mask = mask.to(self.device)
+        self.lora: Optional[dict] = None       # a LoRA variant tree (lora.py:55-79 `variant_state_dict`), applied by text_decoder
         self.reset_cache()
 
     # ---- KV cache (moondream.py:62-78) ----
@@ -242,7 +255,10 @@ class OracleModel:
             pre = f"text.blocks.{i}"
             h = _ln(x, w, pre + ".ln")
             bsz, T, D = h.shape
+            lora = self.lora["text"]["blocks"][str(i)] if self.lora is not None else None
             qkv = _lin(h, w, pre + ".attn.qkv")
+            if lora is not None:
+                qkv = qkv + _adapter(h, lora["attn"]["qkv"])                       # text.py:31-32 (in place there)
             q, k, v = qkv.split([nh * hd, nkv * hd, nkv * hd], dim=-1)
             q = q.view(bsz, T, nh, hd).transpose(1, 2)
             k = k.view(bsz, T, nkv, hd).transpose(1, 2)
@@ -254,7 +270,10 @@ class OracleModel:
             a = F.scaled_dot_product_attention(q, self.k_cache[i], self.v_cache[i], attn_mask=mask,
                                                enable_gqa=nh != nkv)
             a = a.transpose(1, 2).reshape(bsz, T, D)
-            x = x + _lin(a, w, pre + ".attn.proj") + _mlp(h, w, pre + ".mlp")
+            l_attn = _lin(a, w, pre + ".attn.proj")
+            if lora is not None:
+                l_attn = l_attn + _adapter(h, lora["attn"]["proj"])                # text.py:53-56: fed the block INPUT
+            x = x + l_attn + _mlp(h, w, pre + ".mlp", lora["mlp"] if lora is not None else None)
         return x
 
     def lm_head(self, hidden: Tensor) -> Tensor:

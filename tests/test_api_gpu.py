@@ -94,8 +94,8 @@ def test_error_behaviour_matches_the_reference(api):
         model.caption(img, "poetic", settings={"temperature": 0})  # :634-635
     with pytest.raises(ValueError):
         model.caption(img, "short", settings={"temperature": -1.0})
-    with pytest.raises(NotImplementedError):
-        model.caption(img, "short", settings={"temperature": 0, "variant": "foo"})
+    with pytest.raises(RuntimeError):                                # a variant that is not cached is never downloaded
+        model.caption(img, "short", settings={"temperature": 0, "variant": "no-such-variant"})
 
 
 def test_spatial_refs_query_runs(api):

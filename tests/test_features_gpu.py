@@ -419,3 +419,87 @@ def test_seam_adapter_drives_the_reference_flow(tiny):
     seam.release()
     del eng
     torch.cuda.empty_cache()
+
+
+# ------------------------------------------------------------------------------------------------ preprocessing
+def test_device_preprocessing_is_bit_exact_with_pil(tiny):
+    """overlap_crop_image on the device (resize with Pillow's fixed-point Lanczos tables + window extraction) against
+    the host path (PIL itself) and the crop hashes the REFERENCE produced (tests/golden/crops.json)."""
+    import hashlib
+
+    from moondream_b200 import synth
+    from moondream_b200.engine import Engine
+    from moondream_b200.image_crops import overlap_crop_image
+
+    cfg, sd = tiny
+    eng = Engine(cfg, sd, max_batch=4)
+    gold = _gold("crops.json")["cases"]
+    imgs = [synth.synthetic_image(c["image_index"], c["height"], c["width"]) for c in gold]
+    for lo in range(0, len(imgs), 4):
+        batch = imgs[lo: lo + 4]
+        crops, offs, til = eng.stage_images(batch, preprocess="device")
+        host, offs_h, til_h = eng.stage_images(batch, preprocess="host")
+        assert offs == offs_h and til == til_h
+        crops, host = crops.cpu().numpy().copy(), host.cpu().numpy()
+        assert np.array_equal(crops, host)
+        for j, c in enumerate(gold[lo: lo + 4]):
+            mine = crops[offs[j]: offs[j + 1]]
+            assert list(til[j]) == c["tiling"] and mine.shape[0] == c["n_crops"]
+            assert hashlib.sha256(mine.tobytes()).hexdigest()[:16] == c["sha256"], (c["height"], c["width"])
+    # single resize entry point against PIL
+    from PIL import Image
+    img = synth.synthetic_image(77, 480, 640)
+    got = eng.resize_lanczos(torch.from_numpy(img).cuda(), 378, 378).cpu().numpy()
+    want = np.asarray(Image.fromarray(img).resize((378, 378), resample=Image.Resampling.LANCZOS))
+    assert np.array_equal(got, want)
+    del eng
+    torch.cuda.empty_cache()
+
+
+# ------------------------------------------------------------------------------------------------ LoRA variants
+def test_lora_variant_matches_the_reference_golden(tiny, tmp_path, monkeypatch):
+    """settings["variant"] (lora.py:55-79; text.py:31-32,54-56; layers.py:131-143): a synthetic rank-8 variant placed in
+    the reference's cache layout, through the public API, against the tokens / boxes the UNMODIFIED reference produced
+    with the same file (tests/golden/tiny_lora.json) and the oracle's KV prefix."""
+    from moondream_b200 import synth
+    from oracle.moondream_oracle import OracleModel
+
+    cfg, sd = tiny
+    gold = _gold("tiny_lora.json")
+    flat = synth.synthetic_lora(cfg, gold["rank"], gold["seed"])
+    vdir = tmp_path / "md_variants" / "synthetic-r8"
+    vdir.mkdir(parents=True)
+    torch.save(flat, vdir / "final.pt")
+    monkeypatch.setenv("HF_HUB_CACHE", str(tmp_path))
+    model = _model(cfg, sd)
+    orc = OracleModel(cfg, sd)
+    orc.lora = synth.nest_lora(flat)
+    settings = {"temperature": 0, "max_tokens": 12, "variant": "synthetic-r8"}
+    base = {"temperature": 0, "max_tokens": 12}
+    differs = 0
+    for c in gold["cases"]:
+        img = synth.synthetic_image(c["image_index"], c["height"], c["width"])
+        enc = model.encode_image(img, settings)
+        o_enc = orc.encode_image(img)
+        for (k, v), (ok, ov) in zip(enc.caches, o_enc.caches):
+            assert ((k.float().cpu() - ok.float()).norm() / ok.float().norm()).item() < 3e-2
+            assert ((v.float().cpu() - ov.float()).norm() / ov.float().norm()).item() < 3e-2
+        res = model.engine.generate([enc._prefix], [c["prompt"]], 12, lora=model._lora(settings))
+        _agree(res.tokens[0, :12].tolist(), c["tokens"], c["margin_ulps"], "lora tokens")
+        plain = model.engine.generate([model.encode_image(img)._prefix], [c["prompt"]], 12)
+        differs += int(plain.tokens[0, :12].tolist() != res.tokens[0, :12].tolist())
+        det = model.detect(enc, "17 23", settings={"max_objects": 2, "variant": "synthetic-r8"})["objects"]
+        near = any(u < NEAR_TIE_ULPS for o in c["detect_ulps"] for u in o)
+        if not near:
+            assert len(det) == len(c["detect_boxes"])
+            for got, want in zip(det, c["detect_boxes"]):
+                for key in ("x_min", "y_min", "x_max", "y_max"):
+                    assert abs(got[key] - want[key]) < 1e-5
+    assert differs == len(gold["cases"]), "the adapters must change the output"
+    # API level: caption under the variant, sampling under the variant, unknown variants are not downloaded
+    out = model.caption(synth.synthetic_image(0, 378, 378), "short", settings=settings)
+    assert isinstance(out["caption"], str) and out["caption"] != model.caption(synth.synthetic_image(0, 378, 378), "short", settings=base)["caption"]
+    out = model.query(synth.synthetic_image(0, 378, 378), "11 12", settings={"temperature": 0.7, "max_tokens": 6, "variant": "synthetic-r8"})
+    assert len(_ids(out["answer"])) <= 6
+    with pytest.raises(RuntimeError):
+        model.caption(synth.synthetic_image(0, 378, 378), "short", settings={"temperature": 0, "variant": "missing"})

@@ -75,6 +75,24 @@ def test_gqa_decoder_matches_the_reference():
         assert orc.generate(enc, c["prompt"], len(c["tokens"])).tokens == c["tokens"]
 
 
+def test_lora_variant_matches_the_reference(tiny):
+    from moondream_b200 import synth
+    from oracle.moondream_oracle import OracleModel
+
+    cfg, sd = tiny
+    gold = _gold("tiny_lora.json")
+    orc = OracleModel(cfg, sd)
+    orc.lora = synth.nest_lora(synth.synthetic_lora(cfg, gold["rank"], gold["seed"]))
+    for c in gold["cases"]:
+        enc = orc.encode_image(synth.synthetic_image(c["image_index"], c["height"], c["width"]))
+        assert orc.generate(enc, c["prompt"], len(c["tokens"])).tokens == c["tokens"]
+        det = orc.generate_points(enc, c["detect_prompt"], True, 2)
+        assert [o["bins"] for o in det] == c["detect_bins"]
+    orc.lora = None
+    enc = orc.encode_image(synth.synthetic_image(0, 378, 378))
+    assert orc.generate(enc, gold["cases"][0]["prompt"], 12).tokens != gold["cases"][0]["tokens"]   # the adapters matter
+
+
 def test_apply_top_p_matches_the_reference():
     from moondream_b200.sampling import apply_top_p
 
@@ -96,7 +114,7 @@ def test_round2_restatements_are_bit_identical_to_the_reference_here():
     import oracle.make_golden_r2 as G
 
     before = {n: open(os.path.join(HERE, "golden", n)).read() for n in
-              ("tiny_reasoning.json", "tiny_text_only.json", "tiny_gqa.json", "top_p.json")}
+              ("tiny_reasoning.json", "tiny_text_only.json", "tiny_gqa.json", "top_p.json", "tiny_lora.json")}
     G.main()                                  # asserts oracle == reference on every case while writing
     for n, txt in before.items():
         assert open(os.path.join(HERE, "golden", n)).read() == txt, f"{n} is stale: commit the regenerated fixture"
