@@ -130,7 +130,8 @@ int md_rope_kv_write_bf16(const void* qkv, int n_tokens, int n_heads, const int*
 int md_prefill_attention_bf16(const void* q, int n_heads, int total_tokens, const int* q_offsets,
                               const int* start_pos, int n_seqs, int max_q, int prefix_len,
                               const md_kv* kv, int layer, void* out, void* stream);
-/* Testing / A-B timing only: 0 = tcgen05 attention (default), 1 = the legacy mma.sync kernel. */
+/* Testing / A-B timing only: 0 = tcgen05 attention (default), 1 = the legacy mma.sync kernel, 2 = tcgen05 attention with
+ * 3 of every 8 exponentials of the softmax evaluated on the FMA pipe (cubic) instead of MUFU.EX2. */
 void md_debug_attention_impl(int impl);
 /* Testing / A-B timing only: programmatic dependent launch between consecutive kernels (default on). */
 void md_debug_set_pdl(int enable);
@@ -138,8 +139,8 @@ void md_debug_set_pdl(int enable);
  * bit0 [qkv;fc1] GEMM, bit1 its epilogue, bit2 attention, bit3 [proj|fc2] GEMM, bit4 residual+LN epilogue. */
 void md_debug_skip_decode_kernels(int mask);
 /* Timing experiments only, small-batch weight stream:
- * bit2 previous split plan of the [proj | fc2] stream (equal splits); bit3 plans single-segment streams with the
- * operand-read cost model (weight tiles up to 256 rows + K splits); bit6 forces M = 128 MMAs for batches <= 64
+ * bit2 previous split plan of the [proj | fc2] stream (equal splits); bit3 previous plan of the single-segment streams
+ * (tiles <= 128 rows; the default is the operand-read cost model: tiles up to 256 rows + K splits); bit6 forces M = 128 MMAs for batches <= 64
  * (the default there is M = 64).  Other bits are ignored. */
 void md_debug_gemm(int flags);
 /* Experiments only: cap the persistent row-form GEMM's grid at `sms` SMs (0 = all, the default), leaving the others

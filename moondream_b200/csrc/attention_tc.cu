@@ -65,8 +65,30 @@ __device__ __forceinline__ float chunk_max(const uint32_t (&v)[32], bool full, i
   return fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
 }
 
+// 2^x for x <= 0 on the FMA pipe (no MUFU): x = n + f with n = round(x) taken from the low mantissa bits of
+// x + 1.5 * 2^23 and f in [-0.5, 0.5]; 2^f by a minimax cubic (relative error <= 7.5e-5, a fiftieth of a bf16 ulp:
+// the result is rounded to bf16 right after); 2^n by adding n to the exponent field.
+// The softmax of these kernels is bound by the 16 MUFU results per clock an SM produces: a
+// 128 x 128 score tile needs 16384 exponentials = 1024 clocks against 512 clocks of tensor work, so 3 of every 8
+// pairs are computed here instead, which evens out the MUFU and issue budgets.
+__device__ __forceinline__ float2 exp2_fma2(float2 x) {
+  const float kMagic = 12582912.f;                       // 1.5 * 2^23
+  x.x = fmaxf(x.x, -125.f);
+  x.y = fmaxf(x.y, -125.f);
+  const float2 t = fadd2(x, make_float2(kMagic, kMagic));
+  const float2 n = fadd2(t, make_float2(-kMagic, -kMagic));
+  const float2 f = ffma2(n, make_float2(-1.f, -1.f), x);
+  float2 q = ffma2(f, make_float2(0.05517146f, 0.05517146f), make_float2(0.24261086f, 0.24261086f));
+  q = ffma2(q, f, make_float2(0.69326099f, 0.69326099f));
+  q = ffma2(q, f, make_float2(0.99992809f, 0.99992809f));
+  return make_float2(__int_as_float(__float_as_int(q.x) + (__float_as_int(t.x) << 23)),
+                     __int_as_float(__float_as_int(q.y) + (__float_as_int(t.y) << 23)));
+}
+
 // exp2(s * scale - base) for one 32-score chunk -> bf16 -> four swizzled 16-byte chunks of the row's
-// 128-byte line (chunk slots chunk0 .. chunk0+3); returns the row-sum contribution
+// 128-byte line (chunk slots chunk0 .. chunk0+3); returns the row-sum contribution.
+// POLY: pairs 1, 2, 5 of every 8 go through exp2_fma2 instead of MUFU.EX2.
+template <bool POLY>
 __device__ __forceinline__ float chunk_probs(const uint32_t (&v)[32], bool full, int k_first, int kv_len, int qpos,
                                              int prefix_len, float scale_log2, float base, uint8_t* line,
                                              int chunk0, int r) {
@@ -79,8 +101,9 @@ __device__ __forceinline__ float chunk_probs(const uint32_t (&v)[32], bool full,
     for (int i = 0; i < 16; i += 2) {
       const float2 x0 = ffma2(make_float2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1])), sc, nb);
       const float2 x1 = ffma2(make_float2(__uint_as_float(v[2 * i + 2]), __uint_as_float(v[2 * i + 3])), sc, nb);
-      const float2 e0 = make_float2(ex2_approx(x0.x), ex2_approx(x0.y));
-      const float2 e1 = make_float2(ex2_approx(x1.x), ex2_approx(x1.y));
+      // i is a compile-time constant after unrolling: pairs i = 2, 10 and i + 1 = 1, 5, 9, 13 take the FMA-pipe path
+      const float2 e0 = (POLY && (i & 7) == 2) ? exp2_fma2(x0) : make_float2(ex2_approx(x0.x), ex2_approx(x0.y));
+      const float2 e1 = (POLY && (i & 3) == 0) ? exp2_fma2(x1) : make_float2(ex2_approx(x1.x), ex2_approx(x1.y));
       s01 = fadd2(s01, e0);
       s23 = fadd2(s23, e1);
       pk[i] = pack_bf16x2(e0.x, e0.y);
@@ -118,6 +141,7 @@ struct FaTcParams {
   float scale_log2;
 };
 
+template <bool POLY>
 __global__ void __launch_bounds__(fa::kThreads, 2)
 fa_tc_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
                      const FaTcParams p) {
@@ -304,12 +328,12 @@ fa_tc_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         for (int cc = 0; cc < 2; ++cc) {
           tmem_ld_wait();
           tmem_ld_32x32(tS + (2 * cc + 1) * 32, vb);
-          l_run += chunk_probs(va, full, k0 + (2 * cc) * 32, kv_len, qpos, p.prefix_len, p.scale_log2, base,
-                               prow + cc * (BM * 128), 0, r);
+          l_run += chunk_probs<POLY>(va, full, k0 + (2 * cc) * 32, kv_len, qpos, p.prefix_len, p.scale_log2, base,
+                                     prow + cc * (BM * 128), 0, r);
           tmem_ld_wait();
           if (cc == 0) tmem_ld_32x32(tS + 64, va);
-          l_run += chunk_probs(vb, full, k0 + (2 * cc + 1) * 32, kv_len, qpos, p.prefix_len, p.scale_log2, base,
-                               prow + cc * (BM * 128), 4, r);
+          l_run += chunk_probs<POLY>(vb, full, k0 + (2 * cc + 1) * 32, kv_len, qpos, p.prefix_len, p.scale_log2, base,
+                                     prow + cc * (BM * 128), 4, r);
         }
       }
       // S has been consumed; P is in shared memory: publish both
@@ -365,13 +389,13 @@ int prefill_attention_tc(const __nv_bfloat16* q, int n_heads, int n_kv_heads, in
   if (make_tmap_bf16_2d(&tKV, kv_pool, pool_rows, 64, 64, 64)) return 1;
   static DeviceOnce configured;
   if (configured.first()) {
-    cudaError_t e = cudaFuncSetAttribute(fa_tc_prefill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         fa::kSmemTotal);
-    if (e != cudaSuccess) return set_error(cudaGetErrorString(e));
-    // two CTAs per SM need the full shared-memory carve-out
-    e = cudaFuncSetAttribute(fa_tc_prefill_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
-                             cudaSharedmemCarveoutMaxShared);
-    if (e != cudaSuccess) return set_error(cudaGetErrorString(e));
+    for (auto* fn : {fa_tc_prefill_kernel<false>, fa_tc_prefill_kernel<true>}) {
+      cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, fa::kSmemTotal);
+      if (e != cudaSuccess) return set_error(cudaGetErrorString(e));
+      // two CTAs per SM need the full shared-memory carve-out
+      e = cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+      if (e != cudaSuccess) return set_error(cudaGetErrorString(e));
+    }
   }
   FaTcParams p{};
   p.q_offsets = q_offsets; p.start_pos = start_pos; p.block_tables = block_tables;
@@ -379,7 +403,8 @@ int prefill_attention_tc(const __nv_bfloat16* q, int n_heads, int n_kv_heads, in
   p.prefix_len = prefix_len; p.out = out;
   p.scale_log2 = 0.125f * 1.4426950408889634f;
   dim3 grid((max_q + fa::BM - 1) / fa::BM, n_heads, n_seqs);
-  fa_tc_prefill_kernel<<<grid, fa::kThreads, fa::kSmemTotal, stream>>>(tQ, tKV, p);
+  if (g_attention_impl == 2) fa_tc_prefill_kernel<true><<<grid, fa::kThreads, fa::kSmemTotal, stream>>>(tQ, tKV, p);
+  else fa_tc_prefill_kernel<false><<<grid, fa::kThreads, fa::kSmemTotal, stream>>>(tQ, tKV, p);
   count_launch();
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(cudaGetErrorString(e));
@@ -415,6 +440,7 @@ struct FaVitParams {
   float scale_log2;
 };
 
+template <bool POLY>
 __global__ void __launch_bounds__(fv::kThreads, 2)
 fa_tc_vit_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_constant__ CUtensorMap tm16,
                  const FaVitParams p) {
@@ -593,12 +619,12 @@ fa_tc_vit_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_constant
         for (int cc = 0; cc < 2; ++cc) {
           tmem_ld_wait();
           tmem_ld_32x32(tS + (2 * cc + 1) * 32, vb);
-          l_run += chunk_probs(va, full, k0 + (2 * cc) * 32, kv_len, qpos, 0, p.scale_log2, base,
-                               prow + cc * (BM * 128), 0, r);
+          l_run += chunk_probs<POLY>(va, full, k0 + (2 * cc) * 32, kv_len, qpos, 0, p.scale_log2, base,
+                                     prow + cc * (BM * 128), 0, r);
           tmem_ld_wait();
           if (cc == 0) tmem_ld_32x32(tS + 64, va);
-          l_run += chunk_probs(vb, full, k0 + (2 * cc + 1) * 32, kv_len, qpos, 0, p.scale_log2, base,
-                               prow + cc * (BM * 128), 4, r);
+          l_run += chunk_probs<POLY>(vb, full, k0 + (2 * cc + 1) * 32, kv_len, qpos, 0, p.scale_log2, base,
+                                     prow + cc * (BM * 128), 4, r);
         }
       }
       tc_fence_before();
@@ -650,17 +676,19 @@ int vit_attention_tc(const __nv_bfloat16* qkv, int n_crops, int seq, int n_heads
   if (make_tmap_bf16_3d(&t16, qkv, 72, 3LL * n_heads, T, 144, 3 * D * 2, 16, 1, 128, 32)) return 1;
   static DeviceOnce configured;
   if (configured.first()) {
-    cudaError_t e = cudaFuncSetAttribute(fa_tc_vit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, fv::kSmemTotal);
-    if (e != cudaSuccess) return set_error(cudaGetErrorString(e));
-    e = cudaFuncSetAttribute(fa_tc_vit_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
-                             cudaSharedmemCarveoutMaxShared);
-    if (e != cudaSuccess) return set_error(cudaGetErrorString(e));
+    for (auto* fn : {fa_tc_vit_kernel<false>, fa_tc_vit_kernel<true>}) {
+      cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, fv::kSmemTotal);
+      if (e != cudaSuccess) return set_error(cudaGetErrorString(e));
+      e = cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+      if (e != cudaSuccess) return set_error(cudaGetErrorString(e));
+    }
   }
   FaVitParams p{};
   p.seq = seq; p.n_heads = n_heads; p.out = out;
   p.scale_log2 = (1.0f / sqrtf(72.0f)) * 1.4426950408889634f;
   dim3 grid((seq + fv::BM - 1) / fv::BM, n_heads, n_crops);
-  fa_tc_vit_kernel<<<grid, fv::kThreads, fv::kSmemTotal, stream>>>(t64, t16, p);
+  if (g_attention_impl == 2) fa_tc_vit_kernel<true><<<grid, fv::kThreads, fv::kSmemTotal, stream>>>(t64, t16, p);
+  else fa_tc_vit_kernel<false><<<grid, fv::kThreads, fv::kSmemTotal, stream>>>(t64, t16, p);
   count_launch();
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(cudaGetErrorString(e));

@@ -777,12 +777,15 @@ int gemm_rowform(const __nv_bfloat16* A, long long lda, const __nv_bfloat16* W, 
 // that (tiles x splits) fills whole waves of the SMs.  cost = waves x tile_rows x kb is the critical path in
 // units of 128-byte weight rows; ties prefer fewer splits (less partial-sum traffic).
 // kb_divisor > 0 restricts kb to divisors of it.
-// Operand-read model of the stream (md_debug_gemm bit 3): an SS-mode K = 16 MMA fetches its A
+// Operand-read model of the stream (the default plan; md_debug_gemm bit 3 selects the previous one for A/B runs;
+// DESIGN.md section 5.1): an SS-mode K = 16 MMA fetches its A
 // (activation lanes) and B (weight rows) operands from shared memory at ~32 B/clk, one after the other, so a 64-wide
 // k-block of a tile costs 4 * (m_rows + rows16) clocks and weights enter the tensor core at 32 * rows / (m_rows + rows)
 // B/clk per SM.  That explains the measured streams (97-row tiles with M = 128 lanes: 14 of 32 B/clk = 4 TB/s
 // chip-wide; 194 x 2 splits: 10.8 us mean) and says the stream turns HBM-bound (23 B/clk per SM) once
 // rows >= 2.6 * m_rows: tiles up to 256 rows, paid for with K splits.  cost in clocks.
+// Measured (tools/decode_timeline.py, 2B b32, profiles/r02_decode_timeline_wide.json): the [qkv ; fc1] stream
+// 18.4 -> 12.3 us with 208-row tiles x 2 splits and M = 64 MMAs.
 static StreamPlan plan_smallbatch_wide(int n_out, int K, int m_rows) {
   const int k_blocks = (K + BK - 1) / BK;
   const int sms = num_sms();
@@ -811,7 +814,7 @@ static StreamPlan plan_smallbatch_wide(int n_out, int K, int m_rows) {
 }
 
 StreamPlan plan_smallbatch(int n_out, int K, int kb_divisor, int m_rows) {
-  if ((g_gemm_debug & 8) && kb_divisor == 0) return plan_smallbatch_wide(n_out, K, m_rows);
+  if (!(g_gemm_debug & 8) && kb_divisor == 0) return plan_smallbatch_wide(n_out, K, m_rows);
   const int k_blocks = (K + BK - 1) / BK;
   const int sms = num_sms();
   StreamPlan best{BM, k_blocks, 1};
@@ -907,13 +910,14 @@ static int gemm_smallbatch_impl(const __nv_bfloat16* W, long long ldw, const __n
 
 // upper bound over the plans a launch may pick (callers size their partial-sum workspace with it)
 int gemm_smallbatch_splits(int n_out, int K) {
-  int s = plan_smallbatch(n_out, K, 0, 128).splits;
   const int saved = g_gemm_debug;
-  for (int m : {64, 128}) {
-    g_gemm_debug = saved | 8;
-    const int w = plan_smallbatch(n_out, K, 0, m).splits;
-    if (w > s) s = w;
-  }
+  int s = 1;
+  for (int legacy : {0, 8})
+    for (int m : {64, 128}) {
+      g_gemm_debug = (saved & ~8) | legacy;
+      const int w = plan_smallbatch(n_out, K, 0, m).splits;
+      if (w > s) s = w;
+    }
   g_gemm_debug = saved;
   return s;
 }

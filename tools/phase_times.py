@@ -17,6 +17,7 @@ cfg = C.preset(model)
 sd = synth.synthetic_state_dict(cfg, 0)
 eng = Engine(cfg, sd, max_batch=B)
 eng.lib.md_debug_gemm(int(os.environ.get("MD_DEBUG_GEMM", "0")))   # timing experiments (A/B of plans)
+eng.lib.md_debug_attention_impl(int(os.environ.get("MD_ATTENTION_IMPL", "0")))
 images = [synth.synthetic_image(i, 378, 378) for i in range(B)]
 prompts = [synth.synthetic_prompt(i, 32, cfg.text.vocab_size) for i in range(B)]
 crops, offsets, tilings = [], [0], []
