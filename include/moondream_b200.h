@@ -306,6 +306,22 @@ int md_region_encode(md_model* model, int which, const float* values, int batch,
  * logits' last dimension); size = 2^(bin/1023*10 - 10) (the reference hard-codes 1023). */
 int md_region_bins_to_values(int which, const int* bins, int n, int n_bins, float* out, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Native checkpoint reader (replaces the file-reading half of load_weights_into_model, weights.py:156-171)
+ * ---------------------------------------------------------------------------------------------- */
+/* safetensors file -> mmap + parsed header.  md_safetensors_info: name / dtype strings live as long as the handle;
+ * shape8 receives up to 8 extents.  md_safetensors_read copies one tensor's bytes (dst_bytes must equal its size)
+ * from the mapping into device memory (cudaMemcpyAsync on `stream`; the mapping must stay open until the stream has
+ * drained) or, with dst_is_device == 0, into host memory. */
+typedef struct md_file md_file;
+int md_safetensors_open(const char* path, md_file** out);
+int md_safetensors_count(const md_file* file);
+int md_safetensors_info(const md_file* file, int index, const char** name, const char** dtype, int* ndim,
+                        long long* shape8, long long* nbytes);
+int md_safetensors_find(const md_file* file, const char* name);
+int md_safetensors_read(const md_file* file, int index, void* dst, long long dst_bytes, int dst_is_device, void* stream);
+void md_safetensors_close(md_file* file);
+
 #ifdef __cplusplus
 }
 #endif

@@ -84,6 +84,13 @@ _SIGNATURES = {
     "md_store_column_f32": (c_int, [_P, c_int, _P, _LL, _P, c_int, _P]),
     "md_decode_advance": (c_int, [_P, _P, _P, _P, _P, _LL, c_int, c_int, _P, _P]),
     "md_gather_rows_bf16": (c_int, [_P, _LL, _P, c_int, c_int, _P, _LL, _P]),
+    "md_safetensors_open": (c_int, [c_char_p, ctypes.POINTER(c_void_p)]),
+    "md_safetensors_count": (c_int, [_P]),
+    "md_safetensors_info": (c_int, [_P, c_int, ctypes.POINTER(c_char_p), ctypes.POINTER(c_char_p), ctypes.POINTER(c_int),
+                                    ctypes.POINTER(c_longlong), ctypes.POINTER(c_longlong)]),
+    "md_safetensors_find": (c_int, [_P, c_char_p]),
+    "md_safetensors_read": (c_int, [_P, c_int, _P, _LL, c_int, _P]),
+    "md_safetensors_close": (None, [_P]),
     "md_region_workspace_bytes": (_LL, [_P, c_int]),
     "md_region_decode": (c_int, [_P, c_int, _P, _LL, c_int, _P, _P, _P]),
     "md_region_encode": (c_int, [_P, c_int, _P, c_int, _P, _LL, _P, _P]),

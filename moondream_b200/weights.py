@@ -106,16 +106,73 @@ def normalize_state_dict(cfg: MoondreamConfig, keys: Iterable[str],
     return result
 
 
-def load_state_dict_from_file(weights_file: str, cfg: MoondreamConfig) -> Dict[str, torch.Tensor]:
-    if weights_file.endswith(".safetensors"):
-        import safetensors
+_ST_DTYPES = {"BF16": torch.bfloat16, "F16": torch.float16, "F32": torch.float32, "F64": torch.float64,
+              "I64": torch.int64, "I32": torch.int32, "I16": torch.int16, "I8": torch.int8, "U8": torch.uint8,
+              "BOOL": torch.bool}
 
-        with safetensors.safe_open(weights_file, framework="pt") as st:  # pyright: ignore
-            return normalize_state_dict(cfg, list(st.keys()), st.get_tensor)
+
+class NativeSafetensors:
+    """The library's own safetensors reader (csrc/loader.cu: mmap + header parse): tensors are copied from the file
+    mapping straight into the torch tensor `get` allocates — on `device` (e.g. "cuda": one H2D per tensor, no host
+    copy) or on the CPU."""
+
+    def __init__(self, path: str, device="cpu"):
+        import ctypes
+
+        from . import _native as N
+
+        self._N, self._lib = N, N.lib()
+        self.device = torch.device(device)
+        h = ctypes.c_void_p()
+        N.check(self._lib.md_safetensors_open(path.encode(), ctypes.byref(h)), "md_safetensors_open")
+        self._h = h
+        self._index: Dict[str, tuple] = {}
+        for i in range(self._lib.md_safetensors_count(h)):
+            name, dtype = ctypes.c_char_p(), ctypes.c_char_p()
+            ndim, nbytes = ctypes.c_int(), ctypes.c_longlong()
+            shape = (ctypes.c_longlong * 8)()
+            N.check(self._lib.md_safetensors_info(h, i, ctypes.byref(name), ctypes.byref(dtype), ctypes.byref(ndim),
+                                                  shape, ctypes.byref(nbytes)), "md_safetensors_info")
+            self._index[name.value.decode()] = (i, dtype.value.decode(), tuple(shape[: ndim.value]), nbytes.value)
+
+    def keys(self):
+        return list(self._index)
+
+    def get_tensor(self, key: str) -> torch.Tensor:
+        i, dtype, shape, nbytes = self._index[key]
+        if dtype not in _ST_DTYPES:
+            raise ValueError(f"{key}: unsupported safetensors dtype {dtype}")
+        t = torch.empty(shape, dtype=_ST_DTYPES[dtype], device=self.device)
+        on_dev = self.device.type == "cuda"
+        stream = self._N.current_stream() if on_dev else None
+        self._N.check(self._lib.md_safetensors_read(self._h, i, self._N.ptr(t) if t.numel() else None, nbytes, int(on_dev),
+                                                    stream), "md_safetensors_read") if t.numel() else None
+        return t
+
+    def close(self):
+        if self._h is not None:
+            if self.device.type == "cuda":
+                torch.cuda.synchronize(self.device)        # the async copies read the mapping
+            self._lib.md_safetensors_close(self._h)
+            self._h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+
+def load_state_dict_from_file(weights_file: str, cfg: MoondreamConfig, device="cpu") -> Dict[str, torch.Tensor]:
+    """safetensors: through the native reader (tensors land on `device` directly); .pt: torch.load."""
+    if weights_file.endswith(".safetensors"):
+        with NativeSafetensors(weights_file, device) as st:
+            return normalize_state_dict(cfg, st.keys(), st.get_tensor)
     tensors = torch.load(weights_file, map_location="cpu", weights_only=True)
     return normalize_state_dict(cfg, list(tensors.keys()), lambda k: tensors[k])
 
 
 def load_weights_into_model(weights_file: str, model) -> None:
     """Drop-in for ``moondream.torch.weights.load_weights_into_model`` (weights.py:156)."""
-    model.load_state_dict(load_state_dict_from_file(weights_file, model.config))
+    device = model.device if torch.cuda.is_available() else "cpu"
+    model.load_state_dict(load_state_dict_from_file(weights_file, model.config, device))

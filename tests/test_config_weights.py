@@ -164,3 +164,37 @@ def test_loader_agrees_with_the_reference_loader(tmp_path, layout, fmt):
     for k in sd:
         assert k in theirs, k
         assert torch.equal(theirs[k], sd[k]) and torch.equal(ours[k], sd[k]), k
+
+
+def test_native_safetensors_reader_matches_the_safetensors_package(tmp_path):
+    """csrc/loader.cu (mmap + own header parser) against the `safetensors` package the reference loads through
+    (weights.py:156-171): names, dtypes, shapes and bytes, with metadata, a scalar, an empty tensor and odd names."""
+    import pytest
+    from safetensors.torch import save_file
+
+    from moondream_b200 import _native as N
+    from moondream_b200.weights import NativeSafetensors
+
+    g = torch.Generator().manual_seed(0)
+    tensors = {
+        "vision.blocks.0.attn.proj.bias": torch.randn(17, generator=g).to(torch.bfloat16),
+        "text.wte": torch.randn(33, 8, generator=g).to(torch.float16),
+        'weird "name"/with\\escapes': torch.randn(2, 3, 4, generator=g),
+        "ints": torch.arange(10, dtype=torch.int64).view(2, 5),
+        "scalar": torch.tensor(3.5),
+        "empty": torch.zeros((0, 4), dtype=torch.bfloat16),
+        "bytes": torch.arange(7, dtype=torch.uint8),
+    }
+    path = str(tmp_path / "x.safetensors")
+    save_file(tensors, path, metadata={"format": "pt", "note": '{nested: "braces"}'})
+    with NativeSafetensors(path) as st:
+        assert sorted(st.keys()) == sorted(tensors)
+        for k, want in tensors.items():
+            got = st.get_tensor(k)
+            assert got.dtype == want.dtype and tuple(got.shape) == tuple(want.shape) and torch.equal(got, want), k
+    bad = tmp_path / "bad.safetensors"
+    bad.write_bytes(b"\xff\xff\xff\xff\x00\x00\x00\x00{}")
+    with pytest.raises(N.NativeError):
+        NativeSafetensors(str(bad))
+    with pytest.raises(N.NativeError):
+        NativeSafetensors(str(tmp_path / "missing.safetensors"))

@@ -526,3 +526,32 @@ def test_lora_variant_matches_the_reference_golden(tiny, tmp_path, monkeypatch):
     assert len(_ids(out["answer"])) <= 6
     with pytest.raises(RuntimeError):
         model.caption(synth.synthetic_image(0, 378, 378), "short", settings={"temperature": 0, "variant": "missing"})
+
+
+def test_native_loader_reads_straight_into_device_memory(tiny, tmp_path):
+    """load_weights_into_model through csrc/loader.cu: the checkpoint's tensors go from the file mapping to HBM
+    (no host tensors), legacy HF key layout included; the loaded model generates the same tokens."""
+    from safetensors.torch import save_file
+
+    from moondream_b200 import synth
+    from moondream_b200.weights import legacy_key_map, load_state_dict_from_file, load_weights_into_model
+
+    cfg, sd = tiny
+    path = str(tmp_path / "model.safetensors")
+    save_file({k: v.contiguous() for k, v in sd.items()}, path)
+    dev_sd = load_state_dict_from_file(path, cfg, "cuda")
+    assert all(t.is_cuda for t in dev_sd.values())
+    for k, v in sd.items():
+        assert torch.equal(dev_sd[k].cpu(), v), k
+    legacy = {old: sd[new] for old, new in legacy_key_map(cfg).items()}
+    legacy["region_model.coordinate_features.weight"] = sd["region.coord_features"].T.contiguous()
+    legacy["region_model.size_features.weight"] = sd["region.size_features"].T.contiguous()
+    lpath = str(tmp_path / "legacy.safetensors")
+    save_file({k: v.contiguous() for k, v in legacy.items()}, lpath)
+    a, b = _model(cfg, sd), _model(cfg, sd)
+    load_weights_into_model(path, a)
+    load_weights_into_model(lpath, b)
+    img = synth.synthetic_image(0, 378, 378)
+    s = {"temperature": 0, "max_tokens": 8}
+    ref = _model(cfg, sd).caption(img, "short", settings=s)["caption"]
+    assert a.caption(img, "short", settings=s)["caption"] == ref == b.caption(img, "short", settings=s)["caption"]
