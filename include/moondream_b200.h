@@ -140,7 +140,8 @@ void md_debug_set_pdl(int enable);
 void md_debug_skip_decode_kernels(int mask);
 /* Timing experiments only, small-batch weight stream:
  * bit2 previous split plan of the [proj | fc2] stream (equal splits); bit3 previous plan of the single-segment streams
- * (tiles <= 128 rows; the default is the operand-read cost model: tiles up to 256 rows + K splits); bit6 forces M = 128 MMAs for batches <= 64
+ * (tiles <= 128 rows; the default is the operand-read cost model: tiles up to 256 rows + K splits); bit4 lets the last
+ * CTAs of the [proj | fc2] stream finish the residual + LayerNorm rows (no separate epilogue launch); bit6 forces M = 128 MMAs for batches <= 64
  * (the default there is M = 64).  Other bits are ignored. */
 void md_debug_gemm(int flags);
 /* Experiments only: cap the persistent row-form GEMM's grid at `sms` SMs (0 = all, the default), leaving the others

@@ -3,6 +3,7 @@
 // paged KV-cache write, greedy argmax over the vocabulary, Fourier features of the region head.
 #include <math.h>
 
+#include "decode_epilogue.cuh"
 #include "kernels.cuh"
 #include "ptx.cuh"
 
@@ -583,115 +584,18 @@ decode_residual_ln_epilogue_kernel(const float* __restrict__ ws, int splits, int
                                    const __nv_bfloat16* __restrict__ ln_w, const __nv_bfloat16* __restrict__ ln_b,
                                    __nv_bfloat16* __restrict__ ln_out, float eps) {
   const bool tl = tl_on() && threadIdx.x == 0;
-  unsigned long long tl0 = 0, tl1 = 0, tl2 = 0;
+  unsigned long long tl0 = 0, tl1 = 0;
   if (tl) tl0 = tl_now();
   pdl_launch_dependents();
-  constexpr int kMaxChunks = 2;                        // 8-element chunks per thread: D <= 4096
-  constexpr int kBatch = 10;                           // splits fetched per round of independent loads
-  const int b = blockIdx.x;
-  const int tid = threadIdx.x;
-  const int chunks = D >> 3;
   // the kernel is one latency chain (32 CTAs, a few loads per thread): parameters do not depend on the
   // predecessor, so their loads are issued before the dependency wait
-  uint4 bp[kMaxChunks], bf[kMaxChunks], wq[kMaxChunks], bq[kMaxChunks];
-#pragma unroll
-  for (int i = 0; i < kMaxChunks; ++i) {
-    const int c = tid + i * 256;
-    if (c >= chunks) continue;
-    bp[i] = *reinterpret_cast<const uint4*>(bias_proj + c * 8);
-    bf[i] = *reinterpret_cast<const uint4*>(bias_fc2 + c * 8);
-    wq[i] = *reinterpret_cast<const uint4*>(ln_w + c * 8);
-    bq[i] = *reinterpret_cast<const uint4*>(ln_b + c * 8);
-  }
+  ResLnParams P;
+  residual_ln_load_params(P, D, bias_proj, bias_fc2, ln_w, ln_b);
   pdl_wait();
   if (tl) tl1 = tl_now();
-  float v[kMaxChunks][8];
-  float sum = 0.f;
-#pragma unroll
-  for (int i = 0; i < kMaxChunks; ++i) {
-    const int c = tid + i * 256;
-    if (c >= chunks) continue;
-    const int d0 = c * 8;
-    float a[8], m[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) a[k] = m[k] = 0.f;
-    // all loads of a thread are independent 16-byte reads: issue them together (kBatch splits per round) so
-    // the L2 round trips overlap instead of forming a chain; the summation order stays split 0, 1, 2, ...
-    const long long sstride = static_cast<long long>(B) * D;
-    const float* base_ptr = ws + static_cast<long long>(b) * D + d0;
-    const uint4 xq = *reinterpret_cast<const uint4*>(x + static_cast<long long>(b) * D + d0);
-    for (int s0 = 0; s0 < splits; s0 += kBatch) {
-      float4 lo[kBatch], hi[kBatch];
-#pragma unroll
-      for (int u = 0; u < kBatch; ++u) {
-        if (s0 + u < splits) {
-          const float4* src = reinterpret_cast<const float4*>(base_ptr + (s0 + u) * sstride);
-          lo[u] = src[0];
-          hi[u] = src[1];
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < kBatch; ++u) {
-        if (s0 + u < splits) {
-          float* dst = (s0 + u) < proj_splits ? a : m;
-          dst[0] += lo[u].x; dst[1] += lo[u].y; dst[2] += lo[u].z; dst[3] += lo[u].w;
-          dst[4] += hi[u].x; dst[5] += hi[u].y; dst[6] += hi[u].z; dst[7] += hi[u].w;
-        }
-      }
-    }
-    const uint32_t bpw[4] = {bp[i].x, bp[i].y, bp[i].z, bp[i].w}, bfw[4] = {bf[i].x, bf[i].y, bf[i].z, bf[i].w},
-                   xw[4] = {xq.x, xq.y, xq.z, xq.w};
-    uint32_t ow[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const float a0 = bf16_round(a[2 * k] + bf16_lo(bpw[k])), a1 = bf16_round(a[2 * k + 1] + bf16_hi(bpw[k]));
-      const float m0 = bf16_round(m[2 * k] + bf16_lo(bfw[k])), m1 = bf16_round(m[2 * k + 1] + bf16_hi(bfw[k]));
-      const float r0 = bf16_round(bf16_round(bf16_lo(xw[k]) + a0) + m0);
-      const float r1 = bf16_round(bf16_round(bf16_hi(xw[k]) + a1) + m1);
-      v[i][2 * k] = r0; v[i][2 * k + 1] = r1;
-      sum += r0 + r1;
-      ow[k] = pack_bf16x2(r0, r1);
-    }
-    *reinterpret_cast<uint4*>(x + static_cast<long long>(b) * D + d0) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
-  }
-  if (tl) tl2 = tl_now();
-  __shared__ float red[2][8];                          // one array per reduction: a single barrier each
-  auto block_sum = [&](float val, int which) {
-    for (int o = 16; o > 0; o >>= 1) val += __shfl_xor_sync(0xffffffffu, val, o);
-    if ((tid & 31) == 0) red[which][tid >> 5] = val;
-    __syncthreads();
-    float t = 0.f;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) t += red[which][i];
-    return t;
-  };
-  const float mean = block_sum(sum, 0) / D;
-  float sq = 0.f;
-#pragma unroll
-  for (int i = 0; i < kMaxChunks; ++i) {
-    if (tid + i * 256 >= chunks) continue;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) sq += (v[i][k] - mean) * (v[i][k] - mean);
-  }
-  const float var = block_sum(sq, 1) / D;
-  const float rstd = 1.0f / sqrtf(var + eps);
-  const float shift = -rstd * mean;
-#pragma unroll
-  for (int i = 0; i < kMaxChunks; ++i) {
-    const int c = tid + i * 256;
-    if (c >= chunks) continue;
-    const int d0 = c * 8;
-    const uint32_t ww[4] = {wq[i].x, wq[i].y, wq[i].z, wq[i].w}, bw[4] = {bq[i].x, bq[i].y, bq[i].z, bq[i].w};
-    uint32_t ow[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const float y0 = (v[i][2 * k] * rstd + shift) * bf16_lo(ww[k]) + bf16_lo(bw[k]);
-      const float y1 = (v[i][2 * k + 1] * rstd + shift) * bf16_hi(ww[k]) + bf16_hi(bw[k]);
-      ow[k] = pack_bf16x2(y0, y1);
-    }
-    *reinterpret_cast<uint4*>(ln_out + static_cast<long long>(b) * D + d0) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
-  }
-  if (tl) tl_emit(3u << 28, tl0, tl1, tl2, 0ull, tl_now());
+  __shared__ float red[2][8];
+  residual_ln_row<false>(P, ws, splits, proj_splits, B, D, x, ln_out, eps, blockIdx.x, red);
+  if (tl) tl_emit(3u << 28, tl0, tl1, tl1, 0ull, tl_now());
 }
 
 void timeline_install_elementwise(const Timeline& t) { timeline_install(t); }

@@ -324,7 +324,7 @@ static long long smallbatch_ws_floats(const Model& m, int batch) {
 long long text_decode_ws_bytes(const Model& m, int batch) {
   const md_dims& d = m.d;
   return pad256(1LL * batch * d.txt_dim * 2) * 3 + pad256(1LL * batch * (d.txt_dim + d.txt_ff) * 2) +
-         pad256(smallbatch_ws_floats(m, batch) * 4) + 4096;
+         pad256(smallbatch_ws_floats(m, batch) * 4) + 256 /* tail counters */ + 4096;
 }
 
 static int small_linear(const bf16* x, long long ldx, const Lin& l, int batch, int n_out, int K, int mode,
@@ -349,7 +349,10 @@ int text_decode_step(Model& m, bf16* x, const int* pos, int batch, const md_kv& 
   bf16* ln_last = reinterpret_cast<bf16*>(p); p += pad256(1LL * batch * D * 2);
   bf16* qbuf = reinterpret_cast<bf16*>(p); p += pad256(1LL * batch * D * 2);          // grouped-query path only
   bf16* xcat = reinterpret_cast<bf16*>(p); p += pad256(1LL * batch * (D + FF) * 2);   // [att | gelu(fc1)]
+  int* tail_counter = reinterpret_cast<int*>(p); p += 256;
   float* wsf = reinterpret_cast<float*>(p);
+  const bool tail = gemm_stream_tail_enabled(batch);
+  if (tail && cudaMemsetAsync(tail_counter, 0, 8, st) != cudaSuccess) return set_error("md_text_decode_step: memset failed");
   bf16* pool = reinterpret_cast<bf16*>(kv.pool);
   const StreamPlan2 pl2 = plan_smallbatch_2seg(D, D + FF, D);   // no split straddles proj | fc2
   const int proj_splits = pl2.splits_a;
@@ -377,11 +380,17 @@ int text_decode_step(Model& m, bf16* x, const int* pos, int batch, const md_kv& 
     }
     // proj(att) and fc2(hid) both land in the residual: one K-concatenated weight stream
     int s2 = pl2.splits_a + pl2.splits_b;
-    if (!(g_debug_skip & 8)) s2 = gemm_smallbatch_2seg(b.proj.w, D + FF, xcat, D + FF, D, batch, D + FF, D, wsf, st);
-    if (s2 < 0) return 1;
     const bool last = i + 1 == d.txt_layers;
     const Lin& nln = last ? m.txt_post_ln : m.txt[i + 1].ln;
     bf16* ln_dst = last ? (normed_out ? normed_out : ln_last) : ln;
+    if (tail) {
+      // residual + next LayerNorm finished by the stream's own last CTAs (one launch and hand-over fewer per block)
+      if (gemm_smallbatch_2seg_tail(b.proj.w, D + FF, xcat, D + FF, D, batch, D + FF, D, wsf, tail_counter, b.proj.b,
+                                    b.fc2.b, x, nln.w, nln.b, ln_dst, st) < 0) return 1;
+      continue;
+    }
+    if (!(g_debug_skip & 8)) s2 = gemm_smallbatch_2seg(b.proj.w, D + FF, xcat, D + FF, D, batch, D + FF, D, wsf, st);
+    if (s2 < 0) return 1;
     if (!(g_debug_skip & 16) &&
         decode_residual_ln_epilogue(wsf, s2, proj_splits, batch, D, b.proj.b, b.fc2.b, x, nln.w, nln.b, ln_dst, st)) return 1;
   }

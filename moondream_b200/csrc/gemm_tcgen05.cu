@@ -19,6 +19,7 @@
 //     (splitk_epilogue_kernel, the decode attention prologue, the residual + LayerNorm epilogue, argmax).
 #include <vector>
 
+#include "decode_epilogue.cuh"
 #include "kernels.cuh"
 #include "ptx.cuh"
 
@@ -363,6 +364,19 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 // before the dependency wait (no earlier kernel writes weights); only the activation loads, and everything
 // downstream of them, wait for the predecessor.
 // ------------------------------------------------------------------------------------------------
+// Tail of the [proj | fc2] stream (md_debug_gemm bit 4 enables it): instead of handing the fp32 partial sums to a
+// separate residual + LayerNorm kernel, every CTA takes a ticket after publishing its partials; the CTAs holding the
+// last `rows` tickets wait until the ticket counter shows that all partials are out, then each finishes one batch row
+// (decode_epilogue.cuh) — one launch and one grid-to-grid hand-over fewer per decoder block.  The waiting CTAs are at
+// most `rows` (<= 128) of a grid that is fully resident, and every CTA they wait for has already been scheduled, so
+// the spin cannot deadlock.
+struct StreamTail {
+  int* counter;                        // [2] device ints, zero before the launch: tickets, finished rows
+  int proj_splits, D;
+  const __nv_bfloat16 *bias_proj, *bias_fc2, *ln_w, *ln_b;
+  __nv_bfloat16 *x, *ln_out;
+};
+
 constexpr int kSbMaxStages = 12;
 constexpr int kSbThreads = 256;          // warp 0 TMA producer, 1 MMA issuer, 2 TMEM allocator, 4..7 epilogue
 constexpr int kSbTailPad = BM * BK * 2;  // the A descriptor spans 128 rows whatever the batch: keep it in bounds
@@ -375,13 +389,17 @@ struct SmallBatchParams {
   int tmem_cols;
   int trigger_early;
   float* ws;
+  StreamTail tail;                     // tail.counter != nullptr: the last CTAs finish the rows (see the kernel's end)
 };
 
 // MROWS = 128 is the shipped form.  MROWS = 64 (batch <= 64; selected by md_debug_gemm bit 6 until it has been
 // validated on hardware) issues M = 64 MMAs: half the A-operand read per K = 16 step, accumulator rows
 // 16q .. 16q+15 in lanes 0..15 of TMEM lane quadrant q (the 1-CTA M = 64 data-path layout).
-template <int MROWS>
-__global__ void __launch_bounds__(kSbThreads, 1)
+// TAIL = true compiles the row-finishing tail in (its own instantiation, capped at 128 registers: the plain stream
+// keeps its 48 registers, which is what lets its CTAs become resident — and prefetch weights — while CTAs of the
+// preceding kernel still occupy the SM).
+template <int MROWS, bool TAIL = false>
+__global__ void __launch_bounds__(kSbThreads, TAIL ? 2 : 1)
 smallbatch_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
                        const SmallBatchParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -511,6 +529,7 @@ smallbatch_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
     }
   }
 
+  if (TAIL) __threadfence();                            // this thread's partial sums are visible device-wide
   tc_fence_before();
   __syncthreads();
   if (tl && threadIdx.x == 0)
@@ -519,6 +538,38 @@ smallbatch_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, static_cast<uint32_t>(p.tmem_cols));
+  }
+  if constexpr (TAIL) {
+    __shared__ int ticket_s;
+    __shared__ float red[2][8];
+    const int total = static_cast<int>(gridDim.x);
+    const int finishers = p.batch < total ? p.batch : total;
+    if (threadIdx.x == 0) ticket_s = atomicAdd(p.tail.counter, 1);
+    __syncthreads();
+    const int mine = ticket_s - (total - finishers);
+    if (mine >= 0) {                                     // CTA-uniform
+      ResLnParams P;
+      residual_ln_load_params(P, p.tail.D, p.tail.bias_proj, p.tail.bias_fc2, p.tail.ln_w, p.tail.ln_b);
+      if (threadIdx.x == 0) {
+        const long long t0 = clock64();
+        while (*reinterpret_cast<volatile int*>(p.tail.counter) < total)
+          if (clock64() - t0 > 4000000000LL) __trap();    // ~2 s: a lost CTA must not hang the GPU
+        __threadfence();
+      }
+      __syncthreads();
+      for (int b = mine; b < p.batch; b += finishers)
+        residual_ln_row<true>(P, p.ws, p.k_splits, p.tail.proj_splits, p.batch_total, p.tail.D, p.tail.x, p.tail.ln_out,
+                              1e-5f, b, red);
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        const int done = atomicAdd(p.tail.counter + 1, 1);
+        if (done == finishers - 1) {                     // the last finisher re-arms the counters for the next launch
+          p.tail.counter[0] = 0;
+          p.tail.counter[1] = 0;
+          __threadfence();
+        }
+      }
+    }
   }
 }
 
@@ -843,7 +894,8 @@ StreamPlan plan_smallbatch(int n_out, int K, int kb_divisor, int m_rows) {
 // Returns the number of splits (> 0), -1 on error.
 static int gemm_smallbatch_impl(const __nv_bfloat16* W, long long ldw, const __nv_bfloat16* X, long long ldx,
                              int n_out, int batch, int K, int kb_per_split, int tile_n, float* ws,
-                             cudaStream_t stream, int seg_kb = 0, int kb_per_split2 = 0) {
+                             cudaStream_t stream, int seg_kb = 0, int kb_per_split2 = 0,
+                             const StreamTail* tail = nullptr) {
   if (n_out <= 0 || batch <= 0 || K <= 0) { set_error("small-batch GEMM: empty problem"); return -1; }
   if (K % 8) { set_error("small-batch GEMM: K must be a multiple of 8"); return -1; }
   if (tile_n < 1 || tile_n > 256) tile_n = BM;
@@ -883,8 +935,19 @@ static int gemm_smallbatch_impl(const __nv_bfloat16* W, long long ldw, const __n
     cudaError_t e = cudaFuncSetAttribute(smallbatch_gemm_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSbSmemMax);
     if (e != cudaSuccess) { set_error(cudaGetErrorString(e)); return -1; }
   }
+  static DeviceOnce configured_tail;
+  if (tail && configured_tail.first()) {
+    cudaError_t e = cudaFuncSetAttribute(smallbatch_gemm_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSbSmemMax);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(smallbatch_gemm_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSbSmemMax);
+    if (e != cudaSuccess) { set_error(cudaGetErrorString(e)); return -1; }
+  }
   CUtensorMap tW;
   if (make_tmap_bf16_2d(&tW, W, n_out, K, ldw, tile_n)) return -1;
+  if (tail && batch <= BM) {
+    p.tail = *tail;
+    p.tail.proj_splits = p.seg_splits;
+  }
   for (int b0 = 0; b0 < batch; b0 += BM) {
     p.batch = batch - b0 < BM ? batch - b0 : BM;
     const int a_rows = (p.batch + 7) / 8 * 8;
@@ -899,10 +962,13 @@ static int gemm_smallbatch_impl(const __nv_bfloat16* W, long long ldw, const __n
     if (make_tmap_bf16_2d(&tX, X + static_cast<long long>(b0) * ldx, p.batch, K, ldx, a_rows)) return -1;
     const int smem_bytes = p.stages * p.stage_bytes + kSbTailPad + bar_bytes + 1024;
     count_launch();
-    cudaError_t e = m64 ? launch_k(smallbatch_gemm_kernel<64>, dim3(n_tiles * p.k_splits), dim3(kSbThreads),
-                                   static_cast<size_t>(smem_bytes), stream, tX, tW, p)
-                        : launch_k(smallbatch_gemm_kernel<128>, dim3(n_tiles * p.k_splits), dim3(kSbThreads),
-                                   static_cast<size_t>(smem_bytes), stream, tX, tW, p);
+    const dim3 grid(n_tiles * p.k_splits), block(kSbThreads);
+    const size_t smem = static_cast<size_t>(smem_bytes);
+    cudaError_t e;
+    if (p.tail.counter) e = m64 ? launch_k(smallbatch_gemm_kernel<64, true>, grid, block, smem, stream, tX, tW, p)
+                                : launch_k(smallbatch_gemm_kernel<128, true>, grid, block, smem, stream, tX, tW, p);
+    else e = m64 ? launch_k(smallbatch_gemm_kernel<64>, grid, block, smem, stream, tX, tW, p)
+                 : launch_k(smallbatch_gemm_kernel<128>, grid, block, smem, stream, tX, tW, p);
     if (e != cudaSuccess) { set_error(cudaGetErrorString(e)); return -1; }
   }
   return p.k_splits;
@@ -1003,6 +1069,21 @@ int gemm_smallbatch_2seg(const __nv_bfloat16* W, long long ldw, const __nv_bfloa
   if (seg_K <= 0 || seg_K >= K || seg_K % BK) { set_error("gemm_smallbatch_2seg: segment boundary must be a multiple of 64 inside K"); return -1; }
   const StreamPlan2 pl = plan_smallbatch_2seg(n_out, K, seg_K);
   return gemm_smallbatch_impl(W, ldw, X, ldx, n_out, batch, K, pl.kb_a, pl.tile_rows, ws, stream, seg_K / BK, pl.kb_b);
+}
+
+bool gemm_stream_tail_enabled(int batch) { return (g_gemm_debug & 16) && batch <= BM; }
+
+// the [proj | fc2] stream with the residual + LayerNorm rows finished by its own last CTAs (see StreamTail);
+// `counter`: two zeroed device ints
+int gemm_smallbatch_2seg_tail(const __nv_bfloat16* W, long long ldw, const __nv_bfloat16* X, long long ldx, int n_out,
+                              int batch, int K, int seg_K, float* ws, int* counter, const __nv_bfloat16* bias_proj,
+                              const __nv_bfloat16* bias_fc2, __nv_bfloat16* x, const __nv_bfloat16* ln_w,
+                              const __nv_bfloat16* ln_b, __nv_bfloat16* ln_out, cudaStream_t stream) {
+  if (seg_K <= 0 || seg_K >= K || seg_K % BK) { set_error("gemm_smallbatch_2seg: segment boundary must be a multiple of 64 inside K"); return -1; }
+  if (n_out % 8 || n_out > 4096 || batch > BM) { set_error("gemm_smallbatch_2seg_tail: unsupported shape"); return -1; }
+  const StreamPlan2 pl = plan_smallbatch_2seg(n_out, K, seg_K);
+  StreamTail t{counter, 0, n_out, bias_proj, bias_fc2, ln_w, ln_b, x, ln_out};
+  return gemm_smallbatch_impl(W, ldw, X, ldx, n_out, batch, K, pl.kb_a, pl.tile_rows, ws, stream, seg_K / BK, pl.kb_b, &t);
 }
 
 int splitk_epilogue(const float* ws, int splits, int B, int N, int mode, const __nv_bfloat16* bias,

@@ -101,6 +101,11 @@ struct StreamPlan2 { int tile_rows, splits_a, kb_a, splits_b, kb_b; };
 StreamPlan2 plan_smallbatch_2seg(int n_out, int K, int seg_K);
 int gemm_smallbatch_2seg(const __nv_bfloat16* W, long long ldw, const __nv_bfloat16* X, long long ldx,
                       int n_out, int batch, int K, int seg_K, float* ws, cudaStream_t stream);
+bool gemm_stream_tail_enabled(int batch);
+int gemm_smallbatch_2seg_tail(const __nv_bfloat16* W, long long ldw, const __nv_bfloat16* X, long long ldx, int n_out,
+                              int batch, int K, int seg_K, float* ws, int* counter, const __nv_bfloat16* bias_proj,
+                              const __nv_bfloat16* bias_fc2, __nv_bfloat16* x, const __nv_bfloat16* ln_w,
+                              const __nv_bfloat16* ln_b, __nv_bfloat16* ln_out, cudaStream_t stream);
 int splitk_epilogue(const float* ws, int splits, int B, int N, int mode, const __nv_bfloat16* bias,
                     const __nv_bfloat16* res, long long ldr, __nv_bfloat16* out, long long ldo,
                     cudaStream_t stream);

@@ -231,8 +231,10 @@ class Engine:
 
     def _init(self, cfg, state_dict, kv_pages, max_batch):
         import os as _os0
-        if _os0.environ.get("MD_PDL") is not None:          # A/B switch for profiling runs
+        if _os0.environ.get("MD_PDL") is not None:          # A/B switches for profiling / validation runs
             self.lib.md_debug_set_pdl(int(_os0.environ["MD_PDL"]))
+        if _os0.environ.get("MD_DEBUG_GEMM") is not None:
+            self.lib.md_debug_gemm(int(_os0.environ["MD_DEBUG_GEMM"]))
         prepared, self.patch_k, self.vis_ff = prepare_weights(cfg, state_dict)
         self.weights, self._owners = upload_weights(cfg, prepared, self.device)   # keeps device memory alive
         del prepared
