@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define MD_ABI_VERSION 2
+#define MD_ABI_VERSION 3
 
 /* epilogue selectors for the linear entry points */
 #define MD_EPI_BIAS 0          /* y = bf16(x W^T + b)                        layers.py:34-35   */
@@ -78,6 +78,17 @@ long long md_linear_small_batch_workspace_bytes(int n_out, int batch, int K);
 int md_linear_small_batch_bf16(const void* x, long long ldx, const void* w, long long ldw, int batch,
                                int n_out, int K, int epilogue, const void* bias, const void* residual,
                                long long ldr, void* out, long long ldo, void* workspace, void* stream);
+
+/* dequantize_tensor (layers.py:38-44) for a stream-layout matrix: out bf16 [N][K] (row pitch ldo) =
+ * bf16( bf16(q - zero) * scale ); bits in {4, 8}, K % 128 == 0. */
+int md_dequantize_weights(int bits, const void* wq, const float* scale, const float* zero, int N, int K, void* out,
+                          long long ldo, void* stream);
+/* md_linear_small_batch_bf16 with packed weights (see md_model_set_quantized_block for the layout): the result
+ * equals md_linear_small_batch_bf16 on the dequantised matrix bit for bit (same split plan and summation order). */
+int md_linear_small_batch_quant(int bits, const void* x, long long ldx, const void* wq, const float* scale,
+                                const float* zero, int batch, int n_out, int K, int epilogue, const void* bias,
+                                const void* residual, long long ldr, void* out, long long ldo, void* workspace,
+                                void* stream);
 
 /*
  * Image preprocessing on the device: the resize of overlap_crop_image (image_crops.py:124-150, PIL branch) as the two
@@ -194,6 +205,22 @@ int md_model_num_weights(const md_dims* dims);
 int md_model_create(const md_dims* dims, const void* const* weights, int n_weights,
                     const void* pixel_lut, const float* rope_table, md_model** out);
 void md_model_destroy(md_model* model);
+
+/*
+ * Weight-only quantised decoder blocks — the reference's int4 group-128 QuantizedLinear (layers.py:38-110, selected by
+ * TextConfig.group_size, text.py:178) and int8.  Per block the packed tensors of the two fused decode streams, in the
+ * STREAM layout (moondream_b200/quant.py converts the reference checkpoint layout; values untouched):
+ *   bits = 4: wq[n][K / 2] bytes, low nibble = input feature 2j, high nibble = 2j + 1;  bits = 8: wq[n][K] signed bytes;
+ *   scale / zero: fp32 [n][K / 128];   W[n][k] = bf16( bf16(q - zero) * scale )   (dequantize_tensor, layers.py:38-44)
+ *   W1 = [qkv ; fc1]: n = txt_dim + 2 * txt_kv_heads * 64 + txt_ff rows, K = txt_dim;
+ *   W2 = [proj | fc2]: n = txt_dim rows, K = txt_dim + txt_ff (groups never straddle the boundary).
+ * Call it for EVERY block.  The bf16 weight pointers of all decoder blocks given to md_model_create must then alias
+ * ONE scratch pair (W1 / W2): md_text_prefill(_lora) rebuilds block i's bf16 weights there before its GEMMs, and
+ * md_text_decode_step streams the packed bytes (a quarter / half of the bf16 traffic), producing bit for bit what the
+ * bf16 path produces on W.  The model stores the pointers only.
+ */
+int md_model_set_quantized_block(md_model* model, int layer, int bits, const void* w1q, const float* w1_scale,
+                                 const float* w1_zero, const void* w2q, const float* w2_scale, const float* w2_zero);
 
 /* _vis_enc (vision.py:64-74 + prepare_crops' normalisation :36-40 + create_patches :44-61):
  * crops uint8 NHWC [n_crops, crop, crop, 3] -> feats bf16 [n_crops * grid^2, vis_dim]. */

@@ -47,6 +47,9 @@ _SIGNATURES = {
     "md_linear_small_batch_workspace_bytes": (_LL, [c_int, c_int, c_int]),
     "md_linear_small_batch_bf16": (c_int, [_P, _LL, _P, _LL, c_int, c_int, c_int, c_int, _P, _P, _LL, _P,
                                            _LL, _P, _P]),
+    "md_dequantize_weights": (c_int, [c_int, _P, _P, _P, c_int, c_int, _P, _LL, _P]),
+    "md_linear_small_batch_quant": (c_int, [c_int, _P, _LL, _P, _P, _P, c_int, c_int, c_int, c_int, _P, _P, _LL, _P,
+                                            _LL, _P, _P]),
     "md_resample_u8": (c_int, [_P, c_int, c_int, c_int, _P, _P, c_int, c_int, _P, _P]),
     "md_extract_windows_u8": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P]),
     "md_layernorm_bf16": (c_int, [_P, _LL, _P, _P, _P, _LL, c_int, c_int, _P]),
@@ -63,6 +66,7 @@ _SIGNATURES = {
     "md_model_num_weights": (c_int, [_DIMS]),
     "md_model_create": (c_int, [_DIMS, ctypes.POINTER(c_void_p), c_int, _P, _P, ctypes.POINTER(c_void_p)]),
     "md_model_destroy": (None, [_P]),
+    "md_model_set_quantized_block": (c_int, [_P, c_int, c_int, _P, _P, _P, _P, _P, _P]),
     "md_vision_encode_workspace_bytes": (_LL, [_P, c_int]),
     "md_vision_encode": (c_int, [_P, _P, c_int, _P, _P, _P]),
     "md_vision_project_workspace_bytes": (_LL, [_P, c_int]),

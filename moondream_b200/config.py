@@ -145,8 +145,11 @@ class MoondreamConfig:
             raise ValueError("prefix_attn must equal 1 + tokens per crop (moondream.py:143-145)")
         if v.proj_out_dim != t.dim or r.dim != t.dim:
             raise ValueError("projection / region width must equal the text width")
-        if t.group_size is not None or r.group_size is not None:
-            raise ValueError("int4 QuantizedLinear checkpoints (layers.py:47-110) are not supported yet")
+        for gs in (t.group_size, r.group_size):
+            if gs is not None and gs != 128:
+                raise ValueError("QuantizedLinear checkpoints use group_size 128 (layers.py:54)")
+        if t.group_size is not None and (t.dim % 128 or t.ff_dim % 128):
+            raise ValueError("int4 decoder weights need text.dim and text.ff_dim to be multiples of 128")
         for name, val in (("text.dim", t.dim), ("text.ff_dim", t.ff_dim), ("vision.enc_dim", v.enc_dim),
                           ("vision.proj_inner_dim", v.proj_inner_dim), ("region.inner_dim", r.inner_dim),
                           ("text.vocab_size", t.vocab_size)):

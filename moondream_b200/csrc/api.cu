@@ -75,6 +75,25 @@ int md_linear_small_batch_bf16(const void* x, long long ldx, const void* w, long
                              BF(bias), BF(residual), ldr, BFM(out), ldo, STREAM(stream));
 }
 
+int md_dequantize_weights(int bits, const void* wq, const float* scale, const float* zero, int N, int K, void* out,
+                          long long ldo, void* stream) {
+  NEED(wq && scale && zero && out, "md_dequantize_weights");
+  return md::dequant_weights(bits, reinterpret_cast<const uint8_t*>(wq), scale, zero, N, K, BFM(out), ldo, STREAM(stream));
+}
+
+int md_linear_small_batch_quant(int bits, const void* x, long long ldx, const void* wq, const float* scale,
+                                const float* zero, int batch, int n_out, int K, int epilogue, const void* bias,
+                                const void* residual, long long ldr, void* out, long long ldo, void* workspace,
+                                void* stream) {
+  NEED(x && wq && scale && zero && out && workspace, "md_linear_small_batch_quant");
+  if (epilogue < 0 || epilogue > 2) return md::set_error("md_linear_small_batch_quant: bad epilogue");
+  const int used = md::gemm_smallbatch_quant(bits, reinterpret_cast<const uint8_t*>(wq), scale, zero, BF(x), ldx, n_out,
+                                             batch, K, 0, reinterpret_cast<float*>(workspace), STREAM(stream));
+  if (used < 0) return 1;
+  return md::splitk_epilogue(reinterpret_cast<const float*>(workspace), used, batch, n_out, epilogue,
+                             BF(bias), BF(residual), ldr, BFM(out), ldo, STREAM(stream));
+}
+
 int md_resample_u8(const uint8_t* src, int in_h, int in_w, int axis, const int* bounds, const int* coeffs, int ksize,
                    int out_size, uint8_t* dst, void* stream) {
   NEED(src && bounds && coeffs && dst, "md_resample_u8");
@@ -156,6 +175,12 @@ int md_model_create(const md_dims* dims, const void* const* weights, int n_weigh
 }
 
 void md_model_destroy(md_model* model) { delete static_cast<md::Model*>(model); }
+
+int md_model_set_quantized_block(md_model* model, int layer, int bits, const void* w1q, const float* w1_scale,
+                                 const float* w1_zero, const void* w2q, const float* w2_scale, const float* w2_zero) {
+  NEED(model, "md_model_set_quantized_block");
+  return md::model_set_quantized_block(*model, layer, bits, w1q, w1_scale, w1_zero, w2q, w2_scale, w2_zero);
+}
 
 long long md_vision_encode_workspace_bytes(const md_model* model, int n_crops) {
   return model ? md::vision_encode_ws_bytes(*model, n_crops) : -1;

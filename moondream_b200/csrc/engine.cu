@@ -88,6 +88,47 @@ int model_create(const md_dims& d, const void* const* w, int n, const void* lut,
   return 0;
 }
 
+// Quantised decoder blocks (layers.py:38-110): after this call for EVERY block, decode streams the packed bytes and
+// prefill dequantises block i into the scratch the bf16 pointers alias (they must all name the same W1 / W2 buffers).
+int model_set_quantized_block(Model& m, int layer, int bits, const void* w1q, const float* w1_scale, const float* w1_zero,
+                              const void* w2q, const float* w2_scale, const float* w2_zero) {
+  const md_dims& d = m.d;
+  if (layer < 0 || layer >= d.txt_layers) return set_error("md_model_set_quantized_block: layer out of range");
+  if (bits != 4 && bits != 8) return set_error("md_model_set_quantized_block: bits must be 4 or 8");
+  if (!d.txt_fused) return set_error("md_model_set_quantized_block: needs the fused decode layout");
+  if (d.txt_dim % 128 || d.txt_ff % 128) return set_error("md_model_set_quantized_block: txt_dim and txt_ff must be multiples of the group size 128");
+  if (!w1q || !w1_scale || !w1_zero || !w2q || !w2_scale || !w2_zero) return set_error("md_model_set_quantized_block: null pointer");
+  for (const void* p : {w1q, w2q, static_cast<const void*>(w1_scale), static_cast<const void*>(w1_zero),
+                        static_cast<const void*>(w2_scale), static_cast<const void*>(w2_zero)})
+    if (reinterpret_cast<uintptr_t>(p) & 15) return set_error("md_model_set_quantized_block: tensors must be 16-byte aligned");
+  if (m.txt[layer].qkv.w != m.txt[0].qkv.w || m.txt[layer].proj.w != m.txt[0].proj.w)
+    return set_error("md_model_set_quantized_block: the bf16 weight pointers of every decoder block must alias one scratch pair");
+  if (m.tq.empty()) m.tq.resize(d.txt_layers);
+  QuantBlock& q = m.tq[layer];
+  q.bits = bits;
+  q.w1q = reinterpret_cast<const uint8_t*>(w1q); q.w1s = w1_scale; q.w1z = w1_zero;
+  q.w2q = reinterpret_cast<const uint8_t*>(w2q); q.w2s = w2_scale; q.w2z = w2_zero;
+  return 0;
+}
+
+static int quant_ready(const Model& m) {
+  for (const QuantBlock& q : m.tq)
+    if (!q.bits) return set_error("quantised model: md_model_set_quantized_block has not been called for every block");
+  return 0;
+}
+
+// prefill under quantised weights: rebuild block i's bf16 W1 / W2 in the shared scratch (0.1 GB written per block
+// for the 2B, ~30 us; the row-form GEMMs that follow are compute-bound)
+static int dequant_block(Model& m, int i, cudaStream_t st) {
+  if (m.tq.empty()) return 0;
+  const md_dims& d = m.d;
+  const QuantBlock& q = m.tq[i];
+  const int D = d.txt_dim, FF = d.txt_ff, QKV = D + 2 * d.txt_kv_heads * 64;
+  const TxtBlock& b = m.txt[i];
+  if (dequant_weights(q.bits, q.w1q, q.w1s, q.w1z, QKV + FF, D, const_cast<bf16*>(b.qkv.w), D, st)) return 1;
+  return dequant_weights(q.bits, q.w2q, q.w2s, q.w2z, D, D + FF, const_cast<bf16*>(b.proj.w), D + FF, st);
+}
+
 // ------------------------------------------------------------------------------------------------
 // vision encoder
 // ------------------------------------------------------------------------------------------------
@@ -200,8 +241,10 @@ int text_prefill(Model& m, bf16* x, int T, const int* q_offsets, const int* star
   bf16* tmp = reinterpret_cast<bf16*>(p); p += pad256(1LL * T * D * 2);
   bf16* hid = reinterpret_cast<bf16*>(p);
   bf16* pool = reinterpret_cast<bf16*>(kv.pool);
+  if (!m.tq.empty() && quant_ready(m)) return 1;
   for (int i = 0; i < d.txt_layers; ++i) {
     const TxtBlock& b = m.txt[i];
+    if (dequant_block(m, i, st)) return 1;
     // l = ln(x); x = x + attn(l) + mlp(l)                       text.py:145-158
     if (layernorm(x, D, b.ln.w, b.ln.b, ln, D, T, D, 1e-5f, st)) return 1;
     // QKV projection with bias, RoPE and the KV-page write in the GEMM epilogue (no qkv round trip through HBM)
@@ -271,8 +314,10 @@ int text_prefill_lora(Model& m, bf16* x, int T, const int* q_offsets, const int*
     return gemm_rowform(t, rank, reinterpret_cast<const bf16*>(B), rank, T, N, rank, EPI_BIAS, nullptr, nullptr, 0, 0, u, N,
                         0, 0, 0, st);
   };
+  if (!m.tq.empty() && quant_ready(m)) return 1;
   for (int i = 0; i < d.txt_layers; ++i) {
     const TxtBlock& b = m.txt[i];
+    if (dequant_block(m, i, st)) return 1;
     const void* const* L = lora + 8 * i;            // A/B of qkv, proj, fc1, fc2
     for (int j = 0; j < 8; ++j)
       if (!L[j] || (reinterpret_cast<uintptr_t>(L[j]) & 15)) return set_error("md_text_prefill_lora: null or unaligned adapter tensor");
@@ -351,7 +396,9 @@ int text_decode_step(Model& m, bf16* x, const int* pos, int batch, const md_kv& 
   bf16* xcat = reinterpret_cast<bf16*>(p); p += pad256(1LL * batch * (D + FF) * 2);   // [att | gelu(fc1)]
   int* tail_counter = reinterpret_cast<int*>(p); p += 256;
   float* wsf = reinterpret_cast<float*>(p);
-  const bool tail = gemm_stream_tail_enabled(batch);
+  const bool quant = !m.tq.empty();
+  if (quant && quant_ready(m)) return 1;
+  const bool tail = !quant && gemm_stream_tail_enabled(batch);
   if (tail && cudaMemsetAsync(tail_counter, 0, 8, st) != cudaSuccess) return set_error("md_text_decode_step: memset failed");
   bf16* pool = reinterpret_cast<bf16*>(kv.pool);
   const StreamPlan2 pl2 = plan_smallbatch_2seg(D, D + FF, D);   // no split straddles proj | fc2
@@ -363,13 +410,17 @@ int text_decode_step(Model& m, bf16* x, const int* pos, int batch, const md_kv& 
     // KV-page write / GELU, which the attention kernel applies for its own (sequence, head).  (Fusing them into
     // the GEMM epilogue needs whole-K tiles, i.e. 112 streaming SMs instead of 148: measured slower, DESIGN.md.)
     int s1 = gemm_smallbatch_splits(QKV + FF, D);
-    if (!(g_debug_skip & 1)) s1 = gemm_smallbatch(b.qkv.w, D, ln, D, QKV + FF, batch, D, 0, wsf, st);
+    // K/V pages of earlier tokens are requested into L2 by the attention CTAs while this stream is still running
+    // (block 0 excepted: positions are written by the previous step's last kernel, only a few launches back)
+    const int early_pages = (KVH == H && i > 0 && !quant) ? decode_kv_prefetch_pages() : 0;
+    if (quant) s1 = gemm_smallbatch_quant(m.tq[i].bits, m.tq[i].w1q, m.tq[i].w1s, m.tq[i].w1z, ln, D, QKV + FF, batch, D, 0, wsf, st);
+    else if (!(g_debug_skip & 1)) s1 = gemm_smallbatch(b.qkv.w, D, ln, D, QKV + FF, batch, D, 0, wsf, st, early_pages > 0);
     if (s1 < 0) return 1;
     if (KVH == H) {
       // bias / RoPE / KV-row write / GELU of that stream happen inside the attention kernel (one launch fewer)
       if (!(g_debug_skip & 4) &&
           decode_attention_fused(wsf, s1, D, FF, b.qkv.b, m.rope, xcat + D, D + FF, H, pos, batch, pool, kv.n_pages,
-                                 kv.block_tables, kv.max_blocks, i, xcat, D + FF, st)) return 1;
+                                 kv.block_tables, kv.max_blocks, i, xcat, D + FF, st, early_pages)) return 1;
     } else {
       // grouped-query attention: the G query heads of a group share one new K/V row, so the stream is finished by
       // its own small kernel and the plain paged kernel reads KV head h / G
@@ -389,7 +440,8 @@ int text_decode_step(Model& m, bf16* x, const int* pos, int batch, const md_kv& 
                                     b.fc2.b, x, nln.w, nln.b, ln_dst, st) < 0) return 1;
       continue;
     }
-    if (!(g_debug_skip & 8)) s2 = gemm_smallbatch_2seg(b.proj.w, D + FF, xcat, D + FF, D, batch, D + FF, D, wsf, st);
+    if (quant) s2 = gemm_smallbatch_quant(m.tq[i].bits, m.tq[i].w2q, m.tq[i].w2s, m.tq[i].w2z, xcat, D + FF, D, batch, D + FF, D, wsf, st);
+    else if (!(g_debug_skip & 8)) s2 = gemm_smallbatch_2seg(b.proj.w, D + FF, xcat, D + FF, D, batch, D + FF, D, wsf, st);
     if (s2 < 0) return 1;
     if (!(g_debug_skip & 16) &&
         decode_residual_ln_epilogue(wsf, s2, proj_splits, batch, D, b.proj.b, b.fc2.b, x, nln.w, nln.b, ln_dst, st)) return 1;

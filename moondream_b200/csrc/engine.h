@@ -13,8 +13,17 @@ struct Lin { const bf16* w; const bf16* b; long long ld; };   // Linear (weight 
 struct VisBlock { Lin ln1, qkv, proj, ln2, fc1, fc2; };
 struct TxtBlock { Lin ln, qkv, proj, fc1, fc2; };
 
+// Weight-only quantised decoder block (gemm_quant.cu): packed stream tensors of W1 = [qkv ; fc1] and W2 = [proj | fc2];
+// the bf16 pointers of every TxtBlock then alias ONE scratch pair that prefill fills block by block.
+struct QuantBlock {
+  int bits = 0;                                    // 0 = not set
+  const uint8_t *w1q = nullptr, *w2q = nullptr;
+  const float *w1s = nullptr, *w1z = nullptr, *w2s = nullptr, *w2z = nullptr;
+};
+
 struct Model {
   md_dims d;
+  std::vector<QuantBlock> tq;                      // empty: bf16 decoder weights
   const bf16* lut;
   const float* rope;
   const bf16* pos_emb;
@@ -31,6 +40,8 @@ struct Model {
 
 int model_num_weights(const md_dims& d);
 int model_create(const md_dims& d, const void* const* w, int n, const void* lut, const float* rope, Model** out);
+int model_set_quantized_block(Model& m, int layer, int bits, const void* w1q, const float* w1_scale, const float* w1_zero,
+                              const void* w2q, const float* w2_scale, const float* w2_zero);
 
 long long vision_encode_ws_bytes(const Model& m, int n_crops);
 int vision_encode(Model& m, const uint8_t* crops, int n_crops, bf16* feats, void* ws, cudaStream_t st);

@@ -31,6 +31,7 @@ constexpr int kEpiWarps = 8;                        // two warps per TMEM lane q
 constexpr int kGemmThreads = 128 + kEpiWarps * 32;  // producer, MMA, TMEM-alloc, spare + epilogue
 
 static int g_gemm_debug = 0;            // md_debug_gemm: timing experiments only
+constexpr int kDefaultKvPrefetchPages = 0;   // decode attention's early K/V request (see decode_kv_prefetch_pages)
 static int g_gemm_sm_cap = 0;           // md_debug_gemm_sm_cap: 0 = every SM (default)
 
 struct GemmParams {
@@ -124,8 +125,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const GemmParams p) {
   using S = GemmSmem<BN, STAGES, CG>;
-  constexpr uint32_t kTmemCols = (2 * BN < 32) ? 32 : 2 * BN;  // power of two for BN in {32..256}
-  static_assert(BN == 32 || BN == 64 || BN == 128 || BN == 256, "BN must be a power of two");
+  // two accumulator stages; allocations are powers of two, so BN = 192 takes 512 columns with stage 1 at column 256
+  constexpr uint32_t kAccStride = (BN == 192) ? 256 : BN;
+  constexpr uint32_t kTmemCols = (2 * kAccStride < 32) ? 32 : 2 * kAccStride;
+  static_assert(BN == 32 || BN == 64 || BN == 128 || BN == 192 || BN == 256, "unsupported BN");
   static_assert(CG == 1 || CG == 2, "cta group");
 
   extern __shared__ uint8_t smem_raw[];
@@ -215,7 +218,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const uint32_t aphase = (it >> 1) & 1;
         mbar_wait(&tmem_empty[as], aphase ^ 1);
         tc_fence_after();
-        const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(as * BN);
+        const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(as) * kAccStride;
         for (int kb = 0; kb < p.k_blocks; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
@@ -276,7 +279,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       tc_fence_after();
       if (tl && threadIdx.x == 128) tl_s[3] = tl_now();                  // (last) accumulator complete
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
-                             static_cast<uint32_t>(as * BN);
+                             static_cast<uint32_t>(as) * kAccStride;
 
 #pragma unroll 1
       for (int c = half; c < BN / 32; c += 2) {
@@ -646,6 +649,25 @@ int make_tmap_bf16_2d(CUtensorMap* tm, const void* base, long long rows, long lo
   return 0;
 }
 
+// raw bytes, row-major [rows][row_bytes] with row pitch pitch_bytes; box = [box_rows, box_bytes], no swizzle
+// (staging tiles of packed int4 / int8 weights, gemm_quant.cu)
+int make_tmap_u8_2d(CUtensorMap* tm, const void* base, long long rows, long long row_bytes, long long pitch_bytes,
+                    int box_rows, int box_bytes) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return set_error("cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
+  if ((reinterpret_cast<uintptr_t>(base) & 15) || pitch_bytes % 16 || box_bytes % 16 || box_rows < 1 || box_rows > 256)
+    return set_error("TMA byte operand must be 16-byte aligned with 16-byte multiple pitch and box");
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(row_bytes), static_cast<cuuint64_t>(rows)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(pitch_bytes)};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(box_bytes), static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error("cuTensorMapEncodeTiled (bytes) failed");
+  return 0;
+}
+
 // ---- optional per-launch timing of the row-form GEMM (bench.py's roofline leg) ----
 struct GemmProfile {
   bool on = false;
@@ -768,7 +790,8 @@ static int dispatch_gemm(int bn, int cg, const CUtensorMap& tA, const CUtensorMa
                          cudaStream_t stream) {
   if (cg == 2) {
     if (bn == 256) return launch_gemm<256, 6, 2>(tA, tB, p, stream);
-    return set_error("pair GEMM needs BN = 256");
+    if (bn == 192) return launch_gemm<192, 7, 2>(tA, tB, p, stream);
+    return set_error("pair GEMM needs BN = 256 or 192");
   }
   switch (bn) {
     case 256: return launch_gemm<256, 4, 1>(tA, tB, p, stream);
@@ -777,6 +800,21 @@ static int dispatch_gemm(int bn, int cg, const CUtensorMap& tA, const CUtensorMa
     case 32: return launch_gemm<32, 10, 1>(tA, tB, p, stream);
   }
   return set_error("unsupported BN");
+}
+
+// Column-tile width of a pair GEMM: 256-wide tiles give the tensor pipe the longest uninterrupted run, but N = 1152
+// (ViT proj / fc2) fills only 4.5 of 5 such tiles and N = 3456 (ViT qkv) 13.5 of 14; 192-wide tiles divide both.  The
+// persistent kernel walks tiles round-robin over the CTA pairs, so time ~ waves x tile width; ties keep 256.
+// md_debug_gemm bit 7 restores 256 everywhere (A/B).
+static int pick_bn_pair(int M, int N) {
+  if (g_gemm_debug & 128) return 256;
+  const long long units = num_sms() / 2 > 0 ? num_sms() / 2 : 1;
+  const long long m_blocks = (M + 2 * BM - 1) / (2 * BM);
+  auto cost = [&](int bn) {
+    const long long tiles = m_blocks * ((N + bn - 1) / bn);
+    return ((tiles + units - 1) / units) * bn;
+  };
+  return cost(192) * 100 < cost(256) * 97 ? 192 : 256;      // take 192 only for a gain above 3 %
 }
 
 static int pick_bn_rows(int N) {
@@ -795,10 +833,11 @@ int gemm_rowform(const __nv_bfloat16* A, long long lda, const __nv_bfloat16* W, 
   if (N % 8 || K % 8) return set_error("gemm: N and K must be multiples of 8");
   if (mode == EPI_BIAS_RESIDUAL && !res) return set_error("gemm: residual mode without residual");
   if ((ldo % 8) || (res && (ldr % 8))) return set_error("gemm: ldo/ldr must be multiples of 8");
-  const int bn = pick_bn_rows(N);
+  int bn = pick_bn_rows(N);
   int cg = (bn == 256 && M > BM) ? 2 : 1;          // CTA pairs for the large prefill / ViT GEMMs
   if (g_force_cg == 1) cg = 1;
   if (g_force_cg == 2 && bn == 256) cg = 2;
+  if (cg == 2) bn = pick_bn_pair(M, N);
   CUtensorMap tA, tB;
   if (make_tmap_bf16_2d(&tA, A, M, K, lda, BM)) return 1;
   if (make_tmap_bf16_2d(&tB, W, N, K, ldw, bn / cg)) return 1;
@@ -895,7 +934,7 @@ StreamPlan plan_smallbatch(int n_out, int K, int kb_divisor, int m_rows) {
 static int gemm_smallbatch_impl(const __nv_bfloat16* W, long long ldw, const __nv_bfloat16* X, long long ldx,
                              int n_out, int batch, int K, int kb_per_split, int tile_n, float* ws,
                              cudaStream_t stream, int seg_kb = 0, int kb_per_split2 = 0,
-                             const StreamTail* tail = nullptr) {
+                             const StreamTail* tail = nullptr, int dependents_early = 0) {
   if (n_out <= 0 || batch <= 0 || K <= 0) { set_error("small-batch GEMM: empty problem"); return -1; }
   if (K % 8) { set_error("small-batch GEMM: K must be a multiple of 8"); return -1; }
   if (tile_n < 1 || tile_n > 256) tile_n = BM;
@@ -919,8 +958,11 @@ static int gemm_smallbatch_impl(const __nv_bfloat16* W, long long ldw, const __n
     p.seg_splits = p.k_splits; p.seg_kb = p.k_blocks; p.kb_per_split2 = kb_per_split;
   }
   p.tmem_cols = p.n_mma <= 32 ? 32 : p.n_mma <= 64 ? 64 : p.n_mma <= 128 ? 128 : 256;
-  p.trigger_early = g_pdl >= 2 ? 1 : 0;
+  p.trigger_early = (g_pdl >= 2 || (g_pdl && dependents_early)) ? 1 : 0;
   constexpr int kSbSmemMax = 227 * 1024 - 1024;      // leave room for the kernel's few static __shared__ words
+  // dependents_early: the consumer's CTAs (decode attention: ~6.4 KB of shared memory each) become resident beside
+  // this stream's CTA and request their K/V pages into L2 while the weights are still streaming
+  const int smem_budget = dependents_early ? kSbSmemMax - 36 * 1024 : kSbSmemMax;
   static DeviceOnce configured;
   if (configured.first()) {
     cudaError_t e = cudaFuncSetAttribute(smallbatch_gemm_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSbSmemMax);
@@ -954,7 +996,7 @@ static int gemm_smallbatch_impl(const __nv_bfloat16* W, long long ldw, const __n
     p.a_bytes = a_rows * BK * 2;                     // a multiple of 1024: the weight tile stays swizzle-aligned
     p.stage_bytes = p.a_bytes + p.n_mma * BK * 2;
     const int bar_bytes = (2 * kSbMaxStages + 1) * 8 + 16;
-    p.stages = (kSbSmemMax - 1024 - kSbTailPad - bar_bytes) / p.stage_bytes;
+    p.stages = (smem_budget - 1024 - kSbTailPad - bar_bytes) / p.stage_bytes;
     if (p.stages > kSbMaxStages) p.stages = kSbMaxStages;
     if (p.stages < 2) { set_error("small-batch GEMM: tile does not fit shared memory"); return -1; }
     p.ws = ws + static_cast<long long>(b0) * n_out;
@@ -989,10 +1031,18 @@ int gemm_smallbatch_splits(int n_out, int K) {
 }
 
 int gemm_smallbatch(const __nv_bfloat16* W, long long ldw, const __nv_bfloat16* X, long long ldx,
-                 int n_out, int batch, int K, int splits, float* ws, cudaStream_t stream) {
+                 int n_out, int batch, int K, int splits, float* ws, cudaStream_t stream, int dependents_early) {
   (void)splits;                                  // the plan decides (callers size ws with gemm_smallbatch_splits)
   const StreamPlan pl = plan_smallbatch(n_out, K, 0, (!(g_gemm_debug & 64) && batch <= 64) ? 64 : 128);
-  return gemm_smallbatch_impl(W, ldw, X, ldx, n_out, batch, K, pl.kb, pl.tile_rows, ws, stream);
+  return gemm_smallbatch_impl(W, ldw, X, ldx, n_out, batch, K, pl.kb, pl.tile_rows, ws, stream, 0, 0, nullptr,
+                              dependents_early);
+}
+
+// md_debug_gemm bits 8..11: K/V pages each decode-attention CTA requests into L2 before its dependency wait
+// (0 = the default below; 15 = off)
+int decode_kv_prefetch_pages() {
+  const int v = (g_gemm_debug >> 8) & 15;
+  return v == 15 ? 0 : (v ? v : kDefaultKvPrefetchPages);
 }
 
 int gemm_rowform_qkv_rope(const __nv_bfloat16* A, long long lda, const __nv_bfloat16* W, long long ldw, int M,

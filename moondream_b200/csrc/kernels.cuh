@@ -67,6 +67,8 @@ int make_tmap_bf16_2d(CUtensorMap* tm, const void* base, long long rows, long lo
                       long long ld, int box_rows);
 int make_tmap_bf16_3d(CUtensorMap* tm, const void* base, long long d0, long long d1, long long d2,
                       long long s1_bytes, long long s2_bytes, int b0, int b1, int b2, int swizzle_bytes);
+int make_tmap_u8_2d(CUtensorMap* tm, const void* base, long long rows, long long row_bytes, long long pitch_bytes,
+                    int box_rows, int box_bytes);
 int gemm_rowform(const __nv_bfloat16* A, long long lda, const __nv_bfloat16* W, long long ldw, int M,
                  int N, int K, int mode, const __nv_bfloat16* bias, const __nv_bfloat16* res,
                  long long ldr, int res_mod, __nv_bfloat16* out, long long ldo, int remap_gin,
@@ -80,7 +82,8 @@ struct StreamPlan { int tile_rows, kb, splits; };
 StreamPlan plan_smallbatch(int n_out, int K, int kb_divisor, int m_rows = 128);
 int gemm_smallbatch_splits(int n_out, int K);
 int gemm_smallbatch(const __nv_bfloat16* W, long long ldw, const __nv_bfloat16* X, long long ldx,
-                 int n_out, int batch, int K, int splits, float* ws, cudaStream_t stream);
+                 int n_out, int batch, int K, int splits, float* ws, cudaStream_t stream, int dependents_early = 0);
+int decode_kv_prefetch_pages();
 // Prefill QKV projection with RoPE and the KV-cache write fused into the GEMM epilogue (text.py:30-43,
 // rope.py:20-48, moondream.py:74-78): output column block -> (q|k|v, head, half-head); row -> (sequence, position).
 struct RopeEpilogue {
@@ -109,6 +112,12 @@ int gemm_smallbatch_2seg_tail(const __nv_bfloat16* W, long long ldw, const __nv_
 int splitk_epilogue(const float* ws, int splits, int B, int N, int mode, const __nv_bfloat16* bias,
                     const __nv_bfloat16* res, long long ldr, __nv_bfloat16* out, long long ldo,
                     cudaStream_t stream);
+
+// ---- gemm_quant.cu: weight-only int4 (group 128) / int8 decode weight stream (layers.py:38-110) ----
+int dequant_weights(int bits, const uint8_t* q, const float* scale, const float* zero, int N, int K,
+                    __nv_bfloat16* out, long long ldo, cudaStream_t stream);
+int gemm_smallbatch_quant(int bits, const uint8_t* Wq, const float* scale, const float* zero, const __nv_bfloat16* X,
+                          long long ldx, int n_out, int batch, int K, int seg_K, float* ws, cudaStream_t stream);
 
 // ---- elementwise.cu ----
 int layernorm(const __nv_bfloat16* x, long long ldx, const __nv_bfloat16* w, const __nv_bfloat16* b,
@@ -167,7 +176,7 @@ int decode_attention(const __nv_bfloat16* q, int n_heads, int n_kv_heads, const 
 int decode_attention_fused(const float* ws, int splits, int D, int FF, const __nv_bfloat16* bias, const float* freqs,
                            __nv_bfloat16* hid, long long ld_hid, int n_heads, const int* pos, int n_seqs,
                            __nv_bfloat16* kv_pool, int n_pages, const int* block_tables, int max_blocks, int layer,
-                           __nv_bfloat16* out, long long ld_out, cudaStream_t stream);
+                           __nv_bfloat16* out, long long ld_out, cudaStream_t stream, int early_pages = 0);
 int decode_qkv_finish(const float* ws, int splits, int B, int D, int n_kv_heads, int FF, const __nv_bfloat16* bias,
                       const float* freqs, const int* pos, __nv_bfloat16* q_out, __nv_bfloat16* kv_pool, int n_pages,
                       const int* block_tables, int max_blocks, int layer, __nv_bfloat16* hid, long long ld_hid,

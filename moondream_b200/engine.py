@@ -15,6 +15,7 @@ import numpy as np
 import torch
 
 from . import _native as N
+from . import quant as Q
 from .config import MoondreamConfig
 from .image_crops import crop_tiling, overlap_crop_image
 from .synth import state_dict_spec
@@ -55,15 +56,26 @@ def rope_table(head_dim: int, max_context: int, theta: float = 10000.0) -> torch
     return torch.stack([unit.real, unit.imag], dim=-1).contiguous()
 
 
-def prepare_weights(cfg: MoondreamConfig, sd: Dict[str, torch.Tensor]) -> Tuple[List[torch.Tensor], int, int]:
+_BLOCK_WEIGHT_SUFFIXES = ("attn.qkv.weight", "attn.proj.weight", "mlp.fc1.weight", "mlp.fc2.weight")
+
+
+def _is_block_weight(key: str) -> bool:
+    return key.startswith("text.blocks.") and key.endswith(_BLOCK_WEIGHT_SUFFIXES)
+
+
+def prepare_weights(cfg: MoondreamConfig, sd: Dict[str, torch.Tensor],
+                    quantized_blocks: bool = False) -> Tuple[List[Optional[torch.Tensor]], int, int]:
     """One-time re-layout so every GEMM operand is TMA-addressable (16-byte row pitch):
     patch_emb K 588 -> 592 and the ViT MLP width to a multiple of 8 (0.5B: 2690 -> 2696) with zero
     padding, which leaves the arithmetic unchanged (gelu(0) = 0 meets zero fc2 columns)."""
     v = cfg.vision
     patch_k = _round_up(v.patch_dim, 8)
     vis_ff = _round_up(v.enc_ff_dim, 8)
-    out: List[torch.Tensor] = []
+    out: List[Optional[torch.Tensor]] = []
     for key, shape, _ in state_dict_spec(cfg):
+        if quantized_blocks and _is_block_weight(key):
+            out.append(None)                 # lives in packed form (quant.QuantizedText); bf16 scratch on the device
+            continue
         if key not in sd:
             raise KeyError(f"state dict is missing {key}")
         t = sd[key].to(torch.bfloat16)
@@ -82,7 +94,8 @@ def prepare_weights(cfg: MoondreamConfig, sd: Dict[str, torch.Tensor]) -> Tuple[
     return out, patch_k, vis_ff
 
 
-def upload_weights(cfg: MoondreamConfig, prepared: List[torch.Tensor], device) -> Tuple[List[torch.Tensor], list]:
+def upload_weights(cfg: MoondreamConfig, prepared: List[Optional[torch.Tensor]], device,
+                   quantized_blocks: bool = False) -> Tuple[List[torch.Tensor], list]:
     """Upload in canonical order.  The decoder blocks use the fused decode layout the C runtime checks
     (md_dims.txt_fused): W1 = [qkv.weight ; fc1.weight], b1 = [qkv.bias ; fc1.bias] and
     W2 = [proj.weight | fc2.weight]; the canonical entries become views of those buffers, so prefill
@@ -92,13 +105,25 @@ def upload_weights(cfg: MoondreamConfig, prepared: List[torch.Tensor], device) -
     dev: List[Optional[torch.Tensor]] = [None] * len(keys)
     owners = []
     D = cfg.text.dim
+    FF = cfg.text.ff_dim
     Q = D + 2 * cfg.text.n_kv_heads * cfg.text.head_dim          # rows of qkv.weight (text.py:36-38)
+    scratch = None
+    if quantized_blocks:
+        # packed decoder blocks (quant.py): every block's bf16 pointers alias ONE scratch pair that prefill rebuilds
+        # block by block (md_model_set_quantized_block)
+        scratch = (torch.zeros((Q + FF, D), dtype=torch.bfloat16, device=device),
+                   torch.zeros((D, D + FF), dtype=torch.bfloat16, device=device))
+        owners += list(scratch)
     for i in range(cfg.text.n_layers):
         p = f"text.blocks.{i}."
-        w1 = torch.cat([prepared[idx[p + "attn.qkv.weight"]], prepared[idx[p + "mlp.fc1.weight"]]], 0).to(device)
         b1 = torch.cat([prepared[idx[p + "attn.qkv.bias"]], prepared[idx[p + "mlp.fc1.bias"]]], 0).to(device)
-        w2 = torch.cat([prepared[idx[p + "attn.proj.weight"]], prepared[idx[p + "mlp.fc2.weight"]]], 1).to(device)
-        owners += [w1, b1, w2]
+        if scratch is not None:
+            w1, w2 = scratch
+            owners += [b1]
+        else:
+            w1 = torch.cat([prepared[idx[p + "attn.qkv.weight"]], prepared[idx[p + "mlp.fc1.weight"]]], 0).to(device)
+            w2 = torch.cat([prepared[idx[p + "attn.proj.weight"]], prepared[idx[p + "mlp.fc2.weight"]]], 1).to(device)
+            owners += [w1, b1, w2]
         dev[idx[p + "attn.qkv.weight"]] = w1[:Q]
         dev[idx[p + "mlp.fc1.weight"]] = w1[Q:]
         dev[idx[p + "attn.qkv.bias"]] = b1[:Q]
@@ -215,8 +240,14 @@ class Engine:
     _MAX_DECODE_STATES = 4
 
     def __init__(self, cfg: MoondreamConfig, state_dict: Dict[str, torch.Tensor], device="cuda",
-                 kv_pages: Optional[int] = None, max_batch: int = 32):
+                 kv_pages: Optional[int] = None, max_batch: int = 32, quantize: Optional[str] = None):
+        """quantize: None (bf16 decoder weights; a state dict in the reference's int4 QuantizedLinear format is
+        detected by its ``.weight.packed`` keys), or "int4" / "int8": quantise the decoder blocks of a bf16 state
+        dict at load time (quant.quantize_decoder) and stream them packed."""
         cfg.validate()
+        if quantize not in (None, "int4", "int8"):
+            raise ValueError('quantize must be None, "int4" or "int8"')
+        self._quantize = quantize
         if not torch.cuda.is_available():
             raise N.NativeError("moondream_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
         self.cfg = cfg
@@ -235,8 +266,16 @@ class Engine:
             self.lib.md_debug_set_pdl(int(_os0.environ["MD_PDL"]))
         if _os0.environ.get("MD_DEBUG_GEMM") is not None:
             self.lib.md_debug_gemm(int(_os0.environ["MD_DEBUG_GEMM"]))
-        prepared, self.patch_k, self.vis_ff = prepare_weights(cfg, state_dict)
-        self.weights, self._owners = upload_weights(cfg, prepared, self.device)   # keeps device memory alive
+        if _os0.environ.get("MD_ATTENTION_IMPL") is not None:
+            self.lib.md_debug_attention_impl(int(_os0.environ["MD_ATTENTION_IMPL"]))
+        self.quantized: Optional[Q.QuantizedText] = None
+        if Q.is_quantized_checkpoint(state_dict):
+            self.quantized, state_dict = Q.from_reference_checkpoint(cfg, state_dict)
+        elif self._quantize is not None:
+            self.quantized, _ = Q.quantize_decoder(cfg, state_dict, 4 if self._quantize == "int4" else 8)
+        qb = self.quantized is not None
+        prepared, self.patch_k, self.vis_ff = prepare_weights(cfg, state_dict, quantized_blocks=qb)
+        self.weights, self._owners = upload_weights(cfg, prepared, self.device, quantized_blocks=qb)   # keeps device memory alive
         del prepared
         self.lut = pixel_lut().to(self.device)
         self.rope = rope_table(cfg.text.head_dim, cfg.text.max_context).to(self.device)
@@ -256,6 +295,12 @@ class Engine:
         N.check(self.lib.md_model_create(ctypes.byref(self.dims), arr, n, N.ptr(self.lut),
                                          N.ptr(self.rope), ctypes.byref(handle)), "md_model_create")
         self.model = handle
+        if self.quantized is not None:
+            for i in range(t.n_layers):
+                dev = [x.to(self.device) for x in self.quantized.fused(i)]
+                self._owners += dev
+                N.check(self.lib.md_model_set_quantized_block(self.model, i, self.quantized.bits, *[N.ptr(x) for x in dev]),
+                        "md_model_set_quantized_block")
         self.max_blocks = t.max_context // PAGE
         if kv_pages is None:
             kv_pages = max_batch * self.max_blocks

@@ -68,7 +68,10 @@ def _as_array(image) -> np.ndarray:
 
 class MoondreamModel:
     def __init__(self, config: MoondreamConfig, dtype=torch.bfloat16, setup_caches: bool = True,
-                 tokenizer=None, device: str = "cuda", max_batch: int = 32, kv_pages: Optional[int] = None):
+                 tokenizer=None, device: str = "cuda", max_batch: int = 32, kv_pages: Optional[int] = None,
+                 quantize: Optional[str] = None):
+        """quantize: None, "int4" or "int8" — quantise the decoder blocks of a bf16 checkpoint at load time.  A
+        checkpoint already in the reference's int4 QuantizedLinear format (layers.py:47-110) is detected by its keys."""
         if dtype != torch.bfloat16:
             raise ValueError("the path is bf16 end to end, like the reference (vision.py:36, weights.py:32)")
         self.config = config
@@ -76,6 +79,7 @@ class MoondreamModel:
         self._tokenizer = tokenizer
         self._max_batch = max_batch
         self._kv_pages = kv_pages
+        self._quantize = quantize
         self._variants: Dict[str, Any] = {}
         self._engine: Optional[Engine] = None
 
@@ -123,7 +127,7 @@ class MoondreamModel:
     def load_state_dict(self, state_dict: Dict[str, torch.Tensor], strict: bool = False):
         sd = {k.replace("model.", "", 1) if k.startswith("model.") else k: v for k, v in state_dict.items()}
         self._engine = Engine(self.config, sd, device=self._device, kv_pages=self._kv_pages,
-                              max_batch=self._max_batch)
+                              max_batch=self._max_batch, quantize=self._quantize)
         self._seam = None
         return [], []
 

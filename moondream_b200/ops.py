@@ -50,3 +50,29 @@ def linear_small_batch(x, w, bias=None, epilogue=EPI_BIAS, residual=None, out=No
         N.ptr(residual), ldr, N.ptr(out), out.stride(0), N.ptr(workspace), N.current_stream())
     N.check(rc, "md_linear_small_batch_bf16")
     return out
+
+
+def dequantize_weights(bits, wq, scale, zero, n_out, K, out=None):
+    """bf16 [n_out, K] = bf16(bf16(q - zero) * scale) from stream-layout packed weights (md_dequantize_weights)."""
+    _req(wq, torch.uint8), _req(scale, torch.float32), _req(zero, torch.float32)
+    if out is None:
+        out = torch.empty((n_out, K), device=wq.device, dtype=torch.bfloat16)
+    N.check(N.lib().md_dequantize_weights(bits, N.ptr(wq), N.ptr(scale), N.ptr(zero), n_out, K, N.ptr(out), out.stride(0),
+                                          N.current_stream()), "md_dequantize_weights")
+    return out
+
+
+def linear_small_batch_quant(bits, x, wq, scale, zero, n_out, bias=None, epilogue=EPI_BIAS, residual=None, out=None):
+    """linear_small_batch with int4 (group 128) / int8 weights in the stream layout (md_linear_small_batch_quant)."""
+    _req(x), _req(wq, torch.uint8), _req(scale, torch.float32), _req(zero, torch.float32)
+    B, K = x.shape
+    if out is None:
+        out = torch.empty((B, n_out), device=x.device, dtype=torch.bfloat16)
+    need = N.lib().md_linear_small_batch_workspace_bytes(n_out, B, K)
+    workspace = torch.empty(need // 4, device=x.device, dtype=torch.float32)
+    ldr = residual.stride(0) if residual is not None else 0
+    N.check(N.lib().md_linear_small_batch_quant(
+        bits, N.ptr(x), x.stride(0), N.ptr(wq), N.ptr(scale), N.ptr(zero), B, n_out, K, epilogue, N.ptr(bias),
+        N.ptr(residual), ldr, N.ptr(out), out.stride(0), N.ptr(workspace), N.current_stream()),
+        "md_linear_small_batch_quant")
+    return out

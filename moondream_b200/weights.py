@@ -97,6 +97,13 @@ def normalize_state_dict(cfg: MoondreamConfig, keys: Iterable[str],
             out[new] = get(stripped[old]).T
     result: Dict[str, torch.Tensor] = {}
     for key, shape, _ in state_dict_spec(cfg):
+        if key + ".packed" in out:
+            # a QuantizedLinear of the reference's int4 checkpoints (layers.py:58-76): packed uint8 + fp32 scale /
+            # zero_point per group of 128 travel as they are; moondream_b200.quant re-lays them out for the engine
+            result[key + ".packed"] = out[key + ".packed"].to(torch.uint8).contiguous()
+            result[key + ".scale"] = out[key + ".scale"].to(torch.float32).contiguous()
+            result[key + ".zero_point"] = out[key + ".zero_point"].to(torch.float32).contiguous()
+            continue
         if key not in out:
             raise KeyError(f"checkpoint is missing {key}")
         t = out[key].to(torch.bfloat16).contiguous()

@@ -89,6 +89,34 @@ def stitch_crops(local: Tensor, tiling: Tuple[int, int], margin: int) -> Tensor:
 # --------------------------------------------------------------------------------------------
 # primitives (moondream/torch/layers.py, rope.py)
 # --------------------------------------------------------------------------------------------
+def dequantize_tensor(W_q: Tensor, scale: Tensor, zero: Tensor, orig_shape, dtype=torch.bfloat16) -> Tensor:
+    """layers.py:38-44 (`dequantize_tensor`, the unpacking of an int4 group-128 `QuantizedLinear`): rows [0, step) of
+    the result are the high nibbles of `W_q`, rows [step, 2 step) the low nibbles (one row per group of 128 input
+    features); `W_r.sub_(zero).mul_(scale)` runs on a `dtype` tensor with fp32 [groups, 1] parameters, so each step is
+    evaluated in fp32 and rounded to `dtype`."""
+    step = W_q.shape[0]
+    W_r = torch.empty([2 * step, W_q.shape[1]], dtype=dtype)
+    W_r[:step] = ((W_q & 0b11110000) >> 4).to(dtype)
+    W_r[step:] = (W_q & 0b00001111).to(dtype)
+    W_r = (W_r.to(torch.float32) - zero.to(torch.float32)).to(dtype)
+    W_r = (W_r.to(torch.float32) * scale.to(torch.float32)).to(dtype)
+    return W_r.reshape(orig_shape)
+
+
+def dequantized_state_dict(sd: Dict[str, Tensor]) -> Dict[str, Tensor]:
+    """A state dict holding reference-format int4 entries (`X.weight.packed / .scale / .zero_point`, layers.py:58-76)
+    -> the bf16 state dict `QuantizedLinear.unpack` builds from it (layers.py:79-99; the torchao re-quantisation that
+    follows, :102, needs a library this image does not have: SURVEY.md section 8c defines parity on these weights)."""
+    out = {k: v for k, v in sd.items() if ".weight." not in k}
+    for k, v in sd.items():
+        if k.endswith(".weight.packed"):
+            base = k[: -len(".packed")]
+            out_f = sd[base[: -len("weight")] + "bias"].numel()
+            in_f = v.numel() * 2 // out_f
+            out[base] = dequantize_tensor(v, sd[base + ".scale"], sd[base + ".zero_point"], (out_f, in_f))
+    return out
+
+
 def _lin(x: Tensor, w: Dict[str, Tensor], prefix: str) -> Tensor:
     """layers.py:34-35 / nn.Linear."""
     return F.linear(x, w[prefix + ".weight"], w[prefix + ".bias"])

@@ -31,7 +31,7 @@ def test_binding_table_matches_header():
 
     assert N.exported_symbols() == _header_functions()
     lib = N.lib()
-    assert lib.md_abi_version() == 2
+    assert lib.md_abi_version() == 3
     assert lib.md_linear_small_batch_splits(2048, 8192) >= 1
 
 

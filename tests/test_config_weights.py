@@ -53,8 +53,9 @@ def test_validate_rejects_what_the_kernels_do_not_implement():
     bad = C.MoondreamConfig(text=C.TextConfig(dim=1024, n_heads=16))       # the md05 JSON's missing n_kv_heads
     with pytest.raises(ValueError):
         bad.validate()
+    C.MoondreamConfig(text=C.TextConfig(group_size=128)).validate()          # int4 QuantizedLinear blocks (layers.py:54)
     with pytest.raises(ValueError):
-        C.MoondreamConfig(text=C.TextConfig(group_size=128)).validate()
+        C.MoondreamConfig(text=C.TextConfig(group_size=64)).validate()       # the reference hard-codes 128
     with pytest.raises(ValueError):
         C.preset("no-such-model")
 
