@@ -105,6 +105,16 @@ int md_extract_windows_u8(const uint8_t* canvas, int h, int w, int rows, int col
                           void* stream);
 
 /* y = LayerNorm(x) * w + b, eps 1e-5, fp32 statistics (layers.py:118-119). dim % 8 == 0, <= 4096. */
+/* prepare_crops' normalisation + create_patches (vision.py:36-40, 44-61): crops uint8 NHWC [n_crops, crop, crop, 3] ->
+ * patches bf16 [n_crops * (crop / patch)^2, k_pad], feature order (channel, row, column) as the reference's
+ * reshape/permute produces, columns [3 * patch^2, k_pad) zero; pixel_lut = bf16[256], the reference's op chain per byte. */
+int md_patchify_u8(const uint8_t* crops, int n_crops, int crop, int patch, int k_pad, const void* pixel_lut, void* out,
+                   void* stream);
+/* reconstruct_from_crops(patch_size = 1) + adaptive_avg_pool2d + concat (image_crops.py:170-231, vision.py:83-88) for a
+ * batch: feats bf16 [sum crops * grid^2, dim] (crop 0 of each image = global) -> out bf16 [n_images * grid^2, 2 * dim]
+ * = [global | pooled stitched local]; crop_offsets [n_images + 1], tilings [n_images][2] (device int32). */
+int md_stitch_pool_concat_bf16(const void* feats, const int* crop_offsets, const int* tilings, int n_images, int grid,
+                               int margin, int dim, void* out, void* stream);
 int md_layernorm_bf16(const void* x, long long ldx, const void* w, const void* b, void* y,
                       long long ldy, int rows, int dim, void* stream);
 
@@ -142,7 +152,7 @@ int md_prefill_attention_bf16(const void* q, int n_heads, int total_tokens, cons
                               const int* start_pos, int n_seqs, int max_q, int prefix_len,
                               const md_kv* kv, int layer, void* out, void* stream);
 /* Testing / A-B timing only: 0 = tcgen05 attention (default), 1 = the legacy mma.sync kernel, 2 = tcgen05 attention with
- * 3 of every 8 exponentials of the softmax evaluated on the FMA pipe (cubic) instead of MUFU.EX2. */
+ * two softmax warpgroups per CTA (each owns half of a score tile's keys and half of the O columns). */
 void md_debug_attention_impl(int impl);
 /* Testing / A-B timing only: programmatic dependent launch between consecutive kernels (default on). */
 void md_debug_set_pdl(int enable);
@@ -151,9 +161,8 @@ void md_debug_set_pdl(int enable);
 void md_debug_skip_decode_kernels(int mask);
 /* Timing experiments only, small-batch weight stream:
  * bit2 previous split plan of the [proj | fc2] stream (equal splits); bit3 previous plan of the single-segment streams
- * (tiles <= 128 rows; the default is the operand-read cost model: tiles up to 256 rows + K splits); bit4 lets the last
- * CTAs of the [proj | fc2] stream finish the residual + LayerNorm rows (no separate epilogue launch); bit6 forces M = 128 MMAs for batches <= 64
- * (the default there is M = 64).  Other bits are ignored. */
+ * (tiles <= 128 rows; the default is the operand-read cost model: tiles up to 256 rows + K splits); bit6 forces
+ * M = 128 MMAs for batches <= 64 (the default there is M = 64).  Other bits are ignored. */
 void md_debug_gemm(int flags);
 /* Experiments only: cap the persistent row-form GEMM's grid at `sms` SMs (0 = all, the default), leaving the others
  * to kernels of a concurrent stream (encode / decode overlap). */

@@ -52,6 +52,8 @@ _SIGNATURES = {
                                             _LL, _P, _P]),
     "md_resample_u8": (c_int, [_P, c_int, c_int, c_int, _P, _P, c_int, c_int, _P, _P]),
     "md_extract_windows_u8": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P]),
+    "md_patchify_u8": (c_int, [_P, c_int, c_int, c_int, c_int, _P, _P, _P]),
+    "md_stitch_pool_concat_bf16": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, _P, _P]),
     "md_layernorm_bf16": (c_int, [_P, _LL, _P, _P, _P, _LL, c_int, c_int, _P]),
     "md_vit_attention_bf16": (c_int, [_P, c_int, c_int, c_int, _P, _P]),
     "md_rope_kv_write_bf16": (c_int, [_P, c_int, c_int, _P, _P, c_int, _P, _P, _KV, c_int, _P]),

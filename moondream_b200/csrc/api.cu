@@ -106,6 +106,21 @@ int md_extract_windows_u8(const uint8_t* canvas, int h, int w, int rows, int col
   return md::extract_windows_u8(canvas, h, w, rows, cols, stride, crop, crops, STREAM(stream));
 }
 
+int md_patchify_u8(const uint8_t* crops, int n_crops, int crop, int patch, int k_pad, const void* pixel_lut, void* out,
+                   void* stream) {
+  NEED(crops && pixel_lut && out, "md_patchify_u8");
+  if (n_crops <= 0 || patch <= 0 || crop % patch || k_pad < 3 * patch * patch || k_pad % 8)
+    return md::set_error("md_patchify_u8: bad geometry");
+  return md::patchify(crops, n_crops, crop, patch, k_pad, BF(pixel_lut), BFM(out), STREAM(stream));
+}
+
+int md_stitch_pool_concat_bf16(const void* feats, const int* crop_offsets, const int* tilings, int n_images, int grid,
+                               int margin, int dim, void* out, void* stream) {
+  NEED(feats && crop_offsets && tilings && out, "md_stitch_pool_concat_bf16");
+  if (n_images <= 0 || grid <= 0 || dim % 8) return md::set_error("md_stitch_pool_concat_bf16: bad geometry");
+  return md::stitch_pool_concat(BF(feats), crop_offsets, tilings, n_images, grid, margin, dim, BFM(out), STREAM(stream));
+}
+
 int md_layernorm_bf16(const void* x, long long ldx, const void* w, const void* b, void* y,
                       long long ldy, int rows, int dim, void* stream) {
   NEED(x && w && b && y, "md_layernorm_bf16");

@@ -356,32 +356,13 @@ __global__ void __launch_bounds__(128, 7)
 decode_attention_kernel(const __nv_bfloat16* __restrict__ q, int n_heads, int n_kv_heads, const int* __restrict__ pos,
                         __nv_bfloat16* __restrict__ kv_pool, int n_pages,
                         const int* __restrict__ block_tables, int max_blocks, int layer,
-                        __nv_bfloat16* __restrict__ out, long long ld_out, float scale_log2, const DecodeFuse fz,
-                        int early_pages) {
+                        __nv_bfloat16* __restrict__ out, long long ld_out, float scale_log2, const DecodeFuse fz) {
   // all CTAs of this grid are resident at once, so the trigger fires immediately: the next kernel (the
   // [proj|fc2] weight stream) may start prefetching weights while this one is streaming K/V
   const bool tl = tl_on() && threadIdx.x == 0;
   __shared__ unsigned long long tl_s[4];               // debug timeline stamps (thread 0 only; smem keeps them out of registers)
   if (tl) tl_s[0] = tl_now();
   pdl_launch_dependents();
-  if (early_pages > 0) {
-    // K/V rows of EARLIER tokens do not depend on this step's [qkv ; fc1] stream (the predecessor, which released
-    // this grid at its start): ask for the first pages of this (sequence, head) now, so that HBM keeps working
-    // through the stream's drain, the hand-over and the prologue below (~9 us of an otherwise idle memory system
-    // per decoder block, tools/decode_timeline.py).  Positions and block tables were written before this step's
-    // first block (engine.cu passes early_pages = 0 for block 0).
-    const int cur0 = pos[blockIdx.y];
-    const int t_page = threadIdx.x >> 1, plane = threadIdx.x & 1;
-    const int rows = min(kPageTokens, cur0 - t_page * kPageTokens);        // rows of tokens < cur0 in that page
-    if (t_page < early_pages && rows > 0) {
-      const int kvh = FUSED ? blockIdx.x : blockIdx.x / (n_heads / n_kv_heads);
-      const int page = block_tables[static_cast<long long>(blockIdx.y) * max_blocks + t_page];
-      const __nv_bfloat16* src = kv_pool +
-          ((static_cast<long long>(layer) * n_pages + page) * 2 + plane) * n_kv_heads * (kPageTokens * 64) +
-          static_cast<long long>(kvh) * (kPageTokens * 64);
-      prefetch_l2_bulk(src, static_cast<uint32_t>(rows) * 128u);
-    }
-  }
   pdl_wait();
   if (tl) tl_s[1] = tl_now();
   const int head = blockIdx.x, seq = blockIdx.y;
@@ -569,7 +550,7 @@ int decode_attention(const __nv_bfloat16* q, int n_heads, int n_kv_heads, const 
   count_launch();
   cudaError_t e = launch_k(decode_attention_kernel<false>, grid, dim3(128), 0, stream, q, n_heads, n_kv_heads, pos,
                            const_cast<__nv_bfloat16*>(kv_pool), n_pages, block_tables, max_blocks, layer, out, ld_out,
-                           0.125f * 1.4426950408889634f, DecodeFuse{}, 0);
+                           0.125f * 1.4426950408889634f, DecodeFuse{});
   if (e != cudaSuccess) return set_error(cudaGetErrorString(e));
   return 0;
 }
@@ -578,7 +559,7 @@ int decode_attention(const __nv_bfloat16* q, int n_heads, int n_kv_heads, const 
 int decode_attention_fused(const float* ws, int splits, int D, int FF, const __nv_bfloat16* bias, const float* freqs,
                            __nv_bfloat16* hid, long long ld_hid, int n_heads, const int* pos, int n_seqs,
                            __nv_bfloat16* kv_pool, int n_pages, const int* block_tables, int max_blocks, int layer,
-                           __nv_bfloat16* out, long long ld_out, cudaStream_t stream, int early_pages) {
+                           __nv_bfloat16* out, long long ld_out, cudaStream_t stream) {
   if (n_seqs <= 0) return set_error("decode_attention: empty batch");
   if (FF % n_heads || (FF / n_heads) % 2) return set_error("decode_attention_fused: FF must split evenly over the heads");
   DecodeFuse fz{ws, splits, n_seqs, D, FF, bias, freqs, hid, ld_hid};
@@ -586,7 +567,7 @@ int decode_attention_fused(const float* ws, int splits, int D, int FF, const __n
   count_launch();
   cudaError_t e = launch_k(decode_attention_kernel<true>, grid, dim3(128), 0, stream,
                            static_cast<const __nv_bfloat16*>(nullptr), n_heads, n_heads, pos, kv_pool, n_pages, block_tables,
-                           max_blocks, layer, out, ld_out, 0.125f * 1.4426950408889634f, fz, early_pages);
+                           max_blocks, layer, out, ld_out, 0.125f * 1.4426950408889634f, fz);
   if (e != cudaSuccess) return set_error(cudaGetErrorString(e));
   return 0;
 }

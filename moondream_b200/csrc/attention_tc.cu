@@ -30,10 +30,15 @@ constexpr int kKVBytes = BN * HD * 2;           // 16 KB each for K and V
 constexpr int kPBytes = BM * BN * 2;            // 32 KB (two 64-key blocks of [128 x 64])
 constexpr int kSmemTiles = kQBytes + kStages * 2 * kKVBytes + kPBytes;   // 112 KB
 constexpr int kSmemTotal = kSmemTiles + 256;   // two CTAs per SM: 2 x (kSmemTotal + 1 KB reserved) <= 228 KB
-constexpr int kThreads = 192;
+constexpr int kThreads1 = 192, kThreads2 = 320;   // one / two softmax warpgroups (see the kernel's softmax section)
 constexpr uint32_t kTmemCols = 256;
 constexpr uint32_t kColS = 0, kColO = 128;
 }  // namespace fa
+
+// named barrier among the softmax warps only (ids 1..15; 0 is __syncthreads)
+__device__ __forceinline__ void softmax_bar_sync(int threads) {
+  asm volatile("bar.sync 1, %0;" ::"r"(threads) : "memory");
+}
 
 
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -65,30 +70,10 @@ __device__ __forceinline__ float chunk_max(const uint32_t (&v)[32], bool full, i
   return fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
 }
 
-// 2^x for x <= 0 on the FMA pipe (no MUFU): x = n + f with n = round(x) taken from the low mantissa bits of
-// x + 1.5 * 2^23 and f in [-0.5, 0.5]; 2^f by a minimax cubic (relative error <= 7.5e-5, a fiftieth of a bf16 ulp:
-// the result is rounded to bf16 right after); 2^n by adding n to the exponent field.
-// The softmax of these kernels is bound by the 16 MUFU results per clock an SM produces: a
-// 128 x 128 score tile needs 16384 exponentials = 1024 clocks against 512 clocks of tensor work, so 3 of every 8
-// pairs are computed here instead, which evens out the MUFU and issue budgets.
-__device__ __forceinline__ float2 exp2_fma2(float2 x) {
-  const float kMagic = 12582912.f;                       // 1.5 * 2^23
-  x.x = fmaxf(x.x, -125.f);
-  x.y = fmaxf(x.y, -125.f);
-  const float2 t = fadd2(x, make_float2(kMagic, kMagic));
-  const float2 n = fadd2(t, make_float2(-kMagic, -kMagic));
-  const float2 f = ffma2(n, make_float2(-1.f, -1.f), x);
-  float2 q = ffma2(f, make_float2(0.05517146f, 0.05517146f), make_float2(0.24261086f, 0.24261086f));
-  q = ffma2(q, f, make_float2(0.69326099f, 0.69326099f));
-  q = ffma2(q, f, make_float2(0.99992809f, 0.99992809f));
-  return make_float2(__int_as_float(__float_as_int(q.x) + (__float_as_int(t.x) << 23)),
-                     __int_as_float(__float_as_int(q.y) + (__float_as_int(t.y) << 23)));
-}
-
 // exp2(s * scale - base) for one 32-score chunk -> bf16 -> four swizzled 16-byte chunks of the row's
 // 128-byte line (chunk slots chunk0 .. chunk0+3); returns the row-sum contribution.
-// POLY: pairs 1, 2, 5 of every 8 go through exp2_fma2 instead of MUFU.EX2.
-template <bool POLY>
+// (An FMA-pipe polynomial for 3 of every 8 exponential pairs was measured and removed: no gain, the kernels are
+// latency- not MUFU-bound; profiles/r02_attention_ab.json.)
 __device__ __forceinline__ float chunk_probs(const uint32_t (&v)[32], bool full, int k_first, int kv_len, int qpos,
                                              int prefix_len, float scale_log2, float base, uint8_t* line,
                                              int chunk0, int r) {
@@ -101,9 +86,8 @@ __device__ __forceinline__ float chunk_probs(const uint32_t (&v)[32], bool full,
     for (int i = 0; i < 16; i += 2) {
       const float2 x0 = ffma2(make_float2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1])), sc, nb);
       const float2 x1 = ffma2(make_float2(__uint_as_float(v[2 * i + 2]), __uint_as_float(v[2 * i + 3])), sc, nb);
-      // i is a compile-time constant after unrolling: pairs i = 2, 10 and i + 1 = 1, 5, 9, 13 take the FMA-pipe path
-      const float2 e0 = (POLY && (i & 7) == 2) ? exp2_fma2(x0) : make_float2(ex2_approx(x0.x), ex2_approx(x0.y));
-      const float2 e1 = (POLY && (i & 3) == 0) ? exp2_fma2(x1) : make_float2(ex2_approx(x1.x), ex2_approx(x1.y));
+      const float2 e0 = make_float2(ex2_approx(x0.x), ex2_approx(x0.y));
+      const float2 e1 = make_float2(ex2_approx(x1.x), ex2_approx(x1.y));
       s01 = fadd2(s01, e0);
       s23 = fadd2(s23, e1);
       pk[i] = pack_bf16x2(e0.x, e0.y);
@@ -141,8 +125,14 @@ struct FaTcParams {
   float scale_log2;
 };
 
-template <bool POLY>
-__global__ void __launch_bounds__(fa::kThreads, 2)
+// GROUPS = 2: two softmax warpgroups (warps 2-5 and 6-9) share every S tile.  Both compute the row maximum over all 128
+// keys (cheap: TMEM reads and FMNMX), then each turns ITS 64 keys into probabilities, rescales ITS half of the O
+// columns and stores ITS half of the output: the exponentials, conversions, shared-memory stores and the O round trip —
+// the long dependent chain a single warp per SM sub-partition could not hide (tensor pipe 17-21 % with GROUPS = 1,
+// profiles/r02_ncu_decode_summary.json) — run on twice as many warps with no synchronisation between the groups
+// until the final row sums are added.
+template <int GROUPS>
+__global__ void __launch_bounds__(64 + 128 * GROUPS, 2)
 fa_tc_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
                      const FaTcParams p) {
   using namespace fa;
@@ -186,8 +176,8 @@ fa_tc_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     mbar_init(q_full, 1);
     for (int i = 0; i < kStages; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
     mbar_init(s_full, 1);
-    mbar_init(s_empty, 128);
-    mbar_init(p_full, 128);
+    mbar_init(s_empty, 128 * GROUPS);
+    mbar_init(p_full, 128 * GROUPS);
     mbar_init(p_empty, 1);
     fence_barrier_init();
   }
@@ -263,8 +253,9 @@ fa_tc_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       issue_pv(n_tiles - 1);
     }
   } else {
-    // ------------------------------ softmax (128 threads, one query row each) ------------------------------
+    // ------------------------------ softmax (GROUPS x 128 threads, one query row each) ------------------------------
     const int quad = warp & 3;
+    const int grp = (warp - 2) >> 2;                      // softmax warpgroup: which half of the keys / O columns
     const int r = quad * 32 + lane;                       // row in the tile = TMEM lane
     const int qpos = q_pos0 + q0 + r;
     const bool row_ok = q0 + r < n_q;
@@ -281,7 +272,7 @@ fa_tc_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       mbar_wait(s_full, static_cast<uint32_t>(j & 1));
       tc_fence_after();
 
-      // ---- pass 1: row maximum (two 32-column chunks in flight) ----
+      // ---- pass 1: row maximum over all 128 keys (two 32-column chunks in flight) ----
       float mx = m_run;
       {
         uint32_t va[32], vb[32];
@@ -303,17 +294,26 @@ fa_tc_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         mbar_wait(p_empty, static_cast<uint32_t>((j - 1) & 1));
         tc_fence_after();
         if (__any_sync(0xffffffffu, mx != m_run)) {      // warp-uniform: rescale this warp's 32 rows of O
-          uint32_t o0[32], o1[32];
-          tmem_ld_32x32(tO, o0);
-          tmem_ld_32x32(tO + 32, o1);
-          tmem_ld_wait();
+          if (GROUPS == 1) {
+            uint32_t o0[32], o1[32];
+            tmem_ld_32x32(tO, o0);
+            tmem_ld_32x32(tO + 32, o1);
+            tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            o0[i] = __float_as_uint(__uint_as_float(o0[i]) * alpha);
-            o1[i] = __float_as_uint(__uint_as_float(o1[i]) * alpha);
+            for (int i = 0; i < 32; ++i) {
+              o0[i] = __float_as_uint(__uint_as_float(o0[i]) * alpha);
+              o1[i] = __float_as_uint(__uint_as_float(o1[i]) * alpha);
+            }
+            tmem_st_32x32(tO, o0);
+            tmem_st_32x32(tO + 32, o1);
+          } else {
+            uint32_t o0[32];                              // this group's 32 of the 64 O columns
+            tmem_ld_32x32(tO + grp * 32, o0);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o0[i] = __float_as_uint(__uint_as_float(o0[i]) * alpha);
+            tmem_st_32x32(tO + grp * 32, o0);
           }
-          tmem_st_32x32(tO, o0);
-          tmem_st_32x32(tO + 32, o1);
           tmem_st_wait();
         }
       }
@@ -323,17 +323,27 @@ fa_tc_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       // ---- pass 2: probabilities -> bf16 -> swizzled smem (A operand of P V) ----
       {
         uint32_t va[32], vb[32];
-        tmem_ld_32x32(tS, va);
+        if (GROUPS == 1) {
+          tmem_ld_32x32(tS, va);
 #pragma unroll 1
-        for (int cc = 0; cc < 2; ++cc) {
+          for (int cc = 0; cc < 2; ++cc) {
+            tmem_ld_wait();
+            tmem_ld_32x32(tS + (2 * cc + 1) * 32, vb);
+            l_run += chunk_probs(va, full, k0 + (2 * cc) * 32, kv_len, qpos, p.prefix_len, p.scale_log2, base,
+                                 prow + cc * (BM * 128), 0, r);
+            tmem_ld_wait();
+            if (cc == 0) tmem_ld_32x32(tS + 64, va);
+            l_run += chunk_probs(vb, full, k0 + (2 * cc + 1) * 32, kv_len, qpos, p.prefix_len, p.scale_log2, base,
+                                 prow + cc * (BM * 128), 4, r);
+          }
+        } else {                                          // keys 64 grp .. 64 grp + 63 = P's 64-key block grp
+          tmem_ld_32x32(tS + grp * 64, va);
+          tmem_ld_32x32(tS + grp * 64 + 32, vb);
           tmem_ld_wait();
-          tmem_ld_32x32(tS + (2 * cc + 1) * 32, vb);
-          l_run += chunk_probs<POLY>(va, full, k0 + (2 * cc) * 32, kv_len, qpos, p.prefix_len, p.scale_log2, base,
-                                     prow + cc * (BM * 128), 0, r);
-          tmem_ld_wait();
-          if (cc == 0) tmem_ld_32x32(tS + 64, va);
-          l_run += chunk_probs<POLY>(vb, full, k0 + (2 * cc + 1) * 32, kv_len, qpos, p.prefix_len, p.scale_log2, base,
-                                     prow + cc * (BM * 128), 4, r);
+          l_run += chunk_probs(va, full, k0 + grp * 64, kv_len, qpos, p.prefix_len, p.scale_log2, base,
+                               prow + grp * (BM * 128), 0, r);
+          l_run += chunk_probs(vb, full, k0 + grp * 64 + 32, kv_len, qpos, p.prefix_len, p.scale_log2, base,
+                               prow + grp * (BM * 128), 4, r);
         }
       }
       // S has been consumed; P is in shared memory: publish both
@@ -345,10 +355,16 @@ fa_tc_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     // ---- epilogue: O / l -> bf16 -> global ----
     mbar_wait(p_empty, static_cast<uint32_t>((n_tiles - 1) & 1));
     tc_fence_after();
+    if (GROUPS == 2) {                                    // add the two groups' partial row sums (P is no longer read)
+      float* xl = reinterpret_cast<float*>(sP);
+      xl[grp * BM + r] = l_run;
+      softmax_bar_sync(256);
+      l_run = xl[r] + xl[BM + r];
+    }
     const float inv = l_run > 0.f ? 1.0f / l_run : 0.f;
     __nv_bfloat16* orow = p.out + (static_cast<long long>(q_off) + q0 + r) * (static_cast<long long>(p.n_heads) * HD) + head * HD;
 #pragma unroll 1
-    for (int c = 0; c < HD / 32; ++c) {
+    for (int c = (GROUPS == 2 ? grp : 0); c < (GROUPS == 2 ? grp + 1 : HD / 32); ++c) {
       uint32_t o[32];
       tmem_ld_32x32(tO + c * 32, o);
       tmem_ld_wait();
@@ -389,7 +405,7 @@ int prefill_attention_tc(const __nv_bfloat16* q, int n_heads, int n_kv_heads, in
   if (make_tmap_bf16_2d(&tKV, kv_pool, pool_rows, 64, 64, 64)) return 1;
   static DeviceOnce configured;
   if (configured.first()) {
-    for (auto* fn : {fa_tc_prefill_kernel<false>, fa_tc_prefill_kernel<true>}) {
+    for (auto* fn : {fa_tc_prefill_kernel<1>, fa_tc_prefill_kernel<2>}) {
       cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, fa::kSmemTotal);
       if (e != cudaSuccess) return set_error(cudaGetErrorString(e));
       // two CTAs per SM need the full shared-memory carve-out
@@ -403,8 +419,8 @@ int prefill_attention_tc(const __nv_bfloat16* q, int n_heads, int n_kv_heads, in
   p.prefix_len = prefix_len; p.out = out;
   p.scale_log2 = 0.125f * 1.4426950408889634f;
   dim3 grid((max_q + fa::BM - 1) / fa::BM, n_heads, n_seqs);
-  if (g_attention_impl == 2) fa_tc_prefill_kernel<true><<<grid, fa::kThreads, fa::kSmemTotal, stream>>>(tQ, tKV, p);
-  else fa_tc_prefill_kernel<false><<<grid, fa::kThreads, fa::kSmemTotal, stream>>>(tQ, tKV, p);
+  if (g_attention_impl == 2) fa_tc_prefill_kernel<2><<<grid, fa::kThreads2, fa::kSmemTotal, stream>>>(tQ, tKV, p);
+  else fa_tc_prefill_kernel<1><<<grid, fa::kThreads1, fa::kSmemTotal, stream>>>(tQ, tKV, p);
   count_launch();
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(cudaGetErrorString(e));
@@ -429,7 +445,7 @@ constexpr int kTile = kBlk0 + kBlk1;             // 20 KB
 constexpr int kPBytes = BM * BN * 2;             // 32 KB
 constexpr int kSmemTiles = kTile /*Q*/ + 2 * kTile /*K*/ + kTile /*V*/ + kPBytes;   // 112 KB
 constexpr int kSmemTotal = kSmemTiles + 256;
-constexpr int kThreads = 192;
+constexpr int kThreads1 = 192, kThreads2 = 320;
 constexpr uint32_t kTmemCols = 256;
 constexpr uint32_t kColS = 0, kColO = 128;       // O: 80 columns (64 + 16)
 }  // namespace fv
@@ -440,8 +456,9 @@ struct FaVitParams {
   float scale_log2;
 };
 
-template <bool POLY>
-__global__ void __launch_bounds__(fv::kThreads, 2)
+// GROUPS = 2: as in fa_tc_prefill_kernel; of the 80 O columns group 0 owns 0..31 and 64..79, group 1 owns 32..63.
+template <int GROUPS>
+__global__ void __launch_bounds__(64 + 128 * GROUPS, 2)
 fa_tc_vit_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_constant__ CUtensorMap tm16,
                  const FaVitParams p) {
   using namespace fv;
@@ -481,8 +498,8 @@ fa_tc_vit_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_constant
     mbar_init(v_full, 1);
     mbar_init(v_empty, 1);
     mbar_init(s_full, 1);
-    mbar_init(s_empty, 128);
-    mbar_init(p_full, 128);
+    mbar_init(s_empty, 128 * GROUPS);
+    mbar_init(p_full, 128 * GROUPS);
     mbar_init(p_empty, 1);
     fence_barrier_init();
   }
@@ -558,8 +575,9 @@ fa_tc_vit_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_constant
       issue_pv(n_tiles - 1);
     }
   } else {
-    // ------------------------------ softmax ------------------------------
+    // ------------------------------ softmax (GROUPS x 128 threads) ------------------------------
     const int quad = warp & 3;
+    const int grp = (warp - 2) >> 2;
     const int r = quad * 32 + lane;
     const bool row_ok = q0 + r < n_q;
     const uint32_t lane_addr = static_cast<uint32_t>(quad * 32) << 16;
@@ -592,21 +610,26 @@ fa_tc_vit_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_constant
         mbar_wait(p_empty, static_cast<uint32_t>((j - 1) & 1));
         tc_fence_after();
         if (__any_sync(0xffffffffu, mx != m_run)) {
-          uint32_t o0[32], o1[32], o2[16];
-          tmem_ld_32x32(tO, o0);
-          tmem_ld_32x32(tO + 32, o1);
-          tmem_ld_32x16(tO + 64, o2);
-          tmem_ld_wait();
+          if (GROUPS == 1 || grp == 1) {
+            uint32_t o0[32];                                   // columns 32..63 (and 0..31 below when alone)
+            tmem_ld_32x32(tO + 32, o0);
+            tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            o0[i] = __float_as_uint(__uint_as_float(o0[i]) * alpha);
-            o1[i] = __float_as_uint(__uint_as_float(o1[i]) * alpha);
+            for (int i = 0; i < 32; ++i) o0[i] = __float_as_uint(__uint_as_float(o0[i]) * alpha);
+            tmem_st_32x32(tO + 32, o0);
           }
+          if (GROUPS == 1 || grp == 0) {
+            uint32_t o0[32], o2[16];
+            tmem_ld_32x32(tO, o0);
+            tmem_ld_32x16(tO + 64, o2);
+            tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 16; ++i) o2[i] = __float_as_uint(__uint_as_float(o2[i]) * alpha);
-          tmem_st_32x32(tO, o0);
-          tmem_st_32x32(tO + 32, o1);
-          tmem_st_32x16(tO + 64, o2);
+            for (int i = 0; i < 32; ++i) o0[i] = __float_as_uint(__uint_as_float(o0[i]) * alpha);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) o2[i] = __float_as_uint(__uint_as_float(o2[i]) * alpha);
+            tmem_st_32x32(tO, o0);
+            tmem_st_32x16(tO + 64, o2);
+          }
           tmem_st_wait();
         }
       }
@@ -614,17 +637,25 @@ fa_tc_vit_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_constant
       m_run = mx;
       {
         uint32_t va[32], vb[32];
-        tmem_ld_32x32(tS, va);
+        if (GROUPS == 1) {
+          tmem_ld_32x32(tS, va);
 #pragma unroll 1
-        for (int cc = 0; cc < 2; ++cc) {
+          for (int cc = 0; cc < 2; ++cc) {
+            tmem_ld_wait();
+            tmem_ld_32x32(tS + (2 * cc + 1) * 32, vb);
+            l_run += chunk_probs(va, full, k0 + (2 * cc) * 32, kv_len, qpos, 0, p.scale_log2, base,
+                                 prow + cc * (BM * 128), 0, r);
+            tmem_ld_wait();
+            if (cc == 0) tmem_ld_32x32(tS + 64, va);
+            l_run += chunk_probs(vb, full, k0 + (2 * cc + 1) * 32, kv_len, qpos, 0, p.scale_log2, base,
+                                 prow + cc * (BM * 128), 4, r);
+          }
+        } else {
+          tmem_ld_32x32(tS + grp * 64, va);
+          tmem_ld_32x32(tS + grp * 64 + 32, vb);
           tmem_ld_wait();
-          tmem_ld_32x32(tS + (2 * cc + 1) * 32, vb);
-          l_run += chunk_probs<POLY>(va, full, k0 + (2 * cc) * 32, kv_len, qpos, 0, p.scale_log2, base,
-                                     prow + cc * (BM * 128), 0, r);
-          tmem_ld_wait();
-          if (cc == 0) tmem_ld_32x32(tS + 64, va);
-          l_run += chunk_probs<POLY>(vb, full, k0 + (2 * cc + 1) * 32, kv_len, qpos, 0, p.scale_log2, base,
-                                     prow + cc * (BM * 128), 4, r);
+          l_run += chunk_probs(va, full, k0 + grp * 64, kv_len, qpos, 0, p.scale_log2, base, prow + grp * (BM * 128), 0, r);
+          l_run += chunk_probs(vb, full, k0 + grp * 64 + 32, kv_len, qpos, 0, p.scale_log2, base, prow + grp * (BM * 128), 4, r);
         }
       }
       tc_fence_before();
@@ -635,25 +666,41 @@ fa_tc_vit_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_constant
     // ---- epilogue: 72 of the 80 O columns ----
     mbar_wait(p_empty, static_cast<uint32_t>((n_tiles - 1) & 1));
     tc_fence_after();
+    if (GROUPS == 2) {
+      float* xl = reinterpret_cast<float*>(sP);
+      xl[grp * BM + r] = l_run;
+      softmax_bar_sync(256);
+      l_run = xl[r] + xl[BM + r];
+    }
     const float inv = l_run > 0.f ? 1.0f / l_run : 0.f;
     __nv_bfloat16* orow = p.out + (static_cast<long long>(row0) + q0 + r) * (static_cast<long long>(H) * HD) + head * HD;
-    uint32_t o0[32], o1[32], o2[16];
-    tmem_ld_32x32(tO, o0);
-    tmem_ld_32x32(tO + 32, o1);
-    tmem_ld_32x16(tO + 64, o2);
-    tmem_ld_wait();
-    if (row_ok) {
-      auto st8 = [&](const uint32_t* o, int col) {
-        uint4 w;
-        w.x = pack_bf16x2(__uint_as_float(o[0]) * inv, __uint_as_float(o[1]) * inv);
-        w.y = pack_bf16x2(__uint_as_float(o[2]) * inv, __uint_as_float(o[3]) * inv);
-        w.z = pack_bf16x2(__uint_as_float(o[4]) * inv, __uint_as_float(o[5]) * inv);
-        w.w = pack_bf16x2(__uint_as_float(o[6]) * inv, __uint_as_float(o[7]) * inv);
-        *reinterpret_cast<uint4*>(orow + col) = w;
-      };
+    auto st8 = [&](const uint32_t* o, int col) {
+      uint4 w;
+      w.x = pack_bf16x2(__uint_as_float(o[0]) * inv, __uint_as_float(o[1]) * inv);
+      w.y = pack_bf16x2(__uint_as_float(o[2]) * inv, __uint_as_float(o[3]) * inv);
+      w.z = pack_bf16x2(__uint_as_float(o[4]) * inv, __uint_as_float(o[5]) * inv);
+      w.w = pack_bf16x2(__uint_as_float(o[6]) * inv, __uint_as_float(o[7]) * inv);
+      *reinterpret_cast<uint4*>(orow + col) = w;
+    };
+    if (GROUPS == 1 || grp == 1) {
+      uint32_t o1[32];
+      tmem_ld_32x32(tO + 32, o1);
+      tmem_ld_wait();
+      if (row_ok) {
 #pragma unroll
-      for (int g = 0; g < 4; ++g) { st8(o0 + 8 * g, 8 * g); st8(o1 + 8 * g, 32 + 8 * g); }
-      st8(o2, 64);                                           // dims 64..71; 72..79 are padding
+        for (int g = 0; g < 4; ++g) st8(o1 + 8 * g, 32 + 8 * g);
+      }
+    }
+    if (GROUPS == 1 || grp == 0) {
+      uint32_t o0[32], o2[16];
+      tmem_ld_32x32(tO, o0);
+      tmem_ld_32x16(tO + 64, o2);
+      tmem_ld_wait();
+      if (row_ok) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) st8(o0 + 8 * g, 8 * g);
+        st8(o2, 64);                                           // dims 64..71; 72..79 are padding
+      }
     }
   }
 
@@ -676,7 +723,7 @@ int vit_attention_tc(const __nv_bfloat16* qkv, int n_crops, int seq, int n_heads
   if (make_tmap_bf16_3d(&t16, qkv, 72, 3LL * n_heads, T, 144, 3 * D * 2, 16, 1, 128, 32)) return 1;
   static DeviceOnce configured;
   if (configured.first()) {
-    for (auto* fn : {fa_tc_vit_kernel<false>, fa_tc_vit_kernel<true>}) {
+    for (auto* fn : {fa_tc_vit_kernel<1>, fa_tc_vit_kernel<2>}) {
       cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, fv::kSmemTotal);
       if (e != cudaSuccess) return set_error(cudaGetErrorString(e));
       e = cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
@@ -687,8 +734,8 @@ int vit_attention_tc(const __nv_bfloat16* qkv, int n_crops, int seq, int n_heads
   p.seq = seq; p.n_heads = n_heads; p.out = out;
   p.scale_log2 = (1.0f / sqrtf(72.0f)) * 1.4426950408889634f;
   dim3 grid((seq + fv::BM - 1) / fv::BM, n_heads, n_crops);
-  if (g_attention_impl == 2) fa_tc_vit_kernel<true><<<grid, fv::kThreads, fv::kSmemTotal, stream>>>(t64, t16, p);
-  else fa_tc_vit_kernel<false><<<grid, fv::kThreads, fv::kSmemTotal, stream>>>(t64, t16, p);
+  if (g_attention_impl == 2) fa_tc_vit_kernel<2><<<grid, fv::kThreads2, fv::kSmemTotal, stream>>>(t64, t16, p);
+  else fa_tc_vit_kernel<1><<<grid, fv::kThreads1, fv::kSmemTotal, stream>>>(t64, t16, p);
   count_launch();
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(cudaGetErrorString(e));

@@ -369,7 +369,7 @@ static long long smallbatch_ws_floats(const Model& m, int batch) {
 long long text_decode_ws_bytes(const Model& m, int batch) {
   const md_dims& d = m.d;
   return pad256(1LL * batch * d.txt_dim * 2) * 3 + pad256(1LL * batch * (d.txt_dim + d.txt_ff) * 2) +
-         pad256(smallbatch_ws_floats(m, batch) * 4) + 256 /* tail counters */ + 4096;
+         pad256(smallbatch_ws_floats(m, batch) * 4) + 4096;
 }
 
 static int small_linear(const bf16* x, long long ldx, const Lin& l, int batch, int n_out, int K, int mode,
@@ -394,12 +394,9 @@ int text_decode_step(Model& m, bf16* x, const int* pos, int batch, const md_kv& 
   bf16* ln_last = reinterpret_cast<bf16*>(p); p += pad256(1LL * batch * D * 2);
   bf16* qbuf = reinterpret_cast<bf16*>(p); p += pad256(1LL * batch * D * 2);          // grouped-query path only
   bf16* xcat = reinterpret_cast<bf16*>(p); p += pad256(1LL * batch * (D + FF) * 2);   // [att | gelu(fc1)]
-  int* tail_counter = reinterpret_cast<int*>(p); p += 256;
   float* wsf = reinterpret_cast<float*>(p);
   const bool quant = !m.tq.empty();
   if (quant && quant_ready(m)) return 1;
-  const bool tail = !quant && gemm_stream_tail_enabled(batch);
-  if (tail && cudaMemsetAsync(tail_counter, 0, 8, st) != cudaSuccess) return set_error("md_text_decode_step: memset failed");
   bf16* pool = reinterpret_cast<bf16*>(kv.pool);
   const StreamPlan2 pl2 = plan_smallbatch_2seg(D, D + FF, D);   // no split straddles proj | fc2
   const int proj_splits = pl2.splits_a;
@@ -410,17 +407,14 @@ int text_decode_step(Model& m, bf16* x, const int* pos, int batch, const md_kv& 
     // KV-page write / GELU, which the attention kernel applies for its own (sequence, head).  (Fusing them into
     // the GEMM epilogue needs whole-K tiles, i.e. 112 streaming SMs instead of 148: measured slower, DESIGN.md.)
     int s1 = gemm_smallbatch_splits(QKV + FF, D);
-    // K/V pages of earlier tokens are requested into L2 by the attention CTAs while this stream is still running
-    // (block 0 excepted: positions are written by the previous step's last kernel, only a few launches back)
-    const int early_pages = (KVH == H && i > 0 && !quant) ? decode_kv_prefetch_pages() : 0;
     if (quant) s1 = gemm_smallbatch_quant(m.tq[i].bits, m.tq[i].w1q, m.tq[i].w1s, m.tq[i].w1z, ln, D, QKV + FF, batch, D, 0, wsf, st);
-    else if (!(g_debug_skip & 1)) s1 = gemm_smallbatch(b.qkv.w, D, ln, D, QKV + FF, batch, D, 0, wsf, st, early_pages > 0);
+    else if (!(g_debug_skip & 1)) s1 = gemm_smallbatch(b.qkv.w, D, ln, D, QKV + FF, batch, D, 0, wsf, st);
     if (s1 < 0) return 1;
     if (KVH == H) {
       // bias / RoPE / KV-row write / GELU of that stream happen inside the attention kernel (one launch fewer)
       if (!(g_debug_skip & 4) &&
           decode_attention_fused(wsf, s1, D, FF, b.qkv.b, m.rope, xcat + D, D + FF, H, pos, batch, pool, kv.n_pages,
-                                 kv.block_tables, kv.max_blocks, i, xcat, D + FF, st, early_pages)) return 1;
+                                 kv.block_tables, kv.max_blocks, i, xcat, D + FF, st)) return 1;
     } else {
       // grouped-query attention: the G query heads of a group share one new K/V row, so the stream is finished by
       // its own small kernel and the plain paged kernel reads KV head h / G
@@ -434,12 +428,6 @@ int text_decode_step(Model& m, bf16* x, const int* pos, int batch, const md_kv& 
     const bool last = i + 1 == d.txt_layers;
     const Lin& nln = last ? m.txt_post_ln : m.txt[i + 1].ln;
     bf16* ln_dst = last ? (normed_out ? normed_out : ln_last) : ln;
-    if (tail) {
-      // residual + next LayerNorm finished by the stream's own last CTAs (one launch and hand-over fewer per block)
-      if (gemm_smallbatch_2seg_tail(b.proj.w, D + FF, xcat, D + FF, D, batch, D + FF, D, wsf, tail_counter, b.proj.b,
-                                    b.fc2.b, x, nln.w, nln.b, ln_dst, st) < 0) return 1;
-      continue;
-    }
     if (quant) s2 = gemm_smallbatch_quant(m.tq[i].bits, m.tq[i].w2q, m.tq[i].w2s, m.tq[i].w2z, xcat, D + FF, D, batch, D + FF, D, wsf, st);
     else if (!(g_debug_skip & 8)) s2 = gemm_smallbatch_2seg(b.proj.w, D + FF, xcat, D + FF, D, batch, D + FF, D, wsf, st);
     if (s2 < 0) return 1;

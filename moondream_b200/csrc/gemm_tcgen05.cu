@@ -19,7 +19,6 @@
 //     (splitk_epilogue_kernel, the decode attention prologue, the residual + LayerNorm epilogue, argmax).
 #include <vector>
 
-#include "decode_epilogue.cuh"
 #include "kernels.cuh"
 #include "ptx.cuh"
 
@@ -31,7 +30,6 @@ constexpr int kEpiWarps = 8;                        // two warps per TMEM lane q
 constexpr int kGemmThreads = 128 + kEpiWarps * 32;  // producer, MMA, TMEM-alloc, spare + epilogue
 
 static int g_gemm_debug = 0;            // md_debug_gemm: timing experiments only
-constexpr int kDefaultKvPrefetchPages = 0;   // decode attention's early K/V request (see decode_kv_prefetch_pages)
 static int g_gemm_sm_cap = 0;           // md_debug_gemm_sm_cap: 0 = every SM (default)
 
 struct GemmParams {
@@ -125,10 +123,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const GemmParams p) {
   using S = GemmSmem<BN, STAGES, CG>;
-  // two accumulator stages; allocations are powers of two, so BN = 192 takes 512 columns with stage 1 at column 256
-  constexpr uint32_t kAccStride = (BN == 192) ? 256 : BN;
-  constexpr uint32_t kTmemCols = (2 * kAccStride < 32) ? 32 : 2 * kAccStride;
-  static_assert(BN == 32 || BN == 64 || BN == 128 || BN == 192 || BN == 256, "unsupported BN");
+  constexpr uint32_t kTmemCols = (2 * BN < 32) ? 32 : 2 * BN;  // power of two for BN in {32..256}
+  static_assert(BN == 32 || BN == 64 || BN == 128 || BN == 256, "BN must be a power of two");
   static_assert(CG == 1 || CG == 2, "cta group");
 
   extern __shared__ uint8_t smem_raw[];
@@ -218,7 +214,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const uint32_t aphase = (it >> 1) & 1;
         mbar_wait(&tmem_empty[as], aphase ^ 1);
         tc_fence_after();
-        const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(as) * kAccStride;
+        const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(as * BN);
         for (int kb = 0; kb < p.k_blocks; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
@@ -279,7 +275,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       tc_fence_after();
       if (tl && threadIdx.x == 128) tl_s[3] = tl_now();                  // (last) accumulator complete
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
-                             static_cast<uint32_t>(as) * kAccStride;
+                             static_cast<uint32_t>(as * BN);
 
 #pragma unroll 1
       for (int c = half; c < BN / 32; c += 2) {
@@ -367,19 +363,6 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 // before the dependency wait (no earlier kernel writes weights); only the activation loads, and everything
 // downstream of them, wait for the predecessor.
 // ------------------------------------------------------------------------------------------------
-// Tail of the [proj | fc2] stream (md_debug_gemm bit 4 enables it): instead of handing the fp32 partial sums to a
-// separate residual + LayerNorm kernel, every CTA takes a ticket after publishing its partials; the CTAs holding the
-// last `rows` tickets wait until the ticket counter shows that all partials are out, then each finishes one batch row
-// (decode_epilogue.cuh) — one launch and one grid-to-grid hand-over fewer per decoder block.  The waiting CTAs are at
-// most `rows` (<= 128) of a grid that is fully resident, and every CTA they wait for has already been scheduled, so
-// the spin cannot deadlock.
-struct StreamTail {
-  int* counter;                        // [2] device ints, zero before the launch: tickets, finished rows
-  int proj_splits, D;
-  const __nv_bfloat16 *bias_proj, *bias_fc2, *ln_w, *ln_b;
-  __nv_bfloat16 *x, *ln_out;
-};
-
 constexpr int kSbMaxStages = 12;
 constexpr int kSbThreads = 256;          // warp 0 TMA producer, 1 MMA issuer, 2 TMEM allocator, 4..7 epilogue
 constexpr int kSbTailPad = BM * BK * 2;  // the A descriptor spans 128 rows whatever the batch: keep it in bounds
@@ -392,17 +375,13 @@ struct SmallBatchParams {
   int tmem_cols;
   int trigger_early;
   float* ws;
-  StreamTail tail;                     // tail.counter != nullptr: the last CTAs finish the rows (see the kernel's end)
 };
 
 // MROWS = 128 is the shipped form.  MROWS = 64 (batch <= 64; selected by md_debug_gemm bit 6 until it has been
 // validated on hardware) issues M = 64 MMAs: half the A-operand read per K = 16 step, accumulator rows
 // 16q .. 16q+15 in lanes 0..15 of TMEM lane quadrant q (the 1-CTA M = 64 data-path layout).
-// TAIL = true compiles the row-finishing tail in (its own instantiation, capped at 128 registers: the plain stream
-// keeps its 48 registers, which is what lets its CTAs become resident — and prefetch weights — while CTAs of the
-// preceding kernel still occupy the SM).
-template <int MROWS, bool TAIL = false>
-__global__ void __launch_bounds__(kSbThreads, TAIL ? 2 : 1)
+template <int MROWS>
+__global__ void __launch_bounds__(kSbThreads, 1)
 smallbatch_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
                        const SmallBatchParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -532,7 +511,6 @@ smallbatch_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
     }
   }
 
-  if (TAIL) __threadfence();                            // this thread's partial sums are visible device-wide
   tc_fence_before();
   __syncthreads();
   if (tl && threadIdx.x == 0)
@@ -541,38 +519,6 @@ smallbatch_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, static_cast<uint32_t>(p.tmem_cols));
-  }
-  if constexpr (TAIL) {
-    __shared__ int ticket_s;
-    __shared__ float red[2][8];
-    const int total = static_cast<int>(gridDim.x);
-    const int finishers = p.batch < total ? p.batch : total;
-    if (threadIdx.x == 0) ticket_s = atomicAdd(p.tail.counter, 1);
-    __syncthreads();
-    const int mine = ticket_s - (total - finishers);
-    if (mine >= 0) {                                     // CTA-uniform
-      ResLnParams P;
-      residual_ln_load_params(P, p.tail.D, p.tail.bias_proj, p.tail.bias_fc2, p.tail.ln_w, p.tail.ln_b);
-      if (threadIdx.x == 0) {
-        const long long t0 = clock64();
-        while (*reinterpret_cast<volatile int*>(p.tail.counter) < total)
-          if (clock64() - t0 > 4000000000LL) __trap();    // ~2 s: a lost CTA must not hang the GPU
-        __threadfence();
-      }
-      __syncthreads();
-      for (int b = mine; b < p.batch; b += finishers)
-        residual_ln_row<true>(P, p.ws, p.k_splits, p.tail.proj_splits, p.batch_total, p.tail.D, p.tail.x, p.tail.ln_out,
-                              1e-5f, b, red);
-      __syncthreads();
-      if (threadIdx.x == 0) {
-        const int done = atomicAdd(p.tail.counter + 1, 1);
-        if (done == finishers - 1) {                     // the last finisher re-arms the counters for the next launch
-          p.tail.counter[0] = 0;
-          p.tail.counter[1] = 0;
-          __threadfence();
-        }
-      }
-    }
   }
 }
 
@@ -790,8 +736,7 @@ static int dispatch_gemm(int bn, int cg, const CUtensorMap& tA, const CUtensorMa
                          cudaStream_t stream) {
   if (cg == 2) {
     if (bn == 256) return launch_gemm<256, 6, 2>(tA, tB, p, stream);
-    if (bn == 192) return launch_gemm<192, 7, 2>(tA, tB, p, stream);
-    return set_error("pair GEMM needs BN = 256 or 192");
+    return set_error("pair GEMM needs BN = 256");
   }
   switch (bn) {
     case 256: return launch_gemm<256, 4, 1>(tA, tB, p, stream);
@@ -800,21 +745,6 @@ static int dispatch_gemm(int bn, int cg, const CUtensorMap& tA, const CUtensorMa
     case 32: return launch_gemm<32, 10, 1>(tA, tB, p, stream);
   }
   return set_error("unsupported BN");
-}
-
-// Column-tile width of a pair GEMM: 256-wide tiles give the tensor pipe the longest uninterrupted run, but N = 1152
-// (ViT proj / fc2) fills only 4.5 of 5 such tiles and N = 3456 (ViT qkv) 13.5 of 14; 192-wide tiles divide both.  The
-// persistent kernel walks tiles round-robin over the CTA pairs, so time ~ waves x tile width; ties keep 256.
-// md_debug_gemm bit 7 restores 256 everywhere (A/B).
-static int pick_bn_pair(int M, int N) {
-  if (g_gemm_debug & 128) return 256;
-  const long long units = num_sms() / 2 > 0 ? num_sms() / 2 : 1;
-  const long long m_blocks = (M + 2 * BM - 1) / (2 * BM);
-  auto cost = [&](int bn) {
-    const long long tiles = m_blocks * ((N + bn - 1) / bn);
-    return ((tiles + units - 1) / units) * bn;
-  };
-  return cost(192) * 100 < cost(256) * 97 ? 192 : 256;      // take 192 only for a gain above 3 %
 }
 
 static int pick_bn_rows(int N) {
@@ -833,11 +763,10 @@ int gemm_rowform(const __nv_bfloat16* A, long long lda, const __nv_bfloat16* W, 
   if (N % 8 || K % 8) return set_error("gemm: N and K must be multiples of 8");
   if (mode == EPI_BIAS_RESIDUAL && !res) return set_error("gemm: residual mode without residual");
   if ((ldo % 8) || (res && (ldr % 8))) return set_error("gemm: ldo/ldr must be multiples of 8");
-  int bn = pick_bn_rows(N);
+  const int bn = pick_bn_rows(N);
   int cg = (bn == 256 && M > BM) ? 2 : 1;          // CTA pairs for the large prefill / ViT GEMMs
   if (g_force_cg == 1) cg = 1;
   if (g_force_cg == 2 && bn == 256) cg = 2;
-  if (cg == 2) bn = pick_bn_pair(M, N);
   CUtensorMap tA, tB;
   if (make_tmap_bf16_2d(&tA, A, M, K, lda, BM)) return 1;
   if (make_tmap_bf16_2d(&tB, W, N, K, ldw, bn / cg)) return 1;
@@ -933,8 +862,7 @@ StreamPlan plan_smallbatch(int n_out, int K, int kb_divisor, int m_rows) {
 // Returns the number of splits (> 0), -1 on error.
 static int gemm_smallbatch_impl(const __nv_bfloat16* W, long long ldw, const __nv_bfloat16* X, long long ldx,
                              int n_out, int batch, int K, int kb_per_split, int tile_n, float* ws,
-                             cudaStream_t stream, int seg_kb = 0, int kb_per_split2 = 0,
-                             const StreamTail* tail = nullptr, int dependents_early = 0) {
+                             cudaStream_t stream, int seg_kb = 0, int kb_per_split2 = 0) {
   if (n_out <= 0 || batch <= 0 || K <= 0) { set_error("small-batch GEMM: empty problem"); return -1; }
   if (K % 8) { set_error("small-batch GEMM: K must be a multiple of 8"); return -1; }
   if (tile_n < 1 || tile_n > 256) tile_n = BM;
@@ -958,11 +886,8 @@ static int gemm_smallbatch_impl(const __nv_bfloat16* W, long long ldw, const __n
     p.seg_splits = p.k_splits; p.seg_kb = p.k_blocks; p.kb_per_split2 = kb_per_split;
   }
   p.tmem_cols = p.n_mma <= 32 ? 32 : p.n_mma <= 64 ? 64 : p.n_mma <= 128 ? 128 : 256;
-  p.trigger_early = (g_pdl >= 2 || (g_pdl && dependents_early)) ? 1 : 0;
+  p.trigger_early = g_pdl >= 2 ? 1 : 0;
   constexpr int kSbSmemMax = 227 * 1024 - 1024;      // leave room for the kernel's few static __shared__ words
-  // dependents_early: the consumer's CTAs (decode attention: ~6.4 KB of shared memory each) become resident beside
-  // this stream's CTA and request their K/V pages into L2 while the weights are still streaming
-  const int smem_budget = dependents_early ? kSbSmemMax - 36 * 1024 : kSbSmemMax;
   static DeviceOnce configured;
   if (configured.first()) {
     cudaError_t e = cudaFuncSetAttribute(smallbatch_gemm_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSbSmemMax);
@@ -977,26 +902,15 @@ static int gemm_smallbatch_impl(const __nv_bfloat16* W, long long ldw, const __n
     cudaError_t e = cudaFuncSetAttribute(smallbatch_gemm_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSbSmemMax);
     if (e != cudaSuccess) { set_error(cudaGetErrorString(e)); return -1; }
   }
-  static DeviceOnce configured_tail;
-  if (tail && configured_tail.first()) {
-    cudaError_t e = cudaFuncSetAttribute(smallbatch_gemm_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSbSmemMax);
-    if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(smallbatch_gemm_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSbSmemMax);
-    if (e != cudaSuccess) { set_error(cudaGetErrorString(e)); return -1; }
-  }
   CUtensorMap tW;
   if (make_tmap_bf16_2d(&tW, W, n_out, K, ldw, tile_n)) return -1;
-  if (tail && batch <= BM) {
-    p.tail = *tail;
-    p.tail.proj_splits = p.seg_splits;
-  }
   for (int b0 = 0; b0 < batch; b0 += BM) {
     p.batch = batch - b0 < BM ? batch - b0 : BM;
     const int a_rows = (p.batch + 7) / 8 * 8;
     p.a_bytes = a_rows * BK * 2;                     // a multiple of 1024: the weight tile stays swizzle-aligned
     p.stage_bytes = p.a_bytes + p.n_mma * BK * 2;
     const int bar_bytes = (2 * kSbMaxStages + 1) * 8 + 16;
-    p.stages = (smem_budget - 1024 - kSbTailPad - bar_bytes) / p.stage_bytes;
+    p.stages = (kSbSmemMax - 1024 - kSbTailPad - bar_bytes) / p.stage_bytes;
     if (p.stages > kSbMaxStages) p.stages = kSbMaxStages;
     if (p.stages < 2) { set_error("small-batch GEMM: tile does not fit shared memory"); return -1; }
     p.ws = ws + static_cast<long long>(b0) * n_out;
@@ -1006,11 +920,8 @@ static int gemm_smallbatch_impl(const __nv_bfloat16* W, long long ldw, const __n
     count_launch();
     const dim3 grid(n_tiles * p.k_splits), block(kSbThreads);
     const size_t smem = static_cast<size_t>(smem_bytes);
-    cudaError_t e;
-    if (p.tail.counter) e = m64 ? launch_k(smallbatch_gemm_kernel<64, true>, grid, block, smem, stream, tX, tW, p)
-                                : launch_k(smallbatch_gemm_kernel<128, true>, grid, block, smem, stream, tX, tW, p);
-    else e = m64 ? launch_k(smallbatch_gemm_kernel<64>, grid, block, smem, stream, tX, tW, p)
-                 : launch_k(smallbatch_gemm_kernel<128>, grid, block, smem, stream, tX, tW, p);
+    const cudaError_t e = m64 ? launch_k(smallbatch_gemm_kernel<64>, grid, block, smem, stream, tX, tW, p)
+                              : launch_k(smallbatch_gemm_kernel<128>, grid, block, smem, stream, tX, tW, p);
     if (e != cudaSuccess) { set_error(cudaGetErrorString(e)); return -1; }
   }
   return p.k_splits;
@@ -1031,18 +942,10 @@ int gemm_smallbatch_splits(int n_out, int K) {
 }
 
 int gemm_smallbatch(const __nv_bfloat16* W, long long ldw, const __nv_bfloat16* X, long long ldx,
-                 int n_out, int batch, int K, int splits, float* ws, cudaStream_t stream, int dependents_early) {
+                 int n_out, int batch, int K, int splits, float* ws, cudaStream_t stream) {
   (void)splits;                                  // the plan decides (callers size ws with gemm_smallbatch_splits)
   const StreamPlan pl = plan_smallbatch(n_out, K, 0, (!(g_gemm_debug & 64) && batch <= 64) ? 64 : 128);
-  return gemm_smallbatch_impl(W, ldw, X, ldx, n_out, batch, K, pl.kb, pl.tile_rows, ws, stream, 0, 0, nullptr,
-                              dependents_early);
-}
-
-// md_debug_gemm bits 8..11: K/V pages each decode-attention CTA requests into L2 before its dependency wait
-// (0 = the default below; 15 = off)
-int decode_kv_prefetch_pages() {
-  const int v = (g_gemm_debug >> 8) & 15;
-  return v == 15 ? 0 : (v ? v : kDefaultKvPrefetchPages);
+  return gemm_smallbatch_impl(W, ldw, X, ldx, n_out, batch, K, pl.kb, pl.tile_rows, ws, stream);
 }
 
 int gemm_rowform_qkv_rope(const __nv_bfloat16* A, long long lda, const __nv_bfloat16* W, long long ldw, int M,
@@ -1119,21 +1022,6 @@ int gemm_smallbatch_2seg(const __nv_bfloat16* W, long long ldw, const __nv_bfloa
   if (seg_K <= 0 || seg_K >= K || seg_K % BK) { set_error("gemm_smallbatch_2seg: segment boundary must be a multiple of 64 inside K"); return -1; }
   const StreamPlan2 pl = plan_smallbatch_2seg(n_out, K, seg_K);
   return gemm_smallbatch_impl(W, ldw, X, ldx, n_out, batch, K, pl.kb_a, pl.tile_rows, ws, stream, seg_K / BK, pl.kb_b);
-}
-
-bool gemm_stream_tail_enabled(int batch) { return (g_gemm_debug & 16) && batch <= BM; }
-
-// the [proj | fc2] stream with the residual + LayerNorm rows finished by its own last CTAs (see StreamTail);
-// `counter`: two zeroed device ints
-int gemm_smallbatch_2seg_tail(const __nv_bfloat16* W, long long ldw, const __nv_bfloat16* X, long long ldx, int n_out,
-                              int batch, int K, int seg_K, float* ws, int* counter, const __nv_bfloat16* bias_proj,
-                              const __nv_bfloat16* bias_fc2, __nv_bfloat16* x, const __nv_bfloat16* ln_w,
-                              const __nv_bfloat16* ln_b, __nv_bfloat16* ln_out, cudaStream_t stream) {
-  if (seg_K <= 0 || seg_K >= K || seg_K % BK) { set_error("gemm_smallbatch_2seg: segment boundary must be a multiple of 64 inside K"); return -1; }
-  if (n_out % 8 || n_out > 4096 || batch > BM) { set_error("gemm_smallbatch_2seg_tail: unsupported shape"); return -1; }
-  const StreamPlan2 pl = plan_smallbatch_2seg(n_out, K, seg_K);
-  StreamTail t{counter, 0, n_out, bias_proj, bias_fc2, ln_w, ln_b, x, ln_out};
-  return gemm_smallbatch_impl(W, ldw, X, ldx, n_out, batch, K, pl.kb_a, pl.tile_rows, ws, stream, seg_K / BK, pl.kb_b, &t);
 }
 
 int splitk_epilogue(const float* ws, int splits, int B, int N, int mode, const __nv_bfloat16* bias,

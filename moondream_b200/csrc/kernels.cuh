@@ -82,8 +82,7 @@ struct StreamPlan { int tile_rows, kb, splits; };
 StreamPlan plan_smallbatch(int n_out, int K, int kb_divisor, int m_rows = 128);
 int gemm_smallbatch_splits(int n_out, int K);
 int gemm_smallbatch(const __nv_bfloat16* W, long long ldw, const __nv_bfloat16* X, long long ldx,
-                 int n_out, int batch, int K, int splits, float* ws, cudaStream_t stream, int dependents_early = 0);
-int decode_kv_prefetch_pages();
+                 int n_out, int batch, int K, int splits, float* ws, cudaStream_t stream);
 // Prefill QKV projection with RoPE and the KV-cache write fused into the GEMM epilogue (text.py:30-43,
 // rope.py:20-48, moondream.py:74-78): output column block -> (q|k|v, head, half-head); row -> (sequence, position).
 struct RopeEpilogue {
@@ -104,11 +103,6 @@ struct StreamPlan2 { int tile_rows, splits_a, kb_a, splits_b, kb_b; };
 StreamPlan2 plan_smallbatch_2seg(int n_out, int K, int seg_K);
 int gemm_smallbatch_2seg(const __nv_bfloat16* W, long long ldw, const __nv_bfloat16* X, long long ldx,
                       int n_out, int batch, int K, int seg_K, float* ws, cudaStream_t stream);
-bool gemm_stream_tail_enabled(int batch);
-int gemm_smallbatch_2seg_tail(const __nv_bfloat16* W, long long ldw, const __nv_bfloat16* X, long long ldx, int n_out,
-                              int batch, int K, int seg_K, float* ws, int* counter, const __nv_bfloat16* bias_proj,
-                              const __nv_bfloat16* bias_fc2, __nv_bfloat16* x, const __nv_bfloat16* ln_w,
-                              const __nv_bfloat16* ln_b, __nv_bfloat16* ln_out, cudaStream_t stream);
 int splitk_epilogue(const float* ws, int splits, int B, int N, int mode, const __nv_bfloat16* bias,
                     const __nv_bfloat16* res, long long ldr, __nv_bfloat16* out, long long ldo,
                     cudaStream_t stream);
@@ -176,7 +170,7 @@ int decode_attention(const __nv_bfloat16* q, int n_heads, int n_kv_heads, const 
 int decode_attention_fused(const float* ws, int splits, int D, int FF, const __nv_bfloat16* bias, const float* freqs,
                            __nv_bfloat16* hid, long long ld_hid, int n_heads, const int* pos, int n_seqs,
                            __nv_bfloat16* kv_pool, int n_pages, const int* block_tables, int max_blocks, int layer,
-                           __nv_bfloat16* out, long long ld_out, cudaStream_t stream, int early_pages = 0);
+                           __nv_bfloat16* out, long long ld_out, cudaStream_t stream);
 int decode_qkv_finish(const float* ws, int splits, int B, int D, int n_kv_heads, int FF, const __nv_bfloat16* bias,
                       const float* freqs, const int* pos, __nv_bfloat16* q_out, __nv_bfloat16* kv_pool, int n_pages,
                       const int* block_tables, int max_blocks, int layer, __nv_bfloat16* hid, long long ld_hid,

@@ -35,7 +35,7 @@ def test_layernorm(rows, dim):
     assert ((y != ref).float().mean().item()) < 0.02
 
 
-@pytest.mark.parametrize("impl", [0, 1, 2], ids=["tcgen05", "mma_sync", "tcgen05_fma_exp2"])
+@pytest.mark.parametrize("impl", [0, 1, 2], ids=["tcgen05", "mma_sync", "tcgen05_split_softmax"])
 @pytest.mark.parametrize("n_crops,heads", [(1, 16), (3, 2), (2, 10)])
 def test_vit_attention(n_crops, heads, impl):
     N, lib = _lib()
@@ -76,7 +76,7 @@ def _rope_ref(x, table, pos):
     return torch.cat([rot, x[..., 32:]], dim=-1)
 
 
-@pytest.mark.parametrize("impl", [0, 1, 2], ids=["tcgen05", "mma_sync", "tcgen05_fma_exp2"])
+@pytest.mark.parametrize("impl", [0, 1, 2], ids=["tcgen05", "mma_sync", "tcgen05_split_softmax"])
 def test_rope_prefill_decode_attention(impl):
     from moondream_b200.engine import rope_table
 
@@ -186,3 +186,58 @@ def test_small_batch_argmax_ties_and_mask(vocab):
     lg = logits.float().clone()
     lg[:, int(best[0])] = -float("inf")
     assert torch.equal(ids.long(), torch.argmax(lg, dim=-1))
+
+
+@pytest.mark.parametrize("n_crops", [1, 3])
+def test_patchify_is_bit_exact(n_crops):
+    """prepare_crops' normalisation + create_patches (vision.py:36-40, 44-61) with the reference's own torch ops."""
+    from moondream_b200.engine import pixel_lut
+
+    N, lib = _lib()
+    crop, patch, k_pad = 378, 14, 592
+    g = torch.Generator().manual_seed(n_crops)
+    crops = torch.randint(0, 256, (n_crops, crop, crop, 3), dtype=torch.uint8, generator=g)
+    lut = pixel_lut().cuda()
+    out = torch.full((n_crops * 729, k_pad), 5.0, dtype=torch.bfloat16, device="cuda")
+    N.check(lib.md_patchify_u8(N.ptr(crops.cuda()), n_crops, crop, patch, k_pad, N.ptr(lut), N.ptr(out), N.current_stream()))
+    torch.cuda.synchronize()
+    # reference: NHWC uint8 -> NCHW bf16, (x / 255 - 0.5) / 0.5, then the reshape / permute of create_patches
+    x = crops.permute(0, 3, 1, 2).to(torch.bfloat16).div_(255.0).sub_(0.5).div_(0.5)
+    B, C, H, W = x.shape
+    P = patch
+    ref = x.reshape(B, C, H // P, P, W // P, P).permute(0, 2, 4, 1, 3, 5).reshape(B * (H // P) * (W // P), C * P * P)
+    assert torch.equal(out[:, : C * P * P].cpu(), ref)
+    assert bool((out[:, C * P * P:] == 0).all())
+
+
+@pytest.mark.parametrize("tilings", [[(1, 1)], [(2, 2), (1, 1), (3, 3)], [(1, 2), (3, 4), (2, 1)]])
+def test_stitch_pool_concat_matches_the_reference_ops(tilings):
+    """reconstruct_from_crops(patch_size = 1) + adaptive_avg_pool2d + concat (image_crops.py:170-231, vision.py:83-88)
+    against the oracle's restatement run with torch CPU bf16 ops: bit-exact (fp32 window sums in row-major order,
+    divided by the count, like ATen)."""
+    import torch.nn.functional as F
+
+    from oracle.moondream_oracle import stitch_crops
+
+    N, lib = _lib()
+    g, margin, dim = 27, 4, 144
+    n_crops = [1 + th * tw for th, tw in tilings]
+    offs = [0]
+    for c in n_crops:
+        offs.append(offs[-1] + c)
+    gen = torch.Generator().manual_seed(len(tilings) * 7 + offs[-1])
+    feats = torch.randn(offs[-1] * g * g, dim, generator=gen).to(torch.bfloat16)
+    out = torch.empty(len(tilings) * g * g, 2 * dim, dtype=torch.bfloat16, device="cuda")
+    d_offs = torch.tensor(offs, dtype=torch.int32, device="cuda")
+    d_til = torch.tensor(tilings, dtype=torch.int32, device="cuda")
+    N.check(lib.md_stitch_pool_concat_bf16(N.ptr(feats.cuda()), N.ptr(d_offs), N.ptr(d_til), len(tilings), g, margin, dim,
+                                           N.ptr(out), N.current_stream()))
+    torch.cuda.synchronize()
+    got = out.cpu().view(len(tilings), g * g, 2 * dim)
+    f = feats.view(offs[-1], g, g, dim)
+    for i, til in enumerate(tilings):
+        glob = f[offs[i]].reshape(g * g, dim)
+        stitched = stitch_crops(f[offs[i] + 1: offs[i + 1]], til, margin)
+        pooled = F.adaptive_avg_pool2d(stitched.permute(2, 0, 1), output_size=(g, g)).permute(1, 2, 0).reshape(g * g, dim)
+        assert torch.equal(got[i, :, :dim], glob)
+        assert torch.equal(got[i, :, dim:], pooled), (til, (got[i, :, dim:].float() - pooled.float()).abs().max().item())
