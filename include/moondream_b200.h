@@ -152,7 +152,8 @@ int md_prefill_attention_bf16(const void* q, int n_heads, int total_tokens, cons
                               const int* start_pos, int n_seqs, int max_q, int prefix_len,
                               const md_kv* kv, int layer, void* out, void* stream);
 /* Testing / A-B timing only: 0 = tcgen05 attention (default), 1 = the legacy mma.sync kernel, 2 = tcgen05 attention with
- * two softmax warpgroups per CTA (each owns half of a score tile's keys and half of the O columns). */
+ * a single-pass softmax (two warpgroups hold a score tile in registers, lazy O rescale), 3 = 2 with 3 of every 8
+ * exponentials on the FMA pipe. */
 void md_debug_attention_impl(int impl);
 /* Testing / A-B timing only: programmatic dependent launch between consecutive kernels (default on). */
 void md_debug_set_pdl(int enable);
@@ -161,8 +162,10 @@ void md_debug_set_pdl(int enable);
 void md_debug_skip_decode_kernels(int mask);
 /* Timing experiments only, small-batch weight stream:
  * bit2 previous split plan of the [proj | fc2] stream (equal splits); bit3 previous plan of the single-segment streams
- * (tiles <= 128 rows; the default is the operand-read cost model: tiles up to 256 rows + K splits); bit6 forces
- * M = 128 MMAs for batches <= 64 (the default there is M = 64).  Other bits are ignored. */
+ * (tiles <= 128 rows; the default is the operand-read cost model: tiles up to 256 rows + K splits); bit5 stops the
+ * row-form GEMM from releasing its dependent grid early (programmatic dependent launch); bit6 forces M = 128 MMAs for
+ * batches <= 64 (the default there is M = 64); bit7 runs the patch embedding as patchify kernel + row-form GEMM instead
+ * of the im2col-fused kernel.  Other bits are ignored. */
 void md_debug_gemm(int flags);
 /* Experiments only: cap the persistent row-form GEMM's grid at `sms` SMs (0 = all, the default), leaving the others
  * to kernels of a concurrent stream (encode / decode overlap). */

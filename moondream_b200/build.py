@@ -7,7 +7,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-SOURCES = ["gemm_tcgen05.cu", "gemm_quant.cu", "attention.cu", "attention_tc.cu", "elementwise.cu", "sampling.cu", "preprocess.cu", "loader.cu", "engine.cu", "api.cu"]
+SOURCES = ["gemm_tcgen05.cu", "gemm_quant.cu", "patch_embed.cu", "attention.cu", "attention_tc.cu", "elementwise.cu", "sampling.cu", "preprocess.cu", "loader.cu", "engine.cu", "api.cu"]
 HEADERS = ["ptx.cuh", "kernels.cuh", "engine.h", "decode_epilogue.cuh", os.path.join("..", "..", "include", "moondream_b200.h")]
 OUT = os.path.join(CSRC, "libmoondream_b200.so")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

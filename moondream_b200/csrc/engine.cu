@@ -154,10 +154,16 @@ int vision_encode(Model& m, const uint8_t* crops, int n_crops, bf16* feats, void
   bf16* att = reinterpret_cast<bf16*>(p); p += pad256(1LL * T * D * 2);
   bf16* hid = reinterpret_cast<bf16*>(p);
 
-  if (patchify(crops, n_crops, d.crop, d.patch, d.patch_k, m.lut, patches, st)) return 1;
   // x = bf16(bf16(patches W^T + b) + pos_emb[token])           vision.py:67-68
-  if (gemm_rowform(patches, d.patch_k, m.patch_emb.w, d.patch_k, T, D, d.patch_k, EPI_BIAS_RESIDUAL,
-                   m.patch_emb.b, m.pos_emb, D, tok, x, D, 0, 0, 0, st)) return 1;
+  if (!g_patch_embed_unfused && 3 * d.patch * d.patch <= 640) {
+    // one im2col-fused tcgen05 GEMM straight from the uint8 crops (patch_embed.cu): no patch matrix in HBM
+    if (patch_embed_fused(crops, n_crops, d.crop, d.patch, m.lut, m.patch_emb.w, d.patch_k, m.patch_emb.b, m.pos_emb, D, x,
+                          st)) return 1;
+  } else {
+    if (patchify(crops, n_crops, d.crop, d.patch, d.patch_k, m.lut, patches, st)) return 1;
+    if (gemm_rowform(patches, d.patch_k, m.patch_emb.w, d.patch_k, T, D, d.patch_k, EPI_BIAS_RESIDUAL,
+                     m.patch_emb.b, m.pos_emb, D, tok, x, D, 0, 0, 0, st)) return 1;
+  }
   for (int i = 0; i < d.vis_layers; ++i) {
     const VisBlock& b = m.vis[i];
     // x = x + attn(ln1(x))                                      vision.py:70, layers.py:155-166

@@ -44,6 +44,7 @@ struct GemmParams {
   int res_mod;                         // residual row = row % res_mod when > 0 (pos_emb broadcast)
   int remap_gin, remap_gout, remap_goff;  // out row = (r / gin) * gout + r % gin + goff when gin > 0
   RopeEpilogue rope;                   // EPI_QKV_ROPE
+  int early_trigger;                   // release the dependent grid at once (its prologue overlaps this kernel's tail wave)
 };
 
 // Fused epilogue of the prefill QKV projection: this thread owns token row `row` and the 32 output columns
@@ -167,6 +168,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (CG == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  // every dependent kernel waits (griddepcontrol.wait) before it touches global memory, so releasing it here only moves
+  // its launch latency and prologue under this kernel's last, partially filled wave of tiles
+  if (p.early_trigger) pdl_launch_dependents();
 
   const int total_tiles = p.m_blocks * p.n_blocks;
   const int unit = blockIdx.x / CG, n_units = gridDim.x / CG;
@@ -718,7 +722,8 @@ static int launch_gemm(const CUtensorMap& tA, const CUtensorMap& tB, const GemmP
   return 0;
 }
 
-void gemm_debug_flags(int flags) { g_gemm_debug = flags; }
+int g_patch_embed_unfused = 0;   // md_debug_gemm bit 7: patchify kernel + row-form GEMM instead of the fused kernel (A/B, tests)
+void gemm_debug_flags(int flags) { g_gemm_debug = flags; g_patch_embed_unfused = (flags & 128) ? 1 : 0; }
 void gemm_debug_sm_cap(int sms) { g_gemm_sm_cap = sms < 0 ? 0 : sms; }
 static int g_force_cg = 0;   // 0 = auto, 1 / 2 = force (tests and A/B timing)
 void gemm_force_cta_group(int cg) { g_force_cg = cg; }
@@ -778,6 +783,7 @@ int gemm_rowform(const __nv_bfloat16* A, long long lda, const __nv_bfloat16* W, 
   p.mode = mode;
   p.out = out; p.ldo = ldo; p.bias = bias; p.res = res; p.ldr = ldr; p.res_mod = res_mod;
   p.remap_gin = remap_gin; p.remap_gout = remap_gout; p.remap_goff = remap_goff;
+  p.early_trigger = (g_pdl && !(g_gemm_debug & 32)) ? 1 : 0;      // md_debug_gemm bit 5: off (A/B)
   cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
   const bool prof = g_prof.on && cudaStreamIsCapturing(stream, &cap) == cudaSuccess &&
                     cap == cudaStreamCaptureStatusNone;
@@ -968,6 +974,7 @@ int gemm_rowform_qkv_rope(const __nv_bfloat16* A, long long lda, const __nv_bflo
   p.mode = EPI_QKV_ROPE;
   p.bias = bias;
   p.rope = epi;
+  p.early_trigger = (g_pdl && !(g_gemm_debug & 32)) ? 1 : 0;
   cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
   const bool prof = g_prof.on && cudaStreamIsCapturing(stream, &cap) == cudaSuccess &&
                     cap == cudaStreamCaptureStatusNone;

@@ -113,6 +113,12 @@ int dequant_weights(int bits, const uint8_t* q, const float* scale, const float*
 int gemm_smallbatch_quant(int bits, const uint8_t* Wq, const float* scale, const float* zero, const __nv_bfloat16* X,
                           long long ldx, int n_out, int batch, int K, int seg_K, float* ws, cudaStream_t stream);
 
+// ---- patch_embed.cu: im2col-fused patch embedding (vision.py:25-68) ----
+int patch_embed_fused(const uint8_t* crops, int n_crops, int crop, int patch, const __nv_bfloat16* lut,
+                      const __nv_bfloat16* W, int k_pad, const __nv_bfloat16* bias, const __nv_bfloat16* pos_emb, int N,
+                      __nv_bfloat16* out, cudaStream_t stream);
+extern int g_patch_embed_unfused;
+
 // ---- elementwise.cu ----
 int layernorm(const __nv_bfloat16* x, long long ldx, const __nv_bfloat16* w, const __nv_bfloat16* b,
               __nv_bfloat16* y, long long ldy, int rows, int dim, float eps, cudaStream_t stream);

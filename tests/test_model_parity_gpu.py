@@ -281,3 +281,28 @@ def test_generation_with_forced_m128_stream(tiny):
             if a != b:
                 assert gen.margin_ulps[j] < NEAR_TIE_ULPS, (i, j, a, b, gen.margin_ulps[j])
                 break
+
+
+@pytest.mark.parametrize("preset,n_crops", [("tiny", 1), ("tiny", 5), ("moondream-0.5b", 2), ("moondream-2b", 3)])
+def test_fused_patch_embed_equals_patchify_plus_gemm(preset, n_crops):
+    """The im2col-fused patch-embedding kernel (csrc/patch_embed.cu) issues the same K = 16 MMAs in the same order as
+    patchify + the row-form GEMM, so the whole ViT output must be bit-identical with either (md_debug_gemm bit 7 selects
+    the unfused pair).  Covers N = 144 (partial 128-column chunk), 720 and 1152, and a partial last row tile."""
+    from moondream_b200 import config as C, synth
+    from moondream_b200.engine import Engine
+
+    cfg = C.preset(preset)
+    keep = {k: v for k, v in synth.synthetic_state_dict(cfg, 1).items()}
+    eng = Engine(cfg, keep, max_batch=1, kv_pages=40)
+    g = torch.Generator().manual_seed(n_crops)
+    crops = torch.randint(0, 256, (n_crops, 378, 378, 3), dtype=torch.uint8, generator=g).cuda()
+    try:
+        eng.lib.md_debug_gemm(128)
+        want = eng.vision_encode(crops).clone()
+        eng.lib.md_debug_gemm(0)
+        got = eng.vision_encode(crops).clone()
+    finally:
+        eng.lib.md_debug_gemm(0)
+    torch.cuda.synchronize()
+    assert torch.isfinite(got.float()).all()
+    assert torch.equal(got, want), (got.float() - want.float()).abs().max().item()
