@@ -151,9 +151,8 @@ int md_rope_kv_write_bf16(const void* qkv, int n_tokens, int n_heads, const int*
 int md_prefill_attention_bf16(const void* q, int n_heads, int total_tokens, const int* q_offsets,
                               const int* start_pos, int n_seqs, int max_q, int prefix_len,
                               const md_kv* kv, int layer, void* out, void* stream);
-/* Testing / A-B timing only: 0 = tcgen05 attention (default), 1 = the legacy mma.sync kernel, 2 = tcgen05 attention with
- * a single-pass softmax (two warpgroups hold a score tile in registers, lazy O rescale), 3 = 2 with 3 of every 8
- * exponentials on the FMA pipe. */
+/* Testing / A-B timing only: 0 = tcgen05 attention with the single-pass softmax (default: two warpgroups hold a score tile
+ * in registers, lazy O rescale), 1 = the legacy mma.sync kernel, 2 = tcgen05 attention with the two-pass softmax. */
 void md_debug_attention_impl(int impl);
 /* Testing / A-B timing only: programmatic dependent launch between consecutive kernels (default on). */
 void md_debug_set_pdl(int enable);

@@ -73,26 +73,8 @@ __device__ __forceinline__ float chunk_max(const uint32_t (&v)[32], bool full, i
 
 // exp2(s * scale - base) for one 32-score chunk -> bf16 -> four swizzled 16-byte chunks of the row's
 // 128-byte line (chunk slots chunk0 .. chunk0+3); returns the row-sum contribution.
-// POLY: pairs 1, 2, 5 of every 8 go through exp2_fma2 instead of MUFU.EX2.
-// 2^x on the FMA pipe (no MUFU): x = n + f with n = round(x) taken from the low mantissa bits of x + 1.5 * 2^23 and
-// f in [-0.5, 0.5]; 2^f by a minimax cubic (relative error <= 7.5e-5, a fiftieth of a bf16 ulp: the result is rounded
-// to bf16 right after); 2^n by adding n to the exponent field.  With the single-pass softmax (GROUPS = 2) a 128 x 128
-// score tile costs ~1000 clocks of TMEM reads and 1024 clocks of MUFU (16384 exponentials at 16 per clock), so moving
-// 3 of every 8 pairs here takes MUFU off the critical path.
-__device__ __forceinline__ float2 exp2_fma2(float2 x) {
-  const float kMagic = 12582912.f;                       // 1.5 * 2^23
-  x.x = fmaxf(x.x, -125.f);
-  x.y = fmaxf(x.y, -125.f);
-  const float2 t = fadd2(x, make_float2(kMagic, kMagic));
-  const float2 n = fadd2(t, make_float2(-kMagic, -kMagic));
-  const float2 f = ffma2(n, make_float2(-1.f, -1.f), x);
-  float2 q = ffma2(f, make_float2(0.05517146f, 0.05517146f), make_float2(0.24261086f, 0.24261086f));
-  q = ffma2(q, f, make_float2(0.69326099f, 0.69326099f));
-  q = ffma2(q, f, make_float2(0.99992809f, 0.99992809f));
-  return make_float2(__int_as_float(__float_as_int(q.x) + (__float_as_int(t.x) << 23)),
-                     __int_as_float(__float_as_int(q.y) + (__float_as_int(t.y) << 23)));
-}
-template <bool POLY>
+// (Evaluating 3 of every 8 exponential pairs with an FMA-pipe cubic instead of MUFU.EX2 was measured twice — over the
+// two-pass and over the single-pass softmax — and changed nothing (profiles/r02_attention_ab.json): XU runs at 40 %.)
 __device__ __forceinline__ float chunk_probs(const uint32_t (&v)[32], bool full, int k_first, int kv_len, int qpos,
                                              int prefix_len, float scale_log2, float base, uint8_t* line,
                                              int chunk0, int r) {
@@ -105,9 +87,8 @@ __device__ __forceinline__ float chunk_probs(const uint32_t (&v)[32], bool full,
     for (int i = 0; i < 16; i += 2) {
       const float2 x0 = ffma2(make_float2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1])), sc, nb);
       const float2 x1 = ffma2(make_float2(__uint_as_float(v[2 * i + 2]), __uint_as_float(v[2 * i + 3])), sc, nb);
-      // i is a compile-time constant after unrolling: pairs i = 2, 10 and i + 1 = 1, 5, 9, 13 take the FMA-pipe path
-      const float2 e0 = (POLY && (i & 7) == 2) ? exp2_fma2(x0) : make_float2(ex2_approx(x0.x), ex2_approx(x0.y));
-      const float2 e1 = (POLY && (i & 3) == 0) ? exp2_fma2(x1) : make_float2(ex2_approx(x1.x), ex2_approx(x1.y));
+      const float2 e0 = make_float2(ex2_approx(x0.x), ex2_approx(x0.y));
+      const float2 e1 = make_float2(ex2_approx(x1.x), ex2_approx(x1.y));
       s01 = fadd2(s01, e0);
       s23 = fadd2(s23, e1);
       pk[i] = pack_bf16x2(e0.x, e0.y);
@@ -158,7 +139,7 @@ struct FaTcParams {
 //     exceeds m_used by more than 2^8 — otherwise the probabilities simply run up to 2^8 (exact in the final O / l,
 //     which divides the common factor out) — so O is hardly ever read back;
 //   * each group rescales / stores its own half of the O columns; the two partial row sums are added at the end.
-template <int GROUPS, bool POLY>
+template <int GROUPS>
 __global__ void __launch_bounds__(64 + 128 * GROUPS, 2)
 fa_tc_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
                      const FaTcParams p) {
@@ -348,9 +329,9 @@ fa_tc_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         }
         l_run *= alpha;
         const float base = (m_used == -INFINITY) ? 0.f : m_used * p.scale_log2;
-        l_run += chunk_probs<POLY>(va, full, k0 + grp * 64, kv_len, qpos, p.prefix_len, p.scale_log2, base,
+        l_run += chunk_probs(va, full, k0 + grp * 64, kv_len, qpos, p.prefix_len, p.scale_log2, base,
                                    prow + grp * (BM * 128), 0, r);
-        l_run += chunk_probs<POLY>(vb, full, k0 + grp * 64 + 32, kv_len, qpos, p.prefix_len, p.scale_log2, base,
+        l_run += chunk_probs(vb, full, k0 + grp * 64 + 32, kv_len, qpos, p.prefix_len, p.scale_log2, base,
                                    prow + grp * (BM * 128), 4, r);
         tc_fence_before();
         fence_proxy_async_smem();
@@ -405,11 +386,11 @@ fa_tc_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         for (int cc = 0; cc < 2; ++cc) {
           tmem_ld_wait();
           tmem_ld_32x32(tS + (2 * cc + 1) * 32, vb);
-          l_run += chunk_probs<POLY>(va, full, k0 + (2 * cc) * 32, kv_len, qpos, p.prefix_len, p.scale_log2, base,
+          l_run += chunk_probs(va, full, k0 + (2 * cc) * 32, kv_len, qpos, p.prefix_len, p.scale_log2, base,
                                      prow + cc * (BM * 128), 0, r);
           tmem_ld_wait();
           if (cc == 0) tmem_ld_32x32(tS + 64, va);
-          l_run += chunk_probs<POLY>(vb, full, k0 + (2 * cc + 1) * 32, kv_len, qpos, p.prefix_len, p.scale_log2, base,
+          l_run += chunk_probs(vb, full, k0 + (2 * cc + 1) * 32, kv_len, qpos, p.prefix_len, p.scale_log2, base,
                                      prow + cc * (BM * 128), 4, r);
         }
       }
@@ -472,7 +453,7 @@ int prefill_attention_tc(const __nv_bfloat16* q, int n_heads, int n_kv_heads, in
   if (make_tmap_bf16_2d(&tKV, kv_pool, pool_rows, 64, 64, 64)) return 1;
   static DeviceOnce configured;
   if (configured.first()) {
-    for (auto* fn : {fa_tc_prefill_kernel<1, false>, fa_tc_prefill_kernel<2, false>, fa_tc_prefill_kernel<2, true>}) {
+    for (auto* fn : {fa_tc_prefill_kernel<1>, fa_tc_prefill_kernel<2>}) {
       cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, fa::kSmemTotal);
       if (e != cudaSuccess) return set_error(cudaGetErrorString(e));
       // two CTAs per SM need the full shared-memory carve-out
@@ -487,10 +468,10 @@ int prefill_attention_tc(const __nv_bfloat16* q, int n_heads, int n_kv_heads, in
   p.scale_log2 = 0.125f * 1.4426950408889634f;
   dim3 grid((max_q + fa::BM - 1) / fa::BM, n_heads, n_seqs);
   count_launch();
-  const cudaError_t e =
-      g_attention_impl == 3 ? launch_k(fa_tc_prefill_kernel<2, true>, grid, dim3(fa::kThreads2), fa::kSmemTotal, stream, tQ, tKV, p)
-      : g_attention_impl == 2 ? launch_k(fa_tc_prefill_kernel<2, false>, grid, dim3(fa::kThreads2), fa::kSmemTotal, stream, tQ, tKV, p)
-                              : launch_k(fa_tc_prefill_kernel<1, false>, grid, dim3(fa::kThreads1), fa::kSmemTotal, stream, tQ, tKV, p);
+  // default: the single-pass softmax (GROUPS = 2); md_debug_attention_impl(2) selects the two-pass form for A/B runs
+  const cudaError_t e = g_attention_impl == 2
+      ? launch_k(fa_tc_prefill_kernel<1>, grid, dim3(fa::kThreads1), fa::kSmemTotal, stream, tQ, tKV, p)
+      : launch_k(fa_tc_prefill_kernel<2>, grid, dim3(fa::kThreads2), fa::kSmemTotal, stream, tQ, tKV, p);
   if (e != cudaSuccess) return set_error(cudaGetErrorString(e));
   return 0;
 }
@@ -525,7 +506,7 @@ struct FaVitParams {
 };
 
 // GROUPS = 2: as in fa_tc_prefill_kernel; of the 80 O columns group 0 owns 0..31 and 64..79, group 1 owns 32..63.
-template <int GROUPS, bool POLY>
+template <int GROUPS>
 __global__ void __launch_bounds__(64 + 128 * GROUPS, 2)
 fa_tc_vit_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_constant__ CUtensorMap tm16,
                  const FaVitParams p) {
@@ -709,8 +690,8 @@ fa_tc_vit_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_constant
         }
         l_run *= alpha;
         const float base = (m_used == -INFINITY) ? 0.f : m_used * p.scale_log2;
-        l_run += chunk_probs<POLY>(va, full, k0 + grp * 64, kv_len, qpos, 0, p.scale_log2, base, prow + grp * (BM * 128), 0, r);
-        l_run += chunk_probs<POLY>(vb, full, k0 + grp * 64 + 32, kv_len, qpos, 0, p.scale_log2, base, prow + grp * (BM * 128), 4, r);
+        l_run += chunk_probs(va, full, k0 + grp * 64, kv_len, qpos, 0, p.scale_log2, base, prow + grp * (BM * 128), 0, r);
+        l_run += chunk_probs(vb, full, k0 + grp * 64 + 32, kv_len, qpos, 0, p.scale_log2, base, prow + grp * (BM * 128), 4, r);
         tc_fence_before();
         fence_proxy_async_smem();
         mbar_arrive(p_full);
@@ -763,11 +744,11 @@ fa_tc_vit_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_constant
         for (int cc = 0; cc < 2; ++cc) {
           tmem_ld_wait();
           tmem_ld_32x32(tS + (2 * cc + 1) * 32, vb);
-          l_run += chunk_probs<POLY>(va, full, k0 + (2 * cc) * 32, kv_len, qpos, 0, p.scale_log2, base,
+          l_run += chunk_probs(va, full, k0 + (2 * cc) * 32, kv_len, qpos, 0, p.scale_log2, base,
                                      prow + cc * (BM * 128), 0, r);
           tmem_ld_wait();
           if (cc == 0) tmem_ld_32x32(tS + 64, va);
-          l_run += chunk_probs<POLY>(vb, full, k0 + (2 * cc + 1) * 32, kv_len, qpos, 0, p.scale_log2, base,
+          l_run += chunk_probs(vb, full, k0 + (2 * cc + 1) * 32, kv_len, qpos, 0, p.scale_log2, base,
                                      prow + cc * (BM * 128), 4, r);
         }
       }
@@ -836,7 +817,7 @@ int vit_attention_tc(const __nv_bfloat16* qkv, int n_crops, int seq, int n_heads
   if (make_tmap_bf16_3d(&t16, qkv, 72, 3LL * n_heads, T, 144, 3 * D * 2, 16, 1, 128, 32)) return 1;
   static DeviceOnce configured;
   if (configured.first()) {
-    for (auto* fn : {fa_tc_vit_kernel<1, false>, fa_tc_vit_kernel<2, false>, fa_tc_vit_kernel<2, true>}) {
+    for (auto* fn : {fa_tc_vit_kernel<1>, fa_tc_vit_kernel<2>}) {
       cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, fv::kSmemTotal);
       if (e != cudaSuccess) return set_error(cudaGetErrorString(e));
       e = cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
@@ -848,10 +829,9 @@ int vit_attention_tc(const __nv_bfloat16* qkv, int n_crops, int seq, int n_heads
   p.scale_log2 = (1.0f / sqrtf(72.0f)) * 1.4426950408889634f;
   dim3 grid((seq + fv::BM - 1) / fv::BM, n_heads, n_crops);
   count_launch();
-  const cudaError_t e =
-      g_attention_impl == 3 ? launch_k(fa_tc_vit_kernel<2, true>, grid, dim3(fv::kThreads2), fv::kSmemTotal, stream, t64, t16, p)
-      : g_attention_impl == 2 ? launch_k(fa_tc_vit_kernel<2, false>, grid, dim3(fv::kThreads2), fv::kSmemTotal, stream, t64, t16, p)
-                              : launch_k(fa_tc_vit_kernel<1, false>, grid, dim3(fv::kThreads1), fv::kSmemTotal, stream, t64, t16, p);
+  const cudaError_t e = g_attention_impl == 2
+      ? launch_k(fa_tc_vit_kernel<1>, grid, dim3(fv::kThreads1), fv::kSmemTotal, stream, t64, t16, p)
+      : launch_k(fa_tc_vit_kernel<2>, grid, dim3(fv::kThreads2), fv::kSmemTotal, stream, t64, t16, p);
   if (e != cudaSuccess) return set_error(cudaGetErrorString(e));
   return 0;
 }

@@ -991,7 +991,7 @@ int gemm_smallbatch_splits(int n_out, int K) {
   const int saved = g_gemm_debug;
   int s = 1;
   for (int legacy : {0, 8})
-    for (int m : {64, 128}) {
+    for (int m : {0, 64, 128}) {
       g_gemm_debug = (saved & ~8) | legacy;
       const int w = plan_smallbatch(n_out, K, 0, m).splits;
       if (w > s) s = w;
@@ -1003,7 +1003,9 @@ int gemm_smallbatch_splits(int n_out, int K) {
 int gemm_smallbatch(const __nv_bfloat16* W, long long ldw, const __nv_bfloat16* X, long long ldx,
                  int n_out, int batch, int K, int splits, float* ws, cudaStream_t stream) {
   (void)splits;                                  // the plan decides (callers size ws with gemm_smallbatch_splits)
-  const StreamPlan pl = plan_smallbatch(n_out, K, 0, (!(g_gemm_debug & 64) && batch <= 64) ? 64 : 128);
+  // rows of the activation operand the tensor core re-reads from shared memory per K = 16 step (0: through TMEM)
+  const int m_rows = (g_gemm_debug & 16) ? 0 : (!(g_gemm_debug & 64) && batch <= 64) ? 64 : 128;
+  const StreamPlan pl = plan_smallbatch(n_out, K, 0, m_rows);
   return gemm_smallbatch_impl(W, ldw, X, ldx, n_out, batch, K, pl.kb, pl.tile_rows, ws, stream);
 }
 

@@ -1,6 +1,6 @@
 """One flash-attention launch per implementation (after two warm-ups) for `ncu --set full` captures:
     ncu --set full --clock-control none --import-source on -k regex:fa_tc_ -f -o gpurun_out/fa python tools/attn_profile.py
-runs prefill (32 seqs x 32 heads x 730 x 64) and ViT (64 crops x 16 heads x 729 x 72) with impl 0 and impl 2."""
+runs prefill (32 seqs x 32 heads x 730 x 64) and ViT (64 crops x 16 heads x 729 x 72) with the default (single-pass softmax) and impl 2 (two-pass)."""
 import ctypes
 import os
 import sys
