@@ -152,13 +152,19 @@ fa_tc_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   uint8_t* sP = sV + kStages * kKVBytes;            // 32 KB
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kSmemTiles);
   uint64_t* q_full = bars;                          // 1
-  uint64_t* kv_full = bars + 1;                     // [2]
-  uint64_t* kv_empty = bars + 3;                    // [2]
+  // K and V stages are released separately: K right after its Q K^T (early in the PREVIOUS tile's softmax), V after
+  // its P V.  With one barrier pair per (K, V) stage the load of tile j could only be requested once P V of tile j - 2
+  // had finished, i.e. one softmax ahead of its use — less than an L2 round trip under load, which made the kernel
+  // TMA-latency-bound (softmax warps stalled on s_full, profiles/r02_ncu_attention_summary.json).
+  uint64_t* k_full = bars + 1;                      // [2]
+  uint64_t* k_empty = bars + 3;                     // [2]
   uint64_t* s_full = bars + 5;                      // 1
-  uint64_t* s_empty = bars + 6;                     // 1 (128 arrivals)
-  uint64_t* p_full = bars + 7;                      // 1 (128 arrivals)
+  uint64_t* s_empty = bars + 6;                     // 1 (128 arrivals per softmax warpgroup)
+  uint64_t* p_full = bars + 7;                      // 1 (128 arrivals per softmax warpgroup)
   uint64_t* p_empty = bars + 8;                     // 1
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 9);
+  uint64_t* v_full = bars + 9;                      // [2]
+  uint64_t* v_empty = bars + 11;                    // [2]
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 13);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int head = blockIdx.y, seq = blockIdx.z;
@@ -182,7 +188,10 @@ fa_tc_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   }
   if (warp == 1 && lane == 0) {
     mbar_init(q_full, 1);
-    for (int i = 0; i < kStages; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1);
+      mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1);
+    }
     mbar_init(s_full, 1);
     mbar_init(s_empty, 128 * GROUPS);
     mbar_init(p_full, 128 * GROUPS);
@@ -211,17 +220,23 @@ fa_tc_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       for (int j = 0; j < n_tiles; ++j) {
         const int st = j & 1;
         const uint32_t u = static_cast<uint32_t>(j >> 1);
-        mbar_wait(&kv_empty[st], (u & 1) ^ 1);
-        mbar_arrive_expect_tx(&kv_full[st], 2 * kKVBytes);
+        long long row_k[2];
 #pragma unroll
         for (int h2 = 0; h2 < 2; ++h2) {
           const int blk = min(2 * j + h2, p.max_blocks - 1);
-          const long long row_k = (static_cast<long long>(p.layer) * p.n_pages + btab[blk]) * page_rows +
-                                  static_cast<long long>(kv_head) * 64;
-          tma_load_2d(sK + st * kKVBytes + h2 * (kKVBytes / 2), &tmKV, &kv_full[st], 0, static_cast<int32_t>(row_k));
-          tma_load_2d(sV + st * kKVBytes + h2 * (kKVBytes / 2), &tmKV, &kv_full[st], 0,
-                      static_cast<int32_t>(row_k + static_cast<long long>(p.n_kv_heads) * 64));
+          row_k[h2] = (static_cast<long long>(p.layer) * p.n_pages + btab[blk]) * page_rows + static_cast<long long>(kv_head) * 64;
         }
+        mbar_wait(&k_empty[st], (u & 1) ^ 1);
+        mbar_arrive_expect_tx(&k_full[st], kKVBytes);
+#pragma unroll
+        for (int h2 = 0; h2 < 2; ++h2)
+          tma_load_2d(sK + st * kKVBytes + h2 * (kKVBytes / 2), &tmKV, &k_full[st], 0, static_cast<int32_t>(row_k[h2]));
+        mbar_wait(&v_empty[st], (u & 1) ^ 1);
+        mbar_arrive_expect_tx(&v_full[st], kKVBytes);
+#pragma unroll
+        for (int h2 = 0; h2 < 2; ++h2)
+          tma_load_2d(sV + st * kKVBytes + h2 * (kKVBytes / 2), &tmKV, &v_full[st], 0,
+                      static_cast<int32_t>(row_k[h2] + static_cast<long long>(p.n_kv_heads) * 64));
       }
     }
   } else if (warp == 1) {
@@ -234,6 +249,7 @@ fa_tc_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       mbar_wait(q_full, 0);
       auto issue_pv = [&](int j) {
         const int st = j & 1;
+        mbar_wait(&v_full[st], static_cast<uint32_t>(j >> 1) & 1);
         mbar_wait(p_full, static_cast<uint32_t>(j & 1));
         tc_fence_after();
         const uint32_t sp = smem_u32(sP), sv = smem_u32(sV + st * kKVBytes);
@@ -246,12 +262,12 @@ fa_tc_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           umma_bf16(tO, da, db, idesc_pv, (j > 0 || k > 0) ? 1u : 0u);
         }
         umma_commit(p_empty);            // P buffer reusable, O updated
-        umma_commit(&kv_empty[st]);      // K/V stage reusable
+        umma_commit(&v_empty[st]);       // V stage reusable
       };
       for (int j = 0; j < n_tiles; ++j) {
         const int st = j & 1;
         const uint32_t u = static_cast<uint32_t>(j >> 1);
-        mbar_wait(&kv_full[st], u & 1);
+        mbar_wait(&k_full[st], u & 1);
         mbar_wait(s_empty, static_cast<uint32_t>(j & 1) ^ 1);             // softmax(j-1) has read S
         tc_fence_after();
         const uint64_t dK = make_desc_k_sw128(smem_u32(sK + st * kKVBytes));
@@ -259,6 +275,7 @@ fa_tc_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         for (int k = 0; k < HD / 16; ++k)
           umma_bf16(tS, dQ + static_cast<uint64_t>(2 * k), dK + static_cast<uint64_t>(2 * k), idesc_qk, k > 0 ? 1u : 0u);
         umma_commit(s_full);
+        umma_commit(&k_empty[st]);       // K stage reusable as soon as this Q K^T has read it
         if (j > 0) issue_pv(j - 1);
       }
       issue_pv(n_tiles - 1);

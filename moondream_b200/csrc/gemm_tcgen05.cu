@@ -360,7 +360,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 // ~32 B/clk.  With the weights as A (the first version of this stream) that made time proportional to k-blocks
 // and independent of tile height (72-row tiles streamed at 4.3 TB/s chip-wide); as the B operand the weight
 // bytes per k-block can grow to 256 rows for the same A-operand cost, which is what the split plans exploit.
-// Halving the A-operand read (M = 64 MMAs, or the activation tile held in TMEM) is the remaining lever.
+// Halving the A-operand read with M = 64 MMAs paid (layer period 78 -> 71 us); feeding the activation tile through TMEM
+// instead (tcgen05.st into a ring of A slots, tcgen05.mma with a TMEM A operand, M = 128) was built, is bit-identical,
+// and is slower (stream 12 -> 17-18 us: it behaves like the M = 128 shared-memory form), so it was removed again
+// (profiles/r02_decode_timeline_tsmode.json).
 //
 // One CTA per (weight-row tile, K split), all resident at once (the plan keeps tiles * splits <= #SMs where
 // it can).  Under programmatic dependent launch the weight tiles of the first ring of stages are requested
@@ -384,12 +387,7 @@ struct SmallBatchParams {
 // MROWS = 128 is the shipped form.  MROWS = 64 (batch <= 64; selected by md_debug_gemm bit 6 until it has been
 // validated on hardware) issues M = 64 MMAs: half the A-operand read per K = 16 step, accumulator rows
 // 16q .. 16q+15 in lanes 0..15 of TMEM lane quadrant q (the 1-CTA M = 64 data-path layout).
-// TS = true (MROWS = 128): the activation tile goes through TENSOR memory instead of being re-read from shared memory by
-// every MMA: warps 4..7 (idle during the main loop; warp q = TMEM lane quadrant q = batch rows 32q..32q+31) copy their
-// rows of each stage's activation tile shared memory -> registers -> tcgen05.st into a ring of 32-column A slots (one per
-// stage), and the MMAs take A from there (tcgen05.mma with a TMEM A operand).  Only the weight tile is then fetched from
-// shared memory by the tensor core: 32 B/clk of weights per SM instead of 32 * rows / (m_rows + rows).
-template <int MROWS, bool TS = false>
+template <int MROWS>
 __global__ void __launch_bounds__(kSbThreads, 1)
 smallbatch_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
                        const SmallBatchParams p) {
@@ -400,8 +398,6 @@ smallbatch_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
   uint64_t* empty_bar = full_bar + kSbMaxStages;
   uint64_t* tmem_full = empty_bar + kSbMaxStages;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_full + 1);
-  uint64_t* a_ready = reinterpret_cast<uint64_t*>(tmem_ptr_smem + 2);      // [kSbMaxStages], TS only
-  constexpr uint32_t kColA = 256;           // TS: A slots at columns 256 + 32 * stage (accumulator: columns 0..255)
   __shared__ unsigned long long tl_s[5];    // debug timeline stamps (see ptx.cuh), untouched unless installed
   const bool tl = tl_on();
   if (tl && threadIdx.x == 0) tl_s[0] = tl_now();
@@ -417,7 +413,6 @@ smallbatch_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
     for (int i = 0; i < p.stages; ++i) {
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
-      if (TS) mbar_init(&a_ready[i], 128);
     }
     mbar_init(tmem_full, 1);
     fence_barrier_init();
@@ -479,17 +474,10 @@ smallbatch_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
         const uint32_t sx = smem_u32(smem + stage * p.stage_bytes);
         const uint64_t da = make_desc_k_sw128(sx);
         const uint64_t db = make_desc_k_sw128(sx + static_cast<uint32_t>(p.a_bytes));
-        if (TS) {
-          mbar_wait(&a_ready[stage], phase);                  // this stage's activation rows are in their TMEM slot
-          tc_fence_after();
-        }
 #pragma unroll
-        for (int k = 0; k < BK / 16; ++k) {
-          if (TS) umma_bf16_ts(tmem_base, tmem_base + kColA + static_cast<uint32_t>(stage * 32 + k * 8),
-                               db + static_cast<uint64_t>(2 * k), idesc, (j > 0 || k > 0) ? 1u : 0u);
-          else umma_bf16(tmem_base, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k), idesc,
-                         (j > 0 || k > 0) ? 1u : 0u);
-        }
+        for (int k = 0; k < BK / 16; ++k)
+          umma_bf16(tmem_base, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k), idesc,
+                    (j > 0 || k > 0) ? 1u : 0u);
         umma_commit(&empty_bar[stage]);
         if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
@@ -500,34 +488,6 @@ smallbatch_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
     // 16q .. 16q+15 in its first 16 lanes (M = 64)
     constexpr int kRowsPerWarp = MROWS / 4;
     const int q = warp - 4;
-    if (TS) {
-      // activation rows of every stage: shared memory (128B-swizzled TMA image, row = 128 B = 64 K values) -> TMEM slot.
-      // Rows at or beyond the TMA box hold nothing: their lanes get zeros (their accumulator rows are never stored).
-      const int row = q * 32 + lane;
-      const bool have = row * 128 < p.a_bytes;
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int j = 0; j < nk; ++j) {
-        mbar_wait(&full_bar[stage], phase);
-        uint32_t v[32];
-        if (have) {
-          const uint8_t* src = smem + stage * p.stage_bytes + row * 128;
-#pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            const uint4 u = *reinterpret_cast<const uint4*>(src + ((c ^ (row & 7)) << 4));
-            v[4 * c] = u.x; v[4 * c + 1] = u.y; v[4 * c + 2] = u.z; v[4 * c + 3] = u.w;
-          }
-        } else {
-#pragma unroll
-          for (int c = 0; c < 32; ++c) v[c] = 0u;
-        }
-        tmem_st_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + kColA + static_cast<uint32_t>(stage * 32), v);
-        tmem_st_wait();
-        tc_fence_before();
-        mbar_arrive(&a_ready[stage]);
-        if (++stage == p.stages) { stage = 0; phase ^= 1; }
-      }
-    }
     pdl_wait();                              // ws is still being read by the predecessor's consumers
     if (q * kRowsPerWarp < p.batch) {
       const int b = (lane < kRowsPerWarp) ? q * kRowsPerWarp + lane : p.batch;   // surplus lanes store nothing
@@ -935,9 +895,6 @@ static int gemm_smallbatch_impl(const __nv_bfloat16* W, long long ldw, const __n
     p.seg_splits = p.k_splits; p.seg_kb = p.k_blocks; p.kb_per_split2 = kb_per_split;
   }
   p.tmem_cols = p.n_mma <= 32 ? 32 : p.n_mma <= 64 ? 64 : p.n_mma <= 128 ? 128 : 256;
-  // md_debug_gemm bit 4: activation tile through tensor memory (TS-mode MMAs), A/B pending
-  const bool ts = (g_gemm_debug & 16) != 0;
-  if (ts) p.tmem_cols = 512;                     // accumulator (<= 256 columns) + up to 8 A slots of 32 columns
   p.trigger_early = g_pdl >= 2 ? 1 : 0;
   constexpr int kSbSmemMax = 227 * 1024 - 1024;      // leave room for the kernel's few static __shared__ words
   static DeviceOnce configured;
@@ -948,12 +905,7 @@ static int gemm_smallbatch_impl(const __nv_bfloat16* W, long long ldw, const __n
   // batches <= 64 use M = 64 MMAs: half the activation-operand shared-memory read per k-block, which is what bounds
   // the stream (decode layer period 78.1 -> 70.7 us, tools/decode_timeline.py, profiles/r02_decode_timeline_m64.json);
   // md_debug_gemm bit 6 forces the M = 128 instantiation for A/B runs.
-  const bool m64 = !ts && !(g_gemm_debug & 64) && batch <= 64;
-  static DeviceOnce configured_ts;
-  if (ts && configured_ts.first()) {
-    cudaError_t e = cudaFuncSetAttribute(smallbatch_gemm_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSbSmemMax);
-    if (e != cudaSuccess) { set_error(cudaGetErrorString(e)); return -1; }
-  }
+  const bool m64 = !(g_gemm_debug & 64) && batch <= 64;
   static DeviceOnce configured64;
   if (m64 && configured64.first()) {
     cudaError_t e = cudaFuncSetAttribute(smallbatch_gemm_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSbSmemMax);
@@ -966,10 +918,9 @@ static int gemm_smallbatch_impl(const __nv_bfloat16* W, long long ldw, const __n
     const int a_rows = (p.batch + 7) / 8 * 8;
     p.a_bytes = a_rows * BK * 2;                     // a multiple of 1024: the weight tile stays swizzle-aligned
     p.stage_bytes = p.a_bytes + p.n_mma * BK * 2;
-    const int bar_bytes = (3 * kSbMaxStages + 1) * 8 + 16;
+    const int bar_bytes = (2 * kSbMaxStages + 1) * 8 + 16;
     p.stages = (kSbSmemMax - 1024 - kSbTailPad - bar_bytes) / p.stage_bytes;
     if (p.stages > kSbMaxStages) p.stages = kSbMaxStages;
-    if (ts && p.stages > 8) p.stages = 8;          // 8 A slots of 32 TMEM columns
     if (p.stages < 2) { set_error("small-batch GEMM: tile does not fit shared memory"); return -1; }
     p.ws = ws + static_cast<long long>(b0) * n_out;
     CUtensorMap tX;
@@ -978,9 +929,8 @@ static int gemm_smallbatch_impl(const __nv_bfloat16* W, long long ldw, const __n
     count_launch();
     const dim3 grid(n_tiles * p.k_splits), block(kSbThreads);
     const size_t smem = static_cast<size_t>(smem_bytes);
-    const cudaError_t e = ts ? launch_k(smallbatch_gemm_kernel<128, true>, grid, block, smem, stream, tX, tW, p)
-                          : m64 ? launch_k(smallbatch_gemm_kernel<64>, grid, block, smem, stream, tX, tW, p)
-                                : launch_k(smallbatch_gemm_kernel<128>, grid, block, smem, stream, tX, tW, p);
+    const cudaError_t e = m64 ? launch_k(smallbatch_gemm_kernel<64>, grid, block, smem, stream, tX, tW, p)
+                              : launch_k(smallbatch_gemm_kernel<128>, grid, block, smem, stream, tX, tW, p);
     if (e != cudaSuccess) { set_error(cudaGetErrorString(e)); return -1; }
   }
   return p.k_splits;
@@ -991,7 +941,7 @@ int gemm_smallbatch_splits(int n_out, int K) {
   const int saved = g_gemm_debug;
   int s = 1;
   for (int legacy : {0, 8})
-    for (int m : {0, 64, 128}) {
+    for (int m : {64, 128}) {
       g_gemm_debug = (saved & ~8) | legacy;
       const int w = plan_smallbatch(n_out, K, 0, m).splits;
       if (w > s) s = w;
@@ -1003,9 +953,7 @@ int gemm_smallbatch_splits(int n_out, int K) {
 int gemm_smallbatch(const __nv_bfloat16* W, long long ldw, const __nv_bfloat16* X, long long ldx,
                  int n_out, int batch, int K, int splits, float* ws, cudaStream_t stream) {
   (void)splits;                                  // the plan decides (callers size ws with gemm_smallbatch_splits)
-  // rows of the activation operand the tensor core re-reads from shared memory per K = 16 step (0: through TMEM)
-  const int m_rows = (g_gemm_debug & 16) ? 0 : (!(g_gemm_debug & 64) && batch <= 64) ? 64 : 128;
-  const StreamPlan pl = plan_smallbatch(n_out, K, 0, m_rows);
+  const StreamPlan pl = plan_smallbatch(n_out, K, 0, (!(g_gemm_debug & 64) && batch <= 64) ? 64 : 128);
   return gemm_smallbatch_impl(W, ldw, X, ldx, n_out, batch, K, pl.kb, pl.tile_rows, ws, stream);
 }
 

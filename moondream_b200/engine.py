@@ -1140,6 +1140,58 @@ class Engine:
                                                   N.ptr(out), N.current_stream()), "md_region_bins_to_values")
         return out
 
+    def _points_buffers(self, st: dict, B: int):
+        if "pt_h" not in st:
+            dev, t = self.device, self.cfg.text
+            st["pt_h"] = torch.empty((B, t.dim), dtype=torch.bfloat16, device=dev)      # hidden state entering an object
+            st["pt_e"] = torch.empty((B, t.dim), dtype=torch.bfloat16, device=dev)
+            st["pt_xb"] = torch.zeros((B,), dtype=torch.int32, device=dev)
+            st["pt_yb"] = torch.zeros((B,), dtype=torch.int32, device=dev)
+            st["pt_sb"] = torch.zeros((B, 2), dtype=torch.int32, device=dev)
+            st["pt_xv"] = torch.zeros((B, 1), dtype=torch.float32, device=dev)
+            st["pt_yv"] = torch.zeros((B, 1), dtype=torch.float32, device=dev)
+            st["pt_sv"] = torch.zeros((B, 2), dtype=torch.float32, device=dev)
+            st["pt_nxt"] = torch.zeros((B,), dtype=torch.int32, device=dev)
+            st["pt_region_ws"] = torch.empty(int(self.lib.md_region_workspace_bytes(self.model, B)), dtype=torch.uint8,
+                                             device=dev)
+            st["pt_graphs"] = {}
+
+    def _points_object_launch(self, st: dict, B: int, include_size: bool):
+        """One object of `_generate_points` (moondream.py:653-733) for the whole batch, graph-capturable:
+        x = decode_coordinate(h); h = decoder(encode_coordinate(x)); y likewise; [size likewise;] next token = lm_head(h)."""
+        lib, s = self.lib, N.current_stream()
+        r = self.cfg.region
+        kv = self._kv(st["bt"])
+        H, E, rws = st["pt_h"], st["pt_e"], st["pt_region_ws"]
+
+        def dec(which, hid, bins):
+            N.check(lib.md_region_decode(self.model, which, N.ptr(hid), hid.stride(0), B, N.ptr(bins), N.ptr(rws), s),
+                    "md_region_decode")
+
+        def b2v(which, bins, out):
+            N.check(lib.md_region_bins_to_values(which, N.ptr(bins), bins.numel(), r.coord_out_dim, N.ptr(out), s),
+                    "md_region_bins_to_values")
+
+        def enc(which, vals, out):
+            N.check(lib.md_region_encode(self.model, which, N.ptr(vals), B, N.ptr(out), out.stride(0), N.ptr(rws), s),
+                    "md_region_encode")
+
+        def step(x):                       # in place: x becomes the hidden state after this token
+            N.check(lib.md_text_decode_step(self.model, N.ptr(x), N.ptr(st["pos"]), B, ctypes.byref(kv), None,
+                                            N.ptr(st["ws"]), s), "md_text_decode_step")
+            st["pos"].add_(1)
+
+        dec(0, H, st["pt_xb"]); b2v(0, st["pt_xb"], st["pt_xv"]); enc(0, st["pt_xv"], E); step(E)
+        dec(0, E, st["pt_yb"]); b2v(0, st["pt_yb"], st["pt_yv"]); enc(0, st["pt_yv"], H)
+        if include_size:
+            step(H)
+            dec(1, H, st["pt_sb"]); b2v(1, st["pt_sb"], st["pt_sv"]); enc(1, st["pt_sv"], E); step(E)
+            H.copy_(E)
+        else:
+            step(H)
+        off = int(lib.md_text_decode_workspace_bytes(self.model, B))
+        self.lm_head(H, st["pt_nxt"], 1, ws=st["ws"][off:])
+
     @_on_device
     def generate_points(self, prefixes: Sequence[PrefixKV], prompts: Sequence[Sequence[int]],
                         include_size: bool, max_objects: int, lora: Optional["LoraVariant"] = None) -> List[List[dict]]:
@@ -1168,29 +1220,62 @@ class Engine:
             nxt = torch.empty((B,), dtype=torch.int32, device=self.device)
             self.lm_head(hidden, nxt, 1)
             pos = self._i32([prefixes[i].pos + lens[i] for i in range(B)])
-            ws = torch.empty(int(self.lib.md_text_decode_workspace_bytes(self.model, B)), dtype=torch.uint8,
-                             device=self.device)
-            kv = self._kv(bt)
-
             host_pos = [prefixes[i].pos + lens[i] for i in range(B)]
-
-            def step(emb):
-                if lora is not None:       # a variant: the adapter-aware decoder over one row per sequence
-                    self.prefill(emb, list(range(B + 1)), list(host_pos), bt, lora=lora)
-                else:
-                    N.check(self.lib.md_text_decode_step(self.model, N.ptr(emb), N.ptr(pos), B, ctypes.byref(kv),
-                                                         None, N.ptr(ws), N.current_stream()), "md_text_decode_step")
-                pos.add_(1)
-                for b_ in range(B):
-                    host_pos[b_] += 1
-                return emb
-
             active = [True] * B
             tok_host = nxt.tolist()
             for b in range(B):
                 if tok_host[b] == tk.eos_id:
                     active[b] = False
             n_obj = 0
+            if lora is None:
+                # one CUDA graph per object: region decode / encode, the 2 or 3 decode steps between them and the LM head
+                # (~300 launches) replay without host involvement; one host sync per object reads the results
+                st = self._decode_buffers(B)
+                self._points_buffers(st, B)
+                st["bt"].zero_()
+                st["bt"][:, : bt.shape[1]].copy_(bt)
+                st["pos"].copy_(pos)
+                st["pt_h"].copy_(hidden)
+                graph = st["pt_graphs"].get(include_size)
+                if graph is None and any(active) and max_objects > 0:
+                    keep = st["pt_h"].clone()
+                    self._points_object_launch(st, B, include_size)       # warm-up (also validates)
+                    torch.cuda.synchronize()
+                    st["pos"].sub_(steps_per_obj)                          # rewind what the warm-up advanced
+                    st["pt_h"].copy_(keep)
+                    graph = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(graph):
+                        self._points_object_launch(st, B, include_size)
+                    st["pt_graphs"][include_size] = graph
+                while any(active) and n_obj < max_objects:
+                    graph.replay()
+                    xh, yh, tok_host = st["pt_xv"].view(B).tolist(), st["pt_yv"].view(B).tolist(), st["pt_nxt"].tolist()
+                    xbh, ybh = st["pt_xb"].tolist(), st["pt_yb"].tolist()
+                    if include_size:
+                        sh, sbh = st["pt_sv"].tolist(), st["pt_sb"].tolist()
+                    for b in range(B):
+                        if not active[b]:
+                            continue
+                        if include_size:
+                            w, h = sh[b]
+                            results[b].append({"x_min": xh[b] - w / 2, "y_min": yh[b] - h / 2,
+                                               "x_max": xh[b] + w / 2, "y_max": yh[b] + h / 2,
+                                               "bins": [xbh[b], ybh[b], sbh[b][0], sbh[b][1]]})
+                        else:
+                            results[b].append({"x": xh[b], "y": yh[b], "bins": [xbh[b], ybh[b]]})
+                        if tok_host[b] == tk.eos_id:
+                            active[b] = False
+                    n_obj += 1
+                return results
+
+            # a LoRA variant: the adapter-aware decoder over one row per sequence, launched eagerly
+            def step(emb):
+                self.prefill(emb, list(range(B + 1)), list(host_pos), bt, lora=lora)
+                pos.add_(1)
+                for b_ in range(B):
+                    host_pos[b_] += 1
+                return emb
+
             while any(active) and n_obj < max_objects:
                 xb = self.region_decode(0, hidden)
                 xv = self._bins_to_values(0, xb)

@@ -128,30 +128,3 @@ def test_linear_small_batch_forced_m128(B, N, K):
     finally:
         N_.lib().md_debug_gemm(0)
     _close(y, _ref(x, w, b, 0, None), f"small-batch M=128 {B}x{N}x{K}")
-
-
-@pytest.mark.parametrize("B,N,K", [(32, 14336, 2048), (32, 2048, 8192), (5, 1024, 8192), (64, 8192, 2048), (17, 1032, 264),
-                                   (128, 3072, 1024), (200, 2048, 1024)])
-def test_linear_small_batch_ts_mode(B, N, K):
-    """md_debug_gemm bit 4: the activation tile reaches the tensor core through TMEM (tcgen05.mma with a TMEM A operand)
-    instead of shared memory.  Same MMA shapes and order as the M = 128 shared-memory form -> identical bits when both
-    run the same split plan (bit 3 = the plan that does not depend on the operand-read model)."""
-    from moondream_b200 import _native as N_, ops
-
-    g = torch.Generator(device="cuda").manual_seed(B + N + K)
-    x = torch.randn(B, K, device="cuda", generator=g).bfloat16()
-    w = (torch.randn(N, K, device="cuda", generator=g) / K ** 0.5).bfloat16()
-    b = torch.randn(N, device="cuda", generator=g).bfloat16()
-    try:
-        N_.lib().md_debug_gemm(64 | 8)
-        want = ops.linear_small_batch(x, w, b, epilogue=0)
-        N_.lib().md_debug_gemm(16 | 8)
-        got = ops.linear_small_batch(x, w, b, epilogue=0)
-        N_.lib().md_debug_gemm(16)
-        own_plan = ops.linear_small_batch(x, w, b, epilogue=0)
-        torch.cuda.synchronize()
-    finally:
-        N_.lib().md_debug_gemm(0)
-    _close(got, _ref(x, w, b, 0, None), f"small-batch TS {B}x{N}x{K}")
-    _close(own_plan, _ref(x, w, b, 0, None), f"small-batch TS (own plan) {B}x{N}x{K}")
-    assert torch.equal(got, want)
