@@ -117,6 +117,16 @@ __device__ __forceinline__ float chunk_probs(const uint32_t (&v)[32], bool full,
   return (a0 + a1) + (a2 + a3);
 }
 
+// Boundary tiles of the single-pass softmax: a key is visible to a query row iff its position is below the row's limit
+// (kv_len for ViT; under the prefix-LM mask min(kv_len, qpos < prefix ? max(qpos + 1, prefix) : qpos + 1)), so masking
+// a 32-score chunk is one compare + select per element against n_valid = limit - first key; the scores become -inf
+// and the unmasked fast paths (packed FFMA2 / FADD2, ex2(-inf) = 0) run on every tile.  (The per-element predicate +
+// scalar accumulation the two-pass kernel uses on boundary tiles made that one tile in six cost several full tiles.)
+__device__ __forceinline__ void mask_chunk(uint32_t (&v)[32], int n_valid) {
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = (i < n_valid) ? v[i] : 0xff800000u;
+}
+
 struct FaTcParams {
   const int* q_offsets;     // [n_seqs + 1]
   const int* start_pos;     // [n_seqs]
@@ -293,6 +303,8 @@ fa_tc_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     const int q_lo = q_pos0 + q0;                          // smallest query position of this CTA
     uint8_t* prow = sP + r * 128;
     float m_used = -INFINITY;                             // GROUPS = 2: the maximum O and l are currently scaled by
+    // first key position this row may NOT attend to (prefix-LM mask of moondream.py:138-146 + sequence length)
+    const int row_lim = min(kv_len, qpos < p.prefix_len ? max(qpos + 1, p.prefix_len) : qpos + 1);
     for (int j = 0; j < n_tiles; ++j) {
       const int k0 = j * BN;
       // interior tiles need no masking: every key exists and every row of the CTA may attend to it
@@ -308,8 +320,11 @@ fa_tc_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         tmem_ld_wait();
         tc_fence_before();
         mbar_arrive(s_empty);                             // S may be overwritten by the next Q K^T
-        const float pm = fmaxf(chunk_max(va, full, k0 + grp * 64, kv_len, qpos, p.prefix_len),
-                               chunk_max(vb, full, k0 + grp * 64 + 32, kv_len, qpos, p.prefix_len));
+        if (!full) {                                      // tile-uniform: boundary tiles only
+          mask_chunk(va, row_lim - (k0 + grp * 64));
+          mask_chunk(vb, row_lim - (k0 + grp * 64 + 32));
+        }
+        const float pm = fmaxf(chunk_max(va, true, 0, 0, 0, 0), chunk_max(vb, true, 0, 0, 0, 0));
         const uint32_t tX = tmem_base + lane_addr + kColX + 2 * (j & 1);
         tmem_st_32x1(tX + grp, __float_as_uint(pm));
         tmem_st_wait();
@@ -346,10 +361,8 @@ fa_tc_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         }
         l_run *= alpha;
         const float base = (m_used == -INFINITY) ? 0.f : m_used * p.scale_log2;
-        l_run += chunk_probs(va, full, k0 + grp * 64, kv_len, qpos, p.prefix_len, p.scale_log2, base,
-                                   prow + grp * (BM * 128), 0, r);
-        l_run += chunk_probs(vb, full, k0 + grp * 64 + 32, kv_len, qpos, p.prefix_len, p.scale_log2, base,
-                                   prow + grp * (BM * 128), 4, r);
+        l_run += chunk_probs(va, true, 0, 0, 0, 0, p.scale_log2, base, prow + grp * (BM * 128), 0, r);
+        l_run += chunk_probs(vb, true, 0, 0, 0, 0, p.scale_log2, base, prow + grp * (BM * 128), 4, r);
         tc_fence_before();
         fence_proxy_async_smem();
         mbar_arrive(p_full);
@@ -666,8 +679,11 @@ fa_tc_vit_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_constant
         tmem_ld_wait();
         tc_fence_before();
         mbar_arrive(s_empty);
-        const float pm = fmaxf(chunk_max(va, full, k0 + grp * 64, kv_len, qpos, 0),
-                               chunk_max(vb, full, k0 + grp * 64 + 32, kv_len, qpos, 0));
+        if (!full) {
+          mask_chunk(va, kv_len - (k0 + grp * 64));
+          mask_chunk(vb, kv_len - (k0 + grp * 64 + 32));
+        }
+        const float pm = fmaxf(chunk_max(va, true, 0, 0, 0, 0), chunk_max(vb, true, 0, 0, 0, 0));
         const uint32_t tX = tmem_base + lane_addr + kColX + 2 * (j & 1);
         tmem_st_32x1(tX + grp, __float_as_uint(pm));
         tmem_st_wait();
@@ -707,8 +723,8 @@ fa_tc_vit_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_constant
         }
         l_run *= alpha;
         const float base = (m_used == -INFINITY) ? 0.f : m_used * p.scale_log2;
-        l_run += chunk_probs(va, full, k0 + grp * 64, kv_len, qpos, 0, p.scale_log2, base, prow + grp * (BM * 128), 0, r);
-        l_run += chunk_probs(vb, full, k0 + grp * 64 + 32, kv_len, qpos, 0, p.scale_log2, base, prow + grp * (BM * 128), 4, r);
+        l_run += chunk_probs(va, true, 0, 0, 0, 0, p.scale_log2, base, prow + grp * (BM * 128), 0, r);
+        l_run += chunk_probs(vb, true, 0, 0, 0, 0, p.scale_log2, base, prow + grp * (BM * 128), 4, r);
         tc_fence_before();
         fence_proxy_async_smem();
         mbar_arrive(p_full);

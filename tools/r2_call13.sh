@@ -1,0 +1,10 @@
+#!/usr/bin/env bash
+# Round 2, call 13: single-pass softmax with select-based boundary masking.
+set -u
+mkdir -p gpurun_out
+O=gpurun_out
+echo "== [1] kernel tests + model parity"
+timeout 900 python -m pytest tests/test_kernels_gpu.py tests/test_model_parity_gpu.py tests/test_features_gpu.py -q -m gpu > $O/c13_pytest_a.log 2>&1
+echo "rc=$?"; grep -E "passed|failed|error" $O/c13_pytest_a.log | tail -3; grep -E "^(FAILED|ERROR)|Error|assert |error" $O/c13_pytest_a.log | head -30 | cut -c1-300
+echo "== [2] attention kernels A/B"
+timeout 300 python tools/attn_bench.py 2>&1 | tail -12
