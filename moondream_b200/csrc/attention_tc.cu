@@ -29,7 +29,10 @@ constexpr int kQBytes = BM * HD * 2;            // 16 KB
 constexpr int kKVBytes = BN * HD * 2;           // 16 KB each for K and V
 constexpr int kPBytes = BM * BN * 2;            // 32 KB (two 64-key blocks of [128 x 64])
 constexpr int kSmemTiles = kQBytes + kStages * 2 * kKVBytes + kPBytes;   // 112 KB
-constexpr int kSmemTotal = kSmemTiles + 256;   // two CTAs per SM: 2 x (kSmemTotal + 1 KB reserved) <= 228 KB
+// barriers (256 B) + the 512-byte base-agreement buffer of the single-pass softmax; two CTAs per SM:
+// 2 x (kSmemTotal + 1 KB reserved) <= 228 KB.  (Static __shared__ would be padded to the 1024-byte alignment of the
+// tiles and no longer fit.)
+constexpr int kSmemTotal = kSmemTiles + 256 + 512;
 constexpr int kThreads1 = 192, kThreads2 = 320;   // one / two softmax warpgroups (see the kernel's softmax section)
 constexpr uint32_t kTmemCols = 256;
 constexpr uint32_t kColS = 0, kColO = 128, kColX = 224;   // X: four spare columns for the row-maximum exchange
@@ -73,8 +76,27 @@ __device__ __forceinline__ float chunk_max(const uint32_t (&v)[32], bool full, i
 
 // exp2(s * scale - base) for one 32-score chunk -> bf16 -> four swizzled 16-byte chunks of the row's
 // 128-byte line (chunk slots chunk0 .. chunk0+3); returns the row-sum contribution.
-// (Evaluating 3 of every 8 exponential pairs with an FMA-pipe cubic instead of MUFU.EX2 was measured twice — over the
-// two-pass and over the single-pass softmax — and changed nothing (profiles/r02_attention_ab.json): XU runs at 40 %.)
+// POLY: pairs 1, 2, 5 of every 8 go through exp2_fma2 (FMA pipe) instead of MUFU.EX2.  It bought nothing while the
+// boundary tile and the TMEM round trips dominated (profiles/r02_attention_ab.json); with those gone the per-phase clocks
+// (tools/attn_phases.py) show the exponentials + pack + store phase at 1490 of 3990 clocks per tile, paced by the
+// 16-per-clock MUFU shared by four softmax warps per SM sub-partition.
+// 2^x on the FMA pipe: x = n + f with n = round(x) taken from the low mantissa bits of x + 1.5 * 2^23 and f in
+// [-0.5, 0.5]; 2^f by a minimax cubic (relative error <= 7.5e-5, a fiftieth of a bf16 ulp: the result is rounded to
+// bf16 right after); 2^n by adding n to the exponent field.
+__device__ __forceinline__ float2 exp2_fma2(float2 x) {
+  const float kMagic = 12582912.f;                       // 1.5 * 2^23
+  x.x = fmaxf(x.x, -125.f);
+  x.y = fmaxf(x.y, -125.f);
+  const float2 t = fadd2(x, make_float2(kMagic, kMagic));
+  const float2 n = fadd2(t, make_float2(-kMagic, -kMagic));
+  const float2 f = ffma2(n, make_float2(-1.f, -1.f), x);
+  float2 q = ffma2(f, make_float2(0.05517146f, 0.05517146f), make_float2(0.24261086f, 0.24261086f));
+  q = ffma2(q, f, make_float2(0.69326099f, 0.69326099f));
+  q = ffma2(q, f, make_float2(0.99992809f, 0.99992809f));
+  return make_float2(__int_as_float(__float_as_int(q.x) + (__float_as_int(t.x) << 23)),
+                     __int_as_float(__float_as_int(q.y) + (__float_as_int(t.y) << 23)));
+}
+template <bool POLY = false>
 __device__ __forceinline__ float chunk_probs(const uint32_t (&v)[32], bool full, int k_first, int kv_len, int qpos,
                                              int prefix_len, float scale_log2, float base, uint8_t* line,
                                              int chunk0, int r) {
@@ -87,8 +109,9 @@ __device__ __forceinline__ float chunk_probs(const uint32_t (&v)[32], bool full,
     for (int i = 0; i < 16; i += 2) {
       const float2 x0 = ffma2(make_float2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1])), sc, nb);
       const float2 x1 = ffma2(make_float2(__uint_as_float(v[2 * i + 2]), __uint_as_float(v[2 * i + 3])), sc, nb);
-      const float2 e0 = make_float2(ex2_approx(x0.x), ex2_approx(x0.y));
-      const float2 e1 = make_float2(ex2_approx(x1.x), ex2_approx(x1.y));
+      // i is a compile-time constant after unrolling: pairs i = 2, 10 and i + 1 = 1, 5, 9, 13 take the FMA-pipe path
+      const float2 e0 = (POLY && (i & 7) == 2) ? exp2_fma2(x0) : make_float2(ex2_approx(x0.x), ex2_approx(x0.y));
+      const float2 e1 = (POLY && (i & 3) == 0) ? exp2_fma2(x1) : make_float2(ex2_approx(x1.x), ex2_approx(x1.y));
       s01 = fadd2(s01, e0);
       s23 = fadd2(s23, e1);
       pk[i] = pack_bf16x2(e0.x, e0.y);
@@ -127,6 +150,27 @@ __device__ __forceinline__ void mask_chunk(uint32_t (&v)[32], int n_valid) {
   for (int i = 0; i < 32; ++i) v[i] = (i < n_valid) ? v[i] : 0xff800000u;
 }
 
+// V3 agreement on the scaling base (see fa_tc_prefill_kernel): returns the rescale factor for O and l (1 = none).
+// b_used: current base / 2 as an integer, -128 = nothing accumulated yet.  xq: [tile parity][group][row].
+__device__ __forceinline__ float agree_base_v3(float pm, float scale_log2, int j, int grp, int r,
+                                               signed char (*xq)[2][128], int& b_used, bool& grow) {
+  int pq = -128;
+  if (pm != -INFINITY) pq = max(-127, min(127, __float2int_ru(pm * scale_log2 * 0.5f)));
+  xq[j & 1][grp][r] = static_cast<signed char>(pq);
+  softmax_bar_sync(256);
+  const int tq = max(pq, static_cast<int>(xq[j & 1][grp ^ 1][r]));
+  float alpha = 1.f;
+  grow = false;
+  if (b_used == -128) {
+    b_used = tq;
+  } else if (tq - b_used > 4) {                           // the row maximum grew by more than 2^8
+    alpha = __int_as_float(max(0, 127 + 2 * (b_used - tq)) << 23);       // exact 2^(2 (b_used - tq)), 0 below 2^-126
+    b_used = tq;
+    grow = true;
+  }
+  return alpha;
+}
+
 struct FaTcParams {
   const int* q_offsets;     // [n_seqs + 1]
   const int* start_pos;     // [n_seqs]
@@ -149,7 +193,11 @@ struct FaTcParams {
 //     exceeds m_used by more than 2^8 — otherwise the probabilities simply run up to 2^8 (exact in the final O / l,
 //     which divides the common factor out) — so O is hardly ever read back;
 //   * each group rescales / stores its own half of the O columns; the two partial row sums are added at the end.
-template <int GROUPS>
+// V3 (GROUPS = 2 only): the two groups agree on the scaling base through 512 bytes of shared memory instead of TMEM
+// columns — each publishes ceil(partial maximum * scale / 2) as one signed byte (an UPPER bound, granularity 2 in the
+// log2 domain: any common base is exact after the final O / l, it only has to keep 2^(s - base) in range), the base is
+// an integer, the lazy rescale factor an exact power of two — and 3 of 8 exponential pairs run on the FMA pipe.
+template <int GROUPS, bool PROF = false, bool V3 = true>
 __global__ void __launch_bounds__(64 + 128 * GROUPS, 2)
 fa_tc_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
                      const FaTcParams p) {
@@ -303,16 +351,25 @@ fa_tc_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     const int q_lo = q_pos0 + q0;                          // smallest query position of this CTA
     uint8_t* prow = sP + r * 128;
     float m_used = -INFINITY;                             // GROUPS = 2: the maximum O and l are currently scaled by
+    int b_used = -128;                                    // V3: the same as an integer base / 2 (-128 = none yet)
+    signed char (*xq)[2][128] = reinterpret_cast<signed char (*)[2][128]>(smem + kSmemTiles + 256);
     // first key position this row may NOT attend to (prefix-LM mask of moondream.py:138-146 + sequence length)
     const int row_lim = min(kv_len, qpos < p.prefix_len ? max(qpos + 1, p.prefix_len) : qpos + 1);
+    // debug timeline (tools/attn_phases.py): clock sums of the phases of one softmax thread
+    const bool tlp = PROF && tl_on() && threadIdx.x == 64;      // PROF: md_debug_attention_impl(3), profiling launches only
+    long long ph[6] = {0, 0, 0, 0, 0, 0}, tc0 = 0;
+    auto tick = [&](int i) { if (tlp) { const long long now = clock64(); ph[i] += now - tc0; tc0 = now; } };
+    const long long t_begin = tlp ? clock64() : 0;
     for (int j = 0; j < n_tiles; ++j) {
       const int k0 = j * BN;
       // interior tiles need no masking: every key exists and every row of the CTA may attend to it
       const bool full = (k0 + BN <= kv_len) &&
                         (k0 + BN - 1 <= q_lo || (k0 + BN <= p.prefix_len && q_lo + BM <= p.prefix_len));
+      if (tlp) tc0 = clock64();
       mbar_wait(s_full, static_cast<uint32_t>(j & 1));
       tc_fence_after();
       if constexpr (GROUPS == 2) {
+        tick(0);                                          // waited for S
         // ---- single pass: this thread's 64 scores live in registers from here on ----
         uint32_t va[32], vb[32];
         tmem_ld_32x32(tS + grp * 64, va);
@@ -320,29 +377,35 @@ fa_tc_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         tmem_ld_wait();
         tc_fence_before();
         mbar_arrive(s_empty);                             // S may be overwritten by the next Q K^T
+        tick(1);                                          // TMEM load
         if (!full) {                                      // tile-uniform: boundary tiles only
           mask_chunk(va, row_lim - (k0 + grp * 64));
           mask_chunk(vb, row_lim - (k0 + grp * 64 + 32));
         }
         const float pm = fmaxf(chunk_max(va, true, 0, 0, 0, 0), chunk_max(vb, true, 0, 0, 0, 0));
-        const uint32_t tX = tmem_base + lane_addr + kColX + 2 * (j & 1);
-        tmem_st_32x1(tX + grp, __float_as_uint(pm));
-        tmem_st_wait();
-        tc_fence_before();
-        softmax_bar_sync(256);
-        tc_fence_after();
-        const float om = __uint_as_float(tmem_ld_32x1(tX + (grp ^ 1)));
-        tmem_ld_wait();
-        const float tile_max = fmaxf(pm, om);
         float alpha = 1.f;
         bool grow = false;
-        if (m_used == -INFINITY) {
-          m_used = tile_max;                              // nothing accumulated yet
-        } else if ((tile_max - m_used) * p.scale_log2 > kLazyLog2) {
-          alpha = ex2_approx((m_used - tile_max) * p.scale_log2);
-          m_used = tile_max;
-          grow = true;
+        if constexpr (V3) {
+          alpha = agree_base_v3(pm, p.scale_log2, j, grp, r, xq, b_used, grow);
+        } else {
+          const uint32_t tX = tmem_base + lane_addr + kColX + 2 * (j & 1);
+          tmem_st_32x1(tX + grp, __float_as_uint(pm));
+          tmem_st_wait();
+          tc_fence_before();
+          softmax_bar_sync(256);
+          tc_fence_after();
+          const float om = __uint_as_float(tmem_ld_32x1(tX + (grp ^ 1)));
+          tmem_ld_wait();
+          const float tile_max = fmaxf(pm, om);
+          if (m_used == -INFINITY) {
+            m_used = tile_max;                            // nothing accumulated yet
+          } else if ((tile_max - m_used) * p.scale_log2 > kLazyLog2) {
+            alpha = ex2_approx((m_used - tile_max) * p.scale_log2);
+            m_used = tile_max;
+            grow = true;
+          }
         }
+        tick(2);                                          // mask + maximum + agreement on the base
         if (j > 0) {                                      // the previous P V has read P and updated O
           mbar_wait(p_empty, static_cast<uint32_t>((j - 1) & 1));
           tc_fence_after();
@@ -360,12 +423,16 @@ fa_tc_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           }
         }
         l_run *= alpha;
-        const float base = (m_used == -INFINITY) ? 0.f : m_used * p.scale_log2;
-        l_run += chunk_probs(va, true, 0, 0, 0, 0, p.scale_log2, base, prow + grp * (BM * 128), 0, r);
-        l_run += chunk_probs(vb, true, 0, 0, 0, 0, p.scale_log2, base, prow + grp * (BM * 128), 4, r);
+        tick(3);                                          // waited for the previous P V (+ rare rescale)
+        const float base = V3 ? (b_used == -128 ? 0.f : 2.f * static_cast<float>(b_used))
+                              : ((m_used == -INFINITY) ? 0.f : m_used * p.scale_log2);
+        l_run += chunk_probs<V3>(va, true, 0, 0, 0, 0, p.scale_log2, base, prow + grp * (BM * 128), 0, r);
+        l_run += chunk_probs<V3>(vb, true, 0, 0, 0, 0, p.scale_log2, base, prow + grp * (BM * 128), 4, r);
+        tick(4);                                          // exponentials, pack, P stores
         tc_fence_before();
         fence_proxy_async_smem();
         mbar_arrive(p_full);
+        tick(5);                                          // fence + arrive
         continue;
       }
 
@@ -430,6 +497,10 @@ fa_tc_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       fence_proxy_async_smem();
       mbar_arrive(p_full);
     }
+    if (tlp) {     // two records: phase sums [0..4], then [5], total softmax-loop clocks, tiles
+      tl_emit(5u << 28, ph[0], ph[1], ph[2], ph[3], ph[4]);
+      tl_emit(6u << 28, ph[5], clock64() - t_begin, n_tiles, 0, 0);
+    }
     // ---- epilogue: O / l -> bf16 -> global ----
     mbar_wait(p_empty, static_cast<uint32_t>((n_tiles - 1) & 1));
     tc_fence_after();
@@ -483,7 +554,8 @@ int prefill_attention_tc(const __nv_bfloat16* q, int n_heads, int n_kv_heads, in
   if (make_tmap_bf16_2d(&tKV, kv_pool, pool_rows, 64, 64, 64)) return 1;
   static DeviceOnce configured;
   if (configured.first()) {
-    for (auto* fn : {fa_tc_prefill_kernel<1>, fa_tc_prefill_kernel<2>}) {
+    for (auto* fn : {fa_tc_prefill_kernel<1, false, false>, fa_tc_prefill_kernel<2>, fa_tc_prefill_kernel<2, true>,
+                     fa_tc_prefill_kernel<2, false, false>}) {
       cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, fa::kSmemTotal);
       if (e != cudaSuccess) return set_error(cudaGetErrorString(e));
       // two CTAs per SM need the full shared-memory carve-out
@@ -500,7 +572,11 @@ int prefill_attention_tc(const __nv_bfloat16* q, int n_heads, int n_kv_heads, in
   count_launch();
   // default: the single-pass softmax (GROUPS = 2); md_debug_attention_impl(2) selects the two-pass form for A/B runs
   const cudaError_t e = g_attention_impl == 2
-      ? launch_k(fa_tc_prefill_kernel<1>, grid, dim3(fa::kThreads1), fa::kSmemTotal, stream, tQ, tKV, p)
+      ? launch_k(fa_tc_prefill_kernel<1, false, false>, grid, dim3(fa::kThreads1), fa::kSmemTotal, stream, tQ, tKV, p)
+      : g_attention_impl == 3     // the default kernel with per-phase clock sums for tools/attn_phases.py
+      ? launch_k(fa_tc_prefill_kernel<2, true>, grid, dim3(fa::kThreads2), fa::kSmemTotal, stream, tQ, tKV, p)
+      : g_attention_impl == 4     // single pass with the TMEM exchange and MUFU-only exponentials (A/B)
+      ? launch_k(fa_tc_prefill_kernel<2, false, false>, grid, dim3(fa::kThreads2), fa::kSmemTotal, stream, tQ, tKV, p)
       : launch_k(fa_tc_prefill_kernel<2>, grid, dim3(fa::kThreads2), fa::kSmemTotal, stream, tQ, tKV, p);
   if (e != cudaSuccess) return set_error(cudaGetErrorString(e));
   return 0;
@@ -523,7 +599,7 @@ constexpr int kBlk1 = 128 * 32;                  // [128 rows x 16] bf16, 4 KB
 constexpr int kTile = kBlk0 + kBlk1;             // 20 KB
 constexpr int kPBytes = BM * BN * 2;             // 32 KB
 constexpr int kSmemTiles = kTile /*Q*/ + 2 * kTile /*K*/ + kTile /*V*/ + kPBytes;   // 112 KB
-constexpr int kSmemTotal = kSmemTiles + 256;
+constexpr int kSmemTotal = kSmemTiles + 256 + 512;
 constexpr int kThreads1 = 192, kThreads2 = 320;
 constexpr uint32_t kTmemCols = 256;
 constexpr uint32_t kColS = 0, kColO = 128, kColX = 224;       // O: 80 columns (64 + 16); X: row-maximum exchange
@@ -536,7 +612,7 @@ struct FaVitParams {
 };
 
 // GROUPS = 2: as in fa_tc_prefill_kernel; of the 80 O columns group 0 owns 0..31 and 64..79, group 1 owns 32..63.
-template <int GROUPS>
+template <int GROUPS, bool V3 = true>
 __global__ void __launch_bounds__(64 + 128 * GROUPS, 2)
 fa_tc_vit_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_constant__ CUtensorMap tm16,
                  const FaVitParams p) {
@@ -667,6 +743,8 @@ fa_tc_vit_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_constant
     uint8_t* prow = sP + r * 128;
     const int qpos = 1 << 30;                                  // no causal structure: every key is allowed
     float m_used = -INFINITY;
+    int b_used = -128;
+    signed char (*xq)[2][128] = reinterpret_cast<signed char (*)[2][128]>(smem + kSmemTiles + 256);
     for (int j = 0; j < n_tiles; ++j) {
       const int k0 = j * BN;
       const bool full = k0 + BN <= kv_len;
@@ -684,23 +762,27 @@ fa_tc_vit_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_constant
           mask_chunk(vb, kv_len - (k0 + grp * 64 + 32));
         }
         const float pm = fmaxf(chunk_max(va, true, 0, 0, 0, 0), chunk_max(vb, true, 0, 0, 0, 0));
-        const uint32_t tX = tmem_base + lane_addr + kColX + 2 * (j & 1);
-        tmem_st_32x1(tX + grp, __float_as_uint(pm));
-        tmem_st_wait();
-        tc_fence_before();
-        softmax_bar_sync(256);
-        tc_fence_after();
-        const float om = __uint_as_float(tmem_ld_32x1(tX + (grp ^ 1)));
-        tmem_ld_wait();
-        const float tile_max = fmaxf(pm, om);
         float alpha = 1.f;
         bool grow = false;
-        if (m_used == -INFINITY) {
-          m_used = tile_max;
-        } else if ((tile_max - m_used) * p.scale_log2 > fa::kLazyLog2) {
-          alpha = ex2_approx((m_used - tile_max) * p.scale_log2);
-          m_used = tile_max;
-          grow = true;
+        if constexpr (V3) {
+          alpha = agree_base_v3(pm, p.scale_log2, j, grp, r, xq, b_used, grow);
+        } else {
+          const uint32_t tX = tmem_base + lane_addr + kColX + 2 * (j & 1);
+          tmem_st_32x1(tX + grp, __float_as_uint(pm));
+          tmem_st_wait();
+          tc_fence_before();
+          softmax_bar_sync(256);
+          tc_fence_after();
+          const float om = __uint_as_float(tmem_ld_32x1(tX + (grp ^ 1)));
+          tmem_ld_wait();
+          const float tile_max = fmaxf(pm, om);
+          if (m_used == -INFINITY) {
+            m_used = tile_max;
+          } else if ((tile_max - m_used) * p.scale_log2 > fa::kLazyLog2) {
+            alpha = ex2_approx((m_used - tile_max) * p.scale_log2);
+            m_used = tile_max;
+            grow = true;
+          }
         }
         if (j > 0) {
           mbar_wait(p_empty, static_cast<uint32_t>((j - 1) & 1));
@@ -722,9 +804,10 @@ fa_tc_vit_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_constant
           }
         }
         l_run *= alpha;
-        const float base = (m_used == -INFINITY) ? 0.f : m_used * p.scale_log2;
-        l_run += chunk_probs(va, true, 0, 0, 0, 0, p.scale_log2, base, prow + grp * (BM * 128), 0, r);
-        l_run += chunk_probs(vb, true, 0, 0, 0, 0, p.scale_log2, base, prow + grp * (BM * 128), 4, r);
+        const float base = V3 ? (b_used == -128 ? 0.f : 2.f * static_cast<float>(b_used))
+                              : ((m_used == -INFINITY) ? 0.f : m_used * p.scale_log2);
+        l_run += chunk_probs<V3>(va, true, 0, 0, 0, 0, p.scale_log2, base, prow + grp * (BM * 128), 0, r);
+        l_run += chunk_probs<V3>(vb, true, 0, 0, 0, 0, p.scale_log2, base, prow + grp * (BM * 128), 4, r);
         tc_fence_before();
         fence_proxy_async_smem();
         mbar_arrive(p_full);
@@ -839,6 +922,8 @@ fa_tc_vit_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_constant
   }
 }
 
+void timeline_install_attention_tc(const Timeline& t) { timeline_install(t); }
+
 int vit_attention_tc(const __nv_bfloat16* qkv, int n_crops, int seq, int n_heads, __nv_bfloat16* out,
                      cudaStream_t stream) {
   if (n_crops <= 0) return set_error("vit_attention: empty batch");
@@ -850,7 +935,7 @@ int vit_attention_tc(const __nv_bfloat16* qkv, int n_crops, int seq, int n_heads
   if (make_tmap_bf16_3d(&t16, qkv, 72, 3LL * n_heads, T, 144, 3 * D * 2, 16, 1, 128, 32)) return 1;
   static DeviceOnce configured;
   if (configured.first()) {
-    for (auto* fn : {fa_tc_vit_kernel<1>, fa_tc_vit_kernel<2>}) {
+    for (auto* fn : {fa_tc_vit_kernel<1, false>, fa_tc_vit_kernel<2>, fa_tc_vit_kernel<2, false>}) {
       cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, fv::kSmemTotal);
       if (e != cudaSuccess) return set_error(cudaGetErrorString(e));
       e = cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
@@ -863,7 +948,9 @@ int vit_attention_tc(const __nv_bfloat16* qkv, int n_crops, int seq, int n_heads
   dim3 grid((seq + fv::BM - 1) / fv::BM, n_heads, n_crops);
   count_launch();
   const cudaError_t e = g_attention_impl == 2
-      ? launch_k(fa_tc_vit_kernel<1>, grid, dim3(fv::kThreads1), fv::kSmemTotal, stream, t64, t16, p)
+      ? launch_k(fa_tc_vit_kernel<1, false>, grid, dim3(fv::kThreads1), fv::kSmemTotal, stream, t64, t16, p)
+      : g_attention_impl == 4
+      ? launch_k(fa_tc_vit_kernel<2, false>, grid, dim3(fv::kThreads2), fv::kSmemTotal, stream, t64, t16, p)
       : launch_k(fa_tc_vit_kernel<2>, grid, dim3(fv::kThreads2), fv::kSmemTotal, stream, t64, t16, p);
   if (e != cudaSuccess) return set_error(cudaGetErrorString(e));
   return 0;

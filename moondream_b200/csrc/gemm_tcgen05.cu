@@ -736,6 +736,7 @@ int timeline_install_all(unsigned long long* buf, unsigned int* count, unsigned 
   if (timeline_install(t) != cudaSuccess) return set_error("timeline: cudaMemcpyToSymbol failed");
   timeline_install_attention(t);
   timeline_install_elementwise(t);
+  timeline_install_attention_tc(t);
   return 0;
 }
 

@@ -61,6 +61,7 @@ struct Timeline;
 int timeline_install_all(unsigned long long* buf, unsigned int* count, unsigned int cap);
 void timeline_install_attention(const Timeline& t);
 void timeline_install_elementwise(const Timeline& t);
+void timeline_install_attention_tc(const Timeline& t);
 
 // ---- gemm_tcgen05.cu ----
 int make_tmap_bf16_2d(CUtensorMap* tm, const void* base, long long rows, long long cols,
