@@ -6,9 +6,10 @@
 // One CTA = 128 queries of one (sequence, head); key tiles of 128 (= two 64-token KV pages).
 //   warp 0     : TMA loader      (Q once; K and V page boxes into a 2-stage ring)
 //   warp 1     : MMA issuer      (S = Q K^T -> TMEM; O += P V -> TMEM), one elected lane
-//   warps 2-5  : softmax         (thread = query row = TMEM lane: no shuffles; online softmax in the
-//                                 exp2 domain; P written to 128B-swizzled smem as the A operand of PV;
-//                                 O rescaled in TMEM only when a row maximum moved; final normalise + store)
+//   warps 2-5  : softmax         (thread = query row = TMEM lane: no shuffles; SINGLE-PASS online softmax in the
+//                                 exp2 domain: the row's 128 scores of a tile are read from TMEM once and stay in
+//                                 registers; P written to 128B-swizzled smem as the A operand of PV; O rescaled in
+//                                 TMEM lazily, only when the row maximum grew by more than 2^8; final normalise + store)
 // TMEM: S 128 columns + O 64 columns (256 allocated) and ~113 KB of shared memory, so two CTAs fit on an
 // SM and their softmax / MMA phases interleave on the shared tensor pipe.
 // V is consumed as an MN-major B operand straight from the [tokens, 64] page image TMA writes: no
@@ -29,20 +30,12 @@ constexpr int kQBytes = BM * HD * 2;            // 16 KB
 constexpr int kKVBytes = BN * HD * 2;           // 16 KB each for K and V
 constexpr int kPBytes = BM * BN * 2;            // 32 KB (two 64-key blocks of [128 x 64])
 constexpr int kSmemTiles = kQBytes + kStages * 2 * kKVBytes + kPBytes;   // 112 KB
-// barriers (256 B) + the 512-byte base-agreement buffer of the single-pass softmax; two CTAs per SM:
-// 2 x (kSmemTotal + 1 KB reserved) <= 228 KB.  (Static __shared__ would be padded to the 1024-byte alignment of the
-// tiles and no longer fit.)
-constexpr int kSmemTotal = kSmemTiles + 256 + 512;
-constexpr int kThreads1 = 192, kThreads2 = 320;   // one / two softmax warpgroups (see the kernel's softmax section)
+constexpr int kSmemTotal = kSmemTiles + 256;   // two CTAs per SM: 2 x (kSmemTotal + 1 KB reserved) <= 228 KB
+constexpr int kThreads = 192;
 constexpr uint32_t kTmemCols = 256;
-constexpr uint32_t kColS = 0, kColO = 128, kColX = 224;   // X: four spare columns for the row-maximum exchange
+constexpr uint32_t kColS = 0, kColO = 128;
 constexpr float kLazyLog2 = 8.0f;     // O is rescaled only when a row maximum has grown by more than 2^8 (see the kernel)
 }  // namespace fa
-
-// named barrier among the softmax warps only (ids 1..15; 0 is __syncthreads)
-__device__ __forceinline__ void softmax_bar_sync(int threads) {
-  asm volatile("bar.sync 1, %0;" ::"r"(threads) : "memory");
-}
 
 
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -150,27 +143,6 @@ __device__ __forceinline__ void mask_chunk(uint32_t (&v)[32], int n_valid) {
   for (int i = 0; i < 32; ++i) v[i] = (i < n_valid) ? v[i] : 0xff800000u;
 }
 
-// V3 agreement on the scaling base (see fa_tc_prefill_kernel): returns the rescale factor for O and l (1 = none).
-// b_used: current base / 2 as an integer, -128 = nothing accumulated yet.  xq: [tile parity][group][row].
-__device__ __forceinline__ float agree_base_v3(float pm, float scale_log2, int j, int grp, int r,
-                                               signed char (*xq)[2][128], int& b_used, bool& grow) {
-  int pq = -128;
-  if (pm != -INFINITY) pq = max(-127, min(127, __float2int_ru(pm * scale_log2 * 0.5f)));
-  xq[j & 1][grp][r] = static_cast<signed char>(pq);
-  softmax_bar_sync(256);
-  const int tq = max(pq, static_cast<int>(xq[j & 1][grp ^ 1][r]));
-  float alpha = 1.f;
-  grow = false;
-  if (b_used == -128) {
-    b_used = tq;
-  } else if (tq - b_used > 4) {                           // the row maximum grew by more than 2^8
-    alpha = __int_as_float(max(0, 127 + 2 * (b_used - tq)) << 23);       // exact 2^(2 (b_used - tq)), 0 below 2^-126
-    b_used = tq;
-    grow = true;
-  }
-  return alpha;
-}
-
 struct FaTcParams {
   const int* q_offsets;     // [n_seqs + 1]
   const int* start_pos;     // [n_seqs]
@@ -180,25 +152,24 @@ struct FaTcParams {
   float scale_log2;
 };
 
-// What bounds these kernels is the TMEM READ path (~64 B/clk per SM, B300_MICROARCH.md "LDTM throughput"): with one
-// softmax warpgroup (GROUPS = 1) a 128 x 128 score tile is read twice (row maximum, then probabilities: 128 KB) and O
-// is read and rewritten whenever a maximum moved (32-40 KB): ~2600 of the ~3000 clocks a tile takes (tensor pipe
-// 17-21 %, profiles/r02_ncu_decode_summary.json; moving exponentials off MUFU or adding softmax warps changed
-// nothing, profiles/r02_attention_ab.json).  GROUPS = 2 is built around reading S ONCE:
-//   * two softmax warpgroups (warps 2-5, 6-9); a thread holds ITS 64 scores of its row in registers (one TMEM read),
-//     S is released to the MMA warp at once (the next Q K^T overlaps this tile's softmax);
-//   * the row maximum of the tile = max of the two groups' partial maxima, exchanged through spare TMEM columns
-//     (one column per lane) around a named barrier;
-//   * lazy rescale (as FlashAttention-4): O and l stay scaled by m_used; they are rescaled only when the tile maximum
-//     exceeds m_used by more than 2^8 — otherwise the probabilities simply run up to 2^8 (exact in the final O / l,
-//     which divides the common factor out) — so O is hardly ever read back;
-//   * each group rescales / stores its own half of the O columns; the two partial row sums are added at the end.
-// V3 (GROUPS = 2 only): the two groups agree on the scaling base through 512 bytes of shared memory instead of TMEM
-// columns — each publishes ceil(partial maximum * scale / 2) as one signed byte (an UPPER bound, granularity 2 in the
-// log2 domain: any common base is exact after the final O / l, it only has to keep 2^(s - base) in range), the base is
-// an integer, the lazy rescale factor an exact power of two — and 3 of 8 exponential pairs run on the FMA pipe.
-template <int GROUPS, bool PROF = false, bool V3 = true>
-__global__ void __launch_bounds__(64 + 128 * GROUPS, 2)
+// The softmax of these kernels was measured step by step this round (profiles/r02_attention_ab.json,
+// r02_ncu_attention_summary.json, tools/attn_phases.py):
+//   * two passes over S (row maximum, then probabilities) pull 160-200 KB per tile through the TMEM read path
+//     (~64 B/clk per SM) and rewrite O whenever a maximum moved: tensor pipe 18-21 %, nothing else saturated;
+//   * SINGLE = true (default): a thread reads its row's 128 scores ONCE and keeps them in registers (168 registers, two
+//     CTAs per SM still fit), S is released to the MMA warp at once (the next Q K^T overlaps this tile's softmax), and
+//     O is rescaled lazily as in FlashAttention-4: only when the row maximum grew by more than 2^8 — otherwise the
+//     probabilities run up to 2^8, which the final O / l divides out exactly;
+//   * boundary tiles are masked with one compare + select per score against the row's key limit and then take the same
+//     packed fast path (the per-element predicate form cost 1049 instead of 228 instructions per thread on one tile in six);
+//   * 3 of every 8 exponential pairs are evaluated on the FMA pipe (exp2_fma2): the exponential phase is paced by the
+//     16-per-clock MUFU;
+//   * two softmax warpgroups per CTA (64 scores per thread, row maximum agreed through TMEM columns or shared memory)
+//     were built and measured too: the agreement barrier costs more than it saves (0.314 vs 0.300 ms) — removed.
+// SINGLE = false is the round-1 two-pass form, kept for A/B runs (md_debug_attention_impl(2)).
+// PROF adds per-phase clock sums of one softmax thread for tools/attn_phases.py (md_debug_attention_impl(3)).
+template <bool SINGLE, bool PROF = false>
+__global__ void __launch_bounds__(fa::kThreads, 2)
 fa_tc_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
                      const FaTcParams p) {
   using namespace fa;
@@ -251,8 +222,8 @@ fa_tc_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1);
     }
     mbar_init(s_full, 1);
-    mbar_init(s_empty, 128 * GROUPS);
-    mbar_init(p_full, 128 * GROUPS);
+    mbar_init(s_empty, 128);
+    mbar_init(p_full, 128);
     mbar_init(p_empty, 1);
     fence_barrier_init();
   }
@@ -339,24 +310,20 @@ fa_tc_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       issue_pv(n_tiles - 1);
     }
   } else {
-    // ------------------------------ softmax (GROUPS x 128 threads, one query row each) ------------------------------
+    // ------------------------------ softmax (128 threads, one query row each) ------------------------------
     const int quad = warp & 3;
-    const int grp = (warp - 2) >> 2;                      // softmax warpgroup: which half of the keys / O columns
     const int r = quad * 32 + lane;                       // row in the tile = TMEM lane
     const int qpos = q_pos0 + q0 + r;
     const bool row_ok = q0 + r < n_q;
     const uint32_t lane_addr = static_cast<uint32_t>(quad * 32) << 16;
     const uint32_t tS = tmem_base + lane_addr + kColS, tO = tmem_base + lane_addr + kColO;
-    float m_run = -INFINITY, l_run = 0.f;
+    float m_run = -INFINITY, l_run = 0.f;                 // SINGLE: m_run = the maximum O and l are currently scaled by
     const int q_lo = q_pos0 + q0;                          // smallest query position of this CTA
     uint8_t* prow = sP + r * 128;
-    float m_used = -INFINITY;                             // GROUPS = 2: the maximum O and l are currently scaled by
-    int b_used = -128;                                    // V3: the same as an integer base / 2 (-128 = none yet)
-    signed char (*xq)[2][128] = reinterpret_cast<signed char (*)[2][128]>(smem + kSmemTiles + 256);
     // first key position this row may NOT attend to (prefix-LM mask of moondream.py:138-146 + sequence length)
     const int row_lim = min(kv_len, qpos < p.prefix_len ? max(qpos + 1, p.prefix_len) : qpos + 1);
     // debug timeline (tools/attn_phases.py): clock sums of the phases of one softmax thread
-    const bool tlp = PROF && tl_on() && threadIdx.x == 64;      // PROF: md_debug_attention_impl(3), profiling launches only
+    const bool tlp = PROF && tl_on() && threadIdx.x == 64;
     long long ph[6] = {0, 0, 0, 0, 0, 0}, tc0 = 0;
     auto tick = [&](int i) { if (tlp) { const long long now = clock64(); ph[i] += now - tc0; tc0 = now; } };
     const long long t_begin = tlp ? clock64() : 0;
@@ -368,66 +335,59 @@ fa_tc_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       if (tlp) tc0 = clock64();
       mbar_wait(s_full, static_cast<uint32_t>(j & 1));
       tc_fence_after();
-      if constexpr (GROUPS == 2) {
+      if constexpr (SINGLE) {
         tick(0);                                          // waited for S
-        // ---- single pass: this thread's 64 scores live in registers from here on ----
-        uint32_t va[32], vb[32];
-        tmem_ld_32x32(tS + grp * 64, va);
-        tmem_ld_32x32(tS + grp * 64 + 32, vb);
+        // ---- the row's 128 scores are read from TMEM once and live in registers from here on ----
+        uint32_t v0[32], v1[32], v2[32], v3[32];
+        tmem_ld_32x32(tS, v0);
+        tmem_ld_32x32(tS + 32, v1);
+        tmem_ld_32x32(tS + 64, v2);
+        tmem_ld_32x32(tS + 96, v3);
         tmem_ld_wait();
         tc_fence_before();
         mbar_arrive(s_empty);                             // S may be overwritten by the next Q K^T
         tick(1);                                          // TMEM load
         if (!full) {                                      // tile-uniform: boundary tiles only
-          mask_chunk(va, row_lim - (k0 + grp * 64));
-          mask_chunk(vb, row_lim - (k0 + grp * 64 + 32));
+          mask_chunk(v0, row_lim - k0);
+          mask_chunk(v1, row_lim - (k0 + 32));
+          mask_chunk(v2, row_lim - (k0 + 64));
+          mask_chunk(v3, row_lim - (k0 + 96));
         }
-        const float pm = fmaxf(chunk_max(va, true, 0, 0, 0, 0), chunk_max(vb, true, 0, 0, 0, 0));
+        const float tile_max = fmaxf(fmaxf(chunk_max(v0, true, 0, 0, 0, 0), chunk_max(v1, true, 0, 0, 0, 0)),
+                                     fmaxf(chunk_max(v2, true, 0, 0, 0, 0), chunk_max(v3, true, 0, 0, 0, 0)));
         float alpha = 1.f;
         bool grow = false;
-        if constexpr (V3) {
-          alpha = agree_base_v3(pm, p.scale_log2, j, grp, r, xq, b_used, grow);
-        } else {
-          const uint32_t tX = tmem_base + lane_addr + kColX + 2 * (j & 1);
-          tmem_st_32x1(tX + grp, __float_as_uint(pm));
-          tmem_st_wait();
-          tc_fence_before();
-          softmax_bar_sync(256);
-          tc_fence_after();
-          const float om = __uint_as_float(tmem_ld_32x1(tX + (grp ^ 1)));
-          tmem_ld_wait();
-          const float tile_max = fmaxf(pm, om);
-          if (m_used == -INFINITY) {
-            m_used = tile_max;                            // nothing accumulated yet
-          } else if ((tile_max - m_used) * p.scale_log2 > kLazyLog2) {
-            alpha = ex2_approx((m_used - tile_max) * p.scale_log2);
-            m_used = tile_max;
-            grow = true;
-          }
+        if (m_run == -INFINITY) {
+          m_run = tile_max;                               // nothing accumulated yet
+        } else if ((tile_max - m_run) * p.scale_log2 > kLazyLog2) {
+          alpha = ex2_approx((m_run - tile_max) * p.scale_log2);
+          m_run = tile_max;
+          grow = true;
         }
-        tick(2);                                          // mask + maximum + agreement on the base
+        tick(2);                                          // mask + maximum
         if (j > 0) {                                      // the previous P V has read P and updated O
           mbar_wait(p_empty, static_cast<uint32_t>((j - 1) & 1));
           tc_fence_after();
           if (__any_sync(0xffffffffu, grow)) {            // warp-uniform; lanes that did not grow multiply by 1
 #pragma unroll 1
-            for (int c = 0; c < 2; ++c) {                 // 16 columns at a time: the 64 scores stay in registers
+            for (int c = 0; c < HD / 16; ++c) {           // 16 columns at a time: the scores stay in registers
               uint32_t o[16];
-              tmem_ld_32x16(tO + grp * 32 + c * 16, o);
+              tmem_ld_32x16(tO + c * 16, o);
               tmem_ld_wait();
 #pragma unroll
               for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-              tmem_st_32x16(tO + grp * 32 + c * 16, o);
+              tmem_st_32x16(tO + c * 16, o);
             }
             tmem_st_wait();
           }
         }
         l_run *= alpha;
         tick(3);                                          // waited for the previous P V (+ rare rescale)
-        const float base = V3 ? (b_used == -128 ? 0.f : 2.f * static_cast<float>(b_used))
-                              : ((m_used == -INFINITY) ? 0.f : m_used * p.scale_log2);
-        l_run += chunk_probs<V3>(va, true, 0, 0, 0, 0, p.scale_log2, base, prow + grp * (BM * 128), 0, r);
-        l_run += chunk_probs<V3>(vb, true, 0, 0, 0, 0, p.scale_log2, base, prow + grp * (BM * 128), 4, r);
+        const float base = (m_run == -INFINITY) ? 0.f : m_run * p.scale_log2;
+        l_run += chunk_probs<true>(v0, true, 0, 0, 0, 0, p.scale_log2, base, prow, 0, r);
+        l_run += chunk_probs<true>(v1, true, 0, 0, 0, 0, p.scale_log2, base, prow, 4, r);
+        l_run += chunk_probs<true>(v2, true, 0, 0, 0, 0, p.scale_log2, base, prow + BM * 128, 0, r);
+        l_run += chunk_probs<true>(v3, true, 0, 0, 0, 0, p.scale_log2, base, prow + BM * 128, 4, r);
         tick(4);                                          // exponentials, pack, P stores
         tc_fence_before();
         fence_proxy_async_smem();
@@ -436,7 +396,7 @@ fa_tc_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         continue;
       }
 
-      // ---- GROUPS = 1, pass 1: row maximum over all 128 keys (two 32-column chunks in flight) ----
+      // ---- two-pass form (A/B reference), pass 1: row maximum (two 32-column chunks in flight) ----
       float mx = m_run;
       {
         uint32_t va[32], vb[32];
@@ -484,11 +444,11 @@ fa_tc_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           tmem_ld_wait();
           tmem_ld_32x32(tS + (2 * cc + 1) * 32, vb);
           l_run += chunk_probs(va, full, k0 + (2 * cc) * 32, kv_len, qpos, p.prefix_len, p.scale_log2, base,
-                                     prow + cc * (BM * 128), 0, r);
+                               prow + cc * (BM * 128), 0, r);
           tmem_ld_wait();
           if (cc == 0) tmem_ld_32x32(tS + 64, va);
           l_run += chunk_probs(vb, full, k0 + (2 * cc + 1) * 32, kv_len, qpos, p.prefix_len, p.scale_log2, base,
-                                     prow + cc * (BM * 128), 4, r);
+                               prow + cc * (BM * 128), 4, r);
         }
       }
       // S has been consumed; P is in shared memory: publish both
@@ -504,16 +464,10 @@ fa_tc_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     // ---- epilogue: O / l -> bf16 -> global ----
     mbar_wait(p_empty, static_cast<uint32_t>((n_tiles - 1) & 1));
     tc_fence_after();
-    if (GROUPS == 2) {                                    // add the two groups' partial row sums (P is no longer read)
-      float* xl = reinterpret_cast<float*>(sP);
-      xl[grp * BM + r] = l_run;
-      softmax_bar_sync(256);
-      l_run = xl[r] + xl[BM + r];
-    }
     const float inv = l_run > 0.f ? 1.0f / l_run : 0.f;
     __nv_bfloat16* orow = p.out + (static_cast<long long>(q_off) + q0 + r) * (static_cast<long long>(p.n_heads) * HD) + head * HD;
 #pragma unroll 1
-    for (int c = (GROUPS == 2 ? grp : 0); c < (GROUPS == 2 ? grp + 1 : HD / 32); ++c) {
+    for (int c = 0; c < HD / 32; ++c) {
       uint32_t o[32];
       tmem_ld_32x32(tO + c * 32, o);
       tmem_ld_wait();
@@ -554,8 +508,7 @@ int prefill_attention_tc(const __nv_bfloat16* q, int n_heads, int n_kv_heads, in
   if (make_tmap_bf16_2d(&tKV, kv_pool, pool_rows, 64, 64, 64)) return 1;
   static DeviceOnce configured;
   if (configured.first()) {
-    for (auto* fn : {fa_tc_prefill_kernel<1, false, false>, fa_tc_prefill_kernel<2>, fa_tc_prefill_kernel<2, true>,
-                     fa_tc_prefill_kernel<2, false, false>}) {
+    for (auto* fn : {fa_tc_prefill_kernel<true>, fa_tc_prefill_kernel<false>, fa_tc_prefill_kernel<true, true>}) {
       cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, fa::kSmemTotal);
       if (e != cudaSuccess) return set_error(cudaGetErrorString(e));
       // two CTAs per SM need the full shared-memory carve-out
@@ -570,14 +523,12 @@ int prefill_attention_tc(const __nv_bfloat16* q, int n_heads, int n_kv_heads, in
   p.scale_log2 = 0.125f * 1.4426950408889634f;
   dim3 grid((max_q + fa::BM - 1) / fa::BM, n_heads, n_seqs);
   count_launch();
-  // default: the single-pass softmax (GROUPS = 2); md_debug_attention_impl(2) selects the two-pass form for A/B runs
-  const cudaError_t e = g_attention_impl == 2
-      ? launch_k(fa_tc_prefill_kernel<1, false, false>, grid, dim3(fa::kThreads1), fa::kSmemTotal, stream, tQ, tKV, p)
-      : g_attention_impl == 3     // the default kernel with per-phase clock sums for tools/attn_phases.py
-      ? launch_k(fa_tc_prefill_kernel<2, true>, grid, dim3(fa::kThreads2), fa::kSmemTotal, stream, tQ, tKV, p)
-      : g_attention_impl == 4     // single pass with the TMEM exchange and MUFU-only exponentials (A/B)
-      ? launch_k(fa_tc_prefill_kernel<2, false, false>, grid, dim3(fa::kThreads2), fa::kSmemTotal, stream, tQ, tKV, p)
-      : launch_k(fa_tc_prefill_kernel<2>, grid, dim3(fa::kThreads2), fa::kSmemTotal, stream, tQ, tKV, p);
+  // default: the single-pass softmax; md_debug_attention_impl(2) = the two-pass form, (3) = single pass with phase clocks
+  const dim3 block(fa::kThreads);
+  const cudaError_t e =
+      g_attention_impl == 2 ? launch_k(fa_tc_prefill_kernel<false>, grid, block, fa::kSmemTotal, stream, tQ, tKV, p)
+      : g_attention_impl == 3 ? launch_k(fa_tc_prefill_kernel<true, true>, grid, block, fa::kSmemTotal, stream, tQ, tKV, p)
+                              : launch_k(fa_tc_prefill_kernel<true>, grid, block, fa::kSmemTotal, stream, tQ, tKV, p);
   if (e != cudaSuccess) return set_error(cudaGetErrorString(e));
   return 0;
 }
@@ -599,10 +550,10 @@ constexpr int kBlk1 = 128 * 32;                  // [128 rows x 16] bf16, 4 KB
 constexpr int kTile = kBlk0 + kBlk1;             // 20 KB
 constexpr int kPBytes = BM * BN * 2;             // 32 KB
 constexpr int kSmemTiles = kTile /*Q*/ + 2 * kTile /*K*/ + kTile /*V*/ + kPBytes;   // 112 KB
-constexpr int kSmemTotal = kSmemTiles + 256 + 512;
-constexpr int kThreads1 = 192, kThreads2 = 320;
+constexpr int kSmemTotal = kSmemTiles + 256;
+constexpr int kThreads = 192;
 constexpr uint32_t kTmemCols = 256;
-constexpr uint32_t kColS = 0, kColO = 128, kColX = 224;       // O: 80 columns (64 + 16); X: row-maximum exchange
+constexpr uint32_t kColS = 0, kColO = 128;       // O: 80 columns (64 + 16)
 }  // namespace fv
 
 struct FaVitParams {
@@ -611,9 +562,9 @@ struct FaVitParams {
   float scale_log2;
 };
 
-// GROUPS = 2: as in fa_tc_prefill_kernel; of the 80 O columns group 0 owns 0..31 and 64..79, group 1 owns 32..63.
-template <int GROUPS, bool V3 = true>
-__global__ void __launch_bounds__(64 + 128 * GROUPS, 2)
+// SINGLE / two-pass: as in fa_tc_prefill_kernel.
+template <bool SINGLE>
+__global__ void __launch_bounds__(fv::kThreads, 2)
 fa_tc_vit_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_constant__ CUtensorMap tm16,
                  const FaVitParams p) {
   using namespace fv;
@@ -653,8 +604,8 @@ fa_tc_vit_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_constant
     mbar_init(v_full, 1);
     mbar_init(v_empty, 1);
     mbar_init(s_full, 1);
-    mbar_init(s_empty, 128 * GROUPS);
-    mbar_init(p_full, 128 * GROUPS);
+    mbar_init(s_empty, 128);
+    mbar_init(p_full, 128);
     mbar_init(p_empty, 1);
     fence_barrier_init();
   }
@@ -732,9 +683,8 @@ fa_tc_vit_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_constant
       issue_pv(n_tiles - 1);
     }
   } else {
-    // ------------------------------ softmax (GROUPS x 128 threads) ------------------------------
+    // ------------------------------ softmax (128 threads, one query row each) ------------------------------
     const int quad = warp & 3;
-    const int grp = (warp - 2) >> 2;
     const int r = quad * 32 + lane;
     const bool row_ok = q0 + r < n_q;
     const uint32_t lane_addr = static_cast<uint32_t>(quad * 32) << 16;
@@ -742,77 +692,65 @@ fa_tc_vit_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_constant
     float m_run = -INFINITY, l_run = 0.f;
     uint8_t* prow = sP + r * 128;
     const int qpos = 1 << 30;                                  // no causal structure: every key is allowed
-    float m_used = -INFINITY;
-    int b_used = -128;
-    signed char (*xq)[2][128] = reinterpret_cast<signed char (*)[2][128]>(smem + kSmemTiles + 256);
     for (int j = 0; j < n_tiles; ++j) {
       const int k0 = j * BN;
       const bool full = k0 + BN <= kv_len;
       mbar_wait(s_full, static_cast<uint32_t>(j & 1));
       tc_fence_after();
-      if constexpr (GROUPS == 2) {
-        uint32_t va[32], vb[32];
-        tmem_ld_32x32(tS + grp * 64, va);
-        tmem_ld_32x32(tS + grp * 64 + 32, vb);
+      if constexpr (SINGLE) {
+        uint32_t v0[32], v1[32], v2[32], v3[32];
+        tmem_ld_32x32(tS, v0);
+        tmem_ld_32x32(tS + 32, v1);
+        tmem_ld_32x32(tS + 64, v2);
+        tmem_ld_32x32(tS + 96, v3);
         tmem_ld_wait();
         tc_fence_before();
         mbar_arrive(s_empty);
         if (!full) {
-          mask_chunk(va, kv_len - (k0 + grp * 64));
-          mask_chunk(vb, kv_len - (k0 + grp * 64 + 32));
+          mask_chunk(v0, kv_len - k0);
+          mask_chunk(v1, kv_len - (k0 + 32));
+          mask_chunk(v2, kv_len - (k0 + 64));
+          mask_chunk(v3, kv_len - (k0 + 96));
         }
-        const float pm = fmaxf(chunk_max(va, true, 0, 0, 0, 0), chunk_max(vb, true, 0, 0, 0, 0));
+        const float tile_max = fmaxf(fmaxf(chunk_max(v0, true, 0, 0, 0, 0), chunk_max(v1, true, 0, 0, 0, 0)),
+                                     fmaxf(chunk_max(v2, true, 0, 0, 0, 0), chunk_max(v3, true, 0, 0, 0, 0)));
         float alpha = 1.f;
         bool grow = false;
-        if constexpr (V3) {
-          alpha = agree_base_v3(pm, p.scale_log2, j, grp, r, xq, b_used, grow);
-        } else {
-          const uint32_t tX = tmem_base + lane_addr + kColX + 2 * (j & 1);
-          tmem_st_32x1(tX + grp, __float_as_uint(pm));
-          tmem_st_wait();
-          tc_fence_before();
-          softmax_bar_sync(256);
-          tc_fence_after();
-          const float om = __uint_as_float(tmem_ld_32x1(tX + (grp ^ 1)));
-          tmem_ld_wait();
-          const float tile_max = fmaxf(pm, om);
-          if (m_used == -INFINITY) {
-            m_used = tile_max;
-          } else if ((tile_max - m_used) * p.scale_log2 > fa::kLazyLog2) {
-            alpha = ex2_approx((m_used - tile_max) * p.scale_log2);
-            m_used = tile_max;
-            grow = true;
-          }
+        if (m_run == -INFINITY) {
+          m_run = tile_max;
+        } else if ((tile_max - m_run) * p.scale_log2 > fa::kLazyLog2) {
+          alpha = ex2_approx((m_run - tile_max) * p.scale_log2);
+          m_run = tile_max;
+          grow = true;
         }
         if (j > 0) {
           mbar_wait(p_empty, static_cast<uint32_t>((j - 1) & 1));
           tc_fence_after();
           if (__any_sync(0xffffffffu, grow)) {
-            // group 0: columns 0..31 and 64..79, group 1: columns 32..63; 16 at a time (the scores stay in registers)
-            const int n16 = grp == 0 ? 3 : 2;
 #pragma unroll 1
-            for (int c = 0; c < n16; ++c) {
-              const uint32_t col = grp == 0 ? (c < 2 ? c * 16 : 64) : 32 + c * 16;
+            for (int c = 0; c < 5; ++c) {                      // 80 O columns, 16 at a time
               uint32_t o[16];
-              tmem_ld_32x16(tO + col, o);
+              tmem_ld_32x16(tO + c * 16, o);
               tmem_ld_wait();
 #pragma unroll
               for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-              tmem_st_32x16(tO + col, o);
+              tmem_st_32x16(tO + c * 16, o);
             }
             tmem_st_wait();
           }
         }
         l_run *= alpha;
-        const float base = V3 ? (b_used == -128 ? 0.f : 2.f * static_cast<float>(b_used))
-                              : ((m_used == -INFINITY) ? 0.f : m_used * p.scale_log2);
-        l_run += chunk_probs<V3>(va, true, 0, 0, 0, 0, p.scale_log2, base, prow + grp * (BM * 128), 0, r);
-        l_run += chunk_probs<V3>(vb, true, 0, 0, 0, 0, p.scale_log2, base, prow + grp * (BM * 128), 4, r);
+        const float base = (m_run == -INFINITY) ? 0.f : m_run * p.scale_log2;
+        l_run += chunk_probs<true>(v0, true, 0, 0, 0, 0, p.scale_log2, base, prow, 0, r);
+        l_run += chunk_probs<true>(v1, true, 0, 0, 0, 0, p.scale_log2, base, prow, 4, r);
+        l_run += chunk_probs<true>(v2, true, 0, 0, 0, 0, p.scale_log2, base, prow + BM * 128, 0, r);
+        l_run += chunk_probs<true>(v3, true, 0, 0, 0, 0, p.scale_log2, base, prow + BM * 128, 4, r);
         tc_fence_before();
         fence_proxy_async_smem();
         mbar_arrive(p_full);
         continue;
       }
+      // ---- two-pass form (A/B reference) ----
       float mx = m_run;
       {
         uint32_t va[32], vb[32];
@@ -861,11 +799,11 @@ fa_tc_vit_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_constant
           tmem_ld_wait();
           tmem_ld_32x32(tS + (2 * cc + 1) * 32, vb);
           l_run += chunk_probs(va, full, k0 + (2 * cc) * 32, kv_len, qpos, 0, p.scale_log2, base,
-                                     prow + cc * (BM * 128), 0, r);
+                               prow + cc * (BM * 128), 0, r);
           tmem_ld_wait();
           if (cc == 0) tmem_ld_32x32(tS + 64, va);
           l_run += chunk_probs(vb, full, k0 + (2 * cc + 1) * 32, kv_len, qpos, 0, p.scale_log2, base,
-                                     prow + cc * (BM * 128), 4, r);
+                               prow + cc * (BM * 128), 4, r);
         }
       }
       tc_fence_before();
@@ -876,12 +814,6 @@ fa_tc_vit_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_constant
     // ---- epilogue: 72 of the 80 O columns ----
     mbar_wait(p_empty, static_cast<uint32_t>((n_tiles - 1) & 1));
     tc_fence_after();
-    if (GROUPS == 2) {
-      float* xl = reinterpret_cast<float*>(sP);
-      xl[grp * BM + r] = l_run;
-      softmax_bar_sync(256);
-      l_run = xl[r] + xl[BM + r];
-    }
     const float inv = l_run > 0.f ? 1.0f / l_run : 0.f;
     __nv_bfloat16* orow = p.out + (static_cast<long long>(row0) + q0 + r) * (static_cast<long long>(H) * HD) + head * HD;
     auto st8 = [&](const uint32_t* o, int col) {
@@ -892,25 +824,21 @@ fa_tc_vit_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_constant
       w.w = pack_bf16x2(__uint_as_float(o[6]) * inv, __uint_as_float(o[7]) * inv);
       *reinterpret_cast<uint4*>(orow + col) = w;
     };
-    if (GROUPS == 1 || grp == 1) {
-      uint32_t o1[32];
-      tmem_ld_32x32(tO + 32, o1);
+#pragma unroll 1
+    for (int c = 0; c < 2; ++c) {
+      uint32_t o[32];
+      tmem_ld_32x32(tO + c * 32, o);
       tmem_ld_wait();
       if (row_ok) {
 #pragma unroll
-        for (int g = 0; g < 4; ++g) st8(o1 + 8 * g, 32 + 8 * g);
+        for (int g = 0; g < 4; ++g) st8(o + 8 * g, c * 32 + 8 * g);
       }
     }
-    if (GROUPS == 1 || grp == 0) {
-      uint32_t o0[32], o2[16];
-      tmem_ld_32x32(tO, o0);
+    {
+      uint32_t o2[16];
       tmem_ld_32x16(tO + 64, o2);
       tmem_ld_wait();
-      if (row_ok) {
-#pragma unroll
-        for (int g = 0; g < 4; ++g) st8(o0 + 8 * g, 8 * g);
-        st8(o2, 64);                                           // dims 64..71; 72..79 are padding
-      }
+      if (row_ok) st8(o2, 64);                                 // dims 64..71; 72..79 are padding
     }
   }
 
@@ -935,7 +863,7 @@ int vit_attention_tc(const __nv_bfloat16* qkv, int n_crops, int seq, int n_heads
   if (make_tmap_bf16_3d(&t16, qkv, 72, 3LL * n_heads, T, 144, 3 * D * 2, 16, 1, 128, 32)) return 1;
   static DeviceOnce configured;
   if (configured.first()) {
-    for (auto* fn : {fa_tc_vit_kernel<1, false>, fa_tc_vit_kernel<2>, fa_tc_vit_kernel<2, false>}) {
+    for (auto* fn : {fa_tc_vit_kernel<true>, fa_tc_vit_kernel<false>}) {
       cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, fv::kSmemTotal);
       if (e != cudaSuccess) return set_error(cudaGetErrorString(e));
       e = cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
@@ -948,10 +876,8 @@ int vit_attention_tc(const __nv_bfloat16* qkv, int n_crops, int seq, int n_heads
   dim3 grid((seq + fv::BM - 1) / fv::BM, n_heads, n_crops);
   count_launch();
   const cudaError_t e = g_attention_impl == 2
-      ? launch_k(fa_tc_vit_kernel<1, false>, grid, dim3(fv::kThreads1), fv::kSmemTotal, stream, t64, t16, p)
-      : g_attention_impl == 4
-      ? launch_k(fa_tc_vit_kernel<2, false>, grid, dim3(fv::kThreads2), fv::kSmemTotal, stream, t64, t16, p)
-      : launch_k(fa_tc_vit_kernel<2>, grid, dim3(fv::kThreads2), fv::kSmemTotal, stream, t64, t16, p);
+      ? launch_k(fa_tc_vit_kernel<false>, grid, dim3(fv::kThreads), fv::kSmemTotal, stream, t64, t16, p)
+      : launch_k(fa_tc_vit_kernel<true>, grid, dim3(fv::kThreads), fv::kSmemTotal, stream, t64, t16, p);
   if (e != cudaSuccess) return set_error(cudaGetErrorString(e));
   return 0;
 }

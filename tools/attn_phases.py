@@ -31,7 +31,8 @@ def run():
                                           N.ptr(out), N.current_stream()))
 
 
-lib.md_debug_attention_impl(3)
+impl = 3                                                   # the default kernel with phase clocks
+lib.md_debug_attention_impl(impl)
 for _ in range(3):
     run()
 torch.cuda.synchronize()
@@ -51,7 +52,7 @@ r = rec[:n].cpu().numpy().astype(np.int64)
 kind = (r[:, 0] >> 60) & 0xF
 a, b = r[kind == 5], r[kind == 6]
 tiles = b[:, 3].astype(np.float64)
-names = ["wait S (s_full)", "TMEM load of 64 scores + release S", "mask + row max + exchange through TMEM", "wait previous P V (+ rescale)",
+names = ["wait S (s_full)", "TMEM load of 128 scores + release S", "mask + row max", "wait previous P V (+ rescale)",
          "exponentials + pack + P stores"]
 res = {"launch_ms": s.elapsed_time(e), "ctas": int(len(a)), "tiles_per_cta": float(tiles.mean()),
        "clocks_per_tile": {nm: float((a[:, 1 + i] / tiles).mean()) for i, nm in enumerate(names)}}
