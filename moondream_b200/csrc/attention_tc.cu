@@ -193,7 +193,8 @@ fa_tc_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   uint64_t* p_empty = bars + 8;                     // 1
   uint64_t* v_full = bars + 9;                      // [2]
   uint64_t* v_empty = bars + 11;                    // [2]
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 13);
+  uint64_t* p_half = bars + 13;                     // 1: the first 64-key block of P has been read by P V
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 14);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int head = blockIdx.y, seq = blockIdx.z;
@@ -225,6 +226,7 @@ fa_tc_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     mbar_init(s_empty, 128);
     mbar_init(p_full, 128);
     mbar_init(p_empty, 1);
+    mbar_init(p_half, 1);
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -289,6 +291,7 @@ fa_tc_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           const uint64_t da = make_desc_k_sw128(sp + (k >> 2) * (BM * 128)) + static_cast<uint64_t>(2 * (k & 3));
           const uint64_t db = make_desc_mn_sw128(sv + k * 2048, 16);
           umma_bf16(tO, da, db, idesc_pv, (j > 0 || k > 0) ? 1u : 0u);
+          if (k == 3) umma_commit(p_half);   // the first 64-key block of P may be overwritten already
         }
         umma_commit(p_empty);            // P buffer reusable, O updated
         umma_commit(&v_empty[st]);       // V stage reusable
@@ -365,10 +368,15 @@ fa_tc_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           grow = true;
         }
         tick(2);                                          // mask + maximum
-        if (j > 0) {                                      // the previous P V has read P and updated O
-          mbar_wait(p_empty, static_cast<uint32_t>((j - 1) & 1));
-          tc_fence_after();
-          if (__any_sync(0xffffffffu, grow)) {            // warp-uniform; lanes that did not grow multiply by 1
+        // The previous P V reads P's first 64-key block, then its second: this tile's first block may be written as
+        // soon as the first half of that P V is done (p_half); only an O rescale needs all of it.
+        bool pv_done = j == 0;
+        if (j > 0) {
+          const bool any_grow = __any_sync(0xffffffffu, grow);      // warp-uniform; lanes that did not grow multiply by 1
+          if (any_grow) {
+            mbar_wait(p_empty, static_cast<uint32_t>((j - 1) & 1));
+            pv_done = true;
+            tc_fence_after();
 #pragma unroll 1
             for (int c = 0; c < HD / 16; ++c) {           // 16 columns at a time: the scores stay in registers
               uint32_t o[16];
@@ -379,13 +387,16 @@ fa_tc_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
               tmem_st_32x16(tO + c * 16, o);
             }
             tmem_st_wait();
+          } else {
+            mbar_wait(p_half, static_cast<uint32_t>((j - 1) & 1));
           }
         }
         l_run *= alpha;
-        tick(3);                                          // waited for the previous P V (+ rare rescale)
+        tick(3);                                          // waited for (half of) the previous P V (+ rare rescale)
         const float base = (m_run == -INFINITY) ? 0.f : m_run * p.scale_log2;
         l_run += chunk_probs<true>(v0, true, 0, 0, 0, 0, p.scale_log2, base, prow, 0, r);
         l_run += chunk_probs<true>(v1, true, 0, 0, 0, 0, p.scale_log2, base, prow, 4, r);
+        if (!pv_done) mbar_wait(p_empty, static_cast<uint32_t>((j - 1) & 1));
         l_run += chunk_probs<true>(v2, true, 0, 0, 0, 0, p.scale_log2, base, prow + BM * 128, 0, r);
         l_run += chunk_probs<true>(v3, true, 0, 0, 0, 0, p.scale_log2, base, prow + BM * 128, 4, r);
         tick(4);                                          // exponentials, pack, P stores
@@ -584,7 +595,8 @@ fa_tc_vit_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_constant
   uint64_t* s_empty = bars + 8;                     // 128 arrivals
   uint64_t* p_full = bars + 9;                      // 128 arrivals
   uint64_t* p_empty = bars + 10;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 11);
+  uint64_t* p_half = bars + 11;                     // the first 64-key block of P has been read by P V
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 12);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int head = blockIdx.y, crop = blockIdx.z;
@@ -607,6 +619,7 @@ fa_tc_vit_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_constant
     mbar_init(s_empty, 128);
     mbar_init(p_full, 128);
     mbar_init(p_empty, 1);
+    mbar_init(p_half, 1);
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -660,6 +673,7 @@ fa_tc_vit_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_constant
           const uint32_t acc = (j > 0 || k > 0) ? 1u : 0u;
           umma_bf16(tO, da, make_desc_mn_sw128(sv0 + k * 2048, 16), idesc_pv64, acc);       // dims 0..63
           umma_bf16(tO + 64, da, make_desc_sw32(sv1 + k * 512), idesc_pv16, acc);           // dims 64..79
+          if (k == 3) umma_commit(p_half);
         }
         umma_commit(p_empty);
         umma_commit(v_empty);
@@ -723,10 +737,12 @@ fa_tc_vit_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_constant
           m_run = tile_max;
           grow = true;
         }
+        bool pv_done = j == 0;
         if (j > 0) {
-          mbar_wait(p_empty, static_cast<uint32_t>((j - 1) & 1));
-          tc_fence_after();
           if (__any_sync(0xffffffffu, grow)) {
+            mbar_wait(p_empty, static_cast<uint32_t>((j - 1) & 1));
+            pv_done = true;
+            tc_fence_after();
 #pragma unroll 1
             for (int c = 0; c < 5; ++c) {                      // 80 O columns, 16 at a time
               uint32_t o[16];
@@ -737,12 +753,15 @@ fa_tc_vit_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_constant
               tmem_st_32x16(tO + c * 16, o);
             }
             tmem_st_wait();
+          } else {
+            mbar_wait(p_half, static_cast<uint32_t>((j - 1) & 1));
           }
         }
         l_run *= alpha;
         const float base = (m_run == -INFINITY) ? 0.f : m_run * p.scale_log2;
         l_run += chunk_probs<true>(v0, true, 0, 0, 0, 0, p.scale_log2, base, prow, 0, r);
         l_run += chunk_probs<true>(v1, true, 0, 0, 0, 0, p.scale_log2, base, prow, 4, r);
+        if (!pv_done) mbar_wait(p_empty, static_cast<uint32_t>((j - 1) & 1));
         l_run += chunk_probs<true>(v2, true, 0, 0, 0, 0, p.scale_log2, base, prow + BM * 128, 0, r);
         l_run += chunk_probs<true>(v3, true, 0, 0, 0, 0, p.scale_log2, base, prow + BM * 128, 4, r);
         tc_fence_before();
