@@ -153,7 +153,8 @@ int md_prefill_attention_bf16(const void* q, int n_heads, int total_tokens, cons
                               const md_kv* kv, int layer, void* out, void* stream);
 /* Testing / A-B timing only: 0 = tcgen05 attention with the single-pass softmax (default: a thread keeps its row's 128
  * scores of a tile in registers, lazy O rescale), 1 = the legacy mma.sync kernel, 2 = tcgen05 attention with the
- * two-pass softmax, 3 = the default prefill kernel with per-phase clock sums (tools/attn_phases.py). */
+ * two-pass softmax, 3 = the default prefill kernel with per-phase clock sums (tools/attn_phases.py), 4 = the default
+ * kernels launched with one CTA per work item instead of persistent CTAs. */
 void md_debug_attention_impl(int impl);
 /* Testing / A-B timing only: programmatic dependent launch between consecutive kernels (default on). */
 void md_debug_set_pdl(int enable);

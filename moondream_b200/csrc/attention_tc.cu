@@ -148,6 +148,7 @@ struct FaTcParams {
   const int* start_pos;     // [n_seqs]
   const int* block_tables;  // [n_seqs][max_blocks]
   int max_blocks, n_heads, n_kv_heads, layer, n_pages, prefix_len;
+  int n_seqs, nq_tiles;     // work items = nq_tiles x n_heads x n_seqs (128-query tile, head, sequence)
   __nv_bfloat16* out;       // [T_total, n_heads * 64]
   float scale_log2;
 };
@@ -180,38 +181,23 @@ fa_tc_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   uint8_t* sV = sK + kStages * kKVBytes;            // [stage][16 KB]
   uint8_t* sP = sV + kStages * kKVBytes;            // 32 KB
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kSmemTiles);
-  uint64_t* q_full = bars;                          // 1
   // K and V stages are released separately: K right after its Q K^T (early in the PREVIOUS tile's softmax), V after
-  // its P V.  With one barrier pair per (K, V) stage the load of tile j could only be requested once P V of tile j - 2
-  // had finished, i.e. one softmax ahead of its use — less than an L2 round trip under load, which made the kernel
-  // TMA-latency-bound (softmax warps stalled on s_full, profiles/r02_ncu_attention_summary.json).
+  // its P V, so a tile's loads are requested about two softmax durations ahead of their use.
+  uint64_t* q_full = bars;                          // 1
   uint64_t* k_full = bars + 1;                      // [2]
   uint64_t* k_empty = bars + 3;                     // [2]
   uint64_t* s_full = bars + 5;                      // 1
-  uint64_t* s_empty = bars + 6;                     // 1 (128 arrivals per softmax warpgroup)
-  uint64_t* p_full = bars + 7;                      // 1 (128 arrivals per softmax warpgroup)
+  uint64_t* s_empty = bars + 6;                     // 1 (128 arrivals)
+  uint64_t* p_full = bars + 7;                      // 1 (128 arrivals)
   uint64_t* p_empty = bars + 8;                     // 1
   uint64_t* v_full = bars + 9;                      // [2]
   uint64_t* v_empty = bars + 11;                    // [2]
   uint64_t* p_half = bars + 13;                     // 1: the first 64-key block of P has been read by P V
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 14);
+  uint64_t* q_empty = bars + 14;                    // 1: the item's last Q K^T has read Q
+  uint64_t* o_free = bars + 15;                     // 1 (128 arrivals): the item's O has been read out of TMEM
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 16);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int head = blockIdx.y, seq = blockIdx.z;
-  const int q0 = blockIdx.x * BM;
-  const int q_off = p.q_offsets[seq];
-  const int n_q = p.q_offsets[seq + 1] - q_off;
-  if (q0 >= n_q) return;                            // uniform per CTA
-  const int q_pos0 = p.start_pos[seq];
-  const int kv_len = q_pos0 + n_q;
-  const int* btab = p.block_tables + static_cast<long long>(seq) * p.max_blocks;
-
-  // keys this query tile can see (prefix rows see the whole prefix; later rows are causal)
-  int reach = q_pos0 + min(q0 + BM, n_q);
-  if (q_pos0 + q0 < p.prefix_len) reach = max(reach, p.prefix_len);
-  reach = min(reach, kv_len);
-  const int n_tiles = (reach + BN - 1) / BN;
-
   if (warp == 0 && lane == 0) {
     prefetch_tensormap(&tmQ);
     prefetch_tensormap(&tmKV);
@@ -227,6 +213,8 @@ fa_tc_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     mbar_init(p_full, 128);
     mbar_init(p_empty, 1);
     mbar_init(p_half, 1);
+    mbar_init(q_empty, 1);
+    mbar_init(o_free, 128);
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -241,33 +229,69 @@ fa_tc_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   pdl_launch_dependents();
   pdl_wait();
 
+  // PERSISTENT over work items = (128-query tile, head, sequence): a CTA that lives for one item spends a third of its
+  // life outside the key-tile loop (launch, barrier / TMEM set-up, first Q / K round trip, O read-out, exit: measured
+  // with tools/attn_phases.py), so a CTA walks items blockIdx.x, blockIdx.x + gridDim.x, ...; the three roles iterate
+  // the same list, barrier parities run on a global tile counter g and item counter ni, the loader runs ahead into the
+  // next item as soon as Q (q_empty) and the K / V stages are free, and the first P V of an item waits until the
+  // previous item's O has left TMEM (o_free).  With gridDim.x = number of items it degenerates to one item per CTA.
+  const int nq_tiles = p.nq_tiles;
+  const int total_items = nq_tiles * p.n_heads * p.n_seqs;
+  struct Item { int q0, head, q_off, n_q, q_pos0, kv_len, n_tiles; const int* btab; bool ok; };
+  auto get_item = [&](int it) {
+    Item t;
+    const int qt = it % nq_tiles, rest = it / nq_tiles;
+    t.head = rest % p.n_heads;
+    const int seq = rest / p.n_heads;
+    t.q0 = qt * BM;
+    t.q_off = p.q_offsets[seq];
+    t.n_q = p.q_offsets[seq + 1] - t.q_off;
+    t.ok = t.q0 < t.n_q;
+    t.q_pos0 = p.start_pos[seq];
+    t.kv_len = t.q_pos0 + t.n_q;
+    t.btab = p.block_tables + static_cast<long long>(seq) * p.max_blocks;
+    // keys this query tile can see (prefix rows see the whole prefix; later rows are causal)
+    int reach = t.q_pos0 + min(t.q0 + BM, t.n_q);
+    if (t.q_pos0 + t.q0 < p.prefix_len) reach = max(reach, p.prefix_len);
+    reach = min(reach, t.kv_len);
+    t.n_tiles = (reach + BN - 1) / BN;
+    return t;
+  };
+
   if (warp == 0) {
     // ------------------------------ TMA loader ------------------------------
     if (lane == 0) {
-      mbar_arrive_expect_tx(q_full, kQBytes);
-      tma_load_2d(sQ, &tmQ, q_full, head * HD, q_off + q0);
       const long long page_rows = 2LL * p.n_kv_heads * 64;              // rows of one page (k then v)
-      const int kv_head = head / (p.n_heads / p.n_kv_heads);           // grouped-query attention (text.py:49)
-      for (int j = 0; j < n_tiles; ++j) {
-        const int st = j & 1;
-        const uint32_t u = static_cast<uint32_t>(j >> 1);
-        long long row_k[2];
+      uint32_t g = 0, ni = 0;
+      for (int it = blockIdx.x; it < total_items; it += gridDim.x) {
+        const Item t = get_item(it);
+        if (!t.ok) continue;
+        const int kv_head = t.head / (p.n_heads / p.n_kv_heads);       // grouped-query attention (text.py:49)
+        mbar_wait(q_empty, (ni & 1u) ^ 1u);                             // the previous item's Q K^Ts are done with Q
+        mbar_arrive_expect_tx(q_full, kQBytes);
+        tma_load_2d(sQ, &tmQ, q_full, t.head * HD, t.q_off + t.q0);
+        for (int j = 0; j < t.n_tiles; ++j, ++g) {
+          const int st = g & 1;
+          const uint32_t u = g >> 1;
+          long long row_k[2];
 #pragma unroll
-        for (int h2 = 0; h2 < 2; ++h2) {
-          const int blk = min(2 * j + h2, p.max_blocks - 1);
-          row_k[h2] = (static_cast<long long>(p.layer) * p.n_pages + btab[blk]) * page_rows + static_cast<long long>(kv_head) * 64;
+          for (int h2 = 0; h2 < 2; ++h2) {
+            const int blk = min(2 * j + h2, p.max_blocks - 1);
+            row_k[h2] = (static_cast<long long>(p.layer) * p.n_pages + t.btab[blk]) * page_rows + static_cast<long long>(kv_head) * 64;
+          }
+          mbar_wait(&k_empty[st], (u & 1) ^ 1);
+          mbar_arrive_expect_tx(&k_full[st], kKVBytes);
+#pragma unroll
+          for (int h2 = 0; h2 < 2; ++h2)
+            tma_load_2d(sK + st * kKVBytes + h2 * (kKVBytes / 2), &tmKV, &k_full[st], 0, static_cast<int32_t>(row_k[h2]));
+          mbar_wait(&v_empty[st], (u & 1) ^ 1);
+          mbar_arrive_expect_tx(&v_full[st], kKVBytes);
+#pragma unroll
+          for (int h2 = 0; h2 < 2; ++h2)
+            tma_load_2d(sV + st * kKVBytes + h2 * (kKVBytes / 2), &tmKV, &v_full[st], 0,
+                        static_cast<int32_t>(row_k[h2] + static_cast<long long>(p.n_kv_heads) * 64));
         }
-        mbar_wait(&k_empty[st], (u & 1) ^ 1);
-        mbar_arrive_expect_tx(&k_full[st], kKVBytes);
-#pragma unroll
-        for (int h2 = 0; h2 < 2; ++h2)
-          tma_load_2d(sK + st * kKVBytes + h2 * (kKVBytes / 2), &tmKV, &k_full[st], 0, static_cast<int32_t>(row_k[h2]));
-        mbar_wait(&v_empty[st], (u & 1) ^ 1);
-        mbar_arrive_expect_tx(&v_full[st], kKVBytes);
-#pragma unroll
-        for (int h2 = 0; h2 < 2; ++h2)
-          tma_load_2d(sV + st * kKVBytes + h2 * (kKVBytes / 2), &tmKV, &v_full[st], 0,
-                      static_cast<int32_t>(row_k[h2] + static_cast<long long>(p.n_kv_heads) * 64));
+        ++ni;
       }
     }
   } else if (warp == 1) {
@@ -277,11 +301,13 @@ fa_tc_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       constexpr uint32_t idesc_pv = make_idesc_bf16_f32_bmn(BM, HD);      // O[128,64] += P V (V MN-major)
       const uint32_t tS = tmem_base + kColS, tO = tmem_base + kColO;
       const uint64_t dQ = make_desc_k_sw128(smem_u32(sQ));
-      mbar_wait(q_full, 0);
-      auto issue_pv = [&](int j) {
-        const int st = j & 1;
-        mbar_wait(&v_full[st], static_cast<uint32_t>(j >> 1) & 1);
-        mbar_wait(p_full, static_cast<uint32_t>(j & 1));
+      uint32_t g = 0, ni = 0;
+      // P V of the tile with global index gg; `first` = the item's first tile (overwrites O)
+      auto issue_pv = [&](uint32_t gg, bool first) {
+        const int st = gg & 1;
+        mbar_wait(&v_full[st], (gg >> 1) & 1u);
+        mbar_wait(p_full, gg & 1u);
+        if (first) mbar_wait(o_free, (ni & 1u) ^ 1u);                   // the previous item's O has been read out
         tc_fence_after();
         const uint32_t sp = smem_u32(sP), sv = smem_u32(sV + st * kKVBytes);
 #pragma unroll
@@ -290,53 +316,64 @@ fa_tc_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           // B: V, MN-major: 16 keys = 16 rows of 128 B = 2048 B
           const uint64_t da = make_desc_k_sw128(sp + (k >> 2) * (BM * 128)) + static_cast<uint64_t>(2 * (k & 3));
           const uint64_t db = make_desc_mn_sw128(sv + k * 2048, 16);
-          umma_bf16(tO, da, db, idesc_pv, (j > 0 || k > 0) ? 1u : 0u);
+          umma_bf16(tO, da, db, idesc_pv, (!first || k > 0) ? 1u : 0u);
           if (k == 3) umma_commit(p_half);   // the first 64-key block of P may be overwritten already
         }
         umma_commit(p_empty);            // P buffer reusable, O updated
         umma_commit(&v_empty[st]);       // V stage reusable
       };
-      for (int j = 0; j < n_tiles; ++j) {
-        const int st = j & 1;
-        const uint32_t u = static_cast<uint32_t>(j >> 1);
-        mbar_wait(&k_full[st], u & 1);
-        mbar_wait(s_empty, static_cast<uint32_t>(j & 1) ^ 1);             // softmax(j-1) has read S
-        tc_fence_after();
-        const uint64_t dK = make_desc_k_sw128(smem_u32(sK + st * kKVBytes));
+      for (int it = blockIdx.x; it < total_items; it += gridDim.x) {
+        const Item t = get_item(it);
+        if (!t.ok) continue;
+        mbar_wait(q_full, ni & 1u);
+        for (int j = 0; j < t.n_tiles; ++j, ++g) {
+          const int st = g & 1;
+          mbar_wait(&k_full[st], (g >> 1) & 1u);
+          mbar_wait(s_empty, (g & 1u) ^ 1u);                            // the previous tile's softmax has read S
+          tc_fence_after();
+          const uint64_t dK = make_desc_k_sw128(smem_u32(sK + st * kKVBytes));
 #pragma unroll
-        for (int k = 0; k < HD / 16; ++k)
-          umma_bf16(tS, dQ + static_cast<uint64_t>(2 * k), dK + static_cast<uint64_t>(2 * k), idesc_qk, k > 0 ? 1u : 0u);
-        umma_commit(s_full);
-        umma_commit(&k_empty[st]);       // K stage reusable as soon as this Q K^T has read it
-        if (j > 0) issue_pv(j - 1);
+          for (int k = 0; k < HD / 16; ++k)
+            umma_bf16(tS, dQ + static_cast<uint64_t>(2 * k), dK + static_cast<uint64_t>(2 * k), idesc_qk, k > 0 ? 1u : 0u);
+          umma_commit(s_full);
+          umma_commit(&k_empty[st]);       // K stage reusable as soon as this Q K^T has read it
+          if (j + 1 == t.n_tiles) umma_commit(q_empty);                // Q reusable: the loader may fetch the next item's
+          if (j > 0) issue_pv(g - 1, j == 1);
+        }
+        issue_pv(g - 1, t.n_tiles == 1);
+        ++ni;
       }
-      issue_pv(n_tiles - 1);
     }
   } else {
     // ------------------------------ softmax (128 threads, one query row each) ------------------------------
     const int quad = warp & 3;
     const int r = quad * 32 + lane;                       // row in the tile = TMEM lane
-    const int qpos = q_pos0 + q0 + r;
-    const bool row_ok = q0 + r < n_q;
     const uint32_t lane_addr = static_cast<uint32_t>(quad * 32) << 16;
     const uint32_t tS = tmem_base + lane_addr + kColS, tO = tmem_base + lane_addr + kColO;
-    float m_run = -INFINITY, l_run = 0.f;                 // SINGLE: m_run = the maximum O and l are currently scaled by
-    const int q_lo = q_pos0 + q0;                          // smallest query position of this CTA
     uint8_t* prow = sP + r * 128;
-    // first key position this row may NOT attend to (prefix-LM mask of moondream.py:138-146 + sequence length)
-    const int row_lim = min(kv_len, qpos < p.prefix_len ? max(qpos + 1, p.prefix_len) : qpos + 1);
     // debug timeline (tools/attn_phases.py): clock sums of the phases of one softmax thread
     const bool tlp = PROF && tl_on() && threadIdx.x == 64;
-    long long ph[6] = {0, 0, 0, 0, 0, 0}, tc0 = 0;
+    long long ph[6] = {0, 0, 0, 0, 0, 0}, tc0 = 0, tiles_done = 0;
     auto tick = [&](int i) { if (tlp) { const long long now = clock64(); ph[i] += now - tc0; tc0 = now; } };
     const long long t_begin = tlp ? clock64() : 0;
-    for (int j = 0; j < n_tiles; ++j) {
+    uint32_t g = 0;
+    for (int it = blockIdx.x; it < total_items; it += gridDim.x) {
+      const Item t = get_item(it);
+      if (!t.ok) continue;
+      const int q0 = t.q0, head = t.head, q_off = t.q_off, n_q = t.n_q, q_pos0 = t.q_pos0, kv_len = t.kv_len, n_tiles = t.n_tiles;
+      const int qpos = q_pos0 + q0 + r;
+      const bool row_ok = q0 + r < n_q;
+      float m_run = -INFINITY, l_run = 0.f;               // SINGLE: m_run = the maximum O and l are currently scaled by
+      const int q_lo = q_pos0 + q0;                        // smallest query position of this item
+      // first key position this row may NOT attend to (prefix-LM mask of moondream.py:138-146 + sequence length)
+      const int row_lim = min(kv_len, qpos < p.prefix_len ? max(qpos + 1, p.prefix_len) : qpos + 1);
+      for (int j = 0; j < n_tiles; ++j, ++g) {
       const int k0 = j * BN;
       // interior tiles need no masking: every key exists and every row of the CTA may attend to it
       const bool full = (k0 + BN <= kv_len) &&
                         (k0 + BN - 1 <= q_lo || (k0 + BN <= p.prefix_len && q_lo + BM <= p.prefix_len));
       if (tlp) tc0 = clock64();
-      mbar_wait(s_full, static_cast<uint32_t>(j & 1));
+      mbar_wait(s_full, g & 1u);
       tc_fence_after();
       if constexpr (SINGLE) {
         tick(0);                                          // waited for S
@@ -374,7 +411,7 @@ fa_tc_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         if (j > 0) {
           const bool any_grow = __any_sync(0xffffffffu, grow);      // warp-uniform; lanes that did not grow multiply by 1
           if (any_grow) {
-            mbar_wait(p_empty, static_cast<uint32_t>((j - 1) & 1));
+            mbar_wait(p_empty, (g - 1u) & 1u);
             pv_done = true;
             tc_fence_after();
 #pragma unroll 1
@@ -388,7 +425,7 @@ fa_tc_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             }
             tmem_st_wait();
           } else {
-            mbar_wait(p_half, static_cast<uint32_t>((j - 1) & 1));
+            mbar_wait(p_half, (g - 1u) & 1u);
           }
         }
         l_run *= alpha;
@@ -396,7 +433,7 @@ fa_tc_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         const float base = (m_run == -INFINITY) ? 0.f : m_run * p.scale_log2;
         l_run += chunk_probs<true>(v0, true, 0, 0, 0, 0, p.scale_log2, base, prow, 0, r);
         l_run += chunk_probs<true>(v1, true, 0, 0, 0, 0, p.scale_log2, base, prow, 4, r);
-        if (!pv_done) mbar_wait(p_empty, static_cast<uint32_t>((j - 1) & 1));
+        if (!pv_done) mbar_wait(p_empty, (g - 1u) & 1u);
         l_run += chunk_probs<true>(v2, true, 0, 0, 0, 0, p.scale_log2, base, prow + BM * 128, 0, r);
         l_run += chunk_probs<true>(v3, true, 0, 0, 0, 0, p.scale_log2, base, prow + BM * 128, 4, r);
         tick(4);                                          // exponentials, pack, P stores
@@ -426,7 +463,7 @@ fa_tc_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       const float alpha = (m_run == -INFINITY) ? 0.f : ex2_approx(m_run * p.scale_log2 - base);
       // the previous P V must have completed before O is rescaled and P is overwritten
       if (j > 0) {
-        mbar_wait(p_empty, static_cast<uint32_t>((j - 1) & 1));
+        mbar_wait(p_empty, (g - 1u) & 1u);
         tc_fence_after();
         if (__any_sync(0xffffffffu, mx != m_run)) {      // warp-uniform: rescale this warp's 32 rows of O
           uint32_t o0[32], o1[32];
@@ -468,31 +505,42 @@ fa_tc_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       fence_proxy_async_smem();
       mbar_arrive(p_full);
     }
-    if (tlp) {     // two records: phase sums [0..4], then [5], total softmax-loop clocks, tiles
-      tl_emit(5u << 28, ph[0], ph[1], ph[2], ph[3], ph[4]);
-      tl_emit(6u << 28, ph[5], clock64() - t_begin, n_tiles, 0, 0);
-    }
-    // ---- epilogue: O / l -> bf16 -> global ----
-    mbar_wait(p_empty, static_cast<uint32_t>((n_tiles - 1) & 1));
-    tc_fence_after();
-    const float inv = l_run > 0.f ? 1.0f / l_run : 0.f;
-    __nv_bfloat16* orow = p.out + (static_cast<long long>(q_off) + q0 + r) * (static_cast<long long>(p.n_heads) * HD) + head * HD;
-#pragma unroll 1
-    for (int c = 0; c < HD / 32; ++c) {
-      uint32_t o[32];
-      tmem_ld_32x32(tO + c * 32, o);
+      tiles_done += n_tiles;
+      // ---- epilogue: O / l -> bf16 -> global ----
+      mbar_wait(p_empty, (g - 1u) & 1u);
+      tc_fence_after();
+      const float inv = l_run > 0.f ? 1.0f / l_run : 0.f;
+      __nv_bfloat16* orow = p.out + (static_cast<long long>(q_off) + q0 + r) * (static_cast<long long>(p.n_heads) * HD) + head * HD;
+      uint32_t o0[32], o1[32];
+      tmem_ld_32x32(tO, o0);
+      tmem_ld_32x32(tO + 32, o1);
       tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(o_free);                                  // the next item's first P V may overwrite O
       if (row_ok) {
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
+        for (int g8 = 0; g8 < 4; ++g8) {
           uint4 w;
-          w.x = pack_bf16x2(__uint_as_float(o[8 * g]) * inv, __uint_as_float(o[8 * g + 1]) * inv);
-          w.y = pack_bf16x2(__uint_as_float(o[8 * g + 2]) * inv, __uint_as_float(o[8 * g + 3]) * inv);
-          w.z = pack_bf16x2(__uint_as_float(o[8 * g + 4]) * inv, __uint_as_float(o[8 * g + 5]) * inv);
-          w.w = pack_bf16x2(__uint_as_float(o[8 * g + 6]) * inv, __uint_as_float(o[8 * g + 7]) * inv);
-          *reinterpret_cast<uint4*>(orow + c * 32 + g * 8) = w;
+          w.x = pack_bf16x2(__uint_as_float(o0[8 * g8]) * inv, __uint_as_float(o0[8 * g8 + 1]) * inv);
+          w.y = pack_bf16x2(__uint_as_float(o0[8 * g8 + 2]) * inv, __uint_as_float(o0[8 * g8 + 3]) * inv);
+          w.z = pack_bf16x2(__uint_as_float(o0[8 * g8 + 4]) * inv, __uint_as_float(o0[8 * g8 + 5]) * inv);
+          w.w = pack_bf16x2(__uint_as_float(o0[8 * g8 + 6]) * inv, __uint_as_float(o0[8 * g8 + 7]) * inv);
+          *reinterpret_cast<uint4*>(orow + g8 * 8) = w;
+        }
+#pragma unroll
+        for (int g8 = 0; g8 < 4; ++g8) {
+          uint4 w;
+          w.x = pack_bf16x2(__uint_as_float(o1[8 * g8]) * inv, __uint_as_float(o1[8 * g8 + 1]) * inv);
+          w.y = pack_bf16x2(__uint_as_float(o1[8 * g8 + 2]) * inv, __uint_as_float(o1[8 * g8 + 3]) * inv);
+          w.z = pack_bf16x2(__uint_as_float(o1[8 * g8 + 4]) * inv, __uint_as_float(o1[8 * g8 + 5]) * inv);
+          w.w = pack_bf16x2(__uint_as_float(o1[8 * g8 + 6]) * inv, __uint_as_float(o1[8 * g8 + 7]) * inv);
+          *reinterpret_cast<uint4*>(orow + 32 + g8 * 8) = w;
         }
       }
+    }
+    if (tlp) {     // two records: phase sums [0..4], then [5], total softmax-loop clocks, tiles
+      tl_emit(5u << 28, ph[0], ph[1], ph[2], ph[3], ph[4]);
+      tl_emit(6u << 28, ph[5], clock64() - t_begin, tiles_done, 0, 0);
     }
   }
 
@@ -532,7 +580,13 @@ int prefill_attention_tc(const __nv_bfloat16* q, int n_heads, int n_kv_heads, in
   p.max_blocks = max_blocks; p.n_heads = n_heads; p.n_kv_heads = n_kv_heads; p.layer = layer; p.n_pages = n_pages;
   p.prefix_len = prefix_len; p.out = out;
   p.scale_log2 = 0.125f * 1.4426950408889634f;
-  dim3 grid((max_q + fa::BM - 1) / fa::BM, n_heads, n_seqs);
+  p.n_seqs = n_seqs;
+  p.nq_tiles = (max_q + fa::BM - 1) / fa::BM;
+  const long long items = static_cast<long long>(p.nq_tiles) * n_heads * n_seqs;
+  if (items >= (1LL << 31)) return set_error("prefill_attention: too many work items");
+  // persistent: two CTAs per SM walk the items (md_debug_attention_impl(4): one CTA per item, the previous form)
+  const long long resident = 2LL * num_sms();
+  dim3 grid(static_cast<unsigned>(g_attention_impl == 4 || items < resident ? items : resident));
   count_launch();
   // default: the single-pass softmax; md_debug_attention_impl(2) = the two-pass form, (3) = single pass with phase clocks
   const dim3 block(fa::kThreads);

@@ -35,7 +35,7 @@ def test_layernorm(rows, dim):
     assert ((y != ref).float().mean().item()) < 0.02
 
 
-@pytest.mark.parametrize("impl", [0, 1, 2], ids=["tcgen05_single_pass", "mma_sync", "tcgen05_two_pass"])
+@pytest.mark.parametrize("impl", [0, 1, 2, 4], ids=["tcgen05_single_pass", "mma_sync", "tcgen05_two_pass", "tcgen05_single_pass_one_item_per_cta"])
 @pytest.mark.parametrize("n_crops,heads", [(1, 16), (3, 2), (2, 10)])
 def test_vit_attention(n_crops, heads, impl):
     N, lib = _lib()
@@ -76,7 +76,7 @@ def _rope_ref(x, table, pos):
     return torch.cat([rot, x[..., 32:]], dim=-1)
 
 
-@pytest.mark.parametrize("impl", [0, 1, 2], ids=["tcgen05_single_pass", "mma_sync", "tcgen05_two_pass"])
+@pytest.mark.parametrize("impl", [0, 1, 2, 4], ids=["tcgen05_single_pass", "mma_sync", "tcgen05_two_pass", "tcgen05_single_pass_one_item_per_cta"])
 def test_rope_prefill_decode_attention(impl):
     from moondream_b200.engine import rope_table
 

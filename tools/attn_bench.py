@@ -23,7 +23,7 @@ qo = torch.arange(0, T + 1, L, dtype=torch.int32, device="cuda")
 sp = torch.zeros(n_seqs, dtype=torch.int32, device="cuda")
 flops = 4.0 * heads * n_seqs * L * L * 64
 res = {}
-for impl in (0, 1, 2):
+for impl in (0, 1, 2, 4):
     lib.md_debug_attention_impl(impl)
     def run():
         N.check(lib.md_prefill_attention_bf16(N.ptr(q), heads, T, N.ptr(qo), N.ptr(sp), n_seqs, L, 730,
@@ -39,8 +39,8 @@ for impl in (0, 1, 2):
     torch.cuda.synchronize()
     ms = s.elapsed_time(e) / 10
     res[impl] = out.float().clone()
-    print({"impl": {0: "tcgen05 single-pass softmax (default)", 1: "mma.sync", 2: "tcgen05 two-pass softmax"}[impl], "ms": ms, "tflops": flops / ms / 1e9}, flush=True)
-print("rel diff vs mma.sync:", {i: ((res[i] - res[1]).norm() / res[1].norm()).item() for i in (0, 2)})
+    print({"impl": {0: "tcgen05 single-pass softmax, persistent CTAs (default)", 1: "mma.sync", 2: "tcgen05 two-pass softmax", 4: "tcgen05 single-pass, one item per CTA"}[impl], "ms": ms, "tflops": flops / ms / 1e9}, flush=True)
+print("rel diff vs mma.sync:", {i: ((res[i] - res[1]).norm() / res[1].norm()).item() for i in (0, 2, 4)})
 lib.md_debug_attention_impl(0)
 # occupancy probe
 print("done")
@@ -52,7 +52,7 @@ qkv = torch.randn(n_crops * seq, 3 * Dv, device="cuda").bfloat16()
 vout = torch.empty(n_crops * seq, Dv, device="cuda", dtype=torch.bfloat16)
 vflops = 4.0 * vh * n_crops * seq * seq * 72
 vres = {}
-for impl in (0, 1, 2):
+for impl in (0, 1, 2, 4):
     lib.md_debug_attention_impl(impl)
     def runv():
         N.check(lib.md_vit_attention_bf16(N.ptr(qkv), n_crops, seq, vh, N.ptr(vout), N.current_stream()))
@@ -67,6 +67,6 @@ for impl in (0, 1, 2):
     torch.cuda.synchronize()
     ms = s.elapsed_time(e) / 10
     vres[impl] = vout.float().clone()
-    print({"vit impl": {0: "tcgen05 single-pass softmax (default)", 1: "mma.sync", 2: "tcgen05 two-pass softmax"}[impl], "ms": ms, "tflops": vflops / ms / 1e9}, flush=True)
-print("vit rel diff vs mma.sync:", {i: ((vres[i] - vres[1]).norm() / vres[1].norm()).item() for i in (0, 2)})
+    print({"vit impl": {0: "tcgen05 single-pass softmax, persistent CTAs (default)", 1: "mma.sync", 2: "tcgen05 two-pass softmax", 4: "tcgen05 single-pass, one item per CTA"}[impl], "ms": ms, "tflops": vflops / ms / 1e9}, flush=True)
+print("vit rel diff vs mma.sync:", {i: ((vres[i] - vres[1]).norm() / vres[1].norm()).item() for i in (0, 2, 4)})
 lib.md_debug_attention_impl(0)
