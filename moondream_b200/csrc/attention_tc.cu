@@ -622,7 +622,7 @@ constexpr uint32_t kColS = 0, kColO = 128;       // O: 80 columns (64 + 16)
 }  // namespace fv
 
 struct FaVitParams {
-  int seq, n_heads;
+  int seq, n_heads, n_crops;
   __nv_bfloat16* out;        // [n_crops * seq, n_heads * 72]
   float scale_log2;
 };
@@ -650,15 +650,17 @@ fa_tc_vit_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_constant
   uint64_t* p_full = bars + 9;                      // 128 arrivals
   uint64_t* p_empty = bars + 10;
   uint64_t* p_half = bars + 11;                     // the first 64-key block of P has been read by P V
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 12);
+  uint64_t* q_empty = bars + 12;                    // the item's last Q K^T has read Q
+  uint64_t* o_free = bars + 13;                     // 128 arrivals: the item's O has been read out of TMEM
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 14);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int head = blockIdx.y, crop = blockIdx.z;
-  const int q0 = blockIdx.x * BM;
   const int n_q = p.seq, kv_len = p.seq;
   const int n_tiles = (kv_len + BN - 1) / BN;
-  const int row0 = crop * p.seq;                    // first token row of this crop
   const int H = p.n_heads;
+  // persistent over work items (128-query tile, head, crop), as fa_tc_prefill_kernel
+  const int nq_tiles = (p.seq + BM - 1) / BM;
+  const int total_items = nq_tiles * H * p.n_crops;
 
   if (warp == 0 && lane == 0) {
     prefetch_tensormap(&tm64);
@@ -674,6 +676,8 @@ fa_tc_vit_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_constant
     mbar_init(p_full, 128);
     mbar_init(p_empty, 1);
     mbar_init(p_half, 1);
+    mbar_init(q_empty, 1);
+    mbar_init(o_free, 128);
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -690,20 +694,24 @@ fa_tc_vit_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_constant
   if (warp == 0) {
     // ------------------------------ TMA loader ------------------------------
     if (lane == 0) {
-      mbar_arrive_expect_tx(q_full, kTile);
-      tma_load_3d(sQ, &tm64, q_full, 0, head, row0 + q0);
-      tma_load_3d(sQ + kBlk0, &tm16, q_full, 64, head, row0 + q0);
-      for (int j = 0; j < n_tiles; ++j) {
-        const int st = j & 1;
-        const uint32_t u = static_cast<uint32_t>(j >> 1);
-        mbar_wait(&k_empty[st], (u & 1) ^ 1);
-        mbar_arrive_expect_tx(&k_full[st], kTile);
-        tma_load_3d(sK + st * kTile, &tm64, &k_full[st], 0, H + head, row0 + j * BN);
-        tma_load_3d(sK + st * kTile + kBlk0, &tm16, &k_full[st], 64, H + head, row0 + j * BN);
-        mbar_wait(v_empty, static_cast<uint32_t>(j & 1) ^ 1);
-        mbar_arrive_expect_tx(v_full, kTile);
-        tma_load_3d(sV, &tm64, v_full, 0, 2 * H + head, row0 + j * BN);
-        tma_load_3d(sV + kBlk0, &tm16, v_full, 64, 2 * H + head, row0 + j * BN);
+      uint32_t g = 0, ni = 0;
+      for (int it = blockIdx.x; it < total_items; it += gridDim.x, ++ni) {
+        const int q0 = (it % nq_tiles) * BM, head = (it / nq_tiles) % H, row0 = (it / (nq_tiles * H)) * p.seq;
+        mbar_wait(q_empty, (ni & 1u) ^ 1u);
+        mbar_arrive_expect_tx(q_full, kTile);
+        tma_load_3d(sQ, &tm64, q_full, 0, head, row0 + q0);
+        tma_load_3d(sQ + kBlk0, &tm16, q_full, 64, head, row0 + q0);
+        for (int j = 0; j < n_tiles; ++j, ++g) {
+          const int st = g & 1;
+          mbar_wait(&k_empty[st], ((g >> 1) & 1u) ^ 1u);
+          mbar_arrive_expect_tx(&k_full[st], kTile);
+          tma_load_3d(sK + st * kTile, &tm64, &k_full[st], 0, H + head, row0 + j * BN);
+          tma_load_3d(sK + st * kTile + kBlk0, &tm16, &k_full[st], 64, H + head, row0 + j * BN);
+          mbar_wait(v_empty, (g & 1u) ^ 1u);
+          mbar_arrive_expect_tx(v_full, kTile);
+          tma_load_3d(sV, &tm64, v_full, 0, 2 * H + head, row0 + j * BN);
+          tma_load_3d(sV + kBlk0, &tm16, v_full, 64, 2 * H + head, row0 + j * BN);
+        }
       }
     }
   } else if (warp == 1) {
@@ -715,16 +723,17 @@ fa_tc_vit_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_constant
       const uint32_t tS = tmem_base + kColS, tO = tmem_base + kColO;
       const uint64_t dQ0 = make_desc_k_sw128(smem_u32(sQ));
       const uint64_t dQ1 = make_desc_sw32(smem_u32(sQ + kBlk0));
-      mbar_wait(q_full, 0);
-      auto issue_pv = [&](int j) {
-        mbar_wait(v_full, static_cast<uint32_t>(j & 1));
-        mbar_wait(p_full, static_cast<uint32_t>(j & 1));
+      uint32_t g = 0, ni = 0;
+      auto issue_pv = [&](uint32_t gg, bool first) {
+        mbar_wait(v_full, gg & 1u);
+        mbar_wait(p_full, gg & 1u);
+        if (first) mbar_wait(o_free, (ni & 1u) ^ 1u);              // the previous item's O has been read out
         tc_fence_after();
         const uint32_t sp = smem_u32(sP), sv0 = smem_u32(sV), sv1 = smem_u32(sV + kBlk0);
 #pragma unroll
         for (int k = 0; k < BN / 16; ++k) {
           const uint64_t da = make_desc_k_sw128(sp + (k >> 2) * (BM * 128)) + static_cast<uint64_t>(2 * (k & 3));
-          const uint32_t acc = (j > 0 || k > 0) ? 1u : 0u;
+          const uint32_t acc = (!first || k > 0) ? 1u : 0u;
           umma_bf16(tO, da, make_desc_mn_sw128(sv0 + k * 2048, 16), idesc_pv64, acc);       // dims 0..63
           umma_bf16(tO + 64, da, make_desc_sw32(sv1 + k * 512), idesc_pv16, acc);           // dims 64..79
           if (k == 3) umma_commit(p_half);
@@ -732,38 +741,44 @@ fa_tc_vit_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_constant
         umma_commit(p_empty);
         umma_commit(v_empty);
       };
-      for (int j = 0; j < n_tiles; ++j) {
-        const int st = j & 1;
-        const uint32_t u = static_cast<uint32_t>(j >> 1);
-        mbar_wait(&k_full[st], u & 1);
-        mbar_wait(s_empty, static_cast<uint32_t>(j & 1) ^ 1);
-        tc_fence_after();
-        const uint64_t dK0 = make_desc_k_sw128(smem_u32(sK + st * kTile));
-        const uint64_t dK1 = make_desc_sw32(smem_u32(sK + st * kTile + kBlk0));
+      for (int it = blockIdx.x; it < total_items; it += gridDim.x, ++ni) {
+        mbar_wait(q_full, ni & 1u);
+        for (int j = 0; j < n_tiles; ++j, ++g) {
+          const int st = g & 1;
+          mbar_wait(&k_full[st], (g >> 1) & 1u);
+          mbar_wait(s_empty, (g & 1u) ^ 1u);
+          tc_fence_after();
+          const uint64_t dK0 = make_desc_k_sw128(smem_u32(sK + st * kTile));
+          const uint64_t dK1 = make_desc_sw32(smem_u32(sK + st * kTile + kBlk0));
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_bf16(tS, dQ0 + static_cast<uint64_t>(2 * k), dK0 + static_cast<uint64_t>(2 * k), idesc_qk, k > 0 ? 1u : 0u);
-        umma_bf16(tS, dQ1, dK1, idesc_qk, 1u);                     // dims 64..79 (72..79 are zero)
-        umma_commit(s_full);
-        umma_commit(&k_empty[st]);
-        if (j > 0) issue_pv(j - 1);
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(tS, dQ0 + static_cast<uint64_t>(2 * k), dK0 + static_cast<uint64_t>(2 * k), idesc_qk, k > 0 ? 1u : 0u);
+          umma_bf16(tS, dQ1, dK1, idesc_qk, 1u);                     // dims 64..79 (72..79 are zero)
+          umma_commit(s_full);
+          umma_commit(&k_empty[st]);
+          if (j + 1 == n_tiles) umma_commit(q_empty);
+          if (j > 0) issue_pv(g - 1, j == 1);
+        }
+        issue_pv(g - 1, n_tiles == 1);
       }
-      issue_pv(n_tiles - 1);
     }
   } else {
     // ------------------------------ softmax (128 threads, one query row each) ------------------------------
     const int quad = warp & 3;
     const int r = quad * 32 + lane;
-    const bool row_ok = q0 + r < n_q;
     const uint32_t lane_addr = static_cast<uint32_t>(quad * 32) << 16;
     const uint32_t tS = tmem_base + lane_addr + kColS, tO = tmem_base + lane_addr + kColO;
-    float m_run = -INFINITY, l_run = 0.f;
     uint8_t* prow = sP + r * 128;
     const int qpos = 1 << 30;                                  // no causal structure: every key is allowed
-    for (int j = 0; j < n_tiles; ++j) {
+    uint32_t g = 0;
+    for (int it = blockIdx.x; it < total_items; it += gridDim.x) {
+      const int q0 = (it % nq_tiles) * BM, head = (it / nq_tiles) % H, row0 = (it / (nq_tiles * H)) * p.seq;
+      const bool row_ok = q0 + r < n_q;
+      float m_run = -INFINITY, l_run = 0.f;
+      for (int j = 0; j < n_tiles; ++j, ++g) {
       const int k0 = j * BN;
       const bool full = k0 + BN <= kv_len;
-      mbar_wait(s_full, static_cast<uint32_t>(j & 1));
+      mbar_wait(s_full, g & 1u);
       tc_fence_after();
       if constexpr (SINGLE) {
         uint32_t v0[32], v1[32], v2[32], v3[32];
@@ -794,7 +809,7 @@ fa_tc_vit_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_constant
         bool pv_done = j == 0;
         if (j > 0) {
           if (__any_sync(0xffffffffu, grow)) {
-            mbar_wait(p_empty, static_cast<uint32_t>((j - 1) & 1));
+            mbar_wait(p_empty, (g - 1u) & 1u);
             pv_done = true;
             tc_fence_after();
 #pragma unroll 1
@@ -808,14 +823,14 @@ fa_tc_vit_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_constant
             }
             tmem_st_wait();
           } else {
-            mbar_wait(p_half, static_cast<uint32_t>((j - 1) & 1));
+            mbar_wait(p_half, (g - 1u) & 1u);
           }
         }
         l_run *= alpha;
         const float base = (m_run == -INFINITY) ? 0.f : m_run * p.scale_log2;
         l_run += chunk_probs<true>(v0, true, 0, 0, 0, 0, p.scale_log2, base, prow, 0, r);
         l_run += chunk_probs<true>(v1, true, 0, 0, 0, 0, p.scale_log2, base, prow, 4, r);
-        if (!pv_done) mbar_wait(p_empty, static_cast<uint32_t>((j - 1) & 1));
+        if (!pv_done) mbar_wait(p_empty, (g - 1u) & 1u);
         l_run += chunk_probs<true>(v2, true, 0, 0, 0, 0, p.scale_log2, base, prow + BM * 128, 0, r);
         l_run += chunk_probs<true>(v3, true, 0, 0, 0, 0, p.scale_log2, base, prow + BM * 128, 4, r);
         tc_fence_before();
@@ -841,7 +856,7 @@ fa_tc_vit_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_constant
       const float base = (mx == -INFINITY) ? 0.f : mx * p.scale_log2;
       const float alpha = (m_run == -INFINITY) ? 0.f : ex2_approx(m_run * p.scale_log2 - base);
       if (j > 0) {
-        mbar_wait(p_empty, static_cast<uint32_t>((j - 1) & 1));
+        mbar_wait(p_empty, (g - 1u) & 1u);
         tc_fence_after();
         if (__any_sync(0xffffffffu, mx != m_run)) {
           uint32_t o0[32], o1[32], o2[16];
@@ -884,34 +899,31 @@ fa_tc_vit_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_constant
       fence_proxy_async_smem();
       mbar_arrive(p_full);
     }
-    // ---- epilogue: 72 of the 80 O columns ----
-    mbar_wait(p_empty, static_cast<uint32_t>((n_tiles - 1) & 1));
-    tc_fence_after();
-    const float inv = l_run > 0.f ? 1.0f / l_run : 0.f;
-    __nv_bfloat16* orow = p.out + (static_cast<long long>(row0) + q0 + r) * (static_cast<long long>(H) * HD) + head * HD;
-    auto st8 = [&](const uint32_t* o, int col) {
-      uint4 w;
-      w.x = pack_bf16x2(__uint_as_float(o[0]) * inv, __uint_as_float(o[1]) * inv);
-      w.y = pack_bf16x2(__uint_as_float(o[2]) * inv, __uint_as_float(o[3]) * inv);
-      w.z = pack_bf16x2(__uint_as_float(o[4]) * inv, __uint_as_float(o[5]) * inv);
-      w.w = pack_bf16x2(__uint_as_float(o[6]) * inv, __uint_as_float(o[7]) * inv);
-      *reinterpret_cast<uint4*>(orow + col) = w;
-    };
-#pragma unroll 1
-    for (int c = 0; c < 2; ++c) {
-      uint32_t o[32];
-      tmem_ld_32x32(tO + c * 32, o);
-      tmem_ld_wait();
-      if (row_ok) {
-#pragma unroll
-        for (int g = 0; g < 4; ++g) st8(o + 8 * g, c * 32 + 8 * g);
-      }
-    }
-    {
-      uint32_t o2[16];
+      // ---- epilogue: 72 of the 80 O columns ----
+      mbar_wait(p_empty, (g - 1u) & 1u);
+      tc_fence_after();
+      const float inv = l_run > 0.f ? 1.0f / l_run : 0.f;
+      __nv_bfloat16* orow = p.out + (static_cast<long long>(row0) + q0 + r) * (static_cast<long long>(H) * HD) + head * HD;
+      auto st8 = [&](const uint32_t* o, int col) {
+        uint4 w;
+        w.x = pack_bf16x2(__uint_as_float(o[0]) * inv, __uint_as_float(o[1]) * inv);
+        w.y = pack_bf16x2(__uint_as_float(o[2]) * inv, __uint_as_float(o[3]) * inv);
+        w.z = pack_bf16x2(__uint_as_float(o[4]) * inv, __uint_as_float(o[5]) * inv);
+        w.w = pack_bf16x2(__uint_as_float(o[6]) * inv, __uint_as_float(o[7]) * inv);
+        *reinterpret_cast<uint4*>(orow + col) = w;
+      };
+      uint32_t o0[32], o1[32], o2[16];
+      tmem_ld_32x32(tO, o0);
+      tmem_ld_32x32(tO + 32, o1);
       tmem_ld_32x16(tO + 64, o2);
       tmem_ld_wait();
-      if (row_ok) st8(o2, 64);                                 // dims 64..71; 72..79 are padding
+      tc_fence_before();
+      mbar_arrive(o_free);                                       // the next item's first P V may overwrite O
+      if (row_ok) {
+#pragma unroll
+        for (int g8 = 0; g8 < 4; ++g8) { st8(o0 + 8 * g8, 8 * g8); st8(o1 + 8 * g8, 32 + 8 * g8); }
+        st8(o2, 64);                                             // dims 64..71; 72..79 are padding
+      }
     }
   }
 
@@ -944,9 +956,12 @@ int vit_attention_tc(const __nv_bfloat16* qkv, int n_crops, int seq, int n_heads
     }
   }
   FaVitParams p{};
-  p.seq = seq; p.n_heads = n_heads; p.out = out;
+  p.seq = seq; p.n_heads = n_heads; p.n_crops = n_crops; p.out = out;
   p.scale_log2 = (1.0f / sqrtf(72.0f)) * 1.4426950408889634f;
-  dim3 grid((seq + fv::BM - 1) / fv::BM, n_heads, n_crops);
+  const long long items = static_cast<long long>((seq + fv::BM - 1) / fv::BM) * n_heads * n_crops;
+  if (items >= (1LL << 31)) return set_error("vit_attention: too many work items");
+  const long long resident = 2LL * num_sms();                   // persistent: two CTAs per SM walk the items
+  dim3 grid(static_cast<unsigned>(g_attention_impl == 4 || items < resident ? items : resident));
   count_launch();
   const cudaError_t e = g_attention_impl == 2
       ? launch_k(fa_tc_vit_kernel<false>, grid, dim3(fv::kThreads), fv::kSmemTotal, stream, t64, t16, p)
