@@ -606,7 +606,7 @@ int prefill_attention_tc(const __nv_bfloat16* q, int n_heads, int n_kv_heads, in
 // zero fill through a 3-D view [token][3*H heads][72]), so
 //   S  = Q K^T : 4 k-steps on the 64-block + 1 k-step on the 16-block,
 //   O += P V   : N = 64 columns from the 64-block and N = 16 columns from the 16-block (both MN-major).
-// K is double-buffered (released as soon as S is complete), V single-buffered: 112 KB, 2 CTAs per SM.
+// One K tile (released as soon as S is complete) and two V stages: 112 KB, 2 CTAs per SM.
 // ------------------------------------------------------------------------------------------------
 namespace fv {
 constexpr int BM = 128, BN = 128, HD = 72;
@@ -614,7 +614,7 @@ constexpr int kBlk0 = 128 * 128;                 // [128 rows x 64] bf16, 16 KB
 constexpr int kBlk1 = 128 * 32;                  // [128 rows x 16] bf16, 4 KB
 constexpr int kTile = kBlk0 + kBlk1;             // 20 KB
 constexpr int kPBytes = BM * BN * 2;             // 32 KB
-constexpr int kSmemTiles = kTile /*Q*/ + 2 * kTile /*K*/ + kTile /*V*/ + kPBytes;   // 112 KB
+constexpr int kSmemTiles = kTile /*Q*/ + kTile /*K*/ + 2 * kTile /*V*/ + kPBytes;   // 112 KB
 constexpr int kSmemTotal = kSmemTiles + 256;
 constexpr int kThreads = 192;
 constexpr uint32_t kTmemCols = 256;
@@ -636,15 +636,18 @@ fa_tc_vit_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_constant
   extern __shared__ __align__(1024) uint8_t smem[];
   if (smem_u32(smem) & 1023) __trap();
   uint8_t* sQ = smem;                               // blk0 | blk1
-  uint8_t* sK = sQ + kTile;                         // [2][blk0 | blk1]
-  uint8_t* sV = sK + 2 * kTile;
-  uint8_t* sP = sV + kTile;
+  // ONE K tile and TWO V stages: the next Q K^T cannot start before this tile's softmax has read S anyway, and K is
+  // free again as soon as its Q K^T has run (early in the previous tile's softmax), so a second K stage buys nothing;
+  // V is needed at the END of its tile's softmax and, single-buffered, could only be requested at its start.
+  uint8_t* sK = sQ + kTile;                         // [blk0 | blk1]
+  uint8_t* sV = sK + kTile;                         // [2][blk0 | blk1]
+  uint8_t* sP = sV + 2 * kTile;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kSmemTiles);
   uint64_t* q_full = bars;
-  uint64_t* k_full = bars + 1;                      // [2]
-  uint64_t* k_empty = bars + 3;                     // [2]
-  uint64_t* v_full = bars + 5;
-  uint64_t* v_empty = bars + 6;
+  uint64_t* k_full = bars + 1;
+  uint64_t* k_empty = bars + 2;
+  uint64_t* v_full = bars + 3;                      // [2]
+  uint64_t* v_empty = bars + 5;                     // [2]
   uint64_t* s_full = bars + 7;
   uint64_t* s_empty = bars + 8;                     // 128 arrivals
   uint64_t* p_full = bars + 9;                      // 128 arrivals
@@ -668,9 +671,9 @@ fa_tc_vit_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_constant
   }
   if (warp == 1 && lane == 0) {
     mbar_init(q_full, 1);
-    for (int i = 0; i < 2; ++i) { mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1); }
-    mbar_init(v_full, 1);
-    mbar_init(v_empty, 1);
+    mbar_init(k_full, 1);
+    mbar_init(k_empty, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1); }
     mbar_init(s_full, 1);
     mbar_init(s_empty, 128);
     mbar_init(p_full, 128);
@@ -703,14 +706,14 @@ fa_tc_vit_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_constant
         tma_load_3d(sQ + kBlk0, &tm16, q_full, 64, head, row0 + q0);
         for (int j = 0; j < n_tiles; ++j, ++g) {
           const int st = g & 1;
-          mbar_wait(&k_empty[st], ((g >> 1) & 1u) ^ 1u);
-          mbar_arrive_expect_tx(&k_full[st], kTile);
-          tma_load_3d(sK + st * kTile, &tm64, &k_full[st], 0, H + head, row0 + j * BN);
-          tma_load_3d(sK + st * kTile + kBlk0, &tm16, &k_full[st], 64, H + head, row0 + j * BN);
-          mbar_wait(v_empty, (g & 1u) ^ 1u);
-          mbar_arrive_expect_tx(v_full, kTile);
-          tma_load_3d(sV, &tm64, v_full, 0, 2 * H + head, row0 + j * BN);
-          tma_load_3d(sV + kBlk0, &tm16, v_full, 64, 2 * H + head, row0 + j * BN);
+          mbar_wait(k_empty, (g & 1u) ^ 1u);
+          mbar_arrive_expect_tx(k_full, kTile);
+          tma_load_3d(sK, &tm64, k_full, 0, H + head, row0 + j * BN);
+          tma_load_3d(sK + kBlk0, &tm16, k_full, 64, H + head, row0 + j * BN);
+          mbar_wait(&v_empty[st], ((g >> 1) & 1u) ^ 1u);
+          mbar_arrive_expect_tx(&v_full[st], kTile);
+          tma_load_3d(sV + st * kTile, &tm64, &v_full[st], 0, 2 * H + head, row0 + j * BN);
+          tma_load_3d(sV + st * kTile + kBlk0, &tm16, &v_full[st], 64, 2 * H + head, row0 + j * BN);
         }
       }
     }
@@ -725,11 +728,12 @@ fa_tc_vit_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_constant
       const uint64_t dQ1 = make_desc_sw32(smem_u32(sQ + kBlk0));
       uint32_t g = 0, ni = 0;
       auto issue_pv = [&](uint32_t gg, bool first) {
-        mbar_wait(v_full, gg & 1u);
+        const int vs = gg & 1;
+        mbar_wait(&v_full[vs], (gg >> 1) & 1u);
         mbar_wait(p_full, gg & 1u);
         if (first) mbar_wait(o_free, (ni & 1u) ^ 1u);              // the previous item's O has been read out
         tc_fence_after();
-        const uint32_t sp = smem_u32(sP), sv0 = smem_u32(sV), sv1 = smem_u32(sV + kBlk0);
+        const uint32_t sp = smem_u32(sP), sv0 = smem_u32(sV + vs * kTile), sv1 = smem_u32(sV + vs * kTile + kBlk0);
 #pragma unroll
         for (int k = 0; k < BN / 16; ++k) {
           const uint64_t da = make_desc_k_sw128(sp + (k >> 2) * (BM * 128)) + static_cast<uint64_t>(2 * (k & 3));
@@ -739,23 +743,22 @@ fa_tc_vit_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_constant
           if (k == 3) umma_commit(p_half);
         }
         umma_commit(p_empty);
-        umma_commit(v_empty);
+        umma_commit(&v_empty[vs]);
       };
       for (int it = blockIdx.x; it < total_items; it += gridDim.x, ++ni) {
         mbar_wait(q_full, ni & 1u);
         for (int j = 0; j < n_tiles; ++j, ++g) {
-          const int st = g & 1;
-          mbar_wait(&k_full[st], (g >> 1) & 1u);
+          mbar_wait(k_full, g & 1u);
           mbar_wait(s_empty, (g & 1u) ^ 1u);
           tc_fence_after();
-          const uint64_t dK0 = make_desc_k_sw128(smem_u32(sK + st * kTile));
-          const uint64_t dK1 = make_desc_sw32(smem_u32(sK + st * kTile + kBlk0));
+          const uint64_t dK0 = make_desc_k_sw128(smem_u32(sK));
+          const uint64_t dK1 = make_desc_sw32(smem_u32(sK + kBlk0));
 #pragma unroll
           for (int k = 0; k < 4; ++k)
             umma_bf16(tS, dQ0 + static_cast<uint64_t>(2 * k), dK0 + static_cast<uint64_t>(2 * k), idesc_qk, k > 0 ? 1u : 0u);
           umma_bf16(tS, dQ1, dK1, idesc_qk, 1u);                     // dims 64..79 (72..79 are zero)
           umma_commit(s_full);
-          umma_commit(&k_empty[st]);
+          umma_commit(k_empty);
           if (j + 1 == n_tiles) umma_commit(q_empty);
           if (j > 0) issue_pv(g - 1, j == 1);
         }
