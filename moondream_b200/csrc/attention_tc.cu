@@ -3,8 +3,9 @@
 // Replaces F.scaled_dot_product_attention at reference text.py:46-50 under the mask of
 // moondream.py:138-146 for prefill-sized query blocks.
 //
-// One CTA = 128 queries of one (sequence, head); key tiles of 128 (= two 64-token KV pages).
-//   warp 0     : TMA loader      (Q once; K and V page boxes into a 2-stage ring)
+// Work item = 128 queries of one (sequence, head), key tiles of 128 (= two 64-token KV pages); persistent CTAs (two per
+// SM) walk the items.
+//   warp 0     : TMA loader      (Q per item; K and V page boxes into separately released 2-stage rings)
 //   warp 1     : MMA issuer      (S = Q K^T -> TMEM; O += P V -> TMEM), one elected lane
 //   warps 2-5  : softmax         (thread = query row = TMEM lane: no shuffles; SINGLE-PASS online softmax in the
 //                                 exp2 domain: the row's 128 scores of a tile are read from TMEM once and stay in
