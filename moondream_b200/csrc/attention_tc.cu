@@ -90,7 +90,7 @@ __device__ __forceinline__ float2 exp2_fma2(float2 x) {
   return make_float2(__int_as_float(__float_as_int(q.x) + (__float_as_int(t.x) << 23)),
                      __int_as_float(__float_as_int(q.y) + (__float_as_int(t.y) << 23)));
 }
-template <bool POLY = false>
+template <int POLY = 0>       // 0: MUFU only; 3 / 4: that many of every 8 exponential pairs on the FMA pipe (4 measured slower)
 __device__ __forceinline__ float chunk_probs(const uint32_t (&v)[32], bool full, int k_first, int kv_len, int qpos,
                                              int prefix_len, float scale_log2, float base, uint8_t* line,
                                              int chunk0, int r) {
@@ -104,8 +104,10 @@ __device__ __forceinline__ float chunk_probs(const uint32_t (&v)[32], bool full,
       const float2 x0 = ffma2(make_float2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1])), sc, nb);
       const float2 x1 = ffma2(make_float2(__uint_as_float(v[2 * i + 2]), __uint_as_float(v[2 * i + 3])), sc, nb);
       // i is a compile-time constant after unrolling: pairs i = 2, 10 and i + 1 = 1, 5, 9, 13 take the FMA-pipe path
-      const float2 e0 = (POLY && (i & 7) == 2) ? exp2_fma2(x0) : make_float2(ex2_approx(x0.x), ex2_approx(x0.y));
-      const float2 e1 = (POLY && (i & 3) == 0) ? exp2_fma2(x1) : make_float2(ex2_approx(x1.x), ex2_approx(x1.y));
+      const bool poly0 = (POLY == 3 && (i & 7) == 2) || (POLY == 4 && (i & 3) == 2);
+      const bool poly1 = POLY >= 3 && (i & 3) == 0;
+      const float2 e0 = poly0 ? exp2_fma2(x0) : make_float2(ex2_approx(x0.x), ex2_approx(x0.y));
+      const float2 e1 = poly1 ? exp2_fma2(x1) : make_float2(ex2_approx(x1.x), ex2_approx(x1.y));
       s01 = fadd2(s01, e0);
       s23 = fadd2(s23, e1);
       pk[i] = pack_bf16x2(e0.x, e0.y);
@@ -170,7 +172,7 @@ struct FaTcParams {
 //     were built and measured too: the agreement barrier costs more than it saves (0.314 vs 0.300 ms) — removed.
 // SINGLE = false is the round-1 two-pass form, kept for A/B runs (md_debug_attention_impl(2)).
 // PROF adds per-phase clock sums of one softmax thread for tools/attn_phases.py (md_debug_attention_impl(3)).
-template <bool SINGLE, bool PROF = false>
+template <bool SINGLE, bool PROF = false, int POLY = 3>
 __global__ void __launch_bounds__(fa::kThreads, 2)
 fa_tc_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
                      const FaTcParams p) {
@@ -432,11 +434,11 @@ fa_tc_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         l_run *= alpha;
         tick(3);                                          // waited for (half of) the previous P V (+ rare rescale)
         const float base = (m_run == -INFINITY) ? 0.f : m_run * p.scale_log2;
-        l_run += chunk_probs<true>(v0, true, 0, 0, 0, 0, p.scale_log2, base, prow, 0, r);
-        l_run += chunk_probs<true>(v1, true, 0, 0, 0, 0, p.scale_log2, base, prow, 4, r);
+        l_run += chunk_probs<POLY>(v0, true, 0, 0, 0, 0, p.scale_log2, base, prow, 0, r);
+        l_run += chunk_probs<POLY>(v1, true, 0, 0, 0, 0, p.scale_log2, base, prow, 4, r);
         if (!pv_done) mbar_wait(p_empty, (g - 1u) & 1u);
-        l_run += chunk_probs<true>(v2, true, 0, 0, 0, 0, p.scale_log2, base, prow + BM * 128, 0, r);
-        l_run += chunk_probs<true>(v3, true, 0, 0, 0, 0, p.scale_log2, base, prow + BM * 128, 4, r);
+        l_run += chunk_probs<POLY>(v2, true, 0, 0, 0, 0, p.scale_log2, base, prow + BM * 128, 0, r);
+        l_run += chunk_probs<POLY>(v3, true, 0, 0, 0, 0, p.scale_log2, base, prow + BM * 128, 4, r);
         tick(4);                                          // exponentials, pack, P stores
         tc_fence_before();
         fence_proxy_async_smem();
@@ -629,7 +631,7 @@ struct FaVitParams {
 };
 
 // SINGLE / two-pass: as in fa_tc_prefill_kernel.
-template <bool SINGLE>
+template <bool SINGLE, int POLY = 3>
 __global__ void __launch_bounds__(fv::kThreads, 2)
 fa_tc_vit_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_constant__ CUtensorMap tm16,
                  const FaVitParams p) {
@@ -832,11 +834,11 @@ fa_tc_vit_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_constant
         }
         l_run *= alpha;
         const float base = (m_run == -INFINITY) ? 0.f : m_run * p.scale_log2;
-        l_run += chunk_probs<true>(v0, true, 0, 0, 0, 0, p.scale_log2, base, prow, 0, r);
-        l_run += chunk_probs<true>(v1, true, 0, 0, 0, 0, p.scale_log2, base, prow, 4, r);
+        l_run += chunk_probs<POLY>(v0, true, 0, 0, 0, 0, p.scale_log2, base, prow, 0, r);
+        l_run += chunk_probs<POLY>(v1, true, 0, 0, 0, 0, p.scale_log2, base, prow, 4, r);
         if (!pv_done) mbar_wait(p_empty, (g - 1u) & 1u);
-        l_run += chunk_probs<true>(v2, true, 0, 0, 0, 0, p.scale_log2, base, prow + BM * 128, 0, r);
-        l_run += chunk_probs<true>(v3, true, 0, 0, 0, 0, p.scale_log2, base, prow + BM * 128, 4, r);
+        l_run += chunk_probs<POLY>(v2, true, 0, 0, 0, 0, p.scale_log2, base, prow + BM * 128, 0, r);
+        l_run += chunk_probs<POLY>(v3, true, 0, 0, 0, 0, p.scale_log2, base, prow + BM * 128, 4, r);
         tc_fence_before();
         fence_proxy_async_smem();
         mbar_arrive(p_full);
