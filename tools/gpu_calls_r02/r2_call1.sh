@@ -1,6 +1,6 @@
 #!/usr/bin/env bash
 # Round 2, first GPU call: 2B parity tests + the work staged at the end of round 1, all bounded.
-#   gpurun --timeout 1500 -- 'bash tools/r2_call1.sh'
+#   gpurun --timeout 1500 -- 'bash tools/gpu_calls_r02/r2_call1.sh'
 set -u
 mkdir -p gpurun_out
 O=gpurun_out
