@@ -181,3 +181,30 @@ def test_stream_bytes_accounting():
     bf16 = quant.stream_bytes(big)
     assert 0.30 < quant.stream_bytes(big, bits=4) / bf16 < 0.34        # blocks / 4 + scales, LM head bf16
     assert 0.54 < quant.stream_bytes(big, bits=8) / bf16 < 0.58
+
+
+def test_loader_passes_reference_int4_entries_through(tmp_path):
+    """weights.load_state_dict_from_file keeps `…weight.packed / .scale / .zero_point` (layers.py:58-76) as they are —
+    uint8 / fp32, no bf16 cast, no shape check against the dense layout — and still normalises everything else."""
+    from moondream_b200 import weights
+
+    cfg = C.tiny()
+    sd = synth.synthetic_state_dict(cfg, 0)
+    qt, deq = quant.quantize_decoder(cfg, sd, 4)
+    ck = {k: v for k, v in sd.items() if deq[k] is sd[k]}
+    ck.update(quant.reference_checkpoint_entries(cfg, qt))
+    ck = {"model." + k: v for k, v in ck.items()}                 # the reference's optional prefix (weights.py:123-131)
+    path = str(tmp_path / "int4.pt")
+    torch.save(ck, path)
+    loaded = weights.load_state_dict_from_file(path, cfg)
+    assert quant.is_quantized_checkpoint(loaded)
+    k = "text.blocks.2.mlp.fc1.weight"
+    assert k not in loaded and loaded[k + ".packed"].dtype == torch.uint8 and loaded[k + ".scale"].dtype == torch.float32
+    assert loaded["text.blocks.2.mlp.fc1.bias"].dtype == torch.bfloat16 and loaded["vision.pos_emb"].dtype == torch.bfloat16
+    qt2, rest = quant.from_reference_checkpoint(cfg, loaded)
+    assert torch.equal(qt2.blocks[2]["mlp.fc1"].dequantized(), deq[k])
+    with pytest.raises(KeyError):                                  # a dense matrix that is neither present nor packed
+        bad = dict(ck)
+        bad.pop("model.text.blocks.1.attn.proj.weight.packed")
+        torch.save(bad, path)
+        weights.load_state_dict_from_file(path, cfg)
