@@ -384,9 +384,9 @@ struct SmallBatchParams {
   float* ws;
 };
 
-// MROWS = 128 is the shipped form.  MROWS = 64 (batch <= 64; selected by md_debug_gemm bit 6 until it has been
-// validated on hardware) issues M = 64 MMAs: half the A-operand read per K = 16 step, accumulator rows
-// 16q .. 16q+15 in lanes 0..15 of TMEM lane quadrant q (the 1-CTA M = 64 data-path layout).
+// MROWS = 64 (the default for batches <= 64; md_debug_gemm bit 6 forces 128 for A/B runs) issues M = 64 MMAs: half the
+// activation lanes per K = 16 step, accumulator rows 16q .. 16q+15 in lanes 0..15 of TMEM lane quadrant q (the 1-CTA
+// M = 64 data-path layout).  MROWS = 128 serves batches of 65..128 rows.
 template <int MROWS>
 __global__ void __launch_bounds__(kSbThreads, 1)
 smallbatch_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,

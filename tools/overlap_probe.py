@@ -1,4 +1,5 @@
-"""Experiment, NOT part of the product path and not yet run on hardware:
+"""Experiment, NOT part of the product path; run on a B200 this round
+(profiles/r02_overlap_probe.json: +4 % at best, dropped):
 does batch i's decode overlap with batch i+1's ViT + prefill when the two run on different streams?
 
 Two Engine instances (own KV pools, own workspaces, same weights uploaded twice) alternate batches, each on its own
