@@ -1,4 +1,4 @@
-"""A/B timing of the prefill attention kernels (tcgen05 with one or two softmax warpgroups vs legacy mma.sync) at the 2B bench shape."""
+"""A/B timing of the prefill attention kernels (tcgen05 single-pass persistent, two-pass, one item per CTA; legacy mma.sync) at the 2B bench shape."""
 import ctypes
 import os
 import sys
