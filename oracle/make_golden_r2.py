@@ -48,8 +48,10 @@ def _grounding_from(tokens, coords, tk, decode):
     return "".join(texts), out
 
 
-def main():
+def main(out_dir: str | None = None):
+    """writes the five fixtures into out_dir (default tests/golden); the tests regenerate into a scratch directory"""
     assert R.reference_available(), "run in the build container (/root/reference)"
+    out_dir = out_dir or OUT
     torch.manual_seed(0)
     cfg = C.tiny()
     tk = cfg.tokenizer
@@ -87,7 +89,7 @@ def main():
     json.dump({"generator": "oracle/make_golden_r2.py (unmodified reference query(reasoning=True), greedy; tiny preset, "
                             "lm_head bias lifted with synth.special_token_bias%s)" % (REASONING_BIAS,),
                "bias": list(REASONING_BIAS), "cases": cases},
-              open(os.path.join(OUT, "tiny_reasoning.json"), "w"), indent=1)
+              open(os.path.join(out_dir, "tiny_reasoning.json"), "w"), indent=1)
 
     # ---------------- text-only query ----------------
     ref = R.load_reference_model(cfg, sd)
@@ -119,7 +121,7 @@ def main():
                              "reasoning_tokens": r["tokens"], "coords": r["coords"], "margin_ulps": r["margin_ulps"],
                              "coord_ulps": r["coord_ulps"], "end_margin_ulps": r["end_margin_ulps"],
                              "answer_tokens": ans.tokens, "answer_margin_ulps": ans.margin_ulps}},
-              open(os.path.join(OUT, "tiny_text_only.json"), "w"), indent=1)
+              open(os.path.join(out_dir, "tiny_text_only.json"), "w"), indent=1)
 
     # ---------------- grouped-query attention ----------------
     gcfg = C.tiny_gqa()
@@ -145,7 +147,7 @@ def main():
                        "kv_abs_mean_first_last": [float(enc.caches[i][0].float().abs().mean()) for i in (0, 3)]})
         print("gqa", idx, tokens[:8])
     json.dump({"generator": "oracle/make_golden_r2.py (unmodified reference, config tiny-gqa: 4 query heads, 2 KV heads)",
-               "cases": gcases}, open(os.path.join(OUT, "tiny_gqa.json"), "w"), indent=1)
+               "cases": gcases}, open(os.path.join(out_dir, "tiny_gqa.json"), "w"), indent=1)
 
     # ---------------- LoRA variant (settings["variant"], lora.py) ----------------
     import tempfile
@@ -183,7 +185,7 @@ def main():
     orc.lora = None
     json.dump({"generator": "oracle/make_golden_r2.py (unmodified reference with settings['variant'] = a synthetic rank-8 "
                             "LoRA, synth.synthetic_lora(cfg, 8, 0), placed in the reference's variant cache layout)",
-               "rank": 8, "seed": 0, "cases": lcases}, open(os.path.join(OUT, "tiny_lora.json"), "w"), indent=1)
+               "rank": 8, "seed": 0, "cases": lcases}, open(os.path.join(out_dir, "tiny_lora.json"), "w"), indent=1)
 
     # ---------------- _apply_top_p on model logits ----------------
     pcases = []
@@ -208,8 +210,8 @@ def main():
         print("top_p", temp, top_p, len(nz))
     json.dump({"generator": "oracle/make_golden_r2.py (MoondreamModel._apply_top_p of the unmodified reference on bf16 "
                             "prefill logits of the tiny preset)", "cases": pcases},
-              open(os.path.join(OUT, "top_p.json"), "w"), indent=1)
-    print("wrote", sorted(os.listdir(OUT)))
+              open(os.path.join(out_dir, "top_p.json"), "w"), indent=1)
+    print("wrote", sorted(os.listdir(out_dir)))
 
 
 if __name__ == "__main__":

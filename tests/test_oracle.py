@@ -30,22 +30,30 @@ def test_synthetic_weights_are_reproducible(tiny):
 
 
 def test_oracle_reproduces_reference_golden(tiny):
+    """replay of the reference-generated fixture on THIS host's CPU: integers exact up to recorded near-ties, floats
+    within the host-to-host bf16 accumulation-order spread (tests/neartie.py explains both)"""
+    from neartie import MARGIN_ULPS_TOL, check_objects, check_tokens
+
     cfg, sd, orc = tiny
     gold = json.load(open(os.path.join(GOLDEN, "tiny_reference.json")))
+    strict = 0
     for case in gold["cases"]:
         img = synth.synthetic_image(case["image_index"], case["height"], case["width"])
         enc = orc.encode_image(img)
         gen = orc.generate(enc, case["prompt"], len(case["tokens"]))
-        assert gen.tokens == case["tokens"], case["name"]
-        assert np.allclose(gen.margins, case["margins"])
+        n = check_tokens(gen.tokens, case["tokens"], case["margin_ulps"], case["name"])
+        strict += n == len(case["tokens"])
+        assert np.allclose(gen.margin_ulps[:n], case["margin_ulps"][:n], rtol=0, atol=MARGIN_ULPS_TOL)
         det = orc.generate_points(enc, case["detect_prompt"], True, 3)
-        assert [d["bins"] for d in det] == case["detect_bins"]
-        for d, want in zip(det, case["detect_boxes"]):
+        n = check_objects([d["bins"] for d in det], case["detect_bins"], case["detect_ulps"], case["name"] + " detect")
+        for d, want in zip(det[:n], case["detect_boxes"]):
             assert all(d[k] == want[k] for k in want)
         pts = orc.generate_points(enc, case["point_prompt"], False, 3)
-        assert [{"x": p["x"], "y": p["y"]} for p in pts] == case["points"]
+        n = check_objects([p["bins"] for p in pts], case["point_bins"], case["point_ulps"], case["name"] + " point")
+        assert [{"x": p["x"], "y": p["y"]} for p in pts[:n]] == case["points"][:n]
         probe = [float(enc.caches[i][0].float().abs().mean()) for i in (0, cfg.text.n_layers - 1)]
-        assert np.allclose(probe, case["kv_abs_mean_first_last"])
+        assert np.allclose(probe, case["kv_abs_mean_first_last"], rtol=1e-3)
+    assert strict >= len(gold["cases"]) - 1, "token sequences must reproduce exactly except at most one near-tie flip"
 
 
 def test_teacher_forcing_is_consistent(tiny):
@@ -133,15 +141,16 @@ def test_oracle_spatial_refs_and_sampling_are_bit_identical_to_reference(tiny):
 def test_oracle_reproduces_spatial_ref_golden(tiny):
     """tests/golden/tiny_spatial_refs.json (the reference's query(spatial_refs=...) answers; embedding rows taken after
     bit-equality of the prefill logits with the reference)."""
-    import json
-    import os
+    from neartie import check_tokens
 
     cfg, sd, orc = tiny
-    gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "tiny_spatial_refs.json")))
+    gold = json.load(open(os.path.join(GOLDEN, "tiny_spatial_refs.json")))
     idx, h, w = gold["image"]
     o_enc = orc.encode_image(synth.synthetic_image(idx, h, w))
     for c in gold["cases"]:
         refs = [tuple(r) for r in c["spatial_refs"]]
         emb = orc.spatial_prompt_embeds(c["prompt"], refs)
-        assert torch.equal(emb[0, c["rows"]].float(), torch.tensor(c["row_embeds"]))
-        assert orc.generate(o_enc, c["prompt"], len(c["tokens"]), spatial_refs=refs).tokens == c["tokens"]
+        # one bf16 ulp: the Fourier-feature linear's accumulation order is the host's (tests/neartie.py)
+        assert torch.allclose(emb[0, c["rows"]].float(), torch.tensor(c["row_embeds"]), rtol=2 ** -7, atol=1e-6)
+        got = orc.generate(o_enc, c["prompt"], len(c["tokens"]), spatial_refs=refs).tokens
+        check_tokens(got, c["tokens"], c["margin_ulps"], "spatial refs")
