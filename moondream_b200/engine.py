@@ -40,6 +40,21 @@ def _round_up(x: int, m: int) -> int:
     return (x + m - 1) // m * m
 
 
+def _lru_get(cache: dict, key):
+    """dict as an LRU (insertion order = age): a hit moves the entry to the young end"""
+    hit = cache.pop(key, None)
+    if hit is not None:
+        cache[key] = hit
+    return hit
+
+
+def _lru_put(cache: dict, key, value, cap: int):
+    cache.pop(key, None)
+    cache[key] = value
+    while len(cache) > cap:
+        cache.pop(next(iter(cache)))
+
+
 def pixel_lut() -> torch.Tensor:
     """The reference's pixel normalisation (vision.py:33-40) applied to every uint8 value with the
     same torch CPU ops, so the device path is bit-exact: uint8 -> bf16, /255, -0.5, /0.5."""
@@ -238,6 +253,9 @@ class LoraVariant:
 
 class Engine:
     _MAX_DECODE_STATES = 4
+    _MAX_DECODE_GRAPHS = 8      # captured decode steps per batch size: one per DecodeMode (temperature and top_p are
+                                # kernel arguments baked into the capture, so callers that vary them would otherwise
+                                # grow the cache, and the graphs' private memory, without bound)
 
     def __init__(self, cfg: MoondreamConfig, state_dict: Dict[str, torch.Tensor], device="cuda",
                  kv_pages: Optional[int] = None, max_batch: int = 32, quantize: Optional[str] = None):
@@ -849,7 +867,7 @@ class Engine:
         else:
             st["cur"].copy_(st["preds"][:, 0])
         st["pos"].copy_(self._i32(list(pos0)))
-        graph = st["graphs"].get(mode) if use_graph else None
+        graph = _lru_get(st["graphs"], mode) if use_graph else None
         if use_graph and graph is None and max_tokens > 0:
             self._decode_step_launch(st, B, mode)           # warm-up (also validates)
             torch.cuda.synchronize()
@@ -861,7 +879,9 @@ class Engine:
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
                 self._decode_step_launch(st, B, mode)
-            st["graphs"][mode] = graph                      # capture does not execute; state is still at step 0
+            # capture does not execute; state is still at step 0.  An evicted graph is idle: the device was
+            # synchronised after the warm-up step above and nothing has been replayed since
+            _lru_put(st["graphs"], mode, graph, self._MAX_DECODE_GRAPHS)
         lo = 0
         steps = 0
         for s in range(max_tokens):

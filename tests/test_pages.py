@@ -87,3 +87,19 @@ def test_sequence_tables_take_nothing_when_the_pool_cannot_serve_the_batch():
     assert eng.pages.free_pages == 3 and not pres[1]._released and pres[0]._released
     with pytest.raises(ValueError):
         eng._sequence_tables(pres[1:], eng.cfg.text.max_context + 1, consume=False)
+
+
+def test_lru_helpers_bound_the_graph_cache():
+    from moondream_b200.engine import DecodeMode, Engine, _lru_get, _lru_put
+
+    cache = {}
+    modes = [DecodeMode(False, 0.1 * i, 0.3, False, 1, -1, 0) for i in range(Engine._MAX_DECODE_GRAPHS + 3)]
+    for i, m in enumerate(modes[: Engine._MAX_DECODE_GRAPHS]):
+        _lru_put(cache, m, i, Engine._MAX_DECODE_GRAPHS)
+    assert _lru_get(cache, modes[0]) == 0                           # a hit makes the oldest entry the youngest
+    for i, m in enumerate(modes[Engine._MAX_DECODE_GRAPHS:]):
+        _lru_put(cache, m, 100 + i, Engine._MAX_DECODE_GRAPHS)
+    assert len(cache) == Engine._MAX_DECODE_GRAPHS
+    assert modes[0] in cache and modes[1] not in cache and modes[2] not in cache and modes[3] not in cache
+    assert _lru_get(cache, modes[1]) is None and list(cache)[-1] == modes[-1]
+    assert modes[0] == DecodeMode(False, 0.0, 0.3, False, 1, -1, 0) and hash(modes[0]) == hash(DecodeMode(False, 0.0, 0.3, False, 1, -1, 0))
