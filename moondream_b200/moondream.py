@@ -463,14 +463,27 @@ class MoondreamModel:
         tpl = self.config.tokenizer.templates[kind]
         return [list(tpl["prefix"]) + self.tokenizer.encode(" " + o).ids + list(tpl["suffix"]) for o in objects]
 
+    def _points_batch(self, kind: str, images: Sequence[Any], objects: Sequence[str], settings: Optional[dict],
+                      include_size: bool) -> List[List[dict]]:
+        """detect / point for any number of images: at most `max_batch` sequences walk the region head in lock-step
+        at a time (like `_run_images`), and a chunk's image prefixes go back to the pool before the next one is encoded."""
+        if len(objects) != len(images):
+            raise ValueError("one object name per image")
+        max_objects = settings.get("max_objects", DEFAULT_MAX_OBJECTS) if settings else DEFAULT_MAX_OBJECTS
+        lora = self._lora(settings)
+        out: List[List[dict]] = []
+        for lo in range(0, len(images), self._max_batch):
+            enc = self.encode_images(images[lo: lo + self._max_batch], settings)
+            out += self.engine.generate_points([e._prefix for e in enc],
+                                               self._object_prompts(kind, objects[lo: lo + self._max_batch]),
+                                               include_size=include_size, max_objects=max_objects, lora=lora)
+        return out
+
     def detect_batch(self, images: Sequence[Any], objects: Sequence[str],
                      settings: Optional[dict] = None) -> List[Dict[str, list]]:
         if self.config.tokenizer.templates["detect"] is None:
             raise NotImplementedError("Model does not support object detection.")
-        max_objects = settings.get("max_objects", DEFAULT_MAX_OBJECTS) if settings else DEFAULT_MAX_OBJECTS
-        enc = self.encode_images(images, settings)
-        res = self.engine.generate_points([e._prefix for e in enc], self._object_prompts("detect", objects),
-                                          include_size=True, max_objects=max_objects, lora=self._lora(settings))
+        res = self._points_batch("detect", images, objects, settings, include_size=True)
         return [{"objects": [{k: o[k] for k in ("x_min", "y_min", "x_max", "y_max")} for o in r]} for r in res]
 
     def detect(self, image, object: str, settings: Optional[dict] = None):
@@ -480,10 +493,7 @@ class MoondreamModel:
                     settings: Optional[dict] = None) -> List[Dict[str, list]]:
         if self.config.tokenizer.templates["point"] is None:
             raise NotImplementedError("Model does not support pointing.")
-        max_objects = settings.get("max_objects", DEFAULT_MAX_OBJECTS) if settings else DEFAULT_MAX_OBJECTS
-        enc = self.encode_images(images, settings)
-        res = self.engine.generate_points([e._prefix for e in enc], self._object_prompts("point", objects),
-                                          include_size=False, max_objects=max_objects, lora=self._lora(settings))
+        res = self._points_batch("point", images, objects, settings, include_size=False)
         return [{"points": [{"x": o["x"], "y": o["y"]} for o in r]} for r in res]
 
     def point(self, image, object: str, settings: Optional[dict] = None):

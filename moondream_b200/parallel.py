@@ -148,9 +148,17 @@ class ShardedModel:
         self.model = model
         self.sharded = ShardedEngine(model.engine, group)
 
+    @staticmethod
+    def _no_variant(settings):
+        # the sharded calls go through the fused encode + prompt prefill, which has no adapter slots; silently
+        # answering without the adapters would be wrong, so say so (MoondreamModel's own batch calls accept variants)
+        if settings and settings.get("variant") is not None:
+            raise NotImplementedError('settings["variant"] (LoRA) is not supported by the sharded batch calls')
+
     def _generate(self, images, prompts, settings):
         from .moondream import _as_array
 
+        self._no_variant(settings)
         max_tokens, sampling = self.model._text_settings(settings)
         if "sampler" in sampling:
             raise NotImplementedError("the host sampler is a single-process parity path")
@@ -179,6 +187,7 @@ class ShardedModel:
 
         if self.model.config.tokenizer.templates[kind] is None:
             raise NotImplementedError(f"Model does not support {kind}.")
+        self._no_variant(settings)
         max_objects = settings.get("max_objects", DEFAULT_MAX_OBJECTS) if settings else DEFAULT_MAX_OBJECTS
         vals, cnt = self.sharded.detect_boxes([_as_array(im) for im in images], self.model._object_prompts(kind, objects),
                                               max_objects, include_size)

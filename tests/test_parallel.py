@@ -127,3 +127,19 @@ def test_sharded_engine_returns_request_order_on_every_rank(world):
     """ShardedEngine (the N > 1 product path, also what bench.py drives): LPT plan by crop count, local generation,
     one all-gather, rows back in request order — with ragged shards."""
     mp.spawn(_sharded_worker, args=(world, _free_port()), nprocs=world, join=True)
+
+
+def test_sharded_model_rejects_what_it_would_silently_ignore():
+    """settings["variant"] has no slot in the fused sharded path; answering without the adapters would be silently wrong"""
+    from moondream_b200 import config as C
+    from moondream_b200.parallel import ShardedModel
+
+    cfg = C.tiny()
+    model = type("M", (), {"engine": _StubEngine(), "config": cfg})()
+    sm = ShardedModel(model)
+    for call in (lambda: sm.caption_batch([], "short", settings={"variant": "v1"}),
+                 lambda: sm.query_batch([], [], settings={"variant": "v1"}),
+                 lambda: sm.detect_batch([], [], settings={"variant": "v1"}),
+                 lambda: sm.point_batch([], [], settings={"variant": "v1"})):
+        with pytest.raises(NotImplementedError):
+            call()

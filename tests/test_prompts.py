@@ -35,3 +35,57 @@ def test_prompts_equal_the_reference(holder):
         assert M._object_prompts(holder, kind, [g["args"]["object"]]) == [g["prompt"]]
     # every prompt starts after the 730-position image prefix
     assert all(c["pos"] == 730 for c in gold.values())
+
+
+class _PointsEngine:
+    """CPU stand-in for Engine behind MoondreamModel.detect_batch / point_batch: an image's first byte names it."""
+
+    def __init__(self):
+        self.calls = []
+
+    def encode_images(self, arrs, lora=None):
+        from moondream_b200.engine import PrefixKV
+
+        return [PrefixKV(730, [int(a[0, 0, 0])], None) for a in arrs]
+
+    def generate_points(self, prefixes, prompts, include_size, max_objects, lora=None):
+        assert len(prompts) == len(prefixes)
+        self.calls.append((len(prefixes), include_size, max_objects))
+        out = []
+        for p, pr in zip(prefixes, prompts):
+            i = p.pages[0]
+            obj = ({"x_min": float(i), "y_min": float(len(pr)), "x_max": 1.0, "y_max": 2.0, "bins": [0, 0, 0, 0]}
+                   if include_size else {"x": float(i), "y": float(len(pr)), "bins": [0, 0]})
+            out.append([obj] * (i % 3))
+        return out
+
+
+def test_detect_and_point_batches_run_in_chunks_of_max_batch(holder):
+    import numpy as np
+
+    from moondream_b200.moondream import MoondreamModel
+
+    model = MoondreamModel(holder.config, tokenizer=holder.tokenizer, max_batch=3)
+    model._engine = eng = _PointsEngine()
+    images = []
+    for i in range(8):
+        im = np.zeros((20, 20, 3), dtype=np.uint8)
+        im[0, 0, 0] = i
+        images.append(im)
+    objects = [" ".join(str(40 + k) for k in range(1 + i % 4)) for i in range(8)]       # 1..4 tokens per object name
+    tpl = holder.config.tokenizer.templates
+    det = model.detect_batch(images, objects, settings={"max_objects": 5})
+    assert eng.calls == [(3, True, 5), (3, True, 5), (2, True, 5)]
+    for i, d in enumerate(det):
+        n_prompt = len(tpl["detect"]["prefix"]) + 1 + i % 4 + len(tpl["detect"]["suffix"])
+        assert d == {"objects": [{"x_min": float(i), "y_min": float(n_prompt), "x_max": 1.0, "y_max": 2.0}] * (i % 3)}
+    eng.calls.clear()
+    pts = model.point_batch(images[:4], objects[:4])
+    assert eng.calls == [(3, False, 50), (1, False, 50)]                                # the reference's default max_objects
+    for i, d in enumerate(pts):
+        n_prompt = len(tpl["point"]["prefix"]) + 1 + i % 4 + len(tpl["point"]["suffix"])
+        assert d == {"points": [{"x": float(i), "y": float(n_prompt)}] * (i % 3)}
+    assert model.detect(images[2], "7") == det[2] | {"objects": [{**o, "y_min": float(len(tpl["detect"]["prefix"]) + 1 + len(tpl["detect"]["suffix"]))}
+                                                                     for o in det[2]["objects"]]}
+    with pytest.raises(ValueError):
+        model.detect_batch(images[:2], objects[:1])
