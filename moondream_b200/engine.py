@@ -957,18 +957,20 @@ class Engine:
                 self.pages.release(pages)
         return GenerationResult(tokens, margins, steps)
 
-    @_on_device
     def generate_stream(self, prefixes: Sequence[PrefixKV], prompts: Sequence[Sequence[int]], max_tokens: int,
                         chunk: int = 8, temperature: float = 0.0, top_p: float = 1.0, seed: Optional[int] = None,
                         prompt_embeds: Optional[torch.Tensor] = None, prefix_len: int = -1, eos_id: Optional[int] = None):
         """Streaming form of `generate` (the generator of moondream.py:470-537): yields int32 [B, k] host tensors of
         newly decoded tokens every `chunk` graph replays while later steps are still being queued, and stops once every
-        sequence has produced `eos_id`.  Closing the generator early (a consumer's `break`) releases the pages."""
+        sequence has produced `eos_id`.  Closing the generator early (a consumer's `break`) releases the pages.
+        A generator cannot hold a `with torch.cuda.device(...)` across its yields without changing the CALLER's current
+        device while it is suspended, so every resumed segment enters and leaves the engine's device by itself."""
         B = len(prefixes)
         eos = self.cfg.tokenizer.eos_id if eos_id is None else eos_id
         lens = [len(p) for p in prompts]
         total = [prefixes[i].pos + lens[i] + max_tokens + 1 for i in range(B)]
-        bt, owned = self._sequence_tables(prefixes, max(total), consume=False)
+        with torch.cuda.device(self.device):
+            bt, owned = self._sequence_tables(prefixes, max(total), consume=False)
         try:
             with torch.cuda.device(self.device):
                 st = self._decode_buffers(B)
@@ -976,16 +978,21 @@ class Engine:
                 self._prefill_phase(st, prompts, [p.pos for p in prefixes], prompt_embeds, prefix_len)
                 pos0 = [prefixes[i].pos + lens[i] for i in range(B)]
                 mode = self.decode_mode(False, temperature, top_p)
-                done = torch.zeros(B, dtype=torch.bool)
-                for lo, hi in self._decode_phase(st, B, pos0, max_tokens, mode, None, True, False, chunk=chunk, seed=seed):
-                    hi = min(hi, max_tokens)
-                    if hi <= lo:
-                        continue
-                    part = st["preds"][:, lo:hi].to("cpu")          # synchronises on the steps queued so far only
-                    yield part
-                    done |= (part == eos).any(dim=1)
-                    if bool(done.all()):
+                phase = self._decode_phase(st, B, pos0, max_tokens, mode, None, True, False, chunk=chunk, seed=seed)
+            done = torch.zeros(B, dtype=torch.bool)
+            while True:
+                with torch.cuda.device(self.device):
+                    span = next(phase, None)                    # queues the next `chunk` graph replays
+                    if span is None:
                         break
+                    lo, hi = span[0], min(span[1], max_tokens)
+                    part = st["preds"][:, lo:hi].to("cpu") if hi > lo else None    # waits for the steps queued so far only
+                if part is None:
+                    continue
+                yield part
+                done |= (part == eos).any(dim=1)
+                if bool(done.all()):
+                    break
         finally:
             for pages in owned:
                 self.pages.release(pages)
