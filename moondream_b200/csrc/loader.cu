@@ -70,26 +70,33 @@ struct Json {
     long long v = 0;
     bool neg = false, any = false;
     if (p < e && *p == '-') { neg = true; ++p; }
-    while (p < e && *p >= '0' && *p <= '9') { v = v * 10 + (*p - '0'); ++p; any = true; }
+    while (p < e && *p >= '0' && *p <= '9') {
+      if (v > (0x7fffffffffffffffLL - 9) / 10) { ok = false; return 0; }      // would overflow: not a size any file has
+      v = v * 10 + (*p - '0'); ++p; any = true;
+    }
     if (!any) ok = false;
     return neg ? -v : v;
   }
-  void skip() {                           // any value (used for __metadata__)
+  int depth = 0;
+  void skip() {                           // any value (used for __metadata__); nesting is bounded, the file is untrusted
     ws();
-    if (p >= e) { ok = false; return; }
+    if (p >= e || depth > 64) { ok = false; return; }
     if (*p == '"') { str(); return; }
     if (*p == '{' || *p == '[') {
       const char open = *p, close = open == '{' ? '}' : ']';
       ++p;
       ws();
       if (p < e && *p == close) { ++p; return; }
+      ++depth;
       while (ok) {
-        if (open == '{') { str(); if (!eat(':')) { ok = false; return; } }
+        if (open == '{') { str(); if (!eat(':')) { ok = false; break; } }
         skip();
+        if (!ok) break;
         if (eat(',')) continue;
-        if (eat(close)) return;
+        if (eat(close)) { --depth; return; }
         ok = false;
       }
+      --depth;
       return;
     }
     while (p < e && *p != ',' && *p != '}' && *p != ']') ++p;      // number / true / false / null
@@ -108,18 +115,21 @@ static int parse_header(StFile& f, const char* js, size_t n) {
     } else {
       StEntry en;
       en.name = name;
+      int have = 0;                         // 1 dtype, 2 shape, 4 data_offsets: all three are required
       if (!j.eat('{')) return set_error("safetensors: tensor entry is not an object");
       while (j.ok) {
         const std::string key = j.str();
         if (!j.eat(':')) return set_error("safetensors: malformed tensor entry");
-        if (key == "dtype") en.dtype = j.str();
+        if (key == "dtype") { en.dtype = j.str(); have |= 1; }
         else if (key == "shape") {
+          have |= 2;
           if (!j.eat('[')) return set_error("safetensors: shape is not an array");
           if (!j.eat(']')) {
             do { en.shape.push_back(j.num()); } while (j.eat(','));
             if (!j.eat(']')) return set_error("safetensors: malformed shape");
           }
         } else if (key == "data_offsets") {
+          have |= 4;
           if (!j.eat('[')) return set_error("safetensors: data_offsets is not an array");
           en.begin = j.num();
           if (!j.eat(',')) return set_error("safetensors: malformed data_offsets");
@@ -132,12 +142,17 @@ static int parse_header(StFile& f, const char* js, size_t n) {
         if (j.eat('}')) break;
         return set_error("safetensors: malformed tensor entry");
       }
+      if (!j.ok) break;
+      if (have != 7) return set_error("safetensors: a tensor entry lacks dtype, shape or data_offsets");
       f.entries.push_back(en);
     }
     if (j.eat(',')) continue;
     if (j.eat('}')) break;
     return set_error("safetensors: malformed header");
   }
+  j.ws();
+  while (j.p < j.e && (*j.p == '\0' || *j.p == ' ')) ++j.p;        // writers pad the header to 8 bytes (spaces; some NULs)
+  if (j.ok && j.p != j.e) return set_error("safetensors: bytes after the header object");
   return j.ok ? 0 : set_error("safetensors: malformed header");
 }
 
@@ -181,10 +196,13 @@ int md_safetensors_open(const char* path, md_file** out) {
   for (const md::StEntry& en : f->entries) {
     if (rc) break;
     long long elems = 1;
-    for (long long d : en.shape) elems *= d;
+    bool bad = false;
+    for (long long d : en.shape) bad = bad || d < 0 || __builtin_mul_overflow(elems, d, &elems);
     const int sz = md::dtype_size(en.dtype);
-    if (en.begin < 0 || en.end < en.begin || f->data0 + static_cast<size_t>(en.end) > f->size ||
-        (sz && elems * sz != en.end - en.begin))
+    long long bytes = 0;
+    if (sz) bad = bad || __builtin_mul_overflow(elems, static_cast<long long>(sz), &bytes);
+    if (bad || en.begin < 0 || en.end < en.begin || static_cast<unsigned long long>(en.end) > f->size - f->data0 ||
+        (sz && bytes != en.end - en.begin))
       rc = md::set_error("md_safetensors_open: a tensor's offsets do not fit its shape or the file");
   }
   if (rc) { munmap(const_cast<unsigned char*>(f->map), f->size); close(f->fd); delete f; return rc; }

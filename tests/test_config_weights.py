@@ -199,3 +199,67 @@ def test_native_safetensors_reader_matches_the_safetensors_package(tmp_path):
         NativeSafetensors(str(bad))
     with pytest.raises(N.NativeError):
         NativeSafetensors(str(tmp_path / "missing.safetensors"))
+
+
+def _st_file(path, header: bytes, payload: bytes = b""):
+    import struct
+
+    path.write_bytes(struct.pack("<Q", len(header)) + header + payload)
+    return str(path)
+
+
+def test_native_safetensors_reader_rejects_malformed_and_hostile_headers(tmp_path):
+    """A checkpoint is an untrusted file: every malformed header must come back as NativeError — never a crash, a hang,
+    or a tensor whose bytes lie outside the mapping."""
+    import json
+
+    import pytest
+
+    from moondream_b200 import _native as N
+    from moondream_b200.weights import NativeSafetensors
+
+    good = json.dumps({"a": {"dtype": "F32", "shape": [2, 3], "data_offsets": [0, 24]},
+                       "__metadata__": {"k": "v", "n": {"deep": [1, 2, {"x": None}]}}}).encode()
+    payload = bytes(range(24))
+    with NativeSafetensors(_st_file(tmp_path / "good.safetensors", good + b"   ", payload)) as st:     # space padding
+        assert st.keys() == ["a"] and st.get_tensor("a").flatten().view(torch.uint8).tolist() == list(payload)
+    with NativeSafetensors(_st_file(tmp_path / "nul.safetensors", good + b"\0\0", payload)) as st:
+        assert st.keys() == ["a"]
+
+    def entry(**kw):
+        e = {"dtype": "F32", "shape": [2, 3], "data_offsets": [0, 24]}
+        e.update(kw)
+        return {k: v for k, v in e.items() if v is not None}
+
+    hostile = {
+        "deep_metadata": b'{"__metadata__": ' + b"[" * 200000 + b"]" * 200000 + b"}",
+        "deep_objects": b'{"__metadata__": ' + b'{"a":' * 100000 + b"1" + b"}" * 100000 + b"}",
+        "huge_number": b'{"a": {"dtype": "F32", "shape": [' + b"9" * 40 + b'], "data_offsets": [0, 24]}}',
+        "huge_offset": b'{"a": {"dtype": "U8", "shape": [1], "data_offsets": [0, 9223372036854775807]}}',
+        "negative_dims": json.dumps({"a": entry(shape=[-2, -3])}).encode(),
+        "dims_overflow": json.dumps({"a": entry(shape=[2 ** 40, 2 ** 40], dtype="U8", data_offsets=[0, 0])}).encode(),
+        "beyond_file": json.dumps({"a": entry(data_offsets=[100, 124])}).encode(),
+        "negative_offset": json.dumps({"a": entry(data_offsets=[-8, 16])}).encode(),
+        "reversed_offsets": json.dumps({"a": entry(data_offsets=[24, 0])}).encode(),
+        "size_mismatch": json.dumps({"a": entry(shape=[2, 2])}).encode(),
+        "no_dtype": json.dumps({"a": entry(dtype=None)}).encode(),
+        "no_shape": json.dumps({"a": entry(shape=None)}).encode(),
+        "no_offsets": json.dumps({"a": entry(data_offsets=None)}).encode(),
+        "entry_not_object": b'{"a": [1, 2]}',
+        "not_an_object": b'["a"]',
+        "trailing_bytes": good + b"}{",
+        "unterminated_string": b'{"a',
+        "empty": b"",
+    }
+    for name, header in hostile.items():
+        with pytest.raises(N.NativeError):
+            NativeSafetensors(_st_file(tmp_path / f"{name}.safetensors", header, payload))
+    for cut in range(1, len(good)):                     # every truncation of a valid header
+        with pytest.raises(N.NativeError):
+            NativeSafetensors(_st_file(tmp_path / "cut.safetensors", good[:cut], payload))
+    # a header length that points past the end of the file, and a file shorter than the length field
+    (tmp_path / "short.safetensors").write_bytes(b"\x10\x00\x00")
+    (tmp_path / "lies.safetensors").write_bytes((1 << 40).to_bytes(8, "little") + good)
+    for name in ("short", "lies"):
+        with pytest.raises(N.NativeError):
+            NativeSafetensors(str(tmp_path / f"{name}.safetensors"))
