@@ -166,6 +166,12 @@ def test_oracle_is_bit_identical_to_reference_on_the_2b_architecture():
     # comparators.*.first_tokens, produced by the oracle's arithmetic on the B200) -- on hosts whose oneDNN path matches
     if gen.tokens != [1094, 22849, 11037, 121, 36410]:
         assert min(gen.margin_ulps) < 4.5, gen.tokens
+    # region head at 2B widths (detect: coordinate + size decode / encode interleaved with decoder steps, moondream.py:653-733)
+    tk = cfg.tokenizer
+    det = ref.detect(enc, "17 23", settings={"max_objects": 2})["objects"]
+    dprompt = tk.templates["detect"]["prefix"] + [17, 23] + tk.templates["detect"]["suffix"]
+    o_det = orc.generate_points(o_enc, dprompt, True, 2)
+    assert len(o_det) == len(det) and [{k: o[k] for k in d} for o, d in zip(o_det, det)] == det
 
 
 def test_oracle_reproduces_spatial_ref_golden(tiny):
