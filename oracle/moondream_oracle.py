@@ -3,13 +3,14 @@
 Plain torch CPU ops over a flat dict of tensors in the canonical state_dict layout.  With
 ``dtype=torch.bfloat16`` every op rounds where the reference rounds (the reference hard-wires bf16:
 vision.py:36, weights.py:32), which makes this port bit-identical to the unmodified reference on
-the same torch build — ``tests/test_oracle_vs_reference.py`` checks exactly that in the build
-container and ``tests/golden/*.json`` carries the reference's outputs to the GPU box.  With
-``dtype=torch.float32`` it is the "truth" used for error budgeting.
+the same torch build — ``tests/test_oracle.py`` and ``tests/test_oracle_r2.py`` check exactly that in the build
+container (tiny presets, and the Moondream-2B architecture with the bench's weights) and ``tests/golden/*.json``
+carries the reference's outputs to the GPU box.  With ``dtype=torch.float32`` it is the "truth" used for error budgeting.
 
-Parity pinning: the reference's own tests hold no model-path vectors (only tests/test_image_crops.py),
-so the pins are (a) bit-equality with the reference run here and (b) the committed golden fixtures
-generated from the reference by oracle/make_golden.py.
+Parity pinning: PINNED.  The reference's own tests hold no model-path vectors (only tests/test_image_crops.py, re-hosted
+in tests/test_image_crops.py), so the pins are (a) bit-equality with the unmodified reference run in the same process
+(KV caches, prefill logits and hidden states, tokens, boxes, grounding) and (b) the committed golden fixtures generated
+from the reference by oracle/make_golden.py, make_golden_r2.py and make_golden_quant.py.
 
 Every function cites the reference lines it restates (paths relative to /root/reference).
 """
