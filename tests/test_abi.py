@@ -65,3 +65,34 @@ def test_no_cpu_fallback_without_gpu():
     cfg = C.tiny()
     with pytest.raises(NativeError):
         Engine(cfg, synth.synthetic_state_dict(cfg, 0))
+
+
+def test_every_entry_point_reports_null_arguments():
+    """Error behaviour of the boundary: called with null pointers and zero sizes, every entry point that
+    returns a status must come back non-zero with md_last_error() set — before touching CUDA, so this runs without a
+    GPU.  In a subprocess: a crash would otherwise take the test session with it."""
+    import subprocess
+    import sys
+
+    code = r'''
+import ctypes, sys
+from moondream_b200 import _native as N
+lib = N.lib()
+void = [n for n, (res, _) in N._SIGNATURES.items() if res is None]
+info = {"md_last_error", "md_abi_version", "md_launch_count", "md_linear_small_batch_splits",
+        "md_linear_small_batch_workspace_bytes", "md_debug_timeline"}
+bad = []
+for name, (res, args) in N._SIGNATURES.items():
+    if name in void or name in info:
+        continue
+    vals = [0 if a in (ctypes.c_int, ctypes.c_longlong, ctypes.c_uint) else 0.0 if a is ctypes.c_float else None for a in args]
+    rc = getattr(lib, name)(*vals)
+    if rc == 0:
+        bad.append(name)
+    elif res is ctypes.c_int and rc > 0 and not lib.md_last_error():
+        bad.append(name + " (no message)")
+print("BAD", bad)
+'''
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=ROOT, timeout=120)
+    assert r.returncode == 0, r.stderr[-500:]
+    assert "BAD []" in r.stdout, r.stdout
