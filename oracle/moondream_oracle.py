@@ -4,7 +4,7 @@ Plain torch CPU ops over a flat dict of tensors in the canonical state_dict layo
 ``dtype=torch.bfloat16`` every op rounds where the reference rounds (the reference hard-wires bf16:
 vision.py:36, weights.py:32), which makes this port bit-identical to the unmodified reference on
 the same torch build — ``tests/test_oracle.py`` and ``tests/test_oracle_r2.py`` check exactly that in the build
-container (tiny presets, and the Moondream-2B architecture with the bench's weights) and ``tests/golden/*.json``
+container (tiny presets, and the Moondream-2B / 0.5B architectures, the 2B with the bench's weights) and ``tests/golden/*.json``
 carries the reference's outputs to the GPU box.  With ``dtype=torch.float32`` it is the "truth" used for error budgeting.
 
 Parity pinning: PINNED.  The reference's own tests hold no model-path vectors (only tests/test_image_crops.py, re-hosted

@@ -139,24 +139,26 @@ def test_oracle_spatial_refs_and_sampling_are_bit_identical_to_reference(tiny):
 
 
 @pytest.mark.skipif(not R.reference_available(), reason="/root/reference only exists in the build container")
-def test_oracle_is_bit_identical_to_reference_on_the_2b_architecture():
-    """The pin on the configuration the headline is quoted on (BASELINE.json configs[1]): Moondream-2B dimensions
-    (text 2048 x 24 layers x 32 heads, ViT 1152 x 27 layers with head_dim 72, vocab 51200), the bench's synthetic
-    weights (head peak 3) and its image 0 / prompt 0.  The UNMODIFIED reference and the oracle must agree bit for bit
-    on all 24 layers of the 730-token KV prefix and on the greedy tokens.  (~80 s on 8 cores: two 3.9 GB models.)"""
+@pytest.mark.parametrize("preset,head_peak", [("moondream-2b", 3.0), ("moondream-0.5b", 0.0)])
+def test_oracle_is_bit_identical_to_reference_on_the_real_architectures(preset, head_peak):
+    """The pin on the configurations BASELINE.json quotes, not only on the tiny presets.  Moondream-2B (text 2048 x 24
+    layers x 32 heads, ViT 1152 x 27 layers with head_dim 72, vocab 51200) with the bench's synthetic weights (head
+    peak 3), its image 0 / prompt 0; and Moondream-0.5B (text 1024 x 16 heads, ViT 720 x 10 heads, MLP width 2690).
+    The UNMODIFIED reference and the oracle must agree bit for bit on every layer of the 730-token KV prefix, on the
+    greedy tokens and on a 2-object detect.  (~80 s + ~25 s on 8 cores: two copies of each model.)"""
     from PIL import Image
 
-    cfg = C.moondream_2b()
-    sd = synth.synthetic_state_dict(cfg, 0, head_peak=3.0)          # bench.py: HEAD_PEAK
+    cfg = C.preset(preset)
+    sd = synth.synthetic_state_dict(cfg, 0, head_peak=head_peak)          # bench.py: HEAD_PEAK = 3 for the 2B
     ref = R.load_reference_model(cfg, sd)
     orc = OracleModel(cfg, sd)
     img = synth.synthetic_image(0, 378, 378)
     with torch.inference_mode():
         enc = ref.encode_image(Image.fromarray(img))
     o_enc = orc.encode_image(img)
-    assert enc.pos == o_enc.pos == 730 and len(enc.caches) == 24
+    assert enc.pos == o_enc.pos == 730 and len(enc.caches) == cfg.text.n_layers
     for (k, v), (ok, ov) in zip(enc.caches, o_enc.caches):
-        assert tuple(k.shape) == (1, 32, 730, 64) and torch.equal(k, ok) and torch.equal(v, ov)
+        assert tuple(k.shape) == (1, cfg.text.n_kv_heads, 730, 64) and torch.equal(k, ok) and torch.equal(v, ov)
     prompt = synth.synthetic_prompt(0, 32, cfg.text.vocab_size)     # bench.py: PROMPT_LEN
     ref.load_encoded_image(enc)
     text = "".join(ref._generate_answer(torch.tensor([prompt]), enc.pos, {"temperature": 0, "max_tokens": 5}))
@@ -164,9 +166,9 @@ def test_oracle_is_bit_identical_to_reference_on_the_2b_architecture():
     assert R.tokens_from_text(text) == gen.tokens
     # the same five tokens open image 0's caption in every GPU bench run of the round (profiles/r02_bench_final.json:
     # comparators.*.first_tokens, produced by the oracle's arithmetic on the B200) -- on hosts whose oneDNN path matches
-    if gen.tokens != [1094, 22849, 11037, 121, 36410]:
+    if preset == "moondream-2b" and gen.tokens != [1094, 22849, 11037, 121, 36410]:
         assert min(gen.margin_ulps) < 4.5, gen.tokens
-    # region head at 2B widths (detect: coordinate + size decode / encode interleaved with decoder steps, moondream.py:653-733)
+    # region head at full width (detect: coordinate + size decode / encode interleaved with decoder steps, moondream.py:653-733)
     tk = cfg.tokenizer
     det = ref.detect(enc, "17 23", settings={"max_objects": 2})["objects"]
     dprompt = tk.templates["detect"]["prefix"] + [17, 23] + tk.templates["detect"]["suffix"]
