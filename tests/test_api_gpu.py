@@ -1,6 +1,5 @@
 """The drop-in `MoondreamModel` surface (reference moondream/torch/moondream.py) driven the way the reference's
 callers drive it: encode_image / caption / query / detect / point, settings keys, result shapes, exceptions."""
-import numpy as np
 import pytest
 import torch
 from PIL import Image

@@ -1,6 +1,5 @@
 """Kernel-level parity on the GPU: each CUDA kernel against a plain torch fp32 reference of the same op."""
 import ctypes
-import math
 
 import numpy as np
 import pytest
