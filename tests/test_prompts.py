@@ -89,3 +89,34 @@ def test_detect_and_point_batches_run_in_chunks_of_max_batch(holder):
                                                                      for o in det[2]["objects"]]}
     with pytest.raises(ValueError):
         model.detect_batch(images[:2], objects[:1])
+
+
+def test_reasoning_text_and_grounding_equal_the_reference(holder):
+    """MoondreamModel._reasoning_result (the host half of query(reasoning=True): chunking at start_ground_points /
+    end_ground, text spans, point pairs; moondream.py:363-432) on the reasoning tokens and coordinates of
+    tests/golden/tiny_reasoning.json must give the text and grounding the UNMODIFIED reference returned for them."""
+    from moondream_b200.moondream import MoondreamModel as M
+
+    gold = json.load(open(os.path.join(HERE, "golden", "tiny_reasoning.json")))
+    grounded = 0
+    for c in gold["cases"]:
+        text, grounding = M._reasoning_result(holder, c["reasoning_tokens"], c["coords"])
+        assert text == c["reasoning_text"]
+        assert [{"start_idx": g["start_idx"], "end_idx": g["end_idx"], "points": [list(p) for p in g["points"]]}
+                for g in grounding] == c["grounding"]
+        grounded += len(grounding)
+        assert M._query_prompt(holder, c["question"], None, False, reasoning=True) == c["prompt"]
+    assert grounded >= 1, "the fixture must contain at least one grounded span"
+
+
+def test_text_settings_follow_the_reference_defaults():
+    """TextSamplingSettings (moondream.py:443-454, :51-53): temperature 0.5, top_p 0.3, max_tokens 768."""
+    from moondream_b200.moondream import MoondreamModel as M
+
+    assert M._text_settings(None) == (768, {"temperature": 0.5, "top_p": 0.3})
+    assert M._text_settings({"temperature": 0}) == (768, {})
+    assert M._text_settings({"temperature": 1, "top_p": 0.9, "max_tokens": 5, "seed": 7}) == (5, {"temperature": 1.0, "top_p": 0.9, "seed": 7})
+    mt, s = M._text_settings({"temperature": 0.7, "host_sampler": True})
+    assert mt == 768 and set(s) == {"sampler"}
+    with pytest.raises(ValueError):
+        M._text_settings({"temperature": -1})
