@@ -263,3 +263,64 @@ def test_native_safetensors_reader_rejects_malformed_and_hostile_headers(tmp_pat
     for name in ("short", "lies"):
         with pytest.raises(N.NativeError):
             NativeSafetensors(str(tmp_path / f"{name}.safetensors"))
+
+
+def test_variant_files_are_found_and_renamed_like_the_reference(tmp_path, monkeypatch):
+    """settings["variant"] (row f4): MoondreamModel._lora looks a variant id up in the reference's cache layout
+    (lora.py:11-29: $HF_HUB_CACHE/md_variants/<id>/final.pt, else $HF_HOME/hub/...) and applies the reference's key
+    renames (lora.py:64-76) to checkpoints saved with the trainer's names.  Compared with the unmodified reference's
+    `variant_state_dict` where /root/reference exists; the expected tree is also spelt out so the test holds anywhere."""
+    import pytest
+
+    from moondream_b200 import config as C, synth
+    from moondream_b200.moondream import MoondreamModel
+    from oracle import reference_shim as R
+
+    cfg = C.tiny()
+    flat = synth.synthetic_lora(cfg, 8, 0)                       # canonical names: text.blocks.{i}.{attn.qkv, attn.proj, mlp.fc1, mlp.fc2}.{A, B}
+    trainer = {}
+    for k, t in flat.items():                                    # the names the trainer saves (what the renames undo)
+        k2 = (k.replace("text.blocks", "text_model.transformer.h").replace(".attn.qkv", ".mixer.Wqkv")
+               .replace(".attn.proj", ".mixer.out_proj"))
+        k2 = k2[:-2] + ".parametrizations.weight.0" + k2[-2:]
+        trainer[k2] = t
+    assert "text_model.transformer.h.0.mixer.Wqkv.parametrizations.weight.0.A" in trainer
+    hub = tmp_path / "hub_cache"
+    (hub / "md_variants" / "v1").mkdir(parents=True)
+    torch.save(trainer, hub / "md_variants" / "v1" / "final.pt")
+    home = tmp_path / "home"
+    (home / "hub" / "md_variants" / "v2").mkdir(parents=True)
+    torch.save(trainer, home / "hub" / "md_variants" / "v2" / "final.pt")
+
+    seen = []
+    model = MoondreamModel(cfg, tokenizer=R.StubTokenizer(cfg.text.vocab_size))
+    model._engine = type("E", (), {"load_lora": lambda self, d: seen.append(d) or ("variant", len(seen))})()
+    monkeypatch.setenv("HF_HUB_CACHE", str(hub))
+    monkeypatch.delenv("HF_HOME", raising=False)
+    assert model._lora(None) is None and model._lora({"temperature": 0}) is None
+    got = model._lora({"variant": "v1"})
+    assert got == ("variant", 1) and model._lora({"variant": "v1"}) is got          # cached per id
+    assert sorted(seen[0]) == sorted(flat) and all(torch.equal(seen[0][k], flat[k]) for k in flat)
+    with pytest.raises(RuntimeError, match="offline"):
+        model._lora({"variant": "v2"})                                              # not in $HF_HUB_CACHE: never downloaded
+    monkeypatch.delenv("HF_HUB_CACHE")
+    monkeypatch.setenv("HF_HOME", str(home))
+    assert model._lora({"variant": "v2"}) == ("variant", 2) and sorted(seen[1]) == sorted(flat)
+    assert model._lora({"variant": str(hub / "md_variants" / "v1" / "final.pt")}) == ("variant", 3)   # a path works too
+    if R.reference_available():
+        import sys
+
+        if R.REFERENCE_ROOT not in sys.path:
+            sys.path.insert(0, R.REFERENCE_ROOT)
+        from moondream.torch import lora as ref_lora
+
+        ref_lora.variant_state_dict.cache_clear()
+        tree = ref_lora.variant_state_dict("v2")                                    # $HF_HOME/hub/md_variants/v2/final.pt
+        mine = synth.nest_lora(seen[1])
+
+        def same(a, b):
+            if isinstance(a, dict):
+                return isinstance(b, dict) and a.keys() == b.keys() and all(same(a[k], b[k]) for k in a)
+            return torch.equal(a, b)
+
+        assert same(tree, mine)
