@@ -324,3 +324,35 @@ def test_variant_files_are_found_and_renamed_like_the_reference(tmp_path, monkey
             return torch.equal(a, b)
 
         assert same(tree, mine)
+
+
+def test_lora_variant_table_and_shape_checks():
+    """engine.LoraVariant: the per-block (A, B) pointer table the C-ABI takes (md_text_prefill_lora) in the order
+    qkv, proj, fc1, fc2, and the errors for adapters that do not fit the model (host logic; tensors on the CPU here)."""
+    import pytest
+
+    from moondream_b200 import config as C, synth
+    from moondream_b200.engine import LoraVariant
+
+    cfg = C.tiny()
+    t = cfg.text
+    flat = synth.synthetic_lora(cfg, 8, 0)
+    for tree in (synth.nest_lora(flat), synth.nest_lora(flat)["text"]):             # with or without the "text" root
+        v = LoraVariant(cfg, tree, "cpu")
+        assert v.rank == 8 and len(v.tensors) == t.n_layers * 8 and len(v.table) == t.n_layers * 8
+        assert [int(p) for p in v.table] == [x.data_ptr() for x in v.tensors]
+        a, b = v.tensors[0], v.tensors[1]                                            # block 0, attn.qkv
+        assert tuple(a.shape) == (8, t.dim) and tuple(b.shape) == (3 * t.dim, 8)
+        assert torch.equal(a, flat["text.blocks.0.attn.qkv.A"]) and torch.equal(v.tensors[7], flat["text.blocks.0.mlp.fc2.B"])
+    bad = dict(flat)
+    bad["text.blocks.1.mlp.fc1.B"] = bad["text.blocks.1.mlp.fc1.B"][:-1]            # wrong output width
+    with pytest.raises(ValueError, match="block 1 mlp.fc1"):
+        LoraVariant(cfg, synth.nest_lora(bad), "cpu")
+    with pytest.raises(ValueError, match="multiple of 8"):
+        LoraVariant(cfg, synth.nest_lora(synth.synthetic_lora(cfg, 12, 0)), "cpu")
+    mixed = dict(flat)
+    r16 = synth.synthetic_lora(cfg, 16, 0)
+    for k in ("text.blocks.0.attn.proj.A", "text.blocks.0.attn.proj.B"):
+        mixed[k] = r16[k]
+    with pytest.raises(ValueError, match="share one rank"):
+        LoraVariant(cfg, synth.nest_lora(mixed), "cpu")
