@@ -356,3 +356,46 @@ def test_lora_variant_table_and_shape_checks():
         mixed[k] = r16[k]
     with pytest.raises(ValueError, match="share one rank"):
         LoraVariant(cfg, synth.nest_lora(mixed), "cpu")
+
+
+@pytest.mark.parametrize("preset", ["tiny", "tiny-gqa"])
+def test_upload_builds_the_fused_decode_layout_as_views(preset):
+    """engine.upload_weights (device = CPU here): per decoder block W1 = [qkv.weight ; fc1.weight], b1 = [qkv.bias ;
+    fc1.bias], W2 = [proj.weight | fc2.weight]; the canonical tensors the prefill GEMMs use are VIEWS of those buffers
+    (the C runtime checks exactly this adjacency, md_dims.txt_fused), with the checkpoint's values.  With packed
+    decoder blocks every block's bf16 pointers alias ONE scratch pair."""
+    from moondream_b200 import config as C, synth
+    from moondream_b200.engine import upload_weights
+    from moondream_b200.synth import state_dict_spec
+
+    cfg = C.preset(preset)
+    t = cfg.text
+    sd = synth.synthetic_state_dict(cfg, 0)
+    keys = [k for k, _, _ in state_dict_spec(cfg)]
+    idx = {k: i for i, k in enumerate(keys)}
+    prepared, _, _ = prepare_weights(cfg, sd)
+    dev, owners = upload_weights(cfg, prepared, "cpu")
+    q_rows = t.dim + 2 * t.n_kv_heads * t.head_dim
+    for i in range(t.n_layers):
+        p = f"text.blocks.{i}."
+        qkv, fc1 = dev[idx[p + "attn.qkv.weight"]], dev[idx[p + "mlp.fc1.weight"]]
+        proj, fc2 = dev[idx[p + "attn.proj.weight"]], dev[idx[p + "mlp.fc2.weight"]]
+        qb, fb = dev[idx[p + "attn.qkv.bias"]], dev[idx[p + "mlp.fc1.bias"]]
+        assert tuple(qkv.shape) == (q_rows, t.dim) and qkv.is_contiguous() and fc1.is_contiguous()
+        assert fc1.data_ptr() == qkv.data_ptr() + qkv.numel() * 2                   # fc1 rows follow the qkv rows
+        assert fb.data_ptr() == qb.data_ptr() + qb.numel() * 2
+        assert proj.stride(0) == fc2.stride(0) == t.dim + t.ff_dim                  # column blocks of one matrix
+        assert fc2.data_ptr() == proj.data_ptr() + t.dim * 2
+        for name, got in (("attn.qkv.weight", qkv), ("mlp.fc1.weight", fc1), ("attn.proj.weight", proj),
+                          ("mlp.fc2.weight", fc2), ("attn.qkv.bias", qb), ("mlp.fc1.bias", fb)):
+            assert torch.equal(got, sd[p + name]), p + name
+    assert all(torch.equal(dev[i], prepared[i]) for i, k in enumerate(keys) if not k.startswith("text.blocks."))
+    # packed decoder blocks: bf16 block weights are absent from `prepared` and alias one scratch pair on the device
+    prepared_q, _, _ = prepare_weights(cfg, sd, quantized_blocks=True)
+    assert all((prepared_q[idx[k]] is None) == k.endswith(("attn.qkv.weight", "attn.proj.weight", "mlp.fc1.weight", "mlp.fc2.weight"))
+               for k in keys if k.startswith("text.blocks."))
+    dev_q, _ = upload_weights(cfg, prepared_q, "cpu", quantized_blocks=True)
+    w1 = {dev_q[idx[f"text.blocks.{i}.attn.qkv.weight"]].data_ptr() for i in range(t.n_layers)}
+    w2 = {dev_q[idx[f"text.blocks.{i}.attn.proj.weight"]].data_ptr() for i in range(t.n_layers)}
+    assert len(w1) == 1 and len(w2) == 1
+    assert torch.equal(dev_q[idx["text.blocks.1.attn.qkv.bias"]], sd["text.blocks.1.attn.qkv.bias"])   # biases stay per block
