@@ -215,3 +215,62 @@ def test_generate_points_lockstep_loop_on_a_cpu_shell(monkeypatch):
     first_tokens[:] = [eos] * B
     assert eng.generate_points(pre, prompts, include_size=True, max_objects=5) == [[], [], [], []] and not replays
     assert eng.pages.free_pages == free0
+
+
+def test_generate_returns_every_page_when_the_decode_loop_fails(monkeypatch):
+    """Engine.generate: whatever happens after the block tables were built — here the decode loop raises — the pages of
+    the batch go back to the pool exactly once, including consumed prefix pages (whose handles stay marked as handed over);
+    option conflicts are rejected; with `prefilled_hidden` the prompt is not prefilled again."""
+    import contextlib
+
+    import pytest
+    import torch
+
+    from moondream_b200 import config as C
+    from moondream_b200.engine import Engine, PagePool, PrefixKV, PAGE
+
+    monkeypatch.setattr(torch.cuda, "device", lambda _d: contextlib.nullcontext())
+    cfg = C.tiny()
+    eng = Engine.__new__(Engine)
+    eng.cfg, eng.device = cfg, torch.device("cpu")
+    eng.pages = PagePool(cfg, 40, "cpu")
+    eng.max_blocks = cfg.text.max_context // PAGE
+    st = {"S": cfg.text.max_context + 1, "bt": torch.zeros((2, eng.max_blocks), dtype=torch.int32),
+          "x": torch.zeros((2, cfg.text.dim), dtype=torch.bfloat16),
+          "preds": torch.arange(2 * 64, dtype=torch.int32).view(2, 64), "margins": torch.zeros((2, 64))}
+    eng._decode_buffers = lambda B: st
+    prefills = []
+    eng._prefill_phase = lambda st_, prompts, start, emb, prefix_len, lora=None: prefills.append(list(start))
+    boom = {"on": True}
+
+    def decode_phase(st_, B, pos0, max_tokens, mode, forced, use_graph, stop_on_eos, seed=None):
+        if boom["on"]:
+            raise RuntimeError("device fault")
+        st_["steps_run"] = max_tokens
+        st_["pos0"] = list(pos0)
+        yield 0, max_tokens + 1
+
+    eng._decode_phase = decode_phase
+    total = eng.pages.free_pages
+    for consume in (False, True):
+        pre = [PrefixKV(730, eng.pages.alloc(12), eng.pages) for _ in range(2)]
+        with pytest.raises(RuntimeError, match="device fault"):
+            eng.generate(pre, [[1, 2, 3]] * 2, 100, consume=consume)
+        if consume:
+            assert all(p._released for p in pre) and eng.pages.free_pages == total       # handed over, then returned
+        else:
+            assert eng.pages.free_pages == total - 24 and not any(p._released for p in pre)
+        for p in pre:
+            p.release()                                                                   # a no-op for consumed prefixes
+        assert eng.pages.free_pages == total and sorted(eng.pages._free) == list(range(40))   # nothing returned twice
+    boom["on"] = False
+    pre = [PrefixKV(762, eng.pages.alloc(12), eng.pages) for _ in range(2)]                # prefixes that include the prompt
+    prefills.clear()
+    res = eng.generate(pre, [[1, 2, 3]] * 2, 6, consume=True, prefilled_hidden=torch.ones((2, cfg.text.dim), dtype=torch.bfloat16))
+    assert prefills == [] and st["pos0"] == [762, 762] and float(st["x"].float().min()) == 1.0
+    assert tuple(res.tokens.shape) == (2, 7) and res.tokens[1].tolist() == list(range(64, 71)) and res.steps == 6
+    assert eng.pages.free_pages == total
+    pre = [PrefixKV(730, eng.pages.alloc(12), eng.pages) for _ in range(2)]
+    with pytest.raises(ValueError, match="mutually exclusive"):
+        eng.generate(pre, [[1]] * 2, 4, forced=[[1] * 5] * 2, sampler=lambda logits: logits)
+    assert eng.pages.free_pages == total - 24
