@@ -103,8 +103,12 @@ class SeamAdapter:
         T = x.shape[1]
         p0 = self._positions(pos_ids, T)
         prefix_len = -1
-        if p0 < t.prefix_attn and T > 1:
-            bidirectional = bool(attn_mask[0, 0, 0, p0 + T - 1].item()) if attn_mask is not None else True
+        # the two masks can only differ for a row inside the prefix looking at a LATER position that is still inside
+        # the prefix: test the first row against the last such column (rows that reach past the prefix, e.g. a fused
+        # [BOS | image | prompt] pass, are classified by their in-prefix part)
+        last_in_prefix = min(p0 + T - 1, t.prefix_attn - 1)
+        if p0 < t.prefix_attn and last_in_prefix > p0:
+            bidirectional = bool(attn_mask[0, 0, 0, last_in_prefix].item()) if attn_mask is not None else True
             prefix_len = -1 if bidirectional else 0
         with torch.cuda.device(e.device):
             h = x[0].to(e.device, torch.bfloat16).contiguous().clone()

@@ -274,3 +274,44 @@ def test_generate_returns_every_page_when_the_decode_loop_fails(monkeypatch):
     with pytest.raises(ValueError, match="mutually exclusive"):
         eng.generate(pre, [[1]] * 2, 4, forced=[[1] * 5] * 2, sampler=lambda logits: logits)
     assert eng.pages.free_pages == total - 24
+
+
+def test_seam_prefill_tells_the_prefix_lm_mask_from_the_causal_one(monkeypatch):
+    """SeamAdapter._prefill receives the reference's mask tensor and must hand the native prefill the matching rule:
+    prefix-LM (moondream.py:138-146: the first 730 positions see each other) or plain causal (text-only query,
+    :571-574).  Host logic only: the engine is a recorder."""
+    import contextlib
+
+    import torch
+
+    from moondream_b200 import config as C
+    from moondream_b200.seam import SeamAdapter
+
+    monkeypatch.setattr(torch.cuda, "device", lambda _d: contextlib.nullcontext())
+    cfg = C.tiny()
+    t = cfg.text
+    calls = []
+    eng = type("E", (), {"cfg": cfg, "device": torch.device("cpu"),
+                         "prefill": lambda self, h, q_off, start, bt, prefix_len=-1: calls.append((list(q_off), list(start), prefix_len))})()
+    seam = SeamAdapter(eng)
+    seam._table = lambda: None
+    ctx = t.max_context
+    prefix_lm = torch.tril(torch.ones(1, 1, ctx, ctx, dtype=torch.bool))
+    prefix_lm[..., : t.prefix_attn, : t.prefix_attn] = True                        # moondream.py:143-145
+    causal = torch.tril(torch.ones(1, 1, ctx, ctx, dtype=torch.bool))              # moondream.py:571-574
+
+    def run(mask, pos, T):
+        calls.clear()
+        x = torch.zeros((1, T, t.dim), dtype=torch.bfloat16)
+        out = seam._prefill(x, mask[:, :, pos: pos + T, :], torch.arange(pos, pos + T), None)
+        assert tuple(out.shape) == (1, T, t.dim) and calls[0][:2] == ([0, T], [pos])
+        return calls[0][2]
+
+    assert run(prefix_lm, 0, t.prefix_attn) == -1          # encode_image: [BOS | image] under the prefix-LM mask
+    assert run(causal, 0, 9) == 0                          # text-only query: BOS + prompt at position 0, causal
+    assert run(prefix_lm, t.prefix_attn, 12) == -1         # a prompt after the image prefix: the masks coincide there
+    assert run(causal, 40, 5) == 0
+    assert run(prefix_lm, 0, t.prefix_attn + 32) == -1     # one fused pass over [BOS | image | prompt]
+    assert run(causal, 0, t.prefix_attn + 32) == 0
+    assert run(prefix_lm, 700, 100) == -1 and run(causal, 700, 100) == 0           # starts inside the prefix, ends past it
+    assert run(prefix_lm, t.prefix_attn - 1, 4) == -1      # only the prefix's last row: nothing to tell apart, default rule
