@@ -143,3 +143,50 @@ def test_sharded_model_rejects_what_it_would_silently_ignore():
                  lambda: sm.point_batch([], [], settings={"variant": "v1"})):
         with pytest.raises(NotImplementedError):
             call()
+
+
+def _sharded_model_worker(rank, world, port):
+    import numpy as np
+
+    from moondream_b200 import config as C
+    from moondream_b200.moondream import MoondreamModel
+    from moondream_b200.parallel import ShardedModel
+    from oracle.reference_shim import StubTokenizer
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        cfg = C.tiny()
+        model = MoondreamModel(cfg, tokenizer=StubTokenizer(cfg.text.vocab_size))
+        model._engine = _StubEngine()
+        sm = ShardedModel(model)
+        sizes = [(378, 378), (800, 600), (378, 378), (1200, 900), (500, 700)]
+        images = []
+        for i, (h, w) in enumerate(sizes):
+            im = np.zeros((h, w, 3), dtype=np.uint8)
+            im[0, 0, 0] = 10 + i
+            images.append(im)
+        # the stub's "tokens" are [image id, image height, prompt length, 0, ...]; the stub tokenizer prints ids
+        caps = sm.caption_batch(images, "short", settings={"temperature": 0, "max_tokens": 4})
+        n_cap = len(cfg.tokenizer.templates["caption"]["short"])
+        assert [c["caption"] for c in caps] == [f"{10 + i} {h} {n_cap} " for i, (h, w) in enumerate(sizes)]     # 0 = eos: cut
+        qs = ["7", "7 8", "7 8 9", "7", "7 8"]
+        ans = sm.query_batch(images, qs, settings={"temperature": 0, "max_tokens": 4})
+        tq = cfg.tokenizer.templates["query"]
+        assert [a["answer"] for a in ans] == [f"{10 + i} {h} {len(tq['prefix']) + len(q.split()) + 2 * len(tq['suffix'])} "
+                                              for (i, (h, w)), q in zip(enumerate(sizes), qs)]
+        det = sm.detect_batch(images, ["17"] * 5, settings={"max_objects": 3})
+        assert [len(d["objects"]) for d in det] == [(10 + i) % 3 for i in range(5)]
+        assert det[1]["objects"][0] == {"x_min": 11.0, "y_min": 0.0, "x_max": 1.0, "y_max": 2.0}
+        with pytest.raises(NotImplementedError):
+            sm.caption_batch(images, "short", settings={"temperature": 0.5, "host_sampler": True})
+        with pytest.raises(ValueError):
+            sm.caption_batch(images, "epic")
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_model_api_on_two_ranks():
+    """ShardedModel (MoondreamModel's batched calls over the ranks of a box) on 2 gloo ranks with a stub engine: every
+    rank returns the full answer in request order, shaped like the single-process API."""
+    mp.spawn(_sharded_model_worker, args=(2, _free_port()), nprocs=2, join=True)
